@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- QPS @ recall@10 of the batched HNSW index scan, 1M x 128 fp32 vector_l2_ops, m=16,
+ef_construction=64, ef_search=40, 10k-query batches (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one pass of the hot path (get_scan_items for every query of one 10k batch) on each GPU.
+Queries shard across GPUs against a replicated graph (weak scaling: 10k queries per GPU per step,
+no data-path collective).  Prints ONE JSON line on rank 0.
+
+The graph is the reference-exact graph built by the CPU oracle's sequential ambuild loop; because
+that takes ~45 minutes for 1M rows it is cached under data_cache/ (tools/build_graph_cache.py) and
+only rebuilt when the cache is absent.  Vectors and queries are regenerated from seeds.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "QPS@recall@10 and build vectors/s, 1M×128 L2 HNSW, 1/2/4/8 B200"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--m", type=int, default=16)
+    ap.add_argument("--efc", type=int, default=64)
+    ap.add_argument("--ef", type=int, default=40)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--cache", default=os.path.join(ROOT, "data_cache"))
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--recall-sample", type=int, default=200)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def load_or_build_graph(a):
+    """Returns dict(rows, level, adj0, upper_base, adj_up, entry, n) of the oracle-built graph."""
+    from pgvector_rx_b200 import datasets as D
+    rows = D.gaussian_f32(a.n, a.dim, 2)
+    tag = "c2_1m" if (a.n, a.dim, a.m, a.efc) == (1_000_000, 128, 16, 64) else "g_%d_%d_%d_%d" % (a.n, a.dim, a.m, a.efc)
+    d = os.path.join(a.cache, tag)
+    meta_p = os.path.join(d, "meta.json")
+    if os.path.exists(meta_p):
+        meta = json.load(open(meta_p))
+        if (meta["n"], meta["dim"], meta["m"], meta["efc"], meta["data_seed"], meta["level_seed"]) == (a.n, a.dim, a.m, a.efc, 2, 4):
+            g = {k: np.load(os.path.join(d, k + ".npy")) for k in ("level", "adj0", "upper_base", "adj_up")}
+            g.update(rows=rows, entry=meta["entry"], n=meta["n"], source="cache:" + tag,
+                     build_vec_per_s_cpu=meta["n"] / meta["build_seconds"])
+            return g
+    log("graph cache %s missing: building %d rows with the CPU oracle (slow)" % (d, a.n))
+    import oracle_ffi as O
+    lv = D.hnsw_levels(a.n, a.m, 4)
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, a.dim, m=a.m, ef_construction=a.efc, tie_mode=O.TIE_TOTAL_ORDER)
+    t0 = time.time()
+    o.build(rows, lv)
+    dt = time.time() - t0
+    g = o.export_graph()
+    g.update(source="oracle-build", build_vec_per_s_cpu=a.n / dt)
+    try:
+        os.makedirs(d, exist_ok=True)
+        for k in ("level", "adj0", "upper_base", "adj_up"):
+            np.save(os.path.join(d, k + ".npy"), g[k])
+        json.dump(dict(n=int(g["n"]), dim=a.dim, m=a.m, efc=a.efc, data_seed=2, level_seed=4, entry=int(g["entry"]),
+                       build_seconds=dt), open(meta_p, "w"))
+    except OSError:
+        pass
+    return g
+
+
+def query_batches(a, count, rank):
+    from pgvector_rx_b200 import datasets as D
+    return [D.gaussian_f32(a.nq, a.dim, 3 + 1000 * rank + 17 * i) for i in range(count)]
+
+
+def oracle_for(a, g):
+    import oracle_ffi as O
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, a.dim, m=a.m, ef_construction=a.efc, tie_mode=O.TIE_TOTAL_ORDER)
+    o.import_graph(g)
+    return o
+
+
+def cpu_baseline(a, g, queries, sample=0):
+    """The oracle (CPU restatement of the reference's scan) on all host cores over a bounded sample."""
+    o = oracle_for(a, g)
+    cores = os.cpu_count() or 1
+    nq = sample or min(len(queries), 400 * cores)
+    q = queries[:nq]
+    o.search_batch(q[: 4 * cores], ef_search=a.ef, k=a.k, nthreads=cores)      # warm caches / threads
+    t0 = time.perf_counter()
+    ids, _, _ = o.search_batch(q, ef_search=a.ef, k=a.k, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return dict(value=nq / dt, unit="queries/s", cores=cores, kind="port",
+                sample="%d queries of the same batch, ef_search=%d, k=%d, %d threads, %.1f s" % (nq, a.ef, a.k, cores, dt)), ids, o
+
+
+def recall_at_k(a, g, queries, got_ids, sample):
+    import oracle_ffi as O
+    s = min(sample, len(queries))
+    gt, _ = O.flat_topk(O.ELEM_F32, O.L2SQ, a.dim, g["rows"], queries[:s], a.k, nthreads=os.cpu_count() or 1)
+    hit = sum(len(set(got_ids[i].tolist()) & set(gt[i].tolist())) for i in range(s))
+    return hit / float(s * a.k)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.rows, self.proc, self.gpu = [], None, gpu
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the scan kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g = load_or_build_graph(a)
+    batches = query_batches(a, 1, 0)
+    o = oracle_for(a, g)
+    cores = os.cpu_count() or 1
+    per_step = min(a.nq, 200 * cores)          # bounded sample of the 10k-query batch per step
+    q = batches[0][:per_step]
+    for _ in range(max(a.warmup, 1)):
+        o.search_batch(q[: 4 * cores], ef_search=a.ef, k=a.k, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ids, _, _ = o.search_batch(q, ef_search=a.ef, k=a.k, nthreads=cores)
+    dt = time.perf_counter() - t0
+    qps = per_step * a.steps / dt
+    rec = recall_at_k(a, g, q, ids, a.recall_sample)
+    sample = "%d queries/step of the 10k batch, %d threads" % (per_step, cores)
+    out = dict(impl="reference", metric=METRIC, value=qps, unit="queries/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+               ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+               data="synthetic", recall_at_10=rec,
+               config=dict(workload="C2: 1Mx128 fp32 vector_l2_ops m=16 ef_construction=64 ef_search=%d k=%d" % (a.ef, a.k),
+                           n=a.n, dim=a.dim, queries_per_step=per_step, graph=g["source"],
+                           note="CPU restatement of pgvector-rx's scan on flat arrays (the Rust/pgrx reference cannot be built here)"),
+               cpu_baseline=dict(value=qps, unit="queries/s", cores=cores, kind="port", sample=sample),
+               e2e=dict(value=qps, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out), flush=True)
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import pgvector_rx_b200 as P
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device (no CPU path exists)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    g = load_or_build_graph(a)
+    ix = P.HnswIndex("vector_l2_ops", a.dim, m=a.m, ef_construction=a.efc, capacity=a.n, device=local)
+    ix.load_graph(g["rows"], g["level"], g["adj0"], g["upper_base"], g["adj_up"], g["entry"])
+    nb = 4
+    batches = query_batches(a, nb, rank)
+    dev = torch.device("cuda", local)
+    d_q = [torch.from_numpy(b).to(dev) for b in batches]
+    d_ids = torch.empty((a.nq, a.k), dtype=torch.int32, device=dev)
+    d_dists = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)
+    d_cnt = torch.empty((a.nq,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device(i):
+        ix.search_device(d_q[i % nb].data_ptr(), a.nq, a.k, a.ef, d_ids.data_ptr(), d_dists.data_ptr(), d_cnt.data_ptr(), stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ----
+    for i in range(a.warmup):
+        step_device(i)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        step_device(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * a.nq * a.steps / (ms_max / 1e3)
+
+    # ---- end to end through the host-buffer C ABI: pinned H2D + kernels + D2H every step ----
+    pin_q = [torch.from_numpy(b).pin_memory() for b in batches]
+    pin_ids = torch.empty((a.nq, a.k), dtype=torch.int32).pin_memory()
+    pin_d = torch.empty((a.nq, a.k), dtype=torch.float32).pin_memory()
+    pin_c = torch.empty((a.nq,), dtype=torch.int32).pin_memory()
+    import ctypes as C
+
+    def step_host(i):
+        rc = ix.L.pgvrx_search_batch(ix.h, C.c_void_p(pin_q[i % nb].data_ptr()), a.nq, a.ef, a.k, C.c_void_p(pin_ids.data_ptr()),
+                                     C.c_void_p(pin_d.data_ptr()), C.c_void_p(pin_c.data_ptr()), None)
+        ix._check(rc)
+
+    for i in range(max(3, a.warmup // 2)):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        step_host(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * a.nq * a.steps / float(t.item())
+    last_ids = pin_ids.numpy().copy()
+    last_batch = batches[(a.steps - 1) % nb]
+
+    # ---- counters -> algorithmic bytes; parity + recall + CPU baseline on rank 0 ----
+    st = P.SearchStats()
+    ix.search_device(d_q[0].data_ptr(), a.nq, a.k, a.ef, d_ids.data_ptr(), d_dists.data_ptr(), d_cnt.data_ptr(), stream=stream, stats=st)
+    row_bytes = a.dim * 4
+    bytes_step = st.n_dist * row_bytes + st.n_expand0 * 2 * a.m * 4 + st.n_expand_upper * a.m * 4
+    peak, peak_src = measured_peak()
+    step_s = ms_max / 1e3 / a.steps
+    achieved = bytes_step / step_s / 1e9
+    out = None
+    if rank == 0:
+        base, cpu_ids, o = cpu_baseline(a, g, last_batch, a.cpu_sample)
+        nchk = len(cpu_ids)
+        parity_ok = bool(np.array_equal(cpu_ids, last_ids[:nchk]))
+        rec = recall_at_k(a, g, last_batch, last_ids, a.recall_sample)
+        rec_cpu = recall_at_k(a, g, last_batch, cpu_ids, min(a.recall_sample, nchk))
+        out = dict(metric=METRIC, value=value, unit="queries/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
+                   ms_per_step=ms_max / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                   data="synthetic", recall_at_10=rec, recall_at_10_cpu=rec_cpu, ids_match_cpu_oracle=parity_ok,
+                   config=dict(workload="C2: 1Mx128 fp32 vector_l2_ops m=16 ef_construction=64 ef_search=%d k=%d, %d-query batches"
+                                        % (a.ef, a.k, a.nq), n=a.n, dim=a.dim, queries_per_step_per_gpu=a.nq,
+                               parallelism="query-sharded x%d, graph replicated" % world, graph=g["source"],
+                               l2="working set (graph + vectors 0.64 GB, 6.7 GB gathered per step) exceeds L2; batches rotate"),
+                   clocks=clk,
+                   e2e=dict(value=e2e, unit="queries/s", h2d_bytes_per_step=a.nq * row_bytes,
+                            d2h_bytes_per_step=a.nq * (a.k * 8 + 4)),
+                   gpu_launches=3 * a.steps,
+                   roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=ncu_traffic(),
+                                 peak_source=peak_src, kernel="hnsw_scan_kernel<F32,L2SQ>",
+                                 bytes_per_launch=int(bytes_step), bytes_per_query=bytes_step / a.nq,
+                                 counters=dict(n_dist=int(st.n_dist), n_expand0=int(st.n_expand0),
+                                               n_expand_upper=int(st.n_expand_upper), n_retried=int(st.n_retried)),
+                                 note="achieved = (n_dist*512 + n_expand0*128 + n_expand_upper*64 bytes per step) / CUDA-event step time, rank 0 counters"),
+                   cpu_baseline=base,
+                   build=dict(cpu_oracle_vectors_per_s=g.get("build_vec_per_s_cpu"), gpu_vectors_per_s=None,
+                              note="GPU build path not measured in this line"))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ix.close()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+/*
+ * pgvrx_b200.h -- C ABI of the B200-native HNSW hot path for pgvector-rx.
+ *
+ * This is the drop-in boundary: the entry points a pgrx shim (or any FFI) binds in place of
+ * the reference's in-process graph code.  Plain pointers and sizes only; the library owns all
+ * device memory behind the opaque handle; callers own every host buffer; nothing here throws,
+ * unwinds or longjmps -- every call returns a pgvrx_status and leaves a message retrievable with
+ * pgvrx_last_error() (the reference raises pgrx::error!, e.g. src/index/scan.rs:136,733).
+ *
+ * Reference seams replaced (file:line under /root/reference):
+ *   scan : get_scan_items / resume_scan_items          src/index/scan.rs:458-577
+ *          (search_layer_disk + load_element + load_neighbor_tids, scan.rs:155-448)
+ *   build: find_element_neighbors' search_layer calls  src/graph/mod.rs:355-427 (:386,:407)
+ *          distance_fn                                  src/index/build.rs:346-369
+ *   exact: operator-ordered sequential scan (ground truth of tests/t/012..., no dedicated fn)
+ * Parameter names, ranges and defaults mirror the reloptions and GUCs in
+ * src/index/options.rs:81-96,203-225 and src/hnsw_constants.rs:47-112.
+ *
+ * There is no CPU fallback: every compute entry point fails with PGVRX_ERR_CUDA when no
+ * sm_100-class device is usable.
+ */
+#ifndef PGVRX_B200_H
+#define PGVRX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGVRX_ABI_VERSION 1
+
+typedef enum {
+    PGVRX_OK = 0,
+    PGVRX_ERR_INVALID = 1,     /* bad argument / option out of the reference's range            */
+    PGVRX_ERR_CUDA = 2,        /* CUDA runtime or device error (message has the cudaError name) */
+    PGVRX_ERR_NOMEM = 3,
+    PGVRX_ERR_STATE = 4,       /* call order (e.g. search before a graph is loaded)             */
+    PGVRX_ERR_UNSUPPORTED = 5
+} pgvrx_status;
+
+/* indexed type: `vector`, `halfvec`, `bit` (src/types/{vector,halfvec,bitvec}.rs) */
+typedef enum { PGVRX_ELEM_F32 = 0, PGVRX_ELEM_F16 = 1, PGVRX_ELEM_BIT = 2 } pgvrx_elem;
+
+/* opclass FUNCTION 1.  vector_l2_ops/halfvec_l2_ops -> L2SQ (squared, vector.rs:842-845);
+ * *_ip_ops -> NEG_IP; *_cosine_ops -> NEG_IP over rows/queries normalised by the caller with
+ * pgvrx_normalize (FUNCTION 2, vector.rs:852-856, build.rs:426-438, scan.rs:749-754);
+ * *_l1_ops -> L1; bit_hamming_ops / bit_jaccard_ops (bitvec.rs:210-237). */
+typedef enum {
+    PGVRX_METRIC_L2SQ = 0, PGVRX_METRIC_NEG_IP = 1, PGVRX_METRIC_L1 = 2,
+    PGVRX_METRIC_HAMMING = 3, PGVRX_METRIC_JACCARD = 4
+} pgvrx_metric;
+
+/* hnsw.iterative_scan (options.rs:85,168-175) */
+typedef enum { PGVRX_ITER_OFF = 0, PGVRX_ITER_RELAXED = 1, PGVRX_ITER_STRICT = 2 } pgvrx_iterative;
+
+/* reloptions / GUC ranges (hnsw_constants.rs:47-112) */
+#define PGVRX_MIN_M 2
+#define PGVRX_MAX_M 100
+#define PGVRX_DEFAULT_M 16
+#define PGVRX_MIN_EF_CONSTRUCTION 4
+#define PGVRX_MAX_EF_CONSTRUCTION 1000
+#define PGVRX_DEFAULT_EF_CONSTRUCTION 64
+#define PGVRX_MIN_EF_SEARCH 1
+#define PGVRX_MAX_EF_SEARCH 1000
+#define PGVRX_DEFAULT_EF_SEARCH 40
+#define PGVRX_DEFAULT_MAX_SCAN_TUPLES 20000
+#define PGVRX_HEAPTIDS 10
+#define PGVRX_MAX_DIM_VECTOR 2000      /* hnsw_constants.rs:4     */
+#define PGVRX_MAX_DIM_HALFVEC 4000     /* halfvec.rs:875-877      */
+#define PGVRX_MAX_DIM_BIT 64000        /* bitvec.rs:183-185       */
+
+typedef struct pgvrx_index pgvrx_index;
+
+typedef struct {
+    int32_t elem_type;        /* pgvrx_elem                                                  */
+    int32_t metric;           /* pgvrx_metric                                                */
+    int32_t dim;              /* dimensions (bits for PGVRX_ELEM_BIT)                        */
+    int32_t m;                /* reloption m, 2..100                                         */
+    int32_t ef_construction;  /* reloption ef_construction, 4..1000 and >= 2*m               */
+    int32_t device;           /* CUDA device ordinal                                          */
+    int64_t capacity;         /* max graph elements the handle must hold                      */
+} pgvrx_index_desc;
+
+/* per-call work counters: the algorithmic-bytes figure of DESIGN.md is derived from these */
+typedef struct {
+    uint64_t n_dist;          /* distance evaluations (scan.rs:375, graph/mod.rs:218)          */
+    uint64_t n_expand0;       /* candidates expanded at layer 0 (scan.rs:349)                  */
+    uint64_t n_expand_upper;  /* candidates expanded at layers >= 1                            */
+    uint64_t n_visited;       /* ids added to visited sets                                     */
+    uint64_t n_retried;       /* queries re-run with larger scratch (visited/tie overflow)     */
+    uint32_t n_launches;      /* kernels launched by this call                                 */
+    float    kernel_ms;       /* device time of those kernels (CUDA events on the call stream) */
+} pgvrx_search_stats;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int pgvrx_abi_version(void);
+/* message for the last failure on this handle (or the last failed create when idx == NULL);
+ * valid until the next call on the same handle / thread. */
+const char *pgvrx_last_error(const pgvrx_index *idx);
+/* number of usable CUDA devices (0 when none: every compute call then fails) */
+int pgvrx_device_count(void);
+
+/* ---- host-side opclass support (bit-identical to the reference; no device needed) ---------- */
+/* FUNCTION 2 + normalisation (vector.rs:106-126, halfvec.rs:204-233).  Writes the unit row to
+ * out (may alias in).  *norm receives the f64 norm; rows with norm 0 must not be indexed
+ * (build.rs:433-435).  PGVRX_ERR_INVALID on halfvec overflow ("value out of range: overflow"). */
+int pgvrx_normalize(int32_t elem_type, int32_t dim, const void *in, void *out, double *norm);
+/* build.rs:373-377: floor(-ln(max(r, MIN_POSITIVE)) / ln m) capped at the page-size limit
+ * (types/hnsw.rs:337-349).  r is the caller's uniform(0,1) draw. */
+int32_t pgvrx_level_from_uniform(double r, int32_t m);
+int32_t pgvrx_max_level(int32_t m);
+/* bytes per stored row: dim*4, dim*2 or ceil(dim/8) */
+size_t pgvrx_row_bytes(int32_t elem_type, int32_t dim);
+
+/* ---- index lifecycle ------------------------------------------------------------------------ */
+int pgvrx_index_create(const pgvrx_index_desc *desc, pgvrx_index **out);
+void pgvrx_index_destroy(pgvrx_index *idx);
+
+/* Upload a finished graph (from the page exporter, or any builder) into HBM.
+ *   rows        n x row_bytes raw element data, element id == row number
+ *   level       n x u8                                     (HnswElementTupleData.level)
+ *   adj0        n x 2m int32 element ids, -1 after the last neighbour (layer 0)
+ *   upper_base  n x int32: first row in adj_up of an element with level >= 1, else -1
+ *   adj_up      n_upper_rows x m int32; (id, layer l >= 1) is row upper_base[id] + l - 1
+ *   entry       entry point element id (HnswMetaPageData.entry_*), -1 for an empty index
+ * Neighbour order is the stored order: it is the order search visits them (scan.rs:273-279). */
+int pgvrx_index_load_graph(pgvrx_index *idx, const void *rows, int64_t n, const uint8_t *level,
+                           const int32_t *adj0, const int32_t *upper_base, const int32_t *adj_up,
+                           int64_t n_upper_rows, int64_t entry);
+int64_t pgvrx_index_size(const pgvrx_index *idx);
+
+/* ---- scan: get_scan_items, iterative_scan = off (scan.rs:458-530) ------------------------------ */
+/* For each of nq queries (raw element data, row_bytes apart, already normalised for cosine):
+ * runs the greedy descent (ef = 1 per upper layer, fresh visited set per layer) and the layer-0
+ * search with ef_search, and returns the k <= ef_search nearest elements nearest-first
+ * (amgettuple pops results nearest-first, scan.rs:861).  out_ids / out_dists are nq*k, padded
+ * with -1 / +inf; out_counts[q] = number of valid entries.  Equal distances are ordered by
+ * element id.  HOST buffers; the call copies in, launches, copies out and synchronises. */
+int pgvrx_search_batch(pgvrx_index *idx, const void *queries, int64_t nq, int32_t ef_search,
+                       int32_t k, int32_t *out_ids, float *out_dists, int32_t *out_counts,
+                       pgvrx_search_stats *stats /* may be NULL */);
+/* Same, with DEVICE buffers on `cuda_stream` (a cudaStream_t; NULL = the handle's stream).
+ * Asynchronous unless stats != NULL (stats needs the kernels to have finished). */
+int pgvrx_search_batch_device(pgvrx_index *idx, const void *d_queries, int64_t nq, int32_t ef_search,
+                              int32_t k, int32_t *d_ids, float *d_dists, int32_t *d_counts,
+                              pgvrx_search_stats *stats, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,198 @@
+"""pgvector_rx_b200 -- B200-native HNSW hot path for pgvector-rx behind a C ABI.
+
+This module is the thin Python binding of libpgvrx_b200.so (include/pgvrx_b200.h) used by the
+tests and bench.py.  All computation happens in the CUDA library; there is no CPU fallback and
+loading fails loudly when the library has not been built.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgvrx_b200.so")
+
+ELEM_F32, ELEM_F16, ELEM_BIT = 0, 1, 2
+L2SQ, NEG_IP, L1, HAMMING, JACCARD = 0, 1, 2, 3, 4
+ITER_OFF, ITER_RELAXED, ITER_STRICT = 0, 1, 2
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED = range(6)
+
+# operator classes of the reference (src/types/vector.rs:842-865, halfvec.rs:1050-1073,
+# bitvec.rs:210-237): name -> (element type, FUNCTION 1 metric, has FUNCTION 2 norm)
+OPCLASSES = {
+    "vector_l2_ops": (ELEM_F32, L2SQ, False),
+    "vector_ip_ops": (ELEM_F32, NEG_IP, False),
+    "vector_cosine_ops": (ELEM_F32, NEG_IP, True),
+    "vector_l1_ops": (ELEM_F32, L1, False),
+    "halfvec_l2_ops": (ELEM_F16, L2SQ, False),
+    "halfvec_ip_ops": (ELEM_F16, NEG_IP, False),
+    "halfvec_cosine_ops": (ELEM_F16, NEG_IP, True),
+    "halfvec_l1_ops": (ELEM_F16, L1, False),
+    "bit_hamming_ops": (ELEM_BIT, HAMMING, False),
+    "bit_jaccard_ops": (ELEM_BIT, JACCARD, False),
+}
+
+# every symbol include/pgvrx_b200.h declares
+EXPORTS = [
+    "pgvrx_abi_version", "pgvrx_last_error", "pgvrx_device_count", "pgvrx_normalize",
+    "pgvrx_level_from_uniform", "pgvrx_max_level", "pgvrx_row_bytes", "pgvrx_index_create",
+    "pgvrx_index_destroy", "pgvrx_index_load_graph", "pgvrx_index_size", "pgvrx_search_batch",
+    "pgvrx_search_batch_device",
+]
+
+
+class PgvrxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pgvrx error %d: %s" % (code, msg))
+        self.code = code
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [("elem_type", C.c_int32), ("metric", C.c_int32), ("dim", C.c_int32), ("m", C.c_int32),
+                ("ef_construction", C.c_int32), ("device", C.c_int32), ("capacity", C.c_int64)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("n_dist", C.c_uint64), ("n_expand0", C.c_uint64), ("n_expand_upper", C.c_uint64),
+                ("n_visited", C.c_uint64), ("n_retried", C.c_uint64), ("n_launches", C.c_uint32),
+                ("kernel_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Raises if it is missing: the product has no other code path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not built; run `python -m pgvector_rx_b200.build` (needs nvcc)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    sig = {
+        "pgvrx_abi_version": (C.c_int, []),
+        "pgvrx_last_error": (C.c_char_p, [vp]),
+        "pgvrx_device_count": (C.c_int, []),
+        "pgvrx_normalize": (C.c_int, [i32, i32, vp, vp, C.POINTER(C.c_double)]),
+        "pgvrx_level_from_uniform": (i32, [C.c_double, i32]),
+        "pgvrx_max_level": (i32, [i32]),
+        "pgvrx_row_bytes": (C.c_size_t, [i32, i32]),
+        "pgvrx_index_create": (C.c_int, [C.POINTER(IndexDesc), C.POINTER(vp)]),
+        "pgvrx_index_destroy": (None, [vp]),
+        "pgvrx_index_load_graph": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i64, i64]),
+        "pgvrx_index_size": (i64, [vp]),
+        "pgvrx_search_batch": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats)]),
+        "pgvrx_search_batch_device": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats), vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _elem_dtype(elem):
+    return {ELEM_F32: np.float32, ELEM_F16: np.uint16, ELEM_BIT: np.uint8}[elem]
+
+
+def _rows(elem, dim, a):
+    a = np.asarray(a)
+    if elem == ELEM_F16 and a.dtype == np.float16:
+        a = a.view(np.uint16)
+    a = np.ascontiguousarray(a, dtype=_elem_dtype(elem))
+    if a.ndim == 1:
+        a = a[None, :]
+    want = (dim + 7) // 8 if elem == ELEM_BIT else dim
+    if a.shape[1] != want:
+        raise PgvrxError(ERR_INVALID, "expected %d elements per row, got %d" % (want, a.shape[1]))
+    return a
+
+
+def normalize(elem, dim, row):
+    """FUNCTION 2 + normalise, bit-identical to the reference (vector.rs:106-126, halfvec.rs:204-233)."""
+    a = _rows(elem, dim, row)
+    out = np.zeros_like(a)
+    norm = C.c_double()
+    rc = lib().pgvrx_normalize(elem, dim, _p(a), _p(out), C.byref(norm))
+    if rc != OK:
+        raise PgvrxError(rc, lib().pgvrx_last_error(None).decode())
+    return norm.value, out[0]
+
+
+class HnswIndex:
+    """Host-side handle mirroring `CREATE INDEX ... USING hnsw (col <opclass>) WITH (m, ef_construction)`.
+
+    Session settings mirror the GUCs (src/index/options.rs:81-96): `ef_search` (hnsw.ef_search,
+    default 40)."""
+
+    def __init__(self, opclass, dim, m=16, ef_construction=64, capacity=0, device=0):
+        if opclass not in OPCLASSES:
+            raise PgvrxError(ERR_INVALID, "operator class \"%s\" does not exist for access method \"hnsw\"" % opclass)
+        self.opclass = opclass
+        self.elem, self.metric, self.normalized = OPCLASSES[opclass]
+        self.dim, self.m, self.ef_construction = dim, m, ef_construction
+        self.ef_search = 40
+        self.L = lib()
+        d = IndexDesc(self.elem, self.metric, dim, m, ef_construction, device, capacity)
+        h = C.c_void_p()
+        rc = self.L.pgvrx_index_create(C.byref(d), C.byref(h))
+        if rc != OK:
+            raise PgvrxError(rc, self.L.pgvrx_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pgvrx_index_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != OK:
+            raise PgvrxError(rc, self.L.pgvrx_last_error(self.h).decode())
+
+    def __len__(self):
+        return self.L.pgvrx_index_size(self.h)
+
+    def load_graph(self, rows, level, adj0, upper_base, adj_up, entry):
+        rows = _rows(self.elem, self.dim, rows)
+        level = np.ascontiguousarray(level, np.uint8)
+        adj0 = np.ascontiguousarray(adj0, np.int32)
+        upper_base = np.ascontiguousarray(upper_base, np.int32)
+        adj_up = np.ascontiguousarray(adj_up, np.int32).reshape(-1, self.m)
+        self._check(self.L.pgvrx_index_load_graph(self.h, _p(rows), len(rows), _p(level), _p(adj0), _p(upper_base),
+                                                  _p(adj_up) if len(adj_up) else None, len(adj_up), int(entry)))
+
+    def prepare_queries(self, queries):
+        """Query-side half of the opclass: normalise when FUNCTION 2 exists (scan.rs:749-754)."""
+        q = _rows(self.elem, self.dim, queries)
+        if self.normalized:
+            q = np.stack([normalize(self.elem, self.dim, r)[1] for r in q])
+        return q
+
+    def search(self, queries, k=10, ef_search=None, with_stats=False):
+        """Batched index scan (hnsw.iterative_scan = off): k nearest element ids per query."""
+        q = self.prepare_queries(queries)
+        ef = self.ef_search if ef_search is None else ef_search
+        nq = len(q)
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.int32)
+        st = SearchStats()
+        self._check(self.L.pgvrx_search_batch(self.h, _p(q), nq, ef, k, _p(ids), _p(dists), _p(counts),
+                                              C.byref(st) if with_stats else None))
+        return (ids, dists, counts, st.as_dict()) if with_stats else (ids, dists, counts)
+
+    def search_device(self, d_queries_ptr, nq, k, ef_search, d_ids_ptr, d_dists_ptr, d_counts_ptr, stream=0, stats=None):
+        """Device-pointer variant (queries already in HBM); asynchronous on `stream` unless stats is given."""
+        self._check(self.L.pgvrx_search_batch_device(self.h, d_queries_ptr, nq, ef_search, k, d_ids_ptr, d_dists_ptr,
+                                                     d_counts_ptr, C.byref(stats) if stats is not None else None,
+                                                     C.c_void_p(stream) if stream else None))

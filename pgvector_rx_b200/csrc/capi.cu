@@ -1,0 +1,467 @@
+// capi.cu -- implementation of include/pgvrx_b200.h: handle, HBM-resident graph, launches.
+//
+// Nothing here computes a distance or walks a graph on the CPU.  If no CUDA device is usable every
+// compute entry point fails with PGVRX_ERR_CUDA: there is no fallback path.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pgvrx_b200.h"
+#include "hnsw_kernels.h"
+
+using namespace pgvrx;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+inline uint32_t round16u(size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); }
+
+}  // namespace
+
+struct pgvrx_index {
+    pgvrx_index_desc desc{};
+    size_t row_bytes = 0;
+    uint32_t row_stride = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // graph in HBM
+    DevBuf vectors, adj0, adj_up, upper_base, level;
+    int64_t n = 0, n_upper = 0, entry = -1;
+    int entry_level = -1;
+    bool loaded = false;
+    // scratch
+    DevBuf q, ids, dists, counts, status, ctr, vis, vis_retry, qmap, work;
+    std::string err;
+};
+
+namespace {
+
+int fail(pgvrx_index *idx, int code, const std::string &msg) {
+    if (idx) idx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(idx, expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            char _b[512];                                                                       \
+            snprintf(_b, sizeof _b, "%s: %s (%s:%d)", cudaGetErrorName(_e), cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                       \
+            cudaGetLastError();                                                                 \
+            return fail(idx, _e == cudaErrorMemoryAllocation ? PGVRX_ERR_NOMEM : PGVRX_ERR_CUDA, _b); \
+        }                                                                                       \
+    } while (0)
+
+bool metric_ok(int elem, int metric) {
+    if (elem == PGVRX_ELEM_BIT) return metric == PGVRX_METRIC_HAMMING || metric == PGVRX_METRIC_JACCARD;
+    if (elem == PGVRX_ELEM_F32 || elem == PGVRX_ELEM_F16)
+        return metric == PGVRX_METRIC_L2SQ || metric == PGVRX_METRIC_NEG_IP || metric == PGVRX_METRIC_L1;
+    return false;
+}
+
+int max_dim(int elem) {
+    return elem == PGVRX_ELEM_F32 ? PGVRX_MAX_DIM_VECTOR : elem == PGVRX_ELEM_F16 ? PGVRX_MAX_DIM_HALFVEC
+                                                                                 : PGVRX_MAX_DIM_BIT;
+}
+
+GraphView view_of(const pgvrx_index *ix) {
+    GraphView g;
+    g.vectors = (const uint8_t *)ix->vectors.p;
+    g.adj0 = (const int32_t *)ix->adj0.p;
+    g.adj_up = (const int32_t *)ix->adj_up.p;
+    g.upper_base = (const int32_t *)ix->upper_base.p;
+    g.level = (const uint8_t *)ix->level.p;
+    g.n = (int32_t)ix->n;
+    g.m = ix->desc.m;
+    g.dim = ix->desc.dim;
+    g.entry = (int32_t)ix->entry;
+    g.entry_level = ix->entry_level;
+    g.row_stride = ix->row_stride;
+    return g;
+}
+
+uint32_t pow2_at_least(uint64_t x) {
+    uint32_t p = 256;
+    while (p < x && p < (1u << 30)) p <<= 1;
+    return p;
+}
+
+// one search configuration: staging geometry, scratch sizes, grid
+struct ScanConfig {
+    SearchLaunch L;
+    uint32_t vis_entries;
+    size_t smem_block;
+    int grid;
+};
+
+int make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int64_t nq, int max_grid, ScanConfig *out) {
+    const uint32_t STAGE_BUDGET = 17 * 1024;
+    ScanConfig c;
+    c.L.ef = ef;
+    c.L.tail_cap = tail_cap;
+    c.L.row_stride = ix->row_stride;
+    // LDS.128 by one lane per row is conflict free when consecutive rows start 16 B * odd apart
+    c.L.stage_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
+    c.L.R = (int)std::max<uint32_t>(1, std::min<uint32_t>(32, STAGE_BUDGET / c.L.stage_stride));
+    c.vis_entries = vis_entries;
+    c.smem_block = search_warp_smem(c.L) * (SEARCH_THREADS / 32);
+    if (c.smem_block > 227 * 1024) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search configuration exceeds shared memory");
+    int occ = 0;
+    CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.smem_block, &occ));
+    if (occ < 1) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search kernel does not fit on an SM");
+    int64_t want = (nq + SEARCH_THREADS / 32 - 1) / (SEARCH_THREADS / 32);
+    int64_t cap = (int64_t)ix->sm_count * occ;
+    if (max_grid > 0) cap = std::min<int64_t>(cap, max_grid);
+    c.grid = (int)std::max<int64_t>(1, std::min(want, cap));
+    *out = c;
+    return PGVRX_OK;
+}
+
+int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64_t nq, int ef, int k,
+                int32_t *d_ids, float *d_dists, int32_t *d_counts, pgvrx_search_stats *stats,
+                cudaStream_t stream, bool check_status) {
+    if (!ix->loaded) return fail(ix, PGVRX_ERR_STATE, "no graph loaded");
+    if (ef < PGVRX_MIN_EF_SEARCH || ef > PGVRX_MAX_EF_SEARCH)
+        return fail(ix, PGVRX_ERR_INVALID, "hnsw.ef_search must be between 1 and 1000");   // options.rs:157-166
+    if (k < 1 || nq < 0 || nq > (int64_t)1 << 30) return fail(ix, PGVRX_ERR_INVALID, "bad k or nq");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (nq == 0) return PGVRX_OK;
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+
+    const int m = ix->desc.m;
+    ScanConfig main_cfg, retry_cfg;
+    uint32_t vis_main = pow2_at_least(std::max<uint64_t>(1024, (uint64_t)ef * 2 * m * 2));
+    int rc = make_config(ix, ef, 32, vis_main, nq, 0, &main_cfg);
+    if (rc) return rc;
+    uint32_t vis_retry = pow2_at_least(std::min<uint64_t>((uint64_t)vis_main * 16, std::max<uint64_t>(1024, (uint64_t)ix->n * 2)));
+    rc = make_config(ix, ef, 2048, vis_retry, nq, ix->sm_count, &retry_cfg);
+    if (rc) return rc;
+
+    const int wpb = SEARCH_THREADS / 32;
+    CU_TRY(ix, ix->vis.ensure((size_t)main_cfg.grid * wpb * main_cfg.vis_entries * 4));
+    CU_TRY(ix, ix->vis_retry.ensure((size_t)retry_cfg.grid * wpb * retry_cfg.vis_entries * 4));
+    CU_TRY(ix, ix->status.ensure((size_t)nq * 4));
+    CU_TRY(ix, ix->qmap.ensure((size_t)nq * 4));
+    CU_TRY(ix, ix->work.ensure(64));
+    if (stats) CU_TRY(ix, ix->ctr.ensure((size_t)nq * 16));
+
+    int *work = (int *)ix->work.p;   // [0] main counter, [1] retry counter, [2] n_failed
+    CU_TRY(ix, cudaMemsetAsync(work, 0, 64, stream));
+    if (stats) CU_TRY(ix, cudaEventRecord(ix->ev0, stream));
+
+    GraphView g = view_of(ix);
+    SearchParams p;
+    p.queries = (const uint8_t *)d_queries;
+    p.q_stride = q_stride;
+    p.q_bytes = (uint32_t)ix->row_bytes;
+    p.qmap = nullptr;
+    p.n_work = nullptr;
+    p.nq = (int)nq;
+    p.ef = ef;
+    p.k = k;
+    p.tail_cap = main_cfg.L.tail_cap;
+    p.out_ids = d_ids;
+    p.out_dists = d_dists;
+    p.out_counts = d_counts;
+    p.out_status = (uint32_t *)ix->status.p;
+    p.out_ctr = stats ? (uint32_t *)ix->ctr.p : nullptr;
+    p.vis_base = (uint32_t *)ix->vis.p;
+    p.vis_entries = main_cfg.vis_entries;
+    p.work_counter = work + 0;
+    p.stage_stride = main_cfg.L.stage_stride;
+    p.R = main_cfg.L.R;
+    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, g, p, main_cfg.grid, main_cfg.smem_block, stream));
+
+    // queries that overflowed their visited table or tie tail run again with 16x the scratch
+    CU_TRY(ix, launch_collect_failed(p.out_status, (int)nq, (int32_t *)ix->qmap.p, work + 2, stream));
+    SearchParams r = p;
+    r.qmap = (const int32_t *)ix->qmap.p;
+    r.n_work = work + 2;
+    r.tail_cap = retry_cfg.L.tail_cap;
+    r.vis_base = (uint32_t *)ix->vis_retry.p;
+    r.vis_entries = retry_cfg.vis_entries;
+    r.work_counter = work + 1;
+    r.stage_stride = retry_cfg.L.stage_stride;
+    r.R = retry_cfg.L.R;
+    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, g, r, retry_cfg.grid, retry_cfg.smem_block, stream));
+
+    if (stats) {
+        CU_TRY(ix, cudaEventRecord(ix->ev1, stream));
+        CU_TRY(ix, cudaStreamSynchronize(stream));
+        CU_TRY(ix, cudaEventElapsedTime(&stats->kernel_ms, ix->ev0, ix->ev1));
+        stats->n_launches = 3;
+        std::vector<uint32_t> h((size_t)nq * 4);
+        CU_TRY(ix, cudaMemcpy(h.data(), ix->ctr.p, (size_t)nq * 16, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < nq; i++) {
+            stats->n_dist += h[(size_t)i * 4 + 0];
+            stats->n_expand0 += h[(size_t)i * 4 + 1];
+            stats->n_expand_upper += h[(size_t)i * 4 + 2];
+            stats->n_visited += h[(size_t)i * 4 + 3];
+        }
+        int nf = 0;
+        CU_TRY(ix, cudaMemcpy(&nf, work + 2, 4, cudaMemcpyDeviceToHost));
+        stats->n_retried = (uint64_t)nf;
+    }
+    if (check_status) {
+        CU_TRY(ix, cudaStreamSynchronize(stream));
+        std::vector<uint32_t> st((size_t)nq);
+        CU_TRY(ix, cudaMemcpy(st.data(), ix->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < nq; i++)
+            if (st[(size_t)i] != 0) {
+                char b[160];
+                snprintf(b, sizeof b, "query %lld exhausted the search scratch (status %u) even after the retry pass",
+                         (long long)i, st[(size_t)i]);
+                return fail(ix, PGVRX_ERR_UNSUPPORTED, b);
+            }
+    }
+    return PGVRX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgvrx_abi_version(void) { return PGVRX_ABI_VERSION; }
+
+const char *pgvrx_last_error(const pgvrx_index *idx) { return idx ? idx->err.c_str() : g_create_error.c_str(); }
+
+int pgvrx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+size_t pgvrx_row_bytes(int32_t elem_type, int32_t dim) {
+    if (dim <= 0) return 0;
+    switch (elem_type) {
+        case PGVRX_ELEM_F32: return (size_t)dim * 4;
+        case PGVRX_ELEM_F16: return (size_t)dim * 2;
+        case PGVRX_ELEM_BIT: return ((size_t)dim + 7) / 8;
+    }
+    return 0;
+}
+
+// types/hnsw.rs:337-349 with PostgreSQL's 8 KiB page: (8192 - 24 - 8 - 4 - 4) / 6 / m - 2, at most 255
+int32_t pgvrx_max_level(int32_t m) {
+    if (m < 1) return 0;
+    int v = (8192 - 24 - 8 - 4 - 4) / 6 / m - 2;
+    return v < 255 ? v : 255;
+}
+
+// build.rs:373-377
+int32_t pgvrx_level_from_uniform(double r, int32_t m) {
+    if (!(r > std::numeric_limits<double>::min())) r = std::numeric_limits<double>::min();
+    // the reference multiplies by ml = 1/ln(m) (hnsw_constants.rs:132-134); keep that exact form
+    double lv = std::floor(-std::log(r) * (1.0 / std::log((double)m)));
+    int cap = pgvrx_max_level(m);
+    return lv < (double)cap ? (int32_t)lv : cap;
+}
+
+// vector.rs:106-126 / halfvec.rs:204-233.  f32 -> half uses IEEE round-to-nearest-even
+// (__float2half_rn) except that the reference flushes |x| < 2^-24 to zero where IEEE would round
+// (2^-25, 2^-24) up to the smallest subnormal (halfvec.rs:111-113).
+int pgvrx_normalize(int32_t elem_type, int32_t dim, const void *in, void *out, double *norm_out) {
+    if (dim <= 0 || !in || !out) return fail(nullptr, PGVRX_ERR_INVALID, "bad normalize arguments");
+    double norm = 0.0;
+    if (elem_type == PGVRX_ELEM_F32) {
+        const float *a = (const float *)in;
+        float *r = (float *)out;
+        for (int i = 0; i < dim; i++) norm += (double)a[i] * (double)a[i];
+        norm = std::sqrt(norm);
+        for (int i = 0; i < dim; i++) r[i] = norm > 0.0 ? (float)((double)a[i] / norm) : 0.0f;
+    } else if (elem_type == PGVRX_ELEM_F16) {
+        const __half *a = (const __half *)in;
+        __half *r = (__half *)out;
+        for (int i = 0; i < dim; i++) { double v = (double)__half2float(a[i]); norm += v * v; }
+        norm = std::sqrt(norm);
+        bool overflow = false;
+        for (int i = 0; i < dim; i++) {
+            float v = norm > 0.0 ? (float)((double)__half2float(a[i]) / norm) : 0.0f;
+            __half h = std::fabs(v) < 5.9604644775390625e-08f ? __float2half_rn(std::signbit(v) ? -0.0f : 0.0f)
+                                                              : __float2half_rn(v);
+            if (std::isinf(__half2float(h))) overflow = true;
+            r[i] = h;
+        }
+        if (overflow) return fail(nullptr, PGVRX_ERR_INVALID, "value out of range: overflow");   // halfvec.rs:225-230
+    } else {
+        return fail(nullptr, PGVRX_ERR_INVALID, "type has no norm support function");
+    }
+    if (norm_out) *norm_out = norm;
+    return PGVRX_OK;
+}
+
+int pgvrx_index_create(const pgvrx_index_desc *d, pgvrx_index **out) {
+    if (!d || !out) return fail(nullptr, PGVRX_ERR_INVALID, "null argument");
+    *out = nullptr;
+    // messages follow tests/pg_regress/expected/hnsw_vector.out:150-159
+    if (d->m < PGVRX_MIN_M || d->m > PGVRX_MAX_M)
+        return fail(nullptr, PGVRX_ERR_INVALID, "value out of bounds for option \"m\": valid values are between \"2\" and \"100\"");
+    if (d->ef_construction < PGVRX_MIN_EF_CONSTRUCTION || d->ef_construction > PGVRX_MAX_EF_CONSTRUCTION)
+        return fail(nullptr, PGVRX_ERR_INVALID, "value out of bounds for option \"ef_construction\": valid values are between \"4\" and \"1000\"");
+    if (d->ef_construction < 2 * d->m)
+        return fail(nullptr, PGVRX_ERR_INVALID, "ef_construction must be greater than or equal to 2 * m");
+    if (!metric_ok(d->elem_type, d->metric)) return fail(nullptr, PGVRX_ERR_INVALID, "operator class does not match the indexed type");
+    if (d->dim < 1) return fail(nullptr, PGVRX_ERR_INVALID, "column does not have dimensions");
+    if (d->dim > max_dim(d->elem_type)) {
+        char b[128];
+        snprintf(b, sizeof b, "column cannot have more than %d dimensions for hnsw index", max_dim(d->elem_type));
+        return fail(nullptr, PGVRX_ERR_INVALID, b);
+    }
+    if (d->capacity < 0 || d->capacity > (int64_t)0x7ffffff0) return fail(nullptr, PGVRX_ERR_INVALID, "capacity out of range");
+    int ndev = pgvrx_device_count();
+    if (ndev <= 0) return fail(nullptr, PGVRX_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (d->device < 0 || d->device >= ndev) return fail(nullptr, PGVRX_ERR_INVALID, "bad device ordinal");
+    pgvrx_index *ix = new (std::nothrow) pgvrx_index();
+    if (!ix) return fail(nullptr, PGVRX_ERR_NOMEM, "out of host memory");
+    ix->desc = *d;
+    ix->row_bytes = pgvrx_row_bytes(d->elem_type, d->dim);
+    ix->row_stride = round16u(ix->row_bytes);
+    cudaError_t e = cudaSetDevice(d->device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d->device);
+    if (e == cudaSuccess && prop.major < 10) {
+        delete ix;
+        return fail(nullptr, PGVRX_ERR_UNSUPPORTED, "device is not sm_100-class (kernels are built for sm_100a only)");
+    }
+    if (e == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ix->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ix->ev1);
+    if (e != cudaSuccess) {
+        std::string msg = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e);
+        pgvrx_index_destroy(ix);
+        cudaGetLastError();
+        return fail(nullptr, PGVRX_ERR_CUDA, msg);
+    }
+    *out = ix;
+    return PGVRX_OK;
+}
+
+void pgvrx_index_destroy(pgvrx_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->desc.device);
+    DevBuf *bufs[] = {&ix->vectors, &ix->adj0, &ix->adj_up, &ix->upper_base, &ix->level, &ix->q, &ix->ids, &ix->dists,
+                      &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work};
+    for (DevBuf *b : bufs) b->release();
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+int64_t pgvrx_index_size(const pgvrx_index *ix) { return ix ? ix->n : 0; }
+
+int pgvrx_index_load_graph(pgvrx_index *ix, const void *rows, int64_t n, const uint8_t *level, const int32_t *adj0,
+                           const int32_t *upper_base, const int32_t *adj_up, int64_t n_upper_rows, int64_t entry) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (n < 0 || n > ix->desc.capacity) return fail(ix, PGVRX_ERR_INVALID, "n exceeds the handle's capacity");
+    if (n > 0 && (!rows || !level || !adj0 || !upper_base)) return fail(ix, PGVRX_ERR_INVALID, "null graph array");
+    if (n_upper_rows < 0 || (n_upper_rows > 0 && !adj_up)) return fail(ix, PGVRX_ERR_INVALID, "bad upper-layer rows");
+    if (n == 0) entry = -1;
+    if (n > 0 && (entry < 0 || entry >= n)) return fail(ix, PGVRX_ERR_INVALID, "entry point out of range");
+    const int m = ix->desc.m;
+    // validate ids once on the host: the kernels trust them
+    for (int64_t i = 0; i < n; i++) {
+        int lv = level[i];
+        if ((lv > 0) != (upper_base[i] >= 0) || (lv > 0 && upper_base[i] + lv > n_upper_rows))
+            return fail(ix, PGVRX_ERR_INVALID, "upper_base inconsistent with level");
+        if (lv > pgvrx_max_level(m)) return fail(ix, PGVRX_ERR_INVALID, "level above the maximum for m");
+    }
+    for (int64_t i = 0; i < n * 2 * m; i++)
+        if (adj0[i] < -1 || adj0[i] >= n) return fail(ix, PGVRX_ERR_INVALID, "layer-0 neighbour id out of range");
+    for (int64_t i = 0; i < n_upper_rows * m; i++)
+        if (adj_up[i] < -1 || adj_up[i] >= n) return fail(ix, PGVRX_ERR_INVALID, "upper-layer neighbour id out of range");
+
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    ix->loaded = false;
+    CU_TRY(ix, ix->vectors.ensure(std::max<size_t>(16, (size_t)n * ix->row_stride)));
+    CU_TRY(ix, ix->adj0.ensure(std::max<size_t>(16, (size_t)n * 2 * m * 4)));
+    CU_TRY(ix, ix->adj_up.ensure(std::max<size_t>(16, (size_t)n_upper_rows * m * 4)));
+    CU_TRY(ix, ix->upper_base.ensure(std::max<size_t>(16, (size_t)n * 4)));
+    CU_TRY(ix, ix->level.ensure(std::max<size_t>(16, (size_t)n)));
+    if (n > 0) {
+        if (ix->row_stride == ix->row_bytes) {
+            CU_TRY(ix, cudaMemcpyAsync(ix->vectors.p, rows, (size_t)n * ix->row_bytes, cudaMemcpyHostToDevice, ix->stream));
+        } else {
+            CU_TRY(ix, cudaMemsetAsync(ix->vectors.p, 0, (size_t)n * ix->row_stride, ix->stream));
+            CU_TRY(ix, cudaMemcpy2DAsync(ix->vectors.p, ix->row_stride, rows, ix->row_bytes, ix->row_bytes, (size_t)n,
+                                         cudaMemcpyHostToDevice, ix->stream));
+        }
+        CU_TRY(ix, cudaMemcpyAsync(ix->adj0.p, adj0, (size_t)n * 2 * m * 4, cudaMemcpyHostToDevice, ix->stream));
+        if (n_upper_rows > 0)
+            CU_TRY(ix, cudaMemcpyAsync(ix->adj_up.p, adj_up, (size_t)n_upper_rows * m * 4, cudaMemcpyHostToDevice, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(ix->upper_base.p, upper_base, (size_t)n * 4, cudaMemcpyHostToDevice, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(ix->level.p, level, (size_t)n, cudaMemcpyHostToDevice, ix->stream));
+        CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+    }
+    ix->n = n;
+    ix->n_upper = n_upper_rows;
+    ix->entry = entry;
+    ix->entry_level = n > 0 ? level[entry] : -1;
+    ix->loaded = true;
+    return PGVRX_OK;
+}
+
+int pgvrx_search_batch_device(pgvrx_index *ix, const void *d_queries, int64_t nq, int32_t ef_search, int32_t k,
+                              int32_t *d_ids, float *d_dists, int32_t *d_counts, pgvrx_search_stats *stats,
+                              void *cuda_stream) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (nq > 0 && (!d_queries || !d_ids || !d_dists || !d_counts)) return fail(ix, PGVRX_ERR_INVALID, "null device buffer");
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ix->stream;
+    return search_core(ix, d_queries, (uint32_t)ix->row_bytes, nq, ef_search, k, d_ids, d_dists, d_counts, stats, s, false);
+}
+
+int pgvrx_search_batch(pgvrx_index *ix, const void *queries, int64_t nq, int32_t ef_search, int32_t k, int32_t *out_ids,
+                       float *out_dists, int32_t *out_counts, pgvrx_search_stats *stats) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (nq > 0 && (!queries || !out_ids || !out_dists || !out_counts)) return fail(ix, PGVRX_ERR_INVALID, "null buffer");
+    if (nq < 0 || k < 1) return fail(ix, PGVRX_ERR_INVALID, "bad k or nq");
+    if (nq == 0) { if (stats) memset(stats, 0, sizeof *stats); return PGVRX_OK; }
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    CU_TRY(ix, ix->q.ensure((size_t)nq * ix->row_bytes));
+    CU_TRY(ix, ix->ids.ensure((size_t)nq * k * 4));
+    CU_TRY(ix, ix->dists.ensure((size_t)nq * k * 4));
+    CU_TRY(ix, ix->counts.ensure((size_t)nq * 4));
+    CU_TRY(ix, cudaMemcpyAsync(ix->q.p, queries, (size_t)nq * ix->row_bytes, cudaMemcpyHostToDevice, ix->stream));
+    int rc = search_core(ix, ix->q.p, (uint32_t)ix->row_bytes, nq, ef_search, k, (int32_t *)ix->ids.p, (float *)ix->dists.p,
+                         (int32_t *)ix->counts.p, stats, ix->stream, true);
+    if (rc) return rc;
+    CU_TRY(ix, cudaMemcpyAsync(out_ids, ix->ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+    CU_TRY(ix, cudaMemcpyAsync(out_dists, ix->dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+    CU_TRY(ix, cudaMemcpyAsync(out_counts, ix->counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->stream));
+    CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+    return PGVRX_OK;
+}
+
+}  // extern "C"

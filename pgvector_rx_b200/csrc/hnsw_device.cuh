@@ -1,0 +1,336 @@
+// hnsw_device.cuh -- warp-level building blocks of the B200 HNSW search kernels.
+//
+// One warp owns one query.  Per expansion the warp
+//   1. reads the candidate's neighbour row (one coalesced 128-B load for m = 16),
+//   2. tests/marks every neighbour in an exact per-query visited hash table (global, L2 resident),
+//   3. gathers the unvisited neighbours' vectors into shared memory with one TMA bulk copy
+//      (cp.async.bulk, mbarrier completion) per row,
+//   4. evaluates one distance per LANE, each lane walking its row strictly left to right with
+//      separate multiply and add -- bit-identical to the reference's scalar loops
+//      (src/types/vector.rs:518-567, halfvec.rs:687-733, bitvec.rs:97-132),
+//   5. applies the reference's accept / evict rule in neighbour order
+//      (src/graph/mod.rs:205-243, src/index/scan.rs:362-430) against a sorted result list.
+//
+// The candidate heap C and the result heap W of the reference are one sorted array S of
+// (distance, id) keys: W = S[0, ef), an "expanded" flag per entry replaces C, and entries evicted
+// from W that still tie with W's furthest distance are retained behind position ef because the
+// reference would still expand them (stop rule is strict `>`, graph/mod.rs:191, scan.rs:340).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hnsw_kernels.h"
+
+namespace pgvrx {
+
+constexpr uint32_t VIS_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+enum : int { ELEM_F32 = 0, ELEM_F16 = 1, ELEM_BIT = 2 };
+enum : int { METRIC_L2SQ = 0, METRIC_NEG_IP = 1, METRIC_L1 = 2, METRIC_HAMMING = 3, METRIC_JACCARD = 4 };
+
+// per-query status bits (non-zero => the host re-runs the query with larger scratch)
+enum : uint32_t { ST_VIS_OVERFLOW = 1u, ST_TIE_OVERFLOW = 2u };
+
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA bulk copy (global -> shared), L2 eviction policy
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// TMA 1-D bulk copy of one vector row: SASS UBLKCP.  dst/src 16-B aligned, bytes % 16 == 0.
+__device__ __forceinline__ void tma_row_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// keys: (order-preserving f32 bits) << 32 | id << 1 | expanded
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f32_ord(float d) {
+    d = __fadd_rn(d, 0.0f);  // -0.0 -> +0.0 : the reference compares with partial_cmp, where they are equal
+    uint32_t b = __float_as_uint(d);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord_f32(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t make_key(float d, uint32_t id) {
+    return ((uint64_t)f32_ord(d) << 32) | ((uint64_t)id << 1);
+}
+__device__ __forceinline__ uint32_t key_ord(uint64_t k) { return (uint32_t)(k >> 32); }
+__device__ __forceinline__ uint32_t key_id(uint64_t k) { return ((uint32_t)k) >> 1; }
+
+// ------------------------------------------------------------------------------------------
+// exact visited set: open addressing in a per-warp global table (HashSet semantics,
+// graph/mod.rs:171,206-209; scan.rs:317,366-369)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t vis_hash(uint32_t id) { return id * 0x9E3779B1u; }
+
+// returns true when id was not in the set (and is now)
+__device__ __forceinline__ bool vis_insert(uint32_t *tab, uint32_t mask, uint32_t id) {
+    uint32_t h = (vis_hash(id) >> 7) & mask;
+    for (uint32_t probes = 0; probes <= mask; probes++) {
+        uint32_t old = atomicCAS(tab + h, VIS_EMPTY, id);
+        if (old == VIS_EMPTY) return true;
+        if (old == id) return false;
+        h = (h + 1) & mask;
+    }
+    return false;  // unreachable: the caller keeps the load factor <= 3/4
+}
+__device__ __forceinline__ void vis_clear(uint32_t *tab, uint32_t entries, int lane) {
+    uint4 e = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
+    uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+    for (uint32_t i = lane; i < entries / 4; i += 32) t4[i] = e;
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// distances: one LANE per row, strict left-to-right f32 accumulation, no FMA contraction
+// ------------------------------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ float acc_step(float acc, float q, float x) {
+    if (METRIC == METRIC_L2SQ) {
+        float d = __fsub_rn(q, x);                    // vector.rs:522-523
+        return __fadd_rn(acc, __fmul_rn(d, d));
+    } else if (METRIC == METRIC_NEG_IP) {
+        return __fadd_rn(acc, __fmul_rn(q, x));       // vector.rs:534
+    } else {
+        return __fadd_rn(acc, fabsf(__fsub_rn(q, x))); // vector.rs:564
+    }
+}
+
+// q, row: shared memory, 16-B aligned, nvec 16-byte vectors (zero padded: padding adds +0.0 exactly)
+template <int ELEM, int METRIC>
+__device__ __forceinline__ float row_distance(const uint8_t *q, const uint8_t *row, int nvec) {
+    const uint4 *q4 = reinterpret_cast<const uint4 *>(q);
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
+    if (ELEM == ELEM_F32) {
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int j = 0; j < nvec; j++) {
+            uint4 a = q4[j], b = r4[j];
+            acc = acc_step<METRIC>(acc, __uint_as_float(a.x), __uint_as_float(b.x));
+            acc = acc_step<METRIC>(acc, __uint_as_float(a.y), __uint_as_float(b.y));
+            acc = acc_step<METRIC>(acc, __uint_as_float(a.z), __uint_as_float(b.z));
+            acc = acc_step<METRIC>(acc, __uint_as_float(a.w), __uint_as_float(b.w));
+        }
+        return METRIC == METRIC_NEG_IP ? -acc : acc;   // vector.rs:631 (f64 negate, exact)
+    } else if (ELEM == ELEM_F16) {
+        float acc = 0.0f;
+#pragma unroll 2
+        for (int j = 0; j < nvec; j++) {
+            uint4 a = q4[j], b = r4[j];
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                // half -> f32 is exact for every value (halfvec.rs:54-87 restates IEEE decoding)
+                float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&aw[t]));
+                float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&bw[t]));
+                acc = acc_step<METRIC>(acc, fa.x, fb.x);
+                acc = acc_step<METRIC>(acc, fa.y, fb.y);
+            }
+        }
+        return METRIC == METRIC_NEG_IP ? -acc : acc;
+    } else {
+        // bitvec.rs:97-132: integer popcounts (order-free, exact)
+        uint32_t x = 0, ab = 0, aa = 0, bb = 0;
+#pragma unroll 4
+        for (int j = 0; j < nvec; j++) {
+            uint4 a = q4[j], b = r4[j];
+            if (METRIC == METRIC_HAMMING) {
+                x += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+            } else {
+                ab += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+                aa += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w);
+                bb += __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+            }
+        }
+        if (METRIC == METRIC_HAMMING) return (float)x;
+        if (ab == 0) return 1.0f;                                     // bitvec.rs:127-128
+        double j = 1.0 - ((double)ab / (double)(aa + bb - ab));       // bitvec.rs:130
+        return (float)j;                                              // build.rs:367 `as f32`
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-warp search state
+// ------------------------------------------------------------------------------------------
+struct WarpCtx {
+    uint8_t *stage;        // R rows, stage_stride apart
+    uint8_t *qsm;          // query row
+    uint64_t *S;           // cap + 1 sorted keys
+    int32_t *nbr;          // 32 compacted neighbour ids
+    uint64_t *mbar;
+    uint32_t *vis;         // global visited table of this warp slot
+    uint64_t policy;
+    uint32_t stage_stride;
+    int R, nvec;
+    int len, ef, cap, hint;
+    uint32_t phase;
+    uint32_t f_ord;        // ordered bits of W's furthest distance (valid when len >= ef)
+    uint32_t n_dist, n_exp0, n_expu, n_vis, status;
+    int lane;
+};
+
+// insert key into S keeping it sorted ascending; maintain len / hint / f_ord and the tie tail
+__device__ __forceinline__ void list_insert(WarpCtx &c, uint64_t key) {
+    const int lane = c.lane;
+    int pos = 0;
+    for (int base = 0; base < c.len; base += 32) {
+        int i = base + lane;
+        bool lt = i < c.len && c.S[i] < key;
+        pos += __popc(__ballot_sync(FULL, lt));
+    }
+    // shift [pos, len) right by one, highest chunk first
+    for (int base = ((c.len - 1) >> 5) << 5; base >= 0 && base + 31 >= pos && c.len > 0; base -= 32) {
+        int i = base + lane;
+        bool mv = i >= pos && i < c.len;
+        uint64_t v = mv ? c.S[i] : 0;
+        __syncwarp();
+        if (mv) c.S[i + 1] = v;
+        __syncwarp();
+    }
+    if (lane == 0) c.S[pos] = key;
+    __syncwarp();
+    c.len += 1;
+    if (pos < c.hint) c.hint = pos;
+    if (c.len >= c.ef) {
+        c.f_ord = key_ord(c.S[c.ef - 1]);
+        if (c.len > c.ef) {
+            // keep only evicted entries that still tie with the furthest distance of W
+            int keep = 0;
+            for (int base = c.ef; base < c.len; base += 32) {
+                int i = base + lane;
+                bool eq = i < c.len && key_ord(c.S[i]) == c.f_ord;
+                keep += __popc(__ballot_sync(FULL, eq));
+            }
+            c.len = c.ef + keep;
+            if (c.len > c.cap) { c.len = c.cap; c.status |= ST_TIE_OVERFLOW; }
+        }
+    }
+}
+
+// index of the nearest unexpanded entry or -1
+__device__ __forceinline__ int list_first_unexpanded(const WarpCtx &c) {
+    for (int base = (c.hint >> 5) << 5; base < c.len; base += 32) {
+        int i = base + c.lane;
+        bool un = i >= c.hint && i < c.len && (c.S[i] & 1ull) == 0;
+        uint32_t b = __ballot_sync(FULL, un);
+        if (b) return base + __ffs(b) - 1;
+    }
+    return -1;
+}
+
+// search_layer (graph/mod.rs:161-255 == scan.rs:302-448 without the iterative-scan bookkeeping).
+// Precondition: S[0, len) holds the entry points (unexpanded), their ids are in the visited set.
+template <int ELEM, int METRIC>
+__device__ __forceinline__ void search_layer(WarpCtx &c, const GraphView &g, int layer, uint32_t vis_mask,
+                                             uint32_t vis_limit) {
+    const int lane = c.lane;
+    const int lm = layer == 0 ? 2 * g.m : g.m;
+    uint32_t vis_count = (uint32_t)c.len;
+    while (true) {
+        int i = list_first_unexpanded(c);
+        if (i < 0) break;            // every remaining candidate would fail `c.distance > f_dist`
+        uint64_t ckey = c.S[i];
+        __syncwarp();
+        if (lane == 0) c.S[i] = ckey | 1ull;
+        __syncwarp();
+        c.hint = i + 1;
+        const uint32_t cid = key_id(ckey);
+        const int32_t *row;
+        if (layer == 0) {
+            row = g.adj0 + (size_t)cid * (size_t)lm;
+            c.n_exp0++;
+        } else {
+            row = g.adj_up + ((size_t)__ldg(g.upper_base + cid) + (size_t)(layer - 1)) * (size_t)lm;
+            c.n_expu++;
+        }
+        for (int base = 0; base < lm; base += 32) {
+            int j = base + lane;
+            int32_t nb = j < lm ? __ldg(row + j) : -1;
+            bool valid = nb >= 0;                       // lists are dense prefixes (scan.rs:273-279)
+            if (!__any_sync(FULL, valid)) break;
+            bool fresh = valid && vis_insert(c.vis, vis_mask, (uint32_t)nb);   // visited BEFORE the level test
+            uint32_t fm = __ballot_sync(FULL, fresh);
+            vis_count += __popc(fm);
+            c.n_vis += __popc(fm);
+            bool pass = fresh;
+            if (layer > 0 && fresh) pass = __ldg(g.level + nb) >= layer;        // graph/mod.rs:214, scan.rs:410
+            uint32_t pm = __ballot_sync(FULL, pass);
+            int cnt = __popc(pm);
+            if (vis_count > vis_limit) { c.status |= ST_VIS_OVERFLOW; return; }
+            if (cnt == 0) continue;
+            int rank = __popc(pm & ((1u << lane) - 1u));
+            if (pass) c.nbr[rank] = nb;
+            __syncwarp();
+            for (int s = 0; s < cnt; s += c.R) {
+                int nrow = min(c.R, cnt - s);
+                int32_t my = lane < nrow ? c.nbr[s + lane] : -1;
+                if (lane == 0) mbar_arrive_expect_tx(c.mbar, (uint32_t)nrow * g.row_stride);
+                __syncwarp();
+                if (lane < nrow)
+                    tma_row_g2s(c.stage + (size_t)lane * c.stage_stride,
+                                g.vectors + (size_t)my * g.row_stride, g.row_stride, c.mbar, c.policy);
+                mbar_wait(c.mbar, c.phase);
+                c.phase ^= 1u;
+                float d = 0.0f;
+                if (lane < nrow) d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)lane * c.stage_stride, c.nvec);
+                c.n_dist += nrow;
+                // accept in neighbour order (graph/mod.rs:226-242): the threshold only tightens and W only
+                // fills up, so lanes failing against the CURRENT threshold can never be accepted later
+                uint32_t dord = f32_ord(d);
+                bool maybe = lane < nrow && (c.len < c.ef || dord < c.f_ord);
+                uint32_t am = __ballot_sync(FULL, maybe);
+                while (am) {
+                    int r = __ffs(am) - 1;
+                    am &= am - 1;
+                    float dr = __shfl_sync(FULL, d, r);
+                    int32_t idr = __shfl_sync(FULL, my, r);
+                    bool always_add = min(c.len, c.ef) < c.ef;
+                    if (always_add || f32_ord(dr) < c.f_ord) list_insert(c, make_key(dr, (uint32_t)idr));
+                }
+                __syncwarp();   // all lanes done with the staging rows before they are overwritten
+            }
+        }
+    }
+}
+
+}  // namespace pgvrx

@@ -1,0 +1,54 @@
+// hnsw_kernels.h -- launch interface between the C-ABI layer (capi.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace pgvrx {
+
+struct GraphView {
+    const uint8_t *vectors;     // n rows, row_stride bytes apart, zero padded to 16 B
+    const int32_t *adj0;        // n x 2m, -1 after the last neighbour
+    const int32_t *adj_up;      // upper rows x m
+    const int32_t *upper_base;  // n: first upper row or -1
+    const uint8_t *level;       // n
+    int32_t n, m, dim;
+    int32_t entry, entry_level;
+    uint32_t row_stride;        // bytes, multiple of 16
+};
+
+constexpr int SEARCH_THREADS = 128;   // 4 warps = 4 queries in flight per CTA
+
+struct SearchParams {
+    const uint8_t *queries;    // device, q_stride bytes apart, q_bytes valid bytes each
+    uint32_t q_stride, q_bytes;
+    const int32_t *qmap;       // retry launch: indices of the queries to run (else NULL)
+    const int *n_work;         // retry launch: number of entries in qmap (device)
+    int nq;
+    int ef, k, tail_cap;
+    int32_t *out_ids;          // nq x k
+    float *out_dists;          // nq x k
+    int32_t *out_counts;       // nq
+    uint32_t *out_status;      // nq
+    uint32_t *out_ctr;         // nq x 4 (n_dist, n_expand0, n_expand_upper, n_visited) or NULL
+    uint32_t *vis_base;        // per warp-slot visited tables
+    uint32_t vis_entries;      // entries per table, power of two >= 256
+    int *work_counter;         // zeroed before the launch
+    uint32_t stage_stride;     // bytes between staged rows (row_stride, +16 when that avoids bank conflicts)
+    int R;                     // staged rows per warp (<= 32)
+};
+
+// what the host needs to size shared memory
+struct SearchLaunch {
+    int R, ef, tail_cap;
+    uint32_t stage_stride, row_stride;
+};
+
+size_t search_warp_smem(const SearchLaunch &L);
+cudaError_t scan_kernel_occupancy(int elem, int metric, size_t smem_block, int *blocks_per_sm);
+cudaError_t launch_scan_kernel(int elem, int metric, const GraphView &g, const SearchParams &p, int grid,
+                               size_t smem_block, cudaStream_t stream);
+cudaError_t launch_collect_failed(const uint32_t *status, int nq, int32_t *qmap, int *n_work, cudaStream_t stream);
+
+}  // namespace pgvrx

@@ -1,0 +1,198 @@
+// hnsw_search.cu -- K1: batched multi-layer HNSW scan (get_scan_items, src/index/scan.rs:458-530).
+//
+// Persistent grid, one warp per query, queries handed out through an atomic counter so uneven
+// search lengths balance.  See hnsw_device.cuh for the per-warp machinery and DESIGN.md for the
+// data layout and the roofline that bounds this kernel (HBM, gathered vector rows).
+#include "hnsw_device.cuh"
+#include "hnsw_kernels.h"
+
+namespace pgvrx {
+
+__host__ __device__ inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// shared memory bytes one warp needs
+size_t search_warp_smem(const SearchLaunch &L) {
+    size_t b = (size_t)L.R * L.stage_stride;        // staging rows
+    b += L.row_stride;                               // query
+    b += round16((uint32_t)((L.ef + L.tail_cap + 1) * 8));  // S
+    b += 128;                                        // nbr ids
+    b += 16;                                         // mbarrier
+    return b;
+}
+
+template <int ELEM, int METRIC>
+__global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, SearchParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cap = p.ef + p.tail_cap;
+    const size_t s_bytes = round16((uint32_t)((cap + 1) * 8));
+    const size_t per_warp = (size_t)p.R * p.stage_stride + g.row_stride + s_bytes + 128 + 16;
+    uint8_t *base = smem + (size_t)warp * per_warp;
+
+    WarpCtx c;
+    c.stage = base;
+    c.qsm = c.stage + (size_t)p.R * p.stage_stride;
+    c.S = reinterpret_cast<uint64_t *>(c.qsm + g.row_stride);
+    c.nbr = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(c.S) + s_bytes);
+    c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
+    c.stage_stride = p.stage_stride;
+    c.R = p.R;
+    c.nvec = (int)(g.row_stride / 16);
+    c.cap = cap;
+    c.lane = lane;
+    c.phase = 0;
+    c.policy = l2_policy_evict_first();
+    const int slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
+    c.vis = p.vis_base + (size_t)slot * p.vis_entries;
+
+    if (lane == 0) {
+        mbar_init(c.mbar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    const uint32_t up_entries = p.vis_entries < 1024u ? p.vis_entries : 1024u;
+
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(p.work_counter, 1);
+        w = __shfl_sync(FULL, w, 0);
+        const int nwork = p.qmap ? *p.n_work : p.nq;
+        if (w >= nwork) break;
+        const int qi = p.qmap ? p.qmap[w] : w;
+
+        c.n_dist = c.n_exp0 = c.n_expu = c.n_vis = 0;
+        c.status = 0;
+
+        // ---- query row -> shared memory (zero padded to row_stride) ----
+        {
+            const uint8_t *q = p.queries + (size_t)qi * p.q_stride;
+            if ((p.q_stride & 15u) == 0 && p.q_bytes == g.row_stride) {
+                const uint4 *q4 = reinterpret_cast<const uint4 *>(q);
+                uint4 *d4 = reinterpret_cast<uint4 *>(c.qsm);
+                for (int i = lane; i < c.nvec; i += 32) d4[i] = __ldg(q4 + i);
+            } else {
+                for (uint32_t i = lane; i < g.row_stride; i += 32) c.qsm[i] = i < p.q_bytes ? __ldg(q + i) : (uint8_t)0;
+            }
+        }
+        __syncwarp();
+
+        int out_n = 0;
+        if (g.entry >= 0) {      // empty index => no rows (scan.rs:470-472)
+            // ---- distance to the entry point (scan.rs:475-486) ----
+            if (lane == 0) mbar_arrive_expect_tx(c.mbar, g.row_stride);
+            __syncwarp();
+            if (lane == 0) tma_row_g2s(c.stage, g.vectors + (size_t)g.entry * g.row_stride, g.row_stride, c.mbar, c.policy);
+            mbar_wait(c.mbar, c.phase);
+            c.phase ^= 1u;
+            float d0 = 0.0f;
+            if (lane == 0) d0 = row_distance<ELEM, METRIC>(c.qsm, c.stage, c.nvec);
+            d0 = __shfl_sync(FULL, d0, 0);
+            c.n_dist = 1;
+            __syncwarp();
+            if (lane == 0) c.S[0] = make_key(d0, (uint32_t)g.entry);
+            __syncwarp();
+
+            // ---- greedy descent: ef = 1, fresh visited set per layer (scan.rs:492-512) ----
+            c.ef = 1;
+            for (int lc = g.entry_level; lc >= 1 && c.status == 0; lc--) {
+                vis_clear(c.vis, up_entries, lane);
+                if (lane == 0) {
+                    c.S[0] &= ~1ull;
+                    vis_insert(c.vis, up_entries - 1, key_id(c.S[0]));
+                }
+                __syncwarp();
+                c.n_vis++;
+                c.len = 1;
+                c.hint = 0;
+                c.f_ord = key_ord(c.S[0]);
+                search_layer<ELEM, METRIC>(c, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
+            }
+            // ---- layer 0 with ef_search (scan.rs:515-528) ----
+            if (c.status == 0) {
+                vis_clear(c.vis, p.vis_entries, lane);
+                if (lane == 0) {
+                    c.S[0] &= ~1ull;
+                    vis_insert(c.vis, p.vis_entries - 1, key_id(c.S[0]));
+                }
+                __syncwarp();
+                c.n_vis++;
+                c.ef = p.ef;
+                c.len = 1;
+                c.hint = 0;
+                c.f_ord = key_ord(c.S[0]);
+                search_layer<ELEM, METRIC>(c, g, 0, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
+            }
+            out_n = min(min(c.len, c.ef), p.k);   // W = S[0, ef); nearest first (scan.rs:861)
+        }
+
+        // ---- results ----
+        if (c.status == 0) {
+            for (int i = lane; i < p.k; i += 32) {
+                bool ok = i < out_n;
+                uint64_t key = ok ? c.S[i] : 0;
+                p.out_ids[(size_t)qi * p.k + i] = ok ? (int32_t)key_id(key) : -1;
+                p.out_dists[(size_t)qi * p.k + i] = ok ? ord_f32(key_ord(key)) : __int_as_float(0x7f800000);
+            }
+            if (lane == 0) p.out_counts[qi] = out_n;
+        } else if (lane == 0) {
+            p.out_counts[qi] = -1;
+        }
+        if (lane == 0) {
+            p.out_status[qi] = c.status;
+            if (p.out_ctr) {
+                uint4 v = make_uint4(c.n_dist, c.n_exp0, c.n_expu, c.n_vis);
+                reinterpret_cast<uint4 *>(p.out_ctr)[qi] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// gather the queries whose status is non-zero into qmap / n_work for the retry launch
+__global__ void collect_failed_kernel(const uint32_t *status, int nq, int32_t *qmap, int *n_work) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq && status[i] != 0) qmap[atomicAdd(n_work, 1)] = i;
+}
+
+typedef void (*scan_kernel_t)(GraphView, SearchParams);
+
+static scan_kernel_t pick_kernel(int elem, int metric) {
+    if (elem == ELEM_F32) {
+        if (metric == METRIC_L2SQ) return hnsw_scan_kernel<ELEM_F32, METRIC_L2SQ>;
+        if (metric == METRIC_NEG_IP) return hnsw_scan_kernel<ELEM_F32, METRIC_NEG_IP>;
+        if (metric == METRIC_L1) return hnsw_scan_kernel<ELEM_F32, METRIC_L1>;
+    } else if (elem == ELEM_F16) {
+        if (metric == METRIC_L2SQ) return hnsw_scan_kernel<ELEM_F16, METRIC_L2SQ>;
+        if (metric == METRIC_NEG_IP) return hnsw_scan_kernel<ELEM_F16, METRIC_NEG_IP>;
+        if (metric == METRIC_L1) return hnsw_scan_kernel<ELEM_F16, METRIC_L1>;
+    } else if (elem == ELEM_BIT) {
+        if (metric == METRIC_HAMMING) return hnsw_scan_kernel<ELEM_BIT, METRIC_HAMMING>;
+        if (metric == METRIC_JACCARD) return hnsw_scan_kernel<ELEM_BIT, METRIC_JACCARD>;
+    }
+    return nullptr;
+}
+
+cudaError_t scan_kernel_occupancy(int elem, int metric, size_t smem_block, int *blocks_per_sm) {
+    scan_kernel_t k = pick_kernel(elem, metric);
+    if (!k) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, SEARCH_THREADS, smem_block);
+}
+
+cudaError_t launch_scan_kernel(int elem, int metric, const GraphView &g, const SearchParams &p, int grid,
+                               size_t smem_block, cudaStream_t stream) {
+    scan_kernel_t k = pick_kernel(elem, metric);
+    if (!k) return cudaErrorInvalidValue;
+    k<<<grid, SEARCH_THREADS, smem_block, stream>>>(g, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_collect_failed(const uint32_t *status, int nq, int32_t *qmap, int *n_work, cudaStream_t stream) {
+    collect_failed_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(status, nq, qmap, n_work);
+    return cudaGetLastError();
+}
+
+}  // namespace pgvrx

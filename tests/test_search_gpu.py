@@ -1,0 +1,114 @@
+"""GPU parity: the CUDA scan (through the C ABI) against the CPU oracle on the same graph, queries
+and ef_search.  Ids must be identical and distances bit-identical (the kernel reproduces the
+reference's strictly sequential f32 arithmetic); equal distances are ordered by element id on both
+sides (oracle tie mode TOTAL_ORDER)."""
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+import pgvector_rx_b200 as P
+from helpers import assert_same_results, gpu_index, make_rows, oracle_index
+
+pytestmark = pytest.mark.gpu
+
+
+def run_case(opclass, kind, n, dim, nq, m=16, efc=64, efs=(40,), k=10, seed=11):
+    elem, metric, norm = P.OPCLASSES[opclass]
+    rows = make_rows(kind, n, dim, seed)
+    o = oracle_index(opclass, dim, rows, m=m, efc=efc)
+    g = o.export_graph()
+    ix = gpu_index(opclass, dim, g, m=m, efc=efc)
+    q = make_rows(kind, nq, dim, seed + 1)
+    qn = ix.prepare_queries(q)
+    for ef in efs:
+        got = ix.search(q, k=k, ef_search=ef, with_stats=True)
+        want = o.search_batch(qn, ef_search=ef, k=k, with_counters=True)
+        assert_same_results(got, want, "%s n=%d dim=%d ef=%d" % (opclass, n, dim, ef))
+        st, ctr = got[3], want[3]
+        # same traversal => same work counters (these feed the roofline's algorithmic bytes)
+        for key in ("n_dist", "n_expand0", "n_expand_upper", "n_visited"):
+            assert st[key] == ctr[key], (key, st[key], ctr[key])
+        assert st["n_retried"] == 0
+    ix.close()
+
+
+def test_c1_shape_vector_l2_10k():
+    # BASELINE config 1 shape: 10k x 128 fp32, m=16, efc=64, ef_search 40 (and 100)
+    run_case("vector_l2_ops", "f32", 10000, 128, 1000, efs=(40, 100))
+
+
+@pytest.mark.parametrize("opclass", ["vector_ip_ops", "vector_cosine_ops", "vector_l1_ops"])
+def test_vector_metrics(opclass):
+    run_case(opclass, "f32", 3000, 96, 300, efs=(40,))
+
+
+@pytest.mark.parametrize("opclass", ["halfvec_l2_ops", "halfvec_ip_ops", "halfvec_cosine_ops", "halfvec_l1_ops"])
+def test_halfvec_metrics(opclass):
+    run_case(opclass, "f16", 2000, 200, 200, m=8, efc=32, efs=(40,))
+
+
+@pytest.mark.parametrize("opclass,dim", [("bit_hamming_ops", 1024), ("bit_jaccard_ops", 520), ("bit_hamming_ops", 52)])
+def test_bit_metrics_tie_heavy(opclass, dim):
+    # integer distances tie constantly; both sides break ties by element id
+    run_case(opclass, "bit", 3000, dim, 300, efs=(40, 10))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3, 5, 17, 130])
+def test_ragged_dims(dim):
+    run_case("vector_l2_ops", "f32", 600, dim, 100, m=4, efc=16, efs=(8, 40))
+
+
+@pytest.mark.parametrize("m,efc", [(2, 4), (5, 16), (32, 64), (48, 100), (100, 200)])
+def test_m_range(m, efc):
+    run_case("vector_l2_ops", "f32", 1500, 32, 100, m=m, efc=efc, efs=(40,))
+
+
+@pytest.mark.parametrize("ef", [1, 2, 7, 200, 1000])
+def test_ef_search_range(ef):
+    run_case("vector_l2_ops", "f32", 4000, 64, 100, efs=(ef,), k=min(ef, 25))
+
+
+def test_k_larger_than_results_and_tiny_indexes():
+    for n in (1, 2, 5, 33):
+        run_case("vector_l2_ops", "f32", n, 16, 20, m=4, efc=16, efs=(40, 1), k=50)
+
+
+def test_empty_index_returns_no_rows():
+    ix = P.HnswIndex("vector_l2_ops", 8, capacity=4)
+    ix.load_graph(np.zeros((0, 8), np.float32), np.zeros(0, np.uint8), np.zeros((0, 32), np.int32),
+                  np.zeros(0, np.int32), np.zeros((0, 16), np.int32), -1)
+    ids, dists, counts = ix.search(np.ones((3, 8), np.float32), k=5)
+    assert (counts == 0).all() and (ids == -1).all() and np.isinf(dists).all()   # scan.rs:470-472
+    ix.close()
+
+
+def test_duplicates_and_grid_ties():
+    # 10x10 integer grid (scan.rs:1078-1119) queried from lattice points: many exact ties
+    rows = np.array([[i, j] for i in range(10) for j in range(10)], np.float32)
+    o = oracle_index("vector_l2_ops", 2, rows, m=4, efc=16)
+    ix = gpu_index("vector_l2_ops", 2, o.export_graph(), m=4, efc=16)
+    q = np.array([[0, 0], [4.5, 4.5], [9, 0], [3, 3], [-1, 5]], np.float32)
+    for ef in (1, 5, 40):
+        assert_same_results(ix.search(q, k=10, ef_search=ef), o.search_batch(q, ef_search=ef, k=10), "grid ef=%d" % ef)
+    ix.close()
+
+
+def test_invalid_arguments():
+    ix = P.HnswIndex("vector_l2_ops", 4, capacity=8)
+    with pytest.raises(P.PgvrxError) as e:
+        ix.search(np.zeros((1, 4), np.float32))
+    assert e.value.code == P.ERR_STATE
+    rows = np.eye(4, dtype=np.float32)
+    o = oracle_index("vector_l2_ops", 4, rows, m=2, efc=4)
+    ix2 = gpu_index("vector_l2_ops", 4, o.export_graph(), m=2, efc=4)
+    for ef in (0, 1001):                                   # hnsw_vector.out:163-170
+        with pytest.raises(P.PgvrxError) as e:
+            ix2.search(rows, ef_search=ef)
+        assert e.value.code == P.ERR_INVALID and "ef_search" in str(e.value)
+    with pytest.raises(P.PgvrxError):
+        ix2.search(np.zeros((1, 5), np.float32))
+    bad = o.export_graph()
+    bad["adj0"][0, 0] = 99
+    with pytest.raises(P.PgvrxError):
+        gpu_index("vector_l2_ops", 4, bad, m=2, efc=4)
+    ix.close(); ix2.close()
