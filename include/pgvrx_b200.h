@@ -131,6 +131,26 @@ int pgvrx_index_load_graph(pgvrx_index *idx, const void *rows, int64_t n, const 
                            int64_t n_upper_rows, int64_t entry);
 int64_t pgvrx_index_size(const pgvrx_index *idx);
 
+/* ---- page exporter: HNSW relation pages -> the arrays pgvrx_index_load_graph takes ------------- */
+/* `pages` is the index relation's main fork, n_pages * 8192 bytes (block 0 = meta page).  Layout:
+ * src/types/hnsw.rs:18-169; walk: src/index/scan.rs:126-283.  Element ids are assigned in page
+ * order (= build insertion order, build.rs:600-702).  Host code, no device needed. */
+typedef struct {
+    int64_t n_elements;
+    int64_t n_upper_rows;     /* sum of element levels = rows of adj_up                          */
+    int64_t n_heap_tids;
+    int64_t n_deleted;        /* elements flagged deleted (export refuses them for now)          */
+    int64_t entry;            /* element id of HnswMetaPageData.entry_*, -1 when the index is empty */
+    int32_t entry_level;
+    int32_t dims, m, ef_construction;
+} pgvrx_pages_info;
+int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, pgvrx_pages_info *info);
+/* rows: n x row_bytes; level: n; adj0: n x 2m; upper_base: n; adj_up: n_upper_rows x m;
+ * heap_tids (optional): n x 10 as (block << 16 | offset), ~0 when absent; heap_tid_counts (optional): n */
+int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, void *rows, uint8_t *level,
+                       int32_t *adj0, int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids,
+                       uint8_t *heap_tid_counts);
+
 /* ---- scan: get_scan_items, iterative_scan = off (scan.rs:458-530) ------------------------------ */
 /* For each of nq queries (raw element data, row_bytes apart, already normalised for cosine):
  * runs the greedy descent (ef = 1 per upper layer, fresh visited set per layer) and the layer-0

@@ -842,3 +842,149 @@ int orc_flat_topk(int elem_type, int metric, int dim, const void *rows, int64_t 
 }
 
 } // extern "C"
+
+/* ======================================================================================
+ * a19: on-disk pages, written exactly as the flush phase of ambuild does
+ * (src/index/build.rs:545-821; structs src/types/hnsw.rs:18-169; PostgreSQL bufpage.h layout).
+ * Test fixture for the product's page exporter: no PostgreSQL is available in this image.
+ * ==================================================================================== */
+namespace {
+const size_t BLCKSZ = 8192, PAGE_HDR = 24, OPAQUE = 8, ITEMID = 4, ETUP_HDR = 72, NTUP_HDR = 4, TID = 6;
+inline size_t maxalign(size_t x) { return (x + 7) & ~(size_t)7; }                 /* hnsw.rs:316-320 */
+inline void put16(uint8_t *p, uint16_t v) { std::memcpy(p, &v, 2); }
+inline void put32(uint8_t *p, uint32_t v) { std::memcpy(p, &v, 4); }
+inline uint16_t get16(const uint8_t *p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
+inline void put_tid(uint8_t *p, uint32_t blk, uint16_t off) { put16(p, (uint16_t)(blk >> 16)); put16(p + 2, (uint16_t)(blk & 0xffff)); put16(p + 4, off); }
+inline void put_invalid_tid(uint8_t *p) { put_tid(p, 0xFFFFFFFFu, 0); }
+
+struct PageWriter {
+    std::vector<uint8_t> buf;
+    size_t n_pages() const { return buf.size() / BLCKSZ; }
+    uint8_t *page(size_t b) { return buf.data() + b * BLCKSZ; }
+    size_t new_page() {                                   /* hnsw_new_buffer + hnsw_init_page, build.rs:37-64 */
+        size_t b = n_pages();
+        buf.resize(buf.size() + BLCKSZ, 0);
+        uint8_t *p = page(b);
+        put16(p + 12, (uint16_t)PAGE_HDR);                /* pd_lower   */
+        put16(p + 14, (uint16_t)(BLCKSZ - OPAQUE));       /* pd_upper   */
+        put16(p + 16, (uint16_t)(BLCKSZ - OPAQUE));       /* pd_special */
+        put16(p + 18, (uint16_t)(BLCKSZ | 4));            /* pd_pagesize_version */
+        put32(p + BLCKSZ - OPAQUE, 0xFFFFFFFFu);          /* nextblkno = InvalidBlockNumber */
+        put16(p + BLCKSZ - OPAQUE + 4, 0);
+        put16(p + BLCKSZ - OPAQUE + 6, 0xFF90);           /* HNSW_PAGE_ID */
+        return b;
+    }
+    size_t free_space(size_t b) {                         /* PageGetFreeSpace */
+        uint8_t *p = page(b);
+        int space = (int)get16(p + 14) - (int)get16(p + 12);
+        if (space < (int)ITEMID) return 0;
+        return (size_t)space - ITEMID;
+    }
+    uint16_t max_offset(size_t b) { return (uint16_t)((get16(page(b) + 12) - PAGE_HDR) / ITEMID); }
+    uint16_t add_item(size_t b, const uint8_t *item, size_t size) {   /* PageAddItemExtended */
+        uint8_t *p = page(b);
+        uint16_t lower = get16(p + 12), upper = get16(p + 14);
+        size_t al = maxalign(size);
+        uint16_t off = (uint16_t)((lower - PAGE_HDR) / ITEMID + 1);
+        upper = (uint16_t)(upper - al);
+        std::memcpy(p + upper, item, size);
+        uint32_t lp = (uint32_t)upper | (1u << 15) /* LP_NORMAL */ | ((uint32_t)size << 17);
+        put32(p + lower, lp);
+        put16(p + 12, (uint16_t)(lower + ITEMID));
+        put16(p + 14, upper);
+        return off;
+    }
+    uint8_t *item_ptr(size_t b, uint16_t off) {
+        uint8_t *p = page(b);
+        uint32_t lp; std::memcpy(&lp, p + PAGE_HDR + (size_t)(off - 1) * ITEMID, 4);
+        return p + (lp & 0x7fff);
+    }
+};
+} // namespace
+
+extern "C" int64_t orc_write_pages(const orc_index *ix, uint8_t *pages, int64_t cap_pages) {
+    PageWriter w;
+    const size_t max_size = BLCKSZ - maxalign(PAGE_HDR) - maxalign(OPAQUE) - ITEMID;   /* hnsw.rs:325-331 */
+    /* varlena header bytes in front of the raw row: vector/halfvec {vl_len_, i16 dim, i16 unused},
+     * bit {vl_len_, i32 bit_len} (vector.rs:43-48, halfvec.rs:41-46, bitvec.rs:28-32) */
+    const size_t vhdr = 8, value_size = vhdr + ix->row_bytes;
+    /* create_meta_page (build.rs:545-569) */
+    size_t mb = w.new_page();
+    {
+        uint8_t *m = w.page(mb) + PAGE_HDR;
+        put32(m, 0xA953A953u); put32(m + 4, 1); put32(m + 8, (uint32_t)ix->dim);
+        put16(m + 12, (uint16_t)ix->m); put16(m + 14, (uint16_t)ix->efc);
+        put32(m + 16, 0xFFFFFFFFu); put16(m + 20, 0); put16(m + 22, (uint16_t)(int16_t)-1); put32(m + 24, 0xFFFFFFFFu);
+        put16(w.page(mb) + 12, (uint16_t)(PAGE_HDR + 28));
+    }
+    /* create_graph_pages (build.rs:576-702) */
+    size_t cur = w.new_page();
+    struct Loc { uint32_t blk; uint16_t off; uint32_t nblk; uint16_t noff; };
+    std::vector<Loc> locs(ix->elements.size());
+    std::vector<uint8_t> etup, ntup;
+    for (size_t idx = 0; idx < ix->elements.size(); idx++) {
+        const Element &e = ix->elements[idx];
+        size_t etup_size = maxalign(ETUP_HDR + value_size);
+        size_t ntup_size = maxalign(NTUP_HDR + (size_t)(e.level + 2) * ix->m * TID);
+        size_t combined = etup_size + ntup_size + ITEMID;
+        etup.assign(etup_size, 0);
+        etup[0] = 1; etup[1] = (uint8_t)e.level; etup[2] = 0; etup[3] = 0;
+        for (int i = 0; i < HNSW_HEAPTIDS; i++) {
+            if (i < (int)e.heap_tids.size())   /* heap tid = (block tid >> 16, offset tid & 0xffff) for the fixture */
+                put_tid(etup.data() + 4 + i * TID, (uint32_t)(e.heap_tids[(size_t)i] >> 16), (uint16_t)((e.heap_tids[(size_t)i] & 0xffff) + 1));
+            else put_invalid_tid(etup.data() + 4 + i * TID);
+        }
+        uint8_t *val = etup.data() + ETUP_HDR;
+        put32(val, (uint32_t)(value_size << 2));          /* 4-byte varlena header */
+        if (ix->elem_type == ORC_ELEM_BIT) put32(val + 4, (uint32_t)ix->dim);
+        else { put16(val + 4, (uint16_t)ix->dim); put16(val + 6, 0); }
+        std::memcpy(val + vhdr, ix->row((int64_t)idx), ix->row_bytes);
+        size_t fs = w.free_space(cur);
+        bool need_new = fs < etup_size || (combined <= max_size && fs < combined);      /* build.rs:636-638 */
+        if (need_new) { size_t nb = w.new_page(); put32(w.page(cur) + BLCKSZ - OPAQUE, (uint32_t)nb); cur = nb; }
+        uint32_t eblk = (uint32_t)cur;
+        uint16_t eoff = (uint16_t)(w.max_offset(cur) + 1);
+        Loc L;
+        L.blk = eblk; L.off = eoff;
+        if (combined <= max_size) { L.nblk = eblk; L.noff = (uint16_t)(eoff + 1); } else { L.nblk = eblk + 1; L.noff = 1; }
+        locs[idx] = L;
+        put_tid(etup.data() + 4 + HNSW_HEAPTIDS * TID, L.nblk, L.noff);                 /* neighbortid */
+        w.add_item(cur, etup.data(), etup_size);
+        if (w.free_space(cur) < ntup_size) { size_t nb = w.new_page(); put32(w.page(cur) + BLCKSZ - OPAQUE, (uint32_t)nb); cur = nb; }
+        ntup.assign(ntup_size, 0);
+        ntup[0] = 2;
+        w.add_item(cur, ntup.data(), ntup_size);
+    }
+    size_t insert_page = cur;
+    /* write_neighbor_tuples (build.rs:719-790): layers from the top down, lm slots each */
+    for (size_t idx = 0; idx < ix->elements.size(); idx++) {
+        const Element &e = ix->elements[idx];
+        uint8_t *nt = w.item_ptr(locs[idx].nblk, locs[idx].noff);
+        nt[0] = 2; nt[1] = 0;
+        size_t t = 0;
+        for (int lc = e.level; lc >= 0; lc--) {
+            int lm = layer_m(ix->m, lc);
+            for (int i = 0; i < lm; i++, t++) {
+                uint8_t *slot = nt + NTUP_HDR + t * TID;
+                if (i < (int)e.neighbors[(size_t)lc].size()) {
+                    const Loc &n = locs[(size_t)e.neighbors[(size_t)lc][(size_t)i].idx];
+                    put_tid(slot, n.blk, n.off);
+                } else put_invalid_tid(slot);
+            }
+        }
+        put16(nt + 2, (uint16_t)t);
+    }
+    /* update_meta_page (build.rs:797-821) */
+    {
+        uint8_t *m = w.page(mb) + PAGE_HDR;
+        if (ix->entry >= 0) {
+            put32(m + 16, locs[(size_t)ix->entry].blk); put16(m + 20, locs[(size_t)ix->entry].off);
+            put16(m + 22, (uint16_t)(int16_t)ix->elements[(size_t)ix->entry].level);
+        }
+        put32(m + 24, (uint32_t)insert_page);
+    }
+    int64_t np = (int64_t)w.n_pages();
+    if (pages && cap_pages >= np) std::memcpy(pages, w.buf.data(), w.buf.size());
+    return np;
+}
+

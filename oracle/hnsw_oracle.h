@@ -125,6 +125,11 @@ int orc_flat_topk(int elem_type, int metric, int dim, const void *rows, int64_t 
                   const void *queries, int64_t nq, int k, int32_t *out_ids, float *out_dists,
                   int nthreads);
 
+/* ---- a19: on-disk pages (test fixture writer; build.rs:545-821, types/hnsw.rs:18-169) ----- */
+/* serialises the index exactly as the flush phase does; returns number of 8 KiB pages.
+ * Call with pages == NULL to size.  heap TID t is written as (block t >> 16, offset (t & 0xffff) + 1). */
+int64_t orc_write_pages(const orc_index *, uint8_t *pages, int64_t cap_pages);
+
 #ifdef __cplusplus
 }
 #endif

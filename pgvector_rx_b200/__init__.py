@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgvrx_b200.so")
+# PGVRX_LIB selects an alternative build of the same library (e.g. the phase-timing profiling build)
+LIB_PATH = os.environ.get("PGVRX_LIB") or os.path.join(_HERE, "libpgvrx_b200.so")
 
 ELEM_F32, ELEM_F16, ELEM_BIT = 0, 1, 2
 L2SQ, NEG_IP, L1, HAMMING, JACCARD = 0, 1, 2, 3, 4
@@ -37,7 +38,7 @@ EXPORTS = [
     "pgvrx_abi_version", "pgvrx_last_error", "pgvrx_device_count", "pgvrx_normalize",
     "pgvrx_level_from_uniform", "pgvrx_max_level", "pgvrx_row_bytes", "pgvrx_index_create",
     "pgvrx_index_destroy", "pgvrx_index_load_graph", "pgvrx_index_size", "pgvrx_search_batch",
-    "pgvrx_search_batch_device",
+    "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export",
 ]
 
 
@@ -50,6 +51,12 @@ class PgvrxError(RuntimeError):
 class IndexDesc(C.Structure):
     _fields_ = [("elem_type", C.c_int32), ("metric", C.c_int32), ("dim", C.c_int32), ("m", C.c_int32),
                 ("ef_construction", C.c_int32), ("device", C.c_int32), ("capacity", C.c_int64)]
+
+
+class PagesInfo(C.Structure):
+    _fields_ = [("n_elements", C.c_int64), ("n_upper_rows", C.c_int64), ("n_heap_tids", C.c_int64),
+                ("n_deleted", C.c_int64), ("entry", C.c_int64), ("entry_level", C.c_int32), ("dims", C.c_int32),
+                ("m", C.c_int32), ("ef_construction", C.c_int32)]
 
 
 class SearchStats(C.Structure):
@@ -85,6 +92,8 @@ def lib():
         "pgvrx_index_destroy": (None, [vp]),
         "pgvrx_index_load_graph": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i64, i64]),
         "pgvrx_index_size": (i64, [vp]),
+        "pgvrx_pages_inspect": (C.c_int, [vp, i64, i32, C.POINTER(PagesInfo)]),
+        "pgvrx_pages_export": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_search_batch": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats)]),
         "pgvrx_search_batch_device": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats), vp]),
     }
@@ -125,6 +134,34 @@ def normalize(elem, dim, row):
     if rc != OK:
         raise PgvrxError(rc, lib().pgvrx_last_error(None).decode())
     return norm.value, out[0]
+
+
+def export_pages(pages, elem):
+    """Index relation pages (bytes / uint8 array, n * 8192) -> graph dict for HnswIndex.load_graph."""
+    buf = np.ascontiguousarray(np.frombuffer(pages, dtype=np.uint8) if not isinstance(pages, np.ndarray) else pages)
+    n_pages = buf.size // 8192
+    info = PagesInfo()
+    L = lib()
+    rc = L.pgvrx_pages_inspect(_p(buf), n_pages, elem, C.byref(info))
+    if rc != OK:
+        raise PgvrxError(rc, L.pgvrx_last_error(None).decode())
+    n, m = info.n_elements, info.m
+    rb = L.pgvrx_row_bytes(elem, info.dims)
+    rows = np.zeros((n, rb), np.uint8)
+    level = np.zeros(n, np.uint8)
+    adj0 = np.zeros((n, 2 * m), np.int32)
+    upper_base = np.zeros(n, np.int32)
+    adj_up = np.zeros((max(info.n_upper_rows, 1), m), np.int32)
+    tids = np.zeros((n, 10), np.uint64)
+    cnt = np.zeros(n, np.uint8)
+    rc = L.pgvrx_pages_export(_p(buf), n_pages, elem, _p(rows), _p(level), _p(adj0), _p(upper_base), _p(adj_up),
+                              _p(tids), _p(cnt))
+    if rc != OK:
+        raise PgvrxError(rc, L.pgvrx_last_error(None).decode())
+    return dict(rows=rows.view(_elem_dtype(elem)).reshape(n, rb // np.dtype(_elem_dtype(elem)).itemsize), level=level, adj0=adj0, upper_base=upper_base,
+                adj_up=adj_up[:info.n_upper_rows], entry=info.entry, n=n, m=m, dims=info.dims,
+                ef_construction=info.ef_construction, entry_level=info.entry_level, heap_tids=tids,
+                heap_tid_counts=cnt)
 
 
 class HnswIndex:

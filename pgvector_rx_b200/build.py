@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgvrx_b200.so")
-SOURCES = ["capi.cu", "hnsw_search.cu"]
+SOURCES = ["capi.cu", "hnsw_search.cu", "page_export.cpp"]
 HEADERS = ["hnsw_device.cuh", "hnsw_kernels.h", os.path.join("..", "..", "include", "pgvrx_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,18 +32,21 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, timing=False):
+    """timing=True builds libpgvrx_b200_timing.so with per-phase clock64() instrumentation
+    (a profiling aid selected with PGVRX_LIB=...; never the shipped library)."""
+    out = LIB.replace(".so", "_timing.so") if timing else LIB
+    if not force and not timing and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          (["-DPGVRX_PHASE_TIMING"] if timing else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libpgvrx_b200.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timing="--timing" in sys.argv))

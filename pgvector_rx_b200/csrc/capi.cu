@@ -47,6 +47,10 @@ inline uint32_t round16u(size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); 
 
 }  // namespace
 
+namespace pgvrx_host {
+void set_create_error(const std::string &msg) { g_create_error = msg; }
+}
+
 struct pgvrx_index {
     pgvrx_index_desc desc{};
     size_t row_bytes = 0;
@@ -60,7 +64,7 @@ struct pgvrx_index {
     int entry_level = -1;
     bool loaded = false;
     // scratch
-    DevBuf q, ids, dists, counts, status, ctr, vis, vis_retry, qmap, work;
+    DevBuf q, ids, dists, counts, status, ctr, vis, vis_retry, qmap, work, phase;
     std::string err;
 };
 
@@ -125,10 +129,18 @@ struct ScanConfig {
     int grid;
 };
 
+// tail_cap < 0: pick the register-resident list when ef is small enough (capacity 32*J - 1 with at
+// least 16 retained-tie slots), else the shared-memory list with 32 tie slots
 int make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int64_t nq, int max_grid, ScanConfig *out) {
     const uint32_t STAGE_BUDGET = 17 * 1024;
     ScanConfig c;
     c.L.ef = ef;
+    c.L.list_j = 0;
+    if (tail_cap < 0) {
+        tail_cap = 32;
+        for (int j = 2; j <= 8; j *= 2)
+            if (32 * j - 1 - ef >= 16) { c.L.list_j = j; tail_cap = 32 * j - 1 - ef; break; }
+    }
     c.L.tail_cap = tail_cap;
     c.L.row_stride = ix->row_stride;
     // LDS.128 by one lane per row is conflict free when consecutive rows start 16 B * odd apart
@@ -138,7 +150,7 @@ int make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int
     c.smem_block = search_warp_smem(c.L) * (SEARCH_THREADS / 32);
     if (c.smem_block > 227 * 1024) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search configuration exceeds shared memory");
     int occ = 0;
-    CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.smem_block, &occ));
+    CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, &occ));
     if (occ < 1) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search kernel does not fit on an SM");
     int64_t want = (nq + SEARCH_THREADS / 32 - 1) / (SEARCH_THREADS / 32);
     int64_t cap = (int64_t)ix->sm_count * occ;
@@ -162,7 +174,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     const int m = ix->desc.m;
     ScanConfig main_cfg, retry_cfg;
     uint32_t vis_main = pow2_at_least(std::max<uint64_t>(1024, (uint64_t)ef * 2 * m * 2));
-    int rc = make_config(ix, ef, 32, vis_main, nq, 0, &main_cfg);
+    int rc = make_config(ix, ef, -1, vis_main, nq, 0, &main_cfg);
     if (rc) return rc;
     uint32_t vis_retry = pow2_at_least(std::min<uint64_t>((uint64_t)vis_main * 16, std::max<uint64_t>(1024, (uint64_t)ix->n * 2)));
     rc = make_config(ix, ef, 2048, vis_retry, nq, ix->sm_count, &retry_cfg);
@@ -196,12 +208,20 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     p.out_counts = d_counts;
     p.out_status = (uint32_t *)ix->status.p;
     p.out_ctr = stats ? (uint32_t *)ix->ctr.p : nullptr;
+    p.out_phase = nullptr;
+#ifdef PGVRX_PHASE_TIMING
+    if (stats) {
+        CU_TRY(ix, ix->phase.ensure((size_t)nq * 32));
+        CU_TRY(ix, cudaMemsetAsync(ix->phase.p, 0, (size_t)nq * 32, stream));
+        p.out_phase = (uint32_t *)ix->phase.p;
+    }
+#endif
     p.vis_base = (uint32_t *)ix->vis.p;
     p.vis_entries = main_cfg.vis_entries;
     p.work_counter = work + 0;
     p.stage_stride = main_cfg.L.stage_stride;
     p.R = main_cfg.L.R;
-    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, g, p, main_cfg.grid, main_cfg.smem_block, stream));
+    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, stream));
 
     // queries that overflowed their visited table or tie tail run again with 16x the scratch
     CU_TRY(ix, launch_collect_failed(p.out_status, (int)nq, (int32_t *)ix->qmap.p, work + 2, stream));
@@ -214,7 +234,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     r.work_counter = work + 1;
     r.stage_stride = retry_cfg.L.stage_stride;
     r.R = retry_cfg.L.R;
-    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, g, r, retry_cfg.grid, retry_cfg.smem_block, stream));
+    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, retry_cfg.L.list_j, g, r, retry_cfg.grid, retry_cfg.smem_block, stream));
 
     if (stats) {
         CU_TRY(ix, cudaEventRecord(ix->ev1, stream));
@@ -229,6 +249,20 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
             stats->n_expand_upper += h[(size_t)i * 4 + 2];
             stats->n_visited += h[(size_t)i * 4 + 3];
         }
+#ifdef PGVRX_PHASE_TIMING
+        {
+            std::vector<uint32_t> ph((size_t)nq * 8);
+            CU_TRY(ix, cudaMemcpy(ph.data(), ix->phase.p, (size_t)nq * 32, cudaMemcpyDeviceToHost));
+            double sum[8] = {0};
+            for (int64_t i = 0; i < nq; i++) for (int t = 0; t < 8; t++) sum[t] += ph[(size_t)i * 8 + t];
+            fprintf(stderr, "[pgvrx phase cycles/query] pop+adj %.0f  visited %.0f  tma %.0f  distance %.0f  accept %.0f  | total %.0f"
+                            "  (per expansion: %.0f %.0f %.0f %.0f %.0f)\n",
+                    sum[0] / nq, sum[1] / nq, sum[2] / nq, sum[3] / nq, sum[4] / nq, sum[5] / nq,
+                    sum[0] / (stats->n_expand0 + stats->n_expand_upper), sum[1] / (stats->n_expand0 + stats->n_expand_upper),
+                    sum[2] / (stats->n_expand0 + stats->n_expand_upper), sum[3] / (stats->n_expand0 + stats->n_expand_upper),
+                    sum[4] / (stats->n_expand0 + stats->n_expand_upper));
+        }
+#endif
         int nf = 0;
         CU_TRY(ix, cudaMemcpy(&nf, work + 2, 4, cudaMemcpyDeviceToHost));
         stats->n_retried = (uint64_t)nf;
@@ -372,7 +406,7 @@ void pgvrx_index_destroy(pgvrx_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->desc.device);
     DevBuf *bufs[] = {&ix->vectors, &ix->adj0, &ix->adj_up, &ix->upper_base, &ix->level, &ix->q, &ix->ids, &ix->dists,
-                      &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work};
+                      &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work, &ix->phase};
     for (DevBuf *b : bufs) b->release();
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);

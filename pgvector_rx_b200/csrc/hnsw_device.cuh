@@ -124,15 +124,43 @@ __device__ __forceinline__ void vis_clear(uint32_t *tab, uint32_t entries, int l
 // ------------------------------------------------------------------------------------------
 // distances: one LANE per row, strict left-to-right f32 accumulation, no FMA contraction
 // ------------------------------------------------------------------------------------------
+// Blackwell packed fp32: sub.rn.f32x2 / mul.rn.f32x2 (SASS FADD2 / FMUL2) do two IEEE-exact
+// element operations per instruction; only the accumulation has to stay a scalar chain.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    uint64_t ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    uint64_t ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
+// two consecutive elements: element-wise part packed, accumulation strictly in element order
 template <int METRIC>
-__device__ __forceinline__ float acc_step(float acc, float q, float x) {
+__device__ __forceinline__ float acc_step2(float acc, float2 q, float2 x) {
     if (METRIC == METRIC_L2SQ) {
-        float d = __fsub_rn(q, x);                    // vector.rs:522-523
-        return __fadd_rn(acc, __fmul_rn(d, d));
+        float2 d = sub2(q, x);                          // vector.rs:522
+        float2 sq = mul2(d, d);
+        acc = __fadd_rn(acc, sq.x);                     // vector.rs:523
+        return __fadd_rn(acc, sq.y);
     } else if (METRIC == METRIC_NEG_IP) {
-        return __fadd_rn(acc, __fmul_rn(q, x));       // vector.rs:534
+        float2 pr = mul2(q, x);                         // vector.rs:534
+        acc = __fadd_rn(acc, pr.x);
+        return __fadd_rn(acc, pr.y);
     } else {
-        return __fadd_rn(acc, fabsf(__fsub_rn(q, x))); // vector.rs:564
+        float2 d = sub2(q, x);                          // vector.rs:564
+        acc = __fadd_rn(acc, fabsf(d.x));
+        return __fadd_rn(acc, fabsf(d.y));
     }
 }
 
@@ -146,10 +174,10 @@ __device__ __forceinline__ float row_distance(const uint8_t *q, const uint8_t *r
 #pragma unroll 4
         for (int j = 0; j < nvec; j++) {
             uint4 a = q4[j], b = r4[j];
-            acc = acc_step<METRIC>(acc, __uint_as_float(a.x), __uint_as_float(b.x));
-            acc = acc_step<METRIC>(acc, __uint_as_float(a.y), __uint_as_float(b.y));
-            acc = acc_step<METRIC>(acc, __uint_as_float(a.z), __uint_as_float(b.z));
-            acc = acc_step<METRIC>(acc, __uint_as_float(a.w), __uint_as_float(b.w));
+            acc = acc_step2<METRIC>(acc, make_float2(__uint_as_float(a.x), __uint_as_float(a.y)),
+                                    make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
+            acc = acc_step2<METRIC>(acc, make_float2(__uint_as_float(a.z), __uint_as_float(a.w)),
+                                    make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
         }
         return METRIC == METRIC_NEG_IP ? -acc : acc;   // vector.rs:631 (f64 negate, exact)
     } else if (ELEM == ELEM_F16) {
@@ -163,8 +191,7 @@ __device__ __forceinline__ float row_distance(const uint8_t *q, const uint8_t *r
                 // half -> f32 is exact for every value (halfvec.rs:54-87 restates IEEE decoding)
                 float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&aw[t]));
                 float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&bw[t]));
-                acc = acc_step<METRIC>(acc, fa.x, fb.x);
-                acc = acc_step<METRIC>(acc, fa.y, fb.y);
+                acc = acc_step2<METRIC>(acc, fa, fb);
             }
         }
         return METRIC == METRIC_NEG_IP ? -acc : acc;
@@ -195,85 +222,194 @@ __device__ __forceinline__ float row_distance(const uint8_t *q, const uint8_t *r
 struct WarpCtx {
     uint8_t *stage;        // R rows, stage_stride apart
     uint8_t *qsm;          // query row
-    uint64_t *S;           // cap + 1 sorted keys
     int32_t *nbr;          // 32 compacted neighbour ids
     uint64_t *mbar;
     uint32_t *vis;         // global visited table of this warp slot
     uint64_t policy;
     uint32_t stage_stride;
     int R, nvec;
-    int len, ef, cap, hint;
+    int len, ef, cap;      // list length (W plus retained boundary ties), ef, capacity
     uint32_t phase;
     uint32_t f_ord;        // ordered bits of W's furthest distance (valid when len >= ef)
     uint32_t n_dist, n_exp0, n_expu, n_vis, status;
     int lane;
+#ifdef PGVRX_PHASE_TIMING
+    uint32_t t[8];         // cycles: 0 pop+adjacency, 1 visited, 2 tma issue+wait, 3 distance, 4 accept/insert
+    long long t_last;
+#endif
 };
 
-// insert key into S keeping it sorted ascending; maintain len / hint / f_ord and the tie tail
-__device__ __forceinline__ void list_insert(WarpCtx &c, uint64_t key) {
-    const int lane = c.lane;
-    int pos = 0;
-    for (int base = 0; base < c.len; base += 32) {
-        int i = base + lane;
-        bool lt = i < c.len && c.S[i] < key;
-        pos += __popc(__ballot_sync(FULL, lt));
+#ifdef PGVRX_PHASE_TIMING
+#define PH_START(c) (c).t_last = clock64()
+#define PH_TICK(c, slot) do { long long _n = clock64(); (c).t[slot] += (uint32_t)(_n - (c).t_last); (c).t_last = _n; } while (0)
+#else
+#define PH_START(c) do {} while (0)
+#define PH_TICK(c, slot) do {} while (0)
+#endif
+
+constexpr uint64_t KEY_NONE = ~0ull;
+
+// ---- S in registers: entry i lives in lane i / J, register i % J (J * 32 >= cap + 1) -------------
+// No shared-memory round trips: position by REDUX, shift by one shuffle, flag test by ballot.
+template <int J>
+struct RegList {
+    uint64_t k[J];
+
+    __device__ __forceinline__ uint64_t get(const WarpCtx &c, int i) const {
+        uint64_t v = 0;
+#pragma unroll
+        for (int j = 0; j < J; j++) if ((i % J) == j) v = k[j];
+        return __shfl_sync(FULL, v, i / J);
     }
-    // shift [pos, len) right by one, highest chunk first
-    for (int base = ((c.len - 1) >> 5) << 5; base >= 0 && base + 31 >= pos && c.len > 0; base -= 32) {
-        int i = base + lane;
-        bool mv = i >= pos && i < c.len;
-        uint64_t v = mv ? c.S[i] : 0;
-        __syncwarp();
-        if (mv) c.S[i + 1] = v;
-        __syncwarp();
+    __device__ __forceinline__ void reset1(WarpCtx &c, uint64_t key) {
+#pragma unroll
+        for (int j = 0; j < J; j++) k[j] = KEY_NONE;
+        if (c.lane == 0) k[0] = key;
+        c.len = 1;
+        if (c.ef == 1) c.f_ord = key_ord(key);
     }
-    if (lane == 0) c.S[pos] = key;
-    __syncwarp();
-    c.len += 1;
-    if (pos < c.hint) c.hint = pos;
-    if (c.len >= c.ef) {
-        c.f_ord = key_ord(c.S[c.ef - 1]);
-        if (c.len > c.ef) {
-            // keep only evicted entries that still tie with the furthest distance of W
-            int keep = 0;
-            for (int base = c.ef; base < c.len; base += 32) {
-                int i = base + lane;
-                bool eq = i < c.len && key_ord(c.S[i]) == c.f_ord;
-                keep += __popc(__ballot_sync(FULL, eq));
+    __device__ __forceinline__ void insert(WarpCtx &c, uint64_t key) {
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < J; j++) cnt += k[j] < key;           // KEY_NONE is never < key
+        const int pos = __reduce_add_sync(FULL, cnt);
+        const uint64_t carry = __shfl_up_sync(FULL, k[J - 1], 1);
+#pragma unroll
+        for (int j = J - 1; j >= 0; j--) {
+            const int gi = c.lane * J + j;
+            const uint64_t src = j > 0 ? k[j > 0 ? j - 1 : 0] : carry;
+            k[j] = gi > pos ? src : (gi == pos ? key : k[j]);
+        }
+        c.len += 1;
+        if (c.len >= c.ef) {
+            c.f_ord = key_ord(get(c, c.ef - 1));
+            if (c.len > c.ef) {
+                // keep only evicted entries that still tie with the furthest distance of W
+                int keep = 0;
+#pragma unroll
+                for (int j = 0; j < J; j++) {
+                    const int gi = c.lane * J + j;
+                    keep += gi >= c.ef && k[j] != KEY_NONE && key_ord(k[j]) == c.f_ord;
+                }
+                keep = __reduce_add_sync(FULL, keep);
+                int nl = c.ef + keep;
+                if (nl > c.cap) { nl = c.cap; c.status |= ST_TIE_OVERFLOW; }
+#pragma unroll
+                for (int j = 0; j < J; j++) if (c.lane * J + j >= nl) k[j] = KEY_NONE;
+                c.len = nl;
             }
-            c.len = c.ef + keep;
-            if (c.len > c.cap) { c.len = c.cap; c.status |= ST_TIE_OVERFLOW; }
         }
     }
-}
-
-// index of the nearest unexpanded entry or -1
-__device__ __forceinline__ int list_first_unexpanded(const WarpCtx &c) {
-    for (int base = (c.hint >> 5) << 5; base < c.len; base += 32) {
-        int i = base + c.lane;
-        bool un = i >= c.hint && i < c.len && (c.S[i] & 1ull) == 0;
-        uint32_t b = __ballot_sync(FULL, un);
-        if (b) return base + __ffs(b) - 1;
+    // nearest unexpanded entry: mark it expanded and return its key; false when none is left
+    __device__ __forceinline__ bool pop_nearest(WarpCtx &c, uint64_t &key) {
+        int jf = -1;
+#pragma unroll
+        for (int j = J - 1; j >= 0; j--) if (k[j] != KEY_NONE && (k[j] & 1ull) == 0) jf = j;
+        const uint32_t b = __ballot_sync(FULL, jf >= 0);
+        if (!b) return false;
+        const int src = __ffs(b) - 1;
+        uint64_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < J; j++) if (j == jf) mine = k[j];
+        key = __shfl_sync(FULL, mine, src);
+        if (c.lane == src) {
+#pragma unroll
+            for (int j = 0; j < J; j++) if (j == jf) k[j] |= 1ull;
+        }
+        return true;
     }
-    return -1;
-}
+    __device__ __forceinline__ void store(const WarpCtx &c, int32_t *ids, float *dists, int out_n) const {
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+            const int gi = c.lane * J + j;
+            if (gi < out_n) { ids[gi] = (int32_t)key_id(k[j]); dists[gi] = ord_f32(key_ord(k[j])); }
+        }
+    }
+};
+
+// ---- S in shared memory (any ef up to 1000) -------------------------------------------------------
+struct SmemList {
+    uint64_t *S;   // cap + 1 keys
+    int hint;      // every entry below hint is expanded
+
+    __device__ __forceinline__ uint64_t get(const WarpCtx &c, int i) const { return S[i]; }
+    __device__ __forceinline__ void reset1(WarpCtx &c, uint64_t key) {
+        __syncwarp();
+        if (c.lane == 0) S[0] = key;
+        __syncwarp();
+        c.len = 1;
+        hint = 0;
+        if (c.ef == 1) c.f_ord = key_ord(key);
+    }
+    __device__ __forceinline__ void insert(WarpCtx &c, uint64_t key) {
+        const int lane = c.lane;
+        int pos = 0;
+        for (int base = 0; base < c.len; base += 32) {
+            int i = base + lane;
+            bool lt = i < c.len && S[i] < key;
+            pos += __popc(__ballot_sync(FULL, lt));
+        }
+        // shift [pos, len) right by one, highest chunk first
+        for (int base = ((c.len - 1) >> 5) << 5; base >= 0 && base + 31 >= pos && c.len > 0; base -= 32) {
+            int i = base + lane;
+            bool mv = i >= pos && i < c.len;
+            uint64_t v = mv ? S[i] : 0;
+            __syncwarp();
+            if (mv) S[i + 1] = v;
+            __syncwarp();
+        }
+        if (lane == 0) S[pos] = key;
+        __syncwarp();
+        c.len += 1;
+        if (pos < hint) hint = pos;
+        if (c.len >= c.ef) {
+            c.f_ord = key_ord(S[c.ef - 1]);
+            if (c.len > c.ef) {
+                int keep = 0;
+                for (int base = c.ef; base < c.len; base += 32) {
+                    int i = base + lane;
+                    bool eq = i < c.len && key_ord(S[i]) == c.f_ord;
+                    keep += __popc(__ballot_sync(FULL, eq));
+                }
+                c.len = c.ef + keep;
+                if (c.len > c.cap) { c.len = c.cap; c.status |= ST_TIE_OVERFLOW; }
+            }
+        }
+    }
+    __device__ __forceinline__ bool pop_nearest(WarpCtx &c, uint64_t &key) {
+        for (int base = (hint >> 5) << 5; base < c.len; base += 32) {
+            int i = base + c.lane;
+            bool un = i >= hint && i < c.len && (S[i] & 1ull) == 0;
+            uint32_t b = __ballot_sync(FULL, un);
+            if (b) {
+                int idx = base + __ffs(b) - 1;
+                key = S[idx];
+                __syncwarp();
+                if (c.lane == 0) S[idx] = key | 1ull;
+                __syncwarp();
+                hint = idx + 1;
+                return true;
+            }
+        }
+        return false;
+    }
+    __device__ __forceinline__ void store(const WarpCtx &c, int32_t *ids, float *dists, int out_n) const {
+        for (int i = c.lane; i < out_n; i += 32) { ids[i] = (int32_t)key_id(S[i]); dists[i] = ord_f32(key_ord(S[i])); }
+    }
+};
 
 // search_layer (graph/mod.rs:161-255 == scan.rs:302-448 without the iterative-scan bookkeeping).
 // Precondition: S[0, len) holds the entry points (unexpanded), their ids are in the visited set.
-template <int ELEM, int METRIC>
-__device__ __forceinline__ void search_layer(WarpCtx &c, const GraphView &g, int layer, uint32_t vis_mask,
+template <int ELEM, int METRIC, class LIST>
+__device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphView &g, int layer, uint32_t vis_mask,
                                              uint32_t vis_limit) {
     const int lane = c.lane;
     const int lm = layer == 0 ? 2 * g.m : g.m;
     uint32_t vis_count = (uint32_t)c.len;
     while (true) {
-        int i = list_first_unexpanded(c);
-        if (i < 0) break;            // every remaining candidate would fail `c.distance > f_dist`
-        uint64_t ckey = c.S[i];
-        __syncwarp();
-        if (lane == 0) c.S[i] = ckey | 1ull;
-        __syncwarp();
-        c.hint = i + 1;
+        uint64_t ckey;
+        PH_START(c);
+        if (!S.pop_nearest(c, ckey)) break;   // every remaining candidate would fail `c.distance > f_dist`
         const uint32_t cid = key_id(ckey);
         const int32_t *row;
         if (layer == 0) {
@@ -288,6 +424,7 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, const GraphView &g, int
             int32_t nb = j < lm ? __ldg(row + j) : -1;
             bool valid = nb >= 0;                       // lists are dense prefixes (scan.rs:273-279)
             if (!__any_sync(FULL, valid)) break;
+            PH_TICK(c, 0);
             bool fresh = valid && vis_insert(c.vis, vis_mask, (uint32_t)nb);   // visited BEFORE the level test
             uint32_t fm = __ballot_sync(FULL, fresh);
             vis_count += __popc(fm);
@@ -301,6 +438,7 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, const GraphView &g, int
             int rank = __popc(pm & ((1u << lane) - 1u));
             if (pass) c.nbr[rank] = nb;
             __syncwarp();
+            PH_TICK(c, 1);
             for (int s = 0; s < cnt; s += c.R) {
                 int nrow = min(c.R, cnt - s);
                 int32_t my = lane < nrow ? c.nbr[s + lane] : -1;
@@ -311,9 +449,12 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, const GraphView &g, int
                                 g.vectors + (size_t)my * g.row_stride, g.row_stride, c.mbar, c.policy);
                 mbar_wait(c.mbar, c.phase);
                 c.phase ^= 1u;
+                PH_TICK(c, 2);
                 float d = 0.0f;
                 if (lane < nrow) d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)lane * c.stage_stride, c.nvec);
                 c.n_dist += nrow;
+                __syncwarp();
+                PH_TICK(c, 3);
                 // accept in neighbour order (graph/mod.rs:226-242): the threshold only tightens and W only
                 // fills up, so lanes failing against the CURRENT threshold can never be accepted later
                 uint32_t dord = f32_ord(d);
@@ -325,9 +466,10 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, const GraphView &g, int
                     float dr = __shfl_sync(FULL, d, r);
                     int32_t idr = __shfl_sync(FULL, my, r);
                     bool always_add = min(c.len, c.ef) < c.ef;
-                    if (always_add || f32_ord(dr) < c.f_ord) list_insert(c, make_key(dr, (uint32_t)idr));
+                    if (always_add || f32_ord(dr) < c.f_ord) S.insert(c, make_key(dr, (uint32_t)idr));
                 }
                 __syncwarp();   // all lanes done with the staging rows before they are overwritten
+                PH_TICK(c, 4);
             }
         }
     }

@@ -32,6 +32,7 @@ struct SearchParams {
     int32_t *out_counts;       // nq
     uint32_t *out_status;      // nq
     uint32_t *out_ctr;         // nq x 4 (n_dist, n_expand0, n_expand_upper, n_visited) or NULL
+    uint32_t *out_phase;       // nq x 8 per-phase cycle counts (PGVRX_PHASE_TIMING builds only) or NULL
     uint32_t *vis_base;        // per warp-slot visited tables
     uint32_t vis_entries;      // entries per table, power of two >= 256
     int *work_counter;         // zeroed before the launch
@@ -42,12 +43,13 @@ struct SearchParams {
 // what the host needs to size shared memory
 struct SearchLaunch {
     int R, ef, tail_cap;
+    int list_j;                // 0: result list in shared memory; 2/4/8: registers per lane
     uint32_t stage_stride, row_stride;
 };
 
 size_t search_warp_smem(const SearchLaunch &L);
-cudaError_t scan_kernel_occupancy(int elem, int metric, size_t smem_block, int *blocks_per_sm);
-cudaError_t launch_scan_kernel(int elem, int metric, const GraphView &g, const SearchParams &p, int grid,
+cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm);
+cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView &g, const SearchParams &p, int grid,
                                size_t smem_block, cudaStream_t stream);
 cudaError_t launch_collect_failed(const uint32_t *status, int nq, int32_t *qmap, int *n_work, cudaStream_t stream);
 

@@ -14,28 +14,40 @@ __host__ __device__ inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15
 size_t search_warp_smem(const SearchLaunch &L) {
     size_t b = (size_t)L.R * L.stage_stride;        // staging rows
     b += L.row_stride;                               // query
-    b += round16((uint32_t)((L.ef + L.tail_cap + 1) * 8));  // S
+    if (L.list_j == 0) b += round16((uint32_t)((L.ef + L.tail_cap + 1) * 8));  // S (else it lives in registers)
     b += 128;                                        // nbr ids
     b += 16;                                         // mbarrier
     return b;
 }
 
-template <int ELEM, int METRIC>
+template <int J> struct ListOf {
+    typedef RegList<J> type;
+    __device__ static __forceinline__ void attach(type &, uint8_t *) {}
+};
+template <> struct ListOf<0> {
+    typedef SmemList type;
+    __device__ static __forceinline__ void attach(type &l, uint8_t *mem) { l.S = reinterpret_cast<uint64_t *>(mem); l.hint = 0; }
+};
+
+// LISTJ: 0 = result list in shared memory, else registers per lane (list capacity 32 * LISTJ)
+template <int ELEM, int METRIC, int LISTJ>
 __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int cap = p.ef + p.tail_cap;
-    const size_t s_bytes = round16((uint32_t)((cap + 1) * 8));
+    const size_t s_bytes = LISTJ == 0 ? round16((uint32_t)((cap + 1) * 8)) : 0;
     const size_t per_warp = (size_t)p.R * p.stage_stride + g.row_stride + s_bytes + 128 + 16;
     uint8_t *base = smem + (size_t)warp * per_warp;
 
     WarpCtx c;
     c.stage = base;
     c.qsm = c.stage + (size_t)p.R * p.stage_stride;
-    c.S = reinterpret_cast<uint64_t *>(c.qsm + g.row_stride);
-    c.nbr = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(c.S) + s_bytes);
+    uint8_t *s_mem = c.qsm + g.row_stride;
+    c.nbr = reinterpret_cast<int32_t *>(s_mem + s_bytes);
     c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
+    typename ListOf<LISTJ>::type S;
+    ListOf<LISTJ>::attach(S, s_mem);
     c.stage_stride = p.stage_stride;
     c.R = p.R;
     c.nvec = (int)(g.row_stride / 16);
@@ -64,6 +76,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
 
         c.n_dist = c.n_exp0 = c.n_expu = c.n_vis = 0;
         c.status = 0;
+#ifdef PGVRX_PHASE_TIMING
+        for (int t = 0; t < 8; t++) c.t[t] = 0;
+        const long long t_query0 = clock64();
+#endif
 
         // ---- query row -> shared memory (zero padded to row_stride) ----
         {
@@ -91,49 +107,38 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
             d0 = __shfl_sync(FULL, d0, 0);
             c.n_dist = 1;
             __syncwarp();
-            if (lane == 0) c.S[0] = make_key(d0, (uint32_t)g.entry);
-            __syncwarp();
+            uint64_t ep_key = make_key(d0, (uint32_t)g.entry);
 
             // ---- greedy descent: ef = 1, fresh visited set per layer (scan.rs:492-512) ----
             c.ef = 1;
             for (int lc = g.entry_level; lc >= 1 && c.status == 0; lc--) {
                 vis_clear(c.vis, up_entries, lane);
-                if (lane == 0) {
-                    c.S[0] &= ~1ull;
-                    vis_insert(c.vis, up_entries - 1, key_id(c.S[0]));
-                }
+                if (lane == 0) vis_insert(c.vis, up_entries - 1, key_id(ep_key));
                 __syncwarp();
                 c.n_vis++;
-                c.len = 1;
-                c.hint = 0;
-                c.f_ord = key_ord(c.S[0]);
-                search_layer<ELEM, METRIC>(c, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
+                S.reset1(c, ep_key);
+                search_layer<ELEM, METRIC>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
+                ep_key = S.get(c, 0) & ~1ull;     // nearest of W becomes the next entry point (scan.rs:510)
             }
             // ---- layer 0 with ef_search (scan.rs:515-528) ----
             if (c.status == 0) {
                 vis_clear(c.vis, p.vis_entries, lane);
-                if (lane == 0) {
-                    c.S[0] &= ~1ull;
-                    vis_insert(c.vis, p.vis_entries - 1, key_id(c.S[0]));
-                }
+                if (lane == 0) vis_insert(c.vis, p.vis_entries - 1, key_id(ep_key));
                 __syncwarp();
                 c.n_vis++;
                 c.ef = p.ef;
-                c.len = 1;
-                c.hint = 0;
-                c.f_ord = key_ord(c.S[0]);
-                search_layer<ELEM, METRIC>(c, g, 0, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
+                S.reset1(c, ep_key);
+                search_layer<ELEM, METRIC>(c, S, g, 0, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
             }
             out_n = min(min(c.len, c.ef), p.k);   // W = S[0, ef); nearest first (scan.rs:861)
         }
 
         // ---- results ----
         if (c.status == 0) {
-            for (int i = lane; i < p.k; i += 32) {
-                bool ok = i < out_n;
-                uint64_t key = ok ? c.S[i] : 0;
-                p.out_ids[(size_t)qi * p.k + i] = ok ? (int32_t)key_id(key) : -1;
-                p.out_dists[(size_t)qi * p.k + i] = ok ? ord_f32(key_ord(key)) : __int_as_float(0x7f800000);
+            S.store(c, p.out_ids + (size_t)qi * p.k, p.out_dists + (size_t)qi * p.k, out_n);
+            for (int i = out_n + lane; i < p.k; i += 32) {
+                p.out_ids[(size_t)qi * p.k + i] = -1;
+                p.out_dists[(size_t)qi * p.k + i] = __int_as_float(0x7f800000);
             }
             if (lane == 0) p.out_counts[qi] = out_n;
         } else if (lane == 0) {
@@ -145,6 +150,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
                 uint4 v = make_uint4(c.n_dist, c.n_exp0, c.n_expu, c.n_vis);
                 reinterpret_cast<uint4 *>(p.out_ctr)[qi] = v;
             }
+#ifdef PGVRX_PHASE_TIMING
+            if (p.out_phase) {
+                c.t[5] = (uint32_t)(clock64() - t_query0);
+                for (int t = 0; t < 8; t++) p.out_phase[(size_t)qi * 8 + t] = c.t[t];
+            }
+#endif
         }
         __syncwarp();
     }
@@ -158,33 +169,44 @@ __global__ void collect_failed_kernel(const uint32_t *status, int nq, int32_t *q
 
 typedef void (*scan_kernel_t)(GraphView, SearchParams);
 
-static scan_kernel_t pick_kernel(int elem, int metric) {
-    if (elem == ELEM_F32) {
-        if (metric == METRIC_L2SQ) return hnsw_scan_kernel<ELEM_F32, METRIC_L2SQ>;
-        if (metric == METRIC_NEG_IP) return hnsw_scan_kernel<ELEM_F32, METRIC_NEG_IP>;
-        if (metric == METRIC_L1) return hnsw_scan_kernel<ELEM_F32, METRIC_L1>;
-    } else if (elem == ELEM_F16) {
-        if (metric == METRIC_L2SQ) return hnsw_scan_kernel<ELEM_F16, METRIC_L2SQ>;
-        if (metric == METRIC_NEG_IP) return hnsw_scan_kernel<ELEM_F16, METRIC_NEG_IP>;
-        if (metric == METRIC_L1) return hnsw_scan_kernel<ELEM_F16, METRIC_L1>;
-    } else if (elem == ELEM_BIT) {
-        if (metric == METRIC_HAMMING) return hnsw_scan_kernel<ELEM_BIT, METRIC_HAMMING>;
-        if (metric == METRIC_JACCARD) return hnsw_scan_kernel<ELEM_BIT, METRIC_JACCARD>;
+template <int ELEM, int METRIC>
+static scan_kernel_t pick_list(int list_j) {
+    switch (list_j) {
+        case 2: return hnsw_scan_kernel<ELEM, METRIC, 2>;
+        case 4: return hnsw_scan_kernel<ELEM, METRIC, 4>;
+        case 8: return hnsw_scan_kernel<ELEM, METRIC, 8>;
+        case 0: return hnsw_scan_kernel<ELEM, METRIC, 0>;
     }
     return nullptr;
 }
 
-cudaError_t scan_kernel_occupancy(int elem, int metric, size_t smem_block, int *blocks_per_sm) {
-    scan_kernel_t k = pick_kernel(elem, metric);
+static scan_kernel_t pick_kernel(int elem, int metric, int list_j) {
+    if (elem == ELEM_F32) {
+        if (metric == METRIC_L2SQ) return pick_list<ELEM_F32, METRIC_L2SQ>(list_j);
+        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F32, METRIC_NEG_IP>(list_j);
+        if (metric == METRIC_L1) return pick_list<ELEM_F32, METRIC_L1>(list_j);
+    } else if (elem == ELEM_F16) {
+        if (metric == METRIC_L2SQ) return pick_list<ELEM_F16, METRIC_L2SQ>(list_j);
+        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F16, METRIC_NEG_IP>(list_j);
+        if (metric == METRIC_L1) return pick_list<ELEM_F16, METRIC_L1>(list_j);
+    } else if (elem == ELEM_BIT) {
+        if (metric == METRIC_HAMMING) return pick_list<ELEM_BIT, METRIC_HAMMING>(list_j);
+        if (metric == METRIC_JACCARD) return pick_list<ELEM_BIT, METRIC_JACCARD>(list_j);
+    }
+    return nullptr;
+}
+
+cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm) {
+    scan_kernel_t k = pick_kernel(elem, metric, list_j);
     if (!k) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, SEARCH_THREADS, smem_block);
 }
 
-cudaError_t launch_scan_kernel(int elem, int metric, const GraphView &g, const SearchParams &p, int grid,
+cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView &g, const SearchParams &p, int grid,
                                size_t smem_block, cudaStream_t stream) {
-    scan_kernel_t k = pick_kernel(elem, metric);
+    scan_kernel_t k = pick_kernel(elem, metric, list_j);
     if (!k) return cudaErrorInvalidValue;
     k<<<grid, SEARCH_THREADS, smem_block, stream>>>(g, p);
     return cudaGetLastError();

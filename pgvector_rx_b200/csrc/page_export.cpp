@@ -1,0 +1,196 @@
+// page_export.cpp -- HNSW index pages -> flat graph arrays for pgvrx_index_load_graph.
+//
+// Walks the relation exactly as the reference's readers do: meta page at block 0
+// (src/types/hnsw.rs:53-74, src/index/scan.rs:126-146), element pages chained from block 1 through
+// HnswPageOpaqueData.nextblkno (hnsw.rs:18-27, hnsw_constants.rs:37), element tuples of 72 bytes +
+// varlena (hnsw.rs:110-128, scan.rs:155-228) and neighbour tuples holding (level + 2) * m TIDs with
+// layer lc at slots [(level - lc) * m, +lm) terminated by the first invalid TID
+// (hnsw.rs:150-160, scan.rs:236-283).  Element ids are assigned in page-walk order, which is the
+// order build.rs:600-702 wrote them, i.e. insertion order.  Pure host code: one sequential pass.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pgvrx_b200.h"
+
+namespace pgvrx_host {
+void set_create_error(const std::string &msg);   // capi.cu
+}
+
+namespace {
+
+const size_t BLCKSZ = 8192, PAGE_HDR = 24, ITEMID = 4, ETUP_HDR = 72, NTUP_HDR = 4, TID = 6;
+const uint32_t INVALID_BLOCK = 0xFFFFFFFFu;
+
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+struct Tid { uint32_t blk; uint16_t off; bool valid() const { return blk != INVALID_BLOCK && off != 0; } };
+inline Tid rd_tid(const uint8_t *p) { return Tid{((uint32_t)rd16(p) << 16) | rd16(p + 2), rd16(p + 4)}; }
+
+struct Item { const uint8_t *ptr; uint32_t len; bool normal; };
+
+struct Pages {
+    const uint8_t *base;
+    int64_t n;
+    const uint8_t *page(uint32_t b) const { return base + (size_t)b * BLCKSZ; }
+    uint16_t max_offset(uint32_t b) const {
+        uint16_t lower = rd16(page(b) + 12);
+        return lower <= PAGE_HDR ? 0 : (uint16_t)((lower - PAGE_HDR) / ITEMID);
+    }
+    Item item(uint32_t b, uint16_t off) const {
+        const uint8_t *p = page(b);
+        uint32_t lp = rd32(p + PAGE_HDR + (size_t)(off - 1) * ITEMID);
+        uint32_t lp_off = lp & 0x7fff, flags = (lp >> 15) & 3, len = lp >> 17;
+        return Item{p + lp_off, len, flags == 1 /* LP_NORMAL */ && len > 0 && lp_off + len <= BLCKSZ};
+    }
+    uint32_t next(uint32_t b) const { return rd32(page(b) + rd16(page(b) + 16)); }
+    bool is_hnsw(uint32_t b) const { return rd16(page(b) + 16) + 8u <= BLCKSZ && rd16(page(b) + rd16(page(b) + 16) + 6) == 0xFF90; }
+};
+
+int err(const char *msg) {
+    pgvrx_host::set_create_error(msg);
+    return PGVRX_ERR_INVALID;
+}
+
+struct Walk {
+    std::vector<uint32_t> blk;      // per element
+    std::vector<uint16_t> off;
+    std::vector<std::vector<int32_t>> id_of;   // [block][offset] -> element id or -1
+};
+
+int walk_elements(const Pages &pg, Walk &w, int64_t *n_deleted) {
+    w.id_of.assign((size_t)pg.n, {});
+    *n_deleted = 0;
+    std::vector<char> seen((size_t)pg.n, 0);
+    for (uint32_t b = 1; b != INVALID_BLOCK;) {          // HNSW_HEAD_BLKNO
+        if ((int64_t)b >= pg.n) return err("pgvector-rx: page chain points past the end of the relation");
+        if (seen[b]) return err("pgvector-rx: page chain loops");
+        seen[b] = 1;
+        if (!pg.is_hnsw(b)) return err("pgvector-rx: hnsw index is not valid");
+        uint16_t mo = pg.max_offset(b);
+        w.id_of[b].assign((size_t)mo + 1, -1);
+        for (uint16_t o = 1; o <= mo; o++) {
+            Item it = pg.item(b, o);
+            if (!it.normal || it.len < 4) continue;
+            if (it.ptr[0] != 1) continue;                 // HNSW_ELEMENT_TUPLE_TYPE
+            if (it.len < ETUP_HDR + 8) return err("pgvector-rx: truncated element tuple");
+            if (it.ptr[2] != 0) (*n_deleted)++;
+            w.id_of[b][o] = (int32_t)w.blk.size();
+            w.blk.push_back(b);
+            w.off.push_back(o);
+        }
+        b = pg.next(b);
+    }
+    return PGVRX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, pgvrx_pages_info *info) {
+    if (!pages || !info || n_pages < 2) return err("pgvector-rx: need the meta page and the head page");
+    Pages pg{(const uint8_t *)pages, n_pages};
+    memset(info, 0, sizeof *info);
+    const uint8_t *m = pg.page(0) + PAGE_HDR;
+    if (rd32(m) != 0xA953A953u) return err("pgvector-rx: hnsw index is not valid");      // scan.rs:134-137
+    if (rd32(m + 4) != 1) return err("pgvector-rx: unsupported hnsw index version");
+    info->dims = (int32_t)rd32(m + 8);
+    info->m = rd16(m + 12);
+    info->ef_construction = rd16(m + 14);
+    Tid entry{rd32(m + 16), rd16(m + 20)};
+    info->entry_level = (int16_t)rd16(m + 22);
+    Walk w;
+    int rc = walk_elements(pg, w, &info->n_deleted);
+    if (rc) return rc;
+    info->n_elements = (int64_t)w.blk.size();
+    info->entry = -1;
+    if (entry.blk != INVALID_BLOCK) {
+        if ((int64_t)entry.blk >= n_pages || entry.off >= w.id_of[entry.blk].size() || w.id_of[entry.blk][entry.off] < 0)
+            return err("pgvector-rx: entry point does not reference an element tuple");
+        info->entry = w.id_of[entry.blk][entry.off];
+    }
+    size_t want_row = pgvrx_row_bytes(elem_type, info->dims);
+    for (size_t i = 0; i < w.blk.size(); i++) {
+        Item it = pg.item(w.blk[i], w.off[i]);
+        info->n_upper_rows += it.ptr[1];
+        for (int t = 0; t < PGVRX_HEAPTIDS; t++) {
+            if (!rd_tid(it.ptr + 4 + t * TID).valid()) break;
+            info->n_heap_tids++;
+        }
+        uint32_t vl = rd32(it.ptr + ETUP_HDR);
+        if ((vl & 3u) != 0) return err("pgvector-rx: element value is not a plain 4-byte-header varlena");
+        size_t vsize = vl >> 2;
+        if (vsize != want_row + 8 || ETUP_HDR + vsize > it.len) return err("pgvector-rx: element value size does not match the index dimensions");
+    }
+    return PGVRX_OK;
+}
+
+int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, void *rows, uint8_t *level, int32_t *adj0,
+                       int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids, uint8_t *heap_tid_counts) {
+    pgvrx_pages_info info;
+    int rc = pgvrx_pages_inspect(pages, n_pages, elem_type, &info);
+    if (rc) return rc;
+    if (info.n_deleted > 0) {
+        pgvrx_host::set_create_error("pgvector-rx: index holds deleted elements (vacuum in progress); not supported by the exporter yet");
+        return PGVRX_ERR_UNSUPPORTED;
+    }
+    if (info.n_elements > 0 && (!rows || !level || !adj0 || !upper_base || (info.n_upper_rows > 0 && !adj_up)))
+        return err("pgvector-rx: null output array");
+    Pages pg{(const uint8_t *)pages, n_pages};
+    Walk w;
+    int64_t nd;
+    rc = walk_elements(pg, w, &nd);
+    if (rc) return rc;
+    const int m = info.m;
+    const size_t row_bytes = pgvrx_row_bytes(elem_type, info.dims);
+    int64_t up = 0;
+    for (size_t i = 0; i < w.blk.size(); i++) {
+        Item it = pg.item(w.blk[i], w.off[i]);
+        const int lv = it.ptr[1];
+        const uint8_t version = it.ptr[3];
+        level[i] = (uint8_t)lv;
+        memcpy((uint8_t *)rows + i * row_bytes, it.ptr + ETUP_HDR + 8, row_bytes);
+        int nh = 0;
+        for (int t = 0; t < PGVRX_HEAPTIDS; t++) {                    // scan.rs:203-209: stop at the first invalid
+            Tid h = rd_tid(it.ptr + 4 + t * TID);
+            if (!h.valid()) break;
+            if (heap_tids) heap_tids[i * PGVRX_HEAPTIDS + nh] = ((uint64_t)h.blk << 16) | h.off;
+            nh++;
+        }
+        if (heap_tids) for (int t = nh; t < PGVRX_HEAPTIDS; t++) heap_tids[i * PGVRX_HEAPTIDS + t] = ~0ull;
+        if (heap_tid_counts) heap_tid_counts[i] = (uint8_t)nh;
+        upper_base[i] = lv > 0 ? (int32_t)up : -1;
+        for (int j = 0; j < 2 * m; j++) adj0[i * 2 * m + j] = -1;
+        for (int l = 1; l <= lv; l++) for (int j = 0; j < m; j++) adj_up[(size_t)(up + l - 1) * m + j] = -1;
+
+        Tid nt = rd_tid(it.ptr + 4 + PGVRX_HEAPTIDS * TID);
+        bool ok = nt.valid() && (int64_t)nt.blk < n_pages && nt.off <= pg.max_offset(nt.blk);
+        Item ni{nullptr, 0, false};
+        if (ok) ni = pg.item(nt.blk, nt.off);
+        // scan.rs:254-265: wrong type / version / count => the element has no usable lists
+        ok = ok && ni.normal && ni.len >= NTUP_HDR && ni.ptr[0] == 2 && ni.ptr[1] == version &&
+             rd16(ni.ptr + 2) == (lv + 2) * m && NTUP_HDR + (size_t)(lv + 2) * m * TID <= ni.len;
+        if (ok) {
+            for (int lc = lv; lc >= 0; lc--) {
+                const int lm = lc == 0 ? 2 * m : m;
+                const size_t start = (size_t)(lv - lc) * m;            // scan.rs:268
+                int32_t *dst = lc == 0 ? adj0 + i * 2 * m : adj_up + (size_t)(up + lc - 1) * m;
+                for (int j = 0; j < lm; j++) {
+                    Tid t = rd_tid(ni.ptr + NTUP_HDR + (start + j) * TID);
+                    if (!t.valid()) break;                             // scan.rs:275-277
+                    if ((int64_t)t.blk >= n_pages || t.off >= w.id_of[t.blk].size() || w.id_of[t.blk][t.off] < 0)
+                        return err("pgvector-rx: neighbour TID does not reference an element tuple");
+                    dst[j] = w.id_of[t.blk][t.off];
+                }
+            }
+        }
+        up += lv;
+    }
+    return PGVRX_OK;
+}
+
+}  // extern "C"

@@ -71,6 +71,7 @@ def lib():
         "orc_search_batch": (i32, [vp, vp, i64, i32, i32, vp, vp, vp, vp, i32]),
         "orc_scan_stream": (i64, [vp, vp, i32, i32, i64, i64, vp, vp, vp, vp]),
         "orc_flat_topk": (i32, [i32, i32, i32, vp, i64, vp, i64, i32, vp, vp, i32]),
+        "orc_write_pages": (i64, [vp, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -197,6 +198,13 @@ class Oracle:
                                 _p(np.ascontiguousarray(g["adj0"], np.int32)),
                                 _p(np.ascontiguousarray(g["upper_base"], np.int32)), _p(adj_up),
                                 int(g["entry"]))
+
+    def write_pages(self):
+        """The index relation as the reference's flush phase lays it out (8 KiB pages)."""
+        n = self.L.orc_write_pages(self.h, None, 0)
+        buf = np.zeros(n * 8192, np.uint8)
+        assert self.L.orc_write_pages(self.h, _p(buf), n) == n
+        return buf
 
     # ---- a1 / a3 -----------------------------------------------------------------------
     def search_layer(self, query, ep_ids, ep_dists, ef, layer):

@@ -1,0 +1,86 @@
+"""a19: the product's page exporter against pages written by the oracle exactly as the reference's
+flush phase does (build.rs:545-821).  No PostgreSQL exists in this image, so the fixture is
+synthesised; the exporter and the writer are independent implementations of the same layout."""
+import struct
+
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+import pgvector_rx_b200 as P
+from helpers import make_rows, oracle_index
+from pgvector_rx_b200 import datasets as D
+
+
+def roundtrip(opclass, kind, n, dim, m, efc, levels=None, seed=5):
+    elem = P.OPCLASSES[opclass][0]
+    rows = make_rows(kind, n, dim, seed)
+    o = oracle_index(opclass, dim, rows, m=m, efc=efc, levels=levels)
+    pages = o.write_pages()
+    g = P.export_pages(pages, elem)
+    want = o.export_graph()
+    assert g["n"] == want["n"] and g["m"] == m and g["dims"] == dim and g["ef_construction"] == efc
+    assert g["entry"] == want["entry"]
+    if want["n"]:
+        assert g["entry_level"] == want["level"][want["entry"]]
+    for k in ("level", "adj0", "upper_base", "adj_up"):
+        assert np.array_equal(g[k], want[k]), k
+    assert np.array_equal(g["rows"].view(np.uint8), want["rows"].view(np.uint8))
+    for i in range(want["n"]):
+        t = o.heap_tids(i)
+        assert g["heap_tid_counts"][i] == len(t)
+        got = [((int(v) >> 16), (int(v) & 0xffff) - 1) for v in g["heap_tids"][i, :len(t)]]
+        assert got == [(int(x) >> 16, int(x) & 0xffff) for x in t]
+    return pages, g
+
+
+@pytest.mark.parametrize("opclass,kind,dim", [("vector_l2_ops", "f32", 128), ("vector_cosine_ops", "f32", 7),
+                                              ("halfvec_ip_ops", "f16", 33), ("bit_hamming_ops", "bit", 52),
+                                              ("bit_jaccard_ops", "bit", 1024)])
+def test_export_matches_builder(opclass, kind, dim):
+    roundtrip(opclass, kind, 700, dim, 8, 32)
+
+
+def test_export_page_layout_edges():
+    # many elements per page / neighbour tuple forced onto the next page (combined > HNSW_MAX_SIZE,
+    # build.rs:653-657) / very high levels
+    roundtrip("vector_l2_ops", "f32", 300, 3, 4, 16)
+    pages, g = roundtrip("vector_l2_ops", "f32", 40, 2000, 16, 64)
+    assert len(pages) // 8192 >= 2 * 40
+    lv = np.zeros(60, np.int32)
+    lv[[3, 17, 40]] = [9, 40, 2]
+    roundtrip("vector_l2_ops", "f32", 60, 16, 32, 64, levels=lv)
+
+
+def test_export_duplicates_and_empty():
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 3)
+    o.build(np.tile(np.array([1, 2, 3], np.float32), (25, 1)), np.zeros(25, np.int32))
+    g = P.export_pages(o.write_pages(), P.ELEM_F32)
+    assert g["n"] == 3 and sorted(g["heap_tid_counts"].tolist()) == [5, 10, 10]
+    e = O.Oracle(O.ELEM_F32, O.L2SQ, 3)
+    g = P.export_pages(e.write_pages(), P.ELEM_F32)
+    assert g["n"] == 0 and g["entry"] == -1                     # meta + head page only (build.rs:580-589)
+
+
+def test_export_rejects_corrupt_relations():
+    o = oracle_index("vector_l2_ops", 8, make_rows("f32", 50, 8, 1), m=4, efc=16)
+    pages = o.write_pages()
+    bad = pages.copy()
+    bad[24:28] = 0                                               # magic number
+    with pytest.raises(P.PgvrxError) as e:
+        P.export_pages(bad, P.ELEM_F32)
+    assert "hnsw index is not valid" in str(e.value)            # scan.rs:134-137
+    with pytest.raises(P.PgvrxError):
+        P.export_pages(pages, P.ELEM_F16)                       # value size does not match the type
+    with pytest.raises(P.PgvrxError):
+        P.export_pages(pages[:8192], P.ELEM_F32)
+    # stale neighbour tuple (version mismatch) => that element simply has no lists (scan.rs:262)
+    g0 = P.export_pages(pages, P.ELEM_F32)
+    stale = pages.copy()
+    page1 = stale[8192:16384]
+    lp = struct.unpack_from("<I", page1, 24 + 4)[0]              # item 2 of the head page = first neighbour tuple
+    off = lp & 0x7fff
+    assert page1[off] == 2
+    page1[off + 1] = 7
+    g1 = P.export_pages(stale, P.ELEM_F32)
+    assert (g1["adj0"][0] == -1).all() and np.array_equal(g1["adj0"][1:], g0["adj0"][1:])

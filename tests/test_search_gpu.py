@@ -12,7 +12,7 @@ from helpers import assert_same_results, gpu_index, make_rows, oracle_index
 pytestmark = pytest.mark.gpu
 
 
-def run_case(opclass, kind, n, dim, nq, m=16, efc=64, efs=(40,), k=10, seed=11):
+def run_case(opclass, kind, n, dim, nq, m=16, efc=64, efs=(40,), k=10, seed=11, allow_retry=False):
     elem, metric, norm = P.OPCLASSES[opclass]
     rows = make_rows(kind, n, dim, seed)
     o = oracle_index(opclass, dim, rows, m=m, efc=efc)
@@ -28,7 +28,9 @@ def run_case(opclass, kind, n, dim, nq, m=16, efc=64, efs=(40,), k=10, seed=11):
         # same traversal => same work counters (these feed the roofline's algorithmic bytes)
         for key in ("n_dist", "n_expand0", "n_expand_upper", "n_visited"):
             assert st[key] == ctr[key], (key, st[key], ctr[key])
-        assert st["n_retried"] == 0
+        # tie-free data never needs the retry pass; tie-heavy integer distances may overflow the
+        # retained-tie slots and are then re-run (exactly) with the large shared-memory list
+        assert st["n_retried"] == 0 or allow_retry
     ix.close()
 
 
@@ -50,7 +52,7 @@ def test_halfvec_metrics(opclass):
 @pytest.mark.parametrize("opclass,dim", [("bit_hamming_ops", 1024), ("bit_jaccard_ops", 520), ("bit_hamming_ops", 52)])
 def test_bit_metrics_tie_heavy(opclass, dim):
     # integer distances tie constantly; both sides break ties by element id
-    run_case(opclass, "bit", 3000, dim, 300, efs=(40, 10))
+    run_case(opclass, "bit", 3000, dim, 300, efs=(40, 10), allow_retry=True)
 
 
 @pytest.mark.parametrize("dim", [1, 2, 3, 5, 17, 130])
