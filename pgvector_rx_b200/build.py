@@ -32,14 +32,16 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, timing=False):
+def build(force=False, verbose=False, timing=False, cpasync_gather=False):
     """timing=True builds libpgvrx_b200_timing.so with per-phase clock64() instrumentation
     (a profiling aid selected with PGVRX_LIB=...; never the shipped library)."""
     out = LIB.replace(".so", "_timing.so") if timing else LIB
-    if not force and not timing and not is_stale():
+    if cpasync_gather:
+        out = out.replace(".so", "_cpasync.so")
+    if not force and not timing and not cpasync_gather and not is_stale():
         return LIB
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          (["-DPGVRX_PHASE_TIMING"] if timing else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
+          (["-DPGVRX_PHASE_TIMING"] if timing else []) + (["-DPGVRX_GATHER_CPASYNC"] if cpasync_gather else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -49,4 +51,5 @@ def build(force=False, verbose=False, timing=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timing="--timing" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timing="--timing" in sys.argv,
+                cpasync_gather="--cpasync-gather" in sys.argv))

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -132,7 +133,10 @@ struct ScanConfig {
 // tail_cap < 0: pick the register-resident list when ef is small enough (capacity 32*J - 1 with at
 // least 16 retained-tie slots), else the shared-memory list with 32 tie slots
 int make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int64_t nq, int max_grid, ScanConfig *out) {
-    const uint32_t STAGE_BUDGET = 17 * 1024;
+    // bytes of shared memory per warp for staged rows; 32 rows of a 128-d fp32 vector fit in 17 KiB.
+    // PGVRX_STAGE_KB overrides it for tuning experiments (occupancy vs. rows per TMA round).
+    uint32_t STAGE_BUDGET = 17 * 1024;
+    if (const char *e = getenv("PGVRX_STAGE_KB")) { int kb = atoi(e); if (kb >= 1 && kb <= 48) STAGE_BUDGET = (uint32_t)kb * 1024; }
     ScanConfig c;
     c.L.ef = ef;
     c.L.list_j = 0;

@@ -79,6 +79,18 @@ __device__ __forceinline__ void tma_row_g2s(void *dst, const void *src, uint32_t
         : "memory");
 }
 
+// Ampere-style async copy, 16 B per lane (SASS LDGSTS.E.BYPASS.128): kept as a build-time alternative
+// (-DPGVRX_GATHER_CPASYNC) for the row gather.  Measured on B200 it is ~4x SLOWER than per-row TMA bulk
+// copies for this access pattern (12 warps x 25 rows in flight per SM queue up in L1TEX, which TMA
+// bypasses): 7990 vs 2060 cycles per expansion, profiles/r1_notes.md.
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // keys: (order-preserving f32 bits) << 32 | id << 1 | expanded
 // ------------------------------------------------------------------------------------------
@@ -282,21 +294,19 @@ struct RegList {
         }
         c.len += 1;
         if (c.len >= c.ef) {
+            const uint32_t old_f = c.f_ord;
             c.f_ord = key_ord(get(c, c.ef - 1));
             if (c.len > c.ef) {
-                // keep only evicted entries that still tie with the furthest distance of W
-                int keep = 0;
-#pragma unroll
-                for (int j = 0; j < J; j++) {
-                    const int gi = c.lane * J + j;
-                    keep += gi >= c.ef && k[j] != KEY_NONE && key_ord(k[j]) == c.f_ord;
+                // Entries behind W all tie with the OLD furthest distance (invariant).  The element just
+                // pushed out of W has that distance too, so: if W's furthest distance is unchanged they all
+                // stay (the reference would still expand them, stop rule is strict `>`); otherwise none can.
+                if (c.f_ord == old_f) {
+                    if (c.len > c.cap) { c.len = c.cap; c.status |= ST_TIE_OVERFLOW; }
+                } else {
+                    c.len = c.ef;
                 }
-                keep = __reduce_add_sync(FULL, keep);
-                int nl = c.ef + keep;
-                if (nl > c.cap) { nl = c.cap; c.status |= ST_TIE_OVERFLOW; }
 #pragma unroll
-                for (int j = 0; j < J; j++) if (c.lane * J + j >= nl) k[j] = KEY_NONE;
-                c.len = nl;
+                for (int j = 0; j < J; j++) if (c.lane * J + j >= c.len) k[j] = KEY_NONE;
             }
         }
     }
@@ -398,6 +408,45 @@ struct SmemList {
     }
 };
 
+// Gather nrow vector rows (ids in c.nbr[s .. s+nrow)) into the staging area and wait for them.
+// Row r lands at c.stage + r * stage_stride.
+__device__ __forceinline__ void gather_rows(WarpCtx &c, const GraphView &g, int s, int nrow) {
+    const int lane = c.lane;
+#ifndef PGVRX_GATHER_CPASYNC
+    // one TMA bulk copy (UBLKCP) per row, issued by the lane that owns the row, one mbarrier phase
+    int32_t my = lane < nrow ? c.nbr[s + lane] : -1;
+    if (lane == 0) mbar_arrive_expect_tx(c.mbar, (uint32_t)nrow * g.row_stride);
+    __syncwarp();
+    if (lane < nrow)
+        tma_row_g2s(c.stage + (size_t)lane * c.stage_stride, g.vectors + (size_t)my * g.row_stride, g.row_stride,
+                    c.mbar, c.policy);
+    mbar_wait(c.mbar, c.phase);
+    c.phase ^= 1u;
+#else
+    const int nvec = c.nvec;
+    if (nvec >= 32) {
+        // wide rows: the whole warp copies one row per step, 512 contiguous bytes per instruction
+        for (int r = 0; r < nrow; r++) {
+            const uint8_t *src = g.vectors + (size_t)c.nbr[s + r] * g.row_stride;
+            uint8_t *dst = c.stage + (size_t)r * c.stage_stride;
+            for (int v = lane; v < nvec; v += 32) cp_async16(dst + v * 16, src + v * 16, c.policy);
+        }
+    } else {
+        // narrow rows (e.g. 1024-bit vectors = 8 x 16 B): several rows per instruction
+        const int rpi = 32 / nvec;                    // rows per instruction
+        const int lr = lane / nvec, lc = lane - lr * nvec;
+        for (int r0 = 0; r0 < nrow; r0 += rpi) {
+            const int r = r0 + lr;
+            if (lr < rpi && r < nrow)
+                cp_async16(c.stage + (size_t)r * c.stage_stride + lc * 16,
+                           g.vectors + (size_t)c.nbr[s + r] * g.row_stride + lc * 16, c.policy);
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+#endif
+}
+
 // search_layer (graph/mod.rs:161-255 == scan.rs:302-448 without the iterative-scan bookkeeping).
 // Precondition: S[0, len) holds the entry points (unexpanded), their ids are in the visited set.
 template <int ELEM, int METRIC, class LIST>
@@ -442,13 +491,7 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             for (int s = 0; s < cnt; s += c.R) {
                 int nrow = min(c.R, cnt - s);
                 int32_t my = lane < nrow ? c.nbr[s + lane] : -1;
-                if (lane == 0) mbar_arrive_expect_tx(c.mbar, (uint32_t)nrow * g.row_stride);
-                __syncwarp();
-                if (lane < nrow)
-                    tma_row_g2s(c.stage + (size_t)lane * c.stage_stride,
-                                g.vectors + (size_t)my * g.row_stride, g.row_stride, c.mbar, c.policy);
-                mbar_wait(c.mbar, c.phase);
-                c.phase ^= 1u;
+                gather_rows(c, g, s, nrow);
                 PH_TICK(c, 2);
                 float d = 0.0f;
                 if (lane < nrow) d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)lane * c.stage_stride, c.nvec);

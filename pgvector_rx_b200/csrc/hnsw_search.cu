@@ -97,11 +97,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
         int out_n = 0;
         if (g.entry >= 0) {      // empty index => no rows (scan.rs:470-472)
             // ---- distance to the entry point (scan.rs:475-486) ----
-            if (lane == 0) mbar_arrive_expect_tx(c.mbar, g.row_stride);
+            if (lane == 0) c.nbr[0] = g.entry;
             __syncwarp();
-            if (lane == 0) tma_row_g2s(c.stage, g.vectors + (size_t)g.entry * g.row_stride, g.row_stride, c.mbar, c.policy);
-            mbar_wait(c.mbar, c.phase);
-            c.phase ^= 1u;
+            gather_rows(c, g, 0, 1);
             float d0 = 0.0f;
             if (lane == 0) d0 = row_distance<ELEM, METRIC>(c.qsm, c.stage, c.nvec);
             d0 = __shfl_sync(FULL, d0, 0);
