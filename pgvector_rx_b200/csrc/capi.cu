@@ -177,7 +177,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
 
     const int m = ix->desc.m;
     ScanConfig main_cfg, retry_cfg;
-    uint32_t vis_main = pow2_at_least(std::max<uint64_t>(1024, (uint64_t)ef * 2 * m * 2));
+    uint32_t vis_main = pow2_at_least(std::max<uint64_t>(1024, (uint64_t)ef * 2 * m * 4));   // <= ~25 % load
     int rc = make_config(ix, ef, -1, vis_main, nq, 0, &main_cfg);
     if (rc) return rc;
     uint32_t vis_retry = pow2_at_least(std::min<uint64_t>((uint64_t)vis_main * 16, std::max<uint64_t>(1024, (uint64_t)ix->n * 2)));

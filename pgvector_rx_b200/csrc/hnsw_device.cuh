@@ -115,9 +115,14 @@ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return ((uint32_t)k) >>
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t vis_hash(uint32_t id) { return id * 0x9E3779B1u; }
 
-// returns true when id was not in the set (and is now)
-__device__ __forceinline__ bool vis_insert(uint32_t *tab, uint32_t mask, uint32_t id) {
-    uint32_t h = (vis_hash(id) >> 7) & mask;
+// Layout: linear probing over the whole table, scanned in 16-byte buckets of 4 slots.  An id lives in
+// the first slot that was free at/after its home slot 4*bucket(id) when it was inserted; slots never
+// become free again within a search, so "the home bucket still has a free slot and does not hold the
+// id" proves absence with ONE 128-bit load.
+__device__ __forceinline__ uint32_t vis_home(uint32_t id, uint32_t mask) { return ((vis_hash(id) >> 7) & mask) & ~3u; }
+
+// synchronous test-and-set starting at slot `h`: returns true when id was not in the set (and is now)
+__device__ __forceinline__ bool vis_insert_from(uint32_t *tab, uint32_t mask, uint32_t h, uint32_t id) {
     for (uint32_t probes = 0; probes <= mask; probes++) {
         uint32_t old = atomicCAS(tab + h, VIS_EMPTY, id);
         if (old == VIS_EMPTY) return true;
@@ -125,6 +130,9 @@ __device__ __forceinline__ bool vis_insert(uint32_t *tab, uint32_t mask, uint32_
         h = (h + 1) & mask;
     }
     return false;  // unreachable: the caller keeps the load factor <= 3/4
+}
+__device__ __forceinline__ bool vis_insert(uint32_t *tab, uint32_t mask, uint32_t id) {
+    return vis_insert_from(tab, mask, vis_home(id, mask), id);
 }
 __device__ __forceinline__ void vis_clear(uint32_t *tab, uint32_t entries, int lane) {
     uint4 e = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
@@ -469,51 +477,67 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             c.n_expu++;
         }
         for (int base = 0; base < lm; base += 32) {
-            int j = base + lane;
-            int32_t nb = j < lm ? __ldg(row + j) : -1;
-            bool valid = nb >= 0;                       // lists are dense prefixes (scan.rs:273-279)
-            if (!__any_sync(FULL, valid)) break;
+            const int j = base + lane;
+            const int32_t nb = j < lm ? __ldg(row + j) : -1;
+            const bool valid = nb >= 0;                 // lists are dense prefixes (scan.rs:273-279)
+            const uint32_t vm = __ballot_sync(FULL, valid);
+            if (!vm) break;
+            const int cnt = __popc(vm);                 // valid lanes are exactly 0 .. cnt-1
             PH_TICK(c, 0);
-            bool fresh = valid && vis_insert(c.vis, vis_mask, (uint32_t)nb);   // visited BEFORE the level test
-            uint32_t fm = __ballot_sync(FULL, fresh);
-            vis_count += __popc(fm);
-            c.n_vis += __popc(fm);
-            bool pass = fresh;
-            if (layer > 0 && fresh) pass = __ldg(g.level + nb) >= layer;        // graph/mod.rs:214, scan.rs:410
-            uint32_t pm = __ballot_sync(FULL, pass);
-            int cnt = __popc(pm);
-            if (vis_count > vis_limit) { c.status |= ST_VIS_OVERFLOW; return; }
-            if (cnt == 0) continue;
-            int rank = __popc(pm & ((1u << lane) - 1u));
-            if (pass) c.nbr[rank] = nb;
+            // (1) visited test-and-set: the first probe is ISSUED here and only consumed after the distances,
+            //     so its L2 round trip overlaps the row gather instead of preceding it.  Rows of neighbours
+            //     that turn out to be visited already are fetched speculatively and ignored.
+            const uint32_t h = vis_home((uint32_t)nb, vis_mask);
+            uint4 bk = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
+            if (valid) bk = __ldcg(reinterpret_cast<const uint4 *>(c.vis + h));   // L2 (the table is written with atomics)
+            int lvl = 255;
+            if (layer > 0 && valid) lvl = __ldg(g.level + nb);
+            if (valid) c.nbr[lane] = nb;
             __syncwarp();
-            PH_TICK(c, 1);
+            // (2) gather + one distance per lane (lane r <-> neighbour r of this chunk)
+            float d = 0.0f;
             for (int s = 0; s < cnt; s += c.R) {
-                int nrow = min(c.R, cnt - s);
-                int32_t my = lane < nrow ? c.nbr[s + lane] : -1;
+                const int nrow = min(c.R, cnt - s);
                 gather_rows(c, g, s, nrow);
                 PH_TICK(c, 2);
-                float d = 0.0f;
-                if (lane < nrow) d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)lane * c.stage_stride, c.nvec);
-                c.n_dist += nrow;
-                __syncwarp();
-                PH_TICK(c, 3);
-                // accept in neighbour order (graph/mod.rs:226-242): the threshold only tightens and W only
-                // fills up, so lanes failing against the CURRENT threshold can never be accepted later
-                uint32_t dord = f32_ord(d);
-                bool maybe = lane < nrow && (c.len < c.ef || dord < c.f_ord);
-                uint32_t am = __ballot_sync(FULL, maybe);
-                while (am) {
-                    int r = __ffs(am) - 1;
-                    am &= am - 1;
-                    float dr = __shfl_sync(FULL, d, r);
-                    int32_t idr = __shfl_sync(FULL, my, r);
-                    bool always_add = min(c.len, c.ef) < c.ef;
-                    if (always_add || f32_ord(dr) < c.f_ord) S.insert(c, make_key(dr, (uint32_t)idr));
-                }
+                if (lane >= s && lane < s + nrow)
+                    d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
                 __syncwarp();   // all lanes done with the staging rows before they are overwritten
-                PH_TICK(c, 4);
+                PH_TICK(c, 3);
             }
+            // (3) resolve the visited probes (visited BEFORE the level test, graph/mod.rs:206-216)
+            const uint32_t id = (uint32_t)nb;
+            const bool present = bk.x == id || bk.y == id || bk.z == id || bk.w == id;
+            const int free_slot = bk.x == VIS_EMPTY ? 0 : bk.y == VIS_EMPTY ? 1 : bk.z == VIS_EMPTY ? 2 : bk.w == VIS_EMPTY ? 3 : -1;
+            bool fresh = valid && !present && free_slot >= 0;
+            // claim the free slot; the result only matters when another lane of this warp claimed the same
+            // slot in this round (different id), which is checked after the accept loop
+            uint32_t claim_old = VIS_EMPTY;
+            if (fresh) claim_old = atomicCAS(c.vis + h + free_slot, VIS_EMPTY, id);
+            // home bucket full of other ids (rare at <= 40 % load): continue probing synchronously
+            if (valid && !present && free_slot < 0) fresh = vis_insert_from(c.vis, vis_mask, (h + 4) & vis_mask, id);
+            const uint32_t fm = __ballot_sync(FULL, fresh);
+            vis_count += __popc(fm);
+            c.n_vis += __popc(fm);
+            if (vis_count > vis_limit) { c.status |= ST_VIS_OVERFLOW; return; }
+            const bool pass = fresh && lvl >= layer;                     // graph/mod.rs:214, scan.rs:410
+            c.n_dist += __popc(__ballot_sync(FULL, pass));
+            PH_TICK(c, 1);
+            // (4) accept in neighbour order (graph/mod.rs:226-242): the threshold only tightens and W only
+            //     fills up, so lanes failing against the CURRENT threshold can never be accepted later
+            const uint32_t dord = f32_ord(d);
+            uint32_t am = __ballot_sync(FULL, pass && (c.len < c.ef || dord < c.f_ord));
+            while (am) {
+                const int r = __ffs(am) - 1;
+                am &= am - 1;
+                const float dr = __shfl_sync(FULL, d, r);
+                const int32_t idr = __shfl_sync(FULL, nb, r);
+                const bool always_add = c.len < c.ef;
+                if (always_add || f32_ord(dr) < c.f_ord) S.insert(c, make_key(dr, (uint32_t)idr));
+            }
+            // lost a same-slot race inside the warp: the id is new (decided above) but still has to be stored
+            if (fresh && claim_old != VIS_EMPTY) vis_insert_from(c.vis, vis_mask, (h + free_slot + 1) & vis_mask, id);
+            PH_TICK(c, 4);
         }
     }
 }
