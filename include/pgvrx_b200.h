@@ -151,6 +151,41 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
                        int32_t *adj0, int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids,
                        uint8_t *heap_tid_counts);
 
+/* ---- build: the ambuild insert loop (src/index/build.rs:400-535) ------------------------------- */
+typedef struct {
+    uint64_t n_rounds;        /* GPU search rounds                                               */
+    uint64_t n_searched;      /* element searches run on the GPU (>= elements: conflicts re-run)  */
+    uint64_t n_conflicts;     /* speculative results discarded because an earlier commit of the
+                                 same round modified a list the search had read                   */
+    uint64_t n_duplicates;    /* rows merged into an existing element's heap TIDs (build.rs:482-512) */
+    uint64_t n_big_retries;   /* searches re-run alone with large scratch                         */
+    uint64_t n_dist, n_expand0, n_expand_upper;   /* GPU work of the committed searches           */
+    uint64_t n_pair;          /* pairwise distances of select_neighbors on the host (graph/mod.rs:326) */
+    double   gpu_ms;          /* wall time spent in upload + kernel + download                     */
+    double   total_ms;
+    int32_t  host_threads;
+} pgvrx_build_stats;
+
+/* Insert n_rows rows in order, exactly as build_callback does for each heap tuple (NULL rows and,
+ * for cosine opclasses, zero-norm rows must be dropped and the rest normalised by the caller, as
+ * build.rs:411-438 does before the insert).  levels[i] is the level of row i (the reference draws it
+ * from an unseeded RNG, build.rs:373-377; use pgvrx_level_from_uniform).  heap_tids[i] (optional,
+ * default i) is recorded per element, up to 10 per element for byte-identical duplicates.
+ * The search_layer calls of find_element_neighbors (graph/mod.rs:386,407) run on the GPU in
+ * speculative batches; select_neighbors, update_neighbor_connections, the duplicate rule and the
+ * entry-point rule run on the host in the reference's order, and a batched result is only used when
+ * it provably equals the sequential one -- the adjacency is identical to a sequential build.
+ * May be called again to append more rows.  The graph is resident and searchable afterwards. */
+int pgvrx_index_build(pgvrx_index *idx, const void *rows, int64_t n_rows, const int32_t *levels,
+                      const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats);
+int pgvrx_index_graph_info(const pgvrx_index *idx, int64_t *n, int64_t *n_upper_rows, int64_t *entry,
+                           int32_t *entry_level);
+/* copies the built graph out (any pointer may be NULL); shapes as in pgvrx_index_load_graph,
+ * heap_tids n x 10 (~0 when absent), heap_tid_counts n */
+int pgvrx_index_export_graph(pgvrx_index *idx, void *rows, uint8_t *level, int32_t *adj0,
+                             int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids,
+                             uint8_t *heap_tid_counts);
+
 /* ---- scan: get_scan_items, iterative_scan = off (scan.rs:458-530) ------------------------------ */
 /* For each of nq queries (raw element data, row_bytes apart, already normalised for cosine):
  * runs the greedy descent (ef = 1 per upper layer, fresh visited set per layer) and the layer-0

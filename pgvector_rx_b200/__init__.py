@@ -38,7 +38,8 @@ EXPORTS = [
     "pgvrx_abi_version", "pgvrx_last_error", "pgvrx_device_count", "pgvrx_normalize",
     "pgvrx_level_from_uniform", "pgvrx_max_level", "pgvrx_row_bytes", "pgvrx_index_create",
     "pgvrx_index_destroy", "pgvrx_index_load_graph", "pgvrx_index_size", "pgvrx_search_batch",
-    "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export",
+    "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export", "pgvrx_index_build",
+    "pgvrx_index_graph_info", "pgvrx_index_export_graph",
 ]
 
 
@@ -57,6 +58,16 @@ class PagesInfo(C.Structure):
     _fields_ = [("n_elements", C.c_int64), ("n_upper_rows", C.c_int64), ("n_heap_tids", C.c_int64),
                 ("n_deleted", C.c_int64), ("entry", C.c_int64), ("entry_level", C.c_int32), ("dims", C.c_int32),
                 ("m", C.c_int32), ("ef_construction", C.c_int32)]
+
+
+class BuildStats(C.Structure):
+    _fields_ = [("n_rounds", C.c_uint64), ("n_searched", C.c_uint64), ("n_conflicts", C.c_uint64),
+                ("n_duplicates", C.c_uint64), ("n_big_retries", C.c_uint64), ("n_dist", C.c_uint64),
+                ("n_expand0", C.c_uint64), ("n_expand_upper", C.c_uint64), ("n_pair", C.c_uint64),
+                ("gpu_ms", C.c_double), ("total_ms", C.c_double), ("host_threads", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class SearchStats(C.Structure):
@@ -94,6 +105,9 @@ def lib():
         "pgvrx_index_size": (i64, [vp]),
         "pgvrx_pages_inspect": (C.c_int, [vp, i64, i32, C.POINTER(PagesInfo)]),
         "pgvrx_pages_export": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "pgvrx_index_build": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
+        "pgvrx_index_graph_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
+        "pgvrx_index_export_graph": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_search_batch": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats)]),
         "pgvrx_search_batch_device": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats), vp]),
     }
@@ -207,6 +221,49 @@ class HnswIndex:
         adj_up = np.ascontiguousarray(adj_up, np.int32).reshape(-1, self.m)
         self._check(self.L.pgvrx_index_load_graph(self.h, _p(rows), len(rows), _p(level), _p(adj0), _p(upper_base),
                                                   _p(adj_up) if len(adj_up) else None, len(adj_up), int(entry)))
+
+    def build(self, rows, levels, heap_tids=None, host_threads=0):
+        """CREATE INDEX: insert rows in order (ambuild, build.rs:400-535).  Rows of cosine opclasses are
+        normalised here and zero-norm rows dropped, as build_callback does.  Returns build statistics."""
+        rows = _rows(self.elem, self.dim, rows)
+        levels = np.ascontiguousarray(levels, np.int32)
+        tids = None if heap_tids is None else np.ascontiguousarray(heap_tids, np.uint64)
+        if self.normalized:
+            keep, out = [], []
+            for i, r in enumerate(rows):
+                norm, u = normalize(self.elem, self.dim, r)
+                if norm == 0.0:
+                    continue
+                keep.append(i)
+                out.append(u)
+            rows = np.stack(out) if out else rows[:0]
+            levels = levels[keep]
+            tids = np.asarray(keep, np.uint64) if tids is None else tids[keep]
+        st = BuildStats()
+        self._check(self.L.pgvrx_index_build(self.h, _p(rows), len(rows), _p(levels), _p(tids), host_threads, C.byref(st)))
+        return st.as_dict()
+
+    def graph_info(self):
+        n, nu, e, el = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        self._check(self.L.pgvrx_index_graph_info(self.h, C.byref(n), C.byref(nu), C.byref(e), C.byref(el)))
+        return dict(n=n.value, n_upper_rows=nu.value, entry=e.value, entry_level=el.value)
+
+    def export_graph(self):
+        gi = self.graph_info()
+        n, m = gi["n"], self.m
+        rb = self.L.pgvrx_row_bytes(self.elem, self.dim)
+        rows = np.zeros((n, rb), np.uint8)
+        level = np.zeros(n, np.uint8)
+        adj0 = np.zeros((n, 2 * m), np.int32)
+        upper_base = np.zeros(n, np.int32)
+        adj_up = np.zeros((max(gi["n_upper_rows"], 1), m), np.int32)
+        tids = np.zeros((n, 10), np.uint64)
+        cnt = np.zeros(n, np.uint8)
+        self._check(self.L.pgvrx_index_export_graph(self.h, _p(rows), _p(level), _p(adj0), _p(upper_base), _p(adj_up),
+                                                    _p(tids), _p(cnt)))
+        return dict(rows=rows.view(_elem_dtype(self.elem)).reshape(n, rb // np.dtype(_elem_dtype(self.elem)).itemsize),
+                    level=level, adj0=adj0, upper_base=upper_base, adj_up=adj_up[:gi["n_upper_rows"]],
+                    entry=gi["entry"], n=n, heap_tids=tids, heap_tid_counts=cnt)
 
     def prepare_queries(self, queries):
         """Query-side half of the opclass: normalise when FUNCTION 2 exists (scan.rs:749-754)."""

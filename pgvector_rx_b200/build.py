@@ -9,11 +9,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgvrx_b200.so")
-SOURCES = ["capi.cu", "hnsw_search.cu", "page_export.cpp"]
-HEADERS = ["hnsw_device.cuh", "hnsw_kernels.h", os.path.join("..", "..", "include", "pgvrx_b200.h")]
+SOURCES = ["capi.cu", "hnsw_search.cu", "hnsw_build.cu", "build_host.cu", "page_export.cpp"]
+HEADERS = ["hnsw_device.cuh", "hnsw_kernels.h", "index_internal.h", os.path.join("..", "..", "include", "pgvrx_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--fmad=false",   # distances must not contract mul+add
+    "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "--fmad=false",   # distances must not contract mul+add
 ]
 
 
@@ -33,20 +33,45 @@ def is_stale():
 
 
 def build(force=False, verbose=False, timing=False, cpasync_gather=False):
-    """timing=True builds libpgvrx_b200_timing.so with per-phase clock64() instrumentation
-    (a profiling aid selected with PGVRX_LIB=...; never the shipped library)."""
+    """Compile every source to an object in parallel, then link libpgvrx_b200.so.
+
+    timing=True builds libpgvrx_b200_timing.so with per-phase clock64() instrumentation (a profiling
+    aid selected with PGVRX_LIB=...; never the shipped library); cpasync_gather=True builds the
+    measured-slower cp.async row gather for comparison."""
+    from concurrent.futures import ThreadPoolExecutor
     out = LIB.replace(".so", "_timing.so") if timing else LIB
     if cpasync_gather:
         out = out.replace(".so", "_cpasync.so")
-    if not force and not timing and not cpasync_gather and not is_stale():
+    variant = not (out == LIB)
+    if not force and not variant and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          (["-DPGVRX_PHASE_TIMING"] if timing else []) + (["-DPGVRX_GATHER_CPASYNC"] if cpasync_gather else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
+    objdir = os.path.join(HERE, "build", os.path.basename(out).replace(".so", ""))
+    os.makedirs(objdir, exist_ok=True)
+    defs = (["-DPGVRX_PHASE_TIMING"] if timing else []) + (["-DPGVRX_GATHER_CPASYNC"] if cpasync_gather else [])
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + defs
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.rsplit(".", 1)[0] + ".o")
+        sp = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), hdr_t):
+            return obj, 0, ""
+        r = subprocess.run([nvcc_path()] + cflags + ["-c", "-o", obj, sp], capture_output=True, text=True)
+        return obj, r.returncode, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        res = list(ex.map(compile_one, SOURCES))
+    log = "".join(r[2] for r in res)
+    if verbose or any(r[1] for r in res):
+        sys.stderr.write(log)
+    if any(r[1] for r in res):
+        raise RuntimeError("nvcc failed compiling libpgvrx_b200.so")
+    r = subprocess.run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [x[0] for x in res],
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libpgvrx_b200.so")
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking libpgvrx_b200.so")
     return out
 
 

@@ -1,0 +1,652 @@
+// build_host.cu -- pgvrx_index_build: the reference's ambuild insert loop (src/index/build.rs:400-535)
+// with the search_layer calls of find_element_neighbors (src/graph/mod.rs:355-427) batched on the GPU.
+//
+// Division of labour (north star #2): the GPU scores each pending element's ef_construction
+// candidates (K2, hnsw_build.cu); the HOST applies select_neighbors, the duplicate rule,
+// update_neighbor_connections and the entry-point rule in the reference's order, so every neighbour
+// list comes out identical to a sequential build.
+//
+// Exactness under batching.  A round searches B pending elements against the committed snapshot.
+// The search of element j is a deterministic function of the lists of the nodes it expanded (its
+// read set, reported by the kernel), of immutable vectors/levels, and of the entry point.  Elements
+// are committed in order; j's speculative result is used only if no earlier commit of the same round
+// touched a list in j's read set and the entry point did not move -- then a sequential run would have
+// replayed the very same search.  Otherwise the round stops before j and j is searched again next
+// round against the new snapshot (the head of a round is always valid, so progress is guaranteed).
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <cuda_fp16.h>
+
+#include "index_internal.h"
+
+using namespace pgvrx;
+
+namespace pgvrx_host {
+
+// ------------------------------------------------------------------------------------------------
+// strict-order host distances (a13-a15), returned as the build path stores them: f64 -> f32
+// (src/index/build.rs:346-369).  Sequential accumulation, no contraction (nvcc host flags have no
+// -ffast-math and this file is built with -ffp-contract=off via -Xcompiler).
+// ------------------------------------------------------------------------------------------------
+static inline float h2f(uint16_t h) { __half_raw r; r.x = h; return __half2float(__half(r)); }
+
+static float host_distance(int elem, int metric, int dim, const uint8_t *pa, const uint8_t *pb) {
+    if (elem == PGVRX_ELEM_F32) {
+        const float *a = (const float *)pa, *b = (const float *)pb;
+        float acc = 0.0f;
+        if (metric == PGVRX_METRIC_L2SQ) { for (int i = 0; i < dim; i++) { float d = a[i] - b[i]; acc += d * d; } return acc; }
+        if (metric == PGVRX_METRIC_NEG_IP) { for (int i = 0; i < dim; i++) acc += a[i] * b[i]; return (float)(-(double)acc); }
+        for (int i = 0; i < dim; i++) acc += std::fabs(a[i] - b[i]);
+        return acc;
+    }
+    if (elem == PGVRX_ELEM_F16) {
+        const uint16_t *a = (const uint16_t *)pa, *b = (const uint16_t *)pb;
+        float acc = 0.0f;
+        if (metric == PGVRX_METRIC_L2SQ) { for (int i = 0; i < dim; i++) { float d = h2f(a[i]) - h2f(b[i]); acc += d * d; } return acc; }
+        if (metric == PGVRX_METRIC_NEG_IP) { for (int i = 0; i < dim; i++) acc += h2f(a[i]) * h2f(b[i]); return (float)(-(double)acc); }
+        for (int i = 0; i < dim; i++) acc += std::fabs(h2f(a[i]) - h2f(b[i]));
+        return acc;
+    }
+    const size_t nb = ((size_t)dim + 7) / 8;
+    if (metric == PGVRX_METRIC_HAMMING) {
+        uint64_t d = 0;
+        for (size_t i = 0; i < nb; i++) d += (uint64_t)__builtin_popcount((unsigned)(pa[i] ^ pb[i]));
+        return (float)(double)d;
+    }
+    uint64_t ab = 0, aa = 0, bb = 0;
+    for (size_t i = 0; i < nb; i++) {
+        ab += (uint64_t)__builtin_popcount((unsigned)(pa[i] & pb[i]));
+        aa += (uint64_t)__builtin_popcount((unsigned)pa[i]);
+        bb += (uint64_t)__builtin_popcount((unsigned)pb[i]);
+    }
+    if (ab == 0) return 1.0f;
+    return (float)(1.0 - ((double)ab / (double)(aa + bb - ab)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiny fork-join pool
+// ------------------------------------------------------------------------------------------------
+class Pool {
+  public:
+    explicit Pool(int n) : n_(std::max(1, n)) {
+        for (int t = 1; t < n_; t++) th_.emplace_back([this] { worker(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> l(mu_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return n_; }
+    // run fn(i) for i in [0, count) on all threads (dynamic distribution)
+    void parallel_for(int64_t count, const std::function<void(int64_t)> &fn) {
+        if (count <= 0) return;
+        if (n_ == 1 || count == 1) { for (int64_t i = 0; i < count; i++) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            fn_ = &fn; count_ = count; next_.store(0); pending_ = n_ - 1; gen_++;
+        }
+        cv_.notify_all();
+        run();
+        std::unique_lock<std::mutex> l(mu_);
+        done_cv_.wait(l, [this] { return pending_ == 0; });
+    }
+
+  private:
+    void run() {
+        for (;;) {
+            int64_t i = next_.fetch_add(1);
+            if (i >= count_) break;
+            (*fn_)(i);
+        }
+    }
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            run();
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int64_t)> *fn_ = nullptr;
+    int64_t count_ = 0;
+    std::atomic<int64_t> next_{0};
+    int pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// host mirror of the graph (graph/mod.rs:26-84: neighbour lists keep the distance to their owner)
+// ------------------------------------------------------------------------------------------------
+struct Cand { float distance; int32_t idx; };
+
+struct BuildState {
+    int elem = 0, metric = 0, dim = 0, m = 0, efc = 0;
+    size_t row_bytes = 0;
+    int64_t n = 0, n_upper = 0, entry = -1;
+    int entry_level = -1;
+    std::vector<uint8_t> values;        // rows of kept elements, element id * row_bytes (build.rs:242)
+    std::vector<uint8_t> level;
+    std::vector<int32_t> upper_base;
+    std::vector<int32_t> adj0;          // n x 2m
+    std::vector<float> dist0;
+    std::vector<uint8_t> cnt0;
+    std::vector<int32_t> adj_up;        // n_upper x m
+    std::vector<float> dist_up;
+    std::vector<uint8_t> cnt_up;
+    std::vector<uint64_t> tids;         // n x 10 (build.rs:245)
+    std::vector<uint8_t> tid_cnt;
+    std::vector<uint32_t> stamp;        // per node: round in which one of its lists was last modified
+    uint32_t round = 0;
+    std::atomic<uint64_t> n_pair{0};
+
+    const uint8_t *row(int64_t e) const { return values.data() + (size_t)e * row_bytes; }
+    float dist(int64_t a, int64_t b) const { return host_distance(elem, metric, dim, row(a), row(b)); }
+    int lm(int lc) const { return lc == 0 ? 2 * m : m; }
+    int32_t *ids(int64_t v, int lc) { return lc == 0 ? &adj0[(size_t)v * 2 * m] : &adj_up[(size_t)(upper_base[(size_t)v] + lc - 1) * m]; }
+    float *dists(int64_t v, int lc) { return lc == 0 ? &dist0[(size_t)v * 2 * m] : &dist_up[(size_t)(upper_base[(size_t)v] + lc - 1) * m]; }
+    uint8_t &cnt(int64_t v, int lc) { return lc == 0 ? cnt0[(size_t)v] : cnt_up[(size_t)(upper_base[(size_t)v] + lc - 1)]; }
+};
+
+void destroy_build_state(BuildState *b) { delete b; }
+
+// a3: select_neighbors + check_element_closer (graph/mod.rs:269-339)
+static void select_neighbors(BuildState &g, const Cand *cand, int n_cand, int max_neighbors, std::vector<Cand> &out) {
+    out.clear();
+    if (n_cand <= max_neighbors) { out.assign(cand, cand + n_cand); return; }     // :276
+    std::vector<Cand> discarded;
+    uint64_t pairs = 0;
+    for (int i = 0; i < n_cand; i++) {
+        if ((int)out.size() >= max_neighbors) break;                               // :285
+        const Cand &e = cand[i];
+        bool closer = true;
+        for (const Cand &r : out) {                                                // :324-336
+            float d = g.dist(e.idx, r.idx);
+            pairs++;
+            if (d <= e.distance) { closer = false; break; }
+        }
+        if (closer) out.push_back(e); else discarded.push_back(e);
+    }
+    for (const Cand &d : discarded) {                                              // :300-305
+        if ((int)out.size() >= max_neighbors) break;
+        out.push_back(d);
+    }
+    g.n_pair.fetch_add(pairs, std::memory_order_relaxed);
+}
+
+struct Pending {                 // one element of the current round, after phase A
+    int64_t input_row;
+    int level;
+    std::vector<std::vector<Cand>> sel;   // [lc] selected neighbours (graph/mod.rs:419-422)
+    int dup_of = -1;                      // element id this row merges into (build.rs:482-503)
+};
+
+struct Update { int32_t node; int32_t lc; int32_t new_id; float distance; };
+
+}  // namespace pgvrx_host
+
+using namespace pgvrx_host;
+
+namespace {
+
+struct RoundBuffers {
+    DevBuf elem_ids, w_ids, w_dists, w_counts, rs_log, rs_counts, status, ctr, vis, work, sc_off, sc_rows;
+    void release() {
+        DevBuf *b[] = {&elem_ids, &w_ids, &w_dists, &w_counts, &rs_log, &rs_counts, &status, &ctr, &vis, &work, &sc_off, &sc_rows};
+        for (DevBuf *x : b) x->release();
+    }
+};
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, const int32_t *levels,
+                      const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n_rows < 0 || (n_rows > 0 && (!rows_in || !levels))) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null build input");
+    if (ix->loaded && !ix->build) return pgvrx_fail(ix, PGVRX_ERR_STATE, "index was loaded from arrays; build needs a handle that is empty or was built here");
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    const int m = ix->desc.m, efc = ix->desc.ef_construction, l0 = 2 * m;
+    if (!ix->build) {
+        ix->build = new BuildState();
+        BuildState &b = *ix->build;
+        b.elem = ix->desc.elem_type; b.metric = ix->desc.metric; b.dim = ix->desc.dim; b.m = m; b.efc = efc;
+        b.row_bytes = ix->row_bytes;
+    }
+    BuildState &g = *ix->build;
+    if (g.n + n_rows > ix->desc.capacity) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "build exceeds the handle's capacity");
+    const int max_level_allowed = pgvrx_max_level(m);
+    for (int64_t i = 0; i < n_rows; i++)
+        if (levels[i] < 0 || levels[i] > max_level_allowed) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "level out of range");
+
+    const int nthreads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    Pool pool(nthreads);
+    const double t_start = now_ms();
+    double gpu_ms = 0.0;
+
+    // ---- device capacity (grown once to the handle's capacity) ----
+    const int64_t cap = ix->desc.capacity;
+    int64_t up_needed = g.n_upper;
+    for (int64_t i = 0; i < n_rows; i++) up_needed += levels[i];
+    CU_TRY(ix, ix->vectors.ensure_keep(std::max<size_t>(16, (size_t)cap * ix->row_stride), (size_t)g.n * ix->row_stride));
+    CU_TRY(ix, ix->adj0.ensure_keep(std::max<size_t>(16, (size_t)cap * l0 * 4), (size_t)g.n * l0 * 4));
+    CU_TRY(ix, ix->adj_up.ensure_keep(std::max<size_t>(16, (size_t)up_needed * m * 4), (size_t)g.n_upper * m * 4));
+    CU_TRY(ix, ix->upper_base.ensure_keep(std::max<size_t>(16, (size_t)cap * 4), (size_t)g.n * 4));
+    CU_TRY(ix, ix->level.ensure_keep(std::max<size_t>(16, (size_t)cap), (size_t)g.n));
+    ix->loaded = false;
+
+    // ---- host mirror capacity ----
+    g.values.reserve((size_t)(g.n + n_rows) * g.row_bytes);
+    g.level.reserve((size_t)(g.n + n_rows));
+    auto grow_host = [&](int64_t n_new, int64_t up_new) {
+        g.values.resize((size_t)n_new * g.row_bytes);
+        g.level.resize((size_t)n_new);
+        g.upper_base.resize((size_t)n_new);
+        g.adj0.resize((size_t)n_new * l0, -1);
+        g.dist0.resize((size_t)n_new * l0, 0.0f);
+        g.cnt0.resize((size_t)n_new, 0);
+        g.adj_up.resize((size_t)up_new * m, -1);
+        g.dist_up.resize((size_t)up_new * m, 0.0f);
+        g.cnt_up.resize((size_t)up_new, 0);
+        g.tids.resize((size_t)n_new * PGVRX_HEAPTIDS, ~0ull);
+        g.tid_cnt.resize((size_t)n_new, 0);
+        g.stamp.resize((size_t)n_new, 0);
+    };
+
+    const uint8_t *rows = (const uint8_t *)rows_in;
+    auto tid_of = [&](int64_t i) -> uint64_t { return heap_tids ? heap_tids[i] : (uint64_t)i; };
+
+    // place input row i as element id e in the host mirror (no links yet)
+    auto place_element = [&](int64_t i, int64_t e) {
+        grow_host(e + 1, g.n_upper + levels[i]);
+        memcpy(g.values.data() + (size_t)e * g.row_bytes, rows + (size_t)i * g.row_bytes, g.row_bytes);
+        g.level[(size_t)e] = (uint8_t)levels[i];
+        g.upper_base[(size_t)e] = levels[i] > 0 ? (int32_t)g.n_upper : -1;
+        g.cnt0[(size_t)e] = 0;
+        for (int j = 0; j < l0; j++) g.adj0[(size_t)e * l0 + j] = -1;
+        for (int l = 0; l < levels[i]; l++) {
+            g.cnt_up[(size_t)(g.n_upper + l)] = 0;
+            for (int j = 0; j < m; j++) g.adj_up[(size_t)(g.n_upper + l) * m + j] = -1;
+        }
+        g.tid_cnt[(size_t)e] = 0;
+    };
+
+    RoundBuffers rb;
+    struct Cleanup { RoundBuffers &r; ~Cleanup() { r.release(); } } cleanup{rb};
+
+    // scatter staging on the host
+    std::vector<int64_t> sc_off0, sc_offu;
+    std::vector<int32_t> sc_rows0, sc_rowsu;
+    auto queue_row = [&](int64_t v, int lc) {
+        if (lc == 0) {
+            sc_off0.push_back(v * l0);
+            sc_rows0.insert(sc_rows0.end(), &g.adj0[(size_t)v * l0], &g.adj0[(size_t)v * l0] + l0);
+        } else {
+            int64_t r = g.upper_base[(size_t)v] + lc - 1;
+            sc_offu.push_back(r * m);
+            sc_rowsu.insert(sc_rowsu.end(), &g.adj_up[(size_t)r * m], &g.adj_up[(size_t)r * m] + m);
+        }
+    };
+    auto flush_scatter = [&]() -> int {
+        for (int pass = 0; pass < 2; pass++) {
+            std::vector<int64_t> &off = pass == 0 ? sc_off0 : sc_offu;
+            std::vector<int32_t> &dat = pass == 0 ? sc_rows0 : sc_rowsu;
+            if (off.empty()) continue;
+            const int row_len = pass == 0 ? l0 : m;
+            CU_TRY(ix, rb.sc_off.ensure(off.size() * 8));
+            CU_TRY(ix, rb.sc_rows.ensure(dat.size() * 4));
+            CU_TRY(ix, cudaMemcpyAsync(rb.sc_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, cudaMemcpyAsync(rb.sc_rows.p, dat.data(), dat.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, launch_scatter_rows((int32_t *)(pass == 0 ? ix->adj0.p : ix->adj_up.p), (const int64_t *)rb.sc_off.p,
+                                           (const int32_t *)rb.sc_rows.p, row_len, (int)off.size(), ix->stream));
+            CU_TRY(ix, cudaStreamSynchronize(ix->stream));   // host vectors are reused next round
+            off.clear();
+            dat.clear();
+        }
+        return PGVRX_OK;
+    };
+    // upload vector rows / level / upper_base of elements [e0, e1)
+    auto upload_elements = [&](int64_t e0, int64_t e1) -> int {
+        if (e1 <= e0) return PGVRX_OK;
+        if (ix->row_stride == ix->row_bytes)
+            CU_TRY(ix, cudaMemcpyAsync((uint8_t *)ix->vectors.p + (size_t)e0 * ix->row_stride, g.row(e0), (size_t)(e1 - e0) * g.row_bytes,
+                                       cudaMemcpyHostToDevice, ix->stream));
+        else {
+            CU_TRY(ix, cudaMemsetAsync((uint8_t *)ix->vectors.p + (size_t)e0 * ix->row_stride, 0, (size_t)(e1 - e0) * ix->row_stride, ix->stream));
+            CU_TRY(ix, cudaMemcpy2DAsync((uint8_t *)ix->vectors.p + (size_t)e0 * ix->row_stride, ix->row_stride, g.row(e0), g.row_bytes,
+                                         g.row_bytes, (size_t)(e1 - e0), cudaMemcpyHostToDevice, ix->stream));
+        }
+        CU_TRY(ix, cudaMemcpyAsync((uint8_t *)ix->level.p + e0, &g.level[(size_t)e0], (size_t)(e1 - e0), cudaMemcpyHostToDevice, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync((int32_t *)ix->upper_base.p + e0, &g.upper_base[(size_t)e0], (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ix->stream));
+        return PGVRX_OK;
+    };
+
+    int64_t f = 0;                       // next input row
+    uint64_t n_rounds = 0, n_searched = 0, n_conflicts = 0, n_dups = 0, n_retry_big = 0;
+    uint64_t c_dist = 0, c_exp0 = 0, c_expu = 0;
+
+    // the first element of an empty index becomes the entry point without a search (build.rs:526-529)
+    if (g.n == 0 && n_rows > 0) {
+        place_element(0, 0);
+        g.tids[0] = tid_of(0);
+        g.tid_cnt[0] = 1;
+        g.n_upper += levels[0];
+        g.n = 1;
+        g.entry = 0;
+        g.entry_level = levels[0];
+        int rc = upload_elements(0, 1);
+        if (rc) return rc;
+        queue_row(0, 0);
+        for (int l = 1; l <= levels[0]; l++) queue_row(0, l);
+        rc = flush_scatter();
+        if (rc) return rc;
+        f = 1;
+    }
+
+    int window = 4;
+    const int WINDOW_MAX = 512;
+    bool big_next = false;
+    const int rs_cap = std::max(256, 6 * efc + 64);
+    std::vector<int32_t> h_elem, h_wids, h_wcnt, h_rs, h_rscnt;
+    std::vector<float> h_wd;
+    std::vector<uint32_t> h_status, h_ctr;
+
+    while (f < n_rows) {
+        const int B = (int)std::min<int64_t>(big_next ? 1 : window, n_rows - f);
+        g.round++;
+        n_rounds++;
+        // ---- provisional placement: input row f+i -> element id g.n + i (valid while no duplicate commits) ----
+        const int64_t e_base = g.n;
+        const int64_t up_base = g.n_upper;
+        int max_layers = 1;
+        {
+            int64_t up = up_base;
+            for (int i = 0; i < B; i++) {
+                const int64_t save = g.n_upper;
+                g.n_upper = up;                       // place_element reads g.n_upper as this element's first upper row
+                place_element(f + i, e_base + i);
+                g.n_upper = save;
+                up += levels[f + i];
+                max_layers = std::max(max_layers, std::min(levels[f + i], g.entry_level) + 1);
+            }
+        }
+        int rc = upload_elements(e_base, e_base + B);
+        if (rc) return rc;
+
+        // ---- K2 on the GPU ----
+        ScanConfig cfg;
+        uint32_t vis_entries = pgvrx_pow2_at_least(std::max<uint64_t>(1024, (uint64_t)efc * 2 * m * 4));
+        if (big_next) vis_entries = pgvrx_pow2_at_least(std::min<uint64_t>((uint64_t)vis_entries * 16, std::max<uint64_t>(1024, (uint64_t)cap * 2)));
+        rc = pgvrx_make_config(ix, efc, big_next ? 2048 : -1, vis_entries, B, 0, true, &cfg);
+        if (rc) return rc;
+        const int wpb = SEARCH_THREADS / 32;
+        CU_TRY(ix, rb.vis.ensure((size_t)cfg.grid * wpb * cfg.vis_entries * 4));
+        CU_TRY(ix, rb.elem_ids.ensure((size_t)B * 4));
+        CU_TRY(ix, rb.w_ids.ensure((size_t)B * max_layers * efc * 4));
+        CU_TRY(ix, rb.w_dists.ensure((size_t)B * max_layers * efc * 4));
+        CU_TRY(ix, rb.w_counts.ensure((size_t)B * max_layers * 4));
+        CU_TRY(ix, rb.rs_log.ensure((size_t)B * rs_cap * 4));
+        CU_TRY(ix, rb.rs_counts.ensure((size_t)B * 4));
+        CU_TRY(ix, rb.status.ensure((size_t)B * 4));
+        CU_TRY(ix, rb.ctr.ensure((size_t)B * 16));
+        CU_TRY(ix, rb.work.ensure(64));
+        h_elem.resize((size_t)B);
+        for (int i = 0; i < B; i++) h_elem[(size_t)i] = (int32_t)(e_base + i);
+        CU_TRY(ix, cudaMemcpyAsync(rb.elem_ids.p, h_elem.data(), (size_t)B * 4, cudaMemcpyHostToDevice, ix->stream));
+        CU_TRY(ix, cudaMemsetAsync(rb.work.p, 0, 64, ix->stream));
+        ix->n = e_base;                 // snapshot: only committed elements are reachable, but rows of the pending ones are resident
+        ix->entry = g.entry;
+        ix->entry_level = g.entry_level;
+        GraphView gv = pgvrx_view_of(ix);
+        BuildParams bp;
+        bp.elem_ids = (const int32_t *)rb.elem_ids.p;
+        bp.n_pending = B;
+        bp.efc = efc;
+        bp.tail_cap = cfg.L.tail_cap;
+        bp.max_layers = max_layers;
+        bp.w_ids = (int32_t *)rb.w_ids.p;
+        bp.w_dists = (float *)rb.w_dists.p;
+        bp.w_counts = (int32_t *)rb.w_counts.p;
+        bp.rs_log = (int32_t *)rb.rs_log.p;
+        bp.rs_cap = rs_cap;
+        bp.rs_counts = (int32_t *)rb.rs_counts.p;
+        bp.out_status = (uint32_t *)rb.status.p;
+        bp.out_ctr = (uint32_t *)rb.ctr.p;
+        bp.vis_base = (uint32_t *)rb.vis.p;
+        bp.vis_entries = cfg.vis_entries;
+        bp.work_counter = (int *)rb.work.p;
+        bp.stage_stride = cfg.L.stage_stride;
+        bp.R = cfg.L.R;
+        const double tg0 = now_ms();
+        CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, ix->stream));
+        h_wids.resize((size_t)B * max_layers * efc);
+        h_wd.resize((size_t)B * max_layers * efc);
+        h_wcnt.resize((size_t)B * max_layers);
+        h_rs.resize((size_t)B * rs_cap);
+        h_rscnt.resize((size_t)B);
+        h_status.resize((size_t)B);
+        h_ctr.resize((size_t)B * 4);
+        CU_TRY(ix, cudaMemcpyAsync(h_wids.data(), rb.w_ids.p, h_wids.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(h_wd.data(), rb.w_dists.p, h_wd.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(h_wcnt.data(), rb.w_counts.p, h_wcnt.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(h_rs.data(), rb.rs_log.p, h_rs.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(h_rscnt.data(), rb.rs_counts.p, h_rscnt.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(h_status.data(), rb.status.p, h_status.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(h_ctr.data(), rb.ctr.p, h_ctr.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+        gpu_ms += now_ms() - tg0;
+        n_searched += (uint64_t)B;
+
+        // ---- host: phase A (parallel): select_neighbors + duplicate probe for every searched element ----
+        std::vector<Pending> pend((size_t)B);
+        pool.parallel_for(B, [&](int64_t i) {
+            Pending &p = pend[(size_t)i];
+            p.input_row = f + i;
+            p.level = levels[f + i];
+            if (h_status[(size_t)i] != 0) return;
+            const int top = std::min(p.level, g.entry_level);
+            p.sel.resize((size_t)p.level + 1);
+            std::vector<Cand> w;
+            for (int lc = top; lc >= 0; lc--) {
+                const int cnt = h_wcnt[(size_t)i * max_layers + lc];
+                w.resize((size_t)std::max(cnt, 0));
+                const size_t o = ((size_t)i * max_layers + lc) * efc;
+                for (int t = 0; t < cnt; t++) w[(size_t)t] = Cand{h_wd[o + t], h_wids[o + t]};
+                select_neighbors(g, w.data(), cnt, g.lm(lc), p.sel[(size_t)lc]);    // graph/mod.rs:419
+            }
+            // duplicate probe (build.rs:482-503): walk the selected layer-0 neighbours while distance == 0
+            for (const Cand &nb : p.sel[0]) {
+                if (nb.distance != 0.0f) break;
+                if (memcmp(g.row(e_base + i), g.row(nb.idx), g.row_bytes) == 0) { p.dup_of = nb.idx; break; }
+            }
+        });
+
+        // ---- host: sequential validation + commit of the longest valid prefix ----
+        int committed = 0;
+        bool stop = false;
+        std::vector<Update> updates;
+        for (int i = 0; i < B && !stop; i++) {
+            Pending &p = pend[(size_t)i];
+            const int64_t e = e_base + i;
+            if (h_status[(size_t)i] != 0) {                     // scratch overflow: redo alone with large scratch
+                if (i == 0) { big_next = true; n_retry_big++; }
+                break;
+            }
+            bool valid = h_rscnt[(size_t)i] <= rs_cap;
+            if (valid && i > 0) {
+                const int32_t *rs = &h_rs[(size_t)i * rs_cap];
+                for (int t = 0; t < h_rscnt[(size_t)i]; t++)
+                    if (g.stamp[(size_t)rs[t]] == g.round) { valid = false; break; }
+            }
+            if (!valid && i == 0 && h_rscnt[0] > rs_cap) valid = true;   // the head of a round is always exact
+            if (!valid) { n_conflicts++; break; }
+            c_dist += h_ctr[(size_t)i * 4];
+            c_exp0 += h_ctr[(size_t)i * 4 + 1];
+            c_expu += h_ctr[(size_t)i * 4 + 2];
+            big_next = false;
+            committed++;
+            // duplicate merge (build.rs:495-512): the probe skipped the TID-capacity test, apply it in order here
+            bool merged = false;
+            if (p.dup_of >= 0) {
+                for (const Cand &nb : p.sel[0]) {
+                    if (nb.distance != 0.0f) break;
+                    if (memcmp(g.row(e), g.row(nb.idx), g.row_bytes) == 0 && g.tid_cnt[(size_t)nb.idx] < PGVRX_HEAPTIDS) {
+                        g.tids[(size_t)nb.idx * PGVRX_HEAPTIDS + g.tid_cnt[(size_t)nb.idx]++] = tid_of(p.input_row);
+                        merged = true;
+                        break;
+                    }
+                }
+            }
+            if (merged) {                                       // element is dropped: later provisional ids shift
+                n_dups++;
+                stop = true;
+                break;
+            }
+            // new element's own lists (graph/mod.rs:422)
+            const int top = std::min(p.level, g.entry_level);
+            for (int lc = top; lc >= 0; lc--) {
+                const std::vector<Cand> &s = p.sel[(size_t)lc];
+                int32_t *ids = g.ids(e, lc);
+                float *ds = g.dists(e, lc);
+                for (size_t t = 0; t < s.size(); t++) { ids[t] = s[t].idx; ds[t] = s[t].distance; }
+                g.cnt(e, lc) = (uint8_t)s.size();
+                for (const Cand &nb : s) {                      // back-links, applied in phase B (graph/mod.rs:458-487)
+                    updates.push_back(Update{nb.idx, lc, (int32_t)e, nb.distance});
+                    g.stamp[(size_t)nb.idx] = g.round;
+                }
+            }
+            g.tids[(size_t)e * PGVRX_HEAPTIDS] = tid_of(p.input_row);
+            g.tid_cnt[(size_t)e] = 1;
+            g.n = e + 1;
+            g.n_upper = g.upper_base[(size_t)e] >= 0 ? g.upper_base[(size_t)e] + p.level : g.n_upper;
+            if (p.level > g.entry_level) {                      // build.rs:523-525: strictly greater
+                g.entry = e;
+                g.entry_level = p.level;
+                stop = true;                                    // later searches started from the old entry point
+            }
+        }
+        // ---- host: phase B (parallel by node): update_neighbor_connections (graph/mod.rs:442-489) ----
+        // stable order by (node, layer) keeps the per-list updates in insert order
+        std::stable_sort(updates.begin(), updates.end(), [](const Update &a, const Update &b) {
+            return a.node != b.node ? a.node < b.node : a.lc < b.lc; });
+        std::vector<size_t> group_start;
+        for (size_t t = 0; t < updates.size(); t++)
+            if (t == 0 || updates[t].node != updates[t - 1].node || updates[t].lc != updates[t - 1].lc) group_start.push_back(t);
+        group_start.push_back(updates.size());
+        pool.parallel_for((int64_t)group_start.size() - 1, [&](int64_t gi) {
+            std::vector<Cand> all, sel;
+            for (size_t t = group_start[(size_t)gi]; t < group_start[(size_t)gi + 1]; t++) {
+                const Update &u = updates[t];
+                const int lm = g.lm(u.lc);
+                int32_t *ids = g.ids(u.node, u.lc);
+                float *ds = g.dists(u.node, u.lc);
+                uint8_t &c = g.cnt(u.node, u.lc);
+                if ((int)c < lm) {                              // :469-471 room available
+                    ids[c] = u.new_id;
+                    ds[c] = u.distance;
+                    c++;
+                } else {                                        // :473-485 re-select over list + new, replace the list
+                    all.resize((size_t)c + 1);
+                    for (int t2 = 0; t2 < (int)c; t2++) all[(size_t)t2] = Cand{ds[t2], ids[t2]};
+                    all[(size_t)c] = Cand{u.distance, u.new_id};
+                    std::stable_sort(all.begin(), all.end(), [](const Cand &a, const Cand &b) { return a.distance < b.distance; });
+                    select_neighbors(g, all.data(), (int)all.size(), lm, sel);
+                    for (size_t t2 = 0; t2 < sel.size(); t2++) { ids[t2] = sel[t2].idx; ds[t2] = sel[t2].distance; }
+                    for (int t2 = (int)sel.size(); t2 < lm; t2++) ids[t2] = -1;
+                    c = (uint8_t)sel.size();
+                }
+            }
+        });
+
+        // ---- device graph := committed state ----
+        for (size_t gi = 0; gi + 1 < group_start.size(); gi++) queue_row(updates[group_start[gi]].node, updates[group_start[gi]].lc);
+        for (int64_t e = e_base; e < g.n; e++) {
+            queue_row(e, 0);
+            for (int l = 1; l <= g.level[(size_t)e]; l++) queue_row(e, l);
+        }
+        rc = flush_scatter();
+        if (rc) return rc;
+
+        // input rows consumed this round: committed elements plus a merged duplicate
+        f += committed;
+        if (!big_next) window = std::min(WINDOW_MAX, std::max(4, 2 * committed + 2));
+        // host arrays beyond g.n hold provisional (uncommitted) elements; shrink the logical size back
+        grow_host(g.n, g.n_upper);
+    }
+
+    ix->n = g.n;
+    ix->n_upper = g.n_upper;
+    ix->entry = g.entry;
+    ix->entry_level = g.entry_level;
+    ix->loaded = true;
+    if (stats) {
+        stats->n_rounds = n_rounds;
+        stats->n_searched = n_searched;
+        stats->n_conflicts = n_conflicts;
+        stats->n_duplicates = n_dups;
+        stats->n_big_retries = n_retry_big;
+        stats->n_dist = c_dist;
+        stats->n_expand0 = c_exp0;
+        stats->n_expand_upper = c_expu;
+        stats->n_pair = g.n_pair.load();
+        stats->gpu_ms = gpu_ms;
+        stats->total_ms = now_ms() - t_start;
+        stats->host_threads = nthreads;
+    }
+    return PGVRX_OK;
+}
+
+int pgvrx_index_graph_info(const pgvrx_index *ix, int64_t *n, int64_t *n_upper_rows, int64_t *entry, int32_t *entry_level) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (n) *n = ix->n;
+    if (n_upper_rows) *n_upper_rows = ix->n_upper;
+    if (entry) *entry = ix->entry;
+    if (entry_level) *entry_level = ix->entry_level;
+    return PGVRX_OK;
+}
+
+int pgvrx_index_export_graph(pgvrx_index *ix, void *rows, uint8_t *level, int32_t *adj0, int32_t *upper_base, int32_t *adj_up,
+                             uint64_t *heap_tids, uint8_t *heap_tid_counts) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (!ix->build) return pgvrx_fail(ix, PGVRX_ERR_STATE, "export needs an index built with pgvrx_index_build");
+    BuildState &g = *ix->build;
+    const int m = g.m;
+    if (rows) memcpy(rows, g.values.data(), (size_t)g.n * g.row_bytes);
+    if (level) memcpy(level, g.level.data(), (size_t)g.n);
+    if (adj0) memcpy(adj0, g.adj0.data(), (size_t)g.n * 2 * m * 4);
+    if (upper_base) memcpy(upper_base, g.upper_base.data(), (size_t)g.n * 4);
+    if (adj_up) memcpy(adj_up, g.adj_up.data(), (size_t)g.n_upper * m * 4);
+    if (heap_tids) memcpy(heap_tids, g.tids.data(), (size_t)g.n * PGVRX_HEAPTIDS * 8);
+    if (heap_tid_counts) memcpy(heap_tid_counts, g.tid_cnt.data(), (size_t)g.n);
+    return PGVRX_OK;
+}
+
+}  // extern "C"

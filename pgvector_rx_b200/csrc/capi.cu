@@ -15,92 +15,24 @@
 #include <string>
 #include <vector>
 
-#include "../../include/pgvrx_b200.h"
-#include "hnsw_kernels.h"
+#include "index_internal.h"
 
 using namespace pgvrx;
 
 namespace {
-
 thread_local std::string g_create_error;
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-inline uint32_t round16u(size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); }
-
-}  // namespace
+}
 
 namespace pgvrx_host {
 void set_create_error(const std::string &msg) { g_create_error = msg; }
 }
 
-struct pgvrx_index {
-    pgvrx_index_desc desc{};
-    size_t row_bytes = 0;
-    uint32_t row_stride = 0;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // graph in HBM
-    DevBuf vectors, adj0, adj_up, upper_base, level;
-    int64_t n = 0, n_upper = 0, entry = -1;
-    int entry_level = -1;
-    bool loaded = false;
-    // scratch
-    DevBuf q, ids, dists, counts, status, ctr, vis, vis_retry, qmap, work, phase;
-    std::string err;
-};
-
-namespace {
-
-int fail(pgvrx_index *idx, int code, const std::string &msg) {
+int pgvrx_fail(pgvrx_index *idx, int code, const std::string &msg) {
     if (idx) idx->err = msg; else g_create_error = msg;
     return code;
 }
 
-#define CU_TRY(idx, expr)                                                                       \
-    do {                                                                                        \
-        cudaError_t _e = (expr);                                                                \
-        if (_e != cudaSuccess) {                                                                \
-            char _b[512];                                                                       \
-            snprintf(_b, sizeof _b, "%s: %s (%s:%d)", cudaGetErrorName(_e), cudaGetErrorString(_e), \
-                     __FILE__, __LINE__);                                                       \
-            cudaGetLastError();                                                                 \
-            return fail(idx, _e == cudaErrorMemoryAllocation ? PGVRX_ERR_NOMEM : PGVRX_ERR_CUDA, _b); \
-        }                                                                                       \
-    } while (0)
-
-bool metric_ok(int elem, int metric) {
-    if (elem == PGVRX_ELEM_BIT) return metric == PGVRX_METRIC_HAMMING || metric == PGVRX_METRIC_JACCARD;
-    if (elem == PGVRX_ELEM_F32 || elem == PGVRX_ELEM_F16)
-        return metric == PGVRX_METRIC_L2SQ || metric == PGVRX_METRIC_NEG_IP || metric == PGVRX_METRIC_L1;
-    return false;
-}
-
-int max_dim(int elem) {
-    return elem == PGVRX_ELEM_F32 ? PGVRX_MAX_DIM_VECTOR : elem == PGVRX_ELEM_F16 ? PGVRX_MAX_DIM_HALFVEC
-                                                                                 : PGVRX_MAX_DIM_BIT;
-}
-
-GraphView view_of(const pgvrx_index *ix) {
+GraphView pgvrx_view_of(const pgvrx_index *ix) {
     GraphView g;
     g.vectors = (const uint8_t *)ix->vectors.p;
     g.adj0 = (const int32_t *)ix->adj0.p;
@@ -116,23 +48,35 @@ GraphView view_of(const pgvrx_index *ix) {
     return g;
 }
 
-uint32_t pow2_at_least(uint64_t x) {
+namespace {
+
+inline int fail(pgvrx_index *idx, int code, const std::string &msg) { return pgvrx_fail(idx, code, msg); }
+inline GraphView view_of(const pgvrx_index *ix) { return pgvrx_view_of(ix); }
+
+bool metric_ok(int elem, int metric) {
+    if (elem == PGVRX_ELEM_BIT) return metric == PGVRX_METRIC_HAMMING || metric == PGVRX_METRIC_JACCARD;
+    if (elem == PGVRX_ELEM_F32 || elem == PGVRX_ELEM_F16)
+        return metric == PGVRX_METRIC_L2SQ || metric == PGVRX_METRIC_NEG_IP || metric == PGVRX_METRIC_L1;
+    return false;
+}
+
+int max_dim(int elem) {
+    return elem == PGVRX_ELEM_F32 ? PGVRX_MAX_DIM_VECTOR : elem == PGVRX_ELEM_F16 ? PGVRX_MAX_DIM_HALFVEC
+                                                                                 : PGVRX_MAX_DIM_BIT;
+}
+
+}  // namespace
+
+uint32_t pgvrx_pow2_at_least(uint64_t x) {
     uint32_t p = 256;
     while (p < x && p < (1u << 30)) p <<= 1;
     return p;
 }
 
-// one search configuration: staging geometry, scratch sizes, grid
-struct ScanConfig {
-    SearchLaunch L;
-    uint32_t vis_entries;
-    size_t smem_block;
-    int grid;
-};
-
 // tail_cap < 0: pick the register-resident list when ef is small enough (capacity 32*J - 1 with at
 // least 16 retained-tie slots), else the shared-memory list with 32 tie slots
-int make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int64_t nq, int max_grid, ScanConfig *out) {
+int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int64_t nq, int max_grid,
+                      bool for_build, ScanConfig *out) {
     // bytes of shared memory per warp for staged rows; 32 rows of a 128-d fp32 vector fit in 17 KiB.
     // PGVRX_STAGE_KB overrides it for tuning experiments (occupancy vs. rows per TMA round).
     uint32_t STAGE_BUDGET = 17 * 1024;
@@ -154,7 +98,8 @@ int make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int
     c.smem_block = search_warp_smem(c.L) * (SEARCH_THREADS / 32);
     if (c.smem_block > 227 * 1024) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search configuration exceeds shared memory");
     int occ = 0;
-    CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, &occ));
+    if (for_build) CU_TRY(ix, build_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, &occ));
+    else CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, &occ));
     if (occ < 1) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search kernel does not fit on an SM");
     int64_t want = (nq + SEARCH_THREADS / 32 - 1) / (SEARCH_THREADS / 32);
     int64_t cap = (int64_t)ix->sm_count * occ;
@@ -163,6 +108,8 @@ int make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int
     *out = c;
     return PGVRX_OK;
 }
+
+namespace {
 
 int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64_t nq, int ef, int k,
                 int32_t *d_ids, float *d_dists, int32_t *d_counts, pgvrx_search_stats *stats,
@@ -177,11 +124,11 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
 
     const int m = ix->desc.m;
     ScanConfig main_cfg, retry_cfg;
-    uint32_t vis_main = pow2_at_least(std::max<uint64_t>(1024, (uint64_t)ef * 2 * m * 4));   // <= ~25 % load
-    int rc = make_config(ix, ef, -1, vis_main, nq, 0, &main_cfg);
+    uint32_t vis_main = pgvrx_pow2_at_least(std::max<uint64_t>(1024, (uint64_t)ef * 2 * m * 4));   // <= ~25 % load
+    int rc = pgvrx_make_config(ix, ef, -1, vis_main, nq, 0, false, &main_cfg);
     if (rc) return rc;
-    uint32_t vis_retry = pow2_at_least(std::min<uint64_t>((uint64_t)vis_main * 16, std::max<uint64_t>(1024, (uint64_t)ix->n * 2)));
-    rc = make_config(ix, ef, 2048, vis_retry, nq, ix->sm_count, &retry_cfg);
+    uint32_t vis_retry = pgvrx_pow2_at_least(std::min<uint64_t>((uint64_t)vis_main * 16, std::max<uint64_t>(1024, (uint64_t)ix->n * 2)));
+    rc = pgvrx_make_config(ix, ef, 2048, vis_retry, nq, ix->sm_count, false, &retry_cfg);
     if (rc) return rc;
 
     const int wpb = SEARCH_THREADS / 32;
@@ -412,6 +359,7 @@ void pgvrx_index_destroy(pgvrx_index *ix) {
     DevBuf *bufs[] = {&ix->vectors, &ix->adj0, &ix->adj_up, &ix->upper_base, &ix->level, &ix->q, &ix->ids, &ix->dists,
                       &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work, &ix->phase};
     for (DevBuf *b : bufs) b->release();
+    if (ix->build) pgvrx_host::destroy_build_state(ix->build);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
     if (ix->stream) cudaStreamDestroy(ix->stream);

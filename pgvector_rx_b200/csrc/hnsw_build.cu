@@ -1,0 +1,194 @@
+// hnsw_build.cu -- K2: the search half of find_element_neighbors (src/graph/mod.rs:355-427) for a
+// batch of pending inserts, each run by one warp against the same committed snapshot of the graph.
+//
+// Per insert: distance to the entry point (:371-377), greedy ef = 1 descent through layers
+// entry_level .. level+1 (:385-399), then search_layer at ef_construction on layers
+// min(level, entry_level) .. 0 with W of one layer as the entry points of the next (:403-426).
+// Outputs per searched layer: W sorted ascending by (distance, id) -- what select_neighbors consumes
+// on the host -- and the ids of all expanded nodes (the search's read set), which lets the host
+// prove that a speculative result is still exact after earlier inserts of the batch were committed.
+#include "hnsw_device.cuh"
+#include "hnsw_kernels.h"
+
+namespace pgvrx {
+
+__host__ __device__ inline uint32_t round16b(uint32_t x) { return (x + 15u) & ~15u; }
+
+template <int J> struct BListOf {
+    typedef RegList<J> type;
+    __device__ static __forceinline__ void attach(type &, uint8_t *) {}
+};
+template <> struct BListOf<0> {
+    typedef SmemList type;
+    __device__ static __forceinline__ void attach(type &l, uint8_t *mem) { l.S = reinterpret_cast<uint64_t *>(mem); l.hint = 0; }
+};
+
+template <int ELEM, int METRIC, int LISTJ>
+__global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(GraphView g, BuildParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cap = p.efc + p.tail_cap;
+    const size_t s_bytes = LISTJ == 0 ? round16b((uint32_t)((cap + 1) * 8)) : 0;
+    const size_t per_warp = (size_t)p.R * p.stage_stride + g.row_stride + s_bytes + 128 + 16;
+    uint8_t *base = smem + (size_t)warp * per_warp;
+
+    WarpCtx c;
+    c.stage = base;
+    c.qsm = c.stage + (size_t)p.R * p.stage_stride;
+    uint8_t *s_mem = c.qsm + g.row_stride;
+    c.nbr = reinterpret_cast<int32_t *>(s_mem + s_bytes);
+    c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
+    typename BListOf<LISTJ>::type S;
+    BListOf<LISTJ>::attach(S, s_mem);
+    c.stage_stride = p.stage_stride;
+    c.R = p.R;
+    c.nvec = (int)(g.row_stride / 16);
+    c.cap = cap;
+    c.lane = lane;
+    c.phase = 0;
+    c.policy = l2_policy_evict_first();
+    const int slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
+    c.vis = p.vis_base + (size_t)slot * p.vis_entries;
+    if (lane == 0) {
+        mbar_init(c.mbar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const uint32_t up_entries = p.vis_entries < 1024u ? p.vis_entries : 1024u;
+
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(p.work_counter, 1);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= p.n_pending) break;
+        const int e = p.elem_ids[w];
+        const int lvl = g.level[e];
+
+        c.n_dist = c.n_exp0 = c.n_expu = c.n_vis = 0;
+        c.status = 0;
+        c.rs_log = p.rs_log + (size_t)w * p.rs_cap;
+        c.rs_cap = p.rs_cap;
+        c.rs_n = 0;
+        for (int l = lane; l < p.max_layers; l += 32) p.w_counts[(size_t)w * p.max_layers + l] = -1;
+
+        // the new element's own row is the query (build.rs:444-454 copies it into the arena first)
+        {
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(g.vectors + (size_t)e * g.row_stride);
+            uint4 *d4 = reinterpret_cast<uint4 *>(c.qsm);
+            for (int i = lane; i < c.nvec; i += 32) d4[i] = __ldg(q4 + i);
+        }
+        if (lane == 0) c.nbr[0] = g.entry;
+        __syncwarp();
+        gather_rows(c, g, 0, 1);
+        float d0 = 0.0f;
+        if (lane == 0) d0 = row_distance<ELEM, METRIC>(c.qsm, c.stage, c.nvec);    // graph/mod.rs:371-377
+        d0 = __shfl_sync(FULL, d0, 0);
+        c.n_dist = 1;
+        __syncwarp();
+        uint64_t ep_key = make_key(d0, (uint32_t)g.entry);
+
+        // phase 1: greedy descent above the new element's level (graph/mod.rs:385-399)
+        c.ef = 1;
+        for (int lc = g.entry_level; lc > lvl && c.status == 0; lc--) {
+            vis_clear(c.vis, up_entries, lane);
+            if (lane == 0) vis_insert(c.vis, up_entries - 1, key_id(ep_key));
+            __syncwarp();
+            c.n_vis++;
+            S.reset1(c, ep_key);
+            search_layer<ELEM, METRIC>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
+            ep_key = S.get(c, 0) & ~1ull;                                           // :396-398 w[0]
+        }
+        // phase 2: ef_construction search on every layer the new element joins (graph/mod.rs:403-426)
+        c.ef = p.efc;
+        bool first = true;
+        for (int lc = min(lvl, g.entry_level); lc >= 0 && c.status == 0; lc--) {
+            vis_clear(c.vis, p.vis_entries, lane);
+            if (first) {
+                if (lane == 0) vis_insert(c.vis, p.vis_entries - 1, key_id(ep_key));
+                __syncwarp();
+                c.n_vis++;
+                S.reset1(c, ep_key);
+            } else {
+                S.reopen(c, c.vis, p.vis_entries - 1);                              // :425 ep = w
+                c.n_vis += c.len;
+            }
+            first = false;
+            search_layer<ELEM, METRIC>(c, S, g, lc, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
+            if (c.status == 0 && lc < p.max_layers) {
+                const int out_n = min(c.len, c.ef);
+                const size_t o = ((size_t)w * p.max_layers + lc) * p.efc;
+                S.store(c, p.w_ids + o, p.w_dists + o, out_n);
+                if (lane == 0) p.w_counts[(size_t)w * p.max_layers + lc] = out_n;
+            }
+        }
+        if (lane == 0) {
+            p.out_status[w] = c.status;
+            p.rs_counts[w] = c.rs_n;
+            if (p.out_ctr) reinterpret_cast<uint4 *>(p.out_ctr)[w] = make_uint4(c.n_dist, c.n_exp0, c.n_expu, c.n_vis);
+        }
+        __syncwarp();
+    }
+}
+
+// scatter freshly committed neighbour rows into the device adjacency (one thread per int)
+__global__ void scatter_rows_kernel(int32_t *dst, const int64_t *row_offsets, const int32_t *packed, int row_len, int n_rows) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = t / row_len, j = t - r * row_len;
+    if (r < n_rows) dst[row_offsets[r] + j] = packed[(size_t)r * row_len + j];
+}
+
+typedef void (*build_kernel_t)(GraphView, BuildParams);
+
+template <int ELEM, int METRIC>
+static build_kernel_t pick_list(int list_j) {
+    switch (list_j) {
+        case 2: return hnsw_build_search_kernel<ELEM, METRIC, 2>;
+        case 4: return hnsw_build_search_kernel<ELEM, METRIC, 4>;
+        case 8: return hnsw_build_search_kernel<ELEM, METRIC, 8>;
+        case 0: return hnsw_build_search_kernel<ELEM, METRIC, 0>;
+    }
+    return nullptr;
+}
+
+static build_kernel_t pick_kernel(int elem, int metric, int list_j) {
+    if (elem == ELEM_F32) {
+        if (metric == METRIC_L2SQ) return pick_list<ELEM_F32, METRIC_L2SQ>(list_j);
+        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F32, METRIC_NEG_IP>(list_j);
+        if (metric == METRIC_L1) return pick_list<ELEM_F32, METRIC_L1>(list_j);
+    } else if (elem == ELEM_F16) {
+        if (metric == METRIC_L2SQ) return pick_list<ELEM_F16, METRIC_L2SQ>(list_j);
+        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F16, METRIC_NEG_IP>(list_j);
+        if (metric == METRIC_L1) return pick_list<ELEM_F16, METRIC_L1>(list_j);
+    } else if (elem == ELEM_BIT) {
+        if (metric == METRIC_HAMMING) return pick_list<ELEM_BIT, METRIC_HAMMING>(list_j);
+        if (metric == METRIC_JACCARD) return pick_list<ELEM_BIT, METRIC_JACCARD>(list_j);
+    }
+    return nullptr;
+}
+
+cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm) {
+    build_kernel_t k = pick_kernel(elem, metric, list_j);
+    if (!k) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, SEARCH_THREADS, smem_block);
+}
+
+cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
+                                size_t smem_block, cudaStream_t stream) {
+    build_kernel_t k = pick_kernel(elem, metric, list_j);
+    if (!k) return cudaErrorInvalidValue;
+    k<<<grid, SEARCH_THREADS, smem_block, stream>>>(g, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_rows(int32_t *dst, const int64_t *row_offsets, const int32_t *packed, int row_len, int n_rows,
+                                cudaStream_t stream) {
+    if (n_rows <= 0) return cudaSuccess;
+    int total = n_rows * row_len;
+    scatter_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(dst, row_offsets, packed, row_len, n_rows);
+    return cudaGetLastError();
+}
+
+}  // namespace pgvrx

@@ -252,6 +252,8 @@ struct WarpCtx {
     uint32_t phase;
     uint32_t f_ord;        // ordered bits of W's furthest distance (valid when len >= ef)
     uint32_t n_dist, n_exp0, n_expu, n_vis, status;
+    int32_t *rs_log;       // build: ids of the nodes whose neighbour lists this search read (or NULL)
+    int rs_cap, rs_n;      // capacity / count (rs_n may exceed rs_cap: the host then treats the set as unknown)
     int lane;
 #ifdef PGVRX_PHASE_TIMING
     uint32_t t[8];         // cycles: 0 pop+adjacency, 1 visited, 2 tma issue+wait, 3 distance, 4 accept/insert
@@ -336,6 +338,20 @@ struct RegList {
         }
         return true;
     }
+    // Build phase 2 (graph/mod.rs:425 `ep = w`): W of this layer becomes the entry-point list of the next
+    // one.  Drops retained ties (they are not in W), clears the expanded flags, sets f_ord, and inserts
+    // every id into the (freshly cleared) visited table.
+    __device__ __forceinline__ void reopen(WarpCtx &c, uint32_t *vis, uint32_t vis_mask) {
+        c.len = min(c.len, c.ef);
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+            const int gi = c.lane * J + j;
+            if (gi >= c.len) k[j] = KEY_NONE;
+            else { k[j] &= ~1ull; vis_insert(vis, vis_mask, key_id(k[j])); }
+        }
+        __syncwarp();
+        if (c.len >= c.ef) c.f_ord = key_ord(get(c, c.ef - 1));
+    }
     __device__ __forceinline__ void store(const WarpCtx &c, int32_t *ids, float *dists, int out_n) const {
 #pragma unroll
         for (int j = 0; j < J; j++) {
@@ -411,6 +427,17 @@ struct SmemList {
         }
         return false;
     }
+    __device__ __forceinline__ void reopen(WarpCtx &c, uint32_t *vis, uint32_t vis_mask) {
+        c.len = min(c.len, c.ef);
+        __syncwarp();
+        for (int i = c.lane; i < c.len; i += 32) {
+            S[i] &= ~1ull;
+            vis_insert(vis, vis_mask, key_id(S[i]));
+        }
+        __syncwarp();
+        hint = 0;
+        if (c.len >= c.ef) c.f_ord = key_ord(S[c.ef - 1]);
+    }
     __device__ __forceinline__ void store(const WarpCtx &c, int32_t *ids, float *dists, int out_n) const {
         for (int i = c.lane; i < out_n; i += 32) { ids[i] = (int32_t)key_id(S[i]); dists[i] = ord_f32(key_ord(S[i])); }
     }
@@ -468,6 +495,10 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
         PH_START(c);
         if (!S.pop_nearest(c, ckey)) break;   // every remaining candidate would fail `c.distance > f_dist`
         const uint32_t cid = key_id(ckey);
+        if (c.rs_log) {
+            if (lane == 0 && c.rs_n < c.rs_cap) c.rs_log[c.rs_n] = (int32_t)cid;
+            c.rs_n++;
+        }
         const int32_t *row;
         if (layer == 0) {
             row = g.adj0 + (size_t)cid * (size_t)lm;

@@ -40,6 +40,27 @@ struct SearchParams {
     int R;                     // staged rows per warp (<= 32)
 };
 
+// K2: build-side search of a batch of pending inserts (hnsw_build.cu)
+struct BuildParams {
+    const int32_t *elem_ids;   // element id (= row in the vector table) of each pending insert
+    int n_pending;
+    int efc, tail_cap;
+    int max_layers;            // output rows per insert; layer lc of insert w lives at [w][lc]
+    int32_t *w_ids;            // n_pending x max_layers x efc, ascending (distance, id)
+    float *w_dists;
+    int32_t *w_counts;         // n_pending x max_layers, -1 for layers that were not searched
+    int32_t *rs_log;           // n_pending x rs_cap expanded node ids (the search's read set)
+    int rs_cap;
+    int32_t *rs_counts;        // n_pending (may exceed rs_cap => set unknown)
+    uint32_t *out_status;      // n_pending
+    uint32_t *out_ctr;         // n_pending x 4 or NULL
+    uint32_t *vis_base;
+    uint32_t vis_entries;
+    int *work_counter;
+    uint32_t stage_stride;
+    int R;
+};
+
 // what the host needs to size shared memory
 struct SearchLaunch {
     int R, ef, tail_cap;
@@ -51,6 +72,11 @@ size_t search_warp_smem(const SearchLaunch &L);
 cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm);
 cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView &g, const SearchParams &p, int grid,
                                size_t smem_block, cudaStream_t stream);
+cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm);
+cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
+                                size_t smem_block, cudaStream_t stream);
+cudaError_t launch_scatter_rows(int32_t *dst, const int64_t *row_offsets, const int32_t *packed, int row_len, int n_rows,
+                                cudaStream_t stream);
 cudaError_t launch_collect_failed(const uint32_t *status, int nq, int32_t *qmap, int *n_work, cudaStream_t stream);
 
 }  // namespace pgvrx

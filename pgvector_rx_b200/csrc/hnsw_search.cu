@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     c.lane = lane;
     c.phase = 0;
     c.policy = l2_policy_evict_first();
+    c.rs_log = nullptr;
+    c.rs_cap = c.rs_n = 0;
     const int slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
     c.vis = p.vis_base + (size_t)slot * p.vis_entries;
 
