@@ -36,8 +36,8 @@ def log(*a):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=128)
@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cache", default=os.path.join(ROOT, "data_cache"))
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--recall-sample", type=int, default=200)
+    ap.add_argument("--build-rows", type=int, default=100_000,
+                    help="rows of the same dataset built on the GPU for the build vectors/s figure (0 = skip)")
     return ap.parse_args()
 
 
@@ -121,6 +123,34 @@ def cpu_baseline(a, g, queries, sample=0, budget_s=12.0):
                        % (done, done // len(q), len(q), a.ef, a.k, cores, dt)), ids, o
 
 
+def gpu_build_sample(a, local):
+    """Index build (CREATE INDEX) of the first --build-rows rows of the C2 dataset through
+    pgvrx_index_build: GPU-batched search_layer + host heuristic.  When an oracle graph of exactly that
+    prefix is cached, the adjacency is compared with it (it must be identical)."""
+    import pgvector_rx_b200 as P
+    from pgvector_rx_b200 import datasets as D
+    n = min(a.build_rows, a.n)
+    X = D.gaussian_f32(a.n, a.dim, 2)[:n] if n < a.n else D.gaussian_f32(a.n, a.dim, 2)
+    lv = D.hnsw_levels(a.n, a.m, 4)[:n]
+    ix = P.HnswIndex("vector_l2_ops", a.dim, m=a.m, ef_construction=a.efc, capacity=n, device=local)
+    t0 = time.perf_counter()
+    st = ix.build(X, lv)
+    dt = time.perf_counter() - t0
+    out = dict(gpu_vectors_per_s=n / dt, rows=n, seconds=dt, rounds=st["n_rounds"], searches=st["n_searched"],
+               conflicts=st["n_conflicts"], kernel_ms=st["kernel_ms"], host_threads=st["host_threads"],
+               note="first %d rows of the 1M dataset (same seeds); exact sequential semantics, see DESIGN.md" % n)
+    d = os.path.join(a.cache, "g_%d_%d_%d_%d" % (n, a.dim, a.m, a.efc))
+    if os.path.exists(os.path.join(d, "meta.json")):
+        meta = json.load(open(os.path.join(d, "meta.json")))
+        g = ix.export_graph()
+        same = g["entry"] == meta["entry"] and all(np.array_equal(g[k], np.load(os.path.join(d, k + ".npy")))
+                                                   for k in ("level", "adj0", "upper_base", "adj_up"))
+        out["adjacency_identical_to_oracle"] = bool(same)
+        out["cpu_oracle_vectors_per_s_same_rows"] = meta["n"] / meta["build_seconds"]
+    ix.close()
+    return out
+
+
 def recall_at_k(a, g, queries, got_ids, sample):
     import oracle_ffi as O
     s = min(sample, len(queries))
@@ -142,7 +172,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -194,7 +224,7 @@ def run_reference(a):
     batches = query_batches(a, 1, 0)
     o = oracle_for(a, g)
     cores = os.cpu_count() or 1
-    per_step = min(a.nq, 200 * cores)          # bounded sample of the 10k-query batch per step
+    per_step = a.nq if cores >= 8 else min(a.nq, 400 * cores)   # the whole 10k batch per step unless the box is tiny
     q = batches[0][:per_step]
     for _ in range(max(a.warmup, 1)):
         o.search_batch(q[: 4 * cores], ef_search=a.ef, k=a.k, nthreads=cores)
@@ -312,6 +342,10 @@ def run_b200(a):
     achieved = bytes_step / step_s / 1e9
     out = None
     if rank == 0:
+        build_info = dict(cpu_oracle_vectors_per_s=g.get("build_vec_per_s_cpu"), gpu_vectors_per_s=None)
+        if a.build_rows > 0:
+            ix.close()
+            build_info.update(gpu_build_sample(a, local))
         base, cpu_ids, o = cpu_baseline(a, g, last_batch, a.cpu_sample)
         nchk = len(cpu_ids)
         parity_ok = bool(np.array_equal(cpu_ids, last_ids[:nchk]))
@@ -335,8 +369,7 @@ def run_b200(a):
                                                n_expand_upper=int(st.n_expand_upper), n_retried=int(st.n_retried)),
                                  note="achieved = (n_dist*512 + n_expand0*128 + n_expand_upper*64 bytes per step) / CUDA-event step time, rank 0 counters"),
                    cpu_baseline=base,
-                   build=dict(cpu_oracle_vectors_per_s=g.get("build_vec_per_s_cpu"), gpu_vectors_per_s=None,
-                              note="GPU build path not measured in this line"))
+                   build=build_info)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -162,6 +162,7 @@ typedef struct {
     uint64_t n_dist, n_expand0, n_expand_upper;   /* GPU work of the committed searches           */
     uint64_t n_pair;          /* pairwise distances of select_neighbors on the host (graph/mod.rs:326) */
     double   gpu_ms;          /* wall time spent in upload + kernel + download                     */
+    double   kernel_ms;       /* device time of the K2 launches alone (CUDA events)               */
     double   total_ms;
     int32_t  host_threads;
 } pgvrx_build_stats;

@@ -250,7 +250,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     const int nthreads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     Pool pool(nthreads);
     const double t_start = now_ms();
-    double gpu_ms = 0.0;
+    double gpu_ms = 0.0, kernel_ms = 0.0;
 
     // ---- device capacity (grown once to the handle's capacity) ----
     const int64_t cap = ix->desc.capacity;
@@ -446,7 +446,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         bp.stage_stride = cfg.L.stage_stride;
         bp.R = cfg.L.R;
         const double tg0 = now_ms();
+        CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
         CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, ix->stream));
+        CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));
         h_wids.resize((size_t)B * max_layers * efc);
         h_wd.resize((size_t)B * max_layers * efc);
         h_wcnt.resize((size_t)B * max_layers);
@@ -463,6 +465,11 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         CU_TRY(ix, cudaMemcpyAsync(h_ctr.data(), rb.ctr.p, h_ctr.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
         CU_TRY(ix, cudaStreamSynchronize(ix->stream));
         gpu_ms += now_ms() - tg0;
+        {
+            float kms = 0.0f;
+            CU_TRY(ix, cudaEventElapsedTime(&kms, ix->ev0, ix->ev1));
+            kernel_ms += kms;
+        }
         n_searched += (uint64_t)B;
 
         // ---- host: phase A (parallel): select_neighbors + duplicate probe for every searched element ----
@@ -618,6 +625,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         stats->n_expand_upper = c_expu;
         stats->n_pair = g.n_pair.load();
         stats->gpu_ms = gpu_ms;
+        stats->kernel_ms = kernel_ms;
         stats->total_ms = now_ms() - t_start;
         stats->host_threads = nthreads;
     }
