@@ -203,6 +203,46 @@ int pgvrx_search_batch_device(pgvrx_index *idx, const void *d_queries, int64_t n
                               int32_t k, int32_t *d_ids, float *d_dists, int32_t *d_counts,
                               pgvrx_search_stats *stats, void *cuda_stream);
 
+/* ---- exact paths: flat kNN, re-rank, top-k merge ---------------------------------------------- */
+/* The reference has no flat-kNN routine: its ground truth is PostgreSQL's sequential scan ordered by
+ * the distance operator (tests/t/012_hnsw_vector_build_recall.pl:83, 013...pl:95-98; operators
+ * src/types/vector.rs:586-659, halfvec.rs:765-817, bitvec.rs:144-167).  These entry points are that
+ * scan on the GPU: every distance is the opclass FUNCTION 1 value computed with the reference's
+ * arithmetic (bit-identical), results ordered by (distance, element id). */
+typedef struct {
+    uint64_t n_pairs;         /* (query, row) distance evaluations                                */
+    uint64_t n_candidates;    /* rows re-ranked exactly (tensor-core path only)                   */
+    uint32_t n_launches;
+    uint32_t n_splits;        /* base-row splits merged per query                                 */
+    uint32_t path;            /* 0 = sequential f32 chains on CUDA cores; 1 = 3xTF32 tcgen05 candidate
+                                 generation + exact re-rank (large fp32 L2 / IP batches)          */
+    float    kernel_ms;       /* device time of the call's kernels (CUDA events)                  */
+} pgvrx_flat_stats;
+
+/* Upload a vector table without a graph (enough for the exact paths).  Element id == row number. */
+int pgvrx_index_load_rows(pgvrx_index *idx, const void *rows, int64_t n);
+/* k nearest rows per query by exact distance.  out_ids / out_dists are nq*k, padded with -1 / +inf
+ * when the table has fewer than k rows.  HOST buffers. */
+int pgvrx_flat_topk(pgvrx_index *idx, const void *queries, int64_t nq, int32_t k, int32_t *out_ids,
+                    float *out_dists, pgvrx_flat_stats *stats /* may be NULL */);
+/* DEVICE buffers; scans rows [row_begin, row_end) (row_end < 0: to the end) and reports
+ * id_base + (row - row_begin): a rank that holds one shard of a larger base set passes the shard's
+ * first global id.  Asynchronous on cuda_stream unless stats != NULL. */
+int pgvrx_flat_topk_device(pgvrx_index *idx, const void *d_queries, int64_t nq, int32_t k, int64_t row_begin,
+                           int64_t row_end, int64_t id_base, int32_t *d_ids, float *d_dists,
+                           pgvrx_flat_stats *stats, void *cuda_stream);
+/* Exact re-rank: cand_ids is nq x nc element ids (-1 = none); returns the k nearest of each list by
+ * exact distance, ordered by (distance, id). */
+int pgvrx_rerank(pgvrx_index *idx, const void *queries, int64_t nq, const int32_t *cand_ids, int32_t nc,
+                 int32_t k, int32_t *out_ids, float *out_dists);
+int pgvrx_rerank_device(pgvrx_index *idx, const void *d_queries, int64_t nq, const int32_t *d_cand, int32_t nc,
+                        int32_t k, int64_t id_base, int32_t *d_ids, float *d_dists, void *cuda_stream);
+/* K-way merge of per-shard results laid out [part][query][k_in] (what an all-gather of every rank's
+ * pgvrx_flat_topk_device output produces) into the k_out nearest per query.  DEVICE buffers. */
+int pgvrx_topk_merge_device(pgvrx_index *idx, const int32_t *d_part_ids, const float *d_part_dists,
+                            int32_t n_parts, int64_t nq, int32_t k_in, int32_t k_out, int32_t *d_out_ids,
+                            float *d_out_dists, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,8 @@ EXPORTS = [
     "pgvrx_level_from_uniform", "pgvrx_max_level", "pgvrx_row_bytes", "pgvrx_index_create",
     "pgvrx_index_destroy", "pgvrx_index_load_graph", "pgvrx_index_size", "pgvrx_search_batch",
     "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export", "pgvrx_index_build",
-    "pgvrx_index_graph_info", "pgvrx_index_export_graph",
+    "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
+    "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
 ]
 
 
@@ -80,6 +81,14 @@ class SearchStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class FlatStats(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint32),
+                ("n_splits", C.c_uint32), ("path", C.c_uint32), ("kernel_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -111,6 +120,12 @@ def lib():
         "pgvrx_index_export_graph": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_search_batch": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats)]),
         "pgvrx_search_batch_device": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats), vp]),
+        "pgvrx_index_load_rows": (C.c_int, [vp, vp, i64]),
+        "pgvrx_flat_topk": (C.c_int, [vp, vp, i64, i32, vp, vp, C.POINTER(FlatStats)]),
+        "pgvrx_flat_topk_device": (C.c_int, [vp, vp, i64, i32, i64, i64, i64, vp, vp, C.POINTER(FlatStats), vp]),
+        "pgvrx_rerank": (C.c_int, [vp, vp, i64, vp, i32, i32, vp, vp]),
+        "pgvrx_rerank_device": (C.c_int, [vp, vp, i64, vp, i32, i32, i64, vp, vp, vp]),
+        "pgvrx_topk_merge_device": (C.c_int, [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -291,3 +306,45 @@ class HnswIndex:
         self._check(self.L.pgvrx_search_batch_device(self.h, d_queries_ptr, nq, ef_search, k, d_ids_ptr, d_dists_ptr,
                                                      d_counts_ptr, C.byref(stats) if stats is not None else None,
                                                      C.c_void_p(stream) if stream else None))
+
+    # ---- exact paths (sequential scan ordered by the distance operator: the reference's ground truth) ----
+    def load_rows(self, rows):
+        """Vector table only (no graph): enough for flat_topk / rerank.  Cosine opclasses normalise the
+        rows like the build does (zero-norm rows are kept as zero rows here so that ids stay row numbers)."""
+        rows = _rows(self.elem, self.dim, rows)
+        if self.normalized:
+            rows = np.stack([normalize(self.elem, self.dim, r)[1] for r in rows]) if len(rows) else rows
+        self._check(self.L.pgvrx_index_load_rows(self.h, _p(rows), len(rows)))
+
+    def flat_topk(self, queries, k=10, with_stats=False):
+        """Exact k nearest rows per query, ordered by (distance, id)."""
+        q = self.prepare_queries(queries)
+        nq = len(q)
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        st = FlatStats()
+        self._check(self.L.pgvrx_flat_topk(self.h, _p(q), nq, k, _p(ids), _p(dists), C.byref(st) if with_stats else None))
+        return (ids, dists, st.as_dict()) if with_stats else (ids, dists)
+
+    def flat_topk_device(self, d_queries_ptr, nq, k, d_ids_ptr, d_dists_ptr, row_begin=0, row_end=-1, id_base=0, stream=0,
+                         stats=None):
+        self._check(self.L.pgvrx_flat_topk_device(self.h, d_queries_ptr, nq, k, row_begin, row_end, id_base, d_ids_ptr,
+                                                  d_dists_ptr, C.byref(stats) if stats is not None else None,
+                                                  C.c_void_p(stream) if stream else None))
+
+    def rerank(self, queries, cand_ids, k=10):
+        """Exact distances of each query's candidate ids (-1 = none); the k nearest by (distance, id)."""
+        q = self.prepare_queries(queries)
+        cand = np.ascontiguousarray(cand_ids, np.int32)
+        nq, nc = cand.shape
+        if nq != len(q):
+            raise PgvrxError(ERR_INVALID, "one candidate list per query expected")
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        self._check(self.L.pgvrx_rerank(self.h, _p(q), nq, _p(cand), nc, k, _p(ids), _p(dists)))
+        return ids, dists
+
+    def topk_merge_device(self, d_part_ids_ptr, d_part_dists_ptr, n_parts, nq, k_in, k_out, d_out_ids_ptr, d_out_dists_ptr,
+                          stream=0):
+        self._check(self.L.pgvrx_topk_merge_device(self.h, d_part_ids_ptr, d_part_dists_ptr, n_parts, nq, k_in, k_out,
+                                                   d_out_ids_ptr, d_out_dists_ptr, C.c_void_p(stream) if stream else None))

@@ -262,6 +262,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     CU_TRY(ix, ix->upper_base.ensure_keep(std::max<size_t>(16, (size_t)cap * 4), (size_t)g.n * 4));
     CU_TRY(ix, ix->level.ensure_keep(std::max<size_t>(16, (size_t)cap), (size_t)g.n));
     ix->loaded = false;
+    ix->rows_loaded = false;
 
     // ---- host mirror capacity ----
     g.values.reserve((size_t)(g.n + n_rows) * g.row_bytes);
@@ -614,6 +615,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     ix->entry = g.entry;
     ix->entry_level = g.entry_level;
     ix->loaded = true;
+    ix->rows_loaded = true;
     if (stats) {
         stats->n_rounds = n_rounds;
         stats->n_searched = n_searched;

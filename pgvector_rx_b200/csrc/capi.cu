@@ -357,7 +357,8 @@ void pgvrx_index_destroy(pgvrx_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->desc.device);
     DevBuf *bufs[] = {&ix->vectors, &ix->adj0, &ix->adj_up, &ix->upper_base, &ix->level, &ix->q, &ix->ids, &ix->dists,
-                      &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work, &ix->phase};
+                      &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work, &ix->phase,
+                      &ix->part_ids, &ix->part_dists, &ix->cand};
     for (DevBuf *b : bufs) b->release();
     if (ix->build) pgvrx_host::destroy_build_state(ix->build);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
@@ -391,6 +392,7 @@ int pgvrx_index_load_graph(pgvrx_index *ix, const void *rows, int64_t n, const u
 
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     ix->loaded = false;
+    ix->rows_loaded = false;
     CU_TRY(ix, ix->vectors.ensure(std::max<size_t>(16, (size_t)n * ix->row_stride)));
     CU_TRY(ix, ix->adj0.ensure(std::max<size_t>(16, (size_t)n * 2 * m * 4)));
     CU_TRY(ix, ix->adj_up.ensure(std::max<size_t>(16, (size_t)n_upper_rows * m * 4)));
@@ -416,6 +418,7 @@ int pgvrx_index_load_graph(pgvrx_index *ix, const void *rows, int64_t n, const u
     ix->entry = entry;
     ix->entry_level = n > 0 ? level[entry] : -1;
     ix->loaded = true;
+    ix->rows_loaded = true;
     return PGVRX_OK;
 }
 

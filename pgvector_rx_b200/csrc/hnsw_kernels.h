@@ -79,4 +79,51 @@ cudaError_t launch_scatter_rows(int32_t *dst, const int64_t *row_offsets, const 
                                 cudaStream_t stream);
 cudaError_t launch_collect_failed(const uint32_t *status, int nq, int32_t *qmap, int *n_work, cudaStream_t stream);
 
+
+// ---- K4 / K6 / re-rank (flat_knn.cu) ----------------------------------------------------------------
+constexpr int FLAT_THREADS = 128;   // one base row per thread per tile
+constexpr int FLAT_QT = 32;         // queries per CTA: one accumulator chain per (thread, query)
+constexpr int FLAT_CB = 512;        // bytes of a row staged per dimension chunk
+constexpr int FLAT_MAX_K = 1024;
+
+struct FlatGeom {
+    uint32_t chunk_bytes, rstride, q_chunk_bytes;
+    uint32_t rows_bytes, qs_bytes, list_bytes;
+    int n_chunks;
+};
+
+struct FlatParams {
+    const uint8_t *vectors;    // row 0 of the table (local row numbering)
+    uint32_t row_stride;
+    int64_t row_begin, row_end;   // rows [row_begin, row_end) are scanned
+    int64_t rows_per_split;       // multiple of FLAT_THREADS; blockIdx.y selects the split
+    int64_t id_base;              // reported id = id_base + (row - row_begin)
+    const uint8_t *queries;
+    uint32_t q_stride, q_bytes;
+    int nq, k;
+    int32_t *out_ids;          // [n_splits][nq][k], ascending (distance, id), -1 / +inf padded
+    float *out_dists;
+};
+
+struct RerankParams {
+    const uint8_t *vectors;
+    uint32_t row_stride, stage_stride;
+    int64_t n_rows, id_base;   // candidate ids are id_base + local row
+    const uint8_t *queries;
+    uint32_t q_stride, q_bytes;
+    const int32_t *cand;       // nq x nc, -1 = no candidate
+    int nq, nc, k, R;
+    int32_t *out_ids;          // nq x k
+    float *out_dists;
+};
+
+size_t flat_smem_bytes(int elem, uint32_t row_stride, int k, FlatGeom *out);
+cudaError_t flat_kernel_occupancy(int elem, int metric, size_t smem, int *blocks_per_sm);
+cudaError_t launch_flat_partial(int elem, int metric, const FlatParams &p, const FlatGeom &g, int n_qtiles, int n_splits,
+                                size_t smem, cudaStream_t stream);
+cudaError_t launch_topk_merge(const int32_t *ids, const float *dists, int n_parts, int nq, int k_in, int k_out,
+                              int32_t *out_ids, float *out_dists, cudaStream_t stream);
+size_t rerank_smem_bytes(uint32_t row_stride, uint32_t stage_stride, int R, int k);
+cudaError_t launch_rerank(int elem, int metric, const RerankParams &p, int grid, size_t smem, cudaStream_t stream);
+
 }  // namespace pgvrx

@@ -62,9 +62,11 @@ struct pgvrx_index {
     DevBuf vectors, adj0, adj_up, upper_base, level;
     int64_t n = 0, n_upper = 0, entry = -1;
     int entry_level = -1;
-    bool loaded = false;
+    bool loaded = false;        // graph + rows resident
+    bool rows_loaded = false;   // vector table resident (enough for the flat / re-rank paths)
     // scratch
     DevBuf q, ids, dists, counts, status, ctr, vis, vis_retry, qmap, work, phase;
+    DevBuf part_ids, part_dists, cand;   // flat kNN partial lists, re-rank candidates
     pgvrx_host::BuildState *build = nullptr;
     std::string err;
 };
