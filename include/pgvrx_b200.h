@@ -243,6 +243,27 @@ int pgvrx_topk_merge_device(pgvrx_index *idx, const int32_t *d_part_ids, const f
                             int32_t n_parts, int64_t nq, int32_t k_in, int32_t k_out, int32_t *d_out_ids,
                             float *d_out_dists, void *cuda_stream);
 
+/* ---- scan: iterative index scan (hnsw.iterative_scan = relaxed_order | strict_order) ------------- */
+/* A pgvrx_scan is what amrescan creates for a batch of queries: per query the visited set, the
+ * discarded heap, the tuple count and the strict-order watermark (HnswScanState, scan.rs:586-617)
+ * live in HBM behind it.  Each pgvrx_scan_next is, for every query, the block of amgettuple that
+ * refills `results` -- get_scan_items on the first call (scan.rs:458-530), then resume_scan_items
+ * (scan.rs:538-577), or the one-at-a-time drain of `discarded` once hnsw.max_scan_tuples elements
+ * were produced (scan.rs:831-841) -- followed by amgettuple's emission rules: nearest first, each
+ * element counts towards `tuples` (scan.rs:871), strict_order drops elements nearer than the last
+ * one emitted (scan.rs:801-806).  The caller maps element ids to heap TIDs (last to first,
+ * scan.rs:798) and stops asking for a query once its LIMIT is met. */
+typedef struct pgvrx_scan pgvrx_scan;
+int pgvrx_scan_begin(pgvrx_index *idx, const void *queries, int64_t nq, int32_t ef_search,
+                     int32_t iterative_mode /* pgvrx_iterative */, int64_t max_scan_tuples, pgvrx_scan **out);
+/* want_more: nq bytes or NULL (= all); a query with 0 is left untouched this round.
+ * out_ids / out_dists: nq * ef_search, emitted elements first, -1 / +inf padded; out_counts[q] = number
+ * emitted this round; out_done[q] = 1 once the scan of q is exhausted (later rounds emit nothing).
+ * PGVRX_ITER_OFF emits get_scan_items' batch and is then done.  HOST buffers. */
+int pgvrx_scan_next(pgvrx_scan *scan, const uint8_t *want_more, int32_t *out_ids, float *out_dists,
+                    int32_t *out_counts, uint8_t *out_done, pgvrx_search_stats *stats /* may be NULL */);
+void pgvrx_scan_end(pgvrx_scan *scan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,7 @@ EXPORTS = [
     "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export", "pgvrx_index_build",
     "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
+    "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end",
 ]
 
 
@@ -126,6 +127,9 @@ def lib():
         "pgvrx_rerank": (C.c_int, [vp, vp, i64, vp, i32, i32, vp, vp]),
         "pgvrx_rerank_device": (C.c_int, [vp, vp, i64, vp, i32, i32, i64, vp, vp, vp]),
         "pgvrx_topk_merge_device": (C.c_int, [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]),
+        "pgvrx_scan_begin": (C.c_int, [vp, vp, i64, i32, i32, i64, C.POINTER(vp)]),
+        "pgvrx_scan_next": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(SearchStats)]),
+        "pgvrx_scan_end": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -348,3 +352,65 @@ class HnswIndex:
                           stream=0):
         self._check(self.L.pgvrx_topk_merge_device(self.h, d_part_ids_ptr, d_part_dists_ptr, n_parts, nq, k_in, k_out,
                                                    d_out_ids_ptr, d_out_dists_ptr, C.c_void_p(stream) if stream else None))
+
+    # ---- iterative scan (hnsw.iterative_scan, hnsw.max_scan_tuples: options.rs:85-91) ----
+    def scan_begin(self, queries, ef_search=None, iterative_scan=ITER_RELAXED, max_scan_tuples=20000):
+        return IterativeScan(self, queries, self.ef_search if ef_search is None else ef_search, iterative_scan,
+                             max_scan_tuples)
+
+
+class IterativeScan:
+    """amrescan .. amendscan for a batch of queries.  `next()` returns, per query, the next block of
+    elements in amgettuple's emission order; `stream(limit)` drives rounds until every query has
+    `limit` elements or is exhausted."""
+
+    def __init__(self, index, queries, ef_search, mode, max_scan_tuples):
+        self.ix, self.ef = index, ef_search
+        q = index.prepare_queries(queries)
+        self.nq = len(q)
+        h = C.c_void_p()
+        index._check(index.L.pgvrx_scan_begin(index.h, _p(q), self.nq, ef_search, mode, max_scan_tuples, C.byref(h)))
+        self.h = h
+        self.totals = dict(n_dist=0, n_expand0=0, n_expand_upper=0, n_visited=0, kernel_ms=0.0, rounds=0)
+
+    def next(self, want_more=None):
+        ids = np.empty((self.nq, self.ef), np.int32)
+        dists = np.empty((self.nq, self.ef), np.float32)
+        counts = np.empty(self.nq, np.int32)
+        done = np.empty(self.nq, np.uint8)
+        wm = None if want_more is None else np.ascontiguousarray(want_more, np.uint8)
+        st = SearchStats()
+        self.ix._check(self.ix.L.pgvrx_scan_next(self.h, _p(wm), _p(ids), _p(dists), _p(counts), _p(done), C.byref(st)))
+        for k in ("n_dist", "n_expand0", "n_expand_upper", "n_visited", "kernel_ms"):
+            self.totals[k] += getattr(st, k)
+        self.totals["rounds"] += 1
+        return ids, dists, counts, done.astype(bool)
+
+    def stream(self, limit):
+        """Per query: (element ids, distances) in emission order, at most `limit` (None = until exhausted)."""
+        out_i = [[] for _ in range(self.nq)]
+        out_d = [[] for _ in range(self.nq)]
+        have = np.zeros(self.nq, np.int64)
+        done = np.zeros(self.nq, bool)
+        while True:
+            want = ~done if limit is None else (~done & (have < limit))
+            if not want.any():
+                break
+            ids, dists, counts, d = self.next(want.astype(np.uint8))
+            for q in np.nonzero(want)[0]:
+                c = counts[q]
+                out_i[q].append(ids[q, :c])
+                out_d[q].append(dists[q, :c])
+                have[q] += c
+            done |= d
+        cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
+        res_i = [cat(p, np.int32)[:limit] for p in out_i]
+        res_d = [cat(p, np.float32)[:limit] for p in out_d]
+        return res_i, res_d
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ix.L.pgvrx_scan_end(self.h)
+            self.h = None
+
+    __del__ = close

@@ -32,7 +32,7 @@ enum : int { ELEM_F32 = 0, ELEM_F16 = 1, ELEM_BIT = 2 };
 enum : int { METRIC_L2SQ = 0, METRIC_NEG_IP = 1, METRIC_L1 = 2, METRIC_HAMMING = 3, METRIC_JACCARD = 4 };
 
 // per-query status bits (non-zero => the host re-runs the query with larger scratch)
-enum : uint32_t { ST_VIS_OVERFLOW = 1u, ST_TIE_OVERFLOW = 2u };
+enum : uint32_t { ST_VIS_OVERFLOW = 1u, ST_TIE_OVERFLOW = 2u, ST_POOL_OVERFLOW = 4u };
 
 
 // ------------------------------------------------------------------------------------------

@@ -126,4 +126,50 @@ cudaError_t launch_topk_merge(const int32_t *ids, const float *dists, int n_part
 size_t rerank_smem_bytes(uint32_t row_stride, uint32_t stage_stride, int R, int k);
 cudaError_t launch_rerank(int elem, int metric, const RerankParams &p, int grid, size_t smem, cudaStream_t stream);
 
+
+// ---- K3: iterative scan (hnsw_iter.cu) ------------------------------------------------------------------
+constexpr int ITER_CHUNK = 64;            // keys per chunk of a query's discarded chain
+constexpr int ITER_UP_ENTRIES = 4096;     // per-warp hashed visited table for the ef = 1 descent
+constexpr int ITER_TAIL_CAP = 1024;       // retained boundary ties behind W
+
+struct IterQueryState {
+    long long tuples;          // scan.rs:871
+    uint32_t prev_ord;         // ordered bits of previous_distance (scan.rs:801-806); 0 = -infinity
+    int round;                 // rounds this query has run
+    int head, tail, fill, live;   // discarded chain: first / last chunk (-1: none), keys in the last chunk, live keys
+    int done;
+    int pad;
+};
+
+struct IterParams {
+    const uint8_t *queries;
+    uint32_t q_stride, q_bytes;
+    int nq, ef, tail_cap;
+    int mode;                  // pgvrx_iterative
+    long long max_scan_tuples;
+    const uint8_t *want_more;  // nq or NULL
+    IterQueryState *state;
+    uint32_t *bitmap;          // nq x n_words visited bits
+    uint32_t n_words;
+    uint64_t *pool;            // discarded chunks
+    int *next;
+    int *pool_next;
+    int pool_cap;
+    uint32_t *vis_up;          // per warp slot, ITER_UP_ENTRIES
+    int32_t *out_ids;          // nq x ef
+    float *out_dists;
+    int32_t *out_counts;
+    uint8_t *out_done;
+    uint32_t *out_status;
+    uint32_t *out_ctr;         // nq x 4 or NULL
+    int *work_counter;
+    uint32_t stage_stride;
+    int R;
+};
+
+size_t iter_warp_smem(int R, uint32_t stage_stride, uint32_t row_stride, int ef, int tail_cap);
+cudaError_t iter_kernel_occupancy(int elem, int metric, size_t smem_block, int *blocks_per_sm);
+cudaError_t launch_iter_scan(int elem, int metric, const GraphView &g, const IterParams &p, int grid, size_t smem_block,
+                             cudaStream_t stream);
+
 }  // namespace pgvrx

@@ -128,7 +128,7 @@ def test_rerank_matches_brute_force_on_the_candidates(opclass, kind, dim):
     cand[3, :] = -1                       # a query without candidates returns nothing
     ids, dists = ix.rerank(q, cand, k=k)
     for i in range(len(q)):
-        c = cand[i][cand[i] >= 0]
+        c = np.sort(cand[i][cand[i] >= 0])     # ties are ordered by element id: rank the subset in id order
         if len(c) == 0:
             assert (ids[i] == -1).all() and np.isinf(dists[i]).all()
             continue
