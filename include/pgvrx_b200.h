@@ -212,6 +212,7 @@ int pgvrx_search_batch_device(pgvrx_index *idx, const void *d_queries, int64_t n
 typedef struct {
     uint64_t n_pairs;         /* (query, row) distance evaluations                                */
     uint64_t n_candidates;    /* rows re-ranked exactly (tensor-core path only)                   */
+    uint64_t n_uncertified;   /* queries the error bound could not certify, re-run on the exact path */
     uint32_t n_launches;
     uint32_t n_splits;        /* base-row splits merged per query                                 */
     uint32_t path;            /* 0 = sequential f32 chains on CUDA cores; 1 = 3xTF32 tcgen05 candidate
@@ -231,6 +232,10 @@ int pgvrx_flat_topk(pgvrx_index *idx, const void *queries, int64_t nq, int32_t k
 int pgvrx_flat_topk_device(pgvrx_index *idx, const void *d_queries, int64_t nq, int32_t k, int64_t row_begin,
                            int64_t row_end, int64_t id_base, int32_t *d_ids, float *d_dists,
                            pgvrx_flat_stats *stats, void *cuda_stream);
+/* Diagnostic of the tensor-core path (fp32 L2 / inner product): the approximate distances it ranks
+ * candidates by (nq x n, HOST) and, per query, the bound eps it certifies against
+ * (|approximate - exact| <= eps is what makes the final result exact). */
+int pgvrx_flat_tc_scores(pgvrx_index *idx, const void *queries, int64_t nq, float *out_scores, float *out_eps);
 /* Exact re-rank: cand_ids is nq x nc element ids (-1 = none); returns the k nearest of each list by
  * exact distance, ordered by (distance, id). */
 int pgvrx_rerank(pgvrx_index *idx, const void *queries, int64_t nq, const int32_t *cand_ids, int32_t nc,

@@ -41,7 +41,7 @@ EXPORTS = [
     "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export", "pgvrx_index_build",
     "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
-    "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end",
+    "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores",
 ]
 
 
@@ -83,7 +83,7 @@ class SearchStats(C.Structure):
 
 
 class FlatStats(C.Structure):
-    _fields_ = [("n_pairs", C.c_uint64), ("n_candidates", C.c_uint64), ("n_launches", C.c_uint32),
+    _fields_ = [("n_pairs", C.c_uint64), ("n_candidates", C.c_uint64), ("n_uncertified", C.c_uint64), ("n_launches", C.c_uint32),
                 ("n_splits", C.c_uint32), ("path", C.c_uint32), ("kernel_ms", C.c_float)]
 
     def as_dict(self):
@@ -127,6 +127,7 @@ def lib():
         "pgvrx_rerank": (C.c_int, [vp, vp, i64, vp, i32, i32, vp, vp]),
         "pgvrx_rerank_device": (C.c_int, [vp, vp, i64, vp, i32, i32, i64, vp, vp, vp]),
         "pgvrx_topk_merge_device": (C.c_int, [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]),
+        "pgvrx_flat_tc_scores": (C.c_int, [vp, vp, i64, vp, vp]),
         "pgvrx_scan_begin": (C.c_int, [vp, vp, i64, i32, i32, i64, C.POINTER(vp)]),
         "pgvrx_scan_next": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(SearchStats)]),
         "pgvrx_scan_end": (None, [vp]),
@@ -335,6 +336,14 @@ class HnswIndex:
         self._check(self.L.pgvrx_flat_topk_device(self.h, d_queries_ptr, nq, k, row_begin, row_end, id_base, d_ids_ptr,
                                                   d_dists_ptr, C.byref(stats) if stats is not None else None,
                                                   C.c_void_p(stream) if stream else None))
+
+    def flat_tc_scores(self, queries):
+        """Approximate distances of the tensor-core path and its per-query certification bound (diagnostic)."""
+        q = self.prepare_queries(queries)
+        scores = np.empty((len(q), len(self)), np.float32)
+        eps = np.empty(len(q), np.float32)
+        self._check(self.L.pgvrx_flat_tc_scores(self.h, _p(q), len(q), _p(scores), _p(eps)))
+        return scores, eps
 
     def rerank(self, queries, cand_ids, k=10):
         """Exact distances of each query's candidate ids (-1 = none); the k nearest by (distance, id)."""

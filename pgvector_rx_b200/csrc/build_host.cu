@@ -263,6 +263,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     CU_TRY(ix, ix->level.ensure_keep(std::max<size_t>(16, (size_t)cap), (size_t)g.n));
     ix->loaded = false;
     ix->rows_loaded = false;
+    ix->tc_ready = false;
 
     // ---- host mirror capacity ----
     g.values.reserve((size_t)(g.n + n_rows) * g.row_bytes);

@@ -358,7 +358,9 @@ void pgvrx_index_destroy(pgvrx_index *ix) {
     cudaSetDevice(ix->desc.device);
     DevBuf *bufs[] = {&ix->vectors, &ix->adj0, &ix->adj_up, &ix->upper_base, &ix->level, &ix->q, &ix->ids, &ix->dists,
                       &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work, &ix->phase,
-                      &ix->part_ids, &ix->part_dists, &ix->cand};
+                      &ix->part_ids, &ix->part_dists, &ix->cand, &ix->tc_xhi, &ix->tc_xlo, &ix->tc_xnorm, &ix->tc_xmax,
+                      &ix->tc_qhi, &ix->tc_qlo, &ix->tc_qnorm, &ix->tc_cand, &ix->tc_bound, &ix->tc_uncert, &ix->tc_cnt,
+                      &ix->tc_fq, &ix->tc_fids, &ix->tc_fdists, &ix->tc_dbg};
     for (DevBuf *b : bufs) b->release();
     if (ix->build) pgvrx_host::destroy_build_state(ix->build);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
@@ -393,6 +395,7 @@ int pgvrx_index_load_graph(pgvrx_index *ix, const void *rows, int64_t n, const u
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     ix->loaded = false;
     ix->rows_loaded = false;
+    ix->tc_ready = false;
     CU_TRY(ix, ix->vectors.ensure(std::max<size_t>(16, (size_t)n * ix->row_stride)));
     CU_TRY(ix, ix->adj0.ensure(std::max<size_t>(16, (size_t)n * 2 * m * 4)));
     CU_TRY(ix, ix->adj_up.ensure(std::max<size_t>(16, (size_t)n_upper_rows * m * 4)));

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -41,8 +42,15 @@ int flat_plan(pgvrx_index *ix, int64_t nq, int k, int64_t n_rows, FlatPlan *out)
     return PGVRX_OK;
 }
 
-int flat_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k, int64_t row_begin, int64_t row_end, int64_t id_base,
-              int32_t *d_ids, float *d_dists, pgvrx_flat_stats *stats, cudaStream_t stream) {
+}  // namespace
+
+bool pgvrx_flat_tc_eligible(const pgvrx_index *ix, int64_t nq, int k);
+int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k, int64_t id_base, int32_t *d_ids, float *d_dists,
+                       pgvrx_flat_stats *stats, float *d_dbg_scores, cudaStream_t stream);
+
+// K4a: sequential f32 chains on the CUDA cores (every opclass, any k up to 1024, any row range)
+int pgvrx_flat_exact_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k, int64_t row_begin, int64_t row_end,
+                          int64_t id_base, int32_t *d_ids, float *d_dists, pgvrx_flat_stats *stats, cudaStream_t stream) {
     if (!ix->rows_loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "no rows loaded");
     if (k < 1 || k > FLAT_MAX_K) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "k must be between 1 and 1024");
     if (nq < 0 || nq > (int64_t)1 << 30) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "bad nq");
@@ -104,6 +112,22 @@ int flat_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k, int64_t
     return PGVRX_OK;
 }
 
+namespace {
+
+// Which kernel serves a flat request.  The tensor cores take large fp32 L2 / inner-product batches over the
+// whole table (north star item 3); everything else -- and whatever the error bound cannot certify -- runs on the
+// exact CUDA-core kernel.  PGVRX_FLAT_PATH=exact|tc pins the choice (tests, benchmarks).
+int flat_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k, int64_t row_begin, int64_t row_end, int64_t id_base,
+              int32_t *d_ids, float *d_dists, pgvrx_flat_stats *stats, cudaStream_t stream) {
+    if (!ix->rows_loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "no rows loaded");
+    bool tc = row_begin == 0 && row_end == ix->n && k >= 1 && pgvrx_flat_tc_eligible(ix, nq, k);
+    const char *pin = getenv("PGVRX_FLAT_PATH");
+    if (pin && !strcmp(pin, "exact")) tc = false;
+    else if (!(pin && !strcmp(pin, "tc"))) tc = tc && nq >= 512 && ix->n >= 16384;
+    if (tc) return pgvrx_flat_tc_core(ix, d_queries, nq, k, id_base, d_ids, d_dists, stats, nullptr, stream);
+    return pgvrx_flat_exact_core(ix, d_queries, nq, k, row_begin, row_end, id_base, d_ids, d_dists, stats, stream);
+}
+
 }  // namespace
 
 extern "C" {
@@ -116,6 +140,7 @@ int pgvrx_index_load_rows(pgvrx_index *ix, const void *rows, int64_t n) {
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     ix->loaded = false;
     ix->rows_loaded = false;
+    ix->tc_ready = false;
     CU_TRY(ix, ix->vectors.ensure(std::max<size_t>(16, (size_t)n * ix->row_stride)));
     if (n > 0) {
         if (ix->row_stride == ix->row_bytes) {

@@ -1,0 +1,363 @@
+// flat_tc.cu -- K4b: candidate generation for the exact flat kNN of large fp32 L2 / inner-product batches on
+// the 5th-generation tensor cores, as a 3xTF32 split GEMM:
+//
+//     q . x  ~=  q_hi . x_hi + q_hi . x_lo + q_lo . x_hi        (q = q_hi + q_lo + O(2^-22 |q|), same for x)
+//
+// with tf32 operands staged in shared memory by TMA (128-byte swizzle, K-major), tcgen05.mma (kind::tf32,
+// M = 128 queries x N = 128 base rows per instruction group) accumulating in TMEM, and an epilogue that reads
+// the accumulator back with tcgen05.ld, forms the approximate distance and keeps the KP nearest rows of each
+// query.  The result is NOT the answer: the candidates are re-ranked with the reference's exact sequential
+// arithmetic (rerank_kernel), and a query is only accepted when the error bound proves that no row outside
+// its candidate list can belong to the top k (tc_certify_kernel); otherwise it is re-run on the exact path.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2-5 =
+// epilogue (one TMEM lane quarter each; thread <-> query row).  Three pipelines: smem full/empty,
+// TMEM full/empty (two 128-column accumulators), and a static persistent schedule over (query tile, base split).
+#include <cuda.h>
+
+#include "hnsw_device.cuh"
+#include "hnsw_kernels.h"
+
+namespace pgvrx {
+
+constexpr int TC_TILE_BYTES = TC_M * TC_KB * 4;          // one 128 x 32 fp32 operand tile (16 KiB)
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;        // q_hi, q_lo, x_hi, x_lo
+constexpr uint32_t TC_TMEM_COLS = 256;                   // two accumulators of TC_N fp32 columns
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile with 128-byte swizzle: rows are 128 B (32 tf32), 8-row groups are 1024 B apart
+// (cute::UMMA::SmemDescriptor: start >> 4 | LBO 1 | SBO 64 << 32 | version 1 << 46 | SWIZZLE_128B (2) << 61)
+__device__ __forceinline__ uint64_t tc_smem_desc(const void *tile) {
+    const uint32_t a = smem_u32(tile);
+    return (uint64_t)((a & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format TF32 (2) @7/@10, K-major both, N >> 3 @17, M >> 4 @24
+__device__ __forceinline__ uint32_t tc_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- operand preparation: a -> (tf32 hi, tf32 lo) and |a|^2 -------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// one warp per row; rows beyond n_rows (padding up to a tile multiple) and columns beyond dim are zero
+__global__ void __launch_bounds__(256) tc_split_kernel(const uint8_t *__restrict__ src, uint32_t src_stride, int64_t n_rows,
+                                                       int64_t n_pad, int dim, int d_pad, float *__restrict__ hi,
+                                                       float *__restrict__ lo, float *__restrict__ norm, uint32_t *norm_max) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_pad) return;
+    const float *a = reinterpret_cast<const float *>(src + (size_t)row * src_stride);
+    float s = 0.0f;
+    for (int j = lane; j < d_pad; j += 32) {
+        float v = (row < n_rows && j < dim) ? a[j] : 0.0f;
+        const float h = to_tf32(v);
+        const float l = to_tf32(__fsub_rn(v, h));
+        hi[(size_t)row * d_pad + j] = h;
+        lo[(size_t)row * d_pad + j] = l;
+        s = __fmaf_rn(v, v, s);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) {
+        norm[row] = s;
+        if (norm_max) atomicMax(norm_max, __float_as_uint(s));     // s >= 0: float order == unsigned order
+    }
+}
+
+// ---- the GEMM + top-KP kernel -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+               const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo, TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128-byte swizzle atoms
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *stages = smem;                                                   // TC_STAGES x (q_hi | q_lo | x_hi | x_lo)
+    float *sxn = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES); // 2 x TC_N row norms
+    uint64_t *lists = reinterpret_cast<uint64_t *>(sxn + 2 * TC_N);           // 128 x KP keys
+    uint64_t *bars = lists + (size_t)TC_M * p.kp;
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES, *tempty = bars + 2 * TC_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, TC_M); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_units = p.n_mtiles * p.n_splits;
+    const int n_kb = p.d_pad / TC_KB;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint64_t pol_x = l2_policy_evict_first(), pol_q = l2_policy_evict_last();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
+                const int nt0 = sp * p.ntiles_per_split;
+                const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
+                for (int nt = nt0; nt < nt1; nt++) {
+                    for (int kb = 0; kb < n_kb; kb++) {
+                        mbar_wait(empty + stage, phase ^ 1u);
+                        uint8_t *st = stages + (size_t)stage * TC_STAGE_BYTES;
+                        mbar_arrive_expect_tx(full + stage, TC_STAGE_BYTES);
+                        tma_load_2d(st, &map_qhi, kb * TC_KB, mt * TC_M, full + stage, pol_q);
+                        tma_load_2d(st + TC_TILE_BYTES, &map_qlo, kb * TC_KB, mt * TC_M, full + stage, pol_q);
+                        tma_load_2d(st + 2 * TC_TILE_BYTES, &map_xhi, kb * TC_KB, nt * TC_N, full + stage, pol_x);
+                        tma_load_2d(st + 3 * TC_TILE_BYTES, &map_xlo, kb * TC_KB, nt * TC_N, full + stage, pol_x);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc();
+            int stage = 0, buf = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int sp = u / p.n_mtiles;
+                const int nt0 = sp * p.ntiles_per_split;
+                const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
+                for (int nt = nt0; nt < nt1; nt++) {
+                    mbar_wait(tempty + buf, aphase ^ 1u);          // the epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_N;
+                    for (int kb = 0; kb < n_kb; kb++) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint8_t *st = stages + (size_t)stage * TC_STAGE_BYTES;
+                        const uint64_t qhi = tc_smem_desc(st), qlo = tc_smem_desc(st + TC_TILE_BYTES);
+                        const uint64_t xhi = tc_smem_desc(st + 2 * TC_TILE_BYTES), xlo = tc_smem_desc(st + 3 * TC_TILE_BYTES);
+                        // small cross terms first, then the main product (8 tf32 = 32 bytes = +2 in the descriptor per K step)
+#pragma unroll
+                        for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32(d_tmem, qlo + 2 * k, xhi + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32(d_tmem, qhi + 2 * k, xlo + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32(d_tmem, qhi + 2 * k, xhi + 2 * k, idesc, 1u);
+                        tc_commit(empty + stage);                   // frees the smem slot when these MMAs retire
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(tfull + buf);                         // accumulator complete
+                    buf ^= 1;
+                    if (buf == 0) aphase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> approximate distance -> per-query top-KP =====
+        const int quarter = warp & 3;                               // TMEM lanes [32 * quarter, +32) belong to this warp
+        const int r = quarter * 32 + lane;                          // query row inside the tile
+        const int et = (warp - 2) * 32 + lane;                      // 0..127 among the epilogue threads
+        uint64_t *L = lists + (size_t)r * p.kp;
+        int buf = 0;
+        uint32_t aphase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
+            const int nt0 = sp * p.ntiles_per_split;
+            const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
+            const int q = mt * TC_M + r;
+            const bool qvalid = q < p.nq;
+            const float qn = qvalid ? p.qnorm[q] : 0.0f;
+            int len = 0;
+            uint64_t tau = ~0ull;
+            for (int nt = nt0; nt < nt1; nt++) {
+                const int64_t row0 = (int64_t)nt * TC_N;
+                sxn[buf * TC_N + et] = p.xnorm[row0 + et];
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+                mbar_wait(tfull + buf, aphase);
+                tc_fence_after();
+                for (int c = 0; c < TC_N; c += 32) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_N + c), v);
+                    if (p.dbg_scores) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int64_t row = row0 + c + j;
+                            if (qvalid && row < p.n_rows) {
+                                const float s = __uint_as_float(v[j]);
+                                p.dbg_scores[(size_t)q * p.n_rows + row] =
+                                    p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int64_t row = row0 + c + j;
+                        const float s = __uint_as_float(v[j]);
+                        const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
+                        const uint64_t key = ((uint64_t)f32_ord(dist) << 32) | (uint32_t)row;
+                        if (qvalid && row < p.n_rows && key < tau) {
+                            // thread-private insertion into the ascending list (rare once the list has warmed up)
+                            int pos = len < p.kp ? len : p.kp - 1;
+                            while (pos > 0 && L[pos - 1] > key) { L[pos] = L[pos - 1]; pos--; }
+                            L[pos] = key;
+                            if (len < p.kp) len++;
+                            if (len == p.kp) tau = L[p.kp - 1];
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty + buf);
+                buf ^= 1;
+                if (buf == 0) aphase ^= 1u;
+            }
+            if (qvalid) {
+                const size_t o = ((size_t)q * p.n_splits + sp) * p.kp;
+                for (int i = 0; i < p.kp; i++) p.cand_ids[o + i] = i < len ? (int32_t)(uint32_t)L[i] + (int32_t)p.id_base : -1;
+                // every row of this split that was not kept has an approximate distance >= this bound
+                p.cand_bound[(size_t)sp * p.nq + q] = len == p.kp ? ord_f32((uint32_t)(L[p.kp - 1] >> 32)) : __int_as_float(0x7f800000);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- certification ---------------------------------------------------------------------------------------------
+// A query's exact top-k (from the re-rank of its candidates) is final when every row outside the candidate lists
+// is provably further away than its k-th result: exact(r) >= approx(r) - eps >= min_s bound_s - eps > E_k.
+__global__ void tc_certify_kernel(const float *__restrict__ topk_dists, const int32_t *__restrict__ topk_ids, int k,
+                                  const float *__restrict__ cand_bound, int n_splits, int nq, const float *__restrict__ qnorm,
+                                  const uint32_t *__restrict__ xnorm_max, float eps_rel, int metric, int32_t *uncert_list,
+                                  int *n_uncert) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float bound = __int_as_float(0x7f800000);
+    for (int s = 0; s < n_splits; s++) bound = fminf(bound, cand_bound[(size_t)s * nq + q]);
+    bool ok = true;
+    if (bound < __int_as_float(0x7f800000)) {
+        const float xm = __uint_as_float(*xnorm_max);
+        const float eps = eps_rel * (qnorm[q] + xm);
+        // the k-th result must exist and lie strictly inside the certified radius
+        ok = topk_ids[(size_t)q * k + (k - 1)] >= 0 && topk_dists[(size_t)q * k + (k - 1)] < bound - eps;
+    }
+    if (!ok) uncert_list[atomicAdd(n_uncert, 1)] = q;
+    (void)metric;
+}
+
+// gather / scatter of the few queries that have to be re-run on the exact path
+__global__ void tc_gather_queries_kernel(const uint8_t *__restrict__ q, uint32_t q_stride, const int32_t *__restrict__ list, int n,
+                                         uint8_t *__restrict__ out) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const uint8_t *src = q + (size_t)list[i] * q_stride;
+    for (uint32_t b = threadIdx.x; b < q_stride; b += blockDim.x) out[(size_t)i * q_stride + b] = src[b];
+}
+__global__ void tc_scatter_results_kernel(const int32_t *__restrict__ ids, const float *__restrict__ dists, int k,
+                                          const int32_t *__restrict__ list, int n, int32_t *out_ids, float *out_dists) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        out_ids[(size_t)list[i] * k + j] = ids[(size_t)i * k + j];
+        out_dists[(size_t)list[i] * k + j] = dists[(size_t)i * k + j];
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------------------
+size_t tc_smem_bytes(int kp) {
+    return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * TC_N * 4 + (size_t)TC_M * kp * 8 + (2 * TC_STAGES + 4) * 8 + 16;
+}
+
+cudaError_t launch_tc_split(const uint8_t *src, uint32_t src_stride, int64_t n_rows, int64_t n_pad, int dim, int d_pad, float *hi,
+                            float *lo, float *norm, uint32_t *norm_max, cudaStream_t stream) {
+    if (n_pad <= 0) return cudaSuccess;
+    tc_split_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, stream>>>(src, src_stride, n_rows, n_pad, dim, d_pad, hi, lo, norm, norm_max);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_flat_tc(const void *map_qhi, const void *map_qlo, const void *map_xhi, const void *map_xlo, const TcParams &p,
+                           int grid, cudaStream_t stream) {
+    const size_t smem = tc_smem_bytes(p.kp);
+    cudaError_t e = cudaFuncSetAttribute(flat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    flat_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(*reinterpret_cast<const CUtensorMap *>(map_qhi),
+                                                       *reinterpret_cast<const CUtensorMap *>(map_qlo),
+                                                       *reinterpret_cast<const CUtensorMap *>(map_xhi),
+                                                       *reinterpret_cast<const CUtensorMap *>(map_xlo), p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
+                              const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, int32_t *uncert_list,
+                              int *n_uncert, cudaStream_t stream) {
+    tc_certify_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(topk_dists, topk_ids, k, cand_bound, n_splits, nq, qnorm, xnorm_max,
+                                                            eps_rel, metric, uncert_list, n_uncert);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tc_gather_queries(const uint8_t *q, uint32_t q_stride, const int32_t *list, int n, uint8_t *out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    tc_gather_queries_kernel<<<n, 128, 0, stream>>>(q, q_stride, list, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tc_scatter_results(const int32_t *ids, const float *dists, int k, const int32_t *list, int n, int32_t *out_ids,
+                                      float *out_dists, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    tc_scatter_results_kernel<<<n, 32, 0, stream>>>(ids, dists, k, list, n, out_ids, out_dists);
+    return cudaGetLastError();
+}
+
+}  // namespace pgvrx

@@ -172,4 +172,39 @@ cudaError_t iter_kernel_occupancy(int elem, int metric, size_t smem_block, int *
 cudaError_t launch_iter_scan(int elem, int metric, const GraphView &g, const IterParams &p, int grid, size_t smem_block,
                              cudaStream_t stream);
 
+
+// ---- K4b: 3xTF32 tcgen05 candidate generation (flat_tc.cu) ------------------------------------------------
+constexpr int TC_M = 128;          // queries per tile (UMMA M)
+constexpr int TC_N = 128;          // base rows per tile (UMMA N)
+constexpr int TC_KB = 32;          // fp32 elements per K block = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 192;    // TMA warp, MMA warp, four epilogue warps
+constexpr int TC_KP = 32;          // candidates kept per (query, split)
+constexpr int TC_MAX_K = 24;       // largest k served by the tensor-core path
+
+struct TcParams {
+    int nq, n_mtiles;
+    int64_t n_rows;                // valid base rows (the operand arrays are padded to n_ntiles * TC_N)
+    int n_ntiles, n_splits, ntiles_per_split;
+    int d_pad, kp, metric;
+    int64_t id_base;
+    const float *qnorm;            // |q|^2, padded to n_mtiles * TC_M
+    const float *xnorm;            // |x|^2, padded
+    int32_t *cand_ids;             // [nq][n_splits][kp] global ids, -1 padded
+    float *cand_bound;             // [n_splits][nq]: approximate distance every unkept row of the split is at least
+    float *dbg_scores;             // nq x n_rows approximate distances (diagnostic) or NULL
+};
+
+size_t tc_smem_bytes(int kp);
+cudaError_t launch_tc_split(const uint8_t *src, uint32_t src_stride, int64_t n_rows, int64_t n_pad, int dim, int d_pad, float *hi,
+                            float *lo, float *norm, uint32_t *norm_max, cudaStream_t stream);
+cudaError_t launch_flat_tc(const void *map_qhi, const void *map_qlo, const void *map_xhi, const void *map_xlo, const TcParams &p,
+                           int grid, cudaStream_t stream);
+cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
+                              const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, int32_t *uncert_list,
+                              int *n_uncert, cudaStream_t stream);
+cudaError_t launch_tc_gather_queries(const uint8_t *q, uint32_t q_stride, const int32_t *list, int n, uint8_t *out, cudaStream_t stream);
+cudaError_t launch_tc_scatter_results(const int32_t *ids, const float *dists, int k, const int32_t *list, int n, int32_t *out_ids,
+                                      float *out_dists, cudaStream_t stream);
+
 }  // namespace pgvrx
