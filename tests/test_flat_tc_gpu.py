@@ -79,11 +79,13 @@ def test_tc_ragged_shapes(tc_path, n, dim, nq, k):
 
 
 def test_tc_ties_fall_back_to_exact(tc_path):
-    # integer lattice: exact distance ties everywhere, so the bound cannot certify most queries;
-    # they are re-run on the exact path and the result is still the oracle's (ties by id)
-    rows = np.array([[i, j, 0, 0] for i in range(40) for j in range(40)], np.float32)
-    q = np.array([[3, 3, 0, 0], [10.5, 7.5, 0, 0], [0, 0, 0, 0], [39, 39, 0, 0]] * 8, np.float32)
-    st = tc_case("vector_l2_ops", O.L2SQ, None, 4, None, 10, rows=rows, q=q, max_uncert=1.0)
+    # 64 rows at exactly the same distance from the query: the k-th neighbour ties with every candidate the kernel
+    # kept and with rows it did not keep, so the bound cannot certify the query; it is re-run on the exact path
+    # and the result is still the oracle's (ties by id)
+    eye = np.eye(64, dtype=np.float32)
+    rows = np.concatenate([eye, 2 * eye, 3 * eye])
+    q = np.concatenate([np.zeros((1, 64), np.float32), make_rows("f32", 31, 64, 5)])
+    st = tc_case("vector_l2_ops", O.L2SQ, None, 64, None, 10, rows=rows, q=q, max_uncert=1.0)
     assert st["n_uncertified"] > 0
 
 
