@@ -203,10 +203,14 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         }
     } else {
         // ===== epilogue: TMEM -> registers -> approximate distance -> per-query top-KP =====
+        // Thread <-> query row for the arithmetic; the candidate set of a query is an UNORDERED set of TC_KP = 32
+        // keys in shared memory, one per lane, maintained by the whole warp: a qualifying element replaces the
+        // set's maximum (two REDUX per 32-bit half), so an insertion is ~20 warp instructions with no divergent
+        // loop.  Qualifying elements are rare once the sets have warmed up (KP * ln(rows / KP) per query).
         const int quarter = warp & 3;                               // TMEM lanes [32 * quarter, +32) belong to this warp
         const int r = quarter * 32 + lane;                          // query row inside the tile
         const int et = (warp - 2) * 32 + lane;                      // 0..127 among the epilogue threads
-        uint64_t *L = lists + (size_t)r * p.kp;
+        uint64_t *Lw = lists + (size_t)(quarter * 32) * TC_KP;      // this warp's 32 sets: set i = Lw[i * 32 + lane]
         int buf = 0;
         uint32_t aphase = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -216,41 +220,55 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             const int q = mt * TC_M + r;
             const bool qvalid = q < p.nq;
             const float qn = qvalid ? p.qnorm[q] : 0.0f;
-            int len = 0;
-            uint64_t tau = ~0ull;
+            uint64_t tau = ~0ull;                                    // this lane's query: max of its set (all-ones = not full)
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) Lw[i * TC_KP + lane] = ~0ull;
+            __syncwarp();
             for (int nt = nt0; nt < nt1; nt++) {
                 const int64_t row0 = (int64_t)nt * TC_N;
                 sxn[buf * TC_N + et] = p.xnorm[row0 + et];
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
                 mbar_wait(tfull + buf, aphase);
                 tc_fence_after();
+                const int valid_cols = (int)min((int64_t)TC_N, p.n_rows - row0);   // rows beyond n_rows are padding
                 for (int c = 0; c < TC_N; c += 32) {
                     uint32_t v[32];
                     tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_N + c), v);
                     if (p.dbg_scores) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
-                            const int64_t row = row0 + c + j;
-                            if (qvalid && row < p.n_rows) {
+                            if (qvalid && c + j < valid_cols) {
                                 const float s = __uint_as_float(v[j]);
-                                p.dbg_scores[(size_t)q * p.n_rows + row] =
+                                p.dbg_scores[(size_t)q * p.n_rows + row0 + c + j] =
                                     p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
                             }
                         }
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        const int64_t row = row0 + c + j;
                         const float s = __uint_as_float(v[j]);
                         const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
-                        const uint64_t key = ((uint64_t)f32_ord(dist) << 32) | (uint32_t)row;
-                        if (qvalid && row < p.n_rows && key < tau) {
-                            // thread-private insertion into the ascending list (rare once the list has warmed up)
-                            int pos = len < p.kp ? len : p.kp - 1;
-                            while (pos > 0 && L[pos - 1] > key) { L[pos] = L[pos - 1]; pos--; }
-                            L[pos] = key;
-                            if (len < p.kp) len++;
-                            if (len == p.kp) tau = L[p.kp - 1];
+                        const uint32_t khi = f32_ord(dist), klo = (uint32_t)(row0 + c + j);
+                        const uint64_t key = ((uint64_t)khi << 32) | klo;
+                        uint32_t am = __ballot_sync(FULL, qvalid && c + j < valid_cols && key < tau);
+                        while (am) {
+                            const int src = __ffs(am) - 1;
+                            am &= am - 1;
+                            const uint32_t nhi = __shfl_sync(FULL, khi, src), nlo = __shfl_sync(FULL, klo, src);
+                            uint64_t cur = Lw[src * TC_KP + lane];
+                            uint32_t chi = (uint32_t)(cur >> 32), clo = (uint32_t)cur;
+                            // the set's maximum is replaced by the new key
+                            uint32_t mhi = __reduce_max_sync(FULL, chi);
+                            uint32_t mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
+                            const int owner = __ffs(__ballot_sync(FULL, chi == mhi && clo == mlo)) - 1;
+                            if (lane == owner) {
+                                chi = nhi; clo = nlo;
+                                Lw[src * TC_KP + lane] = ((uint64_t)nhi << 32) | nlo;
+                            }
+                            mhi = __reduce_max_sync(FULL, chi);
+                            mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
+                            if (lane == src) tau = ((uint64_t)mhi << 32) | mlo;
+                            __syncwarp();
                         }
                     }
                 }
@@ -259,12 +277,17 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                 buf ^= 1;
                 if (buf == 0) aphase ^= 1u;
             }
-            if (qvalid) {
-                const size_t o = ((size_t)q * p.n_splits + sp) * p.kp;
-                for (int i = 0; i < p.kp; i++) p.cand_ids[o + i] = i < len ? (int32_t)(uint32_t)L[i] + (int32_t)p.id_base : -1;
-                // every row of this split that was not kept has an approximate distance >= this bound
-                p.cand_bound[(size_t)sp * p.nq + q] = len == p.kp ? ord_f32((uint32_t)(L[p.kp - 1] >> 32)) : __int_as_float(0x7f800000);
+            __syncwarp();
+            // candidates of query (quarter * 32 + i), one per lane; -1 where the split had fewer than KP rows
+            for (int i = 0; i < 32; i++) {
+                const int qi = mt * TC_M + quarter * 32 + i;
+                if (qi >= p.nq) break;
+                const uint64_t cur = Lw[i * TC_KP + lane];
+                p.cand_ids[((size_t)qi * p.n_splits + sp) * TC_KP + lane] = cur == ~0ull ? -1 : (int32_t)((uint32_t)cur + (uint32_t)p.id_base);
             }
+            // every row of this split that was not kept has an approximate distance >= this bound
+            if (qvalid) p.cand_bound[(size_t)sp * p.nq + q] = tau == ~0ull ? __int_as_float(0x7f800000) : ord_f32((uint32_t)(tau >> 32));
+            __syncwarp();
         }
     }
     tc_fence_before();

@@ -96,7 +96,7 @@ TcPlan plan_tc(int sm_count, int64_t nq_pad, int64_t n_pad) {
         const int s_eff = (pl.n_ntiles + tps - 1) / tps;
         const long units = (long)pl.n_mtiles * s_eff;
         const long waves = (units + sm_count - 1) / sm_count;
-        const long cost = waves * tps;
+        const long cost = waves * tps + 10L * s_eff;      // each split adds KP candidates per query to the re-rank
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; pl.n_splits = s_eff; pl.tiles_per_split = tps; }
     }
     pl.grid = (int)std::min<long>((long)pl.n_mtiles * pl.n_splits, sm_count);
