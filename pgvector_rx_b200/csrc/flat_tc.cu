@@ -221,6 +221,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             const bool qvalid = q < p.nq;
             const float qn = qvalid ? p.qnorm[q] : 0.0f;
             uint64_t tau = ~0ull;                                    // this lane's query: max of its set (all-ones = not full)
+            float tau_f = __int_as_float(0x7f800000);                // the same threshold as a distance
 #pragma unroll 4
             for (int i = 0; i < 32; i++) Lw[i * TC_KP + lane] = ~0ull;
             __syncwarp();
@@ -244,31 +245,54 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                             }
                         }
                     }
+                    // fast path: one fused multiply-add and one compare per element, no cross-lane traffic
+                    uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const float s = __uint_as_float(v[j]);
                         const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
-                        const uint32_t khi = f32_ord(dist), klo = (uint32_t)(row0 + c + j);
-                        const uint64_t key = ((uint64_t)khi << 32) | klo;
-                        uint32_t am = __ballot_sync(FULL, qvalid && c + j < valid_cols && key < tau);
-                        while (am) {
-                            const int src = __ffs(am) - 1;
-                            am &= am - 1;
-                            const uint32_t nhi = __shfl_sync(FULL, khi, src), nlo = __shfl_sync(FULL, klo, src);
-                            uint64_t cur = Lw[src * TC_KP + lane];
-                            uint32_t chi = (uint32_t)(cur >> 32), clo = (uint32_t)cur;
-                            // the set's maximum is replaced by the new key
-                            uint32_t mhi = __reduce_max_sync(FULL, chi);
-                            uint32_t mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
-                            const int owner = __ffs(__ballot_sync(FULL, chi == mhi && clo == mlo)) - 1;
-                            if (lane == owner) {
-                                chi = nhi; clo = nlo;
-                                Lw[src * TC_KP + lane] = ((uint64_t)nhi << 32) | nlo;
+                        mask |= (dist <= tau_f ? 1u : 0u) << j;                 // superset of key < tau (ties resolved below)
+                    }
+                    const int nvalid = valid_cols - c;
+                    if (!qvalid || nvalid <= 0) mask = 0;
+                    else if (nvalid < 32) mask &= (1u << nvalid) - 1u;
+                    if (__ballot_sync(FULL, mask != 0)) {
+                        // slow path (rare once the sets have warmed up): column by column over the union of the masks
+                        uint32_t um = __reduce_or_sync(FULL, mask);
+                        while (um) {
+                            const int j = __ffs(um) - 1;
+                            um &= um - 1;
+                            uint32_t sv;
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(sv)
+                                         : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_N + c + j)));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            const float s = __uint_as_float(sv);
+                            const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
+                            const uint32_t khi = f32_ord(dist), klo = (uint32_t)(row0 + c + j);
+                            const uint64_t key = ((uint64_t)khi << 32) | klo;
+                            uint32_t am = __ballot_sync(FULL, ((mask >> j) & 1u) && key < tau);
+                            while (am) {
+                                const int src = __ffs(am) - 1;
+                                am &= am - 1;
+                                const uint32_t nhi = __shfl_sync(FULL, khi, src), nlo = __shfl_sync(FULL, klo, src);
+                                const uint64_t cur = Lw[src * TC_KP + lane];
+                                uint32_t chi = (uint32_t)(cur >> 32), clo = (uint32_t)cur;
+                                // the set's maximum is replaced by the new key
+                                uint32_t mhi = __reduce_max_sync(FULL, chi);
+                                uint32_t mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
+                                const int owner = __ffs(__ballot_sync(FULL, chi == mhi && clo == mlo)) - 1;
+                                if (lane == owner) {
+                                    chi = nhi; clo = nlo;
+                                    Lw[src * TC_KP + lane] = ((uint64_t)nhi << 32) | nlo;
+                                }
+                                mhi = __reduce_max_sync(FULL, chi);
+                                mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
+                                if (lane == src) {
+                                    tau = ((uint64_t)mhi << 32) | mlo;
+                                    tau_f = tau == ~0ull ? __int_as_float(0x7f800000) : ord_f32(mhi);
+                                }
+                                __syncwarp();
                             }
-                            mhi = __reduce_max_sync(FULL, chi);
-                            mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
-                            if (lane == src) tau = ((uint64_t)mhi << 32) | mlo;
-                            __syncwarp();
                         }
                     }
                 }
