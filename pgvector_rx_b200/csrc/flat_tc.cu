@@ -23,6 +23,8 @@ namespace pgvrx {
 constexpr int TC_TILE_BYTES = TC_M * TC_KB * 4;          // one 128 x 32 fp32 operand tile (16 KiB)
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;        // q_hi, q_lo, x_hi, x_lo
 constexpr uint32_t TC_TMEM_COLS = 256;                   // two accumulators of TC_N fp32 columns
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_A_RES_BYTES = 4 * 2 * TC_TILE_BYTES;    // resident query tile: up to 4 K blocks of (hi | lo)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -119,13 +121,16 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
     float *sxn = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES); // 2 x TC_N row norms
     uint64_t *lists = reinterpret_cast<uint64_t *>(sxn + 2 * TC_N);           // 128 x KP keys
     uint64_t *bars = lists + (size_t)TC_M * p.kp;
-    uint64_t *full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES, *tempty = bars + 2 * TC_STAGES + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+    uint64_t *full = bars, *empty = bars + TC_MAX_STAGES, *tfull = bars + 2 * TC_MAX_STAGES, *tempty = tfull + 2;
+    uint64_t *afull = tempty + 2, *aempty = afull + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aempty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < TC_MAX_STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, TC_M); }
+        mbar_init(afull, 1);
+        mbar_init(aempty, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -141,26 +146,46 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
     const int n_units = p.n_mtiles * p.n_splits;
     const int n_kb = p.d_pad / TC_KB;
 
+    // Operand staging.  When the whole K extent of a query tile fits (d_pad <= 128) the tile's q_hi / q_lo blocks
+    // stay resident for the unit and only x_hi / x_lo stream through the ring (half the shared-memory fill traffic);
+    // otherwise all four operand tiles of a K block share a ring slot.
+    const bool a_res = p.a_resident != 0;
+    const int n_stages = a_res ? (TC_STAGES * TC_STAGE_BYTES - TC_A_RES_BYTES) / (2 * TC_TILE_BYTES) : TC_STAGES;
+    const uint32_t stage_bytes = a_res ? 2u * TC_TILE_BYTES : (uint32_t)TC_STAGE_BYTES;
+    uint8_t *ring = a_res ? stages + TC_A_RES_BYTES : stages;
+
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             const uint64_t pol_x = l2_policy_evict_first(), pol_q = l2_policy_evict_last();
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, aph = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
                 const int nt0 = sp * p.ntiles_per_split;
                 const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
+                if (a_res) {
+                    mbar_wait(aempty, aph ^ 1u);                    // the MMAs of the previous unit are done with the query tile
+                    mbar_arrive_expect_tx(afull, (uint32_t)n_kb * 2u * TC_TILE_BYTES);
+                    for (int kb = 0; kb < n_kb; kb++) {
+                        tma_load_2d(stages + (size_t)kb * 2 * TC_TILE_BYTES, &map_qhi, kb * TC_KB, mt * TC_M, afull, pol_q);
+                        tma_load_2d(stages + (size_t)kb * 2 * TC_TILE_BYTES + TC_TILE_BYTES, &map_qlo, kb * TC_KB, mt * TC_M, afull, pol_q);
+                    }
+                    aph ^= 1u;
+                }
                 for (int nt = nt0; nt < nt1; nt++) {
                     for (int kb = 0; kb < n_kb; kb++) {
                         mbar_wait(empty + stage, phase ^ 1u);
-                        uint8_t *st = stages + (size_t)stage * TC_STAGE_BYTES;
-                        mbar_arrive_expect_tx(full + stage, TC_STAGE_BYTES);
-                        tma_load_2d(st, &map_qhi, kb * TC_KB, mt * TC_M, full + stage, pol_q);
-                        tma_load_2d(st + TC_TILE_BYTES, &map_qlo, kb * TC_KB, mt * TC_M, full + stage, pol_q);
-                        tma_load_2d(st + 2 * TC_TILE_BYTES, &map_xhi, kb * TC_KB, nt * TC_N, full + stage, pol_x);
-                        tma_load_2d(st + 3 * TC_TILE_BYTES, &map_xlo, kb * TC_KB, nt * TC_N, full + stage, pol_x);
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                        uint8_t *st = ring + (size_t)stage * stage_bytes;
+                        mbar_arrive_expect_tx(full + stage, stage_bytes);
+                        if (!a_res) {
+                            tma_load_2d(st, &map_qhi, kb * TC_KB, mt * TC_M, full + stage, pol_q);
+                            tma_load_2d(st + TC_TILE_BYTES, &map_qlo, kb * TC_KB, mt * TC_M, full + stage, pol_q);
+                            st += 2 * TC_TILE_BYTES;
+                        }
+                        tma_load_2d(st, &map_xhi, kb * TC_KB, nt * TC_N, full + stage, pol_x);
+                        tma_load_2d(st + TC_TILE_BYTES, &map_xlo, kb * TC_KB, nt * TC_N, full + stage, pol_x);
+                        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
@@ -170,11 +195,16 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
         if (lane == 0) {
             const uint32_t idesc = tc_idesc();
             int stage = 0, buf = 0;
-            uint32_t phase = 0, aphase = 0;
+            uint32_t phase = 0, aphase = 0, aph = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const int sp = u / p.n_mtiles;
                 const int nt0 = sp * p.ntiles_per_split;
                 const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
+                if (a_res) {
+                    mbar_wait(afull, aph);
+                    tc_fence_after();
+                    aph ^= 1u;
+                }
                 for (int nt = nt0; nt < nt1; nt++) {
                     mbar_wait(tempty + buf, aphase ^ 1u);          // the epilogue has drained this accumulator
                     tc_fence_after();
@@ -182,9 +212,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                     for (int kb = 0; kb < n_kb; kb++) {
                         mbar_wait(full + stage, phase);
                         tc_fence_after();
-                        const uint8_t *st = stages + (size_t)stage * TC_STAGE_BYTES;
-                        const uint64_t qhi = tc_smem_desc(st), qlo = tc_smem_desc(st + TC_TILE_BYTES);
-                        const uint64_t xhi = tc_smem_desc(st + 2 * TC_TILE_BYTES), xlo = tc_smem_desc(st + 3 * TC_TILE_BYTES);
+                        const uint8_t *st = ring + (size_t)stage * stage_bytes;
+                        const uint8_t *qa = a_res ? stages + (size_t)kb * 2 * TC_TILE_BYTES : st;
+                        const uint8_t *xb = a_res ? st : st + 2 * TC_TILE_BYTES;
+                        const uint64_t qhi = tc_smem_desc(qa), qlo = tc_smem_desc(qa + TC_TILE_BYTES);
+                        const uint64_t xhi = tc_smem_desc(xb), xlo = tc_smem_desc(xb + TC_TILE_BYTES);
                         // small cross terms first, then the main product (8 tf32 = 32 bytes = +2 in the descriptor per K step)
 #pragma unroll
                         for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32(d_tmem, qlo + 2 * k, xhi + 2 * k, idesc, (kb | k) != 0);
@@ -192,13 +224,14 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                         for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32(d_tmem, qhi + 2 * k, xlo + 2 * k, idesc, 1u);
 #pragma unroll
                         for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32(d_tmem, qhi + 2 * k, xhi + 2 * k, idesc, 1u);
-                        tc_commit(empty + stage);                   // frees the smem slot when these MMAs retire
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                        tc_commit(empty + stage);                   // frees the ring slot when these MMAs retire
+                        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit(tfull + buf);                         // accumulator complete
                     buf ^= 1;
                     if (buf == 0) aphase ^= 1u;
                 }
+                if (a_res) tc_commit(aempty);                       // the query tile may be overwritten once all of this retired
             }
         }
     } else {
@@ -364,7 +397,7 @@ __global__ void tc_scatter_results_kernel(const int32_t *__restrict__ ids, const
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
 size_t tc_smem_bytes(int kp) {
-    return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * TC_N * 4 + (size_t)TC_M * kp * 8 + (2 * TC_STAGES + 4) * 8 + 16;
+    return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * TC_N * 4 + (size_t)TC_M * kp * 8 + (2 * TC_MAX_STAGES + 6) * 8 + 16;
 }
 
 cudaError_t launch_tc_split(const uint8_t *src, uint32_t src_stride, int64_t n_rows, int64_t n_pad, int dim, int d_pad, float *hi,

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -152,6 +153,7 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     p.d_pad = d_pad;
     p.kp = TC_KP;
     p.metric = ix->desc.metric;
+    p.a_resident = (d_pad <= 4 * TC_KB && !getenv("PGVRX_TC_STREAM_Q")) ? 1 : 0;
     p.id_base = id_base;
     p.qnorm = (const float *)ix->tc_qnorm.p;
     p.xnorm = (const float *)ix->tc_xnorm.p;

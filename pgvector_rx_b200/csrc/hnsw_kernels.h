@@ -187,6 +187,7 @@ struct TcParams {
     int64_t n_rows;                // valid base rows (the operand arrays are padded to n_ntiles * TC_N)
     int n_ntiles, n_splits, ntiles_per_split;
     int d_pad, kp, metric;
+    int a_resident;                // d_pad <= 128: the query tile stays in shared memory for the whole unit
     int64_t id_base;
     const float *qnorm;            // |q|^2, padded to n_mtiles * TC_M
     const float *xnorm;            // |x|^2, padded
