@@ -360,7 +360,7 @@ void pgvrx_index_destroy(pgvrx_index *ix) {
                       &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work, &ix->phase,
                       &ix->part_ids, &ix->part_dists, &ix->cand, &ix->tc_xhi, &ix->tc_xlo, &ix->tc_xnorm, &ix->tc_xmax,
                       &ix->tc_qhi, &ix->tc_qlo, &ix->tc_qnorm, &ix->tc_cand, &ix->tc_bound, &ix->tc_uncert, &ix->tc_cnt,
-                      &ix->tc_fq, &ix->tc_fids, &ix->tc_fdists, &ix->tc_dbg};
+                      &ix->tc_fq, &ix->tc_fids, &ix->tc_fdists, &ix->tc_dbg, &ix->tc_hint};
     for (DevBuf *b : bufs) b->release();
     if (ix->build) pgvrx_host::destroy_build_state(ix->build);
     if (ix->ev0) cudaEventDestroy(ix->ev0);

@@ -89,7 +89,8 @@ __device__ __forceinline__ float to_tf32(float x) {
 // one warp per row; rows beyond n_rows (padding up to a tile multiple) and columns beyond dim are zero
 __global__ void __launch_bounds__(256) tc_split_kernel(const uint8_t *__restrict__ src, uint32_t src_stride, int64_t n_rows,
                                                        int64_t n_pad, int dim, int d_pad, float *__restrict__ hi,
-                                                       float *__restrict__ lo, float *__restrict__ norm, uint32_t *norm_max) {
+                                                       float *__restrict__ lo, float *__restrict__ norm, uint32_t *norm_max,
+                                                       uint32_t *hint_init) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n_pad) return;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const uint8_t *__restrict
     if (lane == 0) {
         norm[row] = s;
         if (norm_max) atomicMax(norm_max, __float_as_uint(s));     // s >= 0: float order == unsigned order
+        if (hint_init && row < n_rows) hint_init[row] = 0xFF800000u;   // f32_ord(+inf): no threshold known yet
     }
 }
 
@@ -255,15 +257,23 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             const float qn = qvalid ? p.qnorm[q] : 0.0f;
             uint64_t tau = ~0ull;                                    // this lane's query: max of its set (all-ones = not full)
             float tau_f = __int_as_float(0x7f800000);                // the same threshold as a distance
+            // Thresholds travel between the units of a query: hint[q] is the smallest full-set maximum any unit has
+            // reached so far.  Rejecting against it is sound because certification uses the minimum over all units'
+            // final maxima, which is <= every value the hint ever took.
+            float xn_cur = p.xnorm[(int64_t)nt0 * TC_N + et];
 #pragma unroll 4
             for (int i = 0; i < 32; i++) Lw[i * TC_KP + lane] = ~0ull;
             __syncwarp();
             for (int nt = nt0; nt < nt1; nt++) {
                 const int64_t row0 = (int64_t)nt * TC_N;
-                sxn[buf * TC_N + et] = p.xnorm[row0 + et];
+                sxn[buf * TC_N + et] = xn_cur;
+                if (nt + 1 < nt1) xn_cur = p.xnorm[row0 + TC_N + et];          // in flight while this tile is processed
+                const uint32_t hint_ord = qvalid ? __ldcg(p.hint + q) : 0xFF800000u;
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
                 mbar_wait(tfull + buf, aphase);
                 tc_fence_after();
+                const float hint_f = ord_f32(hint_ord);
+                float thr_f = fminf(tau_f, hint_f);
                 const int valid_cols = (int)min((int64_t)TC_N, p.n_rows - row0);   // rows beyond n_rows are padding
                 for (int c = 0; c < TC_N; c += 32) {
                     uint32_t v[32];
@@ -284,7 +294,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                     for (int j = 0; j < 32; j++) {
                         const float s = __uint_as_float(v[j]);
                         const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
-                        mask |= (dist <= tau_f ? 1u : 0u) << j;                 // superset of key < tau (ties resolved below)
+                        mask |= (dist <= thr_f ? 1u : 0u) << j;                 // superset of key < tau (ties resolved below)
                     }
                     const int nvalid = valid_cols - c;
                     if (!qvalid || nvalid <= 0) mask = 0;
@@ -322,7 +332,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                                 mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
                                 if (lane == src) {
                                     tau = ((uint64_t)mhi << 32) | mlo;
-                                    tau_f = tau == ~0ull ? __int_as_float(0x7f800000) : ord_f32(mhi);
+                                    if (tau != ~0ull) {
+                                        tau_f = ord_f32(mhi);
+                                        thr_f = fminf(thr_f, tau_f);
+                                        atomicMin(p.hint + q, mhi);
+                                    }
                                 }
                                 __syncwarp();
                             }
@@ -401,9 +415,10 @@ size_t tc_smem_bytes(int kp) {
 }
 
 cudaError_t launch_tc_split(const uint8_t *src, uint32_t src_stride, int64_t n_rows, int64_t n_pad, int dim, int d_pad, float *hi,
-                            float *lo, float *norm, uint32_t *norm_max, cudaStream_t stream) {
+                            float *lo, float *norm, uint32_t *norm_max, uint32_t *hint_init, cudaStream_t stream) {
     if (n_pad <= 0) return cudaSuccess;
-    tc_split_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, stream>>>(src, src_stride, n_rows, n_pad, dim, d_pad, hi, lo, norm, norm_max);
+    tc_split_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, stream>>>(src, src_stride, n_rows, n_pad, dim, d_pad, hi, lo, norm, norm_max,
+                                                                     hint_init);
     return cudaGetLastError();
 }
 

@@ -70,7 +70,7 @@ int prepare_table(pgvrx_index *ix, cudaStream_t stream) {
     CU_TRY(ix, ix->tc_xmax.ensure(64));
     CU_TRY(ix, cudaMemsetAsync(ix->tc_xmax.p, 0, 64, stream));
     CU_TRY(ix, launch_tc_split((const uint8_t *)ix->vectors.p, ix->row_stride, ix->n, n_pad, dim, d_pad, (float *)ix->tc_xhi.p,
-                               (float *)ix->tc_xlo.p, (float *)ix->tc_xnorm.p, (uint32_t *)ix->tc_xmax.p, stream));
+                               (float *)ix->tc_xlo.p, (float *)ix->tc_xnorm.p, (uint32_t *)ix->tc_xmax.p, nullptr, stream));
     int rc = make_map(ix, ix->tc_map_xhi, ix->tc_xhi.p, n_pad, d_pad);
     if (rc) return rc;
     rc = make_map(ix, ix->tc_map_xlo, ix->tc_xlo.p, n_pad, d_pad);
@@ -127,8 +127,10 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     CU_TRY(ix, ix->tc_qhi.ensure((size_t)nq_pad * d_pad * 4));
     CU_TRY(ix, ix->tc_qlo.ensure((size_t)nq_pad * d_pad * 4));
     CU_TRY(ix, ix->tc_qnorm.ensure((size_t)nq_pad * 4));
+    CU_TRY(ix, ix->tc_hint.ensure((size_t)nq_pad * 4));
     CU_TRY(ix, launch_tc_split((const uint8_t *)d_queries, (uint32_t)ix->row_bytes, nq, nq_pad, ix->desc.dim, d_pad,
-                               (float *)ix->tc_qhi.p, (float *)ix->tc_qlo.p, (float *)ix->tc_qnorm.p, nullptr, stream));
+                               (float *)ix->tc_qhi.p, (float *)ix->tc_qlo.p, (float *)ix->tc_qnorm.p, nullptr,
+                               (uint32_t *)ix->tc_hint.p, stream));
     alignas(64) unsigned char map_qhi[128], map_qlo[128];
     rc = make_map(ix, map_qhi, ix->tc_qhi.p, nq_pad, d_pad);
     if (rc) return rc;
@@ -160,6 +162,7 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     p.cand_ids = (int32_t *)ix->tc_cand.p;
     p.cand_bound = (float *)ix->tc_bound.p;
     p.dbg_scores = d_dbg_scores;
+    p.hint = (uint32_t *)ix->tc_hint.p;
     CU_TRY(ix, launch_flat_tc(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, pl.grid, stream));
     int launches = 2;
     uint64_t n_uncert = 0;

@@ -194,11 +194,12 @@ struct TcParams {
     int32_t *cand_ids;             // [nq][n_splits][kp] global ids, -1 padded
     float *cand_bound;             // [n_splits][nq]: approximate distance every unkept row of the split is at least
     float *dbg_scores;             // nq x n_rows approximate distances (diagnostic) or NULL
+    uint32_t *hint;                // nq: ordered bits of the smallest full candidate-set maximum seen so far per query
 };
 
 size_t tc_smem_bytes(int kp);
 cudaError_t launch_tc_split(const uint8_t *src, uint32_t src_stride, int64_t n_rows, int64_t n_pad, int dim, int d_pad, float *hi,
-                            float *lo, float *norm, uint32_t *norm_max, cudaStream_t stream);
+                            float *lo, float *norm, uint32_t *norm_max, uint32_t *hint_init, cudaStream_t stream);
 cudaError_t launch_flat_tc(const void *map_qhi, const void *map_qlo, const void *map_xhi, const void *map_xlo, const TcParams &p,
                            int grid, cudaStream_t stream);
 cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
