@@ -152,11 +152,87 @@ def gpu_build_sample(a, local):
 
 
 def recall_at_k(a, g, queries, got_ids, sample):
+    """recall@k against the oracle's brute force on a sample of the batch (CPU; used by the reference arm)."""
     import oracle_ffi as O
     s = min(sample, len(queries))
     gt, _ = O.flat_topk(O.ELEM_F32, O.L2SQ, a.dim, g["rows"], queries[:s], a.k, nthreads=os.cpu_count() or 1)
     hit = sum(len(set(got_ids[i].tolist()) & set(gt[i].tolist())) for i in range(s))
     return hit / float(s * a.k)
+
+
+def recall_vs(gt_ids, got_ids):
+    n, k = got_ids.shape
+    hit = sum(len(set(got_ids[i].tolist()) & set(gt_ids[i].tolist())) for i in range(n))
+    return hit / float(n * k)
+
+
+def flat_section(a, ix, g, batch, rank, world, local, dev, tstream):
+    """Exact flat kNN: ground truth for recall and its own throughput line.
+
+    N = 1: the whole table on one GPU (3xTF32 tcgen05 candidates + exact re-rank, certified).
+    N > 1: the base set is sharded by rows, every rank sees the same query batch, local top-k lists are
+    all-gathered over NCCL and merged by the K6 kernel on every rank (strong scaling of one batch)."""
+    import torch
+    import torch.distributed as dist
+    import pgvector_rx_b200 as P
+    from pgvector_rx_b200 import sharded as S
+    stream = tstream.cuda_stream
+    d_q = torch.from_numpy(batch).to(dev)
+    nq, k = len(batch), a.k
+    st = P.FlatStats()
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    ds = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out = {}
+    if world == 1:
+        fx = ix
+        lo = 0
+        run = lambda: fx.flat_topk_device(d_q.data_ptr(), nq, k, ids.data_ptr(), ds.data_ptr(), stream=stream)
+        result = lambda: ids
+    else:
+        lo, hi = S.shard_bounds(a.n, world)[rank]
+        fx = P.HnswIndex("vector_l2_ops", a.dim, m=a.m, ef_construction=a.efc, capacity=hi - lo, device=local)
+        fx.load_rows(g["rows"][lo:hi])
+        sf = S.ShardedFlat.for_index(fx, lo, stream=stream)
+        holder = {}
+
+        def run():
+            holder["r"] = sf.topk(d_q, k)
+        result = lambda: holder["r"][0]
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    fx.flat_topk_device(d_q.data_ptr(), nq, k, ids.data_ptr(), ds.data_ptr(), id_base=lo, stats=st)
+    useful = 2.0 * nq * a.n * a.dim
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf32_peak = peaks.get("bf16_tflops", 2250.0 * 0.73) / 2.0
+    issued = useful * (3 if st.path == 1 else 1) / world
+    out = dict(value=nq / (ms / 1e3), unit="queries/s", ms_per_batch=ms, k=k, rows=a.n, queries=nq, n_gpus=world,
+               path="3xTF32 tcgen05 candidates + exact re-rank (certified)" if st.path == 1 else "sequential f32 chains (CUDA cores)",
+               candidates_per_query=int(st.n_candidates // max(nq, 1)), uncertified=int(st.n_uncertified),
+               parallelism="single table" if world == 1 else "base rows sharded x%d, NCCL all-gather of %d B/rank + K6 merge" % (world, nq * k * 8),
+               roofline=dict(bound="tensor", achieved=issued / (ms / 1e3) / 1e12, peak=tf32_peak, unit="TFLOP/s",
+                             frac=issued / (ms / 1e3) / 1e12 / tf32_peak, traffic=None,
+                             note="issued tf32 flops per GPU (3 products x 2*Q*N*D / n_gpus) / CUDA-event time of the whole call "
+                                  "(operand split, GEMM + top-k, re-rank, certification%s); peak = measured dense bf16 / 2"
+                                  % (", all-gather, merge" if world > 1 else "")))
+    final_ids = result().cpu().numpy()
+    if world > 1:
+        fx.close()
+    return out, final_ids
 
 
 # ---------------------------------------------------------------------------------------------
@@ -340,6 +416,7 @@ def run_b200(a):
     peak, peak_src = measured_peak()
     step_s = ms_max / 1e3 / a.steps
     achieved = bytes_step / step_s / 1e9
+    flat_info, gt_ids = flat_section(a, ix, g, last_batch if world == 1 else batches_rank0_last(a), rank, world, local, dev, tstream)
     out = None
     if rank == 0:
         build_info = dict(cpu_oracle_vectors_per_s=g.get("build_vec_per_s_cpu"), gpu_vectors_per_s=None)
@@ -349,8 +426,14 @@ def run_b200(a):
         base, cpu_ids, o = cpu_baseline(a, g, last_batch, a.cpu_sample)
         nchk = len(cpu_ids)
         parity_ok = bool(np.array_equal(cpu_ids, last_ids[:nchk]))
-        rec = recall_at_k(a, g, last_batch, last_ids, a.recall_sample)
-        rec_cpu = recall_at_k(a, g, last_batch, cpu_ids, min(a.recall_sample, nchk))
+        # recall of the whole batch against the GPU's exact kNN; the exact result itself is cross-checked against the
+        # oracle's brute force on a sample (ids must be identical)
+        import oracle_ffi as O
+        s_chk = min(64, a.nq)
+        o_gt, _ = O.flat_topk(O.ELEM_F32, O.L2SQ, a.dim, g["rows"], last_batch[:s_chk], a.k, nthreads=os.cpu_count() or 1)
+        flat_info["ids_match_cpu_oracle"] = bool(np.array_equal(o_gt, gt_ids[:s_chk]))
+        rec = recall_vs(gt_ids, last_ids)
+        rec_cpu = recall_vs(gt_ids[:nchk], cpu_ids)
         out = dict(metric=METRIC, value=value, unit="queries/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
                    ms_per_step=ms_max / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                    data="synthetic", recall_at_10=rec, recall_at_10_cpu=rec_cpu, ids_match_cpu_oracle=parity_ok,
@@ -369,12 +452,19 @@ def run_b200(a):
                                                n_expand_upper=int(st.n_expand_upper), n_retried=int(st.n_retried)),
                                  note="achieved = (n_dist*512 + n_expand0*128 + n_expand_upper*64 bytes per step) / CUDA-event step time, rank 0 counters"),
                    cpu_baseline=base,
-                   build=build_info)
+                   build=build_info,
+                   flat_knn=flat_info)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ix.close()
+
+
+def batches_rank0_last(a):
+    """The batch rank 0 ran last (every rank needs the same queries for the sharded flat path)."""
+    from pgvector_rx_b200 import datasets as D
+    return D.gaussian_f32(a.nq, a.dim, 3 + 17 * ((a.steps - 1) % 4))
 
 
 def main():
