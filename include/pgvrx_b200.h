@@ -160,7 +160,9 @@ typedef struct {
     uint64_t n_duplicates;    /* rows merged into an existing element's heap TIDs (build.rs:482-512) */
     uint64_t n_big_retries;   /* searches re-run alone with large scratch                         */
     uint64_t n_dist, n_expand0, n_expand_upper;   /* GPU work of the committed searches           */
-    uint64_t n_pair;          /* pairwise distances of select_neighbors on the host (graph/mod.rs:326) */
+    uint64_t n_pair;          /* pairwise distances select_neighbors consulted (graph/mod.rs:326)          */
+    uint64_t n_pair_gpu;      /* pairwise distances computed on the GPU for back-link re-selections        */
+    uint64_t n_validation_dist; /* distances evaluated to validate speculative searches against changed lists */
     double   gpu_ms;          /* wall time spent in upload + kernel + download                     */
     double   kernel_ms;       /* device time of the K2 launches alone (CUDA events)               */
     double   total_ms;

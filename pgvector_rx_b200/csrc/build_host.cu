@@ -23,6 +23,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_fp16.h>
@@ -203,7 +204,51 @@ struct Pending {                 // one element of the current round, after phas
     int dup_of = -1;                      // element id this row merges into (build.rs:482-503)
 };
 
-struct Update { int32_t node; int32_t lc; int32_t new_id; float distance; };
+// one (node, layer) list that pending elements of the current round link back to
+struct Group {
+    int32_t node, lc;
+    int n_list;                       // list length at the start of the round
+    std::vector<int32_t> ids;         // list at the start of the round, then the pending elements that selected it
+    std::vector<int32_t> old_ids;     // the list as the round's searches saw it
+    std::vector<int16_t> pos;         // position in `ids` of every entry of the CURRENT list (-1: unknown)
+    int64_t mat;                      // offset of the group's pairwise matrix (floats) or -1
+    bool modified;
+};
+
+// order-preserving bits of a distance, as the kernels compare them (hnsw_device.cuh f32_ord)
+static inline uint32_t ord_of(float d) {
+    d = d + 0.0f;
+    uint32_t b;
+    memcpy(&b, &d, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// select_neighbors with check_element_closer's distances looked up in a GPU-computed pairwise matrix
+static void select_neighbors_mat(BuildState &g, const Cand *cand, const int16_t *pos, int n_cand, int max_neighbors,
+                                 const float *mat, int mat_n, std::vector<Cand> &out, std::vector<int16_t> &out_pos) {
+    out.clear();
+    out_pos.clear();
+    if (n_cand <= max_neighbors) { out.assign(cand, cand + n_cand); out_pos.assign(pos, pos + n_cand); return; }
+    std::vector<int> discarded;
+    uint64_t pairs = 0;
+    for (int i = 0; i < n_cand; i++) {
+        if ((int)out.size() >= max_neighbors) break;
+        const Cand &e = cand[i];
+        bool closer = true;
+        for (size_t r = 0; r < out.size(); r++) {
+            const float d = (pos[i] >= 0 && out_pos[r] >= 0) ? mat[(size_t)pos[i] * mat_n + out_pos[r]] : g.dist(e.idx, out[r].idx);
+            pairs++;
+            if (d <= e.distance) { closer = false; break; }
+        }
+        if (closer) { out.push_back(e); out_pos.push_back(pos[i]); } else discarded.push_back(i);
+    }
+    for (int di : discarded) {
+        if ((int)out.size() >= max_neighbors) break;
+        out.push_back(cand[di]);
+        out_pos.push_back(pos[di]);
+    }
+    g.n_pair.fetch_add(pairs, std::memory_order_relaxed);
+}
 
 }  // namespace pgvrx_host
 
@@ -212,11 +257,29 @@ using namespace pgvrx_host;
 namespace {
 
 struct RoundBuffers {
-    DevBuf elem_ids, w_ids, w_dists, w_counts, rs_log, rs_counts, status, ctr, vis, work, sc_off, sc_rows;
+    DevBuf elem_ids, w_ids, w_dists, w_counts, rs_log, rs_counts, status, ctr, vis, work, sc_off, sc_rows, g_ids, g_off, g_moff, g_mat;
     void release() {
-        DevBuf *b[] = {&elem_ids, &w_ids, &w_dists, &w_counts, &rs_log, &rs_counts, &status, &ctr, &vis, &work, &sc_off, &sc_rows};
+        DevBuf *b[] = {&elem_ids, &w_ids, &w_dists, &w_counts, &rs_log, &rs_counts, &status, &ctr, &vis, &work, &sc_off, &sc_rows,
+                       &g_ids, &g_off, &g_moff, &g_mat};
         for (DevBuf *x : b) x->release();
     }
+};
+
+// pinned host buffer (device-to-host copies of per-round results run at full PCIe rate and truly asynchronously)
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 2 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
 };
 
 double now_ms() {
@@ -377,6 +440,16 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     const int WINDOW_MAX = 512;
     bool big_next = false;
     const int rs_cap = std::max(256, 6 * efc + 64);
+    std::vector<Group> groups;
+    std::unordered_map<uint64_t, int> group_of;
+    std::vector<int32_t> h_gids, h_goff;
+    std::vector<int64_t> h_moff;
+    PinnedBuf h_mat;
+    uint64_t n_pair_gpu = 0, n_val_dist = 0;
+    // rows a pairwise group may hold: what fits in one CTA's shared memory, at most PAIR_MAX_ROWS
+    const uint32_t pair_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
+    const int pair_rows = (int)std::min<size_t>(PAIR_MAX_ROWS, (100 * 1024) / pair_stride);
+    const int pair_occ = 2;
     std::vector<int32_t> h_elem, h_wids, h_wcnt, h_rs, h_rscnt;
     std::vector<float> h_wd;
     std::vector<uint32_t> h_status, h_ctr;
@@ -415,7 +488,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         CU_TRY(ix, rb.w_ids.ensure((size_t)B * max_layers * efc * 4));
         CU_TRY(ix, rb.w_dists.ensure((size_t)B * max_layers * efc * 4));
         CU_TRY(ix, rb.w_counts.ensure((size_t)B * max_layers * 4));
-        CU_TRY(ix, rb.rs_log.ensure((size_t)B * rs_cap * 4));
+        CU_TRY(ix, rb.rs_log.ensure((size_t)B * rs_cap * 12));
         CU_TRY(ix, rb.rs_counts.ensure((size_t)B * 4));
         CU_TRY(ix, rb.status.ensure((size_t)B * 4));
         CU_TRY(ix, rb.ctr.ensure((size_t)B * 16));
@@ -454,7 +527,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         h_wids.resize((size_t)B * max_layers * efc);
         h_wd.resize((size_t)B * max_layers * efc);
         h_wcnt.resize((size_t)B * max_layers);
-        h_rs.resize((size_t)B * rs_cap);
+        h_rs.resize((size_t)B * rs_cap * 3);
         h_rscnt.resize((size_t)B);
         h_status.resize((size_t)B);
         h_ctr.resize((size_t)B * 4);
@@ -498,10 +571,91 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             }
         });
 
-        // ---- host: sequential validation + commit of the longest valid prefix ----
+        // ---- back-link groups: every (node, layer) some pending element selected, with the pending elements
+        //      that selected it in insert order.  Where a full list will have to be re-selected
+        //      (graph/mod.rs:473-485) the pairwise distances among list + newcomers come from the GPU. ----
+        groups.clear();
+        group_of.clear();
+        for (int i = 0; i < B; i++) {
+            const Pending &p = pend[(size_t)i];
+            if (h_status[(size_t)i] != 0) break;               // nothing after an overflowed search can commit this round
+            for (int lc = 0; lc < (int)p.sel.size(); lc++)
+                for (const Cand &nb : p.sel[(size_t)lc]) {
+                    const uint64_t key = ((uint64_t)(uint32_t)nb.idx << 8) | (uint64_t)lc;
+                    auto it = group_of.find(key);
+                    if (it == group_of.end()) {
+                        it = group_of.emplace(key, (int)groups.size()).first;
+                        groups.emplace_back();
+                        Group &G = groups.back();
+                        G.node = nb.idx;
+                        G.lc = lc;
+                        G.n_list = g.cnt(nb.idx, lc);
+                        const int32_t *ids = g.ids(nb.idx, lc);
+                        G.ids.assign(ids, ids + G.n_list);
+                    }
+                    groups[(size_t)it->second].ids.push_back((int32_t)(e_base + i));
+                }
+        }
+        h_gids.clear();
+        h_goff.clear();
+        h_moff.clear();
+        int64_t mat_floats = 0;
+        int n_dev_groups = 0;
+        for (Group &G : groups) {
+            const int total = (int)G.ids.size();
+            G.old_ids.assign(G.ids.begin(), G.ids.begin() + G.n_list);
+            G.pos.resize((size_t)G.n_list);
+            for (int t = 0; t < G.n_list; t++) G.pos[(size_t)t] = (int16_t)t;
+            G.modified = false;
+            G.mat = -1;
+            if (total > g.lm(G.lc) && total <= pair_rows) {     // a re-selection can happen and the group fits on a CTA
+                G.mat = mat_floats;
+                h_goff.push_back((int32_t)h_gids.size());
+                h_moff.push_back(mat_floats);
+                h_gids.insert(h_gids.end(), G.ids.begin(), G.ids.end());
+                mat_floats += (int64_t)total * total;
+                n_dev_groups++;
+            }
+        }
+        h_goff.push_back((int32_t)h_gids.size());
+        if (n_dev_groups > 0) {
+            const double tp0 = now_ms();
+            CU_TRY(ix, rb.g_ids.ensure(h_gids.size() * 4));
+            CU_TRY(ix, rb.g_off.ensure(h_goff.size() * 4));
+            CU_TRY(ix, rb.g_moff.ensure(h_moff.size() * 8));
+            CU_TRY(ix, rb.g_mat.ensure((size_t)mat_floats * 4));
+            CU_TRY(ix, h_mat.ensure((size_t)mat_floats * 4));
+            CU_TRY(ix, cudaMemcpyAsync(rb.g_ids.p, h_gids.data(), h_gids.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, cudaMemcpyAsync(rb.g_off.p, h_goff.data(), h_goff.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, cudaMemcpyAsync(rb.g_moff.p, h_moff.data(), h_moff.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, cudaMemsetAsync((int *)rb.work.p + 8, 0, 4, ix->stream));
+            PairParams pp;
+            pp.ids = (const int32_t *)rb.g_ids.p;
+            pp.group_off = (const int32_t *)rb.g_off.p;
+            pp.mat_off = (const int64_t *)rb.g_moff.p;
+            pp.n_groups = n_dev_groups;
+            pp.out = (float *)rb.g_mat.p;
+            pp.work_counter = (int *)rb.work.p + 8;
+            pp.stage_stride = cfg.L.stage_stride;
+            CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
+            CU_TRY(ix, launch_pairwise(ix->desc.elem_type, ix->desc.metric, gv, pp, pair_rows, std::min(n_dev_groups, ix->sm_count * pair_occ), ix->stream));
+            CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));
+            CU_TRY(ix, cudaMemcpyAsync(h_mat.p, rb.g_mat.p, (size_t)mat_floats * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+            float kms = 0.0f;
+            CU_TRY(ix, cudaEventElapsedTime(&kms, ix->ev0, ix->ev1));
+            kernel_ms += kms;
+            gpu_ms += now_ms() - tp0;
+            n_pair_gpu += (uint64_t)mat_floats;
+        }
+        const float *mat_all = (const float *)h_mat.p;
+
+        // ---- host: sequential validation + commit in insert order ----
         int committed = 0;
         bool stop = false;
-        std::vector<Update> updates;
+        std::vector<Cand> all, sel_out;
+        std::vector<int16_t> all_pos, sel_pos;
+        std::vector<std::pair<int32_t, float>> dcache;          // d(pending element, y) computed during one validation
         for (int i = 0; i < B && !stop; i++) {
             Pending &p = pend[(size_t)i];
             const int64_t e = e_base + i;
@@ -509,13 +663,52 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                 if (i == 0) { big_next = true; n_retry_big++; }
                 break;
             }
-            bool valid = h_rscnt[(size_t)i] <= rs_cap;
-            if (valid && i > 0) {
-                const int32_t *rs = &h_rs[(size_t)i * rs_cap];
-                for (int t = 0; t < h_rscnt[(size_t)i]; t++)
-                    if (g.stamp[(size_t)rs[t]] == g.round) { valid = false; break; }
+            // -- is the speculative search still the one a sequential build would have run? --
+            // Replay argument: the search is a function of the lists it read.  For a list that changed since the
+            // snapshot, compare what it could contribute at the moment it was read: only neighbours nearer than
+            // W's furthest distance at that expansion (f_t, W full) can be accepted then or ever after (f only
+            // shrinks; equal is rejected, graph/mod.rs:226), everything else merely toggles a visited flag of an
+            // element that is rejected wherever it is met.  If the acceptable neighbours of the old and the new
+            // list are the same sequence, the run is identical.
+            bool valid = true;
+            if (i > 0) {
+                if (h_rscnt[(size_t)i] > rs_cap) valid = false;
+                dcache.clear();
+                const int32_t *rs = &h_rs[(size_t)i * rs_cap * 3];
+                for (int t = 0; valid && t < h_rscnt[(size_t)i]; t++) {
+                    const int32_t v = rs[3 * t], lc = rs[3 * t + 2];
+                    if (g.stamp[(size_t)v] != g.round) continue;
+                    auto it = group_of.find(((uint64_t)(uint32_t)v << 8) | (uint64_t)lc);
+                    if (it == group_of.end()) continue;
+                    const Group &G = groups[(size_t)it->second];
+                    if (!G.modified) continue;
+                    const uint32_t ford = (uint32_t)rs[3 * t + 1];
+                    const int n_new = g.cnt(v, lc);
+                    const int32_t *l_new = g.ids(v, lc);
+                    if (ford == 0xFFFFFFFFu) {                  // W not full: any change of the list matters
+                        valid = n_new == (int)G.old_ids.size() && std::equal(l_new, l_new + n_new, G.old_ids.begin());
+                        continue;
+                    }
+                    auto near = [&](int32_t y) -> bool {        // d(e, y) < f_t, exactly as the kernel compares
+                        float d = 0.0f;
+                        bool have = false;
+                        for (auto &c : dcache) if (c.first == y) { d = c.second; have = true; break; }
+                        if (!have) { d = g.dist(e, y); dcache.emplace_back(y, d); n_val_dist++; }
+                        return ord_of(d) < ford;
+                    };
+                    size_t io = 0;
+                    int in_ = 0;
+                    while (valid) {
+                        while (io < G.old_ids.size() && !near(G.old_ids[io])) io++;
+                        while (in_ < n_new && !near(l_new[in_])) in_++;
+                        const bool eo = io >= G.old_ids.size(), en = in_ >= n_new;
+                        if (eo || en) { valid = eo && en; break; }
+                        if (G.old_ids[io] != l_new[in_]) valid = false;
+                        io++;
+                        in_++;
+                    }
+                }
             }
-            if (!valid && i == 0 && h_rscnt[0] > rs_cap) valid = true;   // the head of a round is always exact
             if (!valid) { n_conflicts++; break; }
             c_dist += h_ctr[(size_t)i * 4];
             c_exp0 += h_ctr[(size_t)i * 4 + 1];
@@ -539,7 +732,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                 stop = true;
                 break;
             }
-            // new element's own lists (graph/mod.rs:422)
+            // new element's own lists (graph/mod.rs:422), then its back-links at once (graph/mod.rs:442-489):
+            // later elements of this round are validated against the lists as they stand after this commit
             const int top = std::min(p.level, g.entry_level);
             for (int lc = top; lc >= 0; lc--) {
                 const std::vector<Cand> &s = p.sel[(size_t)lc];
@@ -547,8 +741,48 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                 float *ds = g.dists(e, lc);
                 for (size_t t = 0; t < s.size(); t++) { ids[t] = s[t].idx; ds[t] = s[t].distance; }
                 g.cnt(e, lc) = (uint8_t)s.size();
-                for (const Cand &nb : s) {                      // back-links, applied in phase B (graph/mod.rs:458-487)
-                    updates.push_back(Update{nb.idx, lc, (int32_t)e, nb.distance});
+            }
+            for (int lc = p.level; lc >= 0; lc--) {             // :455 for lc in (0..=level).rev()
+                if (lc > top) continue;
+                for (const Cand &nb : p.sel[(size_t)lc]) {
+                    Group &G = groups[(size_t)group_of[((uint64_t)(uint32_t)nb.idx << 8) | (uint64_t)lc]];
+                    const int lm = g.lm(lc);
+                    int32_t *ids = g.ids(nb.idx, lc);
+                    float *ds = g.dists(nb.idx, lc);
+                    uint8_t &c = g.cnt(nb.idx, lc);
+                    // position of the new element among the group's rows
+                    int16_t epos = -1;
+                    for (size_t t = (size_t)G.n_list; t < G.ids.size(); t++) if (G.ids[t] == (int32_t)e) { epos = (int16_t)t; break; }
+                    if ((int)c < lm) {                          // :469-471 room available
+                        ids[c] = (int32_t)e;
+                        ds[c] = nb.distance;
+                        G.pos.push_back(epos);
+                        c++;
+                    } else {                                    // :473-485 re-select over list + new, replace the list
+                        const int n_all = (int)c + 1;
+                        all.resize((size_t)n_all);
+                        all_pos.resize((size_t)n_all);
+                        std::vector<int> order((size_t)n_all);
+                        for (int t2 = 0; t2 < n_all; t2++) order[(size_t)t2] = t2;
+                        auto dist_of = [&](int t2) { return t2 < (int)c ? ds[t2] : nb.distance; };
+                        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return dist_of(x) < dist_of(y); });
+                        for (int t2 = 0; t2 < n_all; t2++) {
+                            const int src = order[(size_t)t2];
+                            all[(size_t)t2] = src < (int)c ? Cand{ds[src], ids[src]} : Cand{nb.distance, (int32_t)e};
+                            all_pos[(size_t)t2] = src < (int)c ? G.pos[(size_t)src] : epos;
+                        }
+                        if (G.mat >= 0)
+                            select_neighbors_mat(g, all.data(), all_pos.data(), n_all, lm, mat_all + G.mat, (int)G.ids.size(), sel_out, sel_pos);
+                        else {
+                            select_neighbors(g, all.data(), n_all, lm, sel_out);
+                            sel_pos.assign(sel_out.size(), (int16_t)-1);
+                        }
+                        for (size_t t2 = 0; t2 < sel_out.size(); t2++) { ids[t2] = sel_out[t2].idx; ds[t2] = sel_out[t2].distance; }
+                        for (int t2 = (int)sel_out.size(); t2 < lm; t2++) ids[t2] = -1;
+                        c = (uint8_t)sel_out.size();
+                        G.pos.assign(sel_pos.begin(), sel_pos.end());
+                    }
+                    G.modified = true;
                     g.stamp[(size_t)nb.idx] = g.round;
                 }
             }
@@ -562,41 +796,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                 stop = true;                                    // later searches started from the old entry point
             }
         }
-        // ---- host: phase B (parallel by node): update_neighbor_connections (graph/mod.rs:442-489) ----
-        // stable order by (node, layer) keeps the per-list updates in insert order
-        std::stable_sort(updates.begin(), updates.end(), [](const Update &a, const Update &b) {
-            return a.node != b.node ? a.node < b.node : a.lc < b.lc; });
-        std::vector<size_t> group_start;
-        for (size_t t = 0; t < updates.size(); t++)
-            if (t == 0 || updates[t].node != updates[t - 1].node || updates[t].lc != updates[t - 1].lc) group_start.push_back(t);
-        group_start.push_back(updates.size());
-        pool.parallel_for((int64_t)group_start.size() - 1, [&](int64_t gi) {
-            std::vector<Cand> all, sel;
-            for (size_t t = group_start[(size_t)gi]; t < group_start[(size_t)gi + 1]; t++) {
-                const Update &u = updates[t];
-                const int lm = g.lm(u.lc);
-                int32_t *ids = g.ids(u.node, u.lc);
-                float *ds = g.dists(u.node, u.lc);
-                uint8_t &c = g.cnt(u.node, u.lc);
-                if ((int)c < lm) {                              // :469-471 room available
-                    ids[c] = u.new_id;
-                    ds[c] = u.distance;
-                    c++;
-                } else {                                        // :473-485 re-select over list + new, replace the list
-                    all.resize((size_t)c + 1);
-                    for (int t2 = 0; t2 < (int)c; t2++) all[(size_t)t2] = Cand{ds[t2], ids[t2]};
-                    all[(size_t)c] = Cand{u.distance, u.new_id};
-                    std::stable_sort(all.begin(), all.end(), [](const Cand &a, const Cand &b) { return a.distance < b.distance; });
-                    select_neighbors(g, all.data(), (int)all.size(), lm, sel);
-                    for (size_t t2 = 0; t2 < sel.size(); t2++) { ids[t2] = sel[t2].idx; ds[t2] = sel[t2].distance; }
-                    for (int t2 = (int)sel.size(); t2 < lm; t2++) ids[t2] = -1;
-                    c = (uint8_t)sel.size();
-                }
-            }
-        });
 
         // ---- device graph := committed state ----
-        for (size_t gi = 0; gi + 1 < group_start.size(); gi++) queue_row(updates[group_start[gi]].node, updates[group_start[gi]].lc);
+        for (const Group &G : groups) if (G.modified) queue_row(G.node, G.lc);
         for (int64_t e = e_base; e < g.n; e++) {
             queue_row(e, 0);
             for (int l = 1; l <= g.level[(size_t)e]; l++) queue_row(e, l);
@@ -627,6 +829,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         stats->n_expand0 = c_exp0;
         stats->n_expand_upper = c_expu;
         stats->n_pair = g.n_pair.load();
+        stats->n_pair_gpu = n_pair_gpu;
+        stats->n_validation_dist = n_val_dist;
         stats->gpu_ms = gpu_ms;
         stats->kernel_ms = kernel_ms;
         stats->total_ms = now_ms() - t_start;

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
 
         c.n_dist = c.n_exp0 = c.n_expu = c.n_vis = 0;
         c.status = 0;
-        c.rs_log = p.rs_log + (size_t)w * p.rs_cap;
+        c.rs_log = p.rs_log + (size_t)w * p.rs_cap * 3;
         c.rs_cap = p.rs_cap;
         c.rs_n = 0;
         for (int l = lane; l < p.max_layers; l += 32) p.w_counts[(size_t)w * p.max_layers + l] = -1;
@@ -136,6 +136,80 @@ __global__ void scatter_rows_kernel(int32_t *dst, const int64_t *row_offsets, co
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int r = t / row_len, j = t - r * row_len;
     if (r < n_rows) dst[row_offsets[r] + j] = packed[(size_t)r * row_len + j];
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Pairwise distances inside small groups of elements (select_neighbors' check_element_closer,
+// graph/mod.rs:315-339, when update_neighbor_connections re-selects a full list, :473-485).  One CTA per
+// group: the group's rows are staged once (one TMA bulk copy per row), then lane <-> column b and a row a
+// broadcast from shared memory give d(a, b) with the same sequential arithmetic as everywhere else.
+// out: cnt x cnt floats per group (symmetric; both halves are written).
+// ---------------------------------------------------------------------------------------------------
+template <int ELEM, int METRIC>
+__global__ void __launch_bounds__(SEARCH_THREADS) pairwise_kernel(GraphView g, PairParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *stage = smem + 128;
+    __shared__ int s_group;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const uint64_t policy = l2_policy_evict_first();
+    const int nvec = (int)(g.row_stride / 16);
+    uint32_t phase = 0;
+    while (true) {
+        if (t == 0) s_group = atomicAdd(p.work_counter, 1);
+        __syncthreads();
+        const int gi = s_group;
+        if (gi >= p.n_groups) break;
+        const int off = p.group_off[gi], cnt = p.group_off[gi + 1] - off;
+        float *out = p.out + p.mat_off[gi];
+        if (t == 0) mbar_arrive_expect_tx(mbar, (uint32_t)cnt * g.row_stride);
+        __syncthreads();
+        if (t < cnt)
+            tma_row_g2s(stage + (size_t)t * p.stage_stride, g.vectors + (size_t)p.ids[off + t] * g.row_stride, g.row_stride, mbar, policy);
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+        for (int a = warp; a < cnt; a += SEARCH_THREADS / 32) {
+            const uint8_t *ra = stage + (size_t)a * p.stage_stride;
+            for (int b0 = 0; b0 < cnt; b0 += 32) {
+                const int b = b0 + lane;
+                if (b < cnt) out[(size_t)a * cnt + b] = row_distance<ELEM, METRIC>(ra, stage + (size_t)b * p.stage_stride, nvec);
+            }
+        }
+        // generic-proxy reads of the staging rows are ordered before the next group's TMA writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
+}
+
+typedef void (*pair_kernel_t)(GraphView, PairParams);
+static pair_kernel_t pick_pair(int elem, int metric) {
+    if (elem == ELEM_F32) {
+        if (metric == METRIC_L2SQ) return pairwise_kernel<ELEM_F32, METRIC_L2SQ>;
+        if (metric == METRIC_NEG_IP) return pairwise_kernel<ELEM_F32, METRIC_NEG_IP>;
+        if (metric == METRIC_L1) return pairwise_kernel<ELEM_F32, METRIC_L1>;
+    } else if (elem == ELEM_F16) {
+        if (metric == METRIC_L2SQ) return pairwise_kernel<ELEM_F16, METRIC_L2SQ>;
+        if (metric == METRIC_NEG_IP) return pairwise_kernel<ELEM_F16, METRIC_NEG_IP>;
+        if (metric == METRIC_L1) return pairwise_kernel<ELEM_F16, METRIC_L1>;
+    } else if (elem == ELEM_BIT) {
+        if (metric == METRIC_HAMMING) return pairwise_kernel<ELEM_BIT, METRIC_HAMMING>;
+        if (metric == METRIC_JACCARD) return pairwise_kernel<ELEM_BIT, METRIC_JACCARD>;
+    }
+    return nullptr;
+}
+
+cudaError_t launch_pairwise(int elem, int metric, const GraphView &g, const PairParams &p, int max_rows, int grid, cudaStream_t stream) {
+    pair_kernel_t k = pick_pair(elem, metric);
+    if (!k) return cudaErrorInvalidValue;
+    if (p.n_groups <= 0) return cudaSuccess;
+    const size_t smem = 128 + (size_t)max_rows * p.stage_stride;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, SEARCH_THREADS, smem, stream>>>(g, p);
+    return cudaGetLastError();
 }
 
 typedef void (*build_kernel_t)(GraphView, BuildParams);

@@ -252,7 +252,7 @@ struct WarpCtx {
     uint32_t phase;
     uint32_t f_ord;        // ordered bits of W's furthest distance (valid when len >= ef)
     uint32_t n_dist, n_exp0, n_expu, n_vis, status;
-    int32_t *rs_log;       // build: ids of the nodes whose neighbour lists this search read (or NULL)
+    int32_t *rs_log;       // build: 3 ints per expansion -- node id, ordered bits of f_dist (or -1), layer (or NULL)
     int rs_cap, rs_n;      // capacity / count (rs_n may exceed rs_cap: the host then treats the set as unknown)
     int lane;
 #ifdef PGVRX_PHASE_TIMING
@@ -496,7 +496,13 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
         if (!S.pop_nearest(c, ckey)) break;   // every remaining candidate would fail `c.distance > f_dist`
         const uint32_t cid = key_id(ckey);
         if (c.rs_log) {
-            if (lane == 0 && c.rs_n < c.rs_cap) c.rs_log[c.rs_n] = (int32_t)cid;
+            // build: (expanded node, W's furthest distance at the start of the expansion or ~0 when W is not full, layer)
+            if (lane == 0 && c.rs_n < c.rs_cap) {
+                int32_t *e = c.rs_log + 3 * (size_t)c.rs_n;
+                e[0] = (int32_t)cid;
+                e[1] = c.len >= c.ef ? (int32_t)c.f_ord : -1;
+                e[2] = layer;
+            }
             c.rs_n++;
         }
         const int32_t *row;

@@ -49,7 +49,7 @@ struct BuildParams {
     int32_t *w_ids;            // n_pending x max_layers x efc, ascending (distance, id)
     float *w_dists;
     int32_t *w_counts;         // n_pending x max_layers, -1 for layers that were not searched
-    int32_t *rs_log;           // n_pending x rs_cap expanded node ids (the search's read set)
+    int32_t *rs_log;           // n_pending x rs_cap x 3: expanded node id, ordered f_dist bits at the expansion (-1: W not full), layer
     int rs_cap;
     int32_t *rs_counts;        // n_pending (may exceed rs_cap => set unknown)
     uint32_t *out_status;      // n_pending
@@ -59,6 +59,18 @@ struct BuildParams {
     int *work_counter;
     uint32_t stage_stride;
     int R;
+};
+
+// pairwise distances inside groups of <= PAIR_MAX_ROWS elements (hnsw_build.cu)
+constexpr int PAIR_MAX_ROWS = 128;
+struct PairParams {
+    const int32_t *ids;        // concatenated element ids of all groups
+    const int32_t *group_off;  // n_groups + 1 offsets into ids
+    const int64_t *mat_off;    // n_groups float offsets into out
+    int n_groups;
+    float *out;                // per group cnt x cnt distances
+    int *work_counter;
+    uint32_t stage_stride;
 };
 
 // what the host needs to size shared memory
@@ -75,6 +87,7 @@ cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView
 cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm);
 cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
                                 size_t smem_block, cudaStream_t stream);
+cudaError_t launch_pairwise(int elem, int metric, const GraphView &g, const PairParams &p, int max_rows, int grid, cudaStream_t stream);
 cudaError_t launch_scatter_rows(int32_t *dst, const int64_t *row_offsets, const int32_t *packed, int row_len, int n_rows,
                                 cudaStream_t stream);
 cudaError_t launch_collect_failed(const uint32_t *status, int nq, int32_t *qmap, int *n_work, cudaStream_t stream);
