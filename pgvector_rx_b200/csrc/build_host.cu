@@ -446,6 +446,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     std::vector<int64_t> h_moff;
     PinnedBuf h_mat;
     uint64_t n_pair_gpu = 0, n_val_dist = 0;
+    uint64_t why_overflow = 0, why_notfull = 0, why_pending = 0, why_order = 0;   // conflict reasons (PGVRX_BUILD_DEBUG)
+    double t_phase_a = 0, t_groups = 0, t_commit = 0, t_scatter = 0;
     // rows a pairwise group may hold: what fits in one CTA's shared memory, at most PAIR_MAX_ROWS
     const uint32_t pair_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
     const int pair_rows = (int)std::min<size_t>(PAIR_MAX_ROWS, (100 * 1024) / pair_stride);
@@ -548,6 +550,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         n_searched += (uint64_t)B;
 
         // ---- host: phase A (parallel): select_neighbors + duplicate probe for every searched element ----
+        const double tA0 = now_ms();
         std::vector<Pending> pend((size_t)B);
         pool.parallel_for(B, [&](int64_t i) {
             Pending &p = pend[(size_t)i];
@@ -574,6 +577,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         // ---- back-link groups: every (node, layer) some pending element selected, with the pending elements
         //      that selected it in insert order.  Where a full list will have to be re-selected
         //      (graph/mod.rs:473-485) the pairwise distances among list + newcomers come from the GPU. ----
+        const double tG0 = now_ms();
+        t_phase_a += tG0 - tA0;
         groups.clear();
         group_of.clear();
         for (int i = 0; i < B; i++) {
@@ -618,6 +623,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             }
         }
         h_goff.push_back((int32_t)h_gids.size());
+        t_groups += now_ms() - tG0;
         if (n_dev_groups > 0) {
             const double tp0 = now_ms();
             CU_TRY(ix, rb.g_ids.ensure(h_gids.size() * 4));
@@ -651,6 +657,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const float *mat_all = (const float *)h_mat.p;
 
         // ---- host: sequential validation + commit in insert order ----
+        const double tC0 = now_ms();
         int committed = 0;
         bool stop = false;
         std::vector<Cand> all, sel_out;
@@ -672,7 +679,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             // list are the same sequence, the run is identical.
             bool valid = true;
             if (i > 0) {
-                if (h_rscnt[(size_t)i] > rs_cap) valid = false;
+                if (h_rscnt[(size_t)i] > rs_cap) { valid = false; why_overflow++; }
                 dcache.clear();
                 const int32_t *rs = &h_rs[(size_t)i * rs_cap * 3];
                 for (int t = 0; valid && t < h_rscnt[(size_t)i]; t++) {
@@ -687,6 +694,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                     const int32_t *l_new = g.ids(v, lc);
                     if (ford == 0xFFFFFFFFu) {                  // W not full: any change of the list matters
                         valid = n_new == (int)G.old_ids.size() && std::equal(l_new, l_new + n_new, G.old_ids.begin());
+                        if (!valid) why_notfull++;
                         continue;
                     }
                     auto near = [&](int32_t y) -> bool {        // d(e, y) < f_t, exactly as the kernel compares
@@ -702,8 +710,12 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                         while (io < G.old_ids.size() && !near(G.old_ids[io])) io++;
                         while (in_ < n_new && !near(l_new[in_])) in_++;
                         const bool eo = io >= G.old_ids.size(), en = in_ >= n_new;
-                        if (eo || en) { valid = eo && en; break; }
-                        if (G.old_ids[io] != l_new[in_]) valid = false;
+                        if (eo || en) {
+                            valid = eo && en;
+                            if (!valid) { if (!en && l_new[in_] >= e_base) why_pending++; else why_order++; }
+                            break;
+                        }
+                        if (G.old_ids[io] != l_new[in_]) { valid = false; if (l_new[in_] >= e_base) why_pending++; else why_order++; }
                         io++;
                         in_++;
                     }
@@ -798,6 +810,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         }
 
         // ---- device graph := committed state ----
+        const double tS0 = now_ms();
+        t_commit += tS0 - tC0;
         for (const Group &G : groups) if (G.modified) queue_row(G.node, G.lc);
         for (int64_t e = e_base; e < g.n; e++) {
             queue_row(e, 0);
@@ -805,6 +819,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         }
         rc = flush_scatter();
         if (rc) return rc;
+        t_scatter += now_ms() - tS0;
 
         // input rows consumed this round: committed elements plus a merged duplicate
         f += committed;
@@ -813,6 +828,10 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         grow_host(g.n, g.n_upper);
     }
 
+    if (getenv("PGVRX_BUILD_DEBUG"))
+        fprintf(stderr, "[pgvrx build] conflicts: log overflow %llu, W-not-full %llu, pending element acceptable %llu, order/removal %llu | ms: gpu %.0f (kernels %.0f) phaseA %.0f groups %.0f commit %.0f scatter %.0f\n",
+                (unsigned long long)why_overflow, (unsigned long long)why_notfull, (unsigned long long)why_pending,
+                (unsigned long long)why_order, gpu_ms, kernel_ms, t_phase_a, t_groups, t_commit, t_scatter);
     ix->n = g.n;
     ix->n_upper = g.n_upper;
     ix->entry = g.entry;

@@ -50,10 +50,13 @@ def test_build_vector_l2_exact_adjacency():
     assert_same_graph(ix.export_graph(), o.export_graph(), o)
     assert st["n_searched"] >= 5999 and st["n_rounds"] < st["n_searched"]      # really batched
     oc = o.build_counters()
-    # phase A also runs for speculative searches that are later discarded, so the host does at least
-    # the oracle's heuristic work; the committed GPU searches do exactly the oracle's search work
+    # phase A also runs for speculative searches that are later discarded, so the heuristic consults at least
+    # the oracle's pairs.  A committed speculative search expands exactly the nodes the sequential search would
+    # (that is what the commit rule proves); it may have evaluated a few elements the sequential run would have
+    # found visited already, or vice versa -- all of them rejected either way -- so n_dist can differ marginally.
     assert st["n_pair"] >= oc["n_pair"]
-    assert st["n_dist"] == oc["n_dist"] and st["n_expand0"] == oc["n_expand0"] and st["n_expand_upper"] == oc["n_expand_upper"]
+    assert st["n_expand0"] == oc["n_expand0"] and st["n_expand_upper"] == oc["n_expand_upper"]
+    assert abs(st["n_dist"] - oc["n_dist"]) <= 0.01 * oc["n_dist"]
     print("build stats", st)
     # the built graph is resident: scanning it matches the oracle's scan of its own graph
     q = make_rows("f32", 200, 64, 77)
