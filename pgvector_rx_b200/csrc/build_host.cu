@@ -74,6 +74,33 @@ static float host_distance(int elem, int metric, int dim, const uint8_t *pa, con
     return (float)(1.0 - ((double)ab / (double)(aa + bb - ab)));
 }
 
+// d(a, b) < f, bit-for-bit the comparison the kernel makes, but leaving the accumulation as soon as the running sum
+// reaches f where that is sound: L2 / L1 / Hamming sums only grow (adding a non-negative term never lowers an fp sum).
+static bool host_distance_less(int elem, int metric, int dim, const uint8_t *pa, const uint8_t *pb, float f) {
+    if (metric == PGVRX_METRIC_NEG_IP || metric == PGVRX_METRIC_JACCARD || !(f == f))
+        return host_distance(elem, metric, dim, pa, pb) < f;
+    if (elem == PGVRX_ELEM_F32) {
+        const float *a = (const float *)pa, *b = (const float *)pb;
+        float acc = 0.0f;
+        int i = 0;
+        if (metric == PGVRX_METRIC_L2SQ) {
+            for (; i + 16 <= dim; i += 16) {
+                for (int j = i; j < i + 16; j++) { float d = a[j] - b[j]; acc += d * d; }
+                if (acc >= f) return false;
+            }
+            for (; i < dim; i++) { float d = a[i] - b[i]; acc += d * d; }
+        } else {
+            for (; i + 16 <= dim; i += 16) {
+                for (int j = i; j < i + 16; j++) acc += std::fabs(a[j] - b[j]);
+                if (acc >= f) return false;
+            }
+            for (; i < dim; i++) acc += std::fabs(a[i] - b[i]);
+        }
+        return acc < f;
+    }
+    return host_distance(elem, metric, dim, pa, pb) < f;
+}
+
 // ------------------------------------------------------------------------------------------------
 // tiny fork-join pool
 // ------------------------------------------------------------------------------------------------
@@ -165,6 +192,7 @@ struct BuildState {
 
     const uint8_t *row(int64_t e) const { return values.data() + (size_t)e * row_bytes; }
     float dist(int64_t a, int64_t b) const { return host_distance(elem, metric, dim, row(a), row(b)); }
+    bool dist_less(int64_t a, int64_t b, float f) const { return host_distance_less(elem, metric, dim, row(a), row(b), f); }
     int lm(int lc) const { return lc == 0 ? 2 * m : m; }
     int32_t *ids(int64_t v, int lc) { return lc == 0 ? &adj0[(size_t)v * 2 * m] : &adj_up[(size_t)(upper_base[(size_t)v] + lc - 1) * m]; }
     float *dists(int64_t v, int lc) { return lc == 0 ? &dist0[(size_t)v * 2 * m] : &dist_up[(size_t)(upper_base[(size_t)v] + lc - 1) * m]; }
@@ -208,10 +236,10 @@ struct Pending {                 // one element of the current round, after phas
 struct Group {
     int32_t node, lc;
     int n_list;                       // list length at the start of the round
-    std::vector<int32_t> ids;         // list at the start of the round, then the pending elements that selected it
-    std::vector<int32_t> old_ids;     // the list as the round's searches saw it
-    std::vector<int16_t> pos;         // position in `ids` of every entry of the CURRENT list (-1: unknown)
-    int64_t mat;                      // offset of the group's pairwise matrix (floats) or -1
+    int row_off;                      // first row of the group in the GPU mask arrays, -1: distances on the host
+    std::vector<int32_t> ids;         // the list as the round's searches saw it, then the pending elements linking to it
+    std::vector<float> own;           // distance of every entry of `ids` to the node
+    std::vector<int16_t> pos;         // position in `ids` of every entry of the CURRENT list
     bool modified;
 };
 
@@ -223,29 +251,36 @@ static inline uint32_t ord_of(float d) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// select_neighbors with check_element_closer's distances looked up in a GPU-computed pairwise matrix
-static void select_neighbors_mat(BuildState &g, const Cand *cand, const int16_t *pos, int n_cand, int max_neighbors,
-                                 const float *mat, int mat_n, std::vector<Cand> &out, std::vector<int16_t> &out_pos) {
+// select_neighbors (graph/mod.rs:269-308) with check_element_closer answered by the GPU's masks:
+// masks[pos * W .. +W) has bit r set iff d(member pos, member r) <= own[pos]  (W = PAIR_MAX_ROWS / 32 words)
+static void select_neighbors_mask(BuildState &g, const Cand *cand, const int16_t *pos, int n_cand, int max_neighbors,
+                                  const uint32_t *masks, std::vector<Cand> &out, std::vector<int16_t> &out_pos) {
+    constexpr int W = PAIR_MAX_ROWS / 32;
     out.clear();
     out_pos.clear();
     if (n_cand <= max_neighbors) { out.assign(cand, cand + n_cand); out_pos.assign(pos, pos + n_cand); return; }
-    std::vector<int> discarded;
+    uint32_t kept[W] = {0};
+    int discarded[PAIR_MAX_ROWS + 1];
+    int n_disc = 0;
     uint64_t pairs = 0;
     for (int i = 0; i < n_cand; i++) {
         if ((int)out.size() >= max_neighbors) break;
-        const Cand &e = cand[i];
-        bool closer = true;
-        for (size_t r = 0; r < out.size(); r++) {
-            const float d = (pos[i] >= 0 && out_pos[r] >= 0) ? mat[(size_t)pos[i] * mat_n + out_pos[r]] : g.dist(e.idx, out[r].idx);
-            pairs++;
-            if (d <= e.distance) { closer = false; break; }
+        const uint32_t *c = masks + (size_t)pos[i] * W;
+        uint32_t hit = 0;
+        for (int w = 0; w < W; w++) hit |= c[w] & kept[w];
+        pairs += out.size();
+        if (!hit) {
+            out.push_back(cand[i]);
+            out_pos.push_back(pos[i]);
+            kept[pos[i] >> 5] |= 1u << (pos[i] & 31);
+        } else {
+            discarded[n_disc++] = i;
         }
-        if (closer) { out.push_back(e); out_pos.push_back(pos[i]); } else discarded.push_back(i);
     }
-    for (int di : discarded) {
+    for (int t = 0; t < n_disc; t++) {
         if ((int)out.size() >= max_neighbors) break;
-        out.push_back(cand[di]);
-        out_pos.push_back(pos[di]);
+        out.push_back(cand[discarded[t]]);
+        out_pos.push_back(pos[discarded[t]]);
     }
     g.n_pair.fetch_add(pairs, std::memory_order_relaxed);
 }
@@ -257,10 +292,10 @@ using namespace pgvrx_host;
 namespace {
 
 struct RoundBuffers {
-    DevBuf elem_ids, w_ids, w_dists, w_counts, rs_log, rs_counts, status, ctr, vis, work, sc_off, sc_rows, g_ids, g_off, g_moff, g_mat;
+    DevBuf elem_ids, w_ids, w_dists, w_counts, rs_log, rs_counts, status, ctr, vis, work, sc_off, sc_rows, g_ids, g_off, g_own, g_mat;
     void release() {
         DevBuf *b[] = {&elem_ids, &w_ids, &w_dists, &w_counts, &rs_log, &rs_counts, &status, &ctr, &vis, &work, &sc_off, &sc_rows,
-                       &g_ids, &g_off, &g_moff, &g_mat};
+                       &g_ids, &g_off, &g_own, &g_mat};
         for (DevBuf *x : b) x->release();
     }
 };
@@ -440,10 +475,13 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     const int WINDOW_MAX = 512;
     bool big_next = false;
     const int rs_cap = std::max(256, 6 * efc + 64);
-    std::vector<Group> groups;
-    std::unordered_map<uint64_t, int> group_of;
+    std::vector<Group> groups;                          // reused across rounds (n_groups live entries)
+    int n_groups = 0;
+    std::unordered_map<uint64_t, int> group_up;         // (node, layer >= 1) -> group; layer 0 uses the stamp arrays
+    std::vector<uint32_t> gstamp0;
+    std::vector<int32_t> gidx0;
     std::vector<int32_t> h_gids, h_goff;
-    std::vector<int64_t> h_moff;
+    std::vector<float> h_gown;
     PinnedBuf h_mat;
     uint64_t n_pair_gpu = 0, n_val_dist = 0;
     uint64_t why_overflow = 0, why_notfull = 0, why_pending = 0, why_order = 0;   // conflict reasons (PGVRX_BUILD_DEBUG)
@@ -579,82 +617,93 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         //      (graph/mod.rs:473-485) the pairwise distances among list + newcomers come from the GPU. ----
         const double tG0 = now_ms();
         t_phase_a += tG0 - tA0;
-        groups.clear();
-        group_of.clear();
+        n_groups = 0;
+        group_up.clear();
+        auto find_group = [&](int32_t node, int lc) -> int {
+            if (lc == 0) return gstamp0[(size_t)node] == g.round ? gidx0[(size_t)node] : -1;
+            auto it = group_up.find(((uint64_t)(uint32_t)node << 8) | (uint64_t)lc);
+            return it == group_up.end() ? -1 : it->second;
+        };
+        if ((int64_t)gstamp0.size() < cap) { gstamp0.resize((size_t)cap, 0); gidx0.resize((size_t)cap, -1); }
         for (int i = 0; i < B; i++) {
             const Pending &p = pend[(size_t)i];
             if (h_status[(size_t)i] != 0) break;               // nothing after an overflowed search can commit this round
             for (int lc = 0; lc < (int)p.sel.size(); lc++)
                 for (const Cand &nb : p.sel[(size_t)lc]) {
-                    const uint64_t key = ((uint64_t)(uint32_t)nb.idx << 8) | (uint64_t)lc;
-                    auto it = group_of.find(key);
-                    if (it == group_of.end()) {
-                        it = group_of.emplace(key, (int)groups.size()).first;
-                        groups.emplace_back();
-                        Group &G = groups.back();
+                    int gi = find_group(nb.idx, lc);
+                    if (gi < 0) {
+                        gi = n_groups++;
+                        if ((int)groups.size() < n_groups) groups.emplace_back();
+                        if (lc == 0) { gstamp0[(size_t)nb.idx] = g.round; gidx0[(size_t)nb.idx] = gi; }
+                        else group_up.emplace(((uint64_t)(uint32_t)nb.idx << 8) | (uint64_t)lc, gi);
+                        Group &G = groups[(size_t)gi];
                         G.node = nb.idx;
                         G.lc = lc;
                         G.n_list = g.cnt(nb.idx, lc);
                         const int32_t *ids = g.ids(nb.idx, lc);
+                        const float *ds = g.dists(nb.idx, lc);
                         G.ids.assign(ids, ids + G.n_list);
+                        G.own.assign(ds, ds + G.n_list);
+                        G.modified = false;
                     }
-                    groups[(size_t)it->second].ids.push_back((int32_t)(e_base + i));
+                    groups[(size_t)gi].ids.push_back((int32_t)(e_base + i));
+                    groups[(size_t)gi].own.push_back(nb.distance);
                 }
         }
         h_gids.clear();
+        h_gown.clear();
         h_goff.clear();
-        h_moff.clear();
-        int64_t mat_floats = 0;
         int n_dev_groups = 0;
-        for (Group &G : groups) {
+        for (int gi = 0; gi < n_groups; gi++) {
+            Group &G = groups[(size_t)gi];
             const int total = (int)G.ids.size();
-            G.old_ids.assign(G.ids.begin(), G.ids.begin() + G.n_list);
             G.pos.resize((size_t)G.n_list);
             for (int t = 0; t < G.n_list; t++) G.pos[(size_t)t] = (int16_t)t;
-            G.modified = false;
-            G.mat = -1;
+            G.row_off = -1;
             if (total > g.lm(G.lc) && total <= pair_rows) {     // a re-selection can happen and the group fits on a CTA
-                G.mat = mat_floats;
+                G.row_off = (int)h_gids.size();
                 h_goff.push_back((int32_t)h_gids.size());
-                h_moff.push_back(mat_floats);
                 h_gids.insert(h_gids.end(), G.ids.begin(), G.ids.end());
-                mat_floats += (int64_t)total * total;
+                h_gown.insert(h_gown.end(), G.own.begin(), G.own.end());
                 n_dev_groups++;
             }
         }
         h_goff.push_back((int32_t)h_gids.size());
         t_groups += now_ms() - tG0;
+        constexpr int MW = PAIR_MAX_ROWS / 32;
         if (n_dev_groups > 0) {
             const double tp0 = now_ms();
-            CU_TRY(ix, rb.g_ids.ensure(h_gids.size() * 4));
+            const size_t n_rows_dev = h_gids.size();
+            CU_TRY(ix, rb.g_ids.ensure(n_rows_dev * 4));
+            CU_TRY(ix, rb.g_own.ensure(n_rows_dev * 4));
             CU_TRY(ix, rb.g_off.ensure(h_goff.size() * 4));
-            CU_TRY(ix, rb.g_moff.ensure(h_moff.size() * 8));
-            CU_TRY(ix, rb.g_mat.ensure((size_t)mat_floats * 4));
-            CU_TRY(ix, h_mat.ensure((size_t)mat_floats * 4));
-            CU_TRY(ix, cudaMemcpyAsync(rb.g_ids.p, h_gids.data(), h_gids.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, rb.g_mat.ensure(n_rows_dev * MW * 4));
+            CU_TRY(ix, h_mat.ensure(n_rows_dev * MW * 4));
+            CU_TRY(ix, cudaMemcpyAsync(rb.g_ids.p, h_gids.data(), n_rows_dev * 4, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, cudaMemcpyAsync(rb.g_own.p, h_gown.data(), n_rows_dev * 4, cudaMemcpyHostToDevice, ix->stream));
             CU_TRY(ix, cudaMemcpyAsync(rb.g_off.p, h_goff.data(), h_goff.size() * 4, cudaMemcpyHostToDevice, ix->stream));
-            CU_TRY(ix, cudaMemcpyAsync(rb.g_moff.p, h_moff.data(), h_moff.size() * 8, cudaMemcpyHostToDevice, ix->stream));
             CU_TRY(ix, cudaMemsetAsync((int *)rb.work.p + 8, 0, 4, ix->stream));
             PairParams pp;
             pp.ids = (const int32_t *)rb.g_ids.p;
+            pp.own_dist = (const float *)rb.g_own.p;
             pp.group_off = (const int32_t *)rb.g_off.p;
-            pp.mat_off = (const int64_t *)rb.g_moff.p;
             pp.n_groups = n_dev_groups;
-            pp.out = (float *)rb.g_mat.p;
+            pp.out = (uint32_t *)rb.g_mat.p;
             pp.work_counter = (int *)rb.work.p + 8;
             pp.stage_stride = cfg.L.stage_stride;
             CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
             CU_TRY(ix, launch_pairwise(ix->desc.elem_type, ix->desc.metric, gv, pp, pair_rows, std::min(n_dev_groups, ix->sm_count * pair_occ), ix->stream));
             CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));
-            CU_TRY(ix, cudaMemcpyAsync(h_mat.p, rb.g_mat.p, (size_t)mat_floats * 4, cudaMemcpyDeviceToHost, ix->stream));
+            CU_TRY(ix, cudaMemcpyAsync(h_mat.p, rb.g_mat.p, n_rows_dev * MW * 4, cudaMemcpyDeviceToHost, ix->stream));
             CU_TRY(ix, cudaStreamSynchronize(ix->stream));
             float kms = 0.0f;
             CU_TRY(ix, cudaEventElapsedTime(&kms, ix->ev0, ix->ev1));
             kernel_ms += kms;
             gpu_ms += now_ms() - tp0;
-            n_pair_gpu += (uint64_t)mat_floats;
+            for (int gi = 0; gi < n_groups; gi++)
+                if (groups[(size_t)gi].row_off >= 0) n_pair_gpu += (uint64_t)groups[(size_t)gi].ids.size() * groups[(size_t)gi].ids.size();
         }
-        const float *mat_all = (const float *)h_mat.p;
+        const uint32_t *mask_all = (const uint32_t *)h_mat.p;
 
         // ---- host: sequential validation + commit in insert order ----
         const double tC0 = now_ms();
@@ -662,7 +711,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         bool stop = false;
         std::vector<Cand> all, sel_out;
         std::vector<int16_t> all_pos, sel_pos;
-        std::vector<std::pair<int32_t, float>> dcache;          // d(pending element, y) computed during one validation
+        std::vector<std::pair<int32_t, bool>> dcache;           // d(pending element, y) < f_t for the f_t below
+        uint32_t dcache_ford = 0;
         for (int i = 0; i < B && !stop; i++) {
             Pending &p = pend[(size_t)i];
             const int64_t e = e_base + i;
@@ -681,41 +731,47 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             if (i > 0) {
                 if (h_rscnt[(size_t)i] > rs_cap) { valid = false; why_overflow++; }
                 dcache.clear();
+                dcache_ford = 0;
                 const int32_t *rs = &h_rs[(size_t)i * rs_cap * 3];
                 for (int t = 0; valid && t < h_rscnt[(size_t)i]; t++) {
                     const int32_t v = rs[3 * t], lc = rs[3 * t + 2];
                     if (g.stamp[(size_t)v] != g.round) continue;
-                    auto it = group_of.find(((uint64_t)(uint32_t)v << 8) | (uint64_t)lc);
-                    if (it == group_of.end()) continue;
-                    const Group &G = groups[(size_t)it->second];
+                    const int gi = find_group(v, lc);
+                    if (gi < 0) continue;
+                    const Group &G = groups[(size_t)gi];
                     if (!G.modified) continue;
+                    const int n_old = G.n_list;
+                    const int32_t *l_old = G.ids.data();
                     const uint32_t ford = (uint32_t)rs[3 * t + 1];
                     const int n_new = g.cnt(v, lc);
                     const int32_t *l_new = g.ids(v, lc);
                     if (ford == 0xFFFFFFFFu) {                  // W not full: any change of the list matters
-                        valid = n_new == (int)G.old_ids.size() && std::equal(l_new, l_new + n_new, G.old_ids.begin());
+                        valid = n_new == n_old && std::equal(l_new, l_new + n_new, l_old);
                         if (!valid) why_notfull++;
                         continue;
                     }
-                    auto near = [&](int32_t y) -> bool {        // d(e, y) < f_t, exactly as the kernel compares
-                        float d = 0.0f;
-                        bool have = false;
-                        for (auto &c : dcache) if (c.first == y) { d = c.second; have = true; break; }
-                        if (!have) { d = g.dist(e, y); dcache.emplace_back(y, d); n_val_dist++; }
-                        return ord_of(d) < ford;
+                    // d(e, y) < f_t, exactly as the kernel compares (ordered bits; -0 == +0)
+                    float f_t;
+                    { const uint32_t bits = (ford & 0x80000000u) ? (ford & 0x7FFFFFFFu) : ~ford; memcpy(&f_t, &bits, 4); }
+                    if (dcache_ford != ford) { dcache.clear(); dcache_ford = ford; }
+                    auto near = [&](int32_t y) -> bool {
+                        for (auto &c : dcache) if (c.first == y) return c.second;
+                        const bool r = g.dist_less(e, y, f_t);
+                        dcache.emplace_back(y, r);
+                        n_val_dist++;
+                        return r;
                     };
-                    size_t io = 0;
-                    int in_ = 0;
+                    int io = 0, in_ = 0;
                     while (valid) {
-                        while (io < G.old_ids.size() && !near(G.old_ids[io])) io++;
+                        while (io < n_old && !near(l_old[io])) io++;
                         while (in_ < n_new && !near(l_new[in_])) in_++;
-                        const bool eo = io >= G.old_ids.size(), en = in_ >= n_new;
+                        const bool eo = io >= n_old, en = in_ >= n_new;
                         if (eo || en) {
                             valid = eo && en;
                             if (!valid) { if (!en && l_new[in_] >= e_base) why_pending++; else why_order++; }
                             break;
                         }
-                        if (G.old_ids[io] != l_new[in_]) { valid = false; if (l_new[in_] >= e_base) why_pending++; else why_order++; }
+                        if (l_old[io] != l_new[in_]) { valid = false; if (l_new[in_] >= e_base) why_pending++; else why_order++; }
                         io++;
                         in_++;
                     }
@@ -757,7 +813,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             for (int lc = p.level; lc >= 0; lc--) {             // :455 for lc in (0..=level).rev()
                 if (lc > top) continue;
                 for (const Cand &nb : p.sel[(size_t)lc]) {
-                    Group &G = groups[(size_t)group_of[((uint64_t)(uint32_t)nb.idx << 8) | (uint64_t)lc]];
+                    Group &G = groups[(size_t)find_group(nb.idx, lc)];
                     const int lm = g.lm(lc);
                     int32_t *ids = g.ids(nb.idx, lc);
                     float *ds = g.dists(nb.idx, lc);
@@ -783,8 +839,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                             all[(size_t)t2] = src < (int)c ? Cand{ds[src], ids[src]} : Cand{nb.distance, (int32_t)e};
                             all_pos[(size_t)t2] = src < (int)c ? G.pos[(size_t)src] : epos;
                         }
-                        if (G.mat >= 0)
-                            select_neighbors_mat(g, all.data(), all_pos.data(), n_all, lm, mat_all + G.mat, (int)G.ids.size(), sel_out, sel_pos);
+                        if (G.row_off >= 0)
+                            select_neighbors_mask(g, all.data(), all_pos.data(), n_all, lm, mask_all + (size_t)G.row_off * MW, sel_out, sel_pos);
                         else {
                             select_neighbors(g, all.data(), n_all, lm, sel_out);
                             sel_pos.assign(sel_out.size(), (int16_t)-1);
@@ -812,7 +868,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         // ---- device graph := committed state ----
         const double tS0 = now_ms();
         t_commit += tS0 - tC0;
-        for (const Group &G : groups) if (G.modified) queue_row(G.node, G.lc);
+        for (int gi = 0; gi < n_groups; gi++) if (groups[(size_t)gi].modified) queue_row(groups[(size_t)gi].node, groups[(size_t)gi].lc);
         for (int64_t e = e_base; e < g.n; e++) {
             queue_row(e, 0);
             for (int l = 1; l <= g.level[(size_t)e]; l++) queue_row(e, l);

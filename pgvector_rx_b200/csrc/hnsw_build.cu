@@ -140,11 +140,14 @@ __global__ void scatter_rows_kernel(int32_t *dst, const int64_t *row_offsets, co
 
 
 // ---------------------------------------------------------------------------------------------------
-// Pairwise distances inside small groups of elements (select_neighbors' check_element_closer,
-// graph/mod.rs:315-339, when update_neighbor_connections re-selects a full list, :473-485).  One CTA per
-// group: the group's rows are staged once (one TMA bulk copy per row), then lane <-> column b and a row a
-// broadcast from shared memory give d(a, b) with the same sequential arithmetic as everywhere else.
-// out: cnt x cnt floats per group (symmetric; both halves are written).
+// check_element_closer for whole groups (graph/mod.rs:315-339), used when update_neighbor_connections
+// re-selects a full list (:473-485).  A group is a node's neighbour list plus the pending elements that link
+// back to it; every member a carries its distance to the node, own[a].  The heuristic only ever asks
+// "is d(a, r) <= own[a]" for some already kept r, so the kernel answers that for ALL pairs at once:
+//     mask[a] bit b  =  d(a, b) <= own[a]
+// (128 bits per member).  On the host a candidate is then rejected iff mask[a] & kept != 0.
+// One CTA per group: the rows are staged once (one TMA bulk copy per row), lane <-> column b, row a is
+// broadcast from shared memory; distances use the same sequential arithmetic as everywhere else.
 // ---------------------------------------------------------------------------------------------------
 template <int ELEM, int METRIC>
 __global__ void __launch_bounds__(SEARCH_THREADS) pairwise_kernel(GraphView g, PairParams p) {
@@ -164,7 +167,6 @@ __global__ void __launch_bounds__(SEARCH_THREADS) pairwise_kernel(GraphView g, P
         const int gi = s_group;
         if (gi >= p.n_groups) break;
         const int off = p.group_off[gi], cnt = p.group_off[gi + 1] - off;
-        float *out = p.out + p.mat_off[gi];
         if (t == 0) mbar_arrive_expect_tx(mbar, (uint32_t)cnt * g.row_stride);
         __syncthreads();
         if (t < cnt)
@@ -173,9 +175,13 @@ __global__ void __launch_bounds__(SEARCH_THREADS) pairwise_kernel(GraphView g, P
         phase ^= 1u;
         for (int a = warp; a < cnt; a += SEARCH_THREADS / 32) {
             const uint8_t *ra = stage + (size_t)a * p.stage_stride;
-            for (int b0 = 0; b0 < cnt; b0 += 32) {
+            const float own = p.own_dist[off + a];
+            for (int b0 = 0; b0 < PAIR_MAX_ROWS; b0 += 32) {
                 const int b = b0 + lane;
-                if (b < cnt) out[(size_t)a * cnt + b] = row_distance<ELEM, METRIC>(ra, stage + (size_t)b * p.stage_stride, nvec);
+                bool le = false;
+                if (b0 < cnt && b < cnt) le = row_distance<ELEM, METRIC>(ra, stage + (size_t)b * p.stage_stride, nvec) <= own;   // :333
+                const uint32_t word = b0 < cnt ? __ballot_sync(FULL, le) : 0u;
+                if (lane == 0) p.out[((size_t)off + a) * (PAIR_MAX_ROWS / 32) + (b0 >> 5)] = word;
             }
         }
         // generic-proxy reads of the staging rows are ordered before the next group's TMA writes

@@ -61,14 +61,14 @@ struct BuildParams {
     int R;
 };
 
-// pairwise distances inside groups of <= PAIR_MAX_ROWS elements (hnsw_build.cu)
+// check_element_closer masks for groups of <= PAIR_MAX_ROWS elements (hnsw_build.cu)
 constexpr int PAIR_MAX_ROWS = 128;
 struct PairParams {
     const int32_t *ids;        // concatenated element ids of all groups
+    const float *own_dist;     // per member: its distance to the group's node
     const int32_t *group_off;  // n_groups + 1 offsets into ids
-    const int64_t *mat_off;    // n_groups float offsets into out
     int n_groups;
-    float *out;                // per group cnt x cnt distances
+    uint32_t *out;             // per member PAIR_MAX_ROWS / 32 words: bit b set <=> d(member, b) <= own_dist[member]
     int *work_counter;
     uint32_t stage_stride;
 };
