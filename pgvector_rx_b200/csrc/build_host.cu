@@ -230,6 +230,8 @@ struct Pending {                 // one element of the current round, after phas
     int level;
     std::vector<std::vector<Cand>> sel;   // [lc] selected neighbours (graph/mod.rs:419-422)
     int dup_of = -1;                      // element id this row merges into (build.rs:482-503)
+    std::vector<int32_t> near_idx;        // per logged expansion: offset into near_bits, -1 none, -2 decide lazily
+    std::vector<uint32_t> near_bits;      // PAIR_MAX_ROWS bits per entry: group member nearer than f_dist at that expansion
 };
 
 // one (node, layer) list that pending elements of the current round link back to
@@ -239,9 +241,26 @@ struct Group {
     int row_off;                      // first row of the group in the GPU mask arrays, -1: distances on the host
     std::vector<int32_t> ids;         // the list as the round's searches saw it, then the pending elements linking to it
     std::vector<float> own;           // distance of every entry of `ids` to the node
-    std::vector<int16_t> pos;         // position in `ids` of every entry of the CURRENT list
+    // the list after each of the pending elements has been linked in, in order (graph/mod.rs:458-487), computed for
+    // the whole round up front -- a group's evolution depends on nothing but the group -- so that the sequential commit
+    // only advances `step`: state k (0-based) = list after members 0..k, lm entries each
+    std::vector<int32_t> st_ids;
+    std::vector<float> st_ds;
+    std::vector<int16_t> st_pos;      // position in `ids` of every entry of that list
+    std::vector<uint8_t> st_cnt;
+    int lm;
+    int step;                         // members committed so far (0: the list is still the one the searches saw)
     bool modified;
 };
+
+static int16_t g_identity_pos[256];
+
+// the list of a group as it stands after `step` committed members
+static inline void group_list(const Group &G, const int32_t *&ids, const float *&ds, const int16_t *&pos, int &cnt) {
+    if (G.step == 0) { ids = G.ids.data(); ds = G.own.data(); pos = g_identity_pos; cnt = G.n_list; return; }
+    const size_t o = (size_t)(G.step - 1) * G.lm;
+    ids = &G.st_ids[o]; ds = &G.st_ds[o]; pos = &G.st_pos[o]; cnt = G.st_cnt[(size_t)G.step - 1];
+}
 
 // order-preserving bits of a distance, as the kernels compare them (hnsw_device.cuh f32_ord)
 static inline uint32_t ord_of(float d) {
@@ -283,6 +302,55 @@ static void select_neighbors_mask(BuildState &g, const Cand *cand, const int16_t
         out_pos.push_back(pos[discarded[t]]);
     }
     g.n_pair.fetch_add(pairs, std::memory_order_relaxed);
+}
+
+// update_neighbor_connections for one (node, layer) and all pending elements that link to it, in insert order
+// (graph/mod.rs:458-487): append while there is room, otherwise stable-sort list + newcomer by distance and re-select.
+static void simulate_group(BuildState &g, Group &G, const uint32_t *masks /* rows of this group or NULL */) {
+    const int lm = G.lm, n_members = (int)G.ids.size() - G.n_list;
+    G.st_ids.assign((size_t)n_members * lm, -1);
+    G.st_ds.assign((size_t)n_members * lm, 0.0f);
+    G.st_pos.assign((size_t)n_members * lm, -1);
+    G.st_cnt.assign((size_t)n_members, 0);
+    Cand cur[256], all[257];
+    int16_t cur_pos[256], all_pos[257];
+    int order[257];
+    int cnt = G.n_list;
+    for (int t = 0; t < cnt; t++) { cur[t] = Cand{G.own[(size_t)t], G.ids[(size_t)t]}; cur_pos[t] = (int16_t)t; }
+    std::vector<Cand> sel_out;
+    std::vector<int16_t> sel_pos;
+    for (int k = 0; k < n_members; k++) {
+        const int16_t epos = (int16_t)(G.n_list + k);
+        const Cand nw{G.own[(size_t)epos], G.ids[(size_t)epos]};
+        if (cnt < lm) {                                          // :469-471 room available
+            cur[cnt] = nw;
+            cur_pos[cnt] = epos;
+            cnt++;
+        } else {                                                 // :473-485
+            const int n_all = cnt + 1;
+            for (int t = 0; t < n_all; t++) order[t] = t;
+            auto dist_of = [&](int t) { return t < cnt ? cur[t].distance : nw.distance; };
+            std::stable_sort(order, order + n_all, [&](int x, int y) { return dist_of(x) < dist_of(y); });
+            for (int t = 0; t < n_all; t++) {
+                const int src = order[t];
+                all[t] = src < cnt ? cur[src] : nw;
+                all_pos[t] = src < cnt ? cur_pos[src] : epos;
+            }
+            if (masks) select_neighbors_mask(g, all, all_pos, n_all, lm, masks, sel_out, sel_pos);
+            else { select_neighbors(g, all, n_all, lm, sel_out); sel_pos.resize(sel_out.size()); }
+            cnt = (int)sel_out.size();
+            for (int t = 0; t < cnt; t++) { cur[t] = sel_out[(size_t)t]; cur_pos[t] = masks ? sel_pos[(size_t)t] : (int16_t)-1; }
+            if (!masks) {
+                // positions are still needed by the validation: recover them by id (small groups only take this path
+                // when they do not fit on a CTA, i.e. rarely)
+                for (int t = 0; t < cnt; t++)
+                    for (size_t u = 0; u < G.ids.size(); u++) if (G.ids[u] == cur[t].idx) { cur_pos[t] = (int16_t)u; break; }
+            }
+        }
+        const size_t o = (size_t)k * lm;
+        for (int t = 0; t < cnt; t++) { G.st_ids[o + t] = cur[t].idx; G.st_ds[o + t] = cur[t].distance; G.st_pos[o + t] = cur_pos[t]; }
+        G.st_cnt[(size_t)k] = (uint8_t)cnt;
+    }
 }
 
 }  // namespace pgvrx_host
@@ -484,6 +552,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     std::vector<float> h_gown;
     PinnedBuf h_mat;
     uint64_t n_pair_gpu = 0, n_val_dist = 0;
+    std::atomic<uint64_t> n_val_dist_atomic{0};
+    double t_near = 0, t_sim = 0;
+    for (int t = 0; t < 256; t++) g_identity_pos[t] = (int16_t)t;
     uint64_t why_overflow = 0, why_notfull = 0, why_pending = 0, why_order = 0;   // conflict reasons (PGVRX_BUILD_DEBUG)
     double t_phase_a = 0, t_groups = 0, t_commit = 0, t_scatter = 0;
     // rows a pairwise group may hold: what fits in one CTA's shared memory, at most PAIR_MAX_ROWS
@@ -644,6 +715,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                         const float *ds = g.dists(nb.idx, lc);
                         G.ids.assign(ids, ids + G.n_list);
                         G.own.assign(ds, ds + G.n_list);
+                        G.lm = g.lm(lc);
+                        G.step = 0;
                         G.modified = false;
                     }
                     groups[(size_t)gi].ids.push_back((int32_t)(e_base + i));
@@ -657,8 +730,6 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         for (int gi = 0; gi < n_groups; gi++) {
             Group &G = groups[(size_t)gi];
             const int total = (int)G.ids.size();
-            G.pos.resize((size_t)G.n_list);
-            for (int t = 0; t < G.n_list; t++) G.pos[(size_t)t] = (int16_t)t;
             G.row_off = -1;
             if (total > g.lm(G.lc) && total <= pair_rows) {     // a re-selection can happen and the group fits on a CTA
                 G.row_off = (int)h_gids.size();
@@ -695,24 +766,71 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             CU_TRY(ix, launch_pairwise(ix->desc.elem_type, ix->desc.metric, gv, pp, pair_rows, std::min(n_dev_groups, ix->sm_count * pair_occ), ix->stream));
             CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));
             CU_TRY(ix, cudaMemcpyAsync(h_mat.p, rb.g_mat.p, n_rows_dev * MW * 4, cudaMemcpyDeviceToHost, ix->stream));
+            gpu_ms += now_ms() - tp0;
+        }
+
+        // ---- host (parallel, overlapping the mask kernel): for every expansion of every pending search that read a list
+        //      with a group, which members of the group are nearer than W's furthest distance at that expansion ----
+        const double tN0 = now_ms();
+        int n_ok = 0;
+        while (n_ok < B && h_status[(size_t)n_ok] == 0) n_ok++;
+        pool.parallel_for(n_ok, [&](int64_t i) {
+            Pending &p = pend[(size_t)i];
+            const int n_log = std::min(h_rscnt[(size_t)i], rs_cap);
+            p.near_idx.assign((size_t)n_log, -1);
+            p.near_bits.clear();
+            if (i == 0 || h_rscnt[(size_t)i] > rs_cap) return;     // the head needs no validation; an overflowed log cannot be validated
+            const int32_t *rs = &h_rs[(size_t)i * rs_cap * 3];
+            const int64_t e = e_base + i;
+            uint64_t nd = 0;
+            for (int t = 0; t < n_log; t++) {
+                const uint32_t ford = (uint32_t)rs[3 * t + 1];
+                if (ford == 0xFFFFFFFFu) continue;
+                const int gi = find_group(rs[3 * t], rs[3 * t + 2]);
+                if (gi < 0) continue;
+                const Group &G = groups[(size_t)gi];
+                // only members before this element can have changed the list by the time it is validated
+                if (G.ids[(size_t)G.n_list] >= (int32_t)e) continue;
+                if ((int)G.ids.size() > PAIR_MAX_ROWS) { p.near_idx[(size_t)t] = -2; continue; }     // decided lazily
+                float f_t;
+                { const uint32_t bits = (ford & 0x80000000u) ? (ford & 0x7FFFFFFFu) : ~ford; memcpy(&f_t, &bits, 4); }
+                p.near_idx[(size_t)t] = (int32_t)p.near_bits.size();
+                uint32_t w[MW] = {0};
+                for (size_t u = 0; u < G.ids.size(); u++) {
+                    if (G.ids[u] >= (int32_t)e) break;              // members from this element on are never in the list it is checked against
+                    if (g.dist_less(e, G.ids[u], f_t)) w[u >> 5] |= 1u << (u & 31);
+                    nd++;
+                }
+                p.near_bits.insert(p.near_bits.end(), w, w + MW);
+            }
+            n_val_dist_atomic.fetch_add(nd, std::memory_order_relaxed);
+        });
+        t_near += now_ms() - tN0;
+
+        if (n_dev_groups > 0) {
+            const double tp1 = now_ms();
             CU_TRY(ix, cudaStreamSynchronize(ix->stream));
             float kms = 0.0f;
             CU_TRY(ix, cudaEventElapsedTime(&kms, ix->ev0, ix->ev1));
             kernel_ms += kms;
-            gpu_ms += now_ms() - tp0;
+            gpu_ms += now_ms() - tp1;
             for (int gi = 0; gi < n_groups; gi++)
                 if (groups[(size_t)gi].row_off >= 0) n_pair_gpu += (uint64_t)groups[(size_t)gi].ids.size() * groups[(size_t)gi].ids.size();
         }
         const uint32_t *mask_all = (const uint32_t *)h_mat.p;
 
+        // ---- host (parallel by group): update_neighbor_connections for every group, all members in order ----
+        const double tB0 = now_ms();
+        pool.parallel_for(n_groups, [&](int64_t gi) {
+            Group &G = groups[(size_t)gi];
+            simulate_group(g, G, G.row_off >= 0 ? mask_all + (size_t)G.row_off * MW : nullptr);
+        });
+        t_sim += now_ms() - tB0;
+
         // ---- host: sequential validation + commit in insert order ----
         const double tC0 = now_ms();
         int committed = 0;
         bool stop = false;
-        std::vector<Cand> all, sel_out;
-        std::vector<int16_t> all_pos, sel_pos;
-        std::vector<std::pair<int32_t, bool>> dcache;           // d(pending element, y) < f_t for the f_t below
-        uint32_t dcache_ford = 0;
         for (int i = 0; i < B && !stop; i++) {
             Pending &p = pend[(size_t)i];
             const int64_t e = e_base + i;
@@ -730,8 +848,6 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             bool valid = true;
             if (i > 0) {
                 if (h_rscnt[(size_t)i] > rs_cap) { valid = false; why_overflow++; }
-                dcache.clear();
-                dcache_ford = 0;
                 const int32_t *rs = &h_rs[(size_t)i * rs_cap * 3];
                 for (int t = 0; valid && t < h_rscnt[(size_t)i]; t++) {
                     const int32_t v = rs[3 * t], lc = rs[3 * t + 2];
@@ -739,39 +855,39 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                     const int gi = find_group(v, lc);
                     if (gi < 0) continue;
                     const Group &G = groups[(size_t)gi];
-                    if (!G.modified) continue;
+                    if (G.step == 0) continue;                  // nobody has linked to it yet
                     const int n_old = G.n_list;
-                    const int32_t *l_old = G.ids.data();
                     const uint32_t ford = (uint32_t)rs[3 * t + 1];
-                    const int n_new = g.cnt(v, lc);
-                    const int32_t *l_new = g.ids(v, lc);
+                    const int32_t *l_new;
+                    const float *ds_new;
+                    const int16_t *p_new;
+                    int n_new;
+                    group_list(G, l_new, ds_new, p_new, n_new);
                     if (ford == 0xFFFFFFFFu) {                  // W not full: any change of the list matters
-                        valid = n_new == n_old && std::equal(l_new, l_new + n_new, l_old);
+                        valid = n_new == n_old && std::equal(l_new, l_new + n_new, G.ids.data());
                         if (!valid) why_notfull++;
                         continue;
                     }
-                    // d(e, y) < f_t, exactly as the kernel compares (ordered bits; -0 == +0)
+                    const int32_t ni = p.near_idx[(size_t)t];
+                    const uint32_t *bits = ni >= 0 ? &p.near_bits[(size_t)ni] : nullptr;
                     float f_t;
-                    { const uint32_t bits = (ford & 0x80000000u) ? (ford & 0x7FFFFFFFu) : ~ford; memcpy(&f_t, &bits, 4); }
-                    if (dcache_ford != ford) { dcache.clear(); dcache_ford = ford; }
-                    auto near = [&](int32_t y) -> bool {
-                        for (auto &c : dcache) if (c.first == y) return c.second;
-                        const bool r = g.dist_less(e, y, f_t);
-                        dcache.emplace_back(y, r);
+                    { const uint32_t fb = (ford & 0x80000000u) ? (ford & 0x7FFFFFFFu) : ~ford; memcpy(&f_t, &fb, 4); }
+                    auto near = [&](int pos) -> bool {          // d(e, member pos) < f_t, exactly as the kernel compares
+                        if (bits) return (bits[pos >> 5] >> (pos & 31)) & 1u;
                         n_val_dist++;
-                        return r;
+                        return g.dist_less(e, G.ids[(size_t)pos], f_t);
                     };
                     int io = 0, in_ = 0;
                     while (valid) {
-                        while (io < n_old && !near(l_old[io])) io++;
-                        while (in_ < n_new && !near(l_new[in_])) in_++;
+                        while (io < n_old && !near(io)) io++;
+                        while (in_ < n_new && !near(p_new[in_])) in_++;
                         const bool eo = io >= n_old, en = in_ >= n_new;
                         if (eo || en) {
                             valid = eo && en;
                             if (!valid) { if (!en && l_new[in_] >= e_base) why_pending++; else why_order++; }
                             break;
                         }
-                        if (l_old[io] != l_new[in_]) { valid = false; if (l_new[in_] >= e_base) why_pending++; else why_order++; }
+                        if (io != p_new[in_]) { valid = false; if (l_new[in_] >= e_base) why_pending++; else why_order++; }
                         io++;
                         in_++;
                     }
@@ -810,46 +926,11 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                 for (size_t t = 0; t < s.size(); t++) { ids[t] = s[t].idx; ds[t] = s[t].distance; }
                 g.cnt(e, lc) = (uint8_t)s.size();
             }
-            for (int lc = p.level; lc >= 0; lc--) {             // :455 for lc in (0..=level).rev()
-                if (lc > top) continue;
+            for (int lc = std::min(p.level, top); lc >= 0; lc--) {   // :455 for lc in (0..=level).rev(); lists above `top` are empty
                 for (const Cand &nb : p.sel[(size_t)lc]) {
                     Group &G = groups[(size_t)find_group(nb.idx, lc)];
-                    const int lm = g.lm(lc);
-                    int32_t *ids = g.ids(nb.idx, lc);
-                    float *ds = g.dists(nb.idx, lc);
-                    uint8_t &c = g.cnt(nb.idx, lc);
-                    // position of the new element among the group's rows
-                    int16_t epos = -1;
-                    for (size_t t = (size_t)G.n_list; t < G.ids.size(); t++) if (G.ids[t] == (int32_t)e) { epos = (int16_t)t; break; }
-                    if ((int)c < lm) {                          // :469-471 room available
-                        ids[c] = (int32_t)e;
-                        ds[c] = nb.distance;
-                        G.pos.push_back(epos);
-                        c++;
-                    } else {                                    // :473-485 re-select over list + new, replace the list
-                        const int n_all = (int)c + 1;
-                        all.resize((size_t)n_all);
-                        all_pos.resize((size_t)n_all);
-                        std::vector<int> order((size_t)n_all);
-                        for (int t2 = 0; t2 < n_all; t2++) order[(size_t)t2] = t2;
-                        auto dist_of = [&](int t2) { return t2 < (int)c ? ds[t2] : nb.distance; };
-                        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return dist_of(x) < dist_of(y); });
-                        for (int t2 = 0; t2 < n_all; t2++) {
-                            const int src = order[(size_t)t2];
-                            all[(size_t)t2] = src < (int)c ? Cand{ds[src], ids[src]} : Cand{nb.distance, (int32_t)e};
-                            all_pos[(size_t)t2] = src < (int)c ? G.pos[(size_t)src] : epos;
-                        }
-                        if (G.row_off >= 0)
-                            select_neighbors_mask(g, all.data(), all_pos.data(), n_all, lm, mask_all + (size_t)G.row_off * MW, sel_out, sel_pos);
-                        else {
-                            select_neighbors(g, all.data(), n_all, lm, sel_out);
-                            sel_pos.assign(sel_out.size(), (int16_t)-1);
-                        }
-                        for (size_t t2 = 0; t2 < sel_out.size(); t2++) { ids[t2] = sel_out[t2].idx; ds[t2] = sel_out[t2].distance; }
-                        for (int t2 = (int)sel_out.size(); t2 < lm; t2++) ids[t2] = -1;
-                        c = (uint8_t)sel_out.size();
-                        G.pos.assign(sel_pos.begin(), sel_pos.end());
-                    }
+                    // commits are a prefix of the batch and a group's members are in batch order: this is the next one
+                    G.step++;
                     G.modified = true;
                     g.stamp[(size_t)nb.idx] = g.round;
                 }
@@ -868,7 +949,21 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         // ---- device graph := committed state ----
         const double tS0 = now_ms();
         t_commit += tS0 - tC0;
-        for (int gi = 0; gi < n_groups; gi++) if (groups[(size_t)gi].modified) queue_row(groups[(size_t)gi].node, groups[(size_t)gi].lc);
+        for (int gi = 0; gi < n_groups; gi++) {
+            const Group &G = groups[(size_t)gi];
+            if (!G.modified) continue;
+            const int32_t *l;
+            const float *d;
+            const int16_t *pp_;
+            int cnt;
+            group_list(G, l, d, pp_, cnt);
+            int32_t *ids = g.ids(G.node, G.lc);
+            float *ds = g.dists(G.node, G.lc);
+            for (int t = 0; t < cnt; t++) { ids[t] = l[t]; ds[t] = d[t]; }
+            for (int t = cnt; t < G.lm; t++) ids[t] = -1;
+            g.cnt(G.node, G.lc) = (uint8_t)cnt;
+            queue_row(G.node, G.lc);
+        }
         for (int64_t e = e_base; e < g.n; e++) {
             queue_row(e, 0);
             for (int l = 1; l <= g.level[(size_t)e]; l++) queue_row(e, l);
@@ -885,9 +980,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     }
 
     if (getenv("PGVRX_BUILD_DEBUG"))
-        fprintf(stderr, "[pgvrx build] conflicts: log overflow %llu, W-not-full %llu, pending element acceptable %llu, order/removal %llu | ms: gpu %.0f (kernels %.0f) phaseA %.0f groups %.0f commit %.0f scatter %.0f\n",
+        fprintf(stderr, "[pgvrx build] conflicts: log overflow %llu, W-not-full %llu, pending element acceptable %llu, order/removal %llu | ms: gpu %.0f (kernels %.0f) phaseA %.0f groups %.0f near %.0f simulate %.0f commit %.0f scatter %.0f\n",
                 (unsigned long long)why_overflow, (unsigned long long)why_notfull, (unsigned long long)why_pending,
-                (unsigned long long)why_order, gpu_ms, kernel_ms, t_phase_a, t_groups, t_commit, t_scatter);
+                (unsigned long long)why_order, gpu_ms, kernel_ms, t_phase_a, t_groups, t_near, t_sim, t_commit, t_scatter);
     ix->n = g.n;
     ix->n_upper = g.n_upper;
     ix->entry = g.entry;
@@ -905,7 +1000,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         stats->n_expand_upper = c_expu;
         stats->n_pair = g.n_pair.load();
         stats->n_pair_gpu = n_pair_gpu;
-        stats->n_validation_dist = n_val_dist;
+        stats->n_validation_dist = n_val_dist + n_val_dist_atomic.load();
         stats->gpu_ms = gpu_ms;
         stats->kernel_ms = kernel_ms;
         stats->total_ms = now_ms() - t_start;
