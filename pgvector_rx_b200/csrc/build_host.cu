@@ -230,8 +230,6 @@ struct Pending {                 // one element of the current round, after phas
     int level;
     std::vector<std::vector<Cand>> sel;   // [lc] selected neighbours (graph/mod.rs:419-422)
     int dup_of = -1;                      // element id this row merges into (build.rs:482-503)
-    std::vector<int32_t> near_idx;        // per logged expansion: offset into near_bits, -1 none, -2 decide lazily
-    std::vector<uint32_t> near_bits;      // PAIR_MAX_ROWS bits per entry: group member nearer than f_dist at that expansion
 };
 
 // one (node, layer) list that pending elements of the current round link back to
@@ -543,9 +541,15 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     const int WINDOW_MAX = 512;
     bool big_next = false;
     const int rs_cap = std::max(256, 6 * efc + 64);
-    std::vector<Group> groups;                          // reused across rounds (n_groups live entries)
-    int n_groups = 0;
-    std::unordered_map<uint64_t, int> group_up;         // (node, layer >= 1) -> group; layer 0 uses the stamp arrays
+    const int rs_ent = 3 + (l0 + 31) / 32;               // node, f_dist bits, layer, near-mask words of the list read
+    struct GroupPart {                                  // groups of the nodes with node % NP == part; reused across rounds
+        std::vector<Group> groups;
+        int n = 0;
+        std::unordered_map<uint64_t, int> up;           // (node, layer >= 1) -> group; layer 0 uses the stamp arrays
+    };
+    const uint32_t NP = 16;
+    std::vector<GroupPart> parts(NP);
+    std::vector<Group *> all_groups;
     std::vector<uint32_t> gstamp0;
     std::vector<int32_t> gidx0;
     std::vector<int32_t> h_gids, h_goff;
@@ -599,7 +603,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         CU_TRY(ix, rb.w_ids.ensure((size_t)B * max_layers * efc * 4));
         CU_TRY(ix, rb.w_dists.ensure((size_t)B * max_layers * efc * 4));
         CU_TRY(ix, rb.w_counts.ensure((size_t)B * max_layers * 4));
-        CU_TRY(ix, rb.rs_log.ensure((size_t)B * rs_cap * 12));
+        CU_TRY(ix, rb.rs_log.ensure((size_t)B * rs_cap * rs_ent * 4));
         CU_TRY(ix, rb.rs_counts.ensure((size_t)B * 4));
         CU_TRY(ix, rb.status.ensure((size_t)B * 4));
         CU_TRY(ix, rb.ctr.ensure((size_t)B * 16));
@@ -623,6 +627,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         bp.w_counts = (int32_t *)rb.w_counts.p;
         bp.rs_log = (int32_t *)rb.rs_log.p;
         bp.rs_cap = rs_cap;
+        bp.rs_ent = rs_ent;
         bp.rs_counts = (int32_t *)rb.rs_counts.p;
         bp.out_status = (uint32_t *)rb.status.p;
         bp.out_ctr = (uint32_t *)rb.ctr.p;
@@ -638,7 +643,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         h_wids.resize((size_t)B * max_layers * efc);
         h_wd.resize((size_t)B * max_layers * efc);
         h_wcnt.resize((size_t)B * max_layers);
-        h_rs.resize((size_t)B * rs_cap * 3);
+        h_rs.resize((size_t)B * rs_cap * rs_ent);
         h_rscnt.resize((size_t)B);
         h_status.resize((size_t)B);
         h_ctr.resize((size_t)B * 4);
@@ -688,63 +693,81 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         //      (graph/mod.rs:473-485) the pairwise distances among list + newcomers come from the GPU. ----
         const double tG0 = now_ms();
         t_phase_a += tG0 - tA0;
-        n_groups = 0;
-        group_up.clear();
-        auto find_group = [&](int32_t node, int lc) -> int {
-            if (lc == 0) return gstamp0[(size_t)node] == g.round ? gidx0[(size_t)node] : -1;
-            auto it = group_up.find(((uint64_t)(uint32_t)node << 8) | (uint64_t)lc);
-            return it == group_up.end() ? -1 : it->second;
-        };
+        // groups are built by NP workers, each owning the nodes with node % NP == its part (no shared writes)
+        int n_ok = 0;
+        while (n_ok < B && h_status[(size_t)n_ok] == 0) n_ok++;      // nothing after an overflowed search can commit this round
         if ((int64_t)gstamp0.size() < cap) { gstamp0.resize((size_t)cap, 0); gidx0.resize((size_t)cap, -1); }
-        for (int i = 0; i < B; i++) {
-            const Pending &p = pend[(size_t)i];
-            if (h_status[(size_t)i] != 0) break;               // nothing after an overflowed search can commit this round
-            for (int lc = 0; lc < (int)p.sel.size(); lc++)
-                for (const Cand &nb : p.sel[(size_t)lc]) {
-                    int gi = find_group(nb.idx, lc);
-                    if (gi < 0) {
-                        gi = n_groups++;
-                        if ((int)groups.size() < n_groups) groups.emplace_back();
-                        if (lc == 0) { gstamp0[(size_t)nb.idx] = g.round; gidx0[(size_t)nb.idx] = gi; }
-                        else group_up.emplace(((uint64_t)(uint32_t)nb.idx << 8) | (uint64_t)lc, gi);
-                        Group &G = groups[(size_t)gi];
-                        G.node = nb.idx;
-                        G.lc = lc;
-                        G.n_list = g.cnt(nb.idx, lc);
-                        const int32_t *ids = g.ids(nb.idx, lc);
-                        const float *ds = g.dists(nb.idx, lc);
-                        G.ids.assign(ids, ids + G.n_list);
-                        G.own.assign(ds, ds + G.n_list);
-                        G.lm = g.lm(lc);
-                        G.step = 0;
-                        G.modified = false;
+        auto find_group = [&](int32_t node, int lc) -> Group * {
+            GroupPart &P = parts[(size_t)((uint32_t)node % NP)];
+            if (lc == 0) return gstamp0[(size_t)node] == g.round ? &P.groups[(size_t)gidx0[(size_t)node]] : nullptr;
+            auto it = P.up.find(((uint64_t)(uint32_t)node << 8) | (uint64_t)lc);
+            return it == P.up.end() ? nullptr : &P.groups[(size_t)it->second];
+        };
+        pool.parallel_for(NP, [&](int64_t part) {
+            GroupPart &P = parts[(size_t)part];
+            P.n = 0;
+            P.up.clear();
+            for (int i = 0; i < n_ok; i++) {
+                const Pending &p = pend[(size_t)i];
+                for (int lc = 0; lc < (int)p.sel.size(); lc++)
+                    for (const Cand &nb : p.sel[(size_t)lc]) {
+                        if ((int64_t)((uint32_t)nb.idx % NP) != part) continue;
+                        int gi = -1;
+                        if (lc == 0) { if (gstamp0[(size_t)nb.idx] == g.round) gi = gidx0[(size_t)nb.idx]; }
+                        else { auto it = P.up.find(((uint64_t)(uint32_t)nb.idx << 8) | (uint64_t)lc); if (it != P.up.end()) gi = it->second; }
+                        if (gi < 0) {
+                            gi = P.n++;
+                            if ((int)P.groups.size() < P.n) P.groups.emplace_back();
+                            if (lc == 0) { gstamp0[(size_t)nb.idx] = g.round; gidx0[(size_t)nb.idx] = gi; }
+                            else P.up.emplace(((uint64_t)(uint32_t)nb.idx << 8) | (uint64_t)lc, gi);
+                            Group &G = P.groups[(size_t)gi];
+                            G.node = nb.idx;
+                            G.lc = lc;
+                            G.n_list = g.cnt(nb.idx, lc);
+                            const int32_t *ids = g.ids(nb.idx, lc);
+                            const float *ds = g.dists(nb.idx, lc);
+                            G.ids.assign(ids, ids + G.n_list);
+                            G.own.assign(ds, ds + G.n_list);
+                            G.lm = g.lm(lc);
+                            G.step = 0;
+                            G.modified = false;
+                        }
+                        P.groups[(size_t)gi].ids.push_back((int32_t)(e_base + i));
+                        P.groups[(size_t)gi].own.push_back(nb.distance);
                     }
-                    groups[(size_t)gi].ids.push_back((int32_t)(e_base + i));
-                    groups[(size_t)gi].own.push_back(nb.distance);
-                }
-        }
-        h_gids.clear();
-        h_gown.clear();
-        h_goff.clear();
-        int n_dev_groups = 0;
-        for (int gi = 0; gi < n_groups; gi++) {
-            Group &G = groups[(size_t)gi];
-            const int total = (int)G.ids.size();
-            G.row_off = -1;
-            if (total > g.lm(G.lc) && total <= pair_rows) {     // a re-selection can happen and the group fits on a CTA
-                G.row_off = (int)h_gids.size();
-                h_goff.push_back((int32_t)h_gids.size());
-                h_gids.insert(h_gids.end(), G.ids.begin(), G.ids.end());
-                h_gown.insert(h_gown.end(), G.own.begin(), G.own.end());
-                n_dev_groups++;
             }
-        }
-        h_goff.push_back((int32_t)h_gids.size());
+        });
+        all_groups.clear();
+        h_goff.clear();
+        size_t n_rows_dev = 0;
+        int n_dev_groups = 0;
+        for (GroupPart &P : parts)
+            for (int gi = 0; gi < P.n; gi++) {
+                Group &G = P.groups[(size_t)gi];
+                all_groups.push_back(&G);
+                const int total = (int)G.ids.size();
+                G.row_off = -1;
+                if (total > G.lm && total <= pair_rows) {           // a re-selection can happen and the group fits on a CTA
+                    G.row_off = (int)n_rows_dev;
+                    h_goff.push_back((int32_t)n_rows_dev);
+                    n_rows_dev += (size_t)total;
+                    n_dev_groups++;
+                }
+            }
+        const int n_groups = (int)all_groups.size();
+        h_gids.resize(n_rows_dev);
+        h_gown.resize(n_rows_dev);
+        pool.parallel_for(n_groups, [&](int64_t gi) {
+            const Group &G = *all_groups[(size_t)gi];
+            if (G.row_off < 0) return;
+            std::copy(G.ids.begin(), G.ids.end(), h_gids.begin() + G.row_off);
+            std::copy(G.own.begin(), G.own.end(), h_gown.begin() + G.row_off);
+        });
+        h_goff.push_back((int32_t)n_rows_dev);
         t_groups += now_ms() - tG0;
         constexpr int MW = PAIR_MAX_ROWS / 32;
         if (n_dev_groups > 0) {
             const double tp0 = now_ms();
-            const size_t n_rows_dev = h_gids.size();
             CU_TRY(ix, rb.g_ids.ensure(n_rows_dev * 4));
             CU_TRY(ix, rb.g_own.ensure(n_rows_dev * 4));
             CU_TRY(ix, rb.g_off.ensure(h_goff.size() * 4));
@@ -769,44 +792,6 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             gpu_ms += now_ms() - tp0;
         }
 
-        // ---- host (parallel, overlapping the mask kernel): for every expansion of every pending search that read a list
-        //      with a group, which members of the group are nearer than W's furthest distance at that expansion ----
-        const double tN0 = now_ms();
-        int n_ok = 0;
-        while (n_ok < B && h_status[(size_t)n_ok] == 0) n_ok++;
-        pool.parallel_for(n_ok, [&](int64_t i) {
-            Pending &p = pend[(size_t)i];
-            const int n_log = std::min(h_rscnt[(size_t)i], rs_cap);
-            p.near_idx.assign((size_t)n_log, -1);
-            p.near_bits.clear();
-            if (i == 0 || h_rscnt[(size_t)i] > rs_cap) return;     // the head needs no validation; an overflowed log cannot be validated
-            const int32_t *rs = &h_rs[(size_t)i * rs_cap * 3];
-            const int64_t e = e_base + i;
-            uint64_t nd = 0;
-            for (int t = 0; t < n_log; t++) {
-                const uint32_t ford = (uint32_t)rs[3 * t + 1];
-                if (ford == 0xFFFFFFFFu) continue;
-                const int gi = find_group(rs[3 * t], rs[3 * t + 2]);
-                if (gi < 0) continue;
-                const Group &G = groups[(size_t)gi];
-                // only members before this element can have changed the list by the time it is validated
-                if (G.ids[(size_t)G.n_list] >= (int32_t)e) continue;
-                if ((int)G.ids.size() > PAIR_MAX_ROWS) { p.near_idx[(size_t)t] = -2; continue; }     // decided lazily
-                float f_t;
-                { const uint32_t bits = (ford & 0x80000000u) ? (ford & 0x7FFFFFFFu) : ~ford; memcpy(&f_t, &bits, 4); }
-                p.near_idx[(size_t)t] = (int32_t)p.near_bits.size();
-                uint32_t w[MW] = {0};
-                for (size_t u = 0; u < G.ids.size(); u++) {
-                    if (G.ids[u] >= (int32_t)e) break;              // members from this element on are never in the list it is checked against
-                    if (g.dist_less(e, G.ids[u], f_t)) w[u >> 5] |= 1u << (u & 31);
-                    nd++;
-                }
-                p.near_bits.insert(p.near_bits.end(), w, w + MW);
-            }
-            n_val_dist_atomic.fetch_add(nd, std::memory_order_relaxed);
-        });
-        t_near += now_ms() - tN0;
-
         if (n_dev_groups > 0) {
             const double tp1 = now_ms();
             CU_TRY(ix, cudaStreamSynchronize(ix->stream));
@@ -814,15 +799,15 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             CU_TRY(ix, cudaEventElapsedTime(&kms, ix->ev0, ix->ev1));
             kernel_ms += kms;
             gpu_ms += now_ms() - tp1;
-            for (int gi = 0; gi < n_groups; gi++)
-                if (groups[(size_t)gi].row_off >= 0) n_pair_gpu += (uint64_t)groups[(size_t)gi].ids.size() * groups[(size_t)gi].ids.size();
+            for (const Group *G : all_groups)
+                if (G->row_off >= 0) n_pair_gpu += (uint64_t)G->ids.size() * G->ids.size();
         }
         const uint32_t *mask_all = (const uint32_t *)h_mat.p;
 
         // ---- host (parallel by group): update_neighbor_connections for every group, all members in order ----
         const double tB0 = now_ms();
         pool.parallel_for(n_groups, [&](int64_t gi) {
-            Group &G = groups[(size_t)gi];
+            Group &G = *all_groups[(size_t)gi];
             simulate_group(g, G, G.row_off >= 0 ? mask_all + (size_t)G.row_off * MW : nullptr);
         });
         t_sim += now_ms() - tB0;
@@ -848,16 +833,17 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             bool valid = true;
             if (i > 0) {
                 if (h_rscnt[(size_t)i] > rs_cap) { valid = false; why_overflow++; }
-                const int32_t *rs = &h_rs[(size_t)i * rs_cap * 3];
+                const int32_t *rs = &h_rs[(size_t)i * rs_cap * rs_ent];
                 for (int t = 0; valid && t < h_rscnt[(size_t)i]; t++) {
-                    const int32_t v = rs[3 * t], lc = rs[3 * t + 2];
+                    const int32_t *ent = rs + (size_t)rs_ent * t;
+                    const int32_t v = ent[0], lc = ent[2];
                     if (g.stamp[(size_t)v] != g.round) continue;
-                    const int gi = find_group(v, lc);
-                    if (gi < 0) continue;
-                    const Group &G = groups[(size_t)gi];
+                    const Group *Gp = find_group(v, lc);
+                    if (!Gp) continue;
+                    const Group &G = *Gp;
                     if (G.step == 0) continue;                  // nobody has linked to it yet
                     const int n_old = G.n_list;
-                    const uint32_t ford = (uint32_t)rs[3 * t + 1];
+                    const uint32_t ford = (uint32_t)ent[1];
                     const int32_t *l_new;
                     const float *ds_new;
                     const int16_t *p_new;
@@ -868,12 +854,13 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                         if (!valid) why_notfull++;
                         continue;
                     }
-                    const int32_t ni = p.near_idx[(size_t)t];
-                    const uint32_t *bits = ni >= 0 ? &p.near_bits[(size_t)ni] : nullptr;
+                    // d(e, member) < f_t, exactly as the kernel compares: for the entries of the list the search read the
+                    // kernel logged the answer (it evaluated every entry of the row); newcomers are evaluated here
+                    const uint32_t *bits = reinterpret_cast<const uint32_t *>(ent + 3);
                     float f_t;
                     { const uint32_t fb = (ford & 0x80000000u) ? (ford & 0x7FFFFFFFu) : ~ford; memcpy(&f_t, &fb, 4); }
-                    auto near = [&](int pos) -> bool {          // d(e, member pos) < f_t, exactly as the kernel compares
-                        if (bits) return (bits[pos >> 5] >> (pos & 31)) & 1u;
+                    auto near = [&](int pos) -> bool {
+                        if (pos < n_old) return (bits[pos >> 5] >> (pos & 31)) & 1u;
                         n_val_dist++;
                         return g.dist_less(e, G.ids[(size_t)pos], f_t);
                     };
@@ -928,7 +915,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             }
             for (int lc = std::min(p.level, top); lc >= 0; lc--) {   // :455 for lc in (0..=level).rev(); lists above `top` are empty
                 for (const Cand &nb : p.sel[(size_t)lc]) {
-                    Group &G = groups[(size_t)find_group(nb.idx, lc)];
+                    Group &G = *find_group(nb.idx, lc);
                     // commits are a prefix of the batch and a group's members are in batch order: this is the next one
                     G.step++;
                     G.modified = true;
@@ -950,7 +937,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const double tS0 = now_ms();
         t_commit += tS0 - tC0;
         for (int gi = 0; gi < n_groups; gi++) {
-            const Group &G = groups[(size_t)gi];
+            const Group &G = *all_groups[(size_t)gi];
             if (!G.modified) continue;
             const int32_t *l;
             const float *d;

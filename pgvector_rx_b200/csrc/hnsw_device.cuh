@@ -254,6 +254,7 @@ struct WarpCtx {
     uint32_t n_dist, n_exp0, n_expu, n_vis, status;
     int32_t *rs_log;       // build: 3 ints per expansion -- node id, ordered bits of f_dist (or -1), layer (or NULL)
     int rs_cap, rs_n;      // capacity / count (rs_n may exceed rs_cap: the host then treats the set as unknown)
+    int rs_ent;            // ints per log entry: 3 + one word per 32 list slots
     int lane;
 #ifdef PGVRX_PHASE_TIMING
     uint32_t t[8];         // cycles: 0 pop+adjacency, 1 visited, 2 tma issue+wait, 3 distance, 4 accept/insert
@@ -498,13 +499,15 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
         if (c.rs_log) {
             // build: (expanded node, W's furthest distance at the start of the expansion or ~0 when W is not full, layer)
             if (lane == 0 && c.rs_n < c.rs_cap) {
-                int32_t *e = c.rs_log + 3 * (size_t)c.rs_n;
+                int32_t *e = c.rs_log + (size_t)c.rs_ent * (size_t)c.rs_n;
                 e[0] = (int32_t)cid;
                 e[1] = c.len >= c.ef ? (int32_t)c.f_ord : -1;
                 e[2] = layer;
             }
             c.rs_n++;
         }
+        const bool log_full = c.len >= c.ef;        // W full at the start of this expansion
+        const uint32_t log_f = c.f_ord;
         const int32_t *row;
         if (layer == 0) {
             row = g.adj0 + (size_t)cid * (size_t)lm;
@@ -541,6 +544,12 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
                     d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
                 __syncwarp();   // all lanes done with the staging rows before they are overwritten
                 PH_TICK(c, 3);
+            }
+            // build log: which entries of this list are nearer than W's furthest distance was when the expansion
+            // started (every valid lane has its distance, visited or not) -- the host replays against it
+            if (c.rs_log && c.rs_n <= c.rs_cap) {
+                const uint32_t nm = __ballot_sync(FULL, valid && log_full && f32_ord(d) < log_f);
+                if (lane == 0) c.rs_log[(size_t)c.rs_ent * (size_t)(c.rs_n - 1) + 3 + (base >> 5)] = (int32_t)nm;
             }
             // (3) resolve the visited probes (visited BEFORE the level test, graph/mod.rs:206-216)
             const uint32_t id = (uint32_t)nb;

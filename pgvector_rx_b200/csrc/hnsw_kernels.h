@@ -51,6 +51,7 @@ struct BuildParams {
     int32_t *w_counts;         // n_pending x max_layers, -1 for layers that were not searched
     int32_t *rs_log;           // n_pending x rs_cap x 3: expanded node id, ordered f_dist bits at the expansion (-1: W not full), layer
     int rs_cap;
+    int rs_ent;                // ints per log entry: 3 + ceil(2m / 32) near-mask words
     int32_t *rs_counts;        // n_pending (may exceed rs_cap => set unknown)
     uint32_t *out_status;      // n_pending
     uint32_t *out_ctr;         // n_pending x 4 or NULL

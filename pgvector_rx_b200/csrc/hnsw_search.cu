@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     c.policy = l2_policy_evict_first();
     c.rs_log = nullptr;
     c.rs_cap = c.rs_n = 0;
+    c.rs_ent = 3;
     const int slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
     c.vis = p.vis_base + (size_t)slot * p.vis_entries;
 
