@@ -104,14 +104,16 @@ static bool host_distance_less(int elem, int metric, int dim, const uint8_t *pa,
 // ------------------------------------------------------------------------------------------------
 // tiny fork-join pool
 // ------------------------------------------------------------------------------------------------
+// Workers spin on a generation counter while a build is running: a round issues several short parallel sections
+// (tens of microseconds each), and waking sleeping threads through a condition variable would cost more than the work.
 class Pool {
   public:
     explicit Pool(int n) : n_(std::max(1, n)) {
         for (int t = 1; t < n_; t++) th_.emplace_back([this] { worker(); });
     }
     ~Pool() {
-        { std::lock_guard<std::mutex> l(mu_); stop_ = true; gen_++; }
-        cv_.notify_all();
+        stop_.store(true, std::memory_order_release);
+        gen_.fetch_add(1, std::memory_order_release);
         for (auto &t : th_) t.join();
     }
     int size() const { return n_; }
@@ -119,20 +121,26 @@ class Pool {
     void parallel_for(int64_t count, const std::function<void(int64_t)> &fn) {
         if (count <= 0) return;
         if (n_ == 1 || count == 1) { for (int64_t i = 0; i < count; i++) fn(i); return; }
-        {
-            std::lock_guard<std::mutex> l(mu_);
-            fn_ = &fn; count_ = count; next_.store(0); pending_ = n_ - 1; gen_++;
-        }
-        cv_.notify_all();
+        fn_ = &fn;
+        count_ = count;
+        next_.store(0, std::memory_order_relaxed);
+        pending_.store(n_ - 1, std::memory_order_relaxed);
+        gen_.fetch_add(1, std::memory_order_release);
         run();
-        std::unique_lock<std::mutex> l(mu_);
-        done_cv_.wait(l, [this] { return pending_ == 0; });
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
     }
 
   private:
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
     void run() {
         for (;;) {
-            int64_t i = next_.fetch_add(1);
+            int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
             if (i >= count_) break;
             (*fn_)(i);
         }
@@ -140,29 +148,26 @@ class Pool {
     void worker() {
         uint64_t seen = 0;
         for (;;) {
-            {
-                std::unique_lock<std::mutex> l(mu_);
-                cv_.wait(l, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (stop_) return;
+            uint64_t gnow;
+            int spins = 0;
+            while ((gnow = gen_.load(std::memory_order_acquire)) == seen) {
+                cpu_relax();
+                if (++spins > 200000) { std::this_thread::sleep_for(std::chrono::microseconds(50)); spins = 0; }   // idle build (GPU phase): back off
             }
+            seen = gnow;
+            if (stop_.load(std::memory_order_acquire)) return;
             run();
-            {
-                std::lock_guard<std::mutex> l(mu_);
-                if (--pending_ == 0) done_cv_.notify_one();
-            }
+            pending_.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
     int n_;
     std::vector<std::thread> th_;
-    std::mutex mu_;
-    std::condition_variable cv_, done_cv_;
     const std::function<void(int64_t)> *fn_ = nullptr;
     int64_t count_ = 0;
     std::atomic<int64_t> next_{0};
-    int pending_ = 0;
-    uint64_t gen_ = 0;
-    bool stop_ = false;
+    std::atomic<int> pending_{0};
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<bool> stop_{false};
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -358,10 +363,9 @@ using namespace pgvrx_host;
 namespace {
 
 struct RoundBuffers {
-    DevBuf elem_ids, w_ids, w_dists, w_counts, rs_log, rs_counts, status, ctr, vis, work, sc_off, sc_rows, g_ids, g_off, g_own, g_mat;
+    DevBuf elem_ids, out_pack, vis, work, sc_off, sc_rows, g_ids, g_off, g_own, g_mat;
     void release() {
-        DevBuf *b[] = {&elem_ids, &w_ids, &w_dists, &w_counts, &rs_log, &rs_counts, &status, &ctr, &vis, &work, &sc_off, &sc_rows,
-                       &g_ids, &g_off, &g_own, &g_mat};
+        DevBuf *b[] = {&elem_ids, &out_pack, &vis, &work, &sc_off, &sc_rows, &g_ids, &g_off, &g_own, &g_mat};
         for (DevBuf *x : b) x->release();
     }
 };
@@ -493,7 +497,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             CU_TRY(ix, cudaMemcpyAsync(rb.sc_rows.p, dat.data(), dat.size() * 4, cudaMemcpyHostToDevice, ix->stream));
             CU_TRY(ix, launch_scatter_rows((int32_t *)(pass == 0 ? ix->adj0.p : ix->adj_up.p), (const int64_t *)rb.sc_off.p,
                                            (const int32_t *)rb.sc_rows.p, row_len, (int)off.size(), ix->stream));
-            CU_TRY(ix, cudaStreamSynchronize(ix->stream));   // host vectors are reused next round
+            // (pageable sources are staged before cudaMemcpyAsync returns, so the vectors can be reused at once)
             off.clear();
             dat.clear();
         }
@@ -565,9 +569,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     const uint32_t pair_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
     const int pair_rows = (int)std::min<size_t>(PAIR_MAX_ROWS, (100 * 1024) / pair_stride);
     const int pair_occ = 2;
-    std::vector<int32_t> h_elem, h_wids, h_wcnt, h_rs, h_rscnt;
-    std::vector<float> h_wd;
-    std::vector<uint32_t> h_status, h_ctr;
+    std::vector<int32_t> h_elem;
+    PinnedBuf h_pack;
 
     while (f < n_rows) {
         const int B = (int)std::min<int64_t>(big_next ? 1 : window, n_rows - f);
@@ -600,13 +603,16 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const int wpb = SEARCH_THREADS / 32;
         CU_TRY(ix, rb.vis.ensure((size_t)cfg.grid * wpb * cfg.vis_entries * 4));
         CU_TRY(ix, rb.elem_ids.ensure((size_t)B * 4));
-        CU_TRY(ix, rb.w_ids.ensure((size_t)B * max_layers * efc * 4));
-        CU_TRY(ix, rb.w_dists.ensure((size_t)B * max_layers * efc * 4));
-        CU_TRY(ix, rb.w_counts.ensure((size_t)B * max_layers * 4));
-        CU_TRY(ix, rb.rs_log.ensure((size_t)B * rs_cap * rs_ent * 4));
-        CU_TRY(ix, rb.rs_counts.ensure((size_t)B * 4));
-        CU_TRY(ix, rb.status.ensure((size_t)B * 4));
-        CU_TRY(ix, rb.ctr.ensure((size_t)B * 16));
+        // every per-round result lives in one device block mirrored by one pinned host block: a single D2H copy per round
+        size_t po = 0;
+        auto carve = [&](size_t bytes) { const size_t o = po; po += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_wids = carve((size_t)B * max_layers * efc * 4), o_wd = carve((size_t)B * max_layers * efc * 4);
+        const size_t o_wcnt = carve((size_t)B * max_layers * 4), o_rs = carve((size_t)B * rs_cap * rs_ent * 4);
+        const size_t o_rscnt = carve((size_t)B * 4), o_status = carve((size_t)B * 4), o_ctr = carve((size_t)B * 16);
+        CU_TRY(ix, rb.out_pack.ensure(po));
+        CU_TRY(ix, h_pack.ensure(po));
+        uint8_t *dpk = (uint8_t *)rb.out_pack.p;
+        const uint8_t *hpk = (const uint8_t *)h_pack.p;
         CU_TRY(ix, rb.work.ensure(64));
         h_elem.resize((size_t)B);
         for (int i = 0; i < B; i++) h_elem[(size_t)i] = (int32_t)(e_base + i);
@@ -622,15 +628,15 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         bp.efc = efc;
         bp.tail_cap = cfg.L.tail_cap;
         bp.max_layers = max_layers;
-        bp.w_ids = (int32_t *)rb.w_ids.p;
-        bp.w_dists = (float *)rb.w_dists.p;
-        bp.w_counts = (int32_t *)rb.w_counts.p;
-        bp.rs_log = (int32_t *)rb.rs_log.p;
+        bp.w_ids = (int32_t *)(dpk + o_wids);
+        bp.w_dists = (float *)(dpk + o_wd);
+        bp.w_counts = (int32_t *)(dpk + o_wcnt);
+        bp.rs_log = (int32_t *)(dpk + o_rs);
         bp.rs_cap = rs_cap;
         bp.rs_ent = rs_ent;
-        bp.rs_counts = (int32_t *)rb.rs_counts.p;
-        bp.out_status = (uint32_t *)rb.status.p;
-        bp.out_ctr = (uint32_t *)rb.ctr.p;
+        bp.rs_counts = (int32_t *)(dpk + o_rscnt);
+        bp.out_status = (uint32_t *)(dpk + o_status);
+        bp.out_ctr = (uint32_t *)(dpk + o_ctr);
         bp.vis_base = (uint32_t *)rb.vis.p;
         bp.vis_entries = cfg.vis_entries;
         bp.work_counter = (int *)rb.work.p;
@@ -640,20 +646,14 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
         CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, ix->stream));
         CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));
-        h_wids.resize((size_t)B * max_layers * efc);
-        h_wd.resize((size_t)B * max_layers * efc);
-        h_wcnt.resize((size_t)B * max_layers);
-        h_rs.resize((size_t)B * rs_cap * rs_ent);
-        h_rscnt.resize((size_t)B);
-        h_status.resize((size_t)B);
-        h_ctr.resize((size_t)B * 4);
-        CU_TRY(ix, cudaMemcpyAsync(h_wids.data(), rb.w_ids.p, h_wids.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
-        CU_TRY(ix, cudaMemcpyAsync(h_wd.data(), rb.w_dists.p, h_wd.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
-        CU_TRY(ix, cudaMemcpyAsync(h_wcnt.data(), rb.w_counts.p, h_wcnt.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
-        CU_TRY(ix, cudaMemcpyAsync(h_rs.data(), rb.rs_log.p, h_rs.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
-        CU_TRY(ix, cudaMemcpyAsync(h_rscnt.data(), rb.rs_counts.p, h_rscnt.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
-        CU_TRY(ix, cudaMemcpyAsync(h_status.data(), rb.status.p, h_status.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
-        CU_TRY(ix, cudaMemcpyAsync(h_ctr.data(), rb.ctr.p, h_ctr.size() * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(h_pack.p, rb.out_pack.p, po, cudaMemcpyDeviceToHost, ix->stream));
+        const int32_t *h_wids = (const int32_t *)(hpk + o_wids);
+        const float *h_wd = (const float *)(hpk + o_wd);
+        const int32_t *h_wcnt = (const int32_t *)(hpk + o_wcnt);
+        const int32_t *h_rs = (const int32_t *)(hpk + o_rs);
+        const int32_t *h_rscnt = (const int32_t *)(hpk + o_rscnt);
+        const uint32_t *h_status = (const uint32_t *)(hpk + o_status);
+        const uint32_t *h_ctr = (const uint32_t *)(hpk + o_ctr);
         CU_TRY(ix, cudaStreamSynchronize(ix->stream));
         gpu_ms += now_ms() - tg0;
         {
