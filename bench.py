@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--cache", default=os.path.join(ROOT, "data_cache"))
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--recall-sample", type=int, default=200)
-    ap.add_argument("--build-rows", type=int, default=100_000,
+    ap.add_argument("--build-rows", type=int, default=1_000_000,
                     help="rows of the same dataset built on the GPU for the build vectors/s figure (0 = skip)")
     return ap.parse_args()
 
@@ -138,8 +138,11 @@ def gpu_build_sample(a, local):
     dt = time.perf_counter() - t0
     out = dict(gpu_vectors_per_s=n / dt, rows=n, seconds=dt, rounds=st["n_rounds"], searches=st["n_searched"],
                conflicts=st["n_conflicts"], kernel_ms=st["kernel_ms"], host_threads=st["host_threads"],
-               note="first %d rows of the 1M dataset (same seeds); exact sequential semantics, see DESIGN.md" % n)
-    d = os.path.join(a.cache, "g_%d_%d_%d_%d" % (n, a.dim, a.m, a.efc))
+               commits_per_round=n / max(st["n_rounds"], 1), pairwise_on_gpu=st["n_pair_gpu"],
+               note="%s rows of the C2 dataset (same seeds and levels as the oracle's build); exact sequential semantics, "
+                    "see DESIGN.md" % ("all %d" % n if n == a.n else "first %d" % n))
+    tag = "c2_1m" if (n, a.dim, a.m, a.efc) == (1_000_000, 128, 16, 64) else "g_%d_%d_%d_%d" % (n, a.dim, a.m, a.efc)
+    d = os.path.join(a.cache, tag)
     if os.path.exists(os.path.join(d, "meta.json")):
         meta = json.load(open(os.path.join(d, "meta.json")))
         g = ix.export_graph()

@@ -139,10 +139,13 @@ class Pool {
 #endif
     }
     void run() {
+        // small items (thousands of groups) are handed out in chunks so that the shared counter is not the bottleneck
+        const int64_t chunk = std::max<int64_t>(1, count_ / ((int64_t)n_ * 8));
         for (;;) {
-            int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
-            if (i >= count_) break;
-            (*fn_)(i);
+            const int64_t i0 = next_.fetch_add(chunk, std::memory_order_relaxed);
+            if (i0 >= count_) break;
+            const int64_t i1 = std::min(count_, i0 + chunk);
+            for (int64_t i = i0; i < i1; i++) (*fn_)(i);
         }
     }
     void worker() {
@@ -561,7 +564,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     PinnedBuf h_mat;
     uint64_t n_pair_gpu = 0, n_val_dist = 0;
     std::atomic<uint64_t> n_val_dist_atomic{0};
-    double t_near = 0, t_sim = 0;
+    double t_near = 0, t_sim = 0, t_g1 = 0, t_g2 = 0;
     for (int t = 0; t < 256; t++) g_identity_pos[t] = (int16_t)t;
     uint64_t why_overflow = 0, why_notfull = 0, why_pending = 0, why_order = 0;   // conflict reasons (PGVRX_BUILD_DEBUG)
     double t_phase_a = 0, t_groups = 0, t_commit = 0, t_scatter = 0;
@@ -737,6 +740,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                     }
             }
         });
+        t_g1 += now_ms() - tG0;
+        const double tG1 = now_ms();
         all_groups.clear();
         h_goff.clear();
         size_t n_rows_dev = 0;
@@ -755,6 +760,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                 }
             }
         const int n_groups = (int)all_groups.size();
+        t_g2 += now_ms() - tG1;
         h_gids.resize(n_rows_dev);
         h_gown.resize(n_rows_dev);
         pool.parallel_for(n_groups, [&](int64_t gi) {
@@ -967,9 +973,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     }
 
     if (getenv("PGVRX_BUILD_DEBUG"))
-        fprintf(stderr, "[pgvrx build] conflicts: log overflow %llu, W-not-full %llu, pending element acceptable %llu, order/removal %llu | ms: gpu %.0f (kernels %.0f) phaseA %.0f groups %.0f near %.0f simulate %.0f commit %.0f scatter %.0f\n",
+        fprintf(stderr, "[pgvrx build] conflicts: log overflow %llu, W-not-full %llu, pending element acceptable %llu, order/removal %llu | ms: gpu %.0f (kernels %.0f) phaseA %.0f groups %.0f (build %.0f enum %.0f) simulate %.0f commit %.0f scatter %.0f\n",
                 (unsigned long long)why_overflow, (unsigned long long)why_notfull, (unsigned long long)why_pending,
-                (unsigned long long)why_order, gpu_ms, kernel_ms, t_phase_a, t_groups, t_near, t_sim, t_commit, t_scatter);
+                (unsigned long long)why_order, gpu_ms, kernel_ms, t_phase_a, t_groups, t_g1, t_g2, t_sim, t_commit, t_scatter);
     ix->n = g.n;
     ix->n_upper = g.n_upper;
     ix->entry = g.entry;
