@@ -570,8 +570,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     double t_phase_a = 0, t_groups = 0, t_commit = 0, t_scatter = 0;
     // rows a pairwise group may hold: what fits in one CTA's shared memory, at most PAIR_MAX_ROWS
     const uint32_t pair_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
-    const int pair_rows = (int)std::min<size_t>(PAIR_MAX_ROWS, (100 * 1024) / pair_stride);
-    const int pair_occ = 2;
+    const int pair_rows = (int)std::min<size_t>(PAIR_MAX_ROWS, (200 * 1024) / pair_stride);
+    const int pair_occ = std::max(1, (int)((220 * 1024) / (128 + (size_t)pair_rows * pair_stride)));
+    const bool w_masks = efc <= pair_rows;               // select_neighbors of the new elements answered by GPU masks
     std::vector<int32_t> h_elem;
     PinnedBuf h_pack;
 
@@ -612,6 +613,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const size_t o_wids = carve((size_t)B * max_layers * efc * 4), o_wd = carve((size_t)B * max_layers * efc * 4);
         const size_t o_wcnt = carve((size_t)B * max_layers * 4), o_rs = carve((size_t)B * rs_cap * rs_ent * 4);
         const size_t o_rscnt = carve((size_t)B * 4), o_status = carve((size_t)B * 4), o_ctr = carve((size_t)B * 16);
+        const size_t o_wmask = carve(w_masks ? (size_t)B * max_layers * efc * (PAIR_MAX_ROWS / 32) * 4 : 0);
         CU_TRY(ix, rb.out_pack.ensure(po));
         CU_TRY(ix, h_pack.ensure(po));
         uint8_t *dpk = (uint8_t *)rb.out_pack.p;
@@ -648,6 +650,22 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const double tg0 = now_ms();
         CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
         CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, ix->stream));
+        if (w_masks) {
+            // check_element_closer for the candidate lists the searches just produced (graph/mod.rs:419 -> :315-339)
+            CU_TRY(ix, cudaMemsetAsync((int *)rb.work.p + 4, 0, 4, ix->stream));
+            PairParams wp;
+            wp.ids = bp.w_ids;
+            wp.own_dist = bp.w_dists;
+            wp.group_off = nullptr;
+            wp.w_counts = bp.w_counts;
+            wp.w_pitch = efc;
+            wp.w_layers = max_layers;
+            wp.n_groups = B * max_layers;
+            wp.out = (uint32_t *)(dpk + o_wmask);
+            wp.work_counter = (int *)rb.work.p + 4;
+            wp.stage_stride = cfg.L.stage_stride;
+            CU_TRY(ix, launch_pairwise(ix->desc.elem_type, ix->desc.metric, gv, wp, pair_rows, std::min(B * max_layers, ix->sm_count * pair_occ), ix->stream));
+        }
         CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));
         CU_TRY(ix, cudaMemcpyAsync(h_pack.p, rb.out_pack.p, po, cudaMemcpyDeviceToHost, ix->stream));
         const int32_t *h_wids = (const int32_t *)(hpk + o_wids);
@@ -657,6 +675,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const int32_t *h_rscnt = (const int32_t *)(hpk + o_rscnt);
         const uint32_t *h_status = (const uint32_t *)(hpk + o_status);
         const uint32_t *h_ctr = (const uint32_t *)(hpk + o_ctr);
+        const uint32_t *h_wmask = (const uint32_t *)(hpk + o_wmask);
         CU_TRY(ix, cudaStreamSynchronize(ix->stream));
         gpu_ms += now_ms() - tg0;
         {
@@ -677,12 +696,19 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             const int top = std::min(p.level, g.entry_level);
             p.sel.resize((size_t)p.level + 1);
             std::vector<Cand> w;
+            std::vector<int16_t> wpos, spos;
             for (int lc = top; lc >= 0; lc--) {
                 const int cnt = h_wcnt[(size_t)i * max_layers + lc];
                 w.resize((size_t)std::max(cnt, 0));
                 const size_t o = ((size_t)i * max_layers + lc) * efc;
                 for (int t = 0; t < cnt; t++) w[(size_t)t] = Cand{h_wd[o + t], h_wids[o + t]};
-                select_neighbors(g, w.data(), cnt, g.lm(lc), p.sel[(size_t)lc]);    // graph/mod.rs:419
+                if (w_masks && cnt > g.lm(lc)) {                                     // graph/mod.rs:419 with the GPU's masks
+                    wpos.resize((size_t)cnt);
+                    for (int t = 0; t < cnt; t++) wpos[(size_t)t] = (int16_t)t;
+                    select_neighbors_mask(g, w.data(), wpos.data(), cnt, g.lm(lc), h_wmask + o * (PAIR_MAX_ROWS / 32), p.sel[(size_t)lc], spos);
+                } else {
+                    select_neighbors(g, w.data(), cnt, g.lm(lc), p.sel[(size_t)lc]);
+                }
             }
             // duplicate probe (build.rs:482-503): walk the selected layer-0 neighbours while distance == 0
             for (const Cand &nb : p.sel[0]) {
@@ -787,6 +813,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             pp.ids = (const int32_t *)rb.g_ids.p;
             pp.own_dist = (const float *)rb.g_own.p;
             pp.group_off = (const int32_t *)rb.g_off.p;
+            pp.w_counts = nullptr;
+            pp.w_pitch = pp.w_layers = 0;
             pp.n_groups = n_dev_groups;
             pp.out = (uint32_t *)rb.g_mat.p;
             pp.work_counter = (int *)rb.work.p + 8;

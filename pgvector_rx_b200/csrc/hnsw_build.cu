@@ -167,7 +167,19 @@ __global__ void __launch_bounds__(SEARCH_THREADS) pairwise_kernel(GraphView g, P
         __syncthreads();
         const int gi = s_group;
         if (gi >= p.n_groups) break;
-        const int off = p.group_off[gi], cnt = p.group_off[gi + 1] - off;
+        // explicit groups (back-link lists) or, in W mode, group gi = the candidate list W of (pending element, layer)
+        // as the search kernel left it: fixed pitch, length in w_counts, own distance = distance to the new element
+        int off, cnt;
+        if (p.group_off) {
+            off = p.group_off[gi];
+            cnt = p.group_off[gi + 1] - off;
+        } else {
+            off = gi * p.w_pitch;
+            cnt = p.w_counts[gi];
+            const int lm = (gi % p.w_layers) == 0 ? 2 * g.m : g.m;
+            if (cnt <= lm) cnt = 0;                    // select_neighbors returns such a list unchanged (graph/mod.rs:276)
+        }
+        if (cnt == 0) { __syncthreads(); continue; }
         if (t == 0) mbar_arrive_expect_tx(mbar, (uint32_t)cnt * g.row_stride);
         __syncthreads();
         if (t < cnt)

@@ -67,7 +67,9 @@ constexpr int PAIR_MAX_ROWS = 128;
 struct PairParams {
     const int32_t *ids;        // concatenated element ids of all groups
     const float *own_dist;     // per member: its distance to the group's node
-    const int32_t *group_off;  // n_groups + 1 offsets into ids
+    const int32_t *group_off;  // n_groups + 1 offsets into ids, or NULL in W mode:
+    const int32_t *w_counts;   //   W mode: group gi has w_counts[gi] members (<= 0: none) at ids + gi * w_pitch,
+    int w_pitch, w_layers;     //   gi = pending * w_layers + layer
     int n_groups;
     uint32_t *out;             // per member PAIR_MAX_ROWS / 32 words: bit b set <=> d(member, b) <= own_dist[member]
     int *work_counter;
