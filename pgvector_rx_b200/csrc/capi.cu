@@ -434,6 +434,16 @@ int pgvrx_search_batch_device(pgvrx_index *ix, const void *d_queries, int64_t nq
     return search_core(ix, d_queries, (uint32_t)ix->row_bytes, nq, ef_search, k, d_ids, d_dists, d_counts, stats, s, false);
 }
 
+// device-visible alias of a host buffer when it is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory):
+// the kernels then read queries and write results through it directly (each query row is read once, each result
+// row written once), so the call has no separate copy phases
+static void *mapped_alias(const void *host_ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
 int pgvrx_search_batch(pgvrx_index *ix, const void *queries, int64_t nq, int32_t ef_search, int32_t k, int32_t *out_ids,
                        float *out_dists, int32_t *out_counts, pgvrx_search_stats *stats) {
     if (!ix) return PGVRX_ERR_INVALID;
@@ -441,18 +451,31 @@ int pgvrx_search_batch(pgvrx_index *ix, const void *queries, int64_t nq, int32_t
     if (nq < 0 || k < 1) return fail(ix, PGVRX_ERR_INVALID, "bad k or nq");
     if (nq == 0) { if (stats) memset(stats, 0, sizeof *stats); return PGVRX_OK; }
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
-    CU_TRY(ix, ix->q.ensure((size_t)nq * ix->row_bytes));
-    CU_TRY(ix, ix->ids.ensure((size_t)nq * k * 4));
-    CU_TRY(ix, ix->dists.ensure((size_t)nq * k * 4));
-    CU_TRY(ix, ix->counts.ensure((size_t)nq * 4));
-    CU_TRY(ix, cudaMemcpyAsync(ix->q.p, queries, (size_t)nq * ix->row_bytes, cudaMemcpyHostToDevice, ix->stream));
-    int rc = search_core(ix, ix->q.p, (uint32_t)ix->row_bytes, nq, ef_search, k, (int32_t *)ix->ids.p, (float *)ix->dists.p,
-                         (int32_t *)ix->counts.p, stats, ix->stream, true);
+    // page-locked caller buffers are used in place; pageable ones are staged through device copies
+    const bool zc_ok = getenv("PGVRX_NO_ZEROCOPY") == nullptr && (ix->row_bytes % 16) == 0;
+    void *zq = zc_ok ? mapped_alias(queries) : nullptr;
+    void *zi = zc_ok ? mapped_alias(out_ids) : nullptr, *zd = zc_ok ? mapped_alias(out_dists) : nullptr,
+         *zcnt = zc_ok ? mapped_alias(out_counts) : nullptr;
+    const bool zc_out = zi && zd && zcnt;
+    if (!zq) {
+        CU_TRY(ix, ix->q.ensure((size_t)nq * ix->row_bytes));
+        CU_TRY(ix, cudaMemcpyAsync(ix->q.p, queries, (size_t)nq * ix->row_bytes, cudaMemcpyHostToDevice, ix->stream));
+    }
+    if (!zc_out) {
+        CU_TRY(ix, ix->ids.ensure((size_t)nq * k * 4));
+        CU_TRY(ix, ix->dists.ensure((size_t)nq * k * 4));
+        CU_TRY(ix, ix->counts.ensure((size_t)nq * 4));
+    }
+    int rc = search_core(ix, zq ? zq : ix->q.p, (uint32_t)ix->row_bytes, nq, ef_search, k, zc_out ? (int32_t *)zi : (int32_t *)ix->ids.p,
+                         zc_out ? (float *)zd : (float *)ix->dists.p, zc_out ? (int32_t *)zcnt : (int32_t *)ix->counts.p, stats,
+                         ix->stream, true);
     if (rc) return rc;
-    CU_TRY(ix, cudaMemcpyAsync(out_ids, ix->ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
-    CU_TRY(ix, cudaMemcpyAsync(out_dists, ix->dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
-    CU_TRY(ix, cudaMemcpyAsync(out_counts, ix->counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->stream));
-    CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+    if (!zc_out) {
+        CU_TRY(ix, cudaMemcpyAsync(out_ids, ix->ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(out_dists, ix->dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(out_counts, ix->counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+    }
     return PGVRX_OK;
 }
 
