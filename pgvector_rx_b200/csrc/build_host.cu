@@ -6,13 +6,21 @@
 // update_neighbor_connections and the entry-point rule in the reference's order, so every neighbour
 // list comes out identical to a sequential build.
 //
-// Exactness under batching.  A round searches B pending elements against the committed snapshot.
-// The search of element j is a deterministic function of the lists of the nodes it expanded (its
-// read set, reported by the kernel), of immutable vectors/levels, and of the entry point.  Elements
-// are committed in order; j's speculative result is used only if no earlier commit of the same round
-// touched a list in j's read set and the entry point did not move -- then a sequential run would have
-// replayed the very same search.  Otherwise the round stops before j and j is searched again next
-// round against the new snapshot (the head of a round is always valid, so progress is guaranteed).
+// Exactness under batching.  A round searches B pending elements against the committed snapshot and commits them in
+// insert order.  The kernel logs every expansion of a search: node, layer, W's furthest distance f_t at that moment
+// (or "W not full") and, per entry of the list it read, whether that entry is nearer than f_t.  Element j's
+// speculative result is committed only if, for every logged expansion whose list has changed since the snapshot, the
+// entries nearer than f_t form the same sequence in the old and in the current list (with W not full: the list is
+// unchanged): only those can be accepted then or later, everything else merely toggles the visited flag of an
+// element that is rejected wherever it is met, so a sequential run would have replayed the very same search.
+// Otherwise -- or when the entry point moved or a duplicate was merged -- the round stops before j and j is searched
+// again next round (the head of a round is always valid, so progress is guaranteed).
+//
+// select_neighbors never needs a distance, only "d(e, r) <= d(e, owner)" for kept r (graph/mod.rs:333): the GPU
+// answers that for all pairs of a group at once (pairwise_kernel, 128-bit masks), for the new elements' candidate
+// lists and for every list that pending elements link back to.  Host distances remain only for groups that do not
+// fit on a CTA (ef_construction > 128 or very wide rows) and for comparing a pending element with newcomers of a
+// changed list during validation.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
