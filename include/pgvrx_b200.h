@@ -218,7 +218,8 @@ typedef struct {
     uint32_t n_launches;
     uint32_t n_splits;        /* base-row splits merged per query                                 */
     uint32_t path;            /* 0 = sequential f32 chains on CUDA cores; 1 = 3xTF32 tcgen05 candidate
-                                 generation + exact re-rank (large fp32 L2 / IP batches)          */
+                                 generation + exact re-rank (large fp32 L2 / IP batches);
+                                 2 = the same on CTA pairs (cta_group::2)                         */
     float    kernel_ms;       /* device time of the call's kernels (CUDA events)                  */
 } pgvrx_flat_stats;
 

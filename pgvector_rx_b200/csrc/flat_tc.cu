@@ -24,6 +24,8 @@ constexpr int TC_TILE_BYTES = TC_M * TC_KB * 4;          // one 128 x 32 fp32 op
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;        // q_hi, q_lo, x_hi, x_lo
 constexpr uint32_t TC_TMEM_COLS = 256;                   // two accumulators of TC_N fp32 columns
 constexpr int TC_MAX_STAGES = 4;
+constexpr int TC2_M = 256, TC2_N = 256;                  // 2-CTA tile: 128 query rows per CTA, 128 of the 256 x rows staged per CTA
+constexpr int TC2_STAGES = 2;
 constexpr int TC_A_RES_BYTES = 4 * 2 * TC_TILE_BYTES;    // resident query tile: up to 4 K blocks of (hi | lo)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -110,6 +112,135 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const uint8_t *__restrict
         if (norm_max) atomicMax(norm_max, __float_as_uint(s));     // s >= 0: float order == unsigned order
         if (hint_init && row < n_rows) hint_init[row] = 0xFF800000u;   // f32_ord(+inf): no threshold known yet
     }
+}
+
+// ---- epilogue of one unit (query tile x base split), shared by the 1-CTA and the 2-CTA kernels ------------------
+// TN = accumulator width (base rows per tile).  Thread <-> query row for the arithmetic; the candidate set of a query
+// is an UNORDERED set of TC_KP = 32 keys in shared memory, one per lane, maintained by the whole warp: a qualifying
+// element replaces the set's maximum (two REDUX per 32-bit half), so an insertion is ~20 warp instructions with no
+// divergent loop.  Qualifying elements are rare once the sets have warmed up (KP * ln(rows / KP) per query).
+template <int TN, bool REMOTE_EMPTY>
+__device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0, int sp, int nt0, int nt1, uint32_t tmem_base,
+                                                 float *sxn, uint64_t *Lw, uint64_t *tfull, uint64_t *tempty,
+                                                 uint32_t tempty_leader_addr, int &buf, uint32_t &aphase, int quarter, int lane, int et) {
+    const int r = quarter * 32 + lane;                              // query row inside the tile
+    const int q = q_tile0 + r;
+    const bool qvalid = q < p.nq;
+    const float qn = qvalid ? p.qnorm[q] : 0.0f;
+    uint64_t tau = ~0ull;                                            // this lane's query: max of its set (all-ones = not full)
+    float tau_f = __int_as_float(0x7f800000);                        // the same threshold as a distance
+    // Thresholds travel between the units of a query: hint[q] is the smallest full-set maximum any unit has
+    // reached so far.  Rejecting against it is sound because certification uses the minimum over all units'
+    // final maxima, which is <= every value the hint ever took.
+    float xn_cur[TN / 128];
+#pragma unroll
+    for (int h = 0; h < TN / 128; h++) xn_cur[h] = p.xnorm[(int64_t)nt0 * TN + h * 128 + et];
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) Lw[i * TC_KP + lane] = ~0ull;
+    __syncwarp();
+    for (int nt = nt0; nt < nt1; nt++) {
+        const int64_t row0 = (int64_t)nt * TN;
+#pragma unroll
+        for (int h = 0; h < TN / 128; h++) {
+            sxn[buf * TN + h * 128 + et] = xn_cur[h];
+            if (nt + 1 < nt1) xn_cur[h] = p.xnorm[row0 + TN + h * 128 + et];   // in flight while this tile is processed
+        }
+        const uint32_t hint_ord = qvalid ? __ldcg(p.hint + q) : 0xFF800000u;
+        asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps only
+        mbar_wait(tfull + buf, aphase);
+        tc_fence_after();
+        const float hint_f = ord_f32(hint_ord);
+        float thr_f = fminf(tau_f, hint_f);
+        const int valid_cols = (int)min((int64_t)TN, p.n_rows - row0);   // rows beyond n_rows are padding
+        for (int c = 0; c < TN; c += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TN + c), v);
+            if (p.dbg_scores) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if (qvalid && c + j < valid_cols) {
+                        const float s = __uint_as_float(v[j]);
+                        p.dbg_scores[(size_t)q * p.n_rows + row0 + c + j] =
+                            p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TN + c + j]) : -s;
+                    }
+                }
+            }
+            // fast path: one fused multiply-add and one compare per element, no cross-lane traffic
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float s = __uint_as_float(v[j]);
+                const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TN + c + j]) : -s;
+                mask |= (dist <= thr_f ? 1u : 0u) << j;             // superset of key < tau (ties resolved below)
+            }
+            const int nvalid = valid_cols - c;
+            if (!qvalid || nvalid <= 0) mask = 0;
+            else if (nvalid < 32) mask &= (1u << nvalid) - 1u;
+            if (__ballot_sync(FULL, mask != 0)) {
+                // slow path (rare once the sets have warmed up): column by column over the union of the masks
+                uint32_t um = __reduce_or_sync(FULL, mask);
+                while (um) {
+                    const int j = __ffs(um) - 1;
+                    um &= um - 1;
+                    uint32_t sv;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(sv)
+                                 : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TN + c + j)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const float s = __uint_as_float(sv);
+                    const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TN + c + j]) : -s;
+                    const uint32_t khi = f32_ord(dist), klo = (uint32_t)(row0 + c + j);
+                    const uint64_t key = ((uint64_t)khi << 32) | klo;
+                    uint32_t am = __ballot_sync(FULL, ((mask >> j) & 1u) && key < tau);
+                    while (am) {
+                        const int src = __ffs(am) - 1;
+                        am &= am - 1;
+                        const uint32_t nhi = __shfl_sync(FULL, khi, src), nlo = __shfl_sync(FULL, klo, src);
+                        const uint64_t cur = Lw[src * TC_KP + lane];
+                        uint32_t chi = (uint32_t)(cur >> 32), clo = (uint32_t)cur;
+                        // the set's maximum is replaced by the new key
+                        uint32_t mhi = __reduce_max_sync(FULL, chi);
+                        uint32_t mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
+                        const int owner = __ffs(__ballot_sync(FULL, chi == mhi && clo == mlo)) - 1;
+                        if (lane == owner) {
+                            chi = nhi; clo = nlo;
+                            Lw[src * TC_KP + lane] = ((uint64_t)nhi << 32) | nlo;
+                        }
+                        mhi = __reduce_max_sync(FULL, chi);
+                        mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
+                        if (lane == src) {
+                            tau = ((uint64_t)mhi << 32) | mlo;
+                            if (tau != ~0ull) {
+                                tau_f = ord_f32(mhi);
+                                thr_f = fminf(thr_f, tau_f);
+                                atomicMin(p.hint + q, mhi);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        if (REMOTE_EMPTY) {
+            // 2-CTA: the MMA issuer lives in the leader CTA and waits for the epilogues of both CTAs
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader_addr + (uint32_t)buf * 8u) : "memory");
+        } else {
+            mbar_arrive(tempty + buf);
+        }
+        buf ^= 1;
+        if (buf == 0) aphase ^= 1u;
+    }
+    __syncwarp();
+    // candidates of query (quarter * 32 + i), one per lane; -1 where the split had fewer than KP rows
+    for (int i = 0; i < 32; i++) {
+        const int qi = q_tile0 + quarter * 32 + i;
+        if (qi >= p.nq) break;
+        const uint64_t cur = Lw[i * TC_KP + lane];
+        p.cand_ids[((size_t)qi * p.n_splits + sp) * TC_KP + lane] = cur == ~0ull ? -1 : (int32_t)((uint32_t)cur + (uint32_t)p.id_base);
+    }
+    // every row of this split that was not kept has an approximate distance >= this bound
+    if (qvalid) p.cand_bound[(size_t)sp * p.nq + q] = tau == ~0ull ? __int_as_float(0x7f800000) : ord_f32((uint32_t)(tau >> 32));
+    __syncwarp();
 }
 
 // ---- the GEMM + top-KP kernel -------------------------------------------------------------------------------
@@ -237,13 +368,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> approximate distance -> per-query top-KP =====
-        // Thread <-> query row for the arithmetic; the candidate set of a query is an UNORDERED set of TC_KP = 32
-        // keys in shared memory, one per lane, maintained by the whole warp: a qualifying element replaces the
-        // set's maximum (two REDUX per 32-bit half), so an insertion is ~20 warp instructions with no divergent
-        // loop.  Qualifying elements are rare once the sets have warmed up (KP * ln(rows / KP) per query).
+        // ===== epilogue: TMEM -> registers -> approximate distance -> per-query top-KP (tc_epilogue_unit) =====
         const int quarter = warp & 3;                               // TMEM lanes [32 * quarter, +32) belong to this warp
-        const int r = quarter * 32 + lane;                          // query row inside the tile
         const int et = (warp - 2) * 32 + lane;                      // 0..127 among the epilogue threads
         uint64_t *Lw = lists + (size_t)(quarter * 32) * TC_KP;      // this warp's 32 sets: set i = Lw[i * 32 + lane]
         int buf = 0;
@@ -252,113 +378,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
             const int nt0 = sp * p.ntiles_per_split;
             const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
-            const int q = mt * TC_M + r;
-            const bool qvalid = q < p.nq;
-            const float qn = qvalid ? p.qnorm[q] : 0.0f;
-            uint64_t tau = ~0ull;                                    // this lane's query: max of its set (all-ones = not full)
-            float tau_f = __int_as_float(0x7f800000);                // the same threshold as a distance
-            // Thresholds travel between the units of a query: hint[q] is the smallest full-set maximum any unit has
-            // reached so far.  Rejecting against it is sound because certification uses the minimum over all units'
-            // final maxima, which is <= every value the hint ever took.
-            float xn_cur = p.xnorm[(int64_t)nt0 * TC_N + et];
-#pragma unroll 4
-            for (int i = 0; i < 32; i++) Lw[i * TC_KP + lane] = ~0ull;
-            __syncwarp();
-            for (int nt = nt0; nt < nt1; nt++) {
-                const int64_t row0 = (int64_t)nt * TC_N;
-                sxn[buf * TC_N + et] = xn_cur;
-                if (nt + 1 < nt1) xn_cur = p.xnorm[row0 + TC_N + et];          // in flight while this tile is processed
-                const uint32_t hint_ord = qvalid ? __ldcg(p.hint + q) : 0xFF800000u;
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-                mbar_wait(tfull + buf, aphase);
-                tc_fence_after();
-                const float hint_f = ord_f32(hint_ord);
-                float thr_f = fminf(tau_f, hint_f);
-                const int valid_cols = (int)min((int64_t)TC_N, p.n_rows - row0);   // rows beyond n_rows are padding
-                for (int c = 0; c < TC_N; c += 32) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_N + c), v);
-                    if (p.dbg_scores) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if (qvalid && c + j < valid_cols) {
-                                const float s = __uint_as_float(v[j]);
-                                p.dbg_scores[(size_t)q * p.n_rows + row0 + c + j] =
-                                    p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
-                            }
-                        }
-                    }
-                    // fast path: one fused multiply-add and one compare per element, no cross-lane traffic
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float s = __uint_as_float(v[j]);
-                        const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
-                        mask |= (dist <= thr_f ? 1u : 0u) << j;                 // superset of key < tau (ties resolved below)
-                    }
-                    const int nvalid = valid_cols - c;
-                    if (!qvalid || nvalid <= 0) mask = 0;
-                    else if (nvalid < 32) mask &= (1u << nvalid) - 1u;
-                    if (__ballot_sync(FULL, mask != 0)) {
-                        // slow path (rare once the sets have warmed up): column by column over the union of the masks
-                        uint32_t um = __reduce_or_sync(FULL, mask);
-                        while (um) {
-                            const int j = __ffs(um) - 1;
-                            um &= um - 1;
-                            uint32_t sv;
-                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(sv)
-                                         : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_N + c + j)));
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                            const float s = __uint_as_float(sv);
-                            const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TC_N + c + j]) : -s;
-                            const uint32_t khi = f32_ord(dist), klo = (uint32_t)(row0 + c + j);
-                            const uint64_t key = ((uint64_t)khi << 32) | klo;
-                            uint32_t am = __ballot_sync(FULL, ((mask >> j) & 1u) && key < tau);
-                            while (am) {
-                                const int src = __ffs(am) - 1;
-                                am &= am - 1;
-                                const uint32_t nhi = __shfl_sync(FULL, khi, src), nlo = __shfl_sync(FULL, klo, src);
-                                const uint64_t cur = Lw[src * TC_KP + lane];
-                                uint32_t chi = (uint32_t)(cur >> 32), clo = (uint32_t)cur;
-                                // the set's maximum is replaced by the new key
-                                uint32_t mhi = __reduce_max_sync(FULL, chi);
-                                uint32_t mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
-                                const int owner = __ffs(__ballot_sync(FULL, chi == mhi && clo == mlo)) - 1;
-                                if (lane == owner) {
-                                    chi = nhi; clo = nlo;
-                                    Lw[src * TC_KP + lane] = ((uint64_t)nhi << 32) | nlo;
-                                }
-                                mhi = __reduce_max_sync(FULL, chi);
-                                mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
-                                if (lane == src) {
-                                    tau = ((uint64_t)mhi << 32) | mlo;
-                                    if (tau != ~0ull) {
-                                        tau_f = ord_f32(mhi);
-                                        thr_f = fminf(thr_f, tau_f);
-                                        atomicMin(p.hint + q, mhi);
-                                    }
-                                }
-                                __syncwarp();
-                            }
-                        }
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(tempty + buf);
-                buf ^= 1;
-                if (buf == 0) aphase ^= 1u;
-            }
-            __syncwarp();
-            // candidates of query (quarter * 32 + i), one per lane; -1 where the split had fewer than KP rows
-            for (int i = 0; i < 32; i++) {
-                const int qi = mt * TC_M + quarter * 32 + i;
-                if (qi >= p.nq) break;
-                const uint64_t cur = Lw[i * TC_KP + lane];
-                p.cand_ids[((size_t)qi * p.n_splits + sp) * TC_KP + lane] = cur == ~0ull ? -1 : (int32_t)((uint32_t)cur + (uint32_t)p.id_base);
-            }
-            // every row of this split that was not kept has an approximate distance >= this bound
-            if (qvalid) p.cand_bound[(size_t)sp * p.nq + q] = tau == ~0ull ? __int_as_float(0x7f800000) : ord_f32((uint32_t)(tau >> 32));
-            __syncwarp();
+            tc_epilogue_unit<TC_N, false>(p, mt * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, 0u, buf, aphase, quarter, lane, et);
         }
     }
     tc_fence_before();
@@ -366,6 +386,183 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- the same pipeline on CTA pairs: tcgen05.mma.cta_group::2 ------------------------------------------------------
+// Two CTAs of a cluster (one SM pair) work on 256 queries x 256 base rows per tile.  Each CTA keeps ITS 128 queries'
+// hi/lo K blocks resident and streams ITS half (128 rows) of every x tile; the leader's MMA instructions read both
+// halves, so every SM fills its shared memory with half the x bytes per unit of tensor work -- the x stream is what
+// bounds the 1-CTA kernel (L2 -> SM ~6 TB/s).  Each CTA's TMEM holds its 128 query rows x 256 columns, twice.
+// Barriers: TMA completions of both CTAs land on the LEADER's full / afull barriers; tcgen05.commit is multicast to
+// both CTAs' empty / aempty / tfull barriers; the epilogue threads of both CTAs arrive on the leader's tempty.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
+                const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo, TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *a_res = smem;                                                     // 4 K blocks x (q_hi | q_lo) of this CTA's 128 queries
+    uint8_t *ring = smem + TC_A_RES_BYTES;                                     // TC2_STAGES x (x_hi half | x_lo half)
+    float *sxn = reinterpret_cast<float *>(ring + TC2_STAGES * 2 * TC_TILE_BYTES);   // 2 x TC2_N row norms
+    uint64_t *lists = reinterpret_cast<uint64_t *>(sxn + 2 * TC2_N);
+    uint64_t *bars = lists + (size_t)TC_M * TC_KP;
+    uint64_t *full = bars, *empty = bars + TC2_STAGES, *tfull = empty + TC2_STAGES, *tempty = tfull + 2;
+    uint64_t *afull = tempty + 2, *aempty = afull + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();                               // swizzle atoms need 1024-byte alignment
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC2_STAGES; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 2 * TC_M); }
+        mbar_init(afull, 1);
+        mbar_init(aempty, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                        // both CTAs' barriers exist before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
+    const int n_units = p.n_mtiles * p.n_splits;                               // n_mtiles counts 256-query tiles here
+    const int n_kb = p.d_pad / TC_KB;
+    const uint32_t stage_bytes = 2u * TC_TILE_BYTES;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own queries, own half of every x tile; completions go to the leader =====
+        if (lane == 0) {
+            const uint64_t pol_x = l2_policy_evict_first(), pol_q = l2_policy_evict_last();
+            const uint32_t l_afull = map_to_cta(smem_u32(afull), 0);
+            int stage = 0;
+            uint32_t phase = 0, aph = 0;
+            for (int u = cid; u < n_units; u += n_clusters) {
+                const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
+                const int nt0 = sp * p.ntiles_per_split;
+                const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
+                mbar_wait(aempty, aph ^ 1u);
+                if (leader) mbar_arrive_expect_tx(afull, 2u * (uint32_t)n_kb * 2u * TC_TILE_BYTES);
+                for (int kb = 0; kb < n_kb; kb++) {
+                    tma_load_2d_2sm(a_res + (size_t)kb * 2 * TC_TILE_BYTES, &map_qhi, kb * TC_KB, mt * TC2_M + (int)rank * TC_M, l_afull, pol_q);
+                    tma_load_2d_2sm(a_res + (size_t)kb * 2 * TC_TILE_BYTES + TC_TILE_BYTES, &map_qlo, kb * TC_KB, mt * TC2_M + (int)rank * TC_M, l_afull, pol_q);
+                }
+                aph ^= 1u;
+                for (int nt = nt0; nt < nt1; nt++) {
+                    for (int kb = 0; kb < n_kb; kb++) {
+                        mbar_wait(empty + stage, phase ^ 1u);
+                        uint8_t *st = ring + (size_t)stage * stage_bytes;
+                        if (leader) mbar_arrive_expect_tx(full + stage, 2u * stage_bytes);
+                        const uint32_t l_full = map_to_cta(smem_u32(full + stage), 0);
+                        tma_load_2d_2sm(st, &map_xhi, kb * TC_KB, nt * TC2_N + (int)rank * TC_M, l_full, pol_x);
+                        tma_load_2d_2sm(st + TC_TILE_BYTES, &map_xlo, kb * TC_KB, nt * TC2_N + (int)rank * TC_M, l_full, pol_x);
+                        if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader && lane == 0) {
+            // cute::UMMA::InstrDescriptor: F32 accumulate, TF32 x TF32, K-major, N = 256, M = 256 (128 rows per CTA)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC2_N >> 3) << 17) | ((uint32_t)(TC2_M >> 4) << 24);
+            int stage = 0, buf = 0;
+            uint32_t phase = 0, aphase = 0, aph = 0;
+            for (int u = cid; u < n_units; u += n_clusters) {
+                const int sp = u / p.n_mtiles;
+                const int nt0 = sp * p.ntiles_per_split;
+                const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
+                mbar_wait(afull, aph);
+                tc_fence_after();
+                aph ^= 1u;
+                for (int nt = nt0; nt < nt1; nt++) {
+                    mbar_wait(tempty + buf, aphase ^ 1u);          // both CTAs' epilogues have drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC2_N;
+                    for (int kb = 0; kb < n_kb; kb++) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint8_t *st = ring + (size_t)stage * stage_bytes;
+                        const uint8_t *qa = a_res + (size_t)kb * 2 * TC_TILE_BYTES;
+                        const uint64_t qhi = tc_smem_desc(qa), qlo = tc_smem_desc(qa + TC_TILE_BYTES);
+                        const uint64_t xhi = tc_smem_desc(st), xlo = tc_smem_desc(st + TC_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32_2sm(d_tmem, qlo + 2 * k, xhi + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32_2sm(d_tmem, qhi + 2 * k, xlo + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32_2sm(d_tmem, qhi + 2 * k, xhi + 2 * k, idesc, 1u);
+                        tc_commit_2sm(empty + stage);               // both CTAs' ring slots are free when these MMAs retire
+                        if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit_2sm(tfull + buf);                     // both CTAs' accumulators are complete
+                    buf ^= 1;
+                    if (buf == 0) aphase ^= 1u;
+                }
+                tc_commit_2sm(aempty);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, each on its own 128 query rows) =====
+        const int quarter = warp & 3;
+        const int et = (warp - 2) * 32 + lane;
+        uint64_t *Lw = lists + (size_t)(quarter * 32) * TC_KP;
+        const uint32_t l_tempty = map_to_cta(smem_u32(tempty), 0);
+        int buf = 0;
+        uint32_t aphase = 0;
+        for (int u = cid; u < n_units; u += n_clusters) {
+            const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
+            const int nt0 = sp * p.ntiles_per_split;
+            const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
+            tc_epilogue_unit<TC2_N, true>(p, mt * TC2_M + (int)rank * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, l_tempty, buf,
+                                          aphase, quarter, lane, et);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                        // nobody leaves while the peer may still signal or read
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -431,6 +628,22 @@ cudaError_t launch_flat_tc(const void *map_qhi, const void *map_qlo, const void 
                                                        *reinterpret_cast<const CUtensorMap *>(map_qlo),
                                                        *reinterpret_cast<const CUtensorMap *>(map_xhi),
                                                        *reinterpret_cast<const CUtensorMap *>(map_xlo), p);
+    return cudaGetLastError();
+}
+
+size_t tc2_smem_bytes() {
+    return (size_t)TC_A_RES_BYTES + (size_t)TC2_STAGES * 2 * TC_TILE_BYTES + 2 * TC2_N * 4 + (size_t)TC_M * TC_KP * 8 + (2 * TC2_STAGES + 6) * 8 + 16;
+}
+
+cudaError_t launch_flat_tc2(const void *map_qhi, const void *map_qlo, const void *map_xhi, const void *map_xlo, const TcParams &p,
+                            int grid, cudaStream_t stream) {
+    const size_t smem = tc2_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(flat_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    flat_tc2_kernel<<<grid, TC_THREADS, smem, stream>>>(*reinterpret_cast<const CUtensorMap *>(map_qhi),
+                                                        *reinterpret_cast<const CUtensorMap *>(map_qlo),
+                                                        *reinterpret_cast<const CUtensorMap *>(map_xhi),
+                                                        *reinterpret_cast<const CUtensorMap *>(map_xlo), p);
     return cudaGetLastError();
 }
 

@@ -63,7 +63,7 @@ int prepare_table(pgvrx_index *ix, cudaStream_t stream) {
     if (ix->tc_ready) return PGVRX_OK;
     const int dim = ix->desc.dim;
     const int d_pad = (dim + TC_KB - 1) / TC_KB * TC_KB;
-    const int64_t n_pad = std::max<int64_t>(TC_N, (ix->n + TC_N - 1) / TC_N * TC_N);
+    const int64_t n_pad = std::max<int64_t>(2 * TC_N, (ix->n + 2 * TC_N - 1) / (2 * TC_N) * (2 * TC_N));   // whole 256-row tiles (2-CTA kernel)
     CU_TRY(ix, ix->tc_xhi.ensure((size_t)n_pad * d_pad * 4));
     CU_TRY(ix, ix->tc_xlo.ensure((size_t)n_pad * d_pad * 4));
     CU_TRY(ix, ix->tc_xnorm.ensure((size_t)n_pad * 4));
@@ -83,10 +83,12 @@ int prepare_table(pgvrx_index *ix, cudaStream_t stream) {
 
 struct TcPlan { int n_mtiles, n_ntiles, n_splits, tiles_per_split, grid; };
 
-TcPlan plan_tc(int sm_count, int64_t nq_pad, int64_t n_pad) {
+// tile_m x tile_n = 128 x 128 per CTA, or 256 x 256 per CTA pair (`workers` = CTAs or pairs)
+TcPlan plan_tc(int workers, int64_t nq_pad, int64_t n_pad, int tile_m, int tile_n) {
+    const int sm_count = workers;
     TcPlan pl;
-    pl.n_mtiles = (int)(nq_pad / TC_M);
-    pl.n_ntiles = (int)(n_pad / TC_N);
+    pl.n_mtiles = (int)(nq_pad / tile_m);
+    pl.n_ntiles = (int)(n_pad / tile_n);
     // units = query tiles x base splits are dealt round-robin to one CTA per SM: pick the split count with the
     // least total time (waves x tiles per unit); more splits only add candidates to re-rank
     long best_cost = -1;
@@ -123,7 +125,11 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     int rc = prepare_table(ix, stream);
     if (rc) return rc;
     const int d_pad = ix->tc_d_pad;
-    const int64_t nq_pad = (nq + TC_M - 1) / TC_M * TC_M;
+    // CTA pairs (tcgen05 cta_group::2) when the query tile can stay resident; PGVRX_TC_1CTA pins the single-CTA kernel
+    const bool two_cta = d_pad <= 4 * TC_KB && !getenv("PGVRX_TC_1CTA") && !getenv("PGVRX_TC_STREAM_Q") && (ix->sm_count % 2) == 0 &&
+                         getenv("PGVRX_TC2") != nullptr;
+    const int tile_m = two_cta ? 2 * TC_M : TC_M, tile_n = two_cta ? 2 * TC_N : TC_N;
+    const int64_t nq_pad = (nq + tile_m - 1) / tile_m * tile_m;
     CU_TRY(ix, ix->tc_qhi.ensure((size_t)nq_pad * d_pad * 4));
     CU_TRY(ix, ix->tc_qlo.ensure((size_t)nq_pad * d_pad * 4));
     CU_TRY(ix, ix->tc_qnorm.ensure((size_t)nq_pad * 4));
@@ -137,7 +143,7 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     rc = make_map(ix, map_qlo, ix->tc_qlo.p, nq_pad, d_pad);
     if (rc) return rc;
 
-    const TcPlan pl = plan_tc(ix->sm_count, nq_pad, ix->tc_n_pad);
+    const TcPlan pl = plan_tc(two_cta ? ix->sm_count / 2 : ix->sm_count, nq_pad, ix->tc_n_pad, tile_m, tile_n);
     const int nc = pl.n_splits * TC_KP;
     CU_TRY(ix, ix->tc_cand.ensure((size_t)nq * nc * 4));
     CU_TRY(ix, ix->tc_bound.ensure((size_t)pl.n_splits * nq * 4));
@@ -163,7 +169,8 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     p.cand_bound = (float *)ix->tc_bound.p;
     p.dbg_scores = d_dbg_scores;
     p.hint = (uint32_t *)ix->tc_hint.p;
-    CU_TRY(ix, launch_flat_tc(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, pl.grid, stream));
+    if (two_cta) CU_TRY(ix, launch_flat_tc2(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, 2 * pl.grid, stream));
+    else CU_TRY(ix, launch_flat_tc(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, pl.grid, stream));
     int launches = 2;
     uint64_t n_uncert = 0;
     if (d_ids) {
@@ -201,7 +208,7 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
         stats->n_uncertified = n_uncert;
         stats->n_launches = (uint32_t)launches;
         stats->n_splits = (uint32_t)pl.n_splits;
-        stats->path = 1;
+        stats->path = two_cta ? 2 : 1;
     }
     return PGVRX_OK;
 }

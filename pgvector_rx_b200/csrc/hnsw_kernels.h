@@ -218,6 +218,8 @@ cudaError_t launch_tc_split(const uint8_t *src, uint32_t src_stride, int64_t n_r
                             float *lo, float *norm, uint32_t *norm_max, uint32_t *hint_init, cudaStream_t stream);
 cudaError_t launch_flat_tc(const void *map_qhi, const void *map_qlo, const void *map_xhi, const void *map_xlo, const TcParams &p,
                            int grid, cudaStream_t stream);
+cudaError_t launch_flat_tc2(const void *map_qhi, const void *map_qlo, const void *map_xhi, const void *map_xlo, const TcParams &p,
+                            int grid, cudaStream_t stream);
 cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
                               const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, int32_t *uncert_list,
                               int *n_uncert, cudaStream_t stream);
