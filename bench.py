@@ -222,9 +222,9 @@ def flat_section(a, ix, g, batch, rank, world, local, dev, tstream):
     useful = 2.0 * nq * a.n * a.dim
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     tf32_peak = peaks.get("bf16_tflops", 2250.0 * 0.73) / 2.0
-    issued = useful * (3 if st.path == 1 else 1) / world
+    issued = useful * (3 if st.path >= 1 else 1) / world
     out = dict(value=nq / (ms / 1e3), unit="queries/s", ms_per_batch=ms, k=k, rows=a.n, queries=nq, n_gpus=world,
-               path="3xTF32 tcgen05 candidates + exact re-rank (certified)" if st.path == 1 else "sequential f32 chains (CUDA cores)",
+               path="3xTF32 tcgen05 candidates + exact re-rank (certified)" if st.path >= 1 else "sequential f32 chains (CUDA cores)",
                candidates_per_query=int(st.n_candidates // max(nq, 1)), uncertified=int(st.n_uncertified),
                parallelism="single table" if world == 1 else "base rows sharded x%d, NCCL all-gather of %d B/rank + K6 merge" % (world, nq * k * 8),
                roofline=dict(bound="tensor", achieved=issued / (ms / 1e3) / 1e12, peak=tf32_peak, unit="TFLOP/s",

@@ -57,7 +57,7 @@ def tc_case(opclass, metric, n, dim, nq, k, seed=91, rows=None, q=None, max_unce
     ix = P.HnswIndex(opclass, dim, capacity=len(rows))
     ix.load_rows(rows)
     ids, dists, st = ix.flat_topk(q, k=k, with_stats=True)
-    assert st["path"] == 1 and st["n_candidates"] > 0
+    assert st["path"] in (1, 2) and st["n_candidates"] > 0
     wi, wd = O.flat_topk(O.ELEM_F32, metric, dim, rows, q, k, nthreads=THREADS)
     bad = np.nonzero((ids != wi).any(axis=1))[0]
     assert len(bad) == 0, "%d queries differ, first %d: %s vs %s" % (len(bad), bad[0], ids[bad[0]], wi[bad[0]])
@@ -102,7 +102,7 @@ def test_tc_duplicates_and_shard_ids(tc_path):
     ds = torch.empty((len(q), 10), dtype=torch.float32, device=dev)
     st = P.FlatStats()
     ix.flat_topk_device(d_q.data_ptr(), len(q), 10, ids.data_ptr(), ds.data_ptr(), id_base=1_000_000, stats=st)
-    assert st.path == 1
+    assert st.path in (1, 2)
     wi, wd = O.flat_topk(O.ELEM_F32, O.L2SQ, 48, rows, q, 10, nthreads=THREADS)
     assert np.array_equal(ids.cpu().numpy(), wi + 1_000_000) and np.array_equal(ds.cpu().numpy(), wd)
     ix.close()
@@ -112,7 +112,7 @@ def test_auto_dispatch_picks_tensor_cores_for_large_batches_only():
     rows = make_rows("f32", 20000, 64, 3)
     ix = P.HnswIndex("vector_l2_ops", 64, capacity=len(rows))
     ix.load_rows(rows)
-    assert ix.flat_topk(make_rows("f32", 600, 64, 4), k=10, with_stats=True)[2]["path"] == 1
+    assert ix.flat_topk(make_rows("f32", 600, 64, 4), k=10, with_stats=True)[2]["path"] in (1, 2)
     assert ix.flat_topk(make_rows("f32", 40, 64, 4), k=10, with_stats=True)[2]["path"] == 0      # small batch
     assert ix.flat_topk(make_rows("f32", 600, 64, 4), k=100, with_stats=True)[2]["path"] == 0    # k beyond the candidate lists
     ix.close()

@@ -28,7 +28,7 @@ ds = torch.empty((nq, k), dtype=torch.float32, device=dev)
 for it in range(4):
     st = P.FlatStats()
     ix.flat_topk_device(d_q.data_ptr(), nq, k, ids.data_ptr(), ds.data_ptr(), stats=st)
-    flops = 2.0 * n * nq * dim * (3 if st.path == 1 else 1)
+    flops = 2.0 * n * nq * dim * (3 if st.path >= 1 else 1)
     print("flat %s n=%d nq=%d k=%d dim=%d path=%d: %.2f ms, %.1f kQPS, %.1f TFLOP/s issued, splits %d, candidates/query %d, uncertified %d"
           % (opclass, n, nq, k, dim, st.path, st.kernel_ms, nq / st.kernel_ms, flops / st.kernel_ms / 1e9, st.n_splits,
              st.n_candidates // max(nq, 1), st.n_uncertified), flush=True)
