@@ -126,8 +126,7 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     if (rc) return rc;
     const int d_pad = ix->tc_d_pad;
     // CTA pairs (tcgen05 cta_group::2) when the query tile can stay resident; PGVRX_TC_1CTA pins the single-CTA kernel
-    const bool two_cta = d_pad <= 4 * TC_KB && !getenv("PGVRX_TC_1CTA") && !getenv("PGVRX_TC_STREAM_Q") && (ix->sm_count % 2) == 0 &&
-                         getenv("PGVRX_TC2") != nullptr;
+    const bool two_cta = d_pad <= 4 * TC_KB && !getenv("PGVRX_TC_1CTA") && !getenv("PGVRX_TC_STREAM_Q") && (ix->sm_count % 2) == 0;
     const int tile_m = two_cta ? 2 * TC_M : TC_M, tile_n = two_cta ? 2 * TC_N : TC_N;
     const int64_t nq_pad = (nq + tile_m - 1) / tile_m * tile_m;
     CU_TRY(ix, ix->tc_qhi.ensure((size_t)nq_pad * d_pad * 4));
