@@ -118,3 +118,29 @@ def test_build_appends_across_calls_and_single_thread():
     with pytest.raises(P.PgvrxError):
         ix.build(rows[:1], lv[:1])                         # beyond the handle's capacity
     ix.close()
+
+
+def test_build_wide_rows_take_the_host_heuristic_path():
+    # 2000-d fp32 rows: a CTA cannot stage a whole candidate group, so check_element_closer falls back to host distances
+    ix, o, st = build_both("vector_l2_ops", "f32", 400, 2000, m=16, efc=64)
+    assert st["n_pair_gpu"] == 0
+    assert_same_graph(ix.export_graph(), o.export_graph(), o)
+    ix.close()
+
+
+def test_build_tie_heavy_bits_and_many_duplicates():
+    # 52-bit vectors: integer distances tie constantly and whole rows repeat far more than 10 times, so W's boundary,
+    # the heuristic's `<=` and the replay rule's strict `<` are all exercised on equal distances
+    rows = make_rows("bit", 3000, 52, 19)
+    rows[::7] = rows[3]
+    ix, o, st = build_both("bit_hamming_ops", "bit", 0, 52, m=8, efc=32, rows=rows)
+    assert st["n_duplicates"] > 10
+    assert_same_graph(ix.export_graph(), o.export_graph(), o)
+    ix.close()
+
+
+def test_build_20k_rows_many_commits_per_round():
+    ix, o, st = build_both("vector_l2_ops", "f32", 20000, 24, m=12, efc=48)
+    assert st["n_rounds"] * 3 < 20000                       # several commits per round on average
+    assert_same_graph(ix.export_graph(), o.export_graph(), o)
+    ix.close()
