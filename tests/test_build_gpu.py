@@ -121,9 +121,9 @@ def test_build_appends_across_calls_and_single_thread():
 
 
 def test_build_wide_rows_take_the_host_heuristic_path():
-    # 2000-d fp32 rows: a CTA cannot stage a whole candidate group, so check_element_closer falls back to host distances
+    # 2000-d fp32 rows: a CTA can stage only 25 rows, so layer-0 groups (33+ members) and the candidate lists fall back
+    # to host distances for check_element_closer while the small upper-layer groups still use the GPU masks
     ix, o, st = build_both("vector_l2_ops", "f32", 400, 2000, m=16, efc=64)
-    assert st["n_pair_gpu"] == 0
     assert_same_graph(ix.export_graph(), o.export_graph(), o)
     ix.close()
 
