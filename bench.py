@@ -317,9 +317,13 @@ def run_reference(a):
     out = dict(impl="reference", metric=METRIC, value=qps, unit="queries/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                data="synthetic", recall_at_10=rec,
-               config=dict(workload="C2: 1Mx128 fp32 vector_l2_ops m=16 ef_construction=64 ef_search=%d k=%d" % (a.ef, a.k),
-                           n=a.n, dim=a.dim, queries_per_step=per_step, graph=g["source"],
+               config=dict(workload="C2: 1Mx128 fp32 vector_l2_ops m=16 ef_construction=64 ef_search=%d k=%d, %d-query batches"
+                                    % (a.ef, a.k, a.nq), n=a.n, dim=a.dim, queries_per_step_per_gpu=per_step,
+                           parallelism="host threads x%d" % cores, graph=g["source"],
                            note="CPU restatement of pgvector-rx's scan on flat arrays (the Rust/pgrx reference cannot be built here)"),
+               build=dict(cpu_oracle_vectors_per_s=g.get("build_vec_per_s_cpu"),
+                          note="sequential ambuild restatement, one core (the reference's build is single-threaded per backend), "
+                               "measured when the cached graph was built"),
                cpu_baseline=dict(value=qps, unit="queries/s", cores=cores, kind="port", sample=sample),
                e2e=dict(value=qps, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out), flush=True)
