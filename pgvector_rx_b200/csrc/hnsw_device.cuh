@@ -491,6 +491,10 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
     const int lane = c.lane;
     const int lm = layer == 0 ? 2 * g.m : g.m;
     uint32_t vis_count = (uint32_t)c.len;
+    // a lane that lost a same-slot race inside the warp (see below) still has to store its id; that is checked just
+    // before the NEXT probe of the table, by which time the claim's round trip has long completed
+    bool lost_fresh = false;
+    uint32_t lost_old = VIS_EMPTY, lost_id = 0, lost_from = 0;
     while (true) {
         uint64_t ckey;
         PH_START(c);
@@ -527,6 +531,8 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             // (1) visited test-and-set: the first probe is ISSUED here and only consumed after the distances,
             //     so its L2 round trip overlaps the row gather instead of preceding it.  Rows of neighbours
             //     that turn out to be visited already are fetched speculatively and ignored.
+            if (lost_fresh && lost_old != VIS_EMPTY) vis_insert_from(c.vis, vis_mask, lost_from, lost_id);
+            lost_fresh = false;
             const uint32_t h = vis_home((uint32_t)nb, vis_mask);
             uint4 bk = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
             if (valid) bk = __ldcg(reinterpret_cast<const uint4 *>(c.vis + h));   // L2 (the table is written with atomics)
@@ -581,8 +587,11 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
                 const bool always_add = c.len < c.ef;
                 if (always_add || f32_ord(dr) < c.f_ord) S.insert(c, make_key(dr, (uint32_t)idr));
             }
-            // lost a same-slot race inside the warp: the id is new (decided above) but still has to be stored
-            if (fresh && claim_old != VIS_EMPTY) vis_insert_from(c.vis, vis_mask, (h + free_slot + 1) & vis_mask, id);
+            // lost a same-slot race inside the warp: the id is new (decided above) but still has to be stored -- deferred
+            lost_fresh = fresh && free_slot >= 0;
+            lost_old = claim_old;
+            lost_id = id;
+            lost_from = (h + (uint32_t)free_slot + 1u) & vis_mask;
             PH_TICK(c, 4);
         }
     }
