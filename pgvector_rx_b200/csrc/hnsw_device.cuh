@@ -339,19 +339,6 @@ struct RegList {
         }
         return true;
     }
-    // nearest unexpanded entry without marking it (used to prefetch its neighbour row)
-    __device__ __forceinline__ bool peek_nearest(const WarpCtx &c, uint64_t &key) const {
-        int jf = -1;
-#pragma unroll
-        for (int j = J - 1; j >= 0; j--) if (k[j] != KEY_NONE && (k[j] & 1ull) == 0) jf = j;
-        const uint32_t b = __ballot_sync(FULL, jf >= 0);
-        if (!b) return false;
-        uint64_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < J; j++) if (j == jf) mine = k[j];
-        key = __shfl_sync(FULL, mine, __ffs(b) - 1);
-        return true;
-    }
     // Build phase 2 (graph/mod.rs:425 `ep = w`): W of this layer becomes the entry-point list of the next
     // one.  Drops retained ties (they are not in W), clears the expanded flags, sets f_ord, and inserts
     // every id into the (freshly cleared) visited table.
@@ -441,15 +428,6 @@ struct SmemList {
         }
         return false;
     }
-    __device__ __forceinline__ bool peek_nearest(const WarpCtx &c, uint64_t &key) const {
-        for (int base = (hint >> 5) << 5; base < c.len; base += 32) {
-            const int i = base + c.lane;
-            const bool un = i >= hint && i < c.len && (S[i] & 1ull) == 0;
-            const uint32_t b = __ballot_sync(FULL, un);
-            if (b) { key = S[base + __ffs(b) - 1]; return true; }
-        }
-        return false;
-    }
     __device__ __forceinline__ void reopen(WarpCtx &c, uint32_t *vis, uint32_t vis_mask) {
         c.len = min(c.len, c.ef);
         __syncwarp();
@@ -517,10 +495,6 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
     // before the NEXT probe of the table, by which time the claim's round trip has long completed
     bool lost_fresh = false;
     uint32_t lost_old = VIS_EMPTY, lost_id = 0, lost_from = 0;
-    // neighbour row of the candidate that will most likely be popped next (layer 0): loaded while this expansion's
-    // distances and accepts run, used only if the pop really returns that candidate
-    uint32_t pref_id = 0xFFFFFFFFu;
-    int32_t pref_nb = -1;
     while (true) {
         uint64_t ckey;
         PH_START(c);
@@ -548,9 +522,7 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
         }
         for (int base = 0; base < lm; base += 32) {
             const int j = base + lane;
-            int32_t nb;
-            if (base == 0 && cid == pref_id) nb = pref_nb;
-            else nb = j < lm ? __ldg(row + j) : -1;
+            const int32_t nb = j < lm ? __ldg(row + j) : -1;
             const bool valid = nb >= 0;                 // lists are dense prefixes (scan.rs:273-279)
             const uint32_t vm = __ballot_sync(FULL, valid);
             if (!vm) break;
@@ -568,14 +540,6 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             if (layer > 0 && valid) lvl = __ldg(g.level + nb);
             if (valid) c.nbr[lane] = nb;
             __syncwarp();
-            if (layer == 0 && base == 0) {
-                uint64_t nk;
-                pref_id = 0xFFFFFFFFu;
-                if (S.peek_nearest(c, nk)) {
-                    pref_id = key_id(nk);
-                    pref_nb = lane < lm ? __ldg(g.adj0 + (size_t)pref_id * (size_t)lm + lane) : -1;
-                }
-            }
             // (2) gather + one distance per lane (lane r <-> neighbour r of this chunk)
             float d = 0.0f;
             for (int s = 0; s < cnt; s += c.R) {
