@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
         c.status = 0;
         c.rs_log = p.rs_log + (size_t)w * p.rs_cap * p.rs_ent;
         c.rs_ent = p.rs_ent;
+        c.spec = true;                 // the log needs the distance of every entry of every list read
         c.rs_cap = p.rs_cap;
         c.rs_n = 0;
         for (int l = lane; l < p.max_layers; l += 32) p.w_counts[(size_t)w * p.max_layers + l] = -1;

@@ -255,6 +255,7 @@ struct WarpCtx {
     int32_t *rs_log;       // build: 3 ints per expansion -- node id, ordered bits of f_dist (or -1), layer (or NULL)
     int rs_cap, rs_n;      // capacity / count (rs_n may exceed rs_cap: the host then treats the set as unknown)
     int rs_ent;            // ints per log entry: 3 + one word per 32 list slots
+    bool spec;             // fetch every neighbour's row while the visited probes are in flight (see search_layer)
     int lane;
 #ifdef PGVRX_PHASE_TIMING
     uint32_t t[8];         // cycles: 0 pop+adjacency, 1 visited, 2 tma issue+wait, 3 distance, 4 accept/insert
@@ -483,6 +484,21 @@ __device__ __forceinline__ void gather_rows(WarpCtx &c, const GraphView &g, int 
 #endif
 }
 
+// Same, but only the lanes with `mine` set (lane r <-> staging slot r - s) fetch their row.
+__device__ __forceinline__ void gather_rows_masked(WarpCtx &c, const GraphView &g, int s, int nrow, bool mine) {
+    const int lane = c.lane;
+    const bool issue = mine && lane >= s && lane < s + nrow;
+    const uint32_t m = __ballot_sync(FULL, issue);
+    if (!m) return;
+    if (lane == 0) mbar_arrive_expect_tx(c.mbar, (uint32_t)__popc(m) * g.row_stride);
+    __syncwarp();
+    if (issue)
+        tma_row_g2s(c.stage + (size_t)(lane - s) * c.stage_stride, g.vectors + (size_t)c.nbr[lane] * g.row_stride, g.row_stride,
+                    c.mbar, c.policy);
+    mbar_wait(c.mbar, c.phase);
+    c.phase ^= 1u;
+}
+
 // search_layer (graph/mod.rs:161-255 == scan.rs:302-448 without the iterative-scan bookkeeping).
 // Precondition: S[0, len) holds the entry points (unexpanded), their ids are in the visited set.
 template <int ELEM, int METRIC, class LIST>
@@ -540,22 +556,29 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             if (layer > 0 && valid) lvl = __ldg(g.level + nb);
             if (valid) c.nbr[lane] = nb;
             __syncwarp();
-            // (2) gather + one distance per lane (lane r <-> neighbour r of this chunk)
+            // Two orders of the same steps.  Speculative (c.spec, used by the build, whose log needs every entry's
+            // distance): gather all rows while the probes are in flight, resolve afterwards.  Otherwise: resolve the
+            // probes first and fetch only the rows that will be evaluated -- the scan kernel is bound by the L2 -> SM
+            // fabric (~6.1 TB/s, profiles/r1_notes.md), so not moving the ~15 % of rows that turn out to be visited
+            // is worth more than hiding the probe's round trip.
             float d = 0.0f;
-            for (int s = 0; s < cnt; s += c.R) {
-                const int nrow = min(c.R, cnt - s);
-                gather_rows(c, g, s, nrow);
-                PH_TICK(c, 2);
-                if (lane >= s && lane < s + nrow)
-                    d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
-                __syncwarp();   // all lanes done with the staging rows before they are overwritten
-                PH_TICK(c, 3);
-            }
-            // build log: which entries of this list are nearer than W's furthest distance was when the expansion
-            // started (every valid lane has its distance, visited or not) -- the host replays against it
-            if (c.rs_log && c.rs_n <= c.rs_cap) {
-                const uint32_t nm = __ballot_sync(FULL, valid && log_full && f32_ord(d) < log_f);
-                if (lane == 0) c.rs_log[(size_t)c.rs_ent * (size_t)(c.rs_n - 1) + 3 + (base >> 5)] = (int32_t)nm;
+            if (c.spec) {
+                // (2) gather + one distance per lane (lane r <-> neighbour r of this chunk)
+                for (int s = 0; s < cnt; s += c.R) {
+                    const int nrow = min(c.R, cnt - s);
+                    gather_rows(c, g, s, nrow);
+                    PH_TICK(c, 2);
+                    if (lane >= s && lane < s + nrow)
+                        d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
+                    __syncwarp();   // all lanes done with the staging rows before they are overwritten
+                    PH_TICK(c, 3);
+                }
+                // build log: which entries of this list are nearer than W's furthest distance was when the expansion
+                // started (every valid lane has its distance, visited or not) -- the host replays against it
+                if (c.rs_log && c.rs_n <= c.rs_cap) {
+                    const uint32_t nm = __ballot_sync(FULL, valid && log_full && f32_ord(d) < log_f);
+                    if (lane == 0) c.rs_log[(size_t)c.rs_ent * (size_t)(c.rs_n - 1) + 3 + (base >> 5)] = (int32_t)nm;
+                }
             }
             // (3) resolve the visited probes (visited BEFORE the level test, graph/mod.rs:206-216)
             const uint32_t id = (uint32_t)nb;
@@ -563,7 +586,7 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             const int free_slot = bk.x == VIS_EMPTY ? 0 : bk.y == VIS_EMPTY ? 1 : bk.z == VIS_EMPTY ? 2 : bk.w == VIS_EMPTY ? 3 : -1;
             bool fresh = valid && !present && free_slot >= 0;
             // claim the free slot; the result only matters when another lane of this warp claimed the same
-            // slot in this round (different id), which is checked after the accept loop
+            // slot in this round (different id), which is checked before the next probe of the table
             uint32_t claim_old = VIS_EMPTY;
             if (fresh) claim_old = atomicCAS(c.vis + h + free_slot, VIS_EMPTY, id);
             // home bucket full of other ids (rare at <= 40 % load): continue probing synchronously
@@ -575,6 +598,18 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             const bool pass = fresh && lvl >= layer;                     // graph/mod.rs:214, scan.rs:410
             c.n_dist += __popc(__ballot_sync(FULL, pass));
             PH_TICK(c, 1);
+            if (!c.spec) {
+                // (2') only the rows that are evaluated
+                for (int s = 0; s < cnt; s += c.R) {
+                    const int nrow = min(c.R, cnt - s);
+                    gather_rows_masked(c, g, s, nrow, pass);
+                    PH_TICK(c, 2);
+                    if (pass && lane >= s && lane < s + nrow)
+                        d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
+                    __syncwarp();
+                    PH_TICK(c, 3);
+                }
+            }
             // (4) accept in neighbour order (graph/mod.rs:226-242): the threshold only tightens and W only
             //     fills up, so lanes failing against the CURRENT threshold can never be accepted later
             const uint32_t dord = f32_ord(d);

@@ -38,6 +38,7 @@ struct SearchParams {
     int *work_counter;         // zeroed before the launch
     uint32_t stage_stride;     // bytes between staged rows (row_stride, +16 when that avoids bank conflicts)
     int R;                     // staged rows per warp (<= 32)
+    int spec;                  // 1: gather every neighbour's row before the visited probes resolve (see search_layer)
 };
 
 // K2: build-side search of a batch of pending inserts (hnsw_build.cu)

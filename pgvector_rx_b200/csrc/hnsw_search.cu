@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     c.rs_log = nullptr;
     c.rs_cap = c.rs_n = 0;
     c.rs_ent = 3;
+    c.spec = p.spec != 0;
     const int slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
     c.vis = p.vis_base + (size_t)slot * p.vis_entries;
 
