@@ -172,7 +172,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     p.work_counter = work + 0;
     p.stage_stride = main_cfg.L.stage_stride;
     p.R = main_cfg.L.R;
-    p.spec = getenv("PGVRX_SPEC_GATHER") ? 1 : 0;
+    p.spec = getenv("PGVRX_NO_SPEC_GATHER") ? 0 : 1;   // measured: 6.46 M QPS speculative vs 6.40 M probe-first (profiles/r1_notes.md)
     CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, stream));
 
     // queries that overflowed their visited table or tie tail run again with 16x the scratch

@@ -556,11 +556,10 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             if (layer > 0 && valid) lvl = __ldg(g.level + nb);
             if (valid) c.nbr[lane] = nb;
             __syncwarp();
-            // Two orders of the same steps.  Speculative (c.spec, used by the build, whose log needs every entry's
-            // distance): gather all rows while the probes are in flight, resolve afterwards.  Otherwise: resolve the
-            // probes first and fetch only the rows that will be evaluated -- the scan kernel is bound by the L2 -> SM
-            // fabric (~6.1 TB/s, profiles/r1_notes.md), so not moving the ~15 % of rows that turn out to be visited
-            // is worth more than hiding the probe's round trip.
+            // Two orders of the same steps.  Speculative (c.spec, the default; the build's log also needs every entry's
+            // distance): gather all rows while the probes are in flight, resolve afterwards.  Probe-first
+            // (PGVRX_NO_SPEC_GATHER): resolve the probes, then fetch only the rows that are evaluated -- 17 % less
+            // L2 -> SM traffic, but measured 1 % slower at C2 (the kernel is latency bound, not fabric bound).
             float d = 0.0f;
             if (c.spec) {
                 // (2) gather + one distance per lane (lane r <-> neighbour r of this chunk)
