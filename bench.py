@@ -351,18 +351,24 @@ def run_b200(a):
     batches = query_batches(a, nb, rank)
     dev = torch.device("cuda", local)
     d_q = [torch.from_numpy(b).to(dev) for b in batches]
-    d_ids = torch.empty((a.nq, a.k), dtype=torch.int32, device=dev)
-    d_dists = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)
-    d_cnt = torch.empty((a.nq,), dtype=torch.int32, device=dev)
-    # a real (non-default) stream: the library launches on the stream it is handed, and the
-    # torch events below must be recorded on that same stream to see the kernels
-    tstream = torch.cuda.Stream(device=dev)
+    # two batches in flight: consecutive steps go to alternating streams (each with its own result buffers; the library
+    # keeps one scratch set per stream), so the ragged tail of one persistent launch -- warps finishing their last query
+    # at different times -- is filled by the next batch instead of idling the SMs.  torch events are recorded on the
+    # streams the library launches on.
+    n_fly = 2
+    tstreams = [torch.cuda.Stream(device=dev) for _ in range(n_fly)]
+    tstream = tstreams[0]
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
+    outs = [(torch.empty((a.nq, a.k), dtype=torch.int32, device=dev), torch.empty((a.nq, a.k), dtype=torch.float32, device=dev),
+             torch.empty((a.nq,), dtype=torch.int32, device=dev)) for _ in range(n_fly)]
+    d_ids, d_dists, d_cnt = outs[0]
 
     def step_device(i):
-        ix.search_device(d_q[i % nb].data_ptr(), a.nq, a.k, a.ef, d_ids.data_ptr(), d_dists.data_ptr(), d_cnt.data_ptr(), stream=stream)
+        o = outs[i % n_fly]
+        ix.search_device(d_q[i % nb].data_ptr(), a.nq, a.k, a.ef, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                         stream=tstreams[i % n_fly].cuda_stream)
 
     def barrier():
         if world > 1:
@@ -376,10 +382,14 @@ def run_b200(a):
     clocks = ClockSampler(local)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(tstream)
     for i in range(a.steps):
         step_device(i)
-    e1.record()
+    for t in tstreams[1:]:                       # the timed region ends when every stream has drained
+        ev = torch.cuda.Event()
+        ev.record(t)
+        tstream.wait_event(ev)
+    e1.record(tstream)
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
@@ -452,7 +462,7 @@ def run_b200(a):
                    data="synthetic", recall_at_10=rec, recall_at_10_cpu=rec_cpu, ids_match_cpu_oracle=parity_ok,
                    config=dict(workload="C2: 1Mx128 fp32 vector_l2_ops m=16 ef_construction=64 ef_search=%d k=%d, %d-query batches"
                                         % (a.ef, a.k, a.nq), n=a.n, dim=a.dim, queries_per_step_per_gpu=a.nq,
-                               parallelism="query-sharded x%d, graph replicated" % world, graph=g["source"],
+                               parallelism="query-sharded x%d, graph replicated" % world, batches_in_flight=2, graph=g["source"],
                                l2="working set (graph + vectors 0.64 GB, 6.7 GB gathered per step) exceeds L2; batches rotate"),
                    clocks=clk,
                    e2e=dict(value=e2e, unit="queries/s", h2d_bytes_per_step=a.nq * row_bytes,

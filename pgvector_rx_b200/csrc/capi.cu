@@ -132,14 +132,25 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     if (rc) return rc;
 
     const int wpb = SEARCH_THREADS / 32;
-    CU_TRY(ix, ix->vis.ensure((size_t)main_cfg.grid * wpb * main_cfg.vis_entries * 4));
-    CU_TRY(ix, ix->vis_retry.ensure((size_t)retry_cfg.grid * wpb * retry_cfg.vis_entries * 4));
-    CU_TRY(ix, ix->status.ensure((size_t)nq * 4));
-    CU_TRY(ix, ix->qmap.ensure((size_t)nq * 4));
-    CU_TRY(ix, ix->work.ensure(64));
-    if (stats) CU_TRY(ix, ix->ctr.ensure((size_t)nq * 16));
+    // scratch set of this stream (see index_internal.h)
+    pgvrx_index::ScanScratch *sc = nullptr;
+    for (auto &cand : ix->scan_scratch) if (cand.used && cand.owner == stream) { sc = &cand; break; }
+    if (!sc) for (auto &cand : ix->scan_scratch) if (!cand.used) { sc = &cand; break; }
+    if (!sc) {
+        sc = &ix->scan_scratch[ix->scan_scratch_rr];
+        ix->scan_scratch_rr = (ix->scan_scratch_rr + 1) % pgvrx_index::N_SCAN_SCRATCH;
+        CU_TRY(ix, cudaStreamSynchronize(sc->owner));      // its previous user must be done before another stream touches it
+    }
+    sc->used = true;
+    sc->owner = stream;
+    CU_TRY(ix, sc->vis.ensure((size_t)main_cfg.grid * wpb * main_cfg.vis_entries * 4));
+    CU_TRY(ix, sc->vis_retry.ensure((size_t)retry_cfg.grid * wpb * retry_cfg.vis_entries * 4));
+    CU_TRY(ix, sc->status.ensure((size_t)nq * 4));
+    CU_TRY(ix, sc->qmap.ensure((size_t)nq * 4));
+    CU_TRY(ix, sc->work.ensure(64));
+    if (stats) CU_TRY(ix, sc->ctr.ensure((size_t)nq * 16));
 
-    int *work = (int *)ix->work.p;   // [0] main counter, [1] retry counter, [2] n_failed
+    int *work = (int *)sc->work.p;   // [0] main counter, [1] retry counter, [2] n_failed
     CU_TRY(ix, cudaMemsetAsync(work, 0, 64, stream));
     if (stats) CU_TRY(ix, cudaEventRecord(ix->ev0, stream));
 
@@ -157,17 +168,17 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     p.out_ids = d_ids;
     p.out_dists = d_dists;
     p.out_counts = d_counts;
-    p.out_status = (uint32_t *)ix->status.p;
-    p.out_ctr = stats ? (uint32_t *)ix->ctr.p : nullptr;
+    p.out_status = (uint32_t *)sc->status.p;
+    p.out_ctr = stats ? (uint32_t *)sc->ctr.p : nullptr;
     p.out_phase = nullptr;
 #ifdef PGVRX_PHASE_TIMING
     if (stats) {
-        CU_TRY(ix, ix->phase.ensure((size_t)nq * 32));
-        CU_TRY(ix, cudaMemsetAsync(ix->phase.p, 0, (size_t)nq * 32, stream));
-        p.out_phase = (uint32_t *)ix->phase.p;
+        CU_TRY(ix, sc->phase.ensure((size_t)nq * 32));
+        CU_TRY(ix, cudaMemsetAsync(sc->phase.p, 0, (size_t)nq * 32, stream));
+        p.out_phase = (uint32_t *)sc->phase.p;
     }
 #endif
-    p.vis_base = (uint32_t *)ix->vis.p;
+    p.vis_base = (uint32_t *)sc->vis.p;
     p.vis_entries = main_cfg.vis_entries;
     p.work_counter = work + 0;
     p.stage_stride = main_cfg.L.stage_stride;
@@ -176,12 +187,12 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, stream));
 
     // queries that overflowed their visited table or tie tail run again with 16x the scratch
-    CU_TRY(ix, launch_collect_failed(p.out_status, (int)nq, (int32_t *)ix->qmap.p, work + 2, stream));
+    CU_TRY(ix, launch_collect_failed(p.out_status, (int)nq, (int32_t *)sc->qmap.p, work + 2, stream));
     SearchParams r = p;
-    r.qmap = (const int32_t *)ix->qmap.p;
+    r.qmap = (const int32_t *)sc->qmap.p;
     r.n_work = work + 2;
     r.tail_cap = retry_cfg.L.tail_cap;
-    r.vis_base = (uint32_t *)ix->vis_retry.p;
+    r.vis_base = (uint32_t *)sc->vis_retry.p;
     r.vis_entries = retry_cfg.vis_entries;
     r.work_counter = work + 1;
     r.stage_stride = retry_cfg.L.stage_stride;
@@ -194,7 +205,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
         CU_TRY(ix, cudaEventElapsedTime(&stats->kernel_ms, ix->ev0, ix->ev1));
         stats->n_launches = 3;
         std::vector<uint32_t> h((size_t)nq * 4);
-        CU_TRY(ix, cudaMemcpy(h.data(), ix->ctr.p, (size_t)nq * 16, cudaMemcpyDeviceToHost));
+        CU_TRY(ix, cudaMemcpy(h.data(), sc->ctr.p, (size_t)nq * 16, cudaMemcpyDeviceToHost));
         for (int64_t i = 0; i < nq; i++) {
             stats->n_dist += h[(size_t)i * 4 + 0];
             stats->n_expand0 += h[(size_t)i * 4 + 1];
@@ -204,7 +215,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
 #ifdef PGVRX_PHASE_TIMING
         {
             std::vector<uint32_t> ph((size_t)nq * 8);
-            CU_TRY(ix, cudaMemcpy(ph.data(), ix->phase.p, (size_t)nq * 32, cudaMemcpyDeviceToHost));
+            CU_TRY(ix, cudaMemcpy(ph.data(), sc->phase.p, (size_t)nq * 32, cudaMemcpyDeviceToHost));
             double sum[8] = {0};
             for (int64_t i = 0; i < nq; i++) for (int t = 0; t < 8; t++) sum[t] += ph[(size_t)i * 8 + t];
             fprintf(stderr, "[pgvrx phase cycles/query] pop+adj %.0f  visited %.0f  tma %.0f  distance %.0f  accept %.0f  | total %.0f"
@@ -222,7 +233,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     if (check_status) {
         CU_TRY(ix, cudaStreamSynchronize(stream));
         std::vector<uint32_t> st((size_t)nq);
-        CU_TRY(ix, cudaMemcpy(st.data(), ix->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+        CU_TRY(ix, cudaMemcpy(st.data(), sc->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
         for (int64_t i = 0; i < nq; i++)
             if (st[(size_t)i] != 0) {
                 char b[160];
@@ -358,11 +369,15 @@ void pgvrx_index_destroy(pgvrx_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->desc.device);
     DevBuf *bufs[] = {&ix->vectors, &ix->adj0, &ix->adj_up, &ix->upper_base, &ix->level, &ix->q, &ix->ids, &ix->dists,
-                      &ix->counts, &ix->status, &ix->ctr, &ix->vis, &ix->vis_retry, &ix->qmap, &ix->work, &ix->phase,
+                      &ix->counts,
                       &ix->part_ids, &ix->part_dists, &ix->cand, &ix->tc_xhi, &ix->tc_xlo, &ix->tc_xnorm, &ix->tc_xmax,
                       &ix->tc_qhi, &ix->tc_qlo, &ix->tc_qnorm, &ix->tc_cand, &ix->tc_bound, &ix->tc_uncert, &ix->tc_cnt,
                       &ix->tc_fq, &ix->tc_fids, &ix->tc_fdists, &ix->tc_dbg, &ix->tc_hint};
     for (DevBuf *b : bufs) b->release();
+    for (auto &sc : ix->scan_scratch) {
+        DevBuf *sb[] = {&sc.status, &sc.ctr, &sc.vis, &sc.vis_retry, &sc.qmap, &sc.work, &sc.phase};
+        for (DevBuf *b : sb) b->release();
+    }
     if (ix->build) pgvrx_host::destroy_build_state(ix->build);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);

@@ -65,7 +65,18 @@ struct pgvrx_index {
     bool loaded = false;        // graph + rows resident
     bool rows_loaded = false;   // vector table resident (enough for the flat / re-rank paths)
     // scratch
-    DevBuf q, ids, dists, counts, status, ctr, vis, vis_retry, qmap, work, phase;
+    DevBuf q, ids, dists, counts;
+    // Scan scratch (visited tables, per-query status, work counters).  One set per stream the caller scans on, so that
+    // batches submitted on different streams overlap on the device (the tail of one persistent launch is filled by the
+    // head of the next); a set is rebound to a new stream only after its previous stream has drained.
+    struct ScanScratch {
+        DevBuf status, ctr, vis, vis_retry, qmap, work, phase;
+        cudaStream_t owner = nullptr;
+        bool used = false;
+    };
+    static constexpr int N_SCAN_SCRATCH = 4;
+    ScanScratch scan_scratch[N_SCAN_SCRATCH];
+    int scan_scratch_rr = 0;
     DevBuf part_ids, part_dists, cand;   // flat kNN partial lists, re-rank candidates
     // tensor-core flat path (K4b): tf32 hi/lo splits of the table (built lazily, dropped when the table changes)
     DevBuf tc_xhi, tc_xlo, tc_xnorm, tc_xmax, tc_qhi, tc_qlo, tc_qnorm, tc_cand, tc_bound, tc_uncert, tc_cnt, tc_fq, tc_fids,
