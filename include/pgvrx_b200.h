@@ -199,8 +199,11 @@ int pgvrx_index_export_graph(pgvrx_index *idx, void *rows, uint8_t *level, int32
 int pgvrx_search_batch(pgvrx_index *idx, const void *queries, int64_t nq, int32_t ef_search,
                        int32_t k, int32_t *out_ids, float *out_dists, int32_t *out_counts,
                        pgvrx_search_stats *stats /* may be NULL */);
-/* Same, with DEVICE buffers on `cuda_stream` (a cudaStream_t; NULL = the handle's stream).
- * Asynchronous unless stats != NULL (stats needs the kernels to have finished). */
+/* Same, with DEVICE-accessible buffers on `cuda_stream` (a cudaStream_t; NULL = the handle's stream): device memory
+ * or page-locked host memory (the kernels then read queries from / write results to the host directly).
+ * Asynchronous unless stats != NULL (stats needs the kernels to have finished); calls on different streams overlap on
+ * the device (one scratch set per stream).  A query that exhausted its scratch even in the retry pass is reported
+ * with out_counts[q] = -1 (the blocking pgvrx_search_batch turns that into an error). */
 int pgvrx_search_batch_device(pgvrx_index *idx, const void *d_queries, int64_t nq, int32_t ef_search,
                               int32_t k, int32_t *d_ids, float *d_dists, int32_t *d_counts,
                               pgvrx_search_stats *stats, void *cuda_stream);
