@@ -26,7 +26,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+_JSON_OUT = sys.stdout
 METRIC = "QPS@recall@10 and build vectors/s, 1M×128 L2 HNSW, 1/2/4/8 B200"
+
+
+def host_cores(a=None):
+    """Host threads for the CPU legs: --threads, else the cores this process is allowed to run on."""
+    if a is not None and getattr(a, "threads", 0) > 0:
+        return a.threads
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def log(*a):
@@ -49,10 +60,16 @@ def parse():
     ap.add_argument("--cache", default=os.path.join(ROOT, "data_cache"))
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--recall-sample", type=int, default=200)
-    ap.add_argument("--build-rows", type=int, default=1_000_000,
+    ap.add_argument("--build-rows", type=int, default=-1,
                     help="rows of the same dataset built on the GPU for the build vectors/s figure (0 = skip)")
+    ap.add_argument("--threads", type=int, default=0, help="host threads for the CPU legs (0 = the cores this process may use)")
     ap.add_argument("--no-flat", action="store_true", help="skip the exact flat-kNN section (recall then uses the oracle's brute force on --recall-sample queries)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.build_rows < 0:
+        # the build does not shard (replicas only): the full 1M-row build is measured at N = 1, larger N keep a 100k-row
+        # sample of it on rank 0 so that the scaling runs stay short
+        a.build_rows = 1_000_000 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 100_000
+    return a
 
 
 # ---------------------------------------------------------------------------------------------
@@ -108,7 +125,7 @@ def cpu_baseline(a, g, queries, sample=0, budget_s=12.0):
     """The oracle (CPU restatement of the reference's scan) on all host cores: passes over the same
     10k-query batch (or `sample` queries of it) until about budget_s seconds of wall time are used."""
     o = oracle_for(a, g)
-    cores = os.cpu_count() or 1
+    cores = host_cores(a)
     q = queries[:sample] if sample else queries
     o.search_batch(q[: 8 * cores], ef_search=a.ef, k=a.k, nthreads=cores)      # warm caches / threads
     done, t0, ids = 0, time.perf_counter(), None
@@ -159,7 +176,7 @@ def recall_at_k(a, g, queries, got_ids, sample):
     """recall@k against the oracle's brute force on a sample of the batch (CPU; used by the reference arm)."""
     import oracle_ffi as O
     s = min(sample, len(queries))
-    gt, _ = O.flat_topk(O.ELEM_F32, O.L2SQ, a.dim, g["rows"], queries[:s], a.k, nthreads=os.cpu_count() or 1)
+    gt, _ = O.flat_topk(O.ELEM_F32, O.L2SQ, a.dim, g["rows"], queries[:s], a.k, nthreads=host_cores(a))
     hit = sum(len(set(got_ids[i].tolist()) & set(gt[i].tolist())) for i in range(s))
     return hit / float(s * a.k)
 
@@ -303,7 +320,7 @@ def run_reference(a):
     g = load_or_build_graph(a)
     batches = query_batches(a, 1, 0)
     o = oracle_for(a, g)
-    cores = os.cpu_count() or 1
+    cores = host_cores(a)
     per_step = a.nq if cores >= 8 else min(a.nq, 400 * cores)   # the whole 10k batch per step unless the box is tiny
     q = batches[0][:per_step]
     for _ in range(max(a.warmup, 1)):
@@ -327,7 +344,7 @@ def run_reference(a):
                                "measured when the cached graph was built"),
                cpu_baseline=dict(value=qps, unit="queries/s", cores=cores, kind="port", sample=sample),
                e2e=dict(value=qps, unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_JSON_OUT, flush=True)
 
 
 def run_b200(a):
@@ -469,7 +486,7 @@ def run_b200(a):
             rec_cpu = recall_at_k(a, g, last_batch, cpu_ids, min(a.recall_sample, nchk))
         else:
             s_chk = min(64, a.nq)
-            o_gt, _ = O.flat_topk(O.ELEM_F32, O.L2SQ, a.dim, g["rows"], last_batch[:s_chk], a.k, nthreads=os.cpu_count() or 1)
+            o_gt, _ = O.flat_topk(O.ELEM_F32, O.L2SQ, a.dim, g["rows"], last_batch[:s_chk], a.k, nthreads=host_cores(a))
             flat_info["ids_match_cpu_oracle"] = bool(np.array_equal(o_gt, gt_ids[:s_chk]))
             rec = recall_vs(gt_ids, last_ids)
             rec_cpu = recall_vs(gt_ids[:nchk], cpu_ids)
@@ -496,7 +513,7 @@ def run_b200(a):
                    cpu_baseline=base,
                    build=build_info,
                    flat_knn=flat_info)
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -510,6 +527,10 @@ def batches_rank0_last(a):
 
 
 def main():
+    global _JSON_OUT
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -21,6 +21,8 @@
 // lists and for every list that pending elements link back to.  Host distances remain only for groups that do not
 // fit on a CTA (ef_construction > 128 or very wide rows) and for comparing a pending element with newcomers of a
 // changed list during validation.
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -135,7 +137,10 @@ class Pool {
         pending_.store(n_ - 1, std::memory_order_relaxed);
         gen_.fetch_add(1, std::memory_order_release);
         run();
-        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
+        for (int spins = 0; pending_.load(std::memory_order_acquire) != 0; spins++) {
+            cpu_relax();
+            if (spins > 4000) std::this_thread::yield();
+        }
     }
 
   private:
@@ -163,7 +168,9 @@ class Pool {
             int spins = 0;
             while ((gnow = gen_.load(std::memory_order_acquire)) == seen) {
                 cpu_relax();
-                if (++spins > 200000) { std::this_thread::sleep_for(std::chrono::microseconds(50)); spins = 0; }   // idle build (GPU phase): back off
+                ++spins;
+                if (spins > 200000) { std::this_thread::sleep_for(std::chrono::microseconds(50)); spins = 100000; }   // long GPU phase: back off
+                else if (spins > 4000) std::this_thread::yield();   // never starve the main thread when cores are oversubscribed
             }
             seen = gnow;
             if (stop_.load(std::memory_order_acquire)) return;
@@ -426,7 +433,14 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     for (int64_t i = 0; i < n_rows; i++)
         if (levels[i] < 0 || levels[i] > max_level_allowed) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "level out of range");
 
-    const int nthreads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    // default: the cores this process may actually run on (a launcher may pin each rank to a subset of the machine)
+    int avail = (int)std::max(1u, std::thread::hardware_concurrency());
+    {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) avail = std::min(avail, (int)CPU_COUNT(&set));
+    }
+    const int nthreads = host_threads > 0 ? host_threads : avail;
     Pool pool(nthreads);
     const double t_start = now_ms();
     double gpu_ms = 0.0, kernel_ms = 0.0;
