@@ -156,7 +156,7 @@ def gpu_build_sample(a, local):
     dt = time.perf_counter() - t0
     out = dict(gpu_vectors_per_s=n / dt, rows=n, seconds=dt, rounds=st["n_rounds"], searches=st["n_searched"],
                conflicts=st["n_conflicts"], kernel_ms=st["kernel_ms"], host_threads=st["host_threads"],
-               commits_per_round=n / max(st["n_rounds"], 1), pairwise_on_gpu=st["n_pair_gpu"],
+               commits_per_round=n / max(st["n_rounds"], 1), pairwise_on_gpu=st["n_pair_gpu"], host_distance_evals=st["n_host_dist"],
                note="%s rows of the C2 dataset (same seeds and levels as the oracle's build); exact sequential semantics, "
                     "see DESIGN.md" % ("all %d" % n if n == a.n else "first %d" % n))
     tag = "c2_1m" if (n, a.dim, a.m, a.efc) == (1_000_000, 128, 16, 64) else "g_%d_%d_%d_%d" % (n, a.dim, a.m, a.efc)

@@ -162,7 +162,9 @@ typedef struct {
     uint64_t n_dist, n_expand0, n_expand_upper;   /* GPU work of the committed searches           */
     uint64_t n_pair;          /* pairwise distances select_neighbors consulted (graph/mod.rs:326)          */
     uint64_t n_pair_gpu;      /* pairwise distances computed on the GPU for back-link re-selections        */
-    uint64_t n_validation_dist; /* distances evaluated to validate speculative searches against changed lists */
+    uint64_t n_validation_dist; /* pending-vs-pending distances consulted when validating speculative searches   */
+    uint64_t n_host_dist;     /* distances evaluated on the HOST (0 unless a candidate group does not fit on a CTA:
+                                 ef_construction > 128 or very wide rows)                                   */
     double   gpu_ms;          /* wall time spent in upload + kernel + download                     */
     double   kernel_ms;       /* device time of the K2 launches alone (CUDA events)               */
     double   total_ms;

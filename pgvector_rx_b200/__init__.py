@@ -66,7 +66,7 @@ class BuildStats(C.Structure):
     _fields_ = [("n_rounds", C.c_uint64), ("n_searched", C.c_uint64), ("n_conflicts", C.c_uint64),
                 ("n_duplicates", C.c_uint64), ("n_big_retries", C.c_uint64), ("n_dist", C.c_uint64),
                 ("n_expand0", C.c_uint64), ("n_expand_upper", C.c_uint64), ("n_pair", C.c_uint64),
-                ("n_pair_gpu", C.c_uint64), ("n_validation_dist", C.c_uint64),
+                ("n_pair_gpu", C.c_uint64), ("n_validation_dist", C.c_uint64), ("n_host_dist", C.c_uint64),
                 ("gpu_ms", C.c_double), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("host_threads", C.c_int32)]
 

@@ -19,8 +19,9 @@
 // select_neighbors never needs a distance, only "d(e, r) <= d(e, owner)" for kept r (graph/mod.rs:333): the GPU
 // answers that for all pairs of a group at once (pairwise_kernel, 128-bit masks), for the new elements' candidate
 // lists and for every list that pending elements link back to.  Host distances remain only for groups that do not
-// fit on a CTA (ef_construction > 128 or very wide rows) and for comparing a pending element with newcomers of a
-// changed list during validation.
+// fit on a CTA (ef_construction > 128 or very wide rows); the pending-vs-pending distances the validation needs for
+// newcomers of a changed list come from the GPU as well (pending_pairs_kernel).  For the bench configuration no
+// distance is evaluated on the host (pgvrx_build_stats.n_host_dist == 0).
 #include <sched.h>
 
 #include <algorithm>
@@ -82,33 +83,6 @@ static float host_distance(int elem, int metric, int dim, const uint8_t *pa, con
     }
     if (ab == 0) return 1.0f;
     return (float)(1.0 - ((double)ab / (double)(aa + bb - ab)));
-}
-
-// d(a, b) < f, bit-for-bit the comparison the kernel makes, but leaving the accumulation as soon as the running sum
-// reaches f where that is sound: L2 / L1 / Hamming sums only grow (adding a non-negative term never lowers an fp sum).
-static bool host_distance_less(int elem, int metric, int dim, const uint8_t *pa, const uint8_t *pb, float f) {
-    if (metric == PGVRX_METRIC_NEG_IP || metric == PGVRX_METRIC_JACCARD || !(f == f))
-        return host_distance(elem, metric, dim, pa, pb) < f;
-    if (elem == PGVRX_ELEM_F32) {
-        const float *a = (const float *)pa, *b = (const float *)pb;
-        float acc = 0.0f;
-        int i = 0;
-        if (metric == PGVRX_METRIC_L2SQ) {
-            for (; i + 16 <= dim; i += 16) {
-                for (int j = i; j < i + 16; j++) { float d = a[j] - b[j]; acc += d * d; }
-                if (acc >= f) return false;
-            }
-            for (; i < dim; i++) { float d = a[i] - b[i]; acc += d * d; }
-        } else {
-            for (; i + 16 <= dim; i += 16) {
-                for (int j = i; j < i + 16; j++) acc += std::fabs(a[j] - b[j]);
-                if (acc >= f) return false;
-            }
-            for (; i < dim; i++) acc += std::fabs(a[i] - b[i]);
-        }
-        return acc < f;
-    }
-    return host_distance(elem, metric, dim, pa, pb) < f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -214,8 +188,8 @@ struct BuildState {
     std::atomic<uint64_t> n_pair{0};
 
     const uint8_t *row(int64_t e) const { return values.data() + (size_t)e * row_bytes; }
-    float dist(int64_t a, int64_t b) const { return host_distance(elem, metric, dim, row(a), row(b)); }
-    bool dist_less(int64_t a, int64_t b, float f) const { return host_distance_less(elem, metric, dim, row(a), row(b), f); }
+    std::atomic<uint64_t> n_host_dist{0};   // distances evaluated on the host (groups that do not fit on a CTA)
+    float dist(int64_t a, int64_t b) { n_host_dist.fetch_add(1, std::memory_order_relaxed); return host_distance(elem, metric, dim, row(a), row(b)); }
     int lm(int lc) const { return lc == 0 ? 2 * m : m; }
     int32_t *ids(int64_t v, int lc) { return lc == 0 ? &adj0[(size_t)v * 2 * m] : &adj_up[(size_t)(upper_base[(size_t)v] + lc - 1) * m]; }
     float *dists(int64_t v, int lc) { return lc == 0 ? &dist0[(size_t)v * 2 * m] : &dist_up[(size_t)(upper_base[(size_t)v] + lc - 1) * m]; }
@@ -636,6 +610,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const size_t o_wcnt = carve((size_t)B * max_layers * 4), o_rs = carve((size_t)B * rs_cap * rs_ent * 4);
         const size_t o_rscnt = carve((size_t)B * 4), o_status = carve((size_t)B * 4), o_ctr = carve((size_t)B * 16);
         const size_t o_wmask = carve(w_masks ? (size_t)B * max_layers * efc * (PAIR_MAX_ROWS / 32) * 4 : 0);
+        const size_t o_pp = carve((size_t)B * B * 4);          // d(pending j, pending i), i < j
         CU_TRY(ix, rb.out_pack.ensure(po));
         CU_TRY(ix, h_pack.ensure(po));
         uint8_t *dpk = (uint8_t *)rb.out_pack.p;
@@ -688,6 +663,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             wp.stage_stride = cfg.L.stage_stride;
             CU_TRY(ix, launch_pairwise(ix->desc.elem_type, ix->desc.metric, gv, wp, pair_rows, std::min(B * max_layers, ix->sm_count * pair_occ), ix->stream));
         }
+        CU_TRY(ix, launch_pending_pairs(ix->desc.elem_type, ix->desc.metric, gv, bp.elem_ids, B, (float *)(dpk + o_pp), ix->sm_count, ix->stream));
         CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));
         CU_TRY(ix, cudaMemcpyAsync(h_pack.p, rb.out_pack.p, po, cudaMemcpyDeviceToHost, ix->stream));
         const int32_t *h_wids = (const int32_t *)(hpk + o_wids);
@@ -698,6 +674,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const uint32_t *h_status = (const uint32_t *)(hpk + o_status);
         const uint32_t *h_ctr = (const uint32_t *)(hpk + o_ctr);
         const uint32_t *h_wmask = (const uint32_t *)(hpk + o_wmask);
+        const float *h_pp = (const float *)(hpk + o_pp);
         CU_TRY(ix, cudaStreamSynchronize(ix->stream));
         gpu_ms += now_ms() - tg0;
         {
@@ -917,8 +894,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                     { const uint32_t fb = (ford & 0x80000000u) ? (ford & 0x7FFFFFFFu) : ~ford; memcpy(&f_t, &fb, 4); }
                     auto near = [&](int pos) -> bool {
                         if (pos < n_old) return (bits[pos >> 5] >> (pos & 31)) & 1u;
+                        // a newcomer is a pending element of this round: its distance to e came with the round's results
                         n_val_dist++;
-                        return g.dist_less(e, G.ids[(size_t)pos], f_t);
+                        return ord_of(h_pp[(size_t)i * B + (size_t)(G.ids[(size_t)pos] - (int32_t)e_base)]) < ford;
                     };
                     int io = 0, in_ = 0;
                     while (valid) {
@@ -1043,6 +1021,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         stats->n_expand_upper = c_expu;
         stats->n_pair = g.n_pair.load();
         stats->n_pair_gpu = n_pair_gpu;
+        stats->n_host_dist = g.n_host_dist.load();
         stats->n_validation_dist = n_val_dist + n_val_dist_atomic.load();
         stats->gpu_ms = gpu_ms;
         stats->kernel_ms = kernel_ms;

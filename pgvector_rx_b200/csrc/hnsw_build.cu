@@ -7,6 +7,8 @@
 // Outputs per searched layer: W sorted ascending by (distance, id) -- what select_neighbors consumes
 // on the host -- and the ids of all expanded nodes (the search's read set), which lets the host
 // prove that a speculative result is still exact after earlier inserts of the batch were committed.
+#include <algorithm>
+
 #include "hnsw_device.cuh"
 #include "hnsw_kernels.h"
 
@@ -202,6 +204,58 @@ __global__ void __launch_bounds__(SEARCH_THREADS) pairwise_kernel(GraphView g, P
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
     }
+}
+
+// Distances between the pending elements of a round: out[j * n + i] = d(pending j, pending i) for i < j, evaluated as
+// d(query = j, row = i) like every other distance.  The host needs them when it validates element j against a list
+// that an earlier element i of the same round has joined (build_host.cu).  One warp per j, lanes over i.
+template <int ELEM, int METRIC>
+__global__ void __launch_bounds__(SEARCH_THREADS) pending_pairs_kernel(GraphView g, const int32_t *__restrict__ ids, int n,
+                                                                       float *__restrict__ out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *q = smem + (size_t)warp * g.row_stride;
+    const int nvec = (int)(g.row_stride / 16);
+    for (int j = blockIdx.x * (SEARCH_THREADS / 32) + warp; j < n; j += gridDim.x * (SEARCH_THREADS / 32)) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g.vectors + (size_t)ids[j] * g.row_stride);
+        __syncwarp();
+        for (int v = lane; v < nvec; v += 32) reinterpret_cast<uint4 *>(q)[v] = __ldg(src + v);
+        __syncwarp();
+        for (int i0 = 0; i0 < j; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < j) out[(size_t)j * n + i] = row_distance<ELEM, METRIC>(q, g.vectors + (size_t)ids[i] * g.row_stride, nvec);
+        }
+    }
+}
+
+typedef void (*pp_kernel_t)(GraphView, const int32_t *, int, float *);
+static pp_kernel_t pick_pp(int elem, int metric) {
+    if (elem == ELEM_F32) {
+        if (metric == METRIC_L2SQ) return pending_pairs_kernel<ELEM_F32, METRIC_L2SQ>;
+        if (metric == METRIC_NEG_IP) return pending_pairs_kernel<ELEM_F32, METRIC_NEG_IP>;
+        if (metric == METRIC_L1) return pending_pairs_kernel<ELEM_F32, METRIC_L1>;
+    } else if (elem == ELEM_F16) {
+        if (metric == METRIC_L2SQ) return pending_pairs_kernel<ELEM_F16, METRIC_L2SQ>;
+        if (metric == METRIC_NEG_IP) return pending_pairs_kernel<ELEM_F16, METRIC_NEG_IP>;
+        if (metric == METRIC_L1) return pending_pairs_kernel<ELEM_F16, METRIC_L1>;
+    } else if (elem == ELEM_BIT) {
+        if (metric == METRIC_HAMMING) return pending_pairs_kernel<ELEM_BIT, METRIC_HAMMING>;
+        if (metric == METRIC_JACCARD) return pending_pairs_kernel<ELEM_BIT, METRIC_JACCARD>;
+    }
+    return nullptr;
+}
+
+cudaError_t launch_pending_pairs(int elem, int metric, const GraphView &g, const int32_t *ids, int n, float *out, int sm_count,
+                                 cudaStream_t stream) {
+    pp_kernel_t k = pick_pp(elem, metric);
+    if (!k) return cudaErrorInvalidValue;
+    if (n <= 1) return cudaSuccess;
+    const size_t smem = (size_t)(SEARCH_THREADS / 32) * g.row_stride;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = std::max(1, std::min((n + 3) / 4, sm_count * 4));
+    k<<<grid, SEARCH_THREADS, smem, stream>>>(g, ids, n, out);
+    return cudaGetLastError();
 }
 
 typedef void (*pair_kernel_t)(GraphView, PairParams);

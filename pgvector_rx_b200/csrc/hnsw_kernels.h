@@ -92,6 +92,8 @@ cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem
 cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
                                 size_t smem_block, cudaStream_t stream);
 cudaError_t launch_pairwise(int elem, int metric, const GraphView &g, const PairParams &p, int max_rows, int grid, cudaStream_t stream);
+cudaError_t launch_pending_pairs(int elem, int metric, const GraphView &g, const int32_t *ids, int n, float *out, int sm_count,
+                                 cudaStream_t stream);
 cudaError_t launch_scatter_rows(int32_t *dst, const int64_t *row_offsets, const int32_t *packed, int row_len, int n_rows,
                                 cudaStream_t stream);
 cudaError_t launch_collect_failed(const uint32_t *status, int nq, int32_t *qmap, int *n_work, cudaStream_t stream);

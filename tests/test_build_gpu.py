@@ -57,6 +57,7 @@ def test_build_vector_l2_exact_adjacency():
     assert st["n_pair"] >= oc["n_pair"]
     assert st["n_expand0"] == oc["n_expand0"] and st["n_expand_upper"] == oc["n_expand_upper"]
     assert abs(st["n_dist"] - oc["n_dist"]) <= 0.01 * oc["n_dist"]
+    assert st["n_host_dist"] == 0 and st["n_pair_gpu"] > 0          # every distance of this build was computed on the GPU
     print("build stats", st)
     # the built graph is resident: scanning it matches the oracle's scan of its own graph
     q = make_rows("f32", 200, 64, 77)
@@ -124,6 +125,7 @@ def test_build_wide_rows_take_the_host_heuristic_path():
     # 2000-d fp32 rows: a CTA can stage only 25 rows, so layer-0 groups (33+ members) and the candidate lists fall back
     # to host distances for check_element_closer while the small upper-layer groups still use the GPU masks
     ix, o, st = build_both("vector_l2_ops", "f32", 400, 2000, m=16, efc=64)
+    assert st["n_host_dist"] > 0
     assert_same_graph(ix.export_graph(), o.export_graph(), o)
     ix.close()
 
