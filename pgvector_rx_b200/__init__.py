@@ -200,6 +200,20 @@ def export_pages(pages, elem):
                 heap_tid_counts=cnt)
 
 
+def heap_tid_stream(elem_ids, heap_tids, heap_tid_counts):
+    """amgettuple's fan-out of scan results to heap TIDs: every element emits its TIDs from the BACK of its list
+    (src/index/scan.rs:798 `heaptids.pop()`), elements without a TID are skipped (scan.rs:867).  elem_ids: element ids in
+    emission order (negative = padding); heap_tids / heap_tid_counts: the n x 10 / n arrays of export_graph() or
+    export_pages().  Returns the TIDs as the executor would receive them."""
+    out = []
+    for e in np.asarray(elem_ids).ravel():
+        if e < 0:
+            continue
+        c = int(heap_tid_counts[e])
+        out.extend(int(t) for t in heap_tids[e, :c][::-1])
+    return np.asarray(out, np.uint64)
+
+
 class HnswIndex:
     """Host-side handle mirroring `CREATE INDEX ... USING hnsw (col <opclass>) WITH (m, ef_construction)`.
 

@@ -147,3 +147,30 @@ def test_tiny_and_empty_indexes_and_errors():
             ix.scan_begin(np.ones((1, 4), np.float32), **kw)
         assert e.value.code == P.ERR_INVALID
     ix.close()
+
+
+def test_heap_tid_fanout_with_duplicates():
+    # duplicated rows share one element with up to 10 heap TIDs, emitted from the back of its list (scan.rs:798)
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((200, 8)).astype(np.float32)
+    rows = np.concatenate([base, base[:60], base[:60], np.tile(base[7], (15, 1))])
+    rows = rows[rng.permutation(len(rows))]
+    lv = np.zeros(len(rows), np.int32)
+    lv[::17] = 1
+    ix = P.HnswIndex("vector_l2_ops", 8, m=4, ef_construction=16, capacity=len(rows))
+    ix.build(rows, lv)                                   # heap TID of a row = its row number
+    g = ix.export_graph()
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 8, m=4, ef_construction=16, tie_mode=O.TIE_TOTAL_ORDER)
+    o.build(rows, lv)
+    q = base[[7, 3, 150]] + 0.01
+    for mode in (P.ITER_OFF, P.ITER_RELAXED, P.ITER_STRICT):
+        sc = ix.scan_begin(q, ef_search=10, iterative_scan=mode)
+        ids, _ = sc.stream(None)
+        sc.close()
+        for i in range(len(q)):
+            tids, eids, _, _ = o.scan_stream(q[i], ef_search=10, iterative=mode, max_scan_tuples=20000)
+            assert np.array_equal(ids[i], eids)
+            got = P.heap_tid_stream(ids[i], g["heap_tids"], g["heap_tid_counts"])
+            assert np.array_equal(got.astype(np.int64), tids)
+    assert g["heap_tid_counts"].max() == 10
+    ix.close()
