@@ -95,13 +95,19 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     c.L.stage_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
     c.L.R = (int)std::max<uint32_t>(1, std::min<uint32_t>(32, STAGE_BUDGET / c.L.stage_stride));
     c.vis_entries = vis_entries;
-    c.smem_block = search_warp_smem(c.L) * (SEARCH_THREADS / 32);
+    // scans run one warp (= one query in flight) per CTA: a CTA's slot is handed to the next batch as soon as that warp
+    // has finished its last query instead of waiting for three siblings (measured 6.86 / 6.71 / 6.58 M QPS for 1 / 2 / 4
+    // warps per CTA, profiles/r1_notes.md); PGVRX_SCAN_WARPS overrides
+    int wpb = for_build ? SEARCH_THREADS / 32 : 1;
+    if (!for_build) if (const char *e = getenv("PGVRX_SCAN_WARPS")) { int w = atoi(e); if (w >= 1 && w <= SEARCH_THREADS / 32) wpb = w; }
+    c.wpb = wpb;
+    c.smem_block = search_warp_smem(c.L) * wpb;
     if (c.smem_block > 227 * 1024) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search configuration exceeds shared memory");
     int occ = 0;
     if (for_build) CU_TRY(ix, build_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, &occ));
-    else CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, &occ));
+    else CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, wpb * 32, &occ));
     if (occ < 1) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search kernel does not fit on an SM");
-    int64_t want = (nq + SEARCH_THREADS / 32 - 1) / (SEARCH_THREADS / 32);
+    int64_t want = (nq + wpb - 1) / wpb;
     int64_t cap = (int64_t)ix->sm_count * occ;
     if (max_grid > 0) cap = std::min<int64_t>(cap, max_grid);
     c.grid = (int)std::max<int64_t>(1, std::min(want, cap));
@@ -131,7 +137,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     rc = pgvrx_make_config(ix, ef, 2048, vis_retry, nq, ix->sm_count, false, &retry_cfg);
     if (rc) return rc;
 
-    const int wpb = SEARCH_THREADS / 32;
+    const int wpb = main_cfg.wpb;
     // scratch set of this stream (see index_internal.h)
     pgvrx_index::ScanScratch *sc = nullptr;
     for (auto &cand : ix->scan_scratch) if (cand.used && cand.owner == stream) { sc = &cand; break; }
@@ -144,7 +150,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     sc->used = true;
     sc->owner = stream;
     CU_TRY(ix, sc->vis.ensure((size_t)main_cfg.grid * wpb * main_cfg.vis_entries * 4));
-    CU_TRY(ix, sc->vis_retry.ensure((size_t)retry_cfg.grid * wpb * retry_cfg.vis_entries * 4));
+    CU_TRY(ix, sc->vis_retry.ensure((size_t)retry_cfg.grid * retry_cfg.wpb * retry_cfg.vis_entries * 4));
     CU_TRY(ix, sc->status.ensure((size_t)nq * 4));
     CU_TRY(ix, sc->qmap.ensure((size_t)nq * 4));
     CU_TRY(ix, sc->work.ensure(64));
@@ -184,7 +190,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     p.stage_stride = main_cfg.L.stage_stride;
     p.R = main_cfg.L.R;
     p.spec = getenv("PGVRX_NO_SPEC_GATHER") ? 0 : 1;   // measured: 6.46 M QPS speculative vs 6.40 M probe-first (profiles/r1_notes.md)
-    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, stream));
+    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, main_cfg.wpb * 32, stream));
 
     // queries that overflowed their visited table or tie tail run again with 16x the scratch
     CU_TRY(ix, launch_collect_failed(p.out_status, (int)nq, (int32_t *)sc->qmap.p, work + 2, stream));
@@ -197,7 +203,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     r.work_counter = work + 1;
     r.stage_stride = retry_cfg.L.stage_stride;
     r.R = retry_cfg.L.R;
-    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, retry_cfg.L.list_j, g, r, retry_cfg.grid, retry_cfg.smem_block, stream));
+    CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, retry_cfg.L.list_j, g, r, retry_cfg.grid, retry_cfg.smem_block, retry_cfg.wpb * 32, stream));
 
     if (stats) {
         CU_TRY(ix, cudaEventRecord(ix->ev1, stream));

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     c.rs_cap = c.rs_n = 0;
     c.rs_ent = 3;
     c.spec = p.spec != 0;
-    const int slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
+    const int slot = blockIdx.x * (blockDim.x / 32) + warp;
     c.vis = p.vis_base + (size_t)slot * p.vis_entries;
 
     if (lane == 0) {
@@ -198,19 +198,19 @@ static scan_kernel_t pick_kernel(int elem, int metric, int list_j) {
     return nullptr;
 }
 
-cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm) {
+cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm) {
     scan_kernel_t k = pick_kernel(elem, metric, list_j);
     if (!k) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, SEARCH_THREADS, smem_block);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_block);
 }
 
 cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView &g, const SearchParams &p, int grid,
-                               size_t smem_block, cudaStream_t stream) {
+                               size_t smem_block, int threads, cudaStream_t stream) {
     scan_kernel_t k = pick_kernel(elem, metric, list_j);
     if (!k) return cudaErrorInvalidValue;
-    k<<<grid, SEARCH_THREADS, smem_block, stream>>>(g, p);
+    k<<<grid, threads, smem_block, stream>>>(g, p);
     return cudaGetLastError();
 }
 

@@ -112,6 +112,7 @@ struct ScanConfig {
     uint32_t vis_entries;
     size_t smem_block;
     int grid;
+    int wpb;                   // warps (= queries in flight) per CTA
 };
 // tail_cap < 0: pick the register-resident list when ef is small enough.  for_build selects the K2
 // kernel's occupancy instead of K1's.
