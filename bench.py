@@ -89,9 +89,30 @@ def load_or_build_graph(a):
             g.update(rows=rows, entry=meta["entry"], n=meta["n"], source="cache:" + tag,
                      build_vec_per_s_cpu=meta["n"] / meta["build_seconds"])
             return g
+    lv = D.hnsw_levels(a.n, a.m, 4)
+    g = None
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        # the GPU build produces exactly the oracle's graph (asserted at 1M rows whenever the cache exists); without a
+        # cache it is the quick way to get the reference-exact graph.  The CPU build rate is then unknown.
+        log("graph cache %s missing: building %d rows on the GPU" % (d, a.n))
+        import pgvector_rx_b200 as P
+        bx = P.HnswIndex("vector_l2_ops", a.dim, m=a.m, ef_construction=a.efc, capacity=a.n,
+                         device=int(os.environ.get("LOCAL_RANK", "0")))
+        t0 = time.time()
+        bx.build(rows, lv)
+        dt = time.time() - t0
+        g = bx.export_graph()
+        bx.close()
+        g = dict(rows=rows, level=g["level"], adj0=g["adj0"], upper_base=g["upper_base"], adj_up=g["adj_up"], entry=g["entry"],
+                 n=g["n"], source="gpu-build", build_vec_per_s_cpu=None)
+        return g
     log("graph cache %s missing: building %d rows with the CPU oracle (slow)" % (d, a.n))
     import oracle_ffi as O
-    lv = D.hnsw_levels(a.n, a.m, 4)
     o = O.Oracle(O.ELEM_F32, O.L2SQ, a.dim, m=a.m, ef_construction=a.efc, tie_mode=O.TIE_TOTAL_ORDER)
     t0 = time.time()
     o.build(rows, lv)
