@@ -356,8 +356,8 @@ def run_reference(a):
     out = dict(impl="reference", metric=METRIC, value=qps, unit="queries/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                data="synthetic", recall_at_10=rec,
-               config=dict(workload="C2: 1Mx128 fp32 vector_l2_ops m=16 ef_construction=64 ef_search=%d k=%d, %d-query batches"
-                                    % (a.ef, a.k, a.nq), n=a.n, dim=a.dim, queries_per_step_per_gpu=per_step,
+               config=dict(workload="C2: %sx%d fp32 vector_l2_ops m=%d ef_construction=%d ef_search=%d k=%d, %d-query batches"
+                                    % ("1M" if a.n == 1_000_000 else str(a.n), a.dim, a.m, a.efc, a.ef, a.k, a.nq), n=a.n, dim=a.dim, queries_per_step_per_gpu=per_step,
                            parallelism="host threads x%d" % cores, graph=g["source"],
                            note="CPU restatement of pgvector-rx's scan on flat arrays (the Rust/pgrx reference cannot be built here)"),
                build=dict(cpu_oracle_vectors_per_s=g.get("build_vec_per_s_cpu"),
@@ -514,8 +514,8 @@ def run_b200(a):
         out = dict(metric=METRIC, value=value, unit="queries/s", n_gpus=world, steps=a.steps, warmup=a.warmup,
                    ms_per_step=ms_max / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                    data="synthetic", recall_at_10=rec, recall_at_10_cpu=rec_cpu, ids_match_cpu_oracle=parity_ok,
-                   config=dict(workload="C2: 1Mx128 fp32 vector_l2_ops m=16 ef_construction=64 ef_search=%d k=%d, %d-query batches"
-                                        % (a.ef, a.k, a.nq), n=a.n, dim=a.dim, queries_per_step_per_gpu=a.nq,
+                   config=dict(workload="C2: %sx%d fp32 vector_l2_ops m=%d ef_construction=%d ef_search=%d k=%d, %d-query batches"
+                                        % ("1M" if a.n == 1_000_000 else str(a.n), a.dim, a.m, a.efc, a.ef, a.k, a.nq), n=a.n, dim=a.dim, queries_per_step_per_gpu=a.nq,
                                parallelism="query-sharded x%d, graph replicated" % world, batches_in_flight=2, graph=g["source"],
                                l2="working set (graph + vectors 0.64 GB, 6.7 GB gathered per step) exceeds L2; batches rotate"),
                    clocks=clk,
