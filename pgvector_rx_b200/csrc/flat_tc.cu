@@ -25,7 +25,7 @@ constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;        // q_hi, q_lo, x_hi, x_
 constexpr uint32_t TC_TMEM_COLS = 256;                   // two accumulators of TC_N fp32 columns
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC2_M = 256, TC2_N = 256;                  // 2-CTA tile: 128 query rows per CTA, 128 of the 256 x rows staged per CTA
-constexpr int TC2_STAGES = 2;
+constexpr int TC2_STAGES = 4;                            // ring slots of ONE operand half-tile (16 KiB) each
 constexpr int TC_A_RES_BYTES = 4 * 2 * TC_TILE_BYTES;    // resident query tile: up to 4 K blocks of (hi | lo)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -435,8 +435,8 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                 const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo, TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a_res = smem;                                                     // 4 K blocks x (q_hi | q_lo) of this CTA's 128 queries
-    uint8_t *ring = smem + TC_A_RES_BYTES;                                     // TC2_STAGES x (x_hi half | x_lo half)
-    float *sxn = reinterpret_cast<float *>(ring + TC2_STAGES * 2 * TC_TILE_BYTES);   // 2 x TC2_N row norms
+    uint8_t *ring = smem + TC_A_RES_BYTES;                                     // TC2_STAGES slots: x_hi half, x_lo half, x_hi half, ...
+    float *sxn = reinterpret_cast<float *>(ring + TC2_STAGES * TC_TILE_BYTES);       // 2 x TC2_N row norms
     uint64_t *lists = reinterpret_cast<uint64_t *>(sxn + 2 * TC2_N);
     uint64_t *bars = lists + (size_t)TC_M * TC_KP;
     uint64_t *full = bars, *empty = bars + TC2_STAGES, *tfull = empty + TC2_STAGES, *tempty = tfull + 2;
@@ -467,7 +467,7 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
     const int n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
     const int n_units = p.n_mtiles * p.n_splits;                               // n_mtiles counts 256-query tiles here
     const int n_kb = p.d_pad / TC_KB;
-    const uint32_t stage_bytes = 2u * TC_TILE_BYTES;
+    const uint32_t stage_bytes = TC_TILE_BYTES;                                // fine-grained slots keep the x stream ahead of the MMAs
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own queries, own half of every x tile; completions go to the leader =====
@@ -489,13 +489,14 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                 aph ^= 1u;
                 for (int nt = nt0; nt < nt1; nt++) {
                     for (int kb = 0; kb < n_kb; kb++) {
-                        mbar_wait(empty + stage, phase ^ 1u);
-                        uint8_t *st = ring + (size_t)stage * stage_bytes;
-                        if (leader) mbar_arrive_expect_tx(full + stage, 2u * stage_bytes);
-                        const uint32_t l_full = map_to_cta(smem_u32(full + stage), 0);
-                        tma_load_2d_2sm(st, &map_xhi, kb * TC_KB, nt * TC2_N + (int)rank * TC_M, l_full, pol_x);
-                        tma_load_2d_2sm(st + TC_TILE_BYTES, &map_xlo, kb * TC_KB, nt * TC2_N + (int)rank * TC_M, l_full, pol_x);
-                        if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+#pragma unroll
+                        for (int half = 0; half < 2; half++) {      // x_hi slot, then x_lo slot
+                            mbar_wait(empty + stage, phase ^ 1u);
+                            if (leader) mbar_arrive_expect_tx(full + stage, 2u * stage_bytes);   // this CTA's half and the peer's
+                            tma_load_2d_2sm(ring + (size_t)stage * stage_bytes, half == 0 ? &map_xhi : &map_xlo, kb * TC_KB,
+                                            nt * TC2_N + (int)rank * TC_M, map_to_cta(smem_u32(full + stage), 0), pol_x);
+                            if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                        }
                     }
                 }
             }
@@ -519,19 +520,25 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC2_N;
                     for (int kb = 0; kb < n_kb; kb++) {
-                        mbar_wait(full + stage, phase);
-                        tc_fence_after();
-                        const uint8_t *st = ring + (size_t)stage * stage_bytes;
                         const uint8_t *qa = a_res + (size_t)kb * 2 * TC_TILE_BYTES;
                         const uint64_t qhi = tc_smem_desc(qa), qlo = tc_smem_desc(qa + TC_TILE_BYTES);
-                        const uint64_t xhi = tc_smem_desc(st), xlo = tc_smem_desc(st + TC_TILE_BYTES);
+                        // x_hi slot: the cross term q_lo . x_hi, then the main product
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint64_t xhi = tc_smem_desc(ring + (size_t)stage * stage_bytes);
 #pragma unroll
                         for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32_2sm(d_tmem, qlo + 2 * k, xhi + 2 * k, idesc, (kb | k) != 0);
 #pragma unroll
-                        for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32_2sm(d_tmem, qhi + 2 * k, xlo + 2 * k, idesc, 1u);
-#pragma unroll
                         for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32_2sm(d_tmem, qhi + 2 * k, xhi + 2 * k, idesc, 1u);
-                        tc_commit_2sm(empty + stage);               // both CTAs' ring slots are free when these MMAs retire
+                        tc_commit_2sm(empty + stage);               // both CTAs' slots are free when these MMAs retire
+                        if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
+                        // x_lo slot: the cross term q_hi . x_lo
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint64_t xlo = tc_smem_desc(ring + (size_t)stage * stage_bytes);
+#pragma unroll
+                        for (int k = 0; k < TC_KB / 8; k++) tc_mma_tf32_2sm(d_tmem, qhi + 2 * k, xlo + 2 * k, idesc, 1u);
+                        tc_commit_2sm(empty + stage);
                         if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit_2sm(tfull + buf);                     // both CTAs' accumulators are complete
@@ -632,7 +639,7 @@ cudaError_t launch_flat_tc(const void *map_qhi, const void *map_qlo, const void 
 }
 
 size_t tc2_smem_bytes() {
-    return (size_t)TC_A_RES_BYTES + (size_t)TC2_STAGES * 2 * TC_TILE_BYTES + 2 * TC2_N * 4 + (size_t)TC_M * TC_KP * 8 + (2 * TC2_STAGES + 6) * 8 + 16;
+    return (size_t)TC_A_RES_BYTES + (size_t)TC2_STAGES * TC_TILE_BYTES + 2 * TC2_N * 4 + (size_t)TC_M * TC_KP * 8 + (2 * TC2_STAGES + 6) * 8 + 16;
 }
 
 cudaError_t launch_flat_tc2(const void *map_qhi, const void *map_qlo, const void *map_xhi, const void *map_xlo, const TcParams &p,
