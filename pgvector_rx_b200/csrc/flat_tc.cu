@@ -32,6 +32,22 @@ constexpr int TC_A_RES_BYTES = 4 * 2 * TC_TILE_BYTES;    // resident query tile:
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// wait with back-off: the single-thread producer / MMA-issuer roles share their SM sub-partitions with epilogue warps,
+// and a tight try_wait loop would take issue slots away from them
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, unsigned ns) {
+    const uint32_t a = smem_u32(bar);
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint64_t policy) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
@@ -480,7 +496,7 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                 const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
                 const int nt0 = sp * p.ntiles_per_split;
                 const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
-                mbar_wait(aempty, aph ^ 1u);
+                mbar_wait_backoff(aempty, aph ^ 1u, 200);
                 if (leader) mbar_arrive_expect_tx(afull, 2u * (uint32_t)n_kb * 2u * TC_TILE_BYTES);
                 for (int kb = 0; kb < n_kb; kb++) {
                     tma_load_2d_2sm(a_res + (size_t)kb * 2 * TC_TILE_BYTES, &map_qhi, kb * TC_KB, mt * TC2_M + (int)rank * TC_M, l_afull, pol_q);
@@ -491,7 +507,7 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                     for (int kb = 0; kb < n_kb; kb++) {
 #pragma unroll
                         for (int half = 0; half < 2; half++) {      // x_hi slot, then x_lo slot
-                            mbar_wait(empty + stage, phase ^ 1u);
+                            mbar_wait_backoff(empty + stage, phase ^ 1u, 100);
                             if (leader) mbar_arrive_expect_tx(full + stage, 2u * stage_bytes);   // this CTA's half and the peer's
                             tma_load_2d_2sm(ring + (size_t)stage * stage_bytes, half == 0 ? &map_xhi : &map_xlo, kb * TC_KB,
                                             nt * TC2_N + (int)rank * TC_M, map_to_cta(smem_u32(full + stage), 0), pol_x);
@@ -512,18 +528,18 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                 const int sp = u / p.n_mtiles;
                 const int nt0 = sp * p.ntiles_per_split;
                 const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
-                mbar_wait(afull, aph);
+                mbar_wait_backoff(afull, aph, 100);
                 tc_fence_after();
                 aph ^= 1u;
                 for (int nt = nt0; nt < nt1; nt++) {
-                    mbar_wait(tempty + buf, aphase ^ 1u);          // both CTAs' epilogues have drained this accumulator
+                    mbar_wait_backoff(tempty + buf, aphase ^ 1u, 50);          // both CTAs' epilogues have drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC2_N;
                     for (int kb = 0; kb < n_kb; kb++) {
                         const uint8_t *qa = a_res + (size_t)kb * 2 * TC_TILE_BYTES;
                         const uint64_t qhi = tc_smem_desc(qa), qlo = tc_smem_desc(qa + TC_TILE_BYTES);
                         // x_hi slot: the cross term q_lo . x_hi, then the main product
-                        mbar_wait(full + stage, phase);
+                        mbar_wait_backoff(full + stage, phase, 50);
                         tc_fence_after();
                         const uint64_t xhi = tc_smem_desc(ring + (size_t)stage * stage_bytes);
 #pragma unroll
@@ -533,7 +549,7 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                         tc_commit_2sm(empty + stage);               // both CTAs' slots are free when these MMAs retire
                         if (++stage == TC2_STAGES) { stage = 0; phase ^= 1u; }
                         // x_lo slot: the cross term q_hi . x_lo
-                        mbar_wait(full + stage, phase);
+                        mbar_wait_backoff(full + stage, phase, 50);
                         tc_fence_after();
                         const uint64_t xlo = tc_smem_desc(ring + (size_t)stage * stage_bytes);
 #pragma unroll
