@@ -257,29 +257,27 @@ __device__ __forceinline__ void search_layer_iter(WarpCtx &c, IterList &S, const
             const int32_t nb = j < lm ? __ldg(row + j) : -1;
             const bool valid = nb >= 0;
             if (!__ballot_sync(FULL, valid)) break;
-            bool fresh = false;
-            if (valid) {
-                const uint32_t bit = 1u << (nb & 31);
-                fresh = (atomicOr(bitmap + (nb >> 5), bit) & bit) == 0;      // scan.rs:366-369
-            }
-            const uint32_t fm = __ballot_sync(FULL, fresh);
-            const int nf = __popc(fm);
-            if (nf == 0) continue;
-            c.n_vis += nf;
-            c.n_dist += nf;
-            // fresh ids to the front, in neighbour order: lane r evaluates the r-th fresh neighbour
-            if (fresh) c.nbr[__popc(fm & ((1u << lane) - 1u))] = nb;
+            // visited test-and-set (scan.rs:366-369): issued now, consumed after the distances -- like the one-shot scan
+            // kernel, every listed row is fetched while the (DRAM-resident) bitmap word makes its round trip
+            const uint32_t bit = 1u << (nb & 31);
+            uint32_t old = 0;
+            if (valid) old = atomicOr(bitmap + (nb >> 5), bit);
+            const int cnt = __popc(__ballot_sync(FULL, valid));          // valid lanes are exactly 0 .. cnt-1
+            if (valid) c.nbr[lane] = nb;
             __syncwarp();
             float dd = 0.0f;
-            for (int s = 0; s < nf; s += c.R) {
-                const int nrow = min(c.R, nf - s);
+            for (int s = 0; s < cnt; s += c.R) {
+                const int nrow = min(c.R, cnt - s);
                 gather_rows(c, g, s, nrow);
                 if (lane >= s && lane < s + nrow)
                     dd = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
                 __syncwarp();
             }
-            const bool pass = lane < nf;
-            const int32_t my_id = pass ? c.nbr[lane] : -1;
+            const bool pass = valid && (old & bit) == 0;                 // fresh (level >= 0 always holds at layer 0)
+            const int nf = __popc(__ballot_sync(FULL, pass));
+            c.n_vis += nf;
+            c.n_dist += nf;
+            const int32_t my_id = nb;
             const uint32_t dord = f32_ord(dd);
             bool inserted = false;
             uint32_t am = __ballot_sync(FULL, pass && (c.len < c.ef || dord < c.f_ord));
