@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
     c.rs_cap = c.rs_n = 0;
     c.rs_ent = 3;
     c.spec = true;
-    const int slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
+    const int slot = blockIdx.x * (blockDim.x / 32) + warp;
     c.vis = p.vis_up + (size_t)slot * ITER_UP_ENTRIES;
     if (lane == 0) { mbar_init(c.mbar, 1); fence_mbar_init(); }
     __syncwarp();
@@ -469,14 +469,14 @@ cudaError_t iter_kernel_occupancy(int elem, int metric, size_t smem_block, int *
     if (!kfn) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kfn, SEARCH_THREADS, smem_block);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kfn, ITER_WARPS * 32, smem_block);
 }
 
 cudaError_t launch_iter_scan(int elem, int metric, const GraphView &g, const IterParams &p, int grid, size_t smem_block,
                              cudaStream_t stream) {
     iter_kernel_t kfn = pick_iter(elem, metric);
     if (!kfn) return cudaErrorInvalidValue;
-    kfn<<<grid, SEARCH_THREADS, smem_block, stream>>>(g, p);
+    kfn<<<grid, ITER_WARPS * 32, smem_block, stream>>>(g, p);
     return cudaGetLastError();
 }
 

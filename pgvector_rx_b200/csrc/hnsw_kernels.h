@@ -149,7 +149,9 @@ cudaError_t launch_rerank(int elem, int metric, const RerankParams &p, int grid,
 // ---- K3: iterative scan (hnsw_iter.cu) ------------------------------------------------------------------
 constexpr int ITER_CHUNK = 64;            // keys per chunk of a query's discarded chain
 constexpr int ITER_UP_ENTRIES = 4096;     // per-warp hashed visited table for the ef = 1 descent
-constexpr int ITER_TAIL_CAP = 1024;       // retained boundary ties behind W
+constexpr int ITER_TAIL_CAP = 1024;       // retained boundary ties behind W (bit types)
+constexpr int ITER_TAIL_CAP_FLOAT = 256;  // float types
+constexpr int ITER_WARPS = 1;             // warps (= queries in flight) per CTA: finest occupancy granularity
 
 struct IterQueryState {
     long long tuples;          // scan.rs:871

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -22,7 +23,7 @@ struct pgvrx_scan {
     int reserve_chunks = 0;
     int64_t active = 0;
     int rounds = 0;
-    int R = 0, grid = 0;
+    int R = 0, grid = 0, tail_cap = 0;
     uint32_t stage_stride = 0;
     size_t smem_block = 0;
     DevBuf q, bitmap, state, pool, next, pool_next, ids, dists, counts, done, want, status, ctr, vis_up, work;
@@ -81,13 +82,17 @@ int pgvrx_scan_begin(pgvrx_index *ix, const void *queries, int64_t nq, int32_t e
     // staging geometry: the same rule as the one-shot scan (capi.cu), result list always in shared memory
     s->stage_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
     s->R = (int)std::max<uint32_t>(1, std::min<uint32_t>(32, (17u * 1024u) / s->stage_stride));
-    s->smem_block = iter_warp_smem(s->R, s->stage_stride, ix->row_stride, ef_search, ITER_TAIL_CAP) * (SEARCH_THREADS / 32);
+    // slots for retained boundary ties: integer-valued distances (bit types) tie constantly, float distances only on
+    // duplicated rows -- fewer slots leave room for more resident warps
+    s->tail_cap = ix->desc.elem_type == PGVRX_ELEM_BIT ? ITER_TAIL_CAP : ITER_TAIL_CAP_FLOAT;
+    if (const char *e = getenv("PGVRX_ITER_TAIL")) { int v = atoi(e); if (v >= 16 && v <= 4096) s->tail_cap = v; }
+    s->smem_block = iter_warp_smem(s->R, s->stage_stride, ix->row_stride, ef_search, s->tail_cap) * ITER_WARPS;
     auto bail = [&](int rc) { scan_release(s); delete s; return rc; };
     if (s->smem_block > 227 * 1024) return bail(pgvrx_fail(ix, PGVRX_ERR_UNSUPPORTED, "scan configuration exceeds shared memory"));
     int occ = 0;
     cudaError_t e = iter_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, s->smem_block, &occ);
     if (e != cudaSuccess || occ < 1) { cudaGetLastError(); return bail(pgvrx_fail(ix, PGVRX_ERR_UNSUPPORTED, "iterative scan kernel does not fit on an SM")); }
-    const int wpb = SEARCH_THREADS / 32;
+    const int wpb = ITER_WARPS;
     s->grid = (int)std::max<int64_t>(1, std::min<int64_t>((nq + wpb - 1) / wpb, (int64_t)ix->sm_count * occ));
 
 #define SCAN_TRY(expr)                                                                              \
@@ -153,7 +158,7 @@ int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, f
     p.q_bytes = (uint32_t)ix->row_bytes;
     p.nq = (int)nq;
     p.ef = s->ef;
-    p.tail_cap = ITER_TAIL_CAP;
+    p.tail_cap = s->tail_cap;
     p.mode = s->mode;
     p.max_scan_tuples = s->max_tuples;
     p.want_more = want_more ? (const uint8_t *)s->want.p : nullptr;
@@ -193,7 +198,7 @@ int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, f
         if (st[(size_t)i] != 0) {
             char b[200];
             snprintf(b, sizeof b, "query %lld exhausted the iterative scan's scratch (status %u: %s)", (long long)i, st[(size_t)i],
-                     (st[(size_t)i] & 4u) ? "discarded pool" : (st[(size_t)i] & 2u) ? "more than 1024 boundary ties" : "visited table");
+                     (st[(size_t)i] & 4u) ? "discarded pool" : (st[(size_t)i] & 2u) ? "too many elements tie with the furthest result" : "visited table");
             return pgvrx_fail(ix, (st[(size_t)i] & 4u) ? PGVRX_ERR_NOMEM : PGVRX_ERR_UNSUPPORTED, b);
         }
     }
