@@ -600,7 +600,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         if (big_next) vis_entries = pgvrx_pow2_at_least(std::min<uint64_t>((uint64_t)vis_entries * 16, std::max<uint64_t>(1024, (uint64_t)cap * 2)));
         rc = pgvrx_make_config(ix, efc, big_next ? 2048 : -1, vis_entries, B, 0, true, &cfg);
         if (rc) return rc;
-        const int wpb = SEARCH_THREADS / 32;
+        const int wpb = cfg.wpb;
         CU_TRY(ix, rb.vis.ensure((size_t)cfg.grid * wpb * cfg.vis_entries * 4));
         CU_TRY(ix, rb.elem_ids.ensure((size_t)B * 4));
         // every per-round result lives in one device block mirrored by one pinned host block: a single D2H copy per round
@@ -646,7 +646,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         bp.R = cfg.L.R;
         const double tg0 = now_ms();
         CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
-        CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, ix->stream));
+        CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, cfg.wpb * 32, ix->stream));
         if (w_masks) {
             // check_element_closer for the candidate lists the searches just produced (graph/mod.rs:419 -> :315-339)
             CU_TRY(ix, cudaMemsetAsync((int *)rb.work.p + 4, 0, 4, ix->stream));

@@ -98,13 +98,14 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     // scans run one warp (= one query in flight) per CTA: a CTA's slot is handed to the next batch as soon as that warp
     // has finished its last query instead of waiting for three siblings (measured 6.86 / 6.71 / 6.58 M QPS for 1 / 2 / 4
     // warps per CTA, profiles/r1_notes.md); PGVRX_SCAN_WARPS overrides
-    int wpb = for_build ? SEARCH_THREADS / 32 : 1;
-    if (!for_build) if (const char *e = getenv("PGVRX_SCAN_WARPS")) { int w = atoi(e); if (w >= 1 && w <= SEARCH_THREADS / 32) wpb = w; }
+    // (the build's searches too: a round has only tens of them, one per SM beats four sharing an SM)
+    int wpb = 1;
+    if (const char *e = getenv(for_build ? "PGVRX_BUILD_WARPS" : "PGVRX_SCAN_WARPS")) { int w = atoi(e); if (w >= 1 && w <= SEARCH_THREADS / 32) wpb = w; }
     c.wpb = wpb;
     c.smem_block = search_warp_smem(c.L) * wpb;
     if (c.smem_block > 227 * 1024) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search configuration exceeds shared memory");
     int occ = 0;
-    if (for_build) CU_TRY(ix, build_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, &occ));
+    if (for_build) CU_TRY(ix, build_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, wpb * 32, &occ));
     else CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, wpb * 32, &occ));
     if (occ < 1) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search kernel does not fit on an SM");
     int64_t want = (nq + wpb - 1) / wpb;

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
     c.lane = lane;
     c.phase = 0;
     c.policy = l2_policy_evict_first();
-    const int slot = blockIdx.x * (SEARCH_THREADS / 32) + warp;
+    const int slot = blockIdx.x * (blockDim.x / 32) + warp;
     c.vis = p.vis_base + (size_t)slot * p.vis_entries;
     if (lane == 0) {
         mbar_init(c.mbar, 1);
@@ -315,19 +315,19 @@ static build_kernel_t pick_kernel(int elem, int metric, int list_j) {
     return nullptr;
 }
 
-cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm) {
+cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm) {
     build_kernel_t k = pick_kernel(elem, metric, list_j);
     if (!k) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, SEARCH_THREADS, smem_block);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_block);
 }
 
 cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
-                                size_t smem_block, cudaStream_t stream) {
+                                size_t smem_block, int threads, cudaStream_t stream) {
     build_kernel_t k = pick_kernel(elem, metric, list_j);
     if (!k) return cudaErrorInvalidValue;
-    k<<<grid, SEARCH_THREADS, smem_block, stream>>>(g, p);
+    k<<<grid, threads, smem_block, stream>>>(g, p);
     return cudaGetLastError();
 }
 

@@ -88,9 +88,9 @@ size_t search_warp_smem(const SearchLaunch &L);
 cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm);
 cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView &g, const SearchParams &p, int grid,
                                size_t smem_block, int threads, cudaStream_t stream);
-cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int *blocks_per_sm);
+cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm);
 cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
-                                size_t smem_block, cudaStream_t stream);
+                                size_t smem_block, int threads, cudaStream_t stream);
 cudaError_t launch_pairwise(int elem, int metric, const GraphView &g, const PairParams &p, int max_rows, int grid, cudaStream_t stream);
 cudaError_t launch_pending_pairs(int elem, int metric, const GraphView &g, const int32_t *ids, int n, float *out, int sm_count,
                                  cudaStream_t stream);
