@@ -98,8 +98,8 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     // scans run one warp (= one query in flight) per CTA: a CTA's slot is handed to the next batch as soon as that warp
     // has finished its last query instead of waiting for three siblings (measured 6.86 / 6.71 / 6.58 M QPS for 1 / 2 / 4
     // warps per CTA, profiles/r1_notes.md); PGVRX_SCAN_WARPS overrides
-    // (the build's searches too: a round has only tens of them, one per SM beats four sharing an SM)
-    int wpb = 1;
+    // (the build's latency-bound rounds measured the same with 1 or 4 warps per CTA: 12.4 s of kernels for 300k rows)
+    int wpb = for_build ? SEARCH_THREADS / 32 : 1;
     if (const char *e = getenv(for_build ? "PGVRX_BUILD_WARPS" : "PGVRX_SCAN_WARPS")) { int w = atoi(e); if (w >= 1 && w <= SEARCH_THREADS / 32) wpb = w; }
     c.wpb = wpb;
     c.smem_block = search_warp_smem(c.L) * wpb;
