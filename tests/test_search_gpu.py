@@ -114,3 +114,42 @@ def test_invalid_arguments():
     with pytest.raises(P.PgvrxError):
         gpu_index("vector_l2_ops", 4, bad, m=2, efc=4)
     ix.close(); ix2.close()
+
+
+def test_concurrent_streams_and_page_locked_buffers():
+    # the asynchronous entry point keeps one scratch set per caller stream (four sets; more streams recycle them) and
+    # accepts page-locked host buffers in place of device memory; every variant must give the blocking call's result
+    import torch
+    rows = make_rows("f32", 20000, 64, 91)
+    o = oracle_index("vector_l2_ops", 64, rows)
+    ix = gpu_index("vector_l2_ops", 64, o.export_graph())
+    nq, k = 1500, 10
+    qs = [make_rows("f32", nq, 64, 100 + i) for i in range(6)]
+    want = [ix.search(q, k=k, ef_search=40) for q in qs]
+    dev = torch.device("cuda", 0)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(6)]
+    d_q = [torch.from_numpy(q).to(dev) for q in qs]
+    outs = [(torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+             torch.empty((nq,), dtype=torch.int32, device=dev)) for _ in range(6)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(6):
+            ix.search_device(d_q[i].data_ptr(), nq, k, 40, outs[i][0].data_ptr(), outs[i][1].data_ptr(), outs[i][2].data_ptr(),
+                             stream=streams[i].cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(6):
+        assert np.array_equal(outs[i][0].cpu().numpy(), want[i][0]) and np.array_equal(outs[i][1].cpu().numpy(), want[i][1])
+        assert np.array_equal(outs[i][2].cpu().numpy(), want[i][2])
+    # page-locked host memory, asynchronous and blocking
+    pq = torch.from_numpy(qs[0]).pin_memory()
+    pi, pd, pc = (torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                  torch.empty((nq,), dtype=torch.int32).pin_memory())
+    ix.search_device(pq.data_ptr(), nq, k, 40, pi.data_ptr(), pd.data_ptr(), pc.data_ptr(), stream=streams[1].cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(pi.numpy(), want[0][0]) and np.array_equal(pd.numpy(), want[0][1]) and np.array_equal(pc.numpy(), want[0][2])
+    pi.zero_()
+    import ctypes as C
+    rc = ix.L.pgvrx_search_batch(ix.h, C.c_void_p(pq.data_ptr()), nq, 40, k, C.c_void_p(pi.data_ptr()), C.c_void_p(pd.data_ptr()),
+                                 C.c_void_p(pc.data_ptr()), None)
+    assert rc == 0 and np.array_equal(pi.numpy(), want[0][0])
+    ix.close()
