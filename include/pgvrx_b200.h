@@ -107,6 +107,8 @@ int pgvrx_device_count(void);
  * out (may alias in).  *norm receives the f64 norm; rows with norm 0 must not be indexed
  * (build.rs:433-435).  PGVRX_ERR_INVALID on halfvec overflow ("value out of range: overflow"). */
 int pgvrx_normalize(int32_t elem_type, int32_t dim, const void *in, void *out, double *norm);
+/* the same for n consecutive rows (norms may be NULL); a row with norm 0 comes out as a zero row */
+int pgvrx_normalize_rows(int32_t elem_type, int32_t dim, const void *in, void *out, int64_t n, double *norms);
 /* build.rs:373-377: floor(-ln(max(r, MIN_POSITIVE)) / ln m) capped at the page-size limit
  * (types/hnsw.rs:337-349).  r is the caller's uniform(0,1) draw. */
 int32_t pgvrx_level_from_uniform(double r, int32_t m);

@@ -41,7 +41,7 @@ EXPORTS = [
     "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export", "pgvrx_index_build",
     "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
-    "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores",
+    "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
         "pgvrx_last_error": (C.c_char_p, [vp]),
         "pgvrx_device_count": (C.c_int, []),
         "pgvrx_normalize": (C.c_int, [i32, i32, vp, vp, C.POINTER(C.c_double)]),
+        "pgvrx_normalize_rows": (C.c_int, [i32, i32, vp, vp, i64, vp]),
         "pgvrx_level_from_uniform": (i32, [C.c_double, i32]),
         "pgvrx_max_level": (i32, [i32]),
         "pgvrx_row_bytes": (C.c_size_t, [i32, i32]),
@@ -170,6 +171,17 @@ def normalize(elem, dim, row):
     if rc != OK:
         raise PgvrxError(rc, lib().pgvrx_last_error(None).decode())
     return norm.value, out[0]
+
+
+def normalize_rows(elem, dim, rows):
+    """FUNCTION 2 + normalise for many rows at once: (norms, unit rows); zero-norm rows come out as zero rows."""
+    a = _rows(elem, dim, rows)
+    out = np.zeros_like(a)
+    norms = np.zeros(len(a), np.float64)
+    rc = lib().pgvrx_normalize_rows(elem, dim, _p(a), _p(out), len(a), _p(norms))
+    if rc != OK:
+        raise PgvrxError(rc, lib().pgvrx_last_error(None).decode())
+    return norms, out
 
 
 def export_pages(pages, elem):
@@ -265,16 +277,11 @@ class HnswIndex:
         levels = np.ascontiguousarray(levels, np.int32)
         tids = None if heap_tids is None else np.ascontiguousarray(heap_tids, np.uint64)
         if self.normalized:
-            keep, out = [], []
-            for i, r in enumerate(rows):
-                norm, u = normalize(self.elem, self.dim, r)
-                if norm == 0.0:
-                    continue
-                keep.append(i)
-                out.append(u)
-            rows = np.stack(out) if out else rows[:0]
+            norms, unit = normalize_rows(self.elem, self.dim, rows)
+            keep = np.nonzero(norms != 0.0)[0]
+            rows = np.ascontiguousarray(unit[keep])
             levels = levels[keep]
-            tids = np.asarray(keep, np.uint64) if tids is None else tids[keep]
+            tids = keep.astype(np.uint64) if tids is None else tids[keep]
         st = BuildStats()
         self._check(self.L.pgvrx_index_build(self.h, _p(rows), len(rows), _p(levels), _p(tids), host_threads, C.byref(st)))
         return st.as_dict()
@@ -305,7 +312,7 @@ class HnswIndex:
         """Query-side half of the opclass: normalise when FUNCTION 2 exists (scan.rs:749-754)."""
         q = _rows(self.elem, self.dim, queries)
         if self.normalized:
-            q = np.stack([normalize(self.elem, self.dim, r)[1] for r in q])
+            q = normalize_rows(self.elem, self.dim, q)[1]
         return q
 
     def search(self, queries, k=10, ef_search=None, with_stats=False):
@@ -333,7 +340,7 @@ class HnswIndex:
         rows like the build does (zero-norm rows are kept as zero rows here so that ids stay row numbers)."""
         rows = _rows(self.elem, self.dim, rows)
         if self.normalized:
-            rows = np.stack([normalize(self.elem, self.dim, r)[1] for r in rows]) if len(rows) else rows
+            rows = normalize_rows(self.elem, self.dim, rows)[1]
         self._check(self.L.pgvrx_index_load_rows(self.h, _p(rows), len(rows)))
 
     def flat_topk(self, queries, k=10, with_stats=False):

@@ -325,6 +325,21 @@ int pgvrx_normalize(int32_t elem_type, int32_t dim, const void *in, void *out, d
     return PGVRX_OK;
 }
 
+// n rows at once (row i at in + i * row_bytes); norms (optional) receives every row's norm.  Rows with norm 0 come out as
+// zero rows: the caller drops them from a build (build.rs:433-435) -- queries are normalised the same way (scan.rs:749-754).
+int pgvrx_normalize_rows(int32_t elem_type, int32_t dim, const void *in, void *out, int64_t n, double *norms) {
+    if (n < 0 || (n > 0 && (!in || !out))) return fail(nullptr, PGVRX_ERR_INVALID, "bad normalize arguments");
+    const size_t rb = pgvrx_row_bytes(elem_type, dim);
+    if (rb == 0) return fail(nullptr, PGVRX_ERR_INVALID, "bad normalize arguments");
+    for (int64_t i = 0; i < n; i++) {
+        double nm = 0.0;
+        int rc = pgvrx_normalize(elem_type, dim, (const uint8_t *)in + (size_t)i * rb, (uint8_t *)out + (size_t)i * rb, &nm);
+        if (rc) return rc;
+        if (norms) norms[i] = nm;
+    }
+    return PGVRX_OK;
+}
+
 int pgvrx_index_create(const pgvrx_index_desc *d, pgvrx_index **out) {
     if (!d || !out) return fail(nullptr, PGVRX_ERR_INVALID, "null argument");
     *out = nullptr;

@@ -74,6 +74,12 @@ def test_normalize_bit_identical_to_oracle():
             n1, u1 = P.normalize(P.ELEM_F16, dim, r)
             n2, u2 = O.normalize(O.ELEM_F16, dim, r)
             assert n1 == n2 and np.array_equal(u1, u2)
+        # the batch entry point is the same arithmetic row by row
+        for elem, rows in ((P.ELEM_F32, x), (P.ELEM_F16, h)):
+            norms, unit = P.normalize_rows(elem, dim, rows)
+            for i, r in enumerate(rows):
+                n2, u2 = O.normalize(elem, dim, r)
+                assert norms[i] == n2 and np.array_equal(unit[i].view(np.uint8), u2.view(np.uint8))
     # the reference flushes normalised components below 2^-24 to zero instead of rounding up
     r = np.array([1.0, 2.0 ** -24 * 0.75], np.float32).astype(np.float16).view(np.uint16)
     r = np.array([np.float16(1.0).view(np.uint16), np.float16(4.5e-8).view(np.uint16)], np.uint16)
