@@ -560,7 +560,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     PinnedBuf h_mat;
     uint64_t n_pair_gpu = 0, n_val_dist = 0;
     std::atomic<uint64_t> n_val_dist_atomic{0};
-    double t_near = 0, t_sim = 0, t_g1 = 0, t_g2 = 0;
+    double t_sim = 0, t_g1 = 0, t_g2 = 0;
     for (int t = 0; t < 256; t++) g_identity_pos[t] = (int16_t)t;
     uint64_t why_overflow = 0, why_notfull = 0, why_pending = 0, why_order = 0;   // conflict reasons (PGVRX_BUILD_DEBUG)
     double t_phase_a = 0, t_groups = 0, t_commit = 0, t_scatter = 0;
