@@ -141,7 +141,7 @@ typedef struct {
     int64_t n_elements;
     int64_t n_upper_rows;     /* sum of element levels = rows of adj_up                          */
     int64_t n_heap_tids;
-    int64_t n_deleted;        /* elements flagged deleted (export refuses them for now)          */
+    int64_t n_deleted;        /* elements flagged deleted by a vacuum (exported with a zero row) */
     int64_t entry;            /* element id of HnswMetaPageData.entry_*, -1 when the index is empty */
     int32_t entry_level;
     int32_t dims, m, ef_construction;
@@ -152,6 +152,22 @@ int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, p
 int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, void *rows, uint8_t *level,
                        int32_t *adj0, int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids,
                        uint8_t *heap_tid_counts);
+
+/* ---- what a vacuum leaves on disk, as the scan sees it ------------------------------------------ */
+/* Per-element flags of an index that vacuum has touched (src/index/vacuum.rs:118-190,647-790):
+ *   PGVRX_ELEM_DELETED      HnswElementTupleData.deleted != 0 -- load_element rejects the element before its
+ *                           distance is computed (src/index/scan.rs:179): it is marked visited and nothing else;
+ *                           a deleted entry point makes the scan return no rows (scan.rs:475-486)
+ *   PGVRX_ELEM_NO_HEAPTIDS  no valid heap TID left -- searched like any element, but amgettuple skips it and it
+ *                           does not count towards hnsw.max_scan_tuples (scan.rs:866-871)
+ * A neighbour tuple whose version or count no longer matches its element (scan.rs:262) exports as empty lists.
+ * pgvrx_pages_element_flags fills flags[n_elements] from the pages; pgvrx_index_set_element_flags hands them to a
+ * loaded index (NULL clears; all-zero flags keep the flag-free kernels).  The in-memory build path has no such
+ * elements and refuses to extend an index that carries flags. */
+#define PGVRX_ELEM_DELETED 1
+#define PGVRX_ELEM_NO_HEAPTIDS 2
+int pgvrx_pages_element_flags(const void *pages, int64_t n_pages, uint8_t *flags);
+int pgvrx_index_set_element_flags(pgvrx_index *idx, const uint8_t *flags, int64_t n);
 
 /* ---- build: the ambuild insert loop (src/index/build.rs:400-535) ------------------------------- */
 typedef struct {

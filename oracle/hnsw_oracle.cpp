@@ -262,6 +262,10 @@ struct Element {
     int level;
     std::vector<std::vector<Cand>> neighbors; /* [layer] -> stored order */
     std::vector<int64_t> heap_tids;           /* build.rs:245, <= HNSW_HEAPTIDS */
+    /* state a vacuum leaves behind on disk (types/hnsw.rs:110-128,150-160); a fresh build has none of it */
+    uint8_t deleted = 0;                      /* HnswElementTupleData.deleted (vacuum.rs:749)              */
+    uint8_t version = 0;                      /* element tuple version (vacuum.rs:757)                     */
+    uint8_t stale_neighbors = 0;              /* neighbour tuple version != element version (scan.rs:262)  */
 };
 
 const int HNSW_HEAPTIDS = 10; /* hnsw_constants.rs:85 */
@@ -492,11 +496,15 @@ std::vector<ScanCand> search_layer_scan(orc_index &ix, Visited &local_vis, std::
         }
         const Element &ce = ix.elements[(size_t)c.idx];
         if (ce.level < layer) continue; /* load_neighbor_tids cannot address a layer above the level */
-        if (layer == 0) ctr.n_expand0++; else ctr.n_expand_upper++;
+        if (layer == 0) ctr.n_expand0++; else ctr.n_expand_upper++;   /* the neighbour tuple is read either way */
+        if (ce.stale_neighbors) continue;                        /* :262 version / count mismatch => :360 continue */
         const std::vector<Cand> &nb = ce.neighbors[(size_t)layer];  /* :349 -> :236-283 */
         for (const Cand &n : nb) {
             if (vis->contains(n.idx)) continue;                  /* :366 */
             vis->insert(n.idx); ctr.n_visited++;
+            /* :179 a deleted element fails load_element before its distance is computed, with or without the
+             * distance filter (:376-405): it stays in `visited` and goes nowhere else */
+            if (ix.elements[(size_t)n.idx].deleted) continue;
             bool always_add = w_len < ef;                        /* :371 */
             double f2 = results.empty() ? std::numeric_limits<double>::max() : results.peek().distance;
             double d = ix.dist64(query, ix.row(n.idx));          /* :375 -> :185-192 */
@@ -534,6 +542,7 @@ std::vector<ScanCand> get_scan_items(orc_index &ix, Visited &scratch, const void
                                      Visited *visited, DiscHeap *discarded, orc_counters &ctr) {
     if (ix.entry < 0) return {};                                 /* :470-472 */
     int32_t e = (int32_t)ix.entry;
+    if (ix.elements[(size_t)e].deleted) return {};               /* :475-486 load_element => None (:179) */
     ScanCand ep{ix.dist64(query, ix.row(e)), e};                 /* :475-486 */
     ctr.n_dist++;
     int ep_level = ix.elements[(size_t)e].level;
@@ -693,6 +702,33 @@ int orc_import_graph(orc_index *ix, const void *rows, int64_t n, const uint8_t *
     return 0;
 }
 
+/* Fixture states a vacuum leaves on disk.  The repair pass itself (vacuum.rs:288-640) is out of scope; these
+ * only produce what a scan can meet while or after one runs. */
+int orc_vacuum_mark(orc_index *ix, int64_t id, int what) {
+    if (id < 0 || id >= (int64_t)ix->elements.size()) return -1;
+    Element &e = ix->elements[(size_t)id];
+    auto bump = [](uint8_t v) -> uint8_t { return v >= 15 ? 1 : (uint8_t)(v + 1); };   /* vacuum.rs:797-803 */
+    if (what == ORC_VACUUM_REMOVE_HEAPTIDS) {          /* vacuum.rs:118-190: every heap TID of the element was dead */
+        e.heap_tids.clear();
+    } else if (what == ORC_VACUUM_MARK_DELETED) {      /* vacuum.rs:717-758 */
+        e.heap_tids.clear();
+        for (auto &l : e.neighbors) l.clear();         /* every neighbour TID set invalid */
+        e.deleted = 1;
+        std::memset(ix->values.data() + (size_t)id * ix->row_bytes, 0, ix->row_bytes);   /* value zeroed */
+        e.version = bump(e.version);                   /* both tuples get the new version */
+    } else if (what == ORC_VACUUM_STALE_NEIGHBORS) {   /* element rewritten, neighbour tuple not yet (scan.rs:262) */
+        e.stale_neighbors = 1;
+    } else return -1;
+    return 0;
+}
+
+void orc_element_flags(const orc_index *ix, uint8_t *flags) {
+    for (size_t i = 0; i < ix->elements.size(); i++) {
+        const Element &e = ix->elements[i];
+        flags[i] = (uint8_t)((e.deleted ? ORC_ELEM_DELETED : 0) | (e.heap_tids.empty() ? ORC_ELEM_NO_HEAPTIDS : 0));
+    }
+}
+
 int orc_search_layer(orc_index *ix, const void *query, const int32_t *ep_ids, const float *ep_dists,
                      int n_ep, int ef, int layer, int32_t *out_ids, float *out_dists) {
     std::vector<Cand> ep;
@@ -729,6 +765,7 @@ int orc_search_batch(orc_index *ix, const void *queries, int64_t nq, int ef_sear
             /* amgettuple pops from the back: nearest first (scan.rs:861) */
             int cnt = 0;
             for (size_t i = res.size(); i-- > 0 && cnt < k;) {
+                if (ix->elements[(size_t)res[i].idx].heap_tids.empty()) continue;   /* scan.rs:866-868 */
                 out_ids[(size_t)q * k + cnt] = res[i].idx;
                 out_dists[(size_t)q * k + cnt] = (float)res[i].distance;
                 cnt++;
@@ -928,7 +965,7 @@ extern "C" int64_t orc_write_pages(const orc_index *ix, uint8_t *pages, int64_t 
         size_t ntup_size = maxalign(NTUP_HDR + (size_t)(e.level + 2) * ix->m * TID);
         size_t combined = etup_size + ntup_size + ITEMID;
         etup.assign(etup_size, 0);
-        etup[0] = 1; etup[1] = (uint8_t)e.level; etup[2] = 0; etup[3] = 0;
+        etup[0] = 1; etup[1] = (uint8_t)e.level; etup[2] = e.deleted; etup[3] = e.version;
         for (int i = 0; i < HNSW_HEAPTIDS; i++) {
             if (i < (int)e.heap_tids.size())   /* heap tid = (block tid >> 16, offset tid & 0xffff) for the fixture */
                 put_tid(etup.data() + 4 + i * TID, (uint32_t)(e.heap_tids[(size_t)i] >> 16), (uint16_t)((e.heap_tids[(size_t)i] & 0xffff) + 1));
@@ -939,6 +976,7 @@ extern "C" int64_t orc_write_pages(const orc_index *ix, uint8_t *pages, int64_t 
         if (ix->elem_type == ORC_ELEM_BIT) put32(val + 4, (uint32_t)ix->dim);
         else { put16(val + 4, (uint16_t)ix->dim); put16(val + 6, 0); }
         std::memcpy(val + vhdr, ix->row((int64_t)idx), ix->row_bytes);
+        if (e.deleted) std::memset(val, 0, value_size);   /* vacuum.rs:750-754 zeroes the whole varlena, header included */
         size_t fs = w.free_space(cur);
         bool need_new = fs < etup_size || (combined <= max_size && fs < combined);      /* build.rs:636-638 */
         if (need_new) { size_t nb = w.new_page(); put32(w.page(cur) + BLCKSZ - OPAQUE, (uint32_t)nb); cur = nb; }
@@ -960,7 +998,8 @@ extern "C" int64_t orc_write_pages(const orc_index *ix, uint8_t *pages, int64_t 
     for (size_t idx = 0; idx < ix->elements.size(); idx++) {
         const Element &e = ix->elements[idx];
         uint8_t *nt = w.item_ptr(locs[idx].nblk, locs[idx].noff);
-        nt[0] = 2; nt[1] = 0;
+        nt[0] = 2;
+        nt[1] = e.stale_neighbors ? (uint8_t)(e.version + 1) : e.version;   /* hnsw.rs:150-160 version */
         size_t t = 0;
         for (int lc = e.level; lc >= 0; lc--) {
             int lm = layer_m(ix->m, lc);

@@ -94,6 +94,14 @@ int orc_import_graph(orc_index *, const void *rows, int64_t n, const uint8_t *le
                      const int32_t *adj0, const int32_t *upper_base, const int32_t *adj_up,
                      int64_t entry);
 
+/* ---- what a vacuum leaves on disk (scan-side semantics only: scan.rs:179,262,866-868) --------- */
+enum { ORC_VACUUM_REMOVE_HEAPTIDS = 1, /* vacuum.rs:118-190: element keeps its place in the graph, emits nothing */
+       ORC_VACUUM_MARK_DELETED = 2,    /* vacuum.rs:717-758: deleted = 1, lists and value cleared, version bumped */
+       ORC_VACUUM_STALE_NEIGHBORS = 3  /* neighbour tuple whose version no longer matches (scan.rs:262)            */ };
+enum { ORC_ELEM_DELETED = 1, ORC_ELEM_NO_HEAPTIDS = 2 };
+int  orc_vacuum_mark(orc_index *, int64_t id, int what);
+void orc_element_flags(const orc_index *, uint8_t *flags /* n */);
+
 /* ---- a1-a4 as free-standing calls on the index's graph (unit-test surface) -------------- */
 /* search_layer (graph/mod.rs:161-255). entry points are (ids, dists); returns count written,
  * ascending by distance. query is raw element data. */

@@ -42,7 +42,9 @@ EXPORTS = [
     "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
+    "pgvrx_pages_element_flags", "pgvrx_index_set_element_flags",
 ]
+ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
 
 
 class PgvrxError(RuntimeError):
@@ -118,6 +120,8 @@ def lib():
         "pgvrx_index_size": (i64, [vp]),
         "pgvrx_pages_inspect": (C.c_int, [vp, i64, i32, C.POINTER(PagesInfo)]),
         "pgvrx_pages_export": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "pgvrx_pages_element_flags": (C.c_int, [vp, i64, vp]),
+        "pgvrx_index_set_element_flags": (C.c_int, [vp, vp, i64]),
         "pgvrx_index_build": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
         "pgvrx_index_graph_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "pgvrx_index_export_graph": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -206,7 +210,11 @@ def export_pages(pages, elem):
                               _p(tids), _p(cnt))
     if rc != OK:
         raise PgvrxError(rc, L.pgvrx_last_error(None).decode())
-    return dict(rows=rows.view(_elem_dtype(elem)).reshape(n, rb // np.dtype(_elem_dtype(elem)).itemsize), level=level, adj0=adj0, upper_base=upper_base,
+    flags = np.zeros(n, np.uint8)
+    rc = L.pgvrx_pages_element_flags(_p(buf), n_pages, _p(flags))
+    if rc != OK:
+        raise PgvrxError(rc, L.pgvrx_last_error(None).decode())
+    return dict(flags=flags, n_deleted=info.n_deleted, rows=rows.view(_elem_dtype(elem)).reshape(n, rb // np.dtype(_elem_dtype(elem)).itemsize), level=level, adj0=adj0, upper_base=upper_base,
                 adj_up=adj_up[:info.n_upper_rows], entry=info.entry, n=n, m=m, dims=info.dims,
                 ef_construction=info.ef_construction, entry_level=info.entry_level, heap_tids=tids,
                 heap_tid_counts=cnt)
@@ -269,6 +277,14 @@ class HnswIndex:
         adj_up = np.ascontiguousarray(adj_up, np.int32).reshape(-1, self.m)
         self._check(self.L.pgvrx_index_load_graph(self.h, _p(rows), len(rows), _p(level), _p(adj0), _p(upper_base),
                                                   _p(adj_up) if len(adj_up) else None, len(adj_up), int(entry)))
+
+    def set_element_flags(self, flags):
+        """Per-element vacuum state (ELEM_DELETED / ELEM_NO_HEAPTIDS, scan.rs:179,866-868); None clears."""
+        if flags is None:
+            self._check(self.L.pgvrx_index_set_element_flags(self.h, None, 0))
+            return
+        flags = np.ascontiguousarray(flags, np.uint8)
+        self._check(self.L.pgvrx_index_set_element_flags(self.h, _p(flags), len(flags)))
 
     def build(self, rows, levels, heap_tids=None, host_threads=0):
         """CREATE INDEX: insert rows in order (ambuild, build.rs:400-535).  Rows of cosine opclasses are

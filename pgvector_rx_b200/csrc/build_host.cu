@@ -393,6 +393,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_rows < 0 || (n_rows > 0 && (!rows_in || !levels))) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null build input");
     if (ix->loaded && !ix->build) return pgvrx_fail(ix, PGVRX_ERR_STATE, "index was loaded from arrays; build needs a handle that is empty or was built here");
+    if (ix->has_flags) return pgvrx_fail(ix, PGVRX_ERR_STATE, "element flags are set (vacuumed index); the in-memory build does not extend it");
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     const int m = ix->desc.m, efc = ix->desc.ef_construction, l0 = 2 * m;
     if (!ix->build) {

@@ -39,6 +39,7 @@ GraphView pgvrx_view_of(const pgvrx_index *ix) {
     g.adj_up = (const int32_t *)ix->adj_up.p;
     g.upper_base = (const int32_t *)ix->upper_base.p;
     g.level = (const uint8_t *)ix->level.p;
+    g.flags = ix->has_flags ? (const uint8_t *)ix->flags.p : nullptr;
     g.n = (int32_t)ix->n;
     g.m = ix->desc.m;
     g.dim = ix->desc.dim;
@@ -84,9 +85,11 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     ScanConfig c;
     c.L.ef = ef;
     c.L.list_j = 0;
+    // an index that carries vacuum flags scans with the shared-memory list only (one extra kernel per opclass, not four)
+    const bool flagged = !for_build && ix->has_flags;
     if (tail_cap < 0) {
         tail_cap = 32;
-        for (int j = 2; j <= 8; j *= 2)
+        if (!flagged) for (int j = 2; j <= 8; j *= 2)
             if (32 * j - 1 - ef >= 16) { c.L.list_j = j; tail_cap = 32 * j - 1 - ef; break; }
     }
     c.L.tail_cap = tail_cap;
@@ -106,7 +109,7 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     if (c.smem_block > 227 * 1024) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search configuration exceeds shared memory");
     int occ = 0;
     if (for_build) CU_TRY(ix, build_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, wpb * 32, &occ));
-    else CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, wpb * 32, &occ));
+    else CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, flagged, c.smem_block, wpb * 32, &occ));
     if (occ < 1) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search kernel does not fit on an SM");
     int64_t want = (nq + wpb - 1) / wpb;
     int64_t cap = (int64_t)ix->sm_count * occ;
@@ -390,7 +393,7 @@ int pgvrx_index_create(const pgvrx_index_desc *d, pgvrx_index **out) {
 void pgvrx_index_destroy(pgvrx_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->desc.device);
-    DevBuf *bufs[] = {&ix->vectors, &ix->adj0, &ix->adj_up, &ix->upper_base, &ix->level, &ix->q, &ix->ids, &ix->dists,
+    DevBuf *bufs[] = {&ix->vectors, &ix->adj0, &ix->adj_up, &ix->upper_base, &ix->level, &ix->flags, &ix->q, &ix->ids, &ix->dists,
                       &ix->counts,
                       &ix->part_ids, &ix->part_dists, &ix->cand, &ix->tc_xhi, &ix->tc_xlo, &ix->tc_xnorm, &ix->tc_xmax,
                       &ix->tc_qhi, &ix->tc_qlo, &ix->tc_qnorm, &ix->tc_cand, &ix->tc_bound, &ix->tc_uncert, &ix->tc_cnt,
@@ -434,6 +437,7 @@ int pgvrx_index_load_graph(pgvrx_index *ix, const void *rows, int64_t n, const u
     ix->loaded = false;
     ix->rows_loaded = false;
     ix->tc_ready = false;
+    ix->has_flags = false;
     CU_TRY(ix, ix->vectors.ensure(std::max<size_t>(16, (size_t)n * ix->row_stride)));
     CU_TRY(ix, ix->adj0.ensure(std::max<size_t>(16, (size_t)n * 2 * m * 4)));
     CU_TRY(ix, ix->adj_up.ensure(std::max<size_t>(16, (size_t)n_upper_rows * m * 4)));
@@ -460,6 +464,27 @@ int pgvrx_index_load_graph(pgvrx_index *ix, const void *rows, int64_t n, const u
     ix->entry_level = n > 0 ? level[entry] : -1;
     ix->loaded = true;
     ix->rows_loaded = true;
+    return PGVRX_OK;
+}
+
+int pgvrx_index_set_element_flags(pgvrx_index *ix, const uint8_t *flags, int64_t n) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (!ix->loaded) return fail(ix, PGVRX_ERR_STATE, "no graph loaded");
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    // scans in flight on caller streams read the old flags: drain them before the table changes
+    CU_TRY(ix, cudaDeviceSynchronize());
+    if (!flags) { ix->has_flags = false; return PGVRX_OK; }
+    if (n != ix->n) return fail(ix, PGVRX_ERR_INVALID, "flags must cover every element of the index");
+    bool any = false;
+    for (int64_t i = 0; i < n; i++) {
+        if (flags[i] & ~(PGVRX_ELEM_DELETED | PGVRX_ELEM_NO_HEAPTIDS)) return fail(ix, PGVRX_ERR_INVALID, "unknown element flag");
+        any = any || flags[i] != 0;
+    }
+    ix->has_flags = false;
+    if (!any) return PGVRX_OK;                       // nothing flagged: keep the kernels on the flag-free path
+    CU_TRY(ix, ix->flags.ensure(std::max<size_t>(16, (size_t)n)));
+    CU_TRY(ix, cudaMemcpy(ix->flags.p, flags, (size_t)n, cudaMemcpyHostToDevice));
+    ix->has_flags = true;
     return PGVRX_OK;
 }
 

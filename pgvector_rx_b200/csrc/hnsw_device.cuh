@@ -501,7 +501,8 @@ __device__ __forceinline__ void gather_rows_masked(WarpCtx &c, const GraphView &
 
 // search_layer (graph/mod.rs:161-255 == scan.rs:302-448 without the iterative-scan bookkeeping).
 // Precondition: S[0, len) holds the entry points (unexpanded), their ids are in the visited set.
-template <int ELEM, int METRIC, class LIST>
+// FLAGGED: also honour GraphView::flags (an index a vacuum has touched); the default instantiation carries no trace of it.
+template <int ELEM, int METRIC, bool FLAGGED = false, class LIST>
 __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphView &g, int layer, uint32_t vis_mask,
                                              uint32_t vis_limit) {
     const int lane = c.lane;
@@ -554,6 +555,8 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             if (valid) bk = __ldcg(reinterpret_cast<const uint4 *>(c.vis + h));   // L2 (the table is written with atomics)
             int lvl = 255;
             if (layer > 0 && valid) lvl = __ldg(g.level + nb);
+            uint32_t eflags = 0;                                          // only a vacuumed index carries flags
+            if constexpr (FLAGGED) { if (g.flags != nullptr && valid) eflags = __ldg(g.flags + nb); }
             if (valid) c.nbr[lane] = nb;
             __syncwarp();
             // Two orders of the same steps.  Speculative (c.spec, the default; the build's log also needs every entry's
@@ -594,7 +597,8 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             vis_count += __popc(fm);
             c.n_vis += __popc(fm);
             if (vis_count > vis_limit) { c.status |= ST_VIS_OVERFLOW; return; }
-            const bool pass = fresh && lvl >= layer;                     // graph/mod.rs:214, scan.rs:410
+            // graph/mod.rs:214, scan.rs:410; a deleted element fails load_element before its distance (scan.rs:179)
+            const bool pass = fresh && lvl >= layer && !(eflags & ELEM_FLAG_DELETED);
             c.n_dist += __popc(__ballot_sync(FULL, pass));
             PH_TICK(c, 1);
             if (!c.spec) {

@@ -273,10 +273,12 @@ __device__ __forceinline__ void search_layer_iter(WarpCtx &c, IterList &S, const
                     dd = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
                 __syncwarp();
             }
-            const bool pass = valid && (old & bit) == 0;                 // fresh (level >= 0 always holds at layer 0)
-            const int nf = __popc(__ballot_sync(FULL, pass));
-            c.n_vis += nf;
-            c.n_dist += nf;
+            const bool fresh = valid && (old & bit) == 0;                // level >= 0 always holds at layer 0
+            // a deleted element fails load_element with and without the distance filter (scan.rs:179,376-405):
+            // visited, never evaluated, never remembered in `discarded`
+            const bool pass = fresh && !(g.flags != nullptr && (__ldg(g.flags + nb) & ELEM_FLAG_DELETED));
+            c.n_vis += __popc(__ballot_sync(FULL, fresh));
+            c.n_dist += __popc(__ballot_sync(FULL, pass));
             const int32_t my_id = nb;
             const uint32_t dord = f32_ord(dd);
             bool inserted = false;
@@ -359,7 +361,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
             uint32_t *bitmap = p.bitmap + (size_t)qi * p.n_words;
             int n_res = 0;
             if (st.round == 0) {
-                if (g.entry >= 0) {                                              // scan.rs:470-472
+                // scan.rs:470-472; a deleted entry point ends the scan the same way (scan.rs:475-486 -> :179)
+                if (g.entry >= 0 && !(g.flags != nullptr && (__ldg(g.flags + g.entry) & ELEM_FLAG_DELETED))) {
                     if (lane == 0) c.nbr[0] = g.entry;
                     __syncwarp();
                     gather_rows(c, g, 0, 1);
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
                         __syncwarp();
                         c.n_vis++;
                         up.reset1(c, ep_key);
-                        search_layer<ELEM, METRIC>(c, up, g, lc, ITER_UP_ENTRIES - 1, ITER_UP_ENTRIES / 4 * 3 - 32);
+                        search_layer<ELEM, METRIC, true>(c, up, g, lc, ITER_UP_ENTRIES - 1, ITER_UP_ENTRIES / 4 * 3 - 32);
                         ep_key = up.get(c, 0) & ~1ull;
                     }
                     if (c.status == 0) {                                         // scan.rs:515-528
@@ -407,21 +410,48 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
             }
             c.status |= d.status;
             // ---- emission (scan.rs:794-875): nearest first; strict_order drops what would go backwards ----
-            int skip = 0;
-            if (p.mode == 2) {
+            int n_counted = n_res;
+            if (g.flags == nullptr) {
+                int skip = 0;
+                if (p.mode == 2) {
+                    for (int b0 = 0; b0 < n_res; b0 += 32) {
+                        const int i = b0 + lane;
+                        skip += __popc(__ballot_sync(FULL, i < n_res && key_ord(S.S[i]) < st.prev_ord));
+                    }
+                }
+                emitted = n_res - skip;
+                for (int i = lane; i < emitted; i += 32) {
+                    const uint64_t key = S.S[skip + i];
+                    p.out_ids[(size_t)qi * p.ef + i] = (int32_t)key_id(key);
+                    p.out_dists[(size_t)qi * p.ef + i] = ord_f32(key_ord(key));
+                }
+                if (emitted > 0) st.prev_ord = key_ord(S.S[n_res - 1]);
+            } else {
+                // vacuumed index: an element without heap TIDs is skipped before it counts as a tuple and before the
+                // strict-order test (scan.rs:866-871 precede :801-806)
+                uint32_t last_ord = st.prev_ord;
                 for (int b0 = 0; b0 < n_res; b0 += 32) {
                     const int i = b0 + lane;
-                    skip += __popc(__ballot_sync(FULL, i < n_res && key_ord(S.S[i]) < st.prev_ord));
+                    uint64_t key = 0;
+                    bool has_tid = false;
+                    if (i < n_res) {
+                        key = S.S[i];
+                        has_tid = !(__ldg(g.flags + key_id(key)) & ELEM_FLAG_NO_HEAPTIDS);
+                    }
+                    n_counted -= __popc(__ballot_sync(FULL, i < n_res && !has_tid));
+                    const bool out = has_tid && !(p.mode == 2 && key_ord(key) < st.prev_ord);
+                    const uint32_t om = __ballot_sync(FULL, out);
+                    if (out) {
+                        const int pos = emitted + __popc(om & ((1u << lane) - 1u));
+                        p.out_ids[(size_t)qi * p.ef + pos] = (int32_t)key_id(key);
+                        p.out_dists[(size_t)qi * p.ef + pos] = ord_f32(key_ord(key));
+                    }
+                    if (om) last_ord = __shfl_sync(FULL, key_ord(key), 31 - __clz(om));   // ascending: the last one out is the largest
+                    emitted += __popc(om);
                 }
+                st.prev_ord = last_ord;
             }
-            emitted = n_res - skip;
-            for (int i = lane; i < emitted; i += 32) {
-                const uint64_t key = S.S[skip + i];
-                p.out_ids[(size_t)qi * p.ef + i] = (int32_t)key_id(key);
-                p.out_dists[(size_t)qi * p.ef + i] = ord_f32(key_ord(key));
-            }
-            if (emitted > 0) st.prev_ord = key_ord(S.S[n_res - 1]);
-            st.tuples += n_res;                                                  // scan.rs:871
+            st.tuples += n_counted;                                              // scan.rs:871
             st.round += 1;
             st.head = d.head; st.tail = d.tail; st.fill = d.fill; st.live = d.live;
             if (n_res == 0 || p.mode == 0 || d.live == 0) st.done = 1;            // nothing left to resume from

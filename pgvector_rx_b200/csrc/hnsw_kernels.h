@@ -13,10 +13,15 @@ struct GraphView {
     const int32_t *adj_up;      // upper rows x m
     const int32_t *upper_base;  // n: first upper row or -1
     const uint8_t *level;       // n
+    const uint8_t *flags;       // n or NULL: ELEM_FLAG_* of elements a vacuum touched (NULL for a freshly built index)
     int32_t n, m, dim;
     int32_t entry, entry_level;
     uint32_t row_stride;        // bytes, multiple of 16
 };
+
+// per-element state a vacuum leaves on disk (types/hnsw.rs:110-128)
+constexpr uint32_t ELEM_FLAG_DELETED = 1;      // HnswElementTupleData.deleted: visited, never evaluated or added (scan.rs:179)
+constexpr uint32_t ELEM_FLAG_NO_HEAPTIDS = 2;  // no valid heap TID: searched as usual, emits nothing (scan.rs:866-868)
 
 constexpr int SEARCH_THREADS = 128;   // 4 warps = 4 queries in flight per CTA
 
@@ -85,7 +90,7 @@ struct SearchLaunch {
 };
 
 size_t search_warp_smem(const SearchLaunch &L);
-cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm);
+cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, bool flagged, size_t smem_block, int threads, int *blocks_per_sm);
 cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView &g, const SearchParams &p, int grid,
                                size_t smem_block, int threads, cudaStream_t stream);
 cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm);

@@ -30,7 +30,8 @@ template <> struct ListOf<0> {
 };
 
 // LISTJ: 0 = result list in shared memory, else registers per lane (list capacity 32 * LISTJ)
-template <int ELEM, int METRIC, int LISTJ>
+// FLAGGED: the index carries per-element vacuum flags (GraphView::flags != NULL); only built for the shared-memory list
+template <int ELEM, int METRIC, int LISTJ, bool FLAGGED>
 __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
@@ -98,8 +99,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
         }
         __syncwarp();
 
-        int out_n = 0;
-        if (g.entry >= 0) {      // empty index => no rows (scan.rs:470-472)
+        int out_n = 0, w_n = 0;
+        // empty index => no rows (scan.rs:470-472); so does an entry point flagged deleted (scan.rs:475-486 -> :179)
+        bool entry_ok = g.entry >= 0;
+        if constexpr (FLAGGED) entry_ok = entry_ok && !(__ldg(g.flags + g.entry) & ELEM_FLAG_DELETED);
+        if (entry_ok) {
             // ---- distance to the entry point (scan.rs:475-486) ----
             if (lane == 0) c.nbr[0] = g.entry;
             __syncwarp();
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
                 __syncwarp();
                 c.n_vis++;
                 S.reset1(c, ep_key);
-                search_layer<ELEM, METRIC>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
+                search_layer<ELEM, METRIC, FLAGGED>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
                 ep_key = S.get(c, 0) & ~1ull;     // nearest of W becomes the next entry point (scan.rs:510)
             }
             // ---- layer 0 with ef_search (scan.rs:515-528) ----
@@ -130,14 +134,30 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
                 c.n_vis++;
                 c.ef = p.ef;
                 S.reset1(c, ep_key);
-                search_layer<ELEM, METRIC>(c, S, g, 0, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
+                search_layer<ELEM, METRIC, FLAGGED>(c, S, g, 0, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
             }
-            out_n = min(min(c.len, c.ef), p.k);   // W = S[0, ef); nearest first (scan.rs:861)
+            w_n = min(c.len, c.ef);               // W = S[0, ef); nearest first (scan.rs:861)
+            out_n = min(w_n, p.k);
         }
 
         // ---- results ----
         if (c.status == 0) {
-            S.store(c, p.out_ids + (size_t)qi * p.k, p.out_dists + (size_t)qi * p.k, out_n);
+            if constexpr (!FLAGGED) {
+                S.store(c, p.out_ids + (size_t)qi * p.k, p.out_dists + (size_t)qi * p.k, out_n);
+            } else {
+                // amgettuple skips elements without heap TIDs (scan.rs:866-868): the first k of W that have one
+                int cnt = 0;
+                for (int i = 0; i < w_n && cnt < p.k; i++) {
+                    const uint64_t key = S.get(c, i);
+                    if (__ldg(g.flags + key_id(key)) & ELEM_FLAG_NO_HEAPTIDS) continue;
+                    if (lane == 0) {
+                        p.out_ids[(size_t)qi * p.k + cnt] = (int32_t)key_id(key);
+                        p.out_dists[(size_t)qi * p.k + cnt] = ord_f32(key_ord(key));
+                    }
+                    cnt++;
+                }
+                out_n = cnt;
+            }
             for (int i = out_n + lane; i < p.k; i += 32) {
                 p.out_ids[(size_t)qi * p.k + i] = -1;
                 p.out_dists[(size_t)qi * p.k + i] = __int_as_float(0x7f800000);
@@ -172,34 +192,35 @@ __global__ void collect_failed_kernel(const uint32_t *status, int nq, int32_t *q
 typedef void (*scan_kernel_t)(GraphView, SearchParams);
 
 template <int ELEM, int METRIC>
-static scan_kernel_t pick_list(int list_j) {
+static scan_kernel_t pick_list(int list_j, bool flagged) {
+    if (flagged) return list_j == 0 ? hnsw_scan_kernel<ELEM, METRIC, 0, true> : nullptr;
     switch (list_j) {
-        case 2: return hnsw_scan_kernel<ELEM, METRIC, 2>;
-        case 4: return hnsw_scan_kernel<ELEM, METRIC, 4>;
-        case 8: return hnsw_scan_kernel<ELEM, METRIC, 8>;
-        case 0: return hnsw_scan_kernel<ELEM, METRIC, 0>;
+        case 2: return hnsw_scan_kernel<ELEM, METRIC, 2, false>;
+        case 4: return hnsw_scan_kernel<ELEM, METRIC, 4, false>;
+        case 8: return hnsw_scan_kernel<ELEM, METRIC, 8, false>;
+        case 0: return hnsw_scan_kernel<ELEM, METRIC, 0, false>;
     }
     return nullptr;
 }
 
-static scan_kernel_t pick_kernel(int elem, int metric, int list_j) {
+static scan_kernel_t pick_kernel(int elem, int metric, int list_j, bool flagged) {
     if (elem == ELEM_F32) {
-        if (metric == METRIC_L2SQ) return pick_list<ELEM_F32, METRIC_L2SQ>(list_j);
-        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F32, METRIC_NEG_IP>(list_j);
-        if (metric == METRIC_L1) return pick_list<ELEM_F32, METRIC_L1>(list_j);
+        if (metric == METRIC_L2SQ) return pick_list<ELEM_F32, METRIC_L2SQ>(list_j, flagged);
+        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F32, METRIC_NEG_IP>(list_j, flagged);
+        if (metric == METRIC_L1) return pick_list<ELEM_F32, METRIC_L1>(list_j, flagged);
     } else if (elem == ELEM_F16) {
-        if (metric == METRIC_L2SQ) return pick_list<ELEM_F16, METRIC_L2SQ>(list_j);
-        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F16, METRIC_NEG_IP>(list_j);
-        if (metric == METRIC_L1) return pick_list<ELEM_F16, METRIC_L1>(list_j);
+        if (metric == METRIC_L2SQ) return pick_list<ELEM_F16, METRIC_L2SQ>(list_j, flagged);
+        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F16, METRIC_NEG_IP>(list_j, flagged);
+        if (metric == METRIC_L1) return pick_list<ELEM_F16, METRIC_L1>(list_j, flagged);
     } else if (elem == ELEM_BIT) {
-        if (metric == METRIC_HAMMING) return pick_list<ELEM_BIT, METRIC_HAMMING>(list_j);
-        if (metric == METRIC_JACCARD) return pick_list<ELEM_BIT, METRIC_JACCARD>(list_j);
+        if (metric == METRIC_HAMMING) return pick_list<ELEM_BIT, METRIC_HAMMING>(list_j, flagged);
+        if (metric == METRIC_JACCARD) return pick_list<ELEM_BIT, METRIC_JACCARD>(list_j, flagged);
     }
     return nullptr;
 }
 
-cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm) {
-    scan_kernel_t k = pick_kernel(elem, metric, list_j);
+cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, bool flagged, size_t smem_block, int threads, int *blocks_per_sm) {
+    scan_kernel_t k = pick_kernel(elem, metric, list_j, flagged);
     if (!k) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
     if (e != cudaSuccess) return e;
@@ -208,7 +229,7 @@ cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, size_t smem_
 
 cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView &g, const SearchParams &p, int grid,
                                size_t smem_block, int threads, cudaStream_t stream) {
-    scan_kernel_t k = pick_kernel(elem, metric, list_j);
+    scan_kernel_t k = pick_kernel(elem, metric, list_j, g.flags != nullptr);
     if (!k) return cudaErrorInvalidValue;
     k<<<grid, threads, smem_block, stream>>>(g, p);
     return cudaGetLastError();

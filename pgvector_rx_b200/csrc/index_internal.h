@@ -60,6 +60,8 @@ struct pgvrx_index {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // graph in HBM
     DevBuf vectors, adj0, adj_up, upper_base, level;
+    DevBuf flags;               // per-element vacuum state (pgvrx_index_set_element_flags); used only when has_flags
+    bool has_flags = false;
     int64_t n = 0, n_upper = 0, entry = -1;
     int entry_level = -1;
     bool loaded = false;        // graph + rows resident

@@ -121,6 +121,7 @@ int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, p
             if (!rd_tid(it.ptr + 4 + t * TID).valid()) break;
             info->n_heap_tids++;
         }
+        if (it.ptr[2] != 0) continue;       // deleted: vacuum zeroed the value, varlena header included (vacuum.rs:750-754)
         uint32_t vl = rd32(it.ptr + ETUP_HDR);
         if ((vl & 3u) != 0) return err("pgvector-rx: element value is not a plain 4-byte-header varlena");
         size_t vsize = vl >> 2;
@@ -134,10 +135,6 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
     pgvrx_pages_info info;
     int rc = pgvrx_pages_inspect(pages, n_pages, elem_type, &info);
     if (rc) return rc;
-    if (info.n_deleted > 0) {
-        pgvrx_host::set_create_error("pgvector-rx: index holds deleted elements (vacuum in progress); not supported by the exporter yet");
-        return PGVRX_ERR_UNSUPPORTED;
-    }
     if (info.n_elements > 0 && (!rows || !level || !adj0 || !upper_base || (info.n_upper_rows > 0 && !adj_up)))
         return err("pgvector-rx: null output array");
     Pages pg{(const uint8_t *)pages, n_pages};
@@ -153,7 +150,9 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
         const int lv = it.ptr[1];
         const uint8_t version = it.ptr[3];
         level[i] = (uint8_t)lv;
-        memcpy((uint8_t *)rows + i * row_bytes, it.ptr + ETUP_HDR + 8, row_bytes);
+        // a deleted element keeps its id (neighbour TIDs may still point at it) but has no value; its distance is never used
+        if (it.ptr[2] != 0) memset((uint8_t *)rows + i * row_bytes, 0, row_bytes);
+        else memcpy((uint8_t *)rows + i * row_bytes, it.ptr + ETUP_HDR + 8, row_bytes);
         int nh = 0;
         for (int t = 0; t < PGVRX_HEAPTIDS; t++) {                    // scan.rs:203-209: stop at the first invalid
             Tid h = rd_tid(it.ptr + 4 + t * TID);
@@ -189,6 +188,23 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
             }
         }
         up += lv;
+    }
+    return PGVRX_OK;
+}
+
+int pgvrx_pages_element_flags(const void *pages, int64_t n_pages, uint8_t *flags) {
+    if (!pages || !flags || n_pages < 2) return err("pgvector-rx: need the meta page and the head page");
+    Pages pg{(const uint8_t *)pages, n_pages};
+    Walk w;
+    int64_t nd;
+    int rc = walk_elements(pg, w, &nd);
+    if (rc) return rc;
+    for (size_t i = 0; i < w.blk.size(); i++) {
+        Item it = pg.item(w.blk[i], w.off[i]);
+        uint8_t f = 0;
+        if (it.ptr[2] != 0) f |= PGVRX_ELEM_DELETED;                              // scan.rs:179
+        if (!rd_tid(it.ptr + 4).valid()) f |= PGVRX_ELEM_NO_HEAPTIDS;             // scan.rs:203-209,866-868
+        flags[i] = f;
     }
     return PGVRX_OK;
 }

@@ -41,6 +41,26 @@ def oracle_index(opclass, dim, rows, m=16, efc=64, level_seed=4, tie=O.TIE_TOTAL
     return o
 
 
+def vacuumed_oracle(opclass, kind, n, dim, m, efc, seed=9, frac=0.05, delete_entry=False):
+    """An oracle index in the states a vacuum leaves behind: ~frac of the elements marked deleted
+    (vacuum.rs:717-758), ~frac with every heap TID removed but still in the graph (vacuum.rs:118-190) and a
+    few stale neighbour tuples (scan.rs:262).  Graph repair (vacuum.rs:288-640) is deliberately not run, so
+    live lists still point at deleted elements -- the case scan.rs:179 exists for."""
+    o = oracle_index(opclass, dim, make_rows(kind, n, dim, seed), m=m, efc=efc)
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(o.n)
+    k = max(1, int(o.n * frac))
+    deleted, no_tid, stale = perm[:k], perm[k:2 * k], perm[2 * k:2 * k + max(1, k // 3)]
+    if not delete_entry:
+        deleted = deleted[deleted != o.entry]
+    elif o.entry not in deleted:
+        deleted = np.append(deleted, o.entry)
+    o.vacuum_mark(deleted, O.VACUUM_MARK_DELETED)
+    o.vacuum_mark(no_tid, O.VACUUM_REMOVE_HEAPTIDS)
+    o.vacuum_mark(stale, O.VACUUM_STALE_NEIGHBORS)
+    return o, deleted, no_tid, stale
+
+
 def gpu_index(opclass, dim, graph, m=16, efc=64):
     ix = P.HnswIndex(opclass, dim, m=m, ef_construction=efc, capacity=max(int(graph["n"]), 1))
     ix.load_graph(graph["rows"], graph["level"], graph["adj0"], graph["upper_base"], graph["adj_up"], graph["entry"])

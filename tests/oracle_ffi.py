@@ -17,6 +17,8 @@ ELEM_F32, ELEM_F16, ELEM_BIT = 0, 1, 2
 L2SQ, NEG_IP, L1, HAMMING, JACCARD = 0, 1, 2, 3, 4
 TIE_RUST_HEAP, TIE_TOTAL_ORDER = 0, 1
 ITER_OFF, ITER_RELAXED, ITER_STRICT = 0, 1, 2
+VACUUM_REMOVE_HEAPTIDS, VACUUM_MARK_DELETED, VACUUM_STALE_NEIGHBORS = 1, 2, 3
+ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
 
 
 class Counters(C.Structure):
@@ -72,6 +74,8 @@ def lib():
         "orc_scan_stream": (i64, [vp, vp, i32, i32, i64, i64, vp, vp, vp, vp]),
         "orc_flat_topk": (i32, [i32, i32, i32, vp, i64, vp, i64, i32, vp, vp, i32]),
         "orc_write_pages": (i64, [vp, vp, i64]),
+        "orc_vacuum_mark": (i32, [vp, i64, i32]),
+        "orc_element_flags": (None, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -198,6 +202,16 @@ class Oracle:
                                 _p(np.ascontiguousarray(g["adj0"], np.int32)),
                                 _p(np.ascontiguousarray(g["upper_base"], np.int32)), _p(adj_up),
                                 int(g["entry"]))
+
+    def vacuum_mark(self, ids, what):
+        """Put elements into a state a vacuum leaves on disk (VACUUM_* constants)."""
+        for i in np.atleast_1d(ids):
+            assert self.L.orc_vacuum_mark(self.h, int(i), what) == 0
+
+    def element_flags(self):
+        f = np.zeros(self.n, np.uint8)
+        self.L.orc_element_flags(self.h, _p(f))
+        return f
 
     def write_pages(self):
         """The index relation as the reference's flush phase lays it out (8 KiB pages)."""

@@ -8,7 +8,7 @@ import pytest
 
 import oracle_ffi as O
 import pgvector_rx_b200 as P
-from helpers import make_rows, oracle_index
+from helpers import make_rows, oracle_index, vacuumed_oracle
 from pgvector_rx_b200 import datasets as D
 
 
@@ -84,3 +84,36 @@ def test_export_rejects_corrupt_relations():
     page1[off + 1] = 7
     g1 = P.export_pages(stale, P.ELEM_F32)
     assert (g1["adj0"][0] == -1).all() and np.array_equal(g1["adj0"][1:], g0["adj0"][1:])
+
+
+def test_export_vacuumed_index():
+    o, deleted, no_tid, stale = vacuumed_oracle("vector_l2_ops", "f32", 600, 12, 6, 24)
+    want = o.export_graph()
+    g = P.export_pages(o.write_pages(), P.ELEM_F32)
+    assert g["n"] == want["n"] and g["n_deleted"] == len(deleted) and g["entry"] == want["entry"]
+    flags = o.element_flags()
+    assert np.array_equal(g["flags"], flags)
+    assert (flags[deleted] == (P.ELEM_DELETED | P.ELEM_NO_HEAPTIDS)).all() and (flags[no_tid] == P.ELEM_NO_HEAPTIDS).all()
+    assert (g["rows"][deleted] == 0).all() and (g["adj0"][deleted] == -1).all() and (g["heap_tid_counts"][deleted] == 0).all()
+    # stale neighbour tuples read as empty lists; every other element is exported unchanged
+    assert (g["adj0"][stale] == -1).all()
+    live = np.setdiff1d(np.arange(o.n), np.concatenate([deleted, stale]))
+    assert np.array_equal(g["adj0"][live], want["adj0"][live]) and np.array_equal(g["rows"][live], want["rows"][live])
+    assert np.array_equal(g["level"], want["level"])
+
+
+def test_oracle_scan_semantics_on_vacuumed_index():
+    # scan.rs:179: deleted elements are visited but never returned; scan.rs:866-868: elements without heap TIDs
+    # are searched through but emit nothing; a deleted entry point returns no rows (scan.rs:475-486)
+    o, deleted, no_tid, stale = vacuumed_oracle("vector_l2_ops", "f32", 600, 12, 6, 24)
+    q = make_rows("f32", 40, 12, 3)
+    ids, dists, counts = o.search_batch(q, ef_search=40, k=10)
+    got = set(ids[ids >= 0].tolist())
+    assert not (got & set(deleted.tolist())) and not (got & set(no_tid.tolist()))
+    assert (counts > 0).all()
+    for mode in (O.ITER_RELAXED, O.ITER_STRICT):
+        tids, eids, ds, _ = o.scan_stream(q[0], ef_search=10, iterative=mode)
+        assert not (set(eids.tolist()) & (set(deleted.tolist()) | set(no_tid.tolist())))
+    o2, *_ = vacuumed_oracle("vector_l2_ops", "f32", 600, 12, 6, 24, delete_entry=True)
+    ids, dists, counts = o2.search_batch(q, ef_search=40, k=10)
+    assert (counts == 0).all() and (ids == -1).all()
