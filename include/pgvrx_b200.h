@@ -201,6 +201,20 @@ typedef struct {
  * May be called again to append more rows.  The graph is resident and searchable afterwards. */
 int pgvrx_index_build(pgvrx_index *idx, const void *rows, int64_t n_rows, const int32_t *levels,
                       const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats);
+/* ---- inserts into a live index: aminsert (src/index/insert.rs:1227-1480) ------------------------- */
+/* Same inputs and statistics as pgvrx_index_build, different rules -- the ones the reference applies to an index
+ * that already exists on disk: the new element's lists are the nearest lm candidates of each layer's search, without
+ * the heuristic (find_element_neighbors_on_disk, insert.rs:1021-1123); a neighbour with a free slot gets the
+ * back-link appended, a full list has ONE slot overwritten, chosen by get_update_index (insert.rs:500-738: closer-test
+ * heuristic in which the new element is never pruned and never prunes; the first slot whose element was not kept);
+ * duplicates merge into an existing element with 1..9 heap TIDs (insert.rs:1136-1213); the entry point moves on a
+ * strictly greater level.  Works on a handle built here or loaded with pgvrx_index_load_graph (the host mirror is
+ * then rebuilt from the device arrays; loaded elements count as holding one heap TID = their id).  Page placement and
+ * the reuse of deleted slots (insert.rs:104-470) stay with the storage engine: new elements get the next id.  Not
+ * supported on an index that carries vacuum flags. */
+int pgvrx_index_insert(pgvrx_index *idx, const void *rows, int64_t n_rows, const int32_t *levels,
+                       const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats);
+
 int pgvrx_index_graph_info(const pgvrx_index *idx, int64_t *n, int64_t *n_upper_rows, int64_t *entry,
                            int32_t *entry_level);
 /* copies the built graph out (any pointer may be NULL); shapes as in pgvrx_index_load_graph,

@@ -556,6 +556,136 @@ std::vector<ScanCand> get_scan_items(orc_index &ix, Visited &scratch, const void
     return search_layer_scan(ix, scratch, ep_list, ef_search, 0, query, visited, discarded, true, ctr); /* :515 */
 }
 
+/* ======================================================================================
+ * aminsert on the flat arrays (src/index/insert.rs): the insert path of a LIVE index.  It differs from the
+ * in-memory build (a2-a5) in three ways: the new element's lists are the nearest lm of W, no heuristic
+ * (insert.rs:1096-1117); a full neighbour list is updated by REPLACING ONE SLOT, chosen by a heuristic in
+ * which the new element is never pruned and never prunes (insert.rs:500-738); distances are recomputed
+ * from the vectors in f64 (no cached edge distances on disk).  Page placement / slot reuse
+ * (insert.rs:104-470) is storage-engine work and not restated: a new element always gets the next id.
+ * ==================================================================================== */
+/* find_element_neighbors_on_disk (insert.rs:1021-1123), skip_set = None */
+std::vector<std::vector<ScanCand>> find_element_neighbors_on_disk(orc_index &ix, Visited &scratch, const void *query,
+                                                                  int new_level, orc_counters &ctr) {
+    std::vector<std::vector<ScanCand>> nbl((size_t)new_level + 1);
+    int32_t e = (int32_t)ix.entry;
+    if (ix.elements[(size_t)e].deleted) return nbl;              /* :1036-1047 load_element => None */
+    int entry_level = ix.elements[(size_t)e].level;
+    std::vector<ScanCand> ep_list{ScanCand{ix.dist64(query, ix.row(e)), e}};
+    ctr.n_dist++;
+    for (int lc = entry_level; lc >= new_level + 1; lc--) {      /* :1052-1072 */
+        std::vector<ScanCand> w = search_layer_scan(ix, scratch, ep_list, 1, lc, query, nullptr, nullptr, true, ctr);
+        if (w.empty()) return nbl;
+        ep_list = std::vector<ScanCand>{w.back()};
+    }
+    for (int lc = std::min(new_level, entry_level); lc >= 0; lc--) {   /* :1075-1120 */
+        size_t lm = (size_t)layer_m(ix.m, lc);
+        std::vector<ScanCand> w = search_layer_scan(ix, scratch, ep_list, (size_t)ix.efc, lc, query, nullptr, nullptr,
+                                                    true, ctr);
+        std::vector<ScanCand> sel;                               /* :1110-1116 w is nearest-last: rev().take(lm) */
+        for (size_t i = w.size(); i-- > 0 && sel.size() < lm;) sel.push_back(w[i]);
+        nbl[(size_t)lc] = std::move(sel);
+        ep_list = std::move(w);
+    }
+    return nbl;
+}
+
+/* get_update_index (insert.rs:500-738): -1 = do not link, -2 = free slot, >= 0 = slot to overwrite */
+int get_update_index(orc_index &ix, int32_t nb_idx, int layer, double new_distance, orc_counters &ctr) {
+    const Element &nb = ix.elements[(size_t)nb_idx];
+    if (nb.deleted) return -1;                                   /* :525-528 */
+    if (nb.stale_neighbors || nb.level < layer) return -1;       /* :540-556 load_neighbor_tids => None */
+    const std::vector<Cand> &tids = nb.neighbors[(size_t)layer];
+    size_t lm = (size_t)layer_m(ix.m, layer);
+    if (tids.size() < lm) return -2;                             /* :559-562 */
+    struct HC { int32_t idx; double distance; bool is_new; };
+    std::vector<HC> cand;
+    int pruned_deleted = -1;
+    for (size_t i = 0; i < tids.size(); i++) {                   /* :569-617 */
+        const Element &x = ix.elements[(size_t)tids[i].idx];
+        if (x.deleted || x.heap_tids.empty()) { if (pruned_deleted < 0) pruned_deleted = (int)i; continue; }
+        cand.push_back(HC{tids[i].idx, ix.dist64(ix.row(nb_idx), ix.row(tids[i].idx)), false});
+        ctr.n_pair++;
+    }
+    if (pruned_deleted >= 0) return pruned_deleted;              /* :620-623 */
+    auto by_dist = [](const HC &a, const HC &b) { return a.distance < b.distance; };
+    std::stable_sort(cand.begin(), cand.end(), by_dist);         /* :628-632 stable: ties keep slot order */
+    cand.push_back(HC{-1, new_distance, true});                  /* :652-658 */
+    std::stable_sort(cand.begin(), cand.end(), by_dist);         /* :659-663 the new element stays last among equals */
+    std::vector<const HC *> selected, pruned;
+    for (const HC &hc : cand) {                                  /* :671-705 */
+        if (selected.size() >= lm) break;
+        bool closer = true;
+        for (const HC *sel : selected) {
+            if (!hc.is_new && !sel->is_new) {                    /* :681-689; the new element is exempt both ways */
+                double d = ix.dist64(ix.row(hc.idx), ix.row(sel->idx));
+                ctr.n_pair++;
+                if (d <= hc.distance) { closer = false; break; }
+            }
+        }
+        if (closer) selected.push_back(&hc); else pruned.push_back(&hc);
+    }
+    for (const HC *pr : pruned) {                                /* :708-713 */
+        if (selected.size() >= lm) break;
+        selected.push_back(pr);
+    }
+    bool new_selected = false;
+    for (const HC *sel : selected) new_selected = new_selected || sel->is_new;
+    if (!new_selected) return -1;                                /* :716-720 */
+    for (size_t i = 0; i < tids.size(); i++) {                   /* :731-738 first slot whose element was not kept */
+        bool kept = false;
+        for (const HC *sel : selected) kept = kept || (!sel->is_new && sel->idx == tids[i].idx);
+        if (!kept) return (int)i;
+    }
+    return -1;
+}
+
+/* aminsert (insert.rs:1227-1480) for one row; row already normalised */
+void am_insert(orc_index &ix, const void *rowp, int level, int64_t heap_tid) {
+    size_t off = ix.values.size();
+    ix.values.resize(off + ix.row_bytes);
+    std::memcpy(ix.values.data() + off, rowp, ix.row_bytes);
+    const void *query = ix.values.data() + off;
+    int32_t new_idx = (int32_t)ix.elements.size();
+    int entry_level = ix.entry >= 0 ? ix.elements[(size_t)ix.entry].level : -1;
+    Visited scratch;
+    std::vector<std::vector<ScanCand>> nbl((size_t)level + 1);
+    if (ix.entry >= 0) nbl = find_element_neighbors_on_disk(ix, scratch, query, level, ix.bc);   /* :1317-1334 */
+    for (const ScanCand &n : nbl[0]) {                           /* :1180-1213 find_duplicate_on_disk */
+        if (n.distance != 0.0) break;
+        if (std::memcmp(query, ix.row(n.idx), ix.row_bytes) != 0) continue;
+        std::vector<int64_t> &t = ix.elements[(size_t)n.idx].heap_tids;
+        if (t.empty() || (int)t.size() == HNSW_HEAPTIDS) continue;   /* :1159-1163 being deleted, or full */
+        t.push_back(heap_tid);
+        ix.values.resize(off);
+        return;
+    }
+    Element el;
+    el.level = level;
+    el.neighbors.resize((size_t)level + 1);
+    for (int lc = 0; lc <= level; lc++)                          /* :1390-1414 neighbour tuple, nearest first */
+        for (const ScanCand &n : nbl[(size_t)lc]) el.neighbors[(size_t)lc].push_back(Cand{(float)n.distance, n.idx});
+    el.heap_tids.push_back(heap_tid);
+    ix.elements.push_back(std::move(el));
+    for (int lc = level; lc >= 0; lc--) {                        /* :883-953 update_neighbors_on_disk */
+        size_t lm = (size_t)layer_m(ix.m, lc);
+        for (size_t t = 0; t < nbl[(size_t)lc].size() && t < lm; t++) {
+            const ScanCand &sc = nbl[(size_t)lc][t];
+            if (ix.elements[(size_t)sc.idx].deleted) continue;   /* :903-913 */
+            int idx = get_update_index(ix, sc.idx, lc, sc.distance, ix.bc);
+            if (idx == -1) continue;
+            std::vector<Cand> &tids = ix.elements[(size_t)sc.idx].neighbors[(size_t)lc];   /* :793-870 */
+            bool present = false;
+            for (const Cand &c : tids) present = present || c.idx == new_idx;
+            if (present) continue;
+            Cand link{(float)sc.distance, new_idx};
+            if (idx == -2) { if (tids.size() < lm) tids.push_back(link); }
+            else tids[(size_t)idx] = link;
+        }
+    }
+    if (ix.entry < 0 || level > entry_level) ix.entry = new_idx; /* :1454-1470 */
+}
+
 void add_counters(orc_counters &a, const orc_counters &b) {
     a.n_dist += b.n_dist; a.n_expand0 += b.n_expand0; a.n_expand_upper += b.n_expand_upper;
     a.n_visited += b.n_visited; a.n_pair += b.n_pair;
@@ -633,6 +763,12 @@ size_t orc_row_bytes(const orc_index *ix) { return ix->row_bytes; }
 int64_t orc_build(orc_index *ix, const void *rows, int64_t n, const int32_t *levels, int64_t base_tid) {
     const uint8_t *p = (const uint8_t *)rows;
     for (int64_t i = 0; i < n; i++) build_insert(*ix, p + (size_t)i * ix->row_bytes, levels[i], base_tid + i);
+    return (int64_t)ix->elements.size();
+}
+
+int64_t orc_insert(orc_index *ix, const void *rows, int64_t n, const int32_t *levels, int64_t base_tid) {
+    const uint8_t *p = (const uint8_t *)rows;
+    for (int64_t i = 0; i < n; i++) am_insert(*ix, p + (size_t)i * ix->row_bytes, levels[i], base_tid + i);
     return (int64_t)ix->elements.size();
 }
 

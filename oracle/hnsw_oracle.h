@@ -72,6 +72,12 @@ size_t orc_row_bytes(const orc_index *);
  * heap_tid of row i is base_tid + i.  Returns number of graph elements after the call. */
 int64_t orc_build(orc_index *, const void *rows, int64_t n, const int32_t *levels, int64_t base_tid);
 
+/* aminsert (src/index/insert.rs:1227-1480) for n rows in order, on whatever graph the index holds: nearest-lm lists
+ * for the new element (no heuristic, insert.rs:1096-1117), one-slot back-link updates chosen by get_update_index
+ * (insert.rs:500-738), duplicate merge (insert.rs:1136-1213), entry point on a strictly greater level.  Page
+ * placement and slot reuse are not restated: new elements get the next id.  Returns the element count. */
+int64_t orc_insert(orc_index *, const void *rows, int64_t n, const int32_t *levels, int64_t base_tid);
+
 /* graph introspection (element ids are insertion order among kept elements) */
 int64_t orc_n_elements(const orc_index *);
 int64_t orc_entry_point(const orc_index *);        /* -1 when empty */

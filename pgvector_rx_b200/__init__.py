@@ -42,7 +42,7 @@ EXPORTS = [
     "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
-    "pgvrx_pages_element_flags", "pgvrx_index_set_element_flags",
+    "pgvrx_pages_element_flags", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
 ]
 ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
 
@@ -123,6 +123,7 @@ def lib():
         "pgvrx_pages_element_flags": (C.c_int, [vp, i64, vp]),
         "pgvrx_index_set_element_flags": (C.c_int, [vp, vp, i64]),
         "pgvrx_index_build": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
+        "pgvrx_index_insert": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
         "pgvrx_index_graph_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "pgvrx_index_export_graph": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_search_batch": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats)]),
@@ -300,6 +301,22 @@ class HnswIndex:
             tids = keep.astype(np.uint64) if tids is None else tids[keep]
         st = BuildStats()
         self._check(self.L.pgvrx_index_build(self.h, _p(rows), len(rows), _p(levels), _p(tids), host_threads, C.byref(st)))
+        return st.as_dict()
+
+    def insert(self, rows, levels, heap_tids=None, host_threads=0):
+        """INSERT into a live index: aminsert's rules (src/index/insert.rs:1227-1480) for every row in order.
+        Cosine opclasses normalise and drop zero-norm rows like build().  Returns the same statistics as build()."""
+        rows = _rows(self.elem, self.dim, rows)
+        levels = np.ascontiguousarray(levels, np.int32)
+        tids = None if heap_tids is None else np.ascontiguousarray(heap_tids, np.uint64)
+        if self.normalized:
+            norms, unit = normalize_rows(self.elem, self.dim, rows)
+            keep = np.nonzero(norms != 0.0)[0]
+            rows = np.ascontiguousarray(unit[keep])
+            levels = levels[keep]
+            tids = keep.astype(np.uint64) if tids is None else tids[keep]
+        st = BuildStats()
+        self._check(self.L.pgvrx_index_insert(self.h, _p(rows), len(rows), _p(levels), _p(tids), host_threads, C.byref(st)))
         return st.as_dict()
 
     def graph_info(self):

@@ -348,6 +348,81 @@ static void simulate_group(BuildState &g, Group &G, const uint32_t *masks /* row
     }
 }
 
+// aminsert's back-link rule for one (node, layer) and all pending elements that link to it, in insert order
+// (src/index/insert.rs:500-738 get_update_index + :793-870 write_neighbor_update): append while a slot is free;
+// otherwise sort the list by distance to the node (stable: ties keep slot order, the new element last among equals),
+// run the closer-test heuristic in which the new element is never pruned and never prunes, and if the new element is
+// among the lm kept, overwrite the first slot (in stored order) whose element was not kept.  Slots keep their places.
+static void simulate_group_disk(BuildState &g, Group &G, const uint32_t *masks /* rows of this group or NULL */) {
+    constexpr int W = PAIR_MAX_ROWS / 32;
+    const int lm = G.lm, n_members = (int)G.ids.size() - G.n_list;
+    G.st_ids.assign((size_t)n_members * lm, -1);
+    G.st_ds.assign((size_t)n_members * lm, 0.0f);
+    G.st_pos.assign((size_t)n_members * lm, -1);
+    G.st_cnt.assign((size_t)n_members, 0);
+    Cand cur[256];
+    int16_t cur_pos[256];
+    int order[256], pruned[256];
+    bool kept_slot[256];
+    int cnt = G.n_list;
+    for (int t = 0; t < cnt; t++) { cur[t] = Cand{G.own[(size_t)t], G.ids[(size_t)t]}; cur_pos[t] = (int16_t)t; }
+    uint64_t pairs = 0;
+    for (int k = 0; k < n_members; k++) {
+        const int16_t epos = (int16_t)(G.n_list + k);
+        const Cand nw{G.own[(size_t)epos], G.ids[(size_t)epos]};
+        if (cnt < lm) {                                          // insert.rs:559-562 -> :843-853 first free slot
+            cur[cnt] = nw;
+            cur_pos[cnt] = epos;
+            cnt++;
+        } else {
+            for (int t = 0; t < cnt; t++) { order[t] = t; kept_slot[t] = false; }
+            std::stable_sort(order, order + cnt, [&](int x, int y) { return cur[x].distance < cur[y].distance; });   // :628-632
+            // the new element sorts after every existing entry that is not farther (:652-663)
+            int n_before = 0;
+            while (n_before < cnt && !(nw.distance < cur[order[n_before]].distance)) n_before++;
+            int n_sel = 0, n_pruned = 0;
+            bool new_selected = false;
+            uint32_t kept[W] = {0};
+            int kept_list[256], n_kept = 0;
+            for (int t = 0; t <= cnt && n_sel < lm; t++) {       // :671-705
+                if (t == n_before) { new_selected = true; n_sel++; if (n_sel >= lm) break; }
+                if (t == cnt) break;
+                const int slot = order[t];
+                bool closer = true;
+                if (masks) {
+                    const uint32_t *c = masks + (size_t)cur_pos[slot] * W;
+                    uint32_t hit = 0;
+                    for (int w = 0; w < W; w++) hit |= c[w] & kept[w];
+                    pairs += (uint64_t)n_kept;
+                    closer = hit == 0;
+                } else {
+                    for (int u = 0; u < n_kept; u++) {
+                        pairs++;
+                        if (g.dist(cur[slot].idx, cur[kept_list[u]].idx) <= cur[slot].distance) { closer = false; break; }
+                    }
+                }
+                if (closer) {
+                    kept_slot[slot] = true;
+                    kept[cur_pos[slot] >> 5] |= 1u << (cur_pos[slot] & 31);
+                    kept_list[n_kept++] = slot;
+                    n_sel++;
+                } else {
+                    pruned[n_pruned++] = slot;
+                }
+            }
+            for (int t = 0; t < n_pruned && n_sel < lm; t++) { kept_slot[pruned[t]] = true; n_sel++; }   // :708-713
+            if (new_selected) {                                  // :716-738
+                for (int t = 0; t < cnt; t++)
+                    if (!kept_slot[t]) { cur[t] = nw; cur_pos[t] = epos; break; }
+            }
+        }
+        const size_t o = (size_t)k * lm;
+        for (int t = 0; t < cnt; t++) { G.st_ids[o + t] = cur[t].idx; G.st_ds[o + t] = cur[t].distance; G.st_pos[o + t] = cur_pos[t]; }
+        G.st_cnt[(size_t)k] = (uint8_t)cnt;
+    }
+    g.n_pair.fetch_add(pairs, std::memory_order_relaxed);
+}
+
 }  // namespace pgvrx_host
 
 using namespace pgvrx_host;
@@ -387,14 +462,69 @@ double now_ms() {
 
 extern "C" {
 
-int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, const int32_t *levels,
-                      const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats) {
+// Host mirror of a graph that came in through pgvrx_index_load_graph: arrays back from the device, edge distances
+// recomputed (the on-disk format stores none; get_update_index recomputes them per insert, insert.rs:569-617).
+static int mirror_from_device(pgvrx_index *ix, int nthreads) {
+    const int m = ix->desc.m, l0 = 2 * m;
+    BuildState *b = new BuildState();
+    b->elem = ix->desc.elem_type; b->metric = ix->desc.metric; b->dim = ix->desc.dim; b->m = m; b->efc = ix->desc.ef_construction;
+    b->row_bytes = ix->row_bytes;
+    ix->build = b;
+    BuildState &g = *b;
+    const int64_t n = ix->n, nu = ix->n_upper;
+    g.n = n; g.n_upper = nu; g.entry = ix->entry; g.entry_level = ix->entry_level;
+    g.values.resize((size_t)n * g.row_bytes);
+    g.level.resize((size_t)n);
+    g.upper_base.resize((size_t)n);
+    g.adj0.resize((size_t)n * l0, -1);
+    g.dist0.resize((size_t)n * l0, 0.0f);
+    g.cnt0.resize((size_t)n, 0);
+    g.adj_up.resize((size_t)nu * m, -1);
+    g.dist_up.resize((size_t)nu * m, 0.0f);
+    g.cnt_up.resize((size_t)nu, 0);
+    g.tids.assign((size_t)n * PGVRX_HEAPTIDS, ~0ull);
+    g.tid_cnt.assign((size_t)n, 1);
+    g.stamp.assign((size_t)n, 0);
+    if (n == 0) return PGVRX_OK;
+    CU_TRY(ix, cudaMemcpy2D(g.values.data(), g.row_bytes, ix->vectors.p, ix->row_stride, g.row_bytes, (size_t)n, cudaMemcpyDeviceToHost));
+    CU_TRY(ix, cudaMemcpy(g.level.data(), ix->level.p, (size_t)n, cudaMemcpyDeviceToHost));
+    CU_TRY(ix, cudaMemcpy(g.upper_base.data(), ix->upper_base.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(ix, cudaMemcpy(g.adj0.data(), ix->adj0.p, (size_t)n * l0 * 4, cudaMemcpyDeviceToHost));
+    if (nu > 0) CU_TRY(ix, cudaMemcpy(g.adj_up.data(), ix->adj_up.p, (size_t)nu * m * 4, cudaMemcpyDeviceToHost));
+    for (int64_t e = 0; e < n; e++) g.tids[(size_t)e * PGVRX_HEAPTIDS] = (uint64_t)e;
+    Pool pool(nthreads);
+    pool.parallel_for(n, [&](int64_t v) {
+        for (int lc = 0; lc <= g.level[(size_t)v]; lc++) {
+            const int lm = g.lm(lc);
+            int32_t *ids = g.ids(v, lc);
+            float *ds = g.dists(v, lc);
+            int c = 0;
+            while (c < lm && ids[c] >= 0) { ds[c] = host_distance(g.elem, g.metric, g.dim, g.row(v), g.row(ids[c])); c++; }
+            g.cnt(v, lc) = (uint8_t)c;
+        }
+    });
+    return PGVRX_OK;
+}
+
+// The insert loop shared by CREATE INDEX (disk_rule = false: the in-memory build, graph/mod.rs + build.rs) and by
+// inserts into a live index (disk_rule = true: aminsert, src/index/insert.rs).  Searches, speculation and the replay
+// validation are the same; what differs is how the new element's lists are chosen and how a neighbour's list is updated.
+static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, const int32_t *levels,
+                       const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats, const bool disk_rule) {
     if (!ix) return PGVRX_ERR_INVALID;
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_rows < 0 || (n_rows > 0 && (!rows_in || !levels))) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null build input");
-    if (ix->loaded && !ix->build) return pgvrx_fail(ix, PGVRX_ERR_STATE, "index was loaded from arrays; build needs a handle that is empty or was built here");
-    if (ix->has_flags) return pgvrx_fail(ix, PGVRX_ERR_STATE, "element flags are set (vacuumed index); the in-memory build does not extend it");
+    if (!disk_rule && ix->loaded && !ix->build) return pgvrx_fail(ix, PGVRX_ERR_STATE, "index was loaded from arrays; build needs a handle that is empty or was built here");
+    if (ix->has_flags) return pgvrx_fail(ix, PGVRX_ERR_STATE, "element flags are set (vacuumed index); inserts into it are not supported");
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    if (disk_rule && ix->loaded && !ix->build) {
+        int avail0 = (int)std::max(1u, std::thread::hardware_concurrency());
+        cpu_set_t set0;
+        CPU_ZERO(&set0);
+        if (sched_getaffinity(0, sizeof set0, &set0) == 0 && CPU_COUNT(&set0) > 0) avail0 = std::min(avail0, (int)CPU_COUNT(&set0));
+        int rc0 = mirror_from_device(ix, host_threads > 0 ? host_threads : avail0);
+        if (rc0) return rc0;
+    }
     const int m = ix->desc.m, efc = ix->desc.ef_construction, l0 = 2 * m;
     if (!ix->build) {
         ix->build = new BuildState();
@@ -569,7 +699,7 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
     const uint32_t pair_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
     const int pair_rows = (int)std::min<size_t>(PAIR_MAX_ROWS, (200 * 1024) / pair_stride);
     const int pair_occ = std::max(1, (int)((220 * 1024) / (128 + (size_t)pair_rows * pair_stride)));
-    const bool w_masks = efc <= pair_rows;               // select_neighbors of the new elements answered by GPU masks
+    const bool w_masks = !disk_rule && efc <= pair_rows;  // select_neighbors of the new elements answered by GPU masks
     std::vector<int32_t> h_elem;
     PinnedBuf h_pack;
 
@@ -702,7 +832,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
                 w.resize((size_t)std::max(cnt, 0));
                 const size_t o = ((size_t)i * max_layers + lc) * efc;
                 for (int t = 0; t < cnt; t++) w[(size_t)t] = Cand{h_wd[o + t], h_wids[o + t]};
-                if (w_masks && cnt > g.lm(lc)) {                                     // graph/mod.rs:419 with the GPU's masks
+                if (disk_rule) {                                                     // insert.rs:1110-1116: the nearest lm, no heuristic
+                    p.sel[(size_t)lc].assign(w.begin(), w.begin() + std::min(cnt < 0 ? 0 : cnt, g.lm(lc)));
+                } else if (w_masks && cnt > g.lm(lc)) {                                     // graph/mod.rs:419 with the GPU's masks
                     wpos.resize((size_t)cnt);
                     for (int t = 0; t < cnt; t++) wpos[(size_t)t] = (int16_t)t;
                     select_neighbors_mask(g, w.data(), wpos.data(), cnt, g.lm(lc), h_wmask + o * (PAIR_MAX_ROWS / 32), p.sel[(size_t)lc], spos);
@@ -842,7 +974,8 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         const double tB0 = now_ms();
         pool.parallel_for(n_groups, [&](int64_t gi) {
             Group &G = *all_groups[(size_t)gi];
-            simulate_group(g, G, G.row_off >= 0 ? mask_all + (size_t)G.row_off * MW : nullptr);
+            if (disk_rule) simulate_group_disk(g, G, G.row_off >= 0 ? mask_all + (size_t)G.row_off * MW : nullptr);
+            else simulate_group(g, G, G.row_off >= 0 ? mask_all + (size_t)G.row_off * MW : nullptr);
         });
         t_sim += now_ms() - tB0;
 
@@ -926,7 +1059,9 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
             if (p.dup_of >= 0) {
                 for (const Cand &nb : p.sel[0]) {
                     if (nb.distance != 0.0f) break;
-                    if (memcmp(g.row(e), g.row(nb.idx), g.row_bytes) == 0 && g.tid_cnt[(size_t)nb.idx] < PGVRX_HEAPTIDS) {
+                    // insert.rs:1159-1163 also refuses an element whose first heap TID is gone (being deleted)
+                    if (memcmp(g.row(e), g.row(nb.idx), g.row_bytes) == 0 && g.tid_cnt[(size_t)nb.idx] < PGVRX_HEAPTIDS &&
+                        !(disk_rule && g.tid_cnt[(size_t)nb.idx] == 0)) {
                         g.tids[(size_t)nb.idx * PGVRX_HEAPTIDS + g.tid_cnt[(size_t)nb.idx]++] = tid_of(p.input_row);
                         merged = true;
                         break;
@@ -1030,6 +1165,16 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows_in, int64_t n_rows, cons
         stats->host_threads = nthreads;
     }
     return PGVRX_OK;
+}
+
+int pgvrx_index_build(pgvrx_index *ix, const void *rows, int64_t n_rows, const int32_t *levels, const uint64_t *heap_tids,
+                      int32_t host_threads, pgvrx_build_stats *stats) {
+    return run_inserts(ix, rows, n_rows, levels, heap_tids, host_threads, stats, false);
+}
+
+int pgvrx_index_insert(pgvrx_index *ix, const void *rows, int64_t n_rows, const int32_t *levels, const uint64_t *heap_tids,
+                       int32_t host_threads, pgvrx_build_stats *stats) {
+    return run_inserts(ix, rows, n_rows, levels, heap_tids, host_threads, stats, true);
 }
 
 int pgvrx_index_graph_info(const pgvrx_index *ix, int64_t *n, int64_t *n_upper_rows, int64_t *entry, int32_t *entry_level) {

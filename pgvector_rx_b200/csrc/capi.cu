@@ -438,6 +438,7 @@ int pgvrx_index_load_graph(pgvrx_index *ix, const void *rows, int64_t n, const u
     ix->rows_loaded = false;
     ix->tc_ready = false;
     ix->has_flags = false;
+    if (ix->build) { pgvrx_host::destroy_build_state(ix->build); ix->build = nullptr; }   // the host mirror described the old graph
     CU_TRY(ix, ix->vectors.ensure(std::max<size_t>(16, (size_t)n * ix->row_stride)));
     CU_TRY(ix, ix->adj0.ensure(std::max<size_t>(16, (size_t)n * 2 * m * 4)));
     CU_TRY(ix, ix->adj_up.ensure(std::max<size_t>(16, (size_t)n_upper_rows * m * 4)));

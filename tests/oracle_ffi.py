@@ -59,6 +59,7 @@ def lib():
         "orc_destroy": (None, [vp]),
         "orc_row_bytes": (C.c_size_t, [vp]),
         "orc_build": (i64, [vp, vp, i64, vp, i64]),
+        "orc_insert": (i64, [vp, vp, i64, vp, i64]),
         "orc_n_elements": (i64, [vp]),
         "orc_entry_point": (i64, [vp]),
         "orc_element_level": (i32, [vp, i64]),
@@ -146,6 +147,13 @@ class Oracle:
         levels = np.ascontiguousarray(levels, dtype=np.int32)
         assert len(levels) == len(rows)
         return self.L.orc_build(self.h, _p(rows), len(rows), _p(levels), base_tid)
+
+    def insert(self, rows, levels, base_tid=0):
+        """aminsert for every row in order (src/index/insert.rs:1227-1480)."""
+        rows = as_rows(self.elem_type, self.dim, rows)
+        levels = np.ascontiguousarray(levels, dtype=np.int32)
+        assert len(levels) == len(rows)
+        return self.L.orc_insert(self.h, _p(rows), len(rows), _p(levels), base_tid)
 
     @property
     def n(self):

@@ -274,3 +274,56 @@ def test_duplicates_merge_heap_tids():
     assert len(tids) == 10 and len(set(eids.tolist())) == 1            # exactly 10 TIDs at ef_search=1
     # TIDs are emitted from the back of the element's list (scan.rs:798)
     assert tids.tolist() == o.heap_tids(int(eids[0]))[::-1].tolist()
+
+
+# ---- src/index/insert.rs:1492-1616 (pg_tests of aminsert, restated on the oracle) -------------------
+def test_insert_after_build_is_found():
+    # test_hnsw_insert_basic: index three rows, INSERT [0.5,0.5,0], nearest to it is itself
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 3)
+    o.build(np.stack([f32(1, 0, 0), f32(0, 1, 0), f32(0, 0, 1)]), np.zeros(3, np.int32))
+    assert o.insert(f32(0.5, 0.5, 0)[None], np.zeros(1, np.int32), base_tid=3) == 4
+    ids, ds, _ = o.search_batch(f32(0.5, 0.5, 0)[None], k=1)
+    assert ids[0, 0] == 3 and ds[0, 0] == 0.0
+
+
+def test_insert_into_empty_index():
+    # test_hnsw_insert_into_empty_index: every row goes through aminsert; nearest to [1,0,0] is [1,0,0]
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 3)
+    for i, r in enumerate((f32(1, 0, 0), f32(0, 1, 0), f32(0, 0, 1))):
+        o.insert(r[None], np.zeros(1, np.int32), base_tid=i)
+    assert o.n == 3 and o.entry == 0
+    ids, _, _ = o.search_batch(f32(1, 0, 0)[None], k=1)
+    assert ids[0, 0] == 0
+    # back-links went into free slots (insert.rs:559-562): everyone is linked to everyone
+    for i in range(3):
+        assert sorted(o.neighbors(i, 0).tolist()) == sorted(set(range(3)) - {i})
+
+
+def test_insert_cosine_and_duplicates():
+    # test_hnsw_insert_cosine
+    o = O.Oracle(O.ELEM_F32, O.NEG_IP, 3)
+    o.build(np.stack([f32(1, 0, 0), f32(0, 1, 0)]), np.zeros(2, np.int32))
+    o.insert(f32(0, 0, 1)[None], np.zeros(1, np.int32), base_tid=2)
+    ids, _, _ = o.search_batch(f32(0, 0, 1)[None], k=1)
+    assert ids[0, 0] == 2
+    # the duplicate walk stops at the first neighbour whose distance is not 0.0 (insert.rs:1189-1191): under -dot an
+    # identical unit row is at distance -1, so cosine / inner-product indexes never merge duplicates
+    o.insert(np.tile(f32(0, 0, 1), (3, 1)), np.zeros(3, np.int32), base_tid=3)
+    assert o.n == 6
+    # L2: a duplicate row adds a heap TID to an element holding 1..9 of them (insert.rs:1136-1170)
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 3)
+    o.build(np.stack([f32(1, 0, 0), f32(0, 1, 0)]), np.zeros(2, np.int32))
+    o.insert(np.tile(f32(0, 0, 1), (13, 1)), np.zeros(13, np.int32), base_tid=2)
+    assert o.n == 4 and sorted(len(o.heap_tids(i)) for i in (2, 3)) == [3, 10]
+
+
+def test_insert_replaces_one_slot_of_a_full_list():
+    # get_update_index (insert.rs:500-738) on a full list: m = 2 => lm = 4 at layer 0.  Node 0 at the origin holds
+    # 1, 2, 3, 4 at distances 1, 4, 9, 16 on a line; 5 arrives at distance 2.25 on the other side.  Sorted: 1, 5(new),
+    # 2, 3, 4; 2 is pruned by 1 (d(2,1)=1 <= 4), 3 by 1, 4 by 1; kept = {1, new} + pruned 2, 3 => slot of 4 is overwritten.
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 1, m=2, ef_construction=8)
+    o.insert(np.array([[0.0], [1.0], [2.0], [3.0], [4.0]], np.float32), np.zeros(5, np.int32))
+    assert o.neighbors(0, 0).tolist() == [1, 2, 3, 4]
+    o.insert(np.array([[-1.5]], np.float32), np.zeros(1, np.int32), base_tid=5)
+    assert o.neighbors(0, 0).tolist() == [1, 2, 3, 5]             # slot order kept, only the last slot changed
+    assert o.neighbors(5, 0).tolist() == [0, 1, 2, 3]             # nearest lm of W, no heuristic (insert.rs:1110-1116)
