@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--recall-sample", type=int, default=200)
     ap.add_argument("--build-rows", type=int, default=-1,
                     help="rows of the same dataset built on the GPU for the build vectors/s figure (0 = skip)")
+    ap.add_argument("--insert-rows", type=int, default=-1,
+                    help="rows inserted into the finished index through aminsert's rules (-1 = 20000 when the whole dataset was built at N=1, else 0)")
     ap.add_argument("--threads", type=int, default=0, help="host threads for the CPU legs (0 = the cores this process may use)")
     ap.add_argument("--no-flat", action="store_true", help="skip the exact flat-kNN section (recall then uses the oracle's brute force on --recall-sample queries)")
     a = ap.parse_args()
@@ -162,7 +164,7 @@ def cpu_baseline(a, g, queries, sample=0, budget_s=12.0):
                        % (done, done // len(q), len(q), a.ef, a.k, cores, dt)), ids, o
 
 
-def gpu_build_sample(a, local):
+def gpu_build_sample(a, local, n_insert=0):
     """Index build (CREATE INDEX) of the first --build-rows rows of the C2 dataset through
     pgvrx_index_build: GPU-batched search_layer + host heuristic.  When an oracle graph of exactly that
     prefix is cached, the adjacency is compared with it (it must be identical)."""
@@ -171,7 +173,7 @@ def gpu_build_sample(a, local):
     n = min(a.build_rows, a.n)
     X = D.gaussian_f32(a.n, a.dim, 2)[:n] if n < a.n else D.gaussian_f32(a.n, a.dim, 2)
     lv = D.hnsw_levels(a.n, a.m, 4)[:n]
-    ix = P.HnswIndex("vector_l2_ops", a.dim, m=a.m, ef_construction=a.efc, capacity=n, device=local)
+    ix = P.HnswIndex("vector_l2_ops", a.dim, m=a.m, ef_construction=a.efc, capacity=n + n_insert, device=local)
     t0 = time.perf_counter()
     st = ix.build(X, lv)
     dt = time.perf_counter() - t0
@@ -189,8 +191,40 @@ def gpu_build_sample(a, local):
                                                    for k in ("level", "adj0", "upper_base", "adj_up"))
         out["adjacency_identical_to_oracle"] = bool(same)
         out["cpu_oracle_vectors_per_s_same_rows"] = meta["n"] / meta["build_seconds"]
+    if n_insert > 0:
+        return out, ix
     ix.close()
-    return out
+    return out, None
+
+
+def insert_sample(a, ix, o, n_insert, n_check=1500):
+    """INSERT into the finished index (aminsert, src/index/insert.rs): n_insert new rows through pgvrx_index_insert.
+    The first n_check of them also go through the oracle's aminsert on the same graph and the two graphs are compared
+    (every list of every layer); the rest measure throughput."""
+    from pgvector_rx_b200 import datasets as D
+    X = D.gaussian_f32(n_insert, a.dim, 12)
+    lv = D.hnsw_levels(n_insert, a.m, 13)
+    n_check = min(n_check, n_insert)
+    n0 = ix.graph_info()["n"]
+    t0 = time.perf_counter()
+    o.insert(X[:n_check], lv[:n_check], base_tid=n0)
+    dt_cpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    st1 = ix.insert(X[:n_check], lv[:n_check], heap_tids=np.arange(n0, n0 + n_check, dtype=np.uint64))
+    dt1 = time.perf_counter() - t0
+    g, w = ix.export_graph(), o.export_graph()
+    same = g["n"] == w["n"] and g["entry"] == w["entry"] and all(np.array_equal(g[k], w[k]) for k in ("level", "adj0", "upper_base", "adj_up"))
+    del g, w
+    t0 = time.perf_counter()
+    st2 = ix.insert(X[n_check:], lv[n_check:], heap_tids=np.arange(n0 + n_check, n0 + n_insert, dtype=np.uint64))
+    dt2 = time.perf_counter() - t0
+    return dict(gpu_vectors_per_s=n_insert / (dt1 + dt2), rows=n_insert, into_rows=int(n0), seconds=dt1 + dt2,
+                rounds=st1["n_rounds"] + st2["n_rounds"], conflicts=st1["n_conflicts"] + st2["n_conflicts"],
+                host_distance_evals=st1["n_host_dist"] + st2["n_host_dist"],
+                cpu_oracle_vectors_per_s=n_check / dt_cpu, cpu_sample_rows=n_check,
+                graph_identical_to_oracle=bool(same),
+                note="aminsert rules (nearest-lm lists, one-slot back-link replacement); the oracle inserts the first %d rows "
+                     "single-threaded on the same graph and the resulting graphs are compared" % n_check)
 
 
 def recall_at_k(a, g, queries, got_ids, sample):
@@ -521,10 +555,20 @@ def run_b200(a):
     out = None
     if rank == 0:
         build_info = dict(cpu_oracle_vectors_per_s=g.get("build_vec_per_s_cpu"), gpu_vectors_per_s=None)
+        ix_built = None
         if a.build_rows > 0:
             ix.close()
-            build_info.update(gpu_build_sample(a, local))
+            n_ins = a.insert_rows if a.insert_rows >= 0 else (20000 if (world == 1 and a.build_rows >= a.n) else 0)
+            if a.build_rows < a.n:
+                n_ins = 0                      # the oracle's graph g (the comparison base) holds all a.n rows
+            b_info, ix_built = gpu_build_sample(a, local, n_ins)
+            build_info.update(b_info)
         base, cpu_ids, o = cpu_baseline(a, g, last_batch, a.cpu_sample)
+        if ix_built is not None:
+            # the scan oracle is no longer needed for queries: let it take the same inserts
+            if build_info.get("adjacency_identical_to_oracle", g.get("source") == "gpu-build"):
+                build_info["insert"] = insert_sample(a, ix_built, o, n_ins)
+            ix_built.close()
         nchk = len(cpu_ids)
         parity_ok = bool(np.array_equal(cpu_ids, last_ids[:nchk]))
         # recall of the whole batch against the GPU's exact kNN; the exact result itself is cross-checked against the
