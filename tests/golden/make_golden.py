@@ -59,9 +59,74 @@ def generate(name):
     return out
 
 
+# A LIVE index: n0 rows by CREATE INDEX, n1 rows by aminsert (src/index/insert.rs), then the states a vacuum leaves
+# behind (deleted / no heap TIDs / stale neighbour tuples, src/index/vacuum.rs) and scans over them.
+# name -> (opclass, kind, n0, n1, dim, nq, m, efc, ef_search, k, seed)
+LIVE_CASES = {
+    "live_vector_l2": ("vector_l2_ops", "f32", 1200, 600, 24, 24, 8, 32, 40, 10, 201),
+    "live_bit_hamming": ("bit_hamming_ops", "bit", 900, 500, 256, 16, 6, 24, 20, 10, 202),
+}
+
+
+def live_inputs(name):
+    from pgvector_rx_b200 import datasets as D
+    opclass, kind, n0, n1, dim, nq, m, efc, ef, k, seed = LIVE_CASES[name]
+    rows = make_rows(kind, n0 + n1, dim, seed)
+    lv = D.hnsw_levels(n0 + n1, m, seed + 2)
+    q = make_rows(kind, nq, dim, seed + 1)
+    return rows, lv, q
+
+
+def live_oracle(name):
+    """The oracle after build + insert, then after the seeded vacuum marks; returns (o, graph after insert, marks)."""
+    opclass, kind, n0, n1, dim, nq, m, efc, ef, k, seed = LIVE_CASES[name]
+    elem, metric, norm = P.OPCLASSES[opclass]
+    rows, lv, q = live_inputs(name)
+    o = O.Oracle(elem, metric, dim, m=m, ef_construction=efc, tie_mode=O.TIE_TOTAL_ORDER)
+    o.build(rows[:n0], lv[:n0])
+    o.insert(rows[n0:], lv[n0:], base_tid=n0)
+    after_insert = o.export_graph()
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(o.n)
+    c = o.n // 16
+    deleted, no_tid, stale = perm[:c], perm[c:2 * c], perm[2 * c:2 * c + c // 4]
+    deleted = deleted[deleted != o.entry]
+    o.vacuum_mark(deleted, O.VACUUM_MARK_DELETED)
+    o.vacuum_mark(no_tid, O.VACUUM_REMOVE_HEAPTIDS)
+    o.vacuum_mark(stale, O.VACUUM_STALE_NEIGHBORS)
+    return o, after_insert, q
+
+
+def generate_live(name):
+    opclass, kind, n0, n1, dim, nq, m, efc, ef, k, seed = LIVE_CASES[name]
+    elem = P.OPCLASSES[opclass][0]
+    o, gi, q = live_oracle(name)
+    out = dict(ins_level=gi["level"], ins_adj0=gi["adj0"], ins_upper_base=gi["upper_base"], ins_adj_up=gi["adj_up"],
+               ins_entry=np.int64(gi["entry"]), ins_n=np.int64(gi["n"]))
+    # what the scan sees after the vacuum: the relation's pages through the product's exporter
+    gv = P.export_pages(o.write_pages(), elem)
+    assert np.array_equal(gv["flags"], o.element_flags())
+    out.update(vac_adj0=gv["adj0"], vac_adj_up=gv["adj_up"], vac_flags=gv["flags"])
+    ids, dists, counts, ctr = o.search_batch(q, ef_search=ef, k=k, with_counters=True)
+    out.update(scan_ids=ids, scan_dists=dists, scan_counts=counts,
+               counters=np.array([ctr["n_dist"], ctr["n_expand0"], ctr["n_expand_upper"], ctr["n_visited"]], np.int64))
+    for mode, tag in ((O.ITER_RELAXED, "relaxed"), (O.ITER_STRICT, "strict")):
+        streams = []
+        for i in range(4):
+            _, eids, ds, _ = o.scan_stream(q[i], ef_search=ef, iterative=mode, max_scan_tuples=100, max_emit=150)
+            pad = np.full(150, -1, np.int32)
+            pad[:len(eids)] = eids
+            streams.append(pad)
+        out["iter_" + tag] = np.stack(streams)
+    return out
+
+
 def main():
     for name in CASES:
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **generate(name))
+        print("wrote", name)
+    for name in LIVE_CASES:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **generate_live(name))
         print("wrote", name)
 
 

@@ -83,3 +83,59 @@ def test_gpu_reproduces_golden(name):
             assert np.array_equal(got[i], want[want >= 0])
         sc.close()
     ix.close()
+
+
+# ---- live index: CREATE INDEX + aminsert, then scans over what a vacuum leaves behind ---------------------------------
+from make_golden import LIVE_CASES, live_inputs, live_oracle   # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(LIVE_CASES))
+def test_oracle_reproduces_live_golden(name):
+    opclass, kind, n0, n1, dim, nq, m, efc, ef, k, seed = LIVE_CASES[name]
+    g = load(name)
+    o, gi, q = live_oracle(name)
+    for key in ("level", "adj0", "upper_base", "adj_up"):
+        assert np.array_equal(gi[key], g["ins_" + key]), key
+    assert int(gi["entry"]) == int(g["ins_entry"]) and int(gi["n"]) == int(g["ins_n"])
+    gv = P.export_pages(o.write_pages(), P.OPCLASSES[opclass][0])
+    assert np.array_equal(gv["flags"], g["vac_flags"]) and np.array_equal(gv["adj0"], g["vac_adj0"])
+    ids, dists, counts, ctr = o.search_batch(q, ef_search=ef, k=k, with_counters=True)
+    assert np.array_equal(ids, g["scan_ids"]) and np.array_equal(dists, g["scan_dists"]) and np.array_equal(counts, g["scan_counts"])
+    assert [ctr["n_dist"], ctr["n_expand0"], ctr["n_expand_upper"], ctr["n_visited"]] == g["counters"].tolist()
+    for mode, tag in ((O.ITER_RELAXED, "relaxed"), (O.ITER_STRICT, "strict")):
+        for i in range(4):
+            _, eids, _, _ = o.scan_stream(q[i], ef_search=ef, iterative=mode, max_scan_tuples=100, max_emit=150)
+            want = g["iter_" + tag][i]
+            assert np.array_equal(eids, want[want >= 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(LIVE_CASES))
+def test_gpu_reproduces_live_golden(name):
+    """No oracle on this path: inputs from seeds, expectations from the committed fixture."""
+    opclass, kind, n0, n1, dim, nq, m, efc, ef, k, seed = LIVE_CASES[name]
+    g = load(name)
+    rows, lv, q = live_inputs(name)
+    ix = P.HnswIndex(opclass, dim, m=m, ef_construction=efc, capacity=n0 + n1)
+    ix.build(rows[:n0], lv[:n0])
+    ix.insert(rows[n0:], lv[n0:], heap_tids=np.arange(n0, n0 + n1, dtype=np.uint64))
+    bg = ix.export_graph()
+    for key in ("level", "adj0", "upper_base", "adj_up"):
+        assert np.array_equal(bg[key], g["ins_" + key]), key
+    assert int(bg["entry"]) == int(g["ins_entry"]) and int(bg["n"]) == int(g["ins_n"])
+    # the vacuumed relation as exported from its pages: same elements, some lists emptied, flags set
+    vrows = bg["rows"].copy()
+    vrows[(g["vac_flags"] & P.ELEM_DELETED) != 0] = 0
+    ix.load_graph(vrows, bg["level"], g["vac_adj0"], bg["upper_base"], g["vac_adj_up"], int(bg["entry"]))
+    ix.set_element_flags(g["vac_flags"])
+    ids, dists, counts, st = ix.search(q, k=k, ef_search=ef, with_stats=True)
+    assert np.array_equal(ids, g["scan_ids"]) and np.array_equal(dists, g["scan_dists"]) and np.array_equal(counts, g["scan_counts"])
+    assert [st["n_dist"], st["n_expand0"], st["n_expand_upper"], st["n_visited"]] == g["counters"].tolist()
+    for mode, tag in ((P.ITER_RELAXED, "relaxed"), (P.ITER_STRICT, "strict")):
+        sc = ix.scan_begin(q[:4], ef_search=ef, iterative_scan=mode, max_scan_tuples=100)
+        got, _ = sc.stream(150)
+        sc.close()
+        for i in range(4):
+            want = g["iter_" + tag][i]
+            assert np.array_equal(got[i], want[want >= 0]), (tag, i)
+    ix.close()
