@@ -215,6 +215,12 @@ int pgvrx_index_build(pgvrx_index *idx, const void *rows, int64_t n_rows, const 
 int pgvrx_index_insert(pgvrx_index *idx, const void *rows, int64_t n_rows, const int32_t *levels,
                        const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats);
 
+/* Heap TIDs of a loaded index (n x 10 as block << 16 | offset with ~0 padding, and n counts -- the arrays
+ * pgvrx_pages_export fills): lets pgvrx_index_insert apply the duplicate rule's capacity test (an element takes a
+ * duplicate's TID only while it holds 1..9, insert.rs:1159-1163) and pgvrx_index_export_graph return them.  Without
+ * this call every loaded element counts as holding one heap TID equal to its id. */
+int pgvrx_index_set_heap_tids(pgvrx_index *idx, const uint64_t *heap_tids, const uint8_t *counts, int64_t n);
+
 int pgvrx_index_graph_info(const pgvrx_index *idx, int64_t *n, int64_t *n_upper_rows, int64_t *entry,
                            int32_t *entry_level);
 /* copies the built graph out (any pointer may be NULL); shapes as in pgvrx_index_load_graph,

@@ -43,6 +43,7 @@ EXPORTS = [
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
     "pgvrx_pages_element_flags", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
+    "pgvrx_index_set_heap_tids",
 ]
 ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
 
@@ -124,6 +125,7 @@ def lib():
         "pgvrx_index_set_element_flags": (C.c_int, [vp, vp, i64]),
         "pgvrx_index_build": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
         "pgvrx_index_insert": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
+        "pgvrx_index_set_heap_tids": (C.c_int, [vp, vp, vp, i64]),
         "pgvrx_index_graph_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "pgvrx_index_export_graph": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_search_batch": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats)]),
@@ -278,6 +280,12 @@ class HnswIndex:
         adj_up = np.ascontiguousarray(adj_up, np.int32).reshape(-1, self.m)
         self._check(self.L.pgvrx_index_load_graph(self.h, _p(rows), len(rows), _p(level), _p(adj0), _p(upper_base),
                                                   _p(adj_up) if len(adj_up) else None, len(adj_up), int(entry)))
+
+    def set_heap_tids(self, heap_tids, counts):
+        """Heap TIDs of a loaded index (the n x 10 / n arrays of export_pages / export_graph); see the header."""
+        t = np.ascontiguousarray(heap_tids, np.uint64)
+        c = np.ascontiguousarray(counts, np.uint8)
+        self._check(self.L.pgvrx_index_set_heap_tids(self.h, _p(t), _p(c), len(c)))
 
     def set_element_flags(self, flags):
         """Per-element vacuum state (ELEM_DELETED / ELEM_NO_HEAPTIDS, scan.rs:179,866-868); None clears."""

@@ -33,6 +33,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -186,6 +187,7 @@ struct BuildState {
     std::vector<uint32_t> stamp;        // per node: round in which one of its lists was last modified
     uint32_t round = 0;
     std::atomic<uint64_t> n_pair{0};
+    struct RoundScratch *scratch = nullptr;   // device / pinned round buffers, kept across appending calls
 
     const uint8_t *row(int64_t e) const { return values.data() + (size_t)e * row_bytes; }
     std::atomic<uint64_t> n_host_dist{0};   // distances evaluated on the host (groups that do not fit on a CTA)
@@ -196,7 +198,7 @@ struct BuildState {
     uint8_t &cnt(int64_t v, int lc) { return lc == 0 ? cnt0[(size_t)v] : cnt_up[(size_t)(upper_base[(size_t)v] + lc - 1)]; }
 };
 
-void destroy_build_state(BuildState *b) { delete b; }
+void destroy_build_state(BuildState *b);   // defined below, after RoundScratch
 
 // a3: select_neighbors + check_element_closer (graph/mod.rs:269-339)
 static void select_neighbors(BuildState &g, const Cand *cand, int n_cand, int max_neighbors, std::vector<Cand> &out) {
@@ -460,7 +462,39 @@ double now_ms() {
 
 }  // namespace
 
+namespace pgvrx_host {
+// cudaMalloc / cudaFree / cudaMallocHost cost tens to hundreds of milliseconds per insert call when every call grows
+// its buffers from nothing (measured: 50-250 ms per 6.7k-row call), so they live with the index
+struct RoundScratch {
+    RoundBuffers rb;
+    PinnedBuf h_pack, h_mat;
+    ~RoundScratch() { rb.release(); }
+};
+void destroy_build_state(BuildState *b) {
+    if (b) delete b->scratch;
+    delete b;
+}
+}  // namespace pgvrx_host
+
 extern "C" {
+
+static void reserve_mirror(BuildState &g, int64_t cap) {
+    const size_t c = (size_t)std::max<int64_t>(cap, g.n), l0 = (size_t)2 * g.m;
+    if (g.values.capacity() >= c * g.row_bytes && g.adj0.capacity() >= c * l0) return;
+    try {
+        g.values.reserve(c * g.row_bytes);
+        g.level.reserve(c);
+        g.upper_base.reserve(c);
+        g.adj0.reserve(c * l0);
+        g.dist0.reserve(c * l0);
+        g.cnt0.reserve(c);
+        g.tids.reserve(c * PGVRX_HEAPTIDS);
+        g.tid_cnt.reserve(c);
+        g.stamp.reserve(c);
+    } catch (const std::bad_alloc &) {
+        // a capacity far beyond what is ever inserted: fall back to the vectors' own geometric growth
+    }
+}
 
 // Host mirror of a graph that came in through pgvrx_index_load_graph: arrays back from the device, edge distances
 // recomputed (the on-disk format stores none; get_update_index recomputes them per insert, insert.rs:569-617).
@@ -473,6 +507,7 @@ static int mirror_from_device(pgvrx_index *ix, int nthreads) {
     BuildState &g = *b;
     const int64_t n = ix->n, nu = ix->n_upper;
     g.n = n; g.n_upper = nu; g.entry = ix->entry; g.entry_level = ix->entry_level;
+    reserve_mirror(g, ix->desc.capacity);
     g.values.resize((size_t)n * g.row_bytes);
     g.level.resize((size_t)n);
     g.upper_base.resize((size_t)n);
@@ -564,8 +599,9 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     ix->tc_ready = false;
 
     // ---- host mirror capacity ----
-    g.values.reserve((size_t)(g.n + n_rows) * g.row_bytes);
-    g.level.reserve((size_t)(g.n + n_rows));
+    // the per-element arrays are reserved for the handle's capacity once (address space only, pages are touched as
+    // elements arrive), so appending calls -- pgvrx_index_insert in small batches -- never copy the mirror
+    reserve_mirror(g, cap);
     auto grow_host = [&](int64_t n_new, int64_t up_new) {
         g.values.resize((size_t)n_new * g.row_bytes);
         g.level.resize((size_t)n_new);
@@ -599,8 +635,8 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         g.tid_cnt[(size_t)e] = 0;
     };
 
-    RoundBuffers rb;
-    struct Cleanup { RoundBuffers &r; ~Cleanup() { r.release(); } } cleanup{rb};
+    if (!g.scratch) g.scratch = new RoundScratch();
+    RoundBuffers &rb = g.scratch->rb;
 
     // scatter staging on the host
     std::vector<int64_t> sc_off0, sc_offu;
@@ -688,23 +724,26 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     std::vector<int32_t> gidx0;
     std::vector<int32_t> h_gids, h_goff;
     std::vector<float> h_gown;
-    PinnedBuf h_mat;
+    PinnedBuf &h_mat = g.scratch->h_mat;
     uint64_t n_pair_gpu = 0, n_val_dist = 0;
     std::atomic<uint64_t> n_val_dist_atomic{0};
     double t_sim = 0, t_g1 = 0, t_g2 = 0;
     for (int t = 0; t < 256; t++) g_identity_pos[t] = (int16_t)t;
     uint64_t why_overflow = 0, why_notfull = 0, why_pending = 0, why_order = 0;   // conflict reasons (PGVRX_BUILD_DEBUG)
-    double t_phase_a = 0, t_groups = 0, t_commit = 0, t_scatter = 0;
+    double t_phase_a = 0, t_groups = 0, t_commit = 0, t_scatter = 0, t_prelude = 0, t_tail = 0;
+    const double t_loop0 = now_ms();
+    double t_place = 0, t_upload = 0, t_cfg = 0;
     // rows a pairwise group may hold: what fits in one CTA's shared memory, at most PAIR_MAX_ROWS
     const uint32_t pair_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
     const int pair_rows = (int)std::min<size_t>(PAIR_MAX_ROWS, (200 * 1024) / pair_stride);
     const int pair_occ = std::max(1, (int)((220 * 1024) / (128 + (size_t)pair_rows * pair_stride)));
     const bool w_masks = !disk_rule && efc <= pair_rows;  // select_neighbors of the new elements answered by GPU masks
     std::vector<int32_t> h_elem;
-    PinnedBuf h_pack;
+    PinnedBuf &h_pack = g.scratch->h_pack;
 
     while (f < n_rows) {
         const int B = (int)std::min<int64_t>(big_next ? 1 : window, n_rows - f);
+        const double tP0 = now_ms();
         g.round++;
         n_rounds++;
         // ---- provisional placement: input row f+i -> element id g.n + i (valid while no duplicate commits) ----
@@ -722,8 +761,12 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
                 max_layers = std::max(max_layers, std::min(levels[f + i], g.entry_level) + 1);
             }
         }
+        const double tP1 = now_ms();
+        t_place += tP1 - tP0;
         int rc = upload_elements(e_base, e_base + B);
         if (rc) return rc;
+        const double tP2 = now_ms();
+        t_upload += tP2 - tP1;
 
         // ---- K2 on the GPU ----
         ScanConfig cfg;
@@ -747,6 +790,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         uint8_t *dpk = (uint8_t *)rb.out_pack.p;
         const uint8_t *hpk = (const uint8_t *)h_pack.p;
         CU_TRY(ix, rb.work.ensure(64));
+        t_cfg += now_ms() - tP2;
         h_elem.resize((size_t)B);
         for (int i = 0; i < B; i++) h_elem[(size_t)i] = (int32_t)(e_base + i);
         CU_TRY(ix, cudaMemcpyAsync(rb.elem_ids.p, h_elem.data(), (size_t)B * 4, cudaMemcpyHostToDevice, ix->stream));
@@ -776,6 +820,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         bp.stage_stride = cfg.L.stage_stride;
         bp.R = cfg.L.R;
         const double tg0 = now_ms();
+        t_prelude += tg0 - tP0;
         CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
         CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, cfg.wpb * 32, ix->stream));
         if (w_masks) {
@@ -1130,16 +1175,19 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         t_scatter += now_ms() - tS0;
 
         // input rows consumed this round: committed elements plus a merged duplicate
+        const double tT0 = now_ms();
         f += committed;
         if (!big_next) window = std::min(WINDOW_MAX, std::max(4, 2 * committed + 2));
         // host arrays beyond g.n hold provisional (uncommitted) elements; shrink the logical size back
         grow_host(g.n, g.n_upper);
+        t_tail += now_ms() - tT0;
     }
 
     if (getenv("PGVRX_BUILD_DEBUG"))
-        fprintf(stderr, "[pgvrx build] conflicts: log overflow %llu, W-not-full %llu, pending element acceptable %llu, order/removal %llu | ms: gpu %.0f (kernels %.0f) phaseA %.0f groups %.0f (build %.0f enum %.0f) simulate %.0f commit %.0f scatter %.0f\n",
+        fprintf(stderr, "[pgvrx build] conflicts: log overflow %llu, W-not-full %llu, pending element acceptable %llu, order/removal %llu | ms: gpu %.0f (kernels %.0f) phaseA %.0f groups %.0f (build %.0f enum %.0f) simulate %.0f commit %.0f scatter %.0f | setup %.0f prelude %.0f (place %.0f upload %.0f config+buffers %.0f) tail %.0f total %.0f\n",
                 (unsigned long long)why_overflow, (unsigned long long)why_notfull, (unsigned long long)why_pending,
-                (unsigned long long)why_order, gpu_ms, kernel_ms, t_phase_a, t_groups, t_g1, t_g2, t_sim, t_commit, t_scatter);
+                (unsigned long long)why_order, gpu_ms, kernel_ms, t_phase_a, t_groups, t_g1, t_g2, t_sim, t_commit, t_scatter, t_loop0 - t_start, t_prelude, t_place, t_upload, t_cfg, t_tail,
+                now_ms() - t_start);
     ix->n = g.n;
     ix->n_upper = g.n_upper;
     ix->entry = g.entry;
@@ -1175,6 +1223,27 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows, int64_t n_rows, const i
 int pgvrx_index_insert(pgvrx_index *ix, const void *rows, int64_t n_rows, const int32_t *levels, const uint64_t *heap_tids,
                        int32_t host_threads, pgvrx_build_stats *stats) {
     return run_inserts(ix, rows, n_rows, levels, heap_tids, host_threads, stats, true);
+}
+
+int pgvrx_index_set_heap_tids(pgvrx_index *ix, const uint64_t *heap_tids, const uint8_t *counts, int64_t n) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (!ix->loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "no graph loaded");
+    if (!heap_tids || !counts || n != ix->n) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "heap TID arrays must cover every element of the index");
+    for (int64_t i = 0; i < n; i++)
+        if (counts[i] > PGVRX_HEAPTIDS) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "an element holds at most 10 heap TIDs");
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    if (!ix->build) {
+        int avail = (int)std::max(1u, std::thread::hardware_concurrency());
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) avail = std::min(avail, (int)CPU_COUNT(&set));
+        int rc = mirror_from_device(ix, avail);
+        if (rc) return rc;
+    }
+    BuildState &g = *ix->build;
+    memcpy(g.tids.data(), heap_tids, (size_t)n * PGVRX_HEAPTIDS * 8);
+    memcpy(g.tid_cnt.data(), counts, (size_t)n);
+    return PGVRX_OK;
 }
 
 int pgvrx_index_graph_info(const pgvrx_index *ix, int64_t *n, int64_t *n_upper_rows, int64_t *entry, int32_t *entry_level) {

@@ -135,3 +135,33 @@ def test_insert_refused_on_flagged_index():
         ix.insert(rows[:5], np.zeros(5, np.int32))
     assert e.value.code == P.ERR_STATE
     ix.close()
+
+
+def test_insert_into_page_exported_index_respects_heap_tid_capacity():
+    # an index exported from pages keeps its heap TIDs (pgvrx_index_set_heap_tids): a duplicate row joins an element only
+    # while that element holds 1..9 TIDs (insert.rs:1159-1163), exactly as in the oracle that wrote the pages
+    rng = np.random.default_rng(11)
+    base = rng.standard_normal((150, 8)).astype(np.float32)
+    rows0 = np.concatenate([base, np.tile(base[3], (9, 1)), np.tile(base[4], (4, 1))])     # element 3: 10 TIDs, element 4: 5
+    lv0 = np.zeros(len(rows0), np.int32)
+    lv0[::19] = 1
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 8, m=4, ef_construction=16, tie_mode=O.TIE_TOTAL_ORDER)
+    o.build(rows0, lv0)
+    assert len(o.heap_tids(3)) == 10 and len(o.heap_tids(4)) == 5
+    g = P.export_pages(o.write_pages(), P.ELEM_F32)
+    ix = P.HnswIndex("vector_l2_ops", 8, m=4, ef_construction=16, capacity=400)
+    ix.load_graph(g["rows"], g["level"], g["adj0"], g["upper_base"], g["adj_up"], g["entry"])
+    # the fixture writes heap TID t as (block t >> 16, offset (t & 0xffff) + 1); undo the +1 to compare with the oracle
+    ix.set_heap_tids(np.where(g["heap_tids"] == np.uint64(0xFFFFFFFFFFFFFFFF), g["heap_tids"], g["heap_tids"] - np.uint64(1)),
+                     g["heap_tid_counts"])
+    new = np.concatenate([np.tile(base[3], (3, 1)), np.tile(base[4], (7, 1)), rng.standard_normal((40, 8)).astype(np.float32)])
+    lv1 = np.zeros(len(new), np.int32)
+    t0 = 1000
+    o.insert(new, lv1, base_tid=t0)
+    _insert_raw(ix, new, lv1, np.arange(t0, t0 + len(new), dtype=np.uint64))
+    gg = assert_same_graph(ix, o, "page-exported base")
+    for i in range(o.n):
+        t = o.heap_tids(i)
+        assert gg["heap_tid_counts"][i] == len(t), i
+        assert gg["heap_tids"][i, :len(t)].astype(np.int64).tolist() == t.tolist(), i
+    ix.close()
