@@ -475,7 +475,8 @@ typedef RustHeap<ScanCand, NearestCmp<ScanCand>> DiscHeap;
 
 std::vector<ScanCand> search_layer_scan(orc_index &ix, Visited &local_vis, std::vector<ScanCand> entry_points,
                                         size_t ef, int layer, const void *query, Visited *visited,
-                                        DiscHeap *discarded, bool add_entry_to_visited, orc_counters &ctr) {
+                                        DiscHeap *discarded, bool add_entry_to_visited, orc_counters &ctr,
+                                        const std::vector<char> *skip_count = nullptr /* vacuum repair only, :314 */) {
     Visited *vis = visited;
     if (!vis) { local_vis.reset(ix.elements.size()); vis = &local_vis; }   /* :317-319 */
     RustHeap<ScanCand, NearestCmp<ScanCand>> candidates(NearestCmp<ScanCand>{ix.total()});
@@ -485,7 +486,7 @@ std::vector<ScanCand> search_layer_scan(orc_index &ix, Visited &local_vis, std::
         if (add_entry_to_visited) { vis->insert(ep.idx); ctr.n_visited++; }
         candidates.push(ep);
         results.push(ep);
-        w_len++;
+        if (!skip_count || !(*skip_count)[(size_t)ep.idx]) w_len++;   /* :330-335 */
     }
     while (!candidates.empty()) {                                /* :338 */
         ScanCand c = candidates.pop();
@@ -518,8 +519,8 @@ std::vector<ScanCand> search_layer_scan(orc_index &ix, Visited &local_vis, std::
             ScanCand e{d, n.idx};
             candidates.push(e);                                  /* :414-419 */
             results.push(e);
-            w_len++;
-            if (w_len > ef) {                                    /* :421-429 */
+            if (!skip_count || !(*skip_count)[(size_t)e.idx]) w_len++;
+            if (w_len > ef) {                                    /* :421-429: pops the furthest of W whatever it is */
                 ScanCand ev = results.pop();
                 w_len--;
                 if (discarded) discarded->push(ev);
@@ -566,24 +567,27 @@ std::vector<ScanCand> get_scan_items(orc_index &ix, Visited &scratch, const void
  * ==================================================================================== */
 /* find_element_neighbors_on_disk (insert.rs:1021-1123), skip_set = None */
 std::vector<std::vector<ScanCand>> find_element_neighbors_on_disk(orc_index &ix, Visited &scratch, const void *query,
-                                                                  int new_level, orc_counters &ctr) {
+                                                                  int new_level, orc_counters &ctr,
+                                                                  const std::vector<char> *skip = nullptr,
+                                                                  int32_t entry_override = -1) {
     std::vector<std::vector<ScanCand>> nbl((size_t)new_level + 1);
-    int32_t e = (int32_t)ix.entry;
+    int32_t e = entry_override >= 0 ? entry_override : (int32_t)ix.entry;
     if (ix.elements[(size_t)e].deleted) return nbl;              /* :1036-1047 load_element => None */
     int entry_level = ix.elements[(size_t)e].level;
     std::vector<ScanCand> ep_list{ScanCand{ix.dist64(query, ix.row(e)), e}};
     ctr.n_dist++;
     for (int lc = entry_level; lc >= new_level + 1; lc--) {      /* :1052-1072 */
-        std::vector<ScanCand> w = search_layer_scan(ix, scratch, ep_list, 1, lc, query, nullptr, nullptr, true, ctr);
+        std::vector<ScanCand> w = search_layer_scan(ix, scratch, ep_list, 1, lc, query, nullptr, nullptr, true, ctr, skip);
         if (w.empty()) return nbl;
         ep_list = std::vector<ScanCand>{w.back()};
     }
     for (int lc = std::min(new_level, entry_level); lc >= 0; lc--) {   /* :1075-1120 */
         size_t lm = (size_t)layer_m(ix.m, lc);
-        std::vector<ScanCand> w = search_layer_scan(ix, scratch, ep_list, (size_t)ix.efc, lc, query, nullptr, nullptr,
-                                                    true, ctr);
-        std::vector<ScanCand> sel;                               /* :1110-1116 w is nearest-last: rev().take(lm) */
-        for (size_t i = w.size(); i-- > 0 && sel.size() < lm;) sel.push_back(w[i]);
+        size_t ef = (size_t)ix.efc + (skip ? 1 : 0);             /* :1080-1084 one more for the self-skip */
+        std::vector<ScanCand> w = search_layer_scan(ix, scratch, ep_list, ef, lc, query, nullptr, nullptr, true, ctr, skip);
+        std::vector<ScanCand> sel;                               /* :1101-1116 w is nearest-last: filter, rev().take(lm) */
+        for (size_t i = w.size(); i-- > 0 && sel.size() < lm;)
+            if (!skip || !(*skip)[(size_t)w[i].idx]) sel.push_back(w[i]);
         nbl[(size_t)lc] = std::move(sel);
         ep_list = std::move(w);
     }
@@ -686,6 +690,88 @@ void am_insert(orc_index &ix, const void *rowp, int level, int64_t heap_tid) {
     if (ix.entry < 0 || level > entry_level) ix.entry = new_idx; /* :1454-1470 */
 }
 
+/* ======================================================================================
+ * ambulkdelete on the flat arrays (src/index/vacuum.rs:816-842): pass 1 removes dead heap TIDs and collects the
+ * elements left without any (:118-216), pass 2 re-finds the neighbours of every live element that points at one of
+ * them or whose layer-0 list is not full (:228-281, :288-407, :413-640), pass 3 marks the emptied elements deleted
+ * (:655-790).  Single backend, no concurrent inserts; page placement is not involved.
+ * ==================================================================================== */
+bool needs_updated(const orc_index &ix, const std::vector<char> &deleted, int32_t idx) {   /* :228-281 */
+    const Element &e = ix.elements[(size_t)idx];
+    for (const auto &l : e.neighbors)
+        for (const Cand &c : l) if (deleted[(size_t)c.idx]) return true;
+    return (int)e.neighbors[0].size() < layer_m(ix.m, 0);
+}
+
+void repair_graph_element(orc_index &ix, Visited &scratch, const std::vector<char> &deleted, int32_t idx,
+                          int32_t entry, orc_counters &ctr) {                              /* :288-407 */
+    if (idx == entry) return;                                    /* :300-302 */
+    std::vector<char> skip = deleted;                            /* :338-339 deleted + self */
+    skip[(size_t)idx] = 1;
+    Element &e = ix.elements[(size_t)idx];
+    std::vector<std::vector<ScanCand>> nbl =
+        find_element_neighbors_on_disk(ix, scratch, ix.row(idx), e.level, ctr, &skip, entry);
+    for (int lc = 0; lc <= e.level; lc++) {                      /* :366-377 the whole tuple is rewritten */
+        std::vector<Cand> &l = e.neighbors[(size_t)lc];
+        l.clear();
+        for (const ScanCand &n : nbl[(size_t)lc]) l.push_back(Cand{(float)n.distance, n.idx});
+    }
+}
+
+int64_t bulk_delete(orc_index &ix, const int64_t *dead, int64_t n_dead, orc_counters &ctr) {
+    std::vector<int64_t> dead_sorted(dead, dead + n_dead);
+    std::sort(dead_sorted.begin(), dead_sorted.end());
+    auto is_dead = [&](int64_t t) { return std::binary_search(dead_sorted.begin(), dead_sorted.end(), t); };
+    const size_t n = ix.elements.size();
+    std::vector<char> deleted(n, 0);
+    bool any_deleted = false;
+    int64_t removed = 0;
+    int32_t highest_point = -1;
+    int highest_level = -1;
+    for (size_t i = 0; i < n; i++) {                             /* pass 1, :118-216 */
+        Element &e = ix.elements[i];
+        if (!e.heap_tids.empty()) {
+            std::vector<int64_t> keep;
+            for (int64_t t : e.heap_tids) { if (is_dead(t)) removed++; else keep.push_back(t); }
+            e.heap_tids.swap(keep);
+        }
+        if (e.heap_tids.empty()) { deleted[i] = 1; any_deleted = true; }       /* :188-190 (also elements deleted earlier) */
+        else if (e.level > highest_level && (int64_t)i != ix.entry) { highest_point = (int32_t)i; highest_level = e.level; }
+    }
+    if (!any_deleted) return removed;
+    Visited scratch;
+    /* pass 2: repair_graph_entry_point (:413-523) */
+    if (highest_point >= 0 && !ix.elements[(size_t)highest_point].deleted && needs_updated(ix, deleted, highest_point))
+        repair_graph_element(ix, scratch, deleted, highest_point, (int32_t)ix.entry, ctr);
+    if (ix.entry >= 0) {
+        if (deleted[(size_t)ix.entry]) {
+            ix.entry = highest_point;                            /* :464-484 (-1 clears the entry point) */
+        } else if (!ix.elements[(size_t)ix.entry].deleted && needs_updated(ix, deleted, (int32_t)ix.entry)) {
+            /* :497-514 searched from the highest point; with none, the element is its own entry and nothing happens */
+            int32_t from = highest_point >= 0 ? highest_point : (int32_t)ix.entry;
+            repair_graph_element(ix, scratch, deleted, (int32_t)ix.entry, from, ctr);
+        }
+    }
+    for (size_t i = 0; i < n; i++) {                             /* :549-640 every other live element, in page order */
+        Element &e = ix.elements[i];
+        if (e.heap_tids.empty() || e.deleted) continue;          /* :566-570, :580-592 */
+        if (!needs_updated(ix, deleted, (int32_t)i)) continue;
+        int entry_level = ix.entry >= 0 ? ix.elements[(size_t)ix.entry].level : -1;
+        if (ix.entry < 0) { ix.entry = (int32_t)i; continue; }   /* :606-625: no entry point: nothing to search, it becomes one */
+        repair_graph_element(ix, scratch, deleted, (int32_t)i, (int32_t)ix.entry, ctr);
+        if (e.level > entry_level) ix.entry = (int32_t)i;        /* :614-623 HNSW_UPDATE_ENTRY_GREATER */
+    }
+    for (size_t i = 0; i < n; i++) {                             /* pass 3, :655-790 */
+        Element &e = ix.elements[i];
+        if (e.deleted || !e.heap_tids.empty()) continue;
+        for (auto &l : e.neighbors) l.clear();
+        e.deleted = 1;
+        std::memset(ix.values.data() + i * ix.row_bytes, 0, ix.row_bytes);
+        e.version = e.version >= 15 ? 1 : (uint8_t)(e.version + 1);
+    }
+    return removed;
+}
+
 void add_counters(orc_counters &a, const orc_counters &b) {
     a.n_dist += b.n_dist; a.n_expand0 += b.n_expand0; a.n_expand_upper += b.n_expand_upper;
     a.n_visited += b.n_visited; a.n_pair += b.n_pair;
@@ -770,6 +856,10 @@ int64_t orc_insert(orc_index *ix, const void *rows, int64_t n, const int32_t *le
     const uint8_t *p = (const uint8_t *)rows;
     for (int64_t i = 0; i < n; i++) am_insert(*ix, p + (size_t)i * ix->row_bytes, levels[i], base_tid + i);
     return (int64_t)ix->elements.size();
+}
+
+int64_t orc_bulk_delete(orc_index *ix, const int64_t *dead_tids, int64_t n_dead) {
+    return bulk_delete(*ix, dead_tids, n_dead, ix->bc);
 }
 
 int64_t orc_n_elements(const orc_index *ix) { return (int64_t)ix->elements.size(); }

@@ -7,7 +7,9 @@
  *
  * Parity status: PINNED against every PG-free known answer the reference's own tests hold
  * for this path (see tests/test_oracle_known_answers.py: graph/mod.rs:538-778 unit tests,
- * vector.rs/halfvec.rs/bitvec.rs scalar distance answers, pg_regress expected orders).
+ * vector.rs/halfvec.rs/bitvec.rs scalar distance answers, pg_regress expected orders); the aminsert and
+ * ambulkdelete restatements by the reference's insert pg_tests and its TAP recall thresholds for the insert and
+ * vacuum paths (tests/test_oracle_live_index.py: tests/t/011, 013, 014, 022 on seeded data).
  * UNPINNED (third-party code absent from /root/reference):
  *   - tie order inside Rust std::collections::BinaryHeap (restated from its published
  *     algorithm as ORC_TIE_RUST_HEAP; the reference has no test that pins a tie order);
@@ -105,6 +107,10 @@ enum { ORC_VACUUM_REMOVE_HEAPTIDS = 1, /* vacuum.rs:118-190: element keeps its p
        ORC_VACUUM_MARK_DELETED = 2,    /* vacuum.rs:717-758: deleted = 1, lists and value cleared, version bumped */
        ORC_VACUUM_STALE_NEIGHBORS = 3  /* neighbour tuple whose version no longer matches (scan.rs:262)            */ };
 enum { ORC_ELEM_DELETED = 1, ORC_ELEM_NO_HEAPTIDS = 2 };
+/* ambulkdelete (src/index/vacuum.rs:816-842) with the heap's dead TIDs given as a list: removes them, repairs the
+ * lists of the live elements that pointed at emptied elements (skip-set searches, vacuum.rs:288-407), marks the
+ * emptied elements deleted.  Returns the number of heap TIDs removed. */
+int64_t orc_bulk_delete(orc_index *, const int64_t *dead_tids, int64_t n_dead);
 int  orc_vacuum_mark(orc_index *, int64_t id, int what);
 void orc_element_flags(const orc_index *, uint8_t *flags /* n */);
 

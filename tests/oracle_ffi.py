@@ -76,6 +76,7 @@ def lib():
         "orc_flat_topk": (i32, [i32, i32, i32, vp, i64, vp, i64, i32, vp, vp, i32]),
         "orc_write_pages": (i64, [vp, vp, i64]),
         "orc_vacuum_mark": (i32, [vp, i64, i32]),
+        "orc_bulk_delete": (i64, [vp, vp, i64]),
         "orc_element_flags": (None, [vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -210,6 +211,11 @@ class Oracle:
                                 _p(np.ascontiguousarray(g["adj0"], np.int32)),
                                 _p(np.ascontiguousarray(g["upper_base"], np.int32)), _p(adj_up),
                                 int(g["entry"]))
+
+    def bulk_delete(self, dead_tids):
+        """VACUUM: ambulkdelete with the given dead heap TIDs (src/index/vacuum.rs:816-842)."""
+        t = np.ascontiguousarray(dead_tids, np.int64)
+        return self.L.orc_bulk_delete(self.h, _p(t), len(t))
 
     def vacuum_mark(self, ids, what):
         """Put elements into a state a vacuum leaves on disk (VACUUM_* constants)."""

@@ -103,3 +103,32 @@ def test_flags_api_errors_and_build_refusal():
     b.set_element_flags(None)
     b.build(rows[100:], np.zeros(100, np.int32))
     b.close()
+
+
+@pytest.mark.parametrize("opclass,kind,dim", [("vector_l2_ops", "f32", 16), ("bit_hamming_ops", "bit", 64)])
+def test_scan_after_a_real_vacuum(opclass, kind, dim):
+    # the oracle's restatement of ambulkdelete (src/index/vacuum.rs: remove dead heap TIDs, repair with skip-set searches,
+    # mark deleted) produces the relation; the GPU loads its pages and must scan it like the oracle does
+    from helpers import oracle_index
+    m, efc, n = 6, 24, 3000
+    o = oracle_index(opclass, dim, make_rows(kind, n, dim, 41), m=m, efc=efc)
+    rng = np.random.default_rng(42)
+    dead = rng.permutation(n)[: n // 3]
+    assert o.bulk_delete(dead) == len(dead)
+    ix, g = load_from_pages(o, opclass, dim, m, efc)
+    assert g["n_deleted"] > 0 and (g["flags"] != 0).sum() == g["n_deleted"]
+    q = make_rows(kind, 200, dim, 43)
+    qn = ix.prepare_queries(q)
+    got = ix.search(q, k=10, ef_search=40, with_stats=True)
+    want = o.search_batch(qn, ef_search=40, k=10, with_counters=True)
+    assert_same_results(got, want, opclass + " after vacuum")
+    for key in ("n_dist", "n_expand0", "n_expand_upper", "n_visited"):
+        assert got[3][key] == want[3][key], key
+    assert not np.isin(got[0][got[0] >= 0], np.nonzero(g["flags"])[0]).any()
+    sc = ix.scan_begin(q[:8], ef_search=20, iterative_scan=P.ITER_RELAXED, max_scan_tuples=300)
+    got_i, got_d = sc.stream(None)
+    sc.close()
+    for i in range(8):
+        _, eids, ds, _ = o.scan_stream(qn[i], ef_search=20, iterative=O.ITER_RELAXED, max_scan_tuples=300)
+        assert np.array_equal(got_i[i], eids) and np.array_equal(got_d[i], ds.astype(np.float32))
+    ix.close()
