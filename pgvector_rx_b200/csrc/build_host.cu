@@ -503,7 +503,7 @@ static int mirror_from_device(pgvrx_index *ix, int nthreads) {
     BuildState *b = new BuildState();
     b->elem = ix->desc.elem_type; b->metric = ix->desc.metric; b->dim = ix->desc.dim; b->m = m; b->efc = ix->desc.ef_construction;
     b->row_bytes = ix->row_bytes;
-    ix->build = b;
+    struct Guard { BuildState *b; bool ok; ~Guard() { if (!ok) destroy_build_state(b); } } guard{b, false};   // a failed copy leaves no half-built mirror
     BuildState &g = *b;
     const int64_t n = ix->n, nu = ix->n_upper;
     g.n = n; g.n_upper = nu; g.entry = ix->entry; g.entry_level = ix->entry_level;
@@ -520,7 +520,7 @@ static int mirror_from_device(pgvrx_index *ix, int nthreads) {
     g.tids.assign((size_t)n * PGVRX_HEAPTIDS, ~0ull);
     g.tid_cnt.assign((size_t)n, 1);
     g.stamp.assign((size_t)n, 0);
-    if (n == 0) return PGVRX_OK;
+    if (n == 0) { guard.ok = true; ix->build = b; return PGVRX_OK; }
     CU_TRY(ix, cudaMemcpy2D(g.values.data(), g.row_bytes, ix->vectors.p, ix->row_stride, g.row_bytes, (size_t)n, cudaMemcpyDeviceToHost));
     CU_TRY(ix, cudaMemcpy(g.level.data(), ix->level.p, (size_t)n, cudaMemcpyDeviceToHost));
     CU_TRY(ix, cudaMemcpy(g.upper_base.data(), ix->upper_base.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -538,6 +538,8 @@ static int mirror_from_device(pgvrx_index *ix, int nthreads) {
             g.cnt(v, lc) = (uint8_t)c;
         }
     });
+    guard.ok = true;
+    ix->build = b;
     return PGVRX_OK;
 }
 
