@@ -36,7 +36,14 @@ struct Pages {
     const uint8_t *base;
     int64_t n;
     const uint8_t *page(uint32_t b) const { return base + (size_t)b * BLCKSZ; }
+    // pd_lower / pd_upper / pd_special of a sane page: 24 <= lower <= upper <= special <= 8192 (bufpage.h); anything else
+    // would send the line-pointer walk outside the page
+    bool header_ok(uint32_t b) const {
+        const uint16_t lower = rd16(page(b) + 12), upper = rd16(page(b) + 14), special = rd16(page(b) + 16);
+        return lower >= PAGE_HDR && lower <= upper && upper <= special && special <= BLCKSZ;
+    }
     uint16_t max_offset(uint32_t b) const {
+        if (!header_ok(b)) return 0;
         uint16_t lower = rd16(page(b) + 12);
         return lower <= PAGE_HDR ? 0 : (uint16_t)((lower - PAGE_HDR) / ITEMID);
     }
@@ -70,6 +77,7 @@ int walk_elements(const Pages &pg, Walk &w, int64_t *n_deleted) {
         if (seen[b]) return err("pgvector-rx: page chain loops");
         seen[b] = 1;
         if (!pg.is_hnsw(b)) return err("pgvector-rx: hnsw index is not valid");
+        if (!pg.header_ok(b)) return err("pgvector-rx: corrupt page header in the element chain");
         uint16_t mo = pg.max_offset(b);
         w.id_of[b].assign((size_t)mo + 1, -1);
         for (uint16_t o = 1; o <= mo; o++) {
@@ -101,6 +109,9 @@ int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, p
     info->dims = (int32_t)rd32(m + 8);
     info->m = rd16(m + 12);
     info->ef_construction = rd16(m + 14);
+    // reloption bounds (hnsw_constants.rs:53-65; dimensions up to the bit type's 64000): a meta page outside them is corrupt
+    if (info->m < 2 || info->m > 100 || info->ef_construction < 4 || info->ef_construction > 1000 || info->dims < 1 || info->dims > 64000)
+        return err("pgvector-rx: hnsw index is not valid (meta page parameters out of range)");
     Tid entry{rd32(m + 16), rd16(m + 20)};
     info->entry_level = (int16_t)rd16(m + 22);
     Walk w;
