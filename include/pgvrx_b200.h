@@ -153,6 +153,19 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
                        int32_t *adj0, int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids,
                        uint8_t *heap_tid_counts);
 
+/* ---- page writer: the arrays of pgvrx_index_export_graph -> the index relation's pages ------------------------- */
+/* The flush phase of ambuild (src/index/build.rs:545-821: create_meta_page, create_graph_pages,
+ * write_neighbor_tuples, update_meta_page) for a graph built by pgvrx_index_build: block 0 = meta page, element and
+ * neighbour tuples in element order from block 1, byte for byte what the reference writes from its in-memory build
+ * state -- so build + export + write = CREATE INDEX.  heap_tids / heap_tid_counts as pgvrx_index_export_graph returns
+ * them, each TID as (block << 16 | offset) with offset >= 1; NULL gives element i the synthetic TID of row i
+ * (block i >> 16, offset (i & 0xffff) + 1).  Call with pages == NULL to get the page count in *n_pages_out.
+ * Host code, no device needed. */
+int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_construction, int64_t n,
+                      const void *rows, const uint8_t *level, const int32_t *adj0, const int32_t *upper_base,
+                      const int32_t *adj_up, int64_t entry, const uint64_t *heap_tids,
+                      const uint8_t *heap_tid_counts, void *pages, int64_t cap_pages, int64_t *n_pages_out);
+
 /* ---- what a vacuum leaves on disk, as the scan sees it ------------------------------------------ */
 /* Per-element flags of an index that vacuum has touched (src/index/vacuum.rs:118-190,647-790):
  *   PGVRX_ELEM_DELETED      HnswElementTupleData.deleted != 0 -- load_element rejects the element before its

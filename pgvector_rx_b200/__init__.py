@@ -43,7 +43,7 @@ EXPORTS = [
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
     "pgvrx_pages_element_flags", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
-    "pgvrx_index_set_heap_tids",
+    "pgvrx_index_set_heap_tids", "pgvrx_pages_write",
 ]
 ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
 
@@ -122,6 +122,7 @@ def lib():
         "pgvrx_pages_inspect": (C.c_int, [vp, i64, i32, C.POINTER(PagesInfo)]),
         "pgvrx_pages_export": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_pages_element_flags": (C.c_int, [vp, i64, vp]),
+        "pgvrx_pages_write": (C.c_int, [i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, C.POINTER(i64)]),
         "pgvrx_index_set_element_flags": (C.c_int, [vp, vp, i64]),
         "pgvrx_index_build": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
         "pgvrx_index_insert": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
@@ -221,6 +222,32 @@ def export_pages(pages, elem):
                 adj_up=adj_up[:info.n_upper_rows], entry=info.entry, n=n, m=m, dims=info.dims,
                 ef_construction=info.ef_construction, entry_level=info.entry_level, heap_tids=tids,
                 heap_tid_counts=cnt)
+
+
+def write_pages(elem, dims, m, ef_construction, g, heap_tids=None, heap_tid_counts=None):
+    """Graph dict (export_graph() / export_pages() layout) -> the index relation's pages as the reference's flush
+    phase writes them (build.rs:545-821).  Returns a uint8 array of n_pages * 8192 bytes."""
+    L = lib()
+    n = int(g["n"])
+    rows = _rows(elem, dims, g["rows"]) if n else np.zeros((0, 1), np.uint8)
+    level = np.ascontiguousarray(g["level"], np.uint8)
+    adj0 = np.ascontiguousarray(g["adj0"], np.int32)
+    upper_base = np.ascontiguousarray(g["upper_base"], np.int32)
+    adj_up = np.ascontiguousarray(g["adj_up"], np.int32)
+    if adj_up.size == 0:
+        adj_up = np.zeros((1, m), np.int32)
+    t = None if heap_tids is None else np.ascontiguousarray(heap_tids, np.uint64)
+    c = None if heap_tid_counts is None else np.ascontiguousarray(heap_tid_counts, np.uint8)
+    npg = i64_out = C.c_int64(0)
+    args = (elem, dims, m, ef_construction, n, _p(rows), _p(level), _p(adj0), _p(upper_base), _p(adj_up), int(g["entry"]), _p(t), _p(c))
+    rc = L.pgvrx_pages_write(*args, None, 0, C.byref(npg))
+    if rc != OK:
+        raise PgvrxError(rc, L.pgvrx_last_error(None).decode())
+    pages = np.zeros(npg.value * 8192, np.uint8)
+    rc = L.pgvrx_pages_write(*args, _p(pages), npg.value, C.byref(i64_out))
+    if rc != OK:
+        raise PgvrxError(rc, L.pgvrx_last_error(None).decode())
+    return pages
 
 
 def heap_tid_stream(elem_ids, heap_tids, heap_tid_counts):

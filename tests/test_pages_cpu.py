@@ -117,3 +117,76 @@ def test_oracle_scan_semantics_on_vacuumed_index():
     o2, *_ = vacuumed_oracle("vector_l2_ops", "f32", 600, 12, 6, 24, delete_entry=True)
     ids, dists, counts = o2.search_batch(q, ef_search=40, k=10)
     assert (counts == 0).all() and (ids == -1).all()
+
+
+# ---- the product's page WRITER (pgvrx_pages_write): byte-identical to the oracle's independent writer -----------------
+def fixture_tids(o):
+    """Heap TIDs in the product's (block << 16 | offset) form, under the oracle fixture's convention
+    (heap TID t -> block t >> 16, offset (t & 0xffff) + 1)."""
+    n = o.n
+    tids = np.full((n, 10), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+    cnt = np.zeros(n, np.uint8)
+    for i in range(n):
+        t = o.heap_tids(i)
+        cnt[i] = len(t)
+        for j, v in enumerate(t):
+            tids[i, j] = ((int(v) >> 16) << 16) | ((int(v) & 0xffff) + 1)
+    return tids, cnt
+
+
+def write_matches(opclass, kind, n, dim, m, efc, levels=None, seed=5):
+    elem = P.OPCLASSES[opclass][0]
+    o = oracle_index(opclass, dim, make_rows(kind, n, dim, seed), m=m, efc=efc, levels=levels)
+    want = o.write_pages()
+    tids, cnt = fixture_tids(o)
+    got = P.write_pages(elem, dim, m, efc, o.export_graph(), tids, cnt)
+    assert len(got) == len(want), (len(got) // 8192, len(want) // 8192)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, "first difference in page %d at byte %d" % (bad[0] // 8192, bad[0] % 8192)
+    # and back through the exporter
+    g = P.export_pages(got, elem)
+    w = o.export_graph()
+    for k in ("level", "adj0", "upper_base", "adj_up"):
+        assert np.array_equal(g[k], w[k]), k
+    assert g["entry"] == w["entry"] and np.array_equal(g["heap_tid_counts"], cnt) and np.array_equal(g["heap_tids"], tids)
+    return got
+
+
+@pytest.mark.parametrize("opclass,kind,dim", [("vector_l2_ops", "f32", 128), ("vector_cosine_ops", "f32", 7),
+                                              ("halfvec_ip_ops", "f16", 33), ("bit_hamming_ops", "bit", 52),
+                                              ("bit_jaccard_ops", "bit", 1024)])
+def test_writer_matches_reference_flush(opclass, kind, dim):
+    write_matches(opclass, kind, 700, dim, 8, 32)
+
+
+def test_writer_page_layout_edges():
+    write_matches("vector_l2_ops", "f32", 300, 3, 4, 16)                 # many elements per page
+    pages = write_matches("vector_l2_ops", "f32", 40, 2000, 16, 64)      # neighbour tuple forced onto the next page
+    assert len(pages) // 8192 >= 2 * 40
+    lv = np.zeros(60, np.int32)
+    lv[[3, 17, 40]] = [9, 40, 2]
+    write_matches("vector_l2_ops", "f32", 60, 16, 32, 64, levels=lv)     # very high levels
+    # duplicates (several heap TIDs per element) and the empty index
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 3)
+    o.build(np.tile(np.array([1, 2, 3], np.float32), (25, 1)), np.zeros(25, np.int32))
+    tids, cnt = fixture_tids(o)
+    assert np.array_equal(P.write_pages(P.ELEM_F32, 3, 16, 64, o.export_graph(), tids, cnt), o.write_pages())
+    e = O.Oracle(O.ELEM_F32, O.L2SQ, 3)
+    empty = dict(n=0, rows=np.zeros((0, 3), np.float32), level=np.zeros(0, np.uint8), adj0=np.zeros((0, 32), np.int32),
+                 upper_base=np.zeros(0, np.int32), adj_up=np.zeros((0, 16), np.int32), entry=-1)
+    assert np.array_equal(P.write_pages(P.ELEM_F32, 3, 16, 64, empty), e.write_pages())
+
+
+def test_writer_rejects_bad_input():
+    o = oracle_index("vector_l2_ops", 8, make_rows("f32", 50, 8, 1), m=4, efc=16)
+    g = o.export_graph()
+    bad = dict(g)
+    bad["adj0"] = g["adj0"].copy()
+    bad["adj0"][0, 0] = 50
+    with pytest.raises(P.PgvrxError):
+        P.write_pages(P.ELEM_F32, 8, 4, 16, bad)
+    with pytest.raises(P.PgvrxError):
+        P.write_pages(P.ELEM_F32, 8, 1, 16, g)                          # m below the reloption minimum
+    with pytest.raises(P.PgvrxError) as e:
+        P.write_pages(P.ELEM_F32, 2100, 4, 16, dict(g, rows=np.zeros((50, 2100), np.float32)))
+    assert "index tuple too large" in str(e.value)                       # build.rs:612-614
