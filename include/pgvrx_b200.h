@@ -176,7 +176,8 @@ int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_con
  * A neighbour tuple whose version or count no longer matches its element (scan.rs:262) exports as empty lists.
  * pgvrx_pages_element_flags fills flags[n_elements] from the pages; pgvrx_index_set_element_flags hands them to a
  * loaded index (NULL clears; all-zero flags keep the flag-free kernels).  The in-memory build path has no such
- * elements and refuses to extend an index that carries flags. */
+ * elements and refuses to extend an index that carries flags.  The flags are an index-scan matter: the exact paths
+ * (pgvrx_flat_topk, pgvrx_rerank) stand for a scan of the TABLE and read whatever rows the caller loaded. */
 #define PGVRX_ELEM_DELETED 1
 #define PGVRX_ELEM_NO_HEAPTIDS 2
 int pgvrx_pages_element_flags(const void *pages, int64_t n_pages, uint8_t *flags);
