@@ -41,3 +41,24 @@ def test_tie_heavy_data_modes_are_tie_equivalent():
         for i in range(20):
             for j in range(10):
                 assert O.distance(O.ELEM_BIT, O.HAMMING, 64, q[i], rows[r[0][i, j]]) == r[1][i, j]
+
+
+def test_live_index_paths_agree_across_tie_modes_on_tie_free_data():
+    # aminsert and ambulkdelete restated under both tie policies: with distinct distances the reference's own heap
+    # order (RUST_HEAP) and the GPU's (distance, id) order must leave the same graph
+    from pgvector_rx_b200 import datasets as D
+    rows = make_rows("f32", 3000, 16, 3)
+    lv = D.hnsw_levels(3000, 8, 4)
+    out = []
+    for tie in (O.TIE_RUST_HEAP, O.TIE_TOTAL_ORDER):
+        o = O.Oracle(O.ELEM_F32, O.L2SQ, 16, m=8, ef_construction=32, tie_mode=tie)
+        o.build(rows[:1500], lv[:1500])
+        o.insert(rows[1500:], lv[1500:], base_tid=1500)
+        g1 = o.export_graph()
+        o.bulk_delete(np.arange(0, 3000, 3))
+        out.append((g1, o.export_graph(), o.element_flags(), o.entry))
+    (a1, a2, fa, ea), (b1, b2, fb, eb) = out
+    for k in ("level", "adj0", "upper_base", "adj_up"):
+        assert np.array_equal(a1[k], b1[k]), ("after insert", k)
+        assert np.array_equal(a2[k], b2[k]), ("after vacuum", k)
+    assert np.array_equal(fa, fb) and ea == eb and a1["entry"] == b1["entry"]
