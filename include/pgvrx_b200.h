@@ -229,6 +229,29 @@ int pgvrx_index_build(pgvrx_index *idx, const void *rows, int64_t n_rows, const 
 int pgvrx_index_insert(pgvrx_index *idx, const void *rows, int64_t n_rows, const int32_t *levels,
                        const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats);
 
+/* ---- VACUUM: ambulkdelete (src/index/vacuum.rs:816-842) ----------------------------------------- */
+typedef struct {
+    uint64_t n_heap_tids_removed;  /* pass 1 (vacuum.rs:118-216)                                              */
+    uint64_t n_elements_deleted;   /* pass 3: elements left without heap TIDs, now flagged deleted (vacuum.rs:655-790) */
+    uint64_t n_elements_repaired;  /* pass 2: elements whose lists were re-found (vacuum.rs:288-407)           */
+    uint64_t n_rounds;             /* GPU search rounds                                                       */
+    uint64_t n_searched;           /* repair searches run (>= repaired: conflicts re-run)                      */
+    uint64_t n_conflicts;          /* speculative searches discarded: they had expanded an element repaired
+                                      earlier in the same round                                               */
+    double   kernel_ms, total_ms;
+} pgvrx_vacuum_stats;
+/* dead_tids: the heap TIDs the table's vacuum reports dead, in the same (block << 16 | offset) form the index holds.
+ * Removes them, re-finds the neighbour lists of every live element that pointed at an emptied element or whose layer-0
+ * list is not full -- searches with the skip set, ef_construction + 1 and search_layer_disk's skip_count bookkeeping
+ * (scan.rs:314-336,416-429), run on the GPU in batches and committed in element order -- replaces a deleted entry point
+ * by the highest remaining element, and marks the emptied elements deleted.  The result equals the reference's
+ * sequential vacuum (asserted against the oracle).  Afterwards the index carries element flags
+ * (pgvrx_index_element_flags reads them back) and scans apply them; pgvrx_index_export_graph returns the repaired
+ * lists.  Needs the heap TIDs: a handle built here, or loaded + pgvrx_index_set_heap_tids. */
+int pgvrx_index_vacuum(pgvrx_index *idx, const uint64_t *dead_tids, int64_t n_dead, int32_t host_threads,
+                       pgvrx_vacuum_stats *stats);
+int pgvrx_index_element_flags(pgvrx_index *idx, uint8_t *flags, int64_t n);
+
 /* Heap TIDs of a loaded index (n x 10 as block << 16 | offset with ~0 padding, and n counts -- the arrays
  * pgvrx_pages_export fills): lets pgvrx_index_insert apply the duplicate rule's capacity test (an element takes a
  * duplicate's TID only while it holds 1..9, insert.rs:1159-1163) and pgvrx_index_export_graph return them.  Without

@@ -43,7 +43,7 @@ EXPORTS = [
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
     "pgvrx_pages_element_flags", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
-    "pgvrx_index_set_heap_tids", "pgvrx_pages_write",
+    "pgvrx_index_set_heap_tids", "pgvrx_pages_write", "pgvrx_index_vacuum", "pgvrx_index_element_flags",
 ]
 ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
 
@@ -72,6 +72,15 @@ class BuildStats(C.Structure):
                 ("n_pair_gpu", C.c_uint64), ("n_validation_dist", C.c_uint64), ("n_host_dist", C.c_uint64),
                 ("gpu_ms", C.c_double), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("host_threads", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class VacuumStats(C.Structure):
+    _fields_ = [("n_heap_tids_removed", C.c_uint64), ("n_elements_deleted", C.c_uint64), ("n_elements_repaired", C.c_uint64),
+                ("n_rounds", C.c_uint64), ("n_searched", C.c_uint64), ("n_conflicts", C.c_uint64),
+                ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -127,6 +136,8 @@ def lib():
         "pgvrx_index_build": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
         "pgvrx_index_insert": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
         "pgvrx_index_set_heap_tids": (C.c_int, [vp, vp, vp, i64]),
+        "pgvrx_index_vacuum": (C.c_int, [vp, vp, i64, i32, C.POINTER(VacuumStats)]),
+        "pgvrx_index_element_flags": (C.c_int, [vp, vp, i64]),
         "pgvrx_index_graph_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
         "pgvrx_index_export_graph": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_search_batch": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(SearchStats)]),
@@ -307,6 +318,18 @@ class HnswIndex:
         adj_up = np.ascontiguousarray(adj_up, np.int32).reshape(-1, self.m)
         self._check(self.L.pgvrx_index_load_graph(self.h, _p(rows), len(rows), _p(level), _p(adj0), _p(upper_base),
                                                   _p(adj_up) if len(adj_up) else None, len(adj_up), int(entry)))
+
+    def vacuum(self, dead_tids, host_threads=0):
+        """VACUUM: ambulkdelete (src/index/vacuum.rs:816-842) with the heap's dead TIDs.  Returns statistics."""
+        t = np.ascontiguousarray(dead_tids, np.uint64)
+        st = VacuumStats()
+        self._check(self.L.pgvrx_index_vacuum(self.h, _p(t), len(t), host_threads, C.byref(st)))
+        return st.as_dict()
+
+    def element_flags(self):
+        f = np.zeros(self.graph_info()["n"], np.uint8)
+        self._check(self.L.pgvrx_index_element_flags(self.h, _p(f), len(f)))
+        return f
 
     def set_heap_tids(self, heap_tids, counts):
         """Heap TIDs of a loaded index (the n x 10 / n arrays of export_pages / export_graph); see the header."""

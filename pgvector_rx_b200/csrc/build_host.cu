@@ -184,6 +184,7 @@ struct BuildState {
     std::vector<uint8_t> cnt_up;
     std::vector<uint64_t> tids;         // n x 10 (build.rs:245)
     std::vector<uint8_t> tid_cnt;
+    std::vector<uint8_t> del;           // HnswElementTupleData.deleted (set by pgvrx_index_vacuum's last pass)
     std::vector<uint32_t> stamp;        // per node: round in which one of its lists was last modified
     uint32_t round = 0;
     std::atomic<uint64_t> n_pair{0};
@@ -490,6 +491,7 @@ static void reserve_mirror(BuildState &g, int64_t cap) {
         g.cnt0.reserve(c);
         g.tids.reserve(c * PGVRX_HEAPTIDS);
         g.tid_cnt.reserve(c);
+        g.del.reserve(c);
         g.stamp.reserve(c);
     } catch (const std::bad_alloc &) {
         // a capacity far beyond what is ever inserted: fall back to the vectors' own geometric growth
@@ -519,6 +521,7 @@ static int mirror_from_device(pgvrx_index *ix, int nthreads) {
     g.cnt_up.resize((size_t)nu, 0);
     g.tids.assign((size_t)n * PGVRX_HEAPTIDS, ~0ull);
     g.tid_cnt.assign((size_t)n, 1);
+    g.del.assign((size_t)n, 0);
     g.stamp.assign((size_t)n, 0);
     if (n == 0) { guard.ok = true; ix->build = b; return PGVRX_OK; }
     CU_TRY(ix, cudaMemcpy2D(g.values.data(), g.row_bytes, ix->vectors.p, ix->row_stride, g.row_bytes, (size_t)n, cudaMemcpyDeviceToHost));
@@ -527,6 +530,14 @@ static int mirror_from_device(pgvrx_index *ix, int nthreads) {
     CU_TRY(ix, cudaMemcpy(g.adj0.data(), ix->adj0.p, (size_t)n * l0 * 4, cudaMemcpyDeviceToHost));
     if (nu > 0) CU_TRY(ix, cudaMemcpy(g.adj_up.data(), ix->adj_up.p, (size_t)nu * m * 4, cudaMemcpyDeviceToHost));
     for (int64_t e = 0; e < n; e++) g.tids[(size_t)e * PGVRX_HEAPTIDS] = (uint64_t)e;
+    if (ix->has_flags) {                 // an index a vacuum has touched before: deleted / emptied elements
+        std::vector<uint8_t> f((size_t)n);
+        CU_TRY(ix, cudaMemcpy(f.data(), ix->flags.p, (size_t)n, cudaMemcpyDeviceToHost));
+        for (int64_t e = 0; e < n; e++) {
+            g.del[(size_t)e] = (f[(size_t)e] & PGVRX_ELEM_DELETED) ? 1 : 0;
+            if (f[(size_t)e] & PGVRX_ELEM_NO_HEAPTIDS) { g.tid_cnt[(size_t)e] = 0; g.tids[(size_t)e * PGVRX_HEAPTIDS] = ~0ull; }
+        }
+    }
     Pool pool(nthreads);
     pool.parallel_for(n, [&](int64_t v) {
         for (int lc = 0; lc <= g.level[(size_t)v]; lc++) {
@@ -616,6 +627,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         g.cnt_up.resize((size_t)up_new, 0);
         g.tids.resize((size_t)n_new * PGVRX_HEAPTIDS, ~0ull);
         g.tid_cnt.resize((size_t)n_new, 0);
+        g.del.resize((size_t)n_new, 0);
         g.stamp.resize((size_t)n_new, 0);
     };
 
@@ -1225,6 +1237,344 @@ int pgvrx_index_build(pgvrx_index *ix, const void *rows, int64_t n_rows, const i
 int pgvrx_index_insert(pgvrx_index *ix, const void *rows, int64_t n_rows, const int32_t *levels, const uint64_t *heap_tids,
                        int32_t host_threads, pgvrx_build_stats *stats) {
     return run_inserts(ix, rows, n_rows, levels, heap_tids, host_threads, stats, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// VACUUM: ambulkdelete (src/index/vacuum.rs:816-842) on the host mirror + device graph.
+//   pass 1 (vacuum.rs:118-216)  dead heap TIDs removed; elements left with none form the skip set
+//   pass 2 (vacuum.rs:413-640)  every live element that points at one of them, or whose layer-0 list is not full
+//                               (vacuum.rs:228-281), gets all of its lists re-found: skip-set searches on the GPU in
+//                               speculative batches (hnsw_repair_search_kernel), committed in element order.  A repair
+//                               rewrites only the element's OWN lists, so a later search of the same batch is the one a
+//                               sequential run would have made unless it expanded an element repaired earlier in the
+//                               batch (the kernel's expansion log says so); then the round stops there and the rest is
+//                               searched again.
+//   pass 3 (vacuum.rs:655-790)  emptied elements are marked deleted, their lists and values cleared
+// ------------------------------------------------------------------------------------------------
+int pgvrx_index_vacuum(pgvrx_index *ix, const uint64_t *dead_tids, int64_t n_dead, int32_t host_threads, pgvrx_vacuum_stats *stats) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n_dead < 0 || (n_dead > 0 && !dead_tids)) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null dead TID list");
+    if (!ix->loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "no graph loaded");
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    CU_TRY(ix, cudaDeviceSynchronize());              // scans in flight read the lists this call rewrites
+    int avail = (int)std::max(1u, std::thread::hardware_concurrency());
+    {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) avail = std::min(avail, (int)CPU_COUNT(&set));
+    }
+    const int nthreads = host_threads > 0 ? host_threads : avail;
+    if (!ix->build) {
+        int rc = mirror_from_device(ix, nthreads);
+        if (rc) return rc;
+    }
+    BuildState &g = *ix->build;
+    const double t_start = now_ms();
+    const int m = g.m, efc = g.efc, l0 = 2 * m;
+    const int64_t n = g.n;
+
+    // ---- pass 1 ----
+    std::vector<uint64_t> dead(dead_tids, dead_tids + n_dead);
+    std::sort(dead.begin(), dead.end());
+    std::vector<char> deleted((size_t)n, 0);
+    bool any_deleted = false;
+    uint64_t removed = 0;
+    int64_t hp = -1;
+    int hp_level = -1;
+    for (int64_t i = 0; i < n; i++) {
+        uint8_t &cnt = g.tid_cnt[(size_t)i];
+        uint64_t *t = &g.tids[(size_t)i * PGVRX_HEAPTIDS];
+        if (cnt > 0) {
+            int keep = 0;
+            for (int k = 0; k < cnt; k++) {
+                if (std::binary_search(dead.begin(), dead.end(), t[k])) removed++;
+                else t[keep++] = t[k];
+            }
+            for (int k = keep; k < PGVRX_HEAPTIDS; k++) t[k] = ~0ull;
+            cnt = (uint8_t)keep;
+        }
+        if (cnt == 0) { deleted[(size_t)i] = 1; any_deleted = true; }
+        else if ((int)g.level[(size_t)i] > hp_level && i != g.entry) { hp = i; hp_level = g.level[(size_t)i]; }
+    }
+    if (stats) stats->n_heap_tids_removed = removed;
+    if (!any_deleted) { if (stats) stats->total_ms = now_ms() - t_start; return PGVRX_OK; }
+
+    // the kernels' view of the skip set and of elements deleted by earlier vacuums
+    std::vector<uint8_t> flags((size_t)n);
+    auto upload_flags = [&]() -> int {
+        for (int64_t i = 0; i < n; i++)
+            flags[(size_t)i] = (uint8_t)((g.del[(size_t)i] ? PGVRX_ELEM_DELETED : 0) | (g.tid_cnt[(size_t)i] == 0 ? PGVRX_ELEM_NO_HEAPTIDS : 0));
+        CU_TRY(ix, ix->flags.ensure(std::max<size_t>(16, (size_t)ix->desc.capacity)));
+        CU_TRY(ix, cudaMemcpy(ix->flags.p, flags.data(), (size_t)n, cudaMemcpyHostToDevice));
+        ix->has_flags = true;
+        return PGVRX_OK;
+    };
+    int rc = upload_flags();
+    if (rc) return rc;
+
+    // ---- pass 2 ----
+    auto needs_updated = [&](int64_t i) -> bool {                 // vacuum.rs:228-281
+        for (int lc = 0; lc <= g.level[(size_t)i]; lc++) {
+            const int32_t *ids = g.ids(i, lc);
+            const int c = g.cnt(i, lc);
+            for (int t = 0; t < c; t++) if (deleted[(size_t)ids[t]]) return true;
+        }
+        return g.cnt0[(size_t)i] < l0;
+    };
+    if (!g.scratch) g.scratch = new RoundScratch();
+    RoundBuffers &rb = g.scratch->rb;
+    PinnedBuf &h_pack = g.scratch->h_pack;
+    const int ef = efc + 1;                                       // insert.rs:1080-1084
+    const int tail_cap = std::max(64, 1023 - ef);                 // room for skip members and boundary ties
+    const int w_pitch = ef + tail_cap;
+    const int rs_cap = std::max(256, 6 * ef + 64);
+    const int rs_ent = 3 + (l0 + 31) / 32;
+    uint64_t n_rounds = 0, n_searched = 0, n_conflicts = 0, n_repaired = 0;
+    double kernel_ms = 0.0;
+    std::vector<int64_t> sc_off0, sc_offu;
+    std::vector<int32_t> sc_rows0, sc_rowsu;
+    auto queue_row = [&](int64_t v, int lc) {
+        if (lc == 0) {
+            sc_off0.push_back(v * l0);
+            sc_rows0.insert(sc_rows0.end(), &g.adj0[(size_t)v * l0], &g.adj0[(size_t)v * l0] + l0);
+        } else {
+            int64_t r = g.upper_base[(size_t)v] + lc - 1;
+            sc_offu.push_back(r * m);
+            sc_rowsu.insert(sc_rowsu.end(), &g.adj_up[(size_t)r * m], &g.adj_up[(size_t)r * m] + m);
+        }
+    };
+    auto flush_scatter = [&]() -> int {
+        for (int pass = 0; pass < 2; pass++) {
+            std::vector<int64_t> &off = pass == 0 ? sc_off0 : sc_offu;
+            std::vector<int32_t> &dat = pass == 0 ? sc_rows0 : sc_rowsu;
+            if (off.empty()) continue;
+            const int row_len = pass == 0 ? l0 : m;
+            CU_TRY(ix, rb.sc_off.ensure(off.size() * 8));
+            CU_TRY(ix, rb.sc_rows.ensure(dat.size() * 4));
+            CU_TRY(ix, cudaMemcpyAsync(rb.sc_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, cudaMemcpyAsync(rb.sc_rows.p, dat.data(), dat.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+            CU_TRY(ix, launch_scatter_rows((int32_t *)(pass == 0 ? ix->adj0.p : ix->adj_up.p), (const int64_t *)rb.sc_off.p,
+                                           (const int32_t *)rb.sc_rows.p, row_len, (int)off.size(), ix->stream));
+            CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+            off.clear();
+            dat.clear();
+        }
+        return PGVRX_OK;
+    };
+
+    // one GPU round: searches for `batch` from `entry`; commits a prefix in order; returns how many were committed
+    std::vector<int32_t> h_elem;
+    auto repair_round = [&](const std::vector<int64_t> &batch, int64_t entry, int *n_committed) -> int {
+        const int B = (int)batch.size();
+        *n_committed = 0;
+        g.round++;
+        n_rounds++;
+        n_searched += (uint64_t)B;
+        int max_layers = 1;
+        for (int64_t e : batch) max_layers = std::max(max_layers, (int)g.level[(size_t)e] + 1);
+        ScanConfig cfg;
+        const uint32_t vis_entries = pgvrx_pow2_at_least(std::min<uint64_t>((uint64_t)ef * 2 * m * 4 * 16, std::max<uint64_t>(1024, (uint64_t)n * 2)));
+        int rcc = pgvrx_make_config(ix, ef, tail_cap, vis_entries, B, ix->sm_count, true, &cfg);
+        if (rcc) return rcc;
+        int occ = 0;
+        CU_TRY(ix, repair_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, cfg.smem_block, cfg.wpb * 32, &occ));
+        if (occ < 1) return pgvrx_fail(ix, PGVRX_ERR_UNSUPPORTED, "repair search kernel does not fit on an SM");
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((B + cfg.wpb - 1) / cfg.wpb, (int64_t)ix->sm_count * occ));
+        CU_TRY(ix, rb.vis.ensure((size_t)grid * cfg.wpb * cfg.vis_entries * 4));
+        CU_TRY(ix, rb.elem_ids.ensure((size_t)B * 4));
+        CU_TRY(ix, rb.work.ensure(64));
+        size_t po = 0;
+        auto carve = [&](size_t bytes) { const size_t o = po; po += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_wids = carve((size_t)B * max_layers * w_pitch * 4), o_wd = carve((size_t)B * max_layers * w_pitch * 4);
+        const size_t o_wcnt = carve((size_t)B * max_layers * 4), o_rs = carve((size_t)B * rs_cap * rs_ent * 4);
+        const size_t o_rscnt = carve((size_t)B * 4), o_status = carve((size_t)B * 4), o_ctr = carve((size_t)B * 16);
+        CU_TRY(ix, rb.out_pack.ensure(po));
+        CU_TRY(ix, h_pack.ensure(po));
+        uint8_t *dpk = (uint8_t *)rb.out_pack.p;
+        const uint8_t *hpk = (const uint8_t *)h_pack.p;
+        h_elem.resize((size_t)B);
+        for (int i = 0; i < B; i++) h_elem[(size_t)i] = (int32_t)batch[(size_t)i];
+        CU_TRY(ix, cudaMemcpyAsync(rb.elem_ids.p, h_elem.data(), (size_t)B * 4, cudaMemcpyHostToDevice, ix->stream));
+        CU_TRY(ix, cudaMemsetAsync(rb.work.p, 0, 64, ix->stream));
+        ix->n = n;
+        ix->entry = entry;
+        ix->entry_level = entry >= 0 ? g.level[(size_t)entry] : -1;
+        GraphView gv = pgvrx_view_of(ix);
+        RepairParams rp;
+        rp.elem_ids = (const int32_t *)rb.elem_ids.p;
+        rp.n_pending = B;
+        rp.ef = ef;
+        rp.tail_cap = tail_cap;
+        rp.max_layers = max_layers;
+        rp.w_pitch = w_pitch;
+        rp.w_ids = (int32_t *)(dpk + o_wids);
+        rp.w_dists = (float *)(dpk + o_wd);
+        rp.w_counts = (int32_t *)(dpk + o_wcnt);
+        rp.rs_log = (int32_t *)(dpk + o_rs);
+        rp.rs_cap = rs_cap;
+        rp.rs_ent = rs_ent;
+        rp.rs_counts = (int32_t *)(dpk + o_rscnt);
+        rp.out_status = (uint32_t *)(dpk + o_status);
+        rp.out_ctr = (uint32_t *)(dpk + o_ctr);
+        rp.vis_base = (uint32_t *)rb.vis.p;
+        rp.vis_entries = cfg.vis_entries;
+        rp.work_counter = (int *)rb.work.p;
+        rp.stage_stride = cfg.L.stage_stride;
+        rp.R = cfg.L.R;
+        CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
+        CU_TRY(ix, launch_repair_search(ix->desc.elem_type, ix->desc.metric, gv, rp, grid, cfg.smem_block, cfg.wpb * 32, ix->stream));
+        CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));
+        CU_TRY(ix, cudaMemcpyAsync(h_pack.p, rb.out_pack.p, po, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+        {
+            float kms = 0.0f;
+            CU_TRY(ix, cudaEventElapsedTime(&kms, ix->ev0, ix->ev1));
+            kernel_ms += kms;
+        }
+        const int32_t *h_wids = (const int32_t *)(hpk + o_wids);
+        const float *h_wd = (const float *)(hpk + o_wd);
+        const int32_t *h_wcnt = (const int32_t *)(hpk + o_wcnt);
+        const int32_t *h_rs = (const int32_t *)(hpk + o_rs);
+        const int32_t *h_rscnt = (const int32_t *)(hpk + o_rscnt);
+        const uint32_t *h_status = (const uint32_t *)(hpk + o_status);
+        const int entry_level = entry >= 0 ? g.level[(size_t)entry] : -1;
+        for (int j = 0; j < B; j++) {
+            const int64_t e = batch[(size_t)j];
+            if (h_status[(size_t)j] != 0)
+                return pgvrx_fail(ix, PGVRX_ERR_UNSUPPORTED, "vacuum repair search ran out of scratch (skip set too dense around an element)");
+            if (j > 0) {                                          // did it expand an element repaired earlier in this round?
+                bool valid = h_rscnt[(size_t)j] <= rs_cap;
+                const int32_t *rs = &h_rs[(size_t)j * rs_cap * rs_ent];
+                for (int t = 0; valid && t < h_rscnt[(size_t)j]; t++)
+                    if (g.stamp[(size_t)rs[(size_t)rs_ent * t]] == g.round) valid = false;
+                if (!valid) { n_conflicts++; break; }
+            }
+            // vacuum.rs:366-377: every layer's list := the nearest lm of W that are not in the skip set (insert.rs:1101-1116)
+            const int lv = g.level[(size_t)e];
+            for (int lc = 0; lc <= lv; lc++) {
+                int32_t *ids = g.ids(e, lc);
+                float *ds = g.dists(e, lc);
+                const int lm = g.lm(lc);
+                int c = 0;
+                if (lc <= entry_level && lc < max_layers) {
+                    const int cntw = h_wcnt[(size_t)j * max_layers + lc];
+                    const size_t o = ((size_t)j * max_layers + lc) * w_pitch;
+                    for (int t = 0; t < cntw && c < lm; t++) {
+                        const int32_t x = h_wids[o + t];
+                        if (x == (int32_t)e || deleted[(size_t)x]) continue;
+                        ids[c] = x;
+                        ds[c] = h_wd[o + t];
+                        c++;
+                    }
+                }
+                for (int t = c; t < lm; t++) ids[t] = -1;
+                g.cnt(e, lc) = (uint8_t)c;
+                queue_row(e, lc);
+            }
+            g.stamp[(size_t)e] = g.round;
+            n_repaired++;
+            (*n_committed)++;
+            if (lv > entry_level) {                               // vacuum.rs:614-623: it becomes the entry point
+                g.entry = e;
+                g.entry_level = lv;
+                break;
+            }
+        }
+        return flush_scatter();
+    };
+
+    // repair_graph_entry_point (vacuum.rs:413-523)
+    int done = 0;
+    if (hp >= 0 && !g.del[(size_t)hp] && needs_updated(hp) && g.entry >= 0) {
+        // (the highest point never outranks the entry point here: the entry-level update below applies to the main loop only)
+        const int64_t save_entry = g.entry;
+        const int save_level = g.entry_level;
+        rc = repair_round(std::vector<int64_t>{hp}, g.entry, &done);
+        if (rc) return rc;
+        g.entry = save_entry;
+        g.entry_level = save_level;
+    }
+    if (g.entry >= 0) {
+        if (deleted[(size_t)g.entry]) {                           // vacuum.rs:464-484
+            g.entry = hp;
+            g.entry_level = hp >= 0 ? g.level[(size_t)hp] : -1;
+        } else if (!g.del[(size_t)g.entry] && needs_updated(g.entry) && hp >= 0) {   // vacuum.rs:486-514 (without a highest point
+            const int64_t save_entry = g.entry;                                      //  the element is its own entry: no-op)
+            const int save_level = g.entry_level;
+            rc = repair_round(std::vector<int64_t>{g.entry}, hp, &done);
+            if (rc) return rc;
+            g.entry = save_entry;
+            g.entry_level = save_level;
+        }
+    }
+    // every other live element, in element (= page) order (vacuum.rs:549-640)
+    int window = 8;
+    int64_t pos = 0;
+    std::vector<int64_t> batch;
+    while (pos < n) {
+        batch.clear();
+        int64_t scan = pos;
+        while (scan < n && (int)batch.size() < window) {
+            const int64_t i = scan++;
+            if (g.tid_cnt[(size_t)i] == 0 || g.del[(size_t)i] || i == g.entry) continue;      // vacuum.rs:566-570, :300-302
+            if (!needs_updated(i)) continue;
+            batch.push_back(i);
+        }
+        if (batch.empty()) break;
+        if (g.entry < 0) return pgvrx_fail(ix, PGVRX_ERR_STATE, "live elements but no entry point");
+        rc = repair_round(batch, g.entry, &done);
+        if (rc) return rc;
+        // elements before the first uncommitted one are finished; the rest is looked at again
+        pos = done < (int)batch.size() ? batch[(size_t)done] : scan;
+        window = std::min(512, std::max(8, 2 * done + 2));
+    }
+
+    // ---- pass 3 (vacuum.rs:655-790) ----
+    std::vector<uint8_t> zero_row(ix->row_stride, 0);
+    uint64_t n_marked = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (g.del[(size_t)i] || g.tid_cnt[(size_t)i] != 0) continue;
+        for (int lc = 0; lc <= g.level[(size_t)i]; lc++) {
+            int32_t *ids = g.ids(i, lc);
+            for (int t = 0; t < g.lm(lc); t++) ids[t] = -1;
+            g.cnt(i, lc) = 0;
+            queue_row(i, lc);
+        }
+        g.del[(size_t)i] = 1;
+        memset(g.values.data() + (size_t)i * g.row_bytes, 0, g.row_bytes);
+        CU_TRY(ix, cudaMemcpyAsync((uint8_t *)ix->vectors.p + (size_t)i * ix->row_stride, zero_row.data(), ix->row_stride,
+                                   cudaMemcpyHostToDevice, ix->stream));
+        n_marked++;
+    }
+    rc = flush_scatter();
+    if (rc) return rc;
+    CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+    rc = upload_flags();
+    if (rc) return rc;
+    ix->n = n;
+    ix->entry = g.entry;
+    ix->entry_level = g.entry_level;
+    ix->tc_ready = false;                                         // rows of deleted elements were zeroed
+    if (stats) {
+        stats->n_elements_deleted = n_marked;
+        stats->n_elements_repaired = n_repaired;
+        stats->n_rounds = n_rounds;
+        stats->n_searched = n_searched;
+        stats->n_conflicts = n_conflicts;
+        stats->kernel_ms = kernel_ms;
+        stats->total_ms = now_ms() - t_start;
+    }
+    return PGVRX_OK;
+}
+
+int pgvrx_index_element_flags(pgvrx_index *ix, uint8_t *flags, int64_t n) {
+    if (!ix || !flags) return PGVRX_ERR_INVALID;
+    if (!ix->loaded || n != ix->n) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "flags must cover every element of the index");
+    if (!ix->has_flags) { memset(flags, 0, (size_t)n); return PGVRX_OK; }
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    CU_TRY(ix, cudaMemcpy(flags, ix->flags.p, (size_t)n, cudaMemcpyDeviceToHost));
+    return PGVRX_OK;
 }
 
 int pgvrx_index_set_heap_tids(pgvrx_index *ix, const uint64_t *heap_tids, const uint8_t *counts, int64_t n) {

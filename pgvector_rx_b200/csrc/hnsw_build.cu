@@ -135,6 +135,166 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Vacuum repair search: find_element_neighbors_on_disk(..., skip_set) (insert.rs:1021-1123) for elements that are
+// already in the graph (vacuum.rs:288-407).  Same walk as the kernel above with three differences: members of the skip
+// set (elements without heap TIDs, and the element itself) are traversed but do not count towards ef (search_layer's
+// SKIP mode); ef = ef_construction + 1; elements flagged deleted by an EARLIER vacuum are visited and nothing else
+// (FLAGGED).  W is written out whole, skip members included: the host filters them and keeps the nearest lm.
+// Shared-memory list only.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool repair_is_skip(const GraphView &g, const WarpCtx &c, uint32_t id) {
+    return (int32_t)id == c.self_id || (__ldg(g.flags + id) & ELEM_FLAG_NO_HEAPTIDS);
+}
+
+// seed a layer's search with one entry point (insert.rs:1050, :1069-1071)
+__device__ __forceinline__ void repair_seed1(WarpCtx &c, SmemList &S, const GraphView &g, uint64_t ep_key, int ef) {
+    c.ef = ef + (repair_is_skip(g, c, key_id(ep_key)) ? 1 : 0);
+    c.excess = 0;
+    S.reset1(c, ep_key);
+    if (c.len >= c.ef) c.f_ord = key_ord(ep_key);
+}
+
+// W of the layer above becomes the entry points of this one (insert.rs:1119 ep_list = w): every member is pushed, the
+// counted ones raise w_len -- possibly past ef, nothing is evicted while seeding (scan.rs:326-336)
+__device__ __forceinline__ void repair_reopen(WarpCtx &c, SmemList &S, const GraphView &g, uint32_t *vis, uint32_t vis_mask, int ef) {
+    c.len = min(c.len, c.ef);
+    __syncwarp();
+    int n_skip = 0;
+    for (int base = 0; base < c.len; base += 32) {
+        const int i = base + c.lane;
+        bool sk = false;
+        if (i < c.len) {
+            S.S[i] &= ~1ull;
+            vis_insert(vis, vis_mask, key_id(S.S[i]));
+            sk = repair_is_skip(g, c, key_id(S.S[i]));
+        }
+        n_skip += __popc(__ballot_sync(FULL, sk));
+    }
+    __syncwarp();
+    S.hint = 0;
+    c.ef = max(ef, c.len - n_skip) + n_skip;
+    c.excess = max(0, c.len - n_skip - ef);
+    if (c.ef >= c.cap) { c.status |= ST_TIE_OVERFLOW; c.ef = c.cap - 1; }
+    if (c.len >= c.ef) c.f_ord = key_ord(S.S[c.ef - 1]);
+}
+
+template <int ELEM, int METRIC>
+__global__ void __launch_bounds__(SEARCH_THREADS) hnsw_repair_search_kernel(GraphView g, RepairParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cap = p.ef + p.tail_cap;
+    const size_t s_bytes = round16b((uint32_t)((cap + 1) * 8));
+    const size_t per_warp = (size_t)p.R * p.stage_stride + g.row_stride + s_bytes + 128 + 16;
+    uint8_t *base = smem + (size_t)warp * per_warp;
+
+    WarpCtx c;
+    c.stage = base;
+    c.qsm = c.stage + (size_t)p.R * p.stage_stride;
+    uint8_t *s_mem = c.qsm + g.row_stride;
+    c.nbr = reinterpret_cast<int32_t *>(s_mem + s_bytes);
+    c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
+    SmemList S;
+    S.S = reinterpret_cast<uint64_t *>(s_mem);
+    S.hint = 0;
+    c.stage_stride = p.stage_stride;
+    c.R = p.R;
+    c.nvec = (int)(g.row_stride / 16);
+    c.cap = cap;
+    c.lane = lane;
+    c.phase = 0;
+    c.policy = l2_policy_evict_first();
+    const int slot = blockIdx.x * (blockDim.x / 32) + warp;
+    c.vis = p.vis_base + (size_t)slot * p.vis_entries;
+    if (lane == 0) {
+        mbar_init(c.mbar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const uint32_t up_entries = p.vis_entries < 1024u ? p.vis_entries : 1024u;
+
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(p.work_counter, 1);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= p.n_pending) break;
+        const int e = p.elem_ids[w];
+        const int lvl = g.level[e];
+
+        c.n_dist = c.n_exp0 = c.n_expu = c.n_vis = 0;
+        c.status = 0;
+        c.rs_log = p.rs_log + (size_t)w * p.rs_cap * p.rs_ent;
+        c.rs_ent = p.rs_ent;
+        c.spec = true;
+        c.rs_cap = p.rs_cap;
+        c.rs_n = 0;
+        c.self_id = e;
+        for (int l = lane; l < p.max_layers; l += 32) p.w_counts[(size_t)w * p.max_layers + l] = -1;
+        {
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(g.vectors + (size_t)e * g.row_stride);
+            uint4 *d4 = reinterpret_cast<uint4 *>(c.qsm);
+            for (int i = lane; i < c.nvec; i += 32) d4[i] = __ldg(q4 + i);
+        }
+        __syncwarp();
+        // load_element(entry) fails for an entry point flagged deleted: every list comes back empty (insert.rs:1036-1047)
+        const bool entry_ok = g.entry >= 0 && !(__ldg(g.flags + g.entry) & ELEM_FLAG_DELETED);
+        if (entry_ok) {
+            if (lane == 0) c.nbr[0] = g.entry;
+            __syncwarp();
+            gather_rows(c, g, 0, 1);
+            float d0 = 0.0f;
+            if (lane == 0) d0 = row_distance<ELEM, METRIC>(c.qsm, c.stage, c.nvec);
+            d0 = __shfl_sync(FULL, d0, 0);
+            c.n_dist = 1;
+            __syncwarp();
+            uint64_t ep_key = make_key(d0, (uint32_t)g.entry);
+
+            // phase 1: ef = 1 above the element's level (insert.rs:1052-1072)
+            for (int lc = g.entry_level; lc > lvl && c.status == 0; lc--) {
+                vis_clear(c.vis, up_entries, lane);
+                if (lane == 0) vis_insert(c.vis, up_entries - 1, key_id(ep_key));
+                __syncwarp();
+                c.n_vis++;
+                repair_seed1(c, S, g, ep_key, 1);
+                search_layer<ELEM, METRIC, true, true>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
+                ep_key = S.get(c, 0) & ~1ull;                                       // nearest of W, skip member or not
+            }
+            // phase 2: ef_construction + 1 on the element's layers (insert.rs:1075-1120)
+            bool first = true;
+            for (int lc = min(lvl, g.entry_level); lc >= 0 && c.status == 0; lc--) {
+                vis_clear(c.vis, p.vis_entries, lane);
+                if (first) {
+                    if (lane == 0) vis_insert(c.vis, p.vis_entries - 1, key_id(ep_key));
+                    __syncwarp();
+                    c.n_vis++;
+                    repair_seed1(c, S, g, ep_key, p.ef);
+                } else {
+                    repair_reopen(c, S, g, c.vis, p.vis_entries - 1, p.ef);
+                    c.n_vis += c.len;
+                }
+                first = false;
+                search_layer<ELEM, METRIC, true, true>(c, S, g, lc, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
+                if (c.status == 0 && lc < p.max_layers) {
+                    const int out_n = min(c.len, c.ef);
+                    if (out_n > p.w_pitch) c.status |= ST_TIE_OVERFLOW;            // more skip members than the output row holds
+                    else {
+                        const size_t o = ((size_t)w * p.max_layers + lc) * p.w_pitch;
+                        S.store(c, p.w_ids + o, p.w_dists + o, out_n);
+                        if (lane == 0) p.w_counts[(size_t)w * p.max_layers + lc] = out_n;
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            p.out_status[w] = c.status;
+            p.rs_counts[w] = c.rs_n;
+            if (p.out_ctr) reinterpret_cast<uint4 *>(p.out_ctr)[w] = make_uint4(c.n_dist, c.n_exp0, c.n_expu, c.n_vis);
+        }
+        __syncwarp();
+    }
+}
+
 // scatter freshly committed neighbour rows into the device adjacency (one thread per int)
 __global__ void scatter_rows_kernel(int32_t *dst, const int64_t *row_offsets, const int32_t *packed, int row_len, int n_rows) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -326,6 +486,39 @@ cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem
 cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
                                 size_t smem_block, int threads, cudaStream_t stream) {
     build_kernel_t k = pick_kernel(elem, metric, list_j);
+    if (!k) return cudaErrorInvalidValue;
+    k<<<grid, threads, smem_block, stream>>>(g, p);
+    return cudaGetLastError();
+}
+
+typedef void (*repair_kernel_t)(GraphView, RepairParams);
+static repair_kernel_t pick_repair(int elem, int metric) {
+    if (elem == ELEM_F32) {
+        if (metric == METRIC_L2SQ) return hnsw_repair_search_kernel<ELEM_F32, METRIC_L2SQ>;
+        if (metric == METRIC_NEG_IP) return hnsw_repair_search_kernel<ELEM_F32, METRIC_NEG_IP>;
+        if (metric == METRIC_L1) return hnsw_repair_search_kernel<ELEM_F32, METRIC_L1>;
+    } else if (elem == ELEM_F16) {
+        if (metric == METRIC_L2SQ) return hnsw_repair_search_kernel<ELEM_F16, METRIC_L2SQ>;
+        if (metric == METRIC_NEG_IP) return hnsw_repair_search_kernel<ELEM_F16, METRIC_NEG_IP>;
+        if (metric == METRIC_L1) return hnsw_repair_search_kernel<ELEM_F16, METRIC_L1>;
+    } else if (elem == ELEM_BIT) {
+        if (metric == METRIC_HAMMING) return hnsw_repair_search_kernel<ELEM_BIT, METRIC_HAMMING>;
+        if (metric == METRIC_JACCARD) return hnsw_repair_search_kernel<ELEM_BIT, METRIC_JACCARD>;
+    }
+    return nullptr;
+}
+
+cudaError_t repair_kernel_occupancy(int elem, int metric, size_t smem_block, int threads, int *blocks_per_sm) {
+    repair_kernel_t k = pick_repair(elem, metric);
+    if (!k) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_block);
+}
+
+cudaError_t launch_repair_search(int elem, int metric, const GraphView &g, const RepairParams &p, int grid, size_t smem_block,
+                                 int threads, cudaStream_t stream) {
+    repair_kernel_t k = pick_repair(elem, metric);
     if (!k) return cudaErrorInvalidValue;
     k<<<grid, threads, smem_block, stream>>>(g, p);
     return cudaGetLastError();

@@ -256,6 +256,8 @@ struct WarpCtx {
     int rs_cap, rs_n;      // capacity / count (rs_n may exceed rs_cap: the host then treats the set as unknown)
     int rs_ent;            // ints per log entry: 3 + one word per 32 list slots
     bool spec;             // fetch every neighbour's row while the visited probes are in flight (see search_layer)
+    int32_t self_id;       // vacuum repair search only: the element being repaired (member of the skip set)
+    int excess;            // vacuum repair search only: counted entry points seeded beyond ef (w_len - ef, scan.rs:326-336)
     int lane;
 #ifdef PGVRX_PHASE_TIMING
     uint32_t t[8];         // cycles: 0 pop+adjacency, 1 visited, 2 tma issue+wait, 3 distance, 4 accept/insert
@@ -502,7 +504,15 @@ __device__ __forceinline__ void gather_rows_masked(WarpCtx &c, const GraphView &
 // search_layer (graph/mod.rs:161-255 == scan.rs:302-448 without the iterative-scan bookkeeping).
 // Precondition: S[0, len) holds the entry points (unexpanded), their ids are in the visited set.
 // FLAGGED: also honour GraphView::flags (an index a vacuum has touched); the default instantiation carries no trace of it.
-template <int ELEM, int METRIC, bool FLAGGED = false, class LIST>
+// SKIP: the vacuum repair search (scan.rs:314-336,416-429 `skip_count`): members of the skip set -- elements left without
+// heap TIDs and the element being repaired -- enter W and C like anyone else but do not count towards ef.  Since the
+// reference evicts the furthest of W (whatever it is) only when a COUNTED member pushed w_len past ef, W is always the
+// first min(counted pushes, ef) + (skip pushes) entries of the sorted list: the boundary c.ef simply moves out by one
+// with every skip member that is pushed, and "W full" stays len >= ef.  One wrinkle: a layer seeded with MORE than ef
+// counted entry points starts with w_len > ef (nothing is evicted while seeding), and then `if w_len > ef` fires after
+// every push, skip members included, each time taking w_len down by one: the first `excess` skip pushes evict like
+// counted ones and only the later ones move the boundary.
+template <int ELEM, int METRIC, bool FLAGGED = false, bool SKIP = false, class LIST>
 __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphView &g, int layer, uint32_t vis_mask,
                                              uint32_t vis_limit) {
     const int lane = c.lane;
@@ -623,7 +633,15 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
                 const float dr = __shfl_sync(FULL, d, r);
                 const int32_t idr = __shfl_sync(FULL, nb, r);
                 const bool always_add = c.len < c.ef;
-                if (always_add || f32_ord(dr) < c.f_ord) S.insert(c, make_key(dr, (uint32_t)idr));
+                if (always_add || f32_ord(dr) < c.f_ord) {
+                    if constexpr (SKIP) {
+                        if (idr == c.self_id || (__ldg(g.flags + idr) & ELEM_FLAG_NO_HEAPTIDS)) {
+                            if (c.excess > 0) c.excess -= 1; else c.ef += 1;
+                        }
+                        if (c.ef >= c.cap) { c.status |= ST_TIE_OVERFLOW; return; }   // more skip members than the list holds
+                    }
+                    S.insert(c, make_key(dr, (uint32_t)idr));
+                }
             }
             // lost a same-slot race inside the warp: the id is new (decided above) but still has to be stored -- deferred
             lost_fresh = fresh && free_slot >= 0;

@@ -68,6 +68,32 @@ struct BuildParams {
     int R;
 };
 
+// vacuum repair searches (hnsw_build.cu: hnsw_repair_search_kernel): find_element_neighbors_on_disk with a skip set
+// (src/index/insert.rs:1021-1123 called from vacuum.rs:341-353)
+struct RepairParams {
+    const int32_t *elem_ids;   // elements to repair (already in the graph)
+    int n_pending;
+    int ef, tail_cap;          // ef = ef_construction + 1 (insert.rs:1080-1084); list capacity = ef + tail_cap
+    int max_layers;
+    int w_pitch;               // entries per (element, layer) in w_ids / w_dists: W holds skip members on top of ef
+    int32_t *w_ids;            // n_pending x max_layers x w_pitch, ascending (distance, id), skip members included
+    float *w_dists;
+    int32_t *w_counts;         // n_pending x max_layers, -1 for layers that were not searched
+    int32_t *rs_log;           // expansion log as in BuildParams
+    int rs_cap, rs_ent;
+    int32_t *rs_counts;
+    uint32_t *out_status;
+    uint32_t *out_ctr;
+    uint32_t *vis_base;
+    uint32_t vis_entries;
+    int *work_counter;
+    uint32_t stage_stride;
+    int R;
+};
+cudaError_t launch_repair_search(int elem, int metric, const GraphView &g, const RepairParams &p, int grid, size_t smem_block,
+                                 int threads, cudaStream_t stream);
+cudaError_t repair_kernel_occupancy(int elem, int metric, size_t smem_block, int threads, int *blocks_per_sm);
+
 // check_element_closer masks for groups of <= PAIR_MAX_ROWS elements (hnsw_build.cu)
 constexpr int PAIR_MAX_ROWS = 128;
 struct PairParams {
