@@ -190,3 +190,21 @@ def test_writer_rejects_bad_input():
     with pytest.raises(P.PgvrxError) as e:
         P.write_pages(P.ELEM_F32, 2100, 4, 16, dict(g, rows=np.zeros((50, 2100), np.float32)))
     assert "index tuple too large" in str(e.value)                       # build.rs:612-614
+
+
+def test_export_after_a_real_vacuum():
+    # the relation the oracle's ambulkdelete restatement leaves behind (repaired lists, deleted elements with zeroed values
+    # and bumped versions) goes through the exporter unchanged
+    o = oracle_index("vector_l2_ops", 10, make_rows("f32", 900, 10, 3), m=5, efc=20)
+    dead = np.random.default_rng(4).permutation(900)[:300]
+    assert o.bulk_delete(dead) == 300
+    want = o.export_graph()
+    g = P.export_pages(o.write_pages(), P.ELEM_F32)
+    assert g["n_deleted"] == 300 and np.array_equal(g["flags"], o.element_flags())
+    for k in ("level", "adj0", "upper_base", "adj_up"):
+        assert np.array_equal(g[k], want[k]), k
+    assert g["entry"] == want["entry"] and np.array_equal(g["rows"], want["rows"])
+    gone = np.nonzero(g["flags"] & P.ELEM_DELETED)[0]
+    assert sorted(gone.tolist()) == sorted(dead.tolist())
+    live_lists = g["adj0"][g["flags"] == 0]
+    assert not np.isin(live_lists[live_lists >= 0], gone).any()         # repair removed every pointer to a deleted element
