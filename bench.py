@@ -64,6 +64,9 @@ def parse():
                     help="rows of the same dataset built on the GPU for the build vectors/s figure (0 = skip)")
     ap.add_argument("--insert-rows", type=int, default=-1,
                     help="rows inserted into the finished index through aminsert's rules (-1 = 20000 when the whole dataset was built at N=1, else 0)")
+    ap.add_argument("--vacuum-rows", type=int, default=0,
+                    help="after the insert sample: delete this many rows of the built index and VACUUM it on the GPU and in the "
+                         "oracle, comparing the graphs (0 = skip; every deleted row makes ~2m live elements need a repair search)")
     ap.add_argument("--threads", type=int, default=0, help="host threads for the CPU legs (0 = the cores this process may use)")
     ap.add_argument("--no-flat", action="store_true", help="skip the exact flat-kNN section (recall then uses the oracle's brute force on --recall-sample queries)")
     a = ap.parse_args()
@@ -225,6 +228,26 @@ def insert_sample(a, ix, o, n_insert, n_check=1500):
                 graph_identical_to_oracle=bool(same),
                 note="aminsert rules (nearest-lm lists, one-slot back-link replacement); the oracle inserts the first %d rows "
                      "single-threaded on the same graph and the resulting graphs are compared" % n_check)
+
+
+def vacuum_sample(a, ix, o, n_dead):
+    """VACUUM (ambulkdelete, src/index/vacuum.rs) after deleting n_dead rows spread over the index: pgvrx_index_vacuum on
+    the GPU and the oracle's bulk_delete on the same graph, graphs and flags compared.  Off by default (--vacuum-rows)."""
+    n = ix.graph_info()["n"]
+    dead = np.random.default_rng(21).permutation(n)[:n_dead].astype(np.int64)
+    t0 = time.perf_counter()
+    o.bulk_delete(dead)
+    dt_cpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    st = ix.vacuum(dead.astype(np.uint64))
+    dt = time.perf_counter() - t0
+    g, w = ix.export_graph(), o.export_graph()
+    same = g["entry"] == w["entry"] and all(np.array_equal(g[k], w[k]) for k in ("adj0", "adj_up")) and \
+        np.array_equal(ix.element_flags(), o.element_flags())
+    return dict(rows_deleted=int(n_dead), elements_repaired=int(st["n_elements_repaired"]), seconds=dt,
+                repairs_per_s=st["n_elements_repaired"] / dt, rounds=int(st["n_rounds"]), conflicts=int(st["n_conflicts"]),
+                kernel_ms=st["kernel_ms"], cpu_oracle_seconds=dt_cpu, cpu_oracle_repairs_per_s=st["n_elements_repaired"] / dt_cpu,
+                graph_identical_to_oracle=bool(same))
 
 
 def recall_at_k(a, g, queries, got_ids, sample):
@@ -568,6 +591,8 @@ def run_b200(a):
             # the scan oracle is no longer needed for queries: let it take the same inserts
             if build_info.get("adjacency_identical_to_oracle", g.get("source") == "gpu-build"):
                 build_info["insert"] = insert_sample(a, ix_built, o, n_ins)
+                if a.vacuum_rows > 0 and build_info["insert"]["graph_identical_to_oracle"]:
+                    build_info["vacuum"] = vacuum_sample(a, ix_built, o, a.vacuum_rows)
             ix_built.close()
         nchk = len(cpu_ids)
         parity_ok = bool(np.array_equal(cpu_ids, last_ids[:nchk]))
