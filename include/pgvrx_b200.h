@@ -163,7 +163,7 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
  * Host code, no device needed. */
 int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_construction, int64_t n,
                       const void *rows, const uint8_t *level, const int32_t *adj0, const int32_t *upper_base,
-                      const int32_t *adj_up, int64_t entry, const uint64_t *heap_tids,
+                      const int32_t *adj_up, int64_t n_upper_rows, int64_t entry, const uint64_t *heap_tids,
                       const uint8_t *heap_tid_counts, void *pages, int64_t cap_pages, int64_t *n_pages_out);
 
 /* ---- what a vacuum leaves on disk, as the scan sees it ------------------------------------------ */

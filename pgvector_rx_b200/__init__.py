@@ -131,7 +131,7 @@ def lib():
         "pgvrx_pages_inspect": (C.c_int, [vp, i64, i32, C.POINTER(PagesInfo)]),
         "pgvrx_pages_export": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_pages_element_flags": (C.c_int, [vp, i64, vp]),
-        "pgvrx_pages_write": (C.c_int, [i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, C.POINTER(i64)]),
+        "pgvrx_pages_write": (C.c_int, [i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, C.POINTER(i64)]),
         "pgvrx_index_set_element_flags": (C.c_int, [vp, vp, i64]),
         "pgvrx_index_build": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
         "pgvrx_index_insert": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
@@ -244,13 +244,15 @@ def write_pages(elem, dims, m, ef_construction, g, heap_tids=None, heap_tid_coun
     level = np.ascontiguousarray(g["level"], np.uint8)
     adj0 = np.ascontiguousarray(g["adj0"], np.int32)
     upper_base = np.ascontiguousarray(g["upper_base"], np.int32)
-    adj_up = np.ascontiguousarray(g["adj_up"], np.int32)
+    adj_up = np.ascontiguousarray(g["adj_up"], np.int32).reshape(-1, m)
+    n_upper = len(adj_up)
     if adj_up.size == 0:
         adj_up = np.zeros((1, m), np.int32)
     t = None if heap_tids is None else np.ascontiguousarray(heap_tids, np.uint64)
     c = None if heap_tid_counts is None else np.ascontiguousarray(heap_tid_counts, np.uint8)
     npg = i64_out = C.c_int64(0)
-    args = (elem, dims, m, ef_construction, n, _p(rows), _p(level), _p(adj0), _p(upper_base), _p(adj_up), int(g["entry"]), _p(t), _p(c))
+    args = (elem, dims, m, ef_construction, n, _p(rows), _p(level), _p(adj0), _p(upper_base), _p(adj_up), n_upper,
+            int(g["entry"]), _p(t), _p(c))
     rc = L.pgvrx_pages_write(*args, None, 0, C.byref(npg))
     if rc != OK:
         raise PgvrxError(rc, L.pgvrx_last_error(None).decode())

@@ -82,7 +82,7 @@ void put_item(uint8_t *page, const Slot &s, const uint8_t *tuple, size_t size) {
 
 extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_construction, int64_t n, const void *rows,
                                  const uint8_t *level, const int32_t *adj0, const int32_t *upper_base, const int32_t *adj_up,
-                                 int64_t entry, const uint64_t *heap_tids, const uint8_t *heap_tid_counts, void *pages,
+                                 int64_t n_upper_rows, int64_t entry, const uint64_t *heap_tids, const uint8_t *heap_tid_counts, void *pages,
                                  int64_t cap_pages, int64_t *n_pages_out) {
     if (elem_type < PGVRX_ELEM_F32 || elem_type > PGVRX_ELEM_BIT) return fail("pgvector-rx: unknown element type");
     if (m < 2 || m > 100 || ef_construction < 4 || ef_construction > 1000 || dims < 1 || dims > 64000)
@@ -120,6 +120,7 @@ extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int
         if (loc[(size_t)i].nbr.blk != want_blk || loc[(size_t)i].nbr.off != want_off)
             return fail("pgvector-rx: failed to add neighbor tuple to page");              // build.rs:699-701
     }
+    if (up_rows != n_upper_rows) return fail("pgvector-rx: adj_up does not hold one row per upper layer of every element");
     const int64_t n_pages = (int64_t)cur.blk + 1;
     if (n_pages_out) *n_pages_out = n_pages;
     if (!pages) return PGVRX_OK;                                         // sizing call

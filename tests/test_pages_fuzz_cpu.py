@@ -65,3 +65,21 @@ def test_exporter_survives_corrupt_relations(tmp_path):
     assert "asan fuzz:" in r.stdout
     accepted = int(r.stdout.split("asan fuzz:")[1].split("accepted")[0])
     assert 1 <= accepted < len(files)                 # the intact relation is accepted, most mutants are not
+
+
+def test_writer_survives_corrupt_graph_arrays(tmp_path):
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "writer_fuzz")
+    r = subprocess.run([cxx, "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "fuzz", "writer_fuzz_main.cpp"),
+                        os.path.join(ROOT, "pgvector_rx_b200", "csrc", "page_write.cpp"), "-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build unavailable: " + r.stderr[-200:])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    assert "writer fuzz:" in r.stdout
+    written = int(r.stdout.split("writer fuzz:")[1].split("written")[0])
+    assert written > 100
