@@ -86,3 +86,11 @@ def test_normalize_bit_identical_to_oracle():
     assert np.array_equal(P.normalize(P.ELEM_F16, 2, r)[1], O.normalize(O.ELEM_F16, 2, r)[1])
     with pytest.raises(P.PgvrxError):
         P.normalize(P.ELEM_BIT, 8, np.zeros(1, np.uint8))
+
+
+def test_integration_doc_lists_every_export():
+    # INTEGRATION.md shows the reference-side (pgrx) binding of the boundary: it has to name every entry point
+    import os
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    missing = [e for e in P.EXPORTS if e not in doc]
+    assert not missing, missing
