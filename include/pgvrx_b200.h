@@ -159,7 +159,7 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
  * neighbour tuples in element order from block 1, byte for byte what the reference writes from its in-memory build
  * state -- so build + export + write = CREATE INDEX.  heap_tids / heap_tid_counts as pgvrx_index_export_graph returns
  * them, each TID as (block << 16 | offset) with offset >= 1; NULL gives element i the synthetic TID of row i
- * (block i >> 16, offset (i & 0xffff) + 1).  Call with pages == NULL to get the page count in *n_pages_out.
+ * (block i / 65535, offset i % 65535 + 1: always a valid TID).  Call with pages == NULL to get the page count in *n_pages_out.
  * Host code, no device needed. */
 int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_construction, int64_t n,
                       const void *rows, const uint8_t *level, const int32_t *adj0, const int32_t *upper_base,

@@ -6,11 +6,16 @@
 // varlena (hnsw.rs:110-128, scan.rs:155-228) and neighbour tuples holding (level + 2) * m TIDs with
 // layer lc at slots [(level - lc) * m, +lm) terminated by the first invalid TID
 // (hnsw.rs:150-160, scan.rs:236-283).  Element ids are assigned in page-walk order, which is the
-// order build.rs:600-702 wrote them, i.e. insertion order.  Pure host code: one sequential pass.
+// order build.rs:600-702 wrote them, i.e. insertion order.  Pure host code: one sequential walk of the page chain
+// assigns the element ids (a flat (block, offset) -> id table), then the elements are decoded by a few host threads --
+// every element writes only its own output rows, and the layer rows of adj_up come from a prefix sum over the levels.
+#include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pgvrx_b200.h"
@@ -65,28 +70,36 @@ int err(const char *msg) {
 struct Walk {
     std::vector<uint32_t> blk;      // per element
     std::vector<uint16_t> off;
-    std::vector<std::vector<int32_t>> id_of;   // [block][offset] -> element id or -1
+    std::vector<int64_t> slot0;     // per block: first entry of that block in id_flat, -1 for a block off the chain
+    std::vector<uint16_t> slots;    // per block: max offset + 1 (entries in id_flat)
+    std::vector<int32_t> id_flat;   // [slot0[block] + offset] -> element id or -1
+    int32_t id_of(uint32_t b, uint16_t o) const {
+        if ((size_t)b >= slot0.size() || slot0[b] < 0 || o >= slots[b]) return -1;
+        return id_flat[(size_t)slot0[b] + o];
+    }
 };
 
 int walk_elements(const Pages &pg, Walk &w, int64_t *n_deleted) {
-    w.id_of.assign((size_t)pg.n, {});
+    w.slot0.assign((size_t)pg.n, -1);
+    w.slots.assign((size_t)pg.n, 0);
     *n_deleted = 0;
-    std::vector<char> seen((size_t)pg.n, 0);
     for (uint32_t b = 1; b != INVALID_BLOCK;) {          // HNSW_HEAD_BLKNO
         if ((int64_t)b >= pg.n) return err("pgvector-rx: page chain points past the end of the relation");
-        if (seen[b]) return err("pgvector-rx: page chain loops");
-        seen[b] = 1;
+        if (w.slot0[b] >= 0) return err("pgvector-rx: page chain loops");
         if (!pg.is_hnsw(b)) return err("pgvector-rx: hnsw index is not valid");
         if (!pg.header_ok(b)) return err("pgvector-rx: corrupt page header in the element chain");
         uint16_t mo = pg.max_offset(b);
-        w.id_of[b].assign((size_t)mo + 1, -1);
+        w.slot0[b] = (int64_t)w.id_flat.size();
+        w.slots[b] = (uint16_t)(mo + 1);
+        w.id_flat.resize(w.id_flat.size() + (size_t)mo + 1, -1);
+        int32_t *ids = w.id_flat.data() + w.slot0[b];
         for (uint16_t o = 1; o <= mo; o++) {
             Item it = pg.item(b, o);
             if (!it.normal || it.len < 4) continue;
             if (it.ptr[0] != 1) continue;                 // HNSW_ELEMENT_TUPLE_TYPE
             if (it.len < ETUP_HDR + 8) return err("pgvector-rx: truncated element tuple");
             if (it.ptr[2] != 0) (*n_deleted)++;
-            w.id_of[b][o] = (int32_t)w.blk.size();
+            ids[o] = (int32_t)w.blk.size();
             w.blk.push_back(b);
             w.off.push_back(o);
         }
@@ -95,13 +108,18 @@ int walk_elements(const Pages &pg, Walk &w, int64_t *n_deleted) {
     return PGVRX_OK;
 }
 
-}  // namespace
+// fn(lo, hi) over [0, n) on a few threads; small relations stay on the calling thread
+template <class F> void parallel_ranges(int64_t n, F fn) {
+    int nt = (int)std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / 16384);
+    if (nt <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> ts;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) ts.emplace_back([=]() { fn(std::min(n, t * per), std::min(n, (t + 1) * per)); });
+    for (auto &t : ts) t.join();
+}
 
-extern "C" {
-
-int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, pgvrx_pages_info *info) {
-    if (!pages || !info || n_pages < 2) return err("pgvector-rx: need the meta page and the head page");
-    Pages pg{(const uint8_t *)pages, n_pages};
+// meta page + element walk + per-element validation, shared by inspect and export (which needs the walk as well)
+int inspect_walk(const Pages &pg, int32_t elem_type, pgvrx_pages_info *info, Walk &w) {
     memset(info, 0, sizeof *info);
     const uint8_t *m = pg.page(0) + PAGE_HDR;
     if (rd32(m) != 0xA953A953u) return err("pgvector-rx: hnsw index is not valid");      // scan.rs:134-137
@@ -114,77 +132,106 @@ int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, p
         return err("pgvector-rx: hnsw index is not valid (meta page parameters out of range)");
     Tid entry{rd32(m + 16), rd16(m + 20)};
     info->entry_level = (int16_t)rd16(m + 22);
-    Walk w;
     int rc = walk_elements(pg, w, &info->n_deleted);
     if (rc) return rc;
     info->n_elements = (int64_t)w.blk.size();
     info->entry = -1;
     if (entry.blk != INVALID_BLOCK) {
-        if ((int64_t)entry.blk >= n_pages || entry.off >= w.id_of[entry.blk].size() || w.id_of[entry.blk][entry.off] < 0)
-            return err("pgvector-rx: entry point does not reference an element tuple");
-        info->entry = w.id_of[entry.blk][entry.off];
+        if (w.id_of(entry.blk, entry.off) < 0) return err("pgvector-rx: entry point does not reference an element tuple");
+        info->entry = w.id_of(entry.blk, entry.off);
     }
-    size_t want_row = pgvrx_row_bytes(elem_type, info->dims);
-    for (size_t i = 0; i < w.blk.size(); i++) {
-        Item it = pg.item(w.blk[i], w.off[i]);
-        info->n_upper_rows += it.ptr[1];
-        for (int t = 0; t < PGVRX_HEAPTIDS; t++) {
-            if (!rd_tid(it.ptr + 4 + t * TID).valid()) break;
-            info->n_heap_tids++;
+    const size_t want_row = pgvrx_row_bytes(elem_type, info->dims);
+    std::atomic<int64_t> n_upper{0}, n_tids{0};
+    std::atomic<int> bad{0};                 // 1 = varlena header, 2 = value size
+    parallel_ranges((int64_t)w.blk.size(), [&](int64_t lo, int64_t hi) {
+        int64_t up = 0, tids = 0;
+        int b = 0;
+        for (int64_t i = lo; i < hi && !b; i++) {
+            Item it = pg.item(w.blk[(size_t)i], w.off[(size_t)i]);
+            up += it.ptr[1];
+            for (int t = 0; t < PGVRX_HEAPTIDS; t++) {
+                if (!rd_tid(it.ptr + 4 + t * TID).valid()) break;
+                tids++;
+            }
+            if (it.ptr[2] != 0) continue;       // deleted: vacuum zeroed the value, varlena header included (vacuum.rs:750-754)
+            uint32_t vl = rd32(it.ptr + ETUP_HDR);
+            if ((vl & 3u) != 0) { b = 1; break; }
+            size_t vsize = vl >> 2;
+            if (vsize != want_row + 8 || ETUP_HDR + vsize > it.len) { b = 2; break; }
         }
-        if (it.ptr[2] != 0) continue;       // deleted: vacuum zeroed the value, varlena header included (vacuum.rs:750-754)
-        uint32_t vl = rd32(it.ptr + ETUP_HDR);
-        if ((vl & 3u) != 0) return err("pgvector-rx: element value is not a plain 4-byte-header varlena");
-        size_t vsize = vl >> 2;
-        if (vsize != want_row + 8 || ETUP_HDR + vsize > it.len) return err("pgvector-rx: element value size does not match the index dimensions");
-    }
+        n_upper += up; n_tids += tids;
+        if (b) { int zero = 0; bad.compare_exchange_strong(zero, b); }
+    });
+    if (bad.load() == 1) return err("pgvector-rx: element value is not a plain 4-byte-header varlena");
+    if (bad.load() == 2) return err("pgvector-rx: element value size does not match the index dimensions");
+    info->n_upper_rows = n_upper.load();
+    info->n_heap_tids = n_tids.load();
     return PGVRX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, pgvrx_pages_info *info) {
+    if (!pages || !info || n_pages < 2) return err("pgvector-rx: need the meta page and the head page");
+    Pages pg{(const uint8_t *)pages, n_pages};
+    Walk w;
+    return inspect_walk(pg, elem_type, info, w);
 }
 
 int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, void *rows, uint8_t *level, int32_t *adj0,
                        int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids, uint8_t *heap_tid_counts) {
+    if (!pages || n_pages < 2) return err("pgvector-rx: need the meta page and the head page");
+    Pages pg{(const uint8_t *)pages, n_pages};
     pgvrx_pages_info info;
-    int rc = pgvrx_pages_inspect(pages, n_pages, elem_type, &info);
+    Walk w;
+    int rc = inspect_walk(pg, elem_type, &info, w);
     if (rc) return rc;
     if (info.n_elements > 0 && (!rows || !level || !adj0 || !upper_base || (info.n_upper_rows > 0 && !adj_up)))
         return err("pgvector-rx: null output array");
-    Pages pg{(const uint8_t *)pages, n_pages};
-    Walk w;
-    int64_t nd;
-    rc = walk_elements(pg, w, &nd);
-    if (rc) return rc;
     const int m = info.m;
     const size_t row_bytes = pgvrx_row_bytes(elem_type, info.dims);
-    int64_t up = 0;
-    for (size_t i = 0; i < w.blk.size(); i++) {
-        Item it = pg.item(w.blk[i], w.off[i]);
-        const int lv = it.ptr[1];
-        const uint8_t version = it.ptr[3];
-        level[i] = (uint8_t)lv;
-        // a deleted element keeps its id (neighbour TIDs may still point at it) but has no value; its distance is never used
-        if (it.ptr[2] != 0) memset((uint8_t *)rows + i * row_bytes, 0, row_bytes);
-        else memcpy((uint8_t *)rows + i * row_bytes, it.ptr + ETUP_HDR + 8, row_bytes);
-        int nh = 0;
-        for (int t = 0; t < PGVRX_HEAPTIDS; t++) {                    // scan.rs:203-209: stop at the first invalid
-            Tid h = rd_tid(it.ptr + 4 + t * TID);
-            if (!h.valid()) break;
-            if (heap_tids) heap_tids[i * PGVRX_HEAPTIDS + nh] = ((uint64_t)h.blk << 16) | h.off;
-            nh++;
-        }
-        if (heap_tids) for (int t = nh; t < PGVRX_HEAPTIDS; t++) heap_tids[i * PGVRX_HEAPTIDS + t] = ~0ull;
-        if (heap_tid_counts) heap_tid_counts[i] = (uint8_t)nh;
-        upper_base[i] = lv > 0 ? (int32_t)up : -1;
-        for (int j = 0; j < 2 * m; j++) adj0[i * 2 * m + j] = -1;
-        for (int l = 1; l <= lv; l++) for (int j = 0; j < m; j++) adj_up[(size_t)(up + l - 1) * m + j] = -1;
+    const int64_t n = info.n_elements;
+    // first adj_up row of every element = sum of the levels before it (element order)
+    std::vector<int64_t> up_of((size_t)n);
+    {
+        int64_t up = 0;
+        for (int64_t i = 0; i < n; i++) { up_of[(size_t)i] = up; up += pg.item(w.blk[(size_t)i], w.off[(size_t)i]).ptr[1]; }
+    }
+    std::atomic<int> bad{0};
+    parallel_ranges(n, [&](int64_t lo, int64_t hi) {
+        for (int64_t ii = lo; ii < hi; ii++) {
+            const size_t i = (size_t)ii;
+            Item it = pg.item(w.blk[i], w.off[i]);
+            const int lv = it.ptr[1];
+            const uint8_t version = it.ptr[3];
+            const int64_t up = up_of[i];
+            level[i] = (uint8_t)lv;
+            // a deleted element keeps its id (neighbour TIDs may still point at it) but has no value; its distance is never used
+            if (it.ptr[2] != 0) memset((uint8_t *)rows + i * row_bytes, 0, row_bytes);
+            else memcpy((uint8_t *)rows + i * row_bytes, it.ptr + ETUP_HDR + 8, row_bytes);
+            int nh = 0;
+            for (int t = 0; t < PGVRX_HEAPTIDS; t++) {                    // scan.rs:203-209: stop at the first invalid
+                Tid h = rd_tid(it.ptr + 4 + t * TID);
+                if (!h.valid()) break;
+                if (heap_tids) heap_tids[i * PGVRX_HEAPTIDS + nh] = ((uint64_t)h.blk << 16) | h.off;
+                nh++;
+            }
+            if (heap_tids) for (int t = nh; t < PGVRX_HEAPTIDS; t++) heap_tids[i * PGVRX_HEAPTIDS + t] = ~0ull;
+            if (heap_tid_counts) heap_tid_counts[i] = (uint8_t)nh;
+            upper_base[i] = lv > 0 ? (int32_t)up : -1;
+            for (int j = 0; j < 2 * m; j++) adj0[i * 2 * m + j] = -1;
+            for (int l = 1; l <= lv; l++) for (int j = 0; j < m; j++) adj_up[(size_t)(up + l - 1) * m + j] = -1;
 
-        Tid nt = rd_tid(it.ptr + 4 + PGVRX_HEAPTIDS * TID);
-        bool ok = nt.valid() && (int64_t)nt.blk < n_pages && nt.off <= pg.max_offset(nt.blk);
-        Item ni{nullptr, 0, false};
-        if (ok) ni = pg.item(nt.blk, nt.off);
-        // scan.rs:254-265: wrong type / version / count => the element has no usable lists
-        ok = ok && ni.normal && ni.len >= NTUP_HDR && ni.ptr[0] == 2 && ni.ptr[1] == version &&
-             rd16(ni.ptr + 2) == (lv + 2) * m && NTUP_HDR + (size_t)(lv + 2) * m * TID <= ni.len;
-        if (ok) {
+            Tid nt = rd_tid(it.ptr + 4 + PGVRX_HEAPTIDS * TID);
+            bool ok = nt.valid() && (int64_t)nt.blk < n_pages && nt.off <= pg.max_offset(nt.blk);
+            Item ni{nullptr, 0, false};
+            if (ok) ni = pg.item(nt.blk, nt.off);
+            // scan.rs:254-265: wrong type / version / count => the element has no usable lists
+            ok = ok && ni.normal && ni.len >= NTUP_HDR && ni.ptr[0] == 2 && ni.ptr[1] == version &&
+                 rd16(ni.ptr + 2) == (lv + 2) * m && NTUP_HDR + (size_t)(lv + 2) * m * TID <= ni.len;
+            if (!ok) continue;
             for (int lc = lv; lc >= 0; lc--) {
                 const int lm = lc == 0 ? 2 * m : m;
                 const size_t start = (size_t)(lv - lc) * m;            // scan.rs:268
@@ -192,14 +239,14 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
                 for (int j = 0; j < lm; j++) {
                     Tid t = rd_tid(ni.ptr + NTUP_HDR + (start + j) * TID);
                     if (!t.valid()) break;                             // scan.rs:275-277
-                    if ((int64_t)t.blk >= n_pages || t.off >= w.id_of[t.blk].size() || w.id_of[t.blk][t.off] < 0)
-                        return err("pgvector-rx: neighbour TID does not reference an element tuple");
-                    dst[j] = w.id_of[t.blk][t.off];
+                    const int32_t id = w.id_of(t.blk, t.off);
+                    if (id < 0) { bad.store(1); return; }
+                    dst[j] = id;
                 }
             }
         }
-        up += lv;
-    }
+    });
+    if (bad.load()) return err("pgvector-rx: neighbour TID does not reference an element tuple");
     return PGVRX_OK;
 }
 

@@ -10,12 +10,16 @@
 //   write_neighbor_tuples build.rs:719-790   (level + 2) * m TIDs, layers from the top down, invalid TID after the last
 //   update_meta_page      build.rs:797-821   entry point + insert page (= the last page written)
 //
-// Two passes: placement is computed from tuple sizes alone (PageAddItemExtended / PageGetFreeSpace arithmetic), then
-// the pages are filled.  Pure host code.  Layouts: src/types/hnsw.rs:18-169; the exporter (page_export.cpp) is the
+// Two passes: placement is computed from tuple sizes alone (PageAddItemExtended / PageGetFreeSpace arithmetic) in one
+// sequential sweep, then the pages are filled -- by a few host threads for large graphs: every tuple has its own
+// bytes and its own line pointer, and the page headers follow from the placement.  Pure host code.  Layouts: src/types/hnsw.rs:18-169; the exporter (page_export.cpp) is the
 // inverse and the tests check both directions against the oracle's independent writer.
+#include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pgvrx_b200.h"
@@ -78,6 +82,16 @@ void put_item(uint8_t *page, const Slot &s, const uint8_t *tuple, size_t size) {
     wr32(page + PAGE_HDR + (size_t)(s.off - 1) * ITEMID, lp);
 }
 
+// fn(lo, hi) over [0, n) on a few threads; small graphs stay on the calling thread
+template <class F> void parallel_ranges(int64_t n, int64_t grain, F fn) {
+    int nt = (int)std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / grain);
+    if (nt <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> ts;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) ts.emplace_back([=]() { fn(std::min(n, t * per), std::min(n, (t + 1) * per)); });
+    for (auto &t : ts) t.join();
+}
+
 }  // namespace
 
 extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_construction, int64_t n, const void *rows,
@@ -128,10 +142,12 @@ extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int
 
     // ---- pass 2: fill ----
     uint8_t *base = (uint8_t *)pages;
-    for (int64_t b = 0; b < n_pages; b++) {
-        init_page(base + (size_t)b * BLCKSZ);
-        if (b >= 1 && b + 1 < n_pages) wr32(base + (size_t)b * BLCKSZ + SPECIAL, (uint32_t)(b + 1));   // hnsw_build_append_page
-    }
+    parallel_ranges(n_pages, 1024, [&](int64_t lo, int64_t hi) {
+        for (int64_t b = lo; b < hi; b++) {
+            init_page(base + (size_t)b * BLCKSZ);
+            if (b >= 1 && b + 1 < n_pages) wr32(base + (size_t)b * BLCKSZ + SPECIAL, (uint32_t)(b + 1));   // hnsw_build_append_page
+        }
+    });
     {   // create_meta_page + update_meta_page
         uint8_t *mp = base + PAGE_HDR;
         wr32(mp, 0xA953A953u);                                           // HNSW_MAGIC_NUMBER
@@ -151,63 +167,65 @@ extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int
         wr32(mp + 24, (uint32_t)cur.blk);                                // insert_page = last page written
         wr16(base + 12, (uint16_t)(PAGE_HDR + 28));                      // pd_lower past HnswMetaPageData
     }
-    std::vector<uint8_t> etup(etup_size), ntup;
-    std::vector<uint16_t> lower((size_t)n_pages, (uint16_t)PAGE_HDR), upper((size_t)n_pages, (uint16_t)SPECIAL);
-    for (int64_t i = 0; i < n; i++) {
-        const Placement &L = loc[(size_t)i];
-        const int lv = level[i];
-        // element tuple (hnsw.rs:110-128)
-        memset(etup.data(), 0, etup_size);
-        etup[0] = 1;                                                     // HNSW_ELEMENT_TUPLE_TYPE
-        etup[1] = (uint8_t)lv;
-        const int n_tids = heap_tids ? heap_tid_counts[i] : 1;
-        if (n_tids < 0 || n_tids > PGVRX_HEAPTIDS) return fail("pgvector-rx: an element holds at most 10 heap TIDs");
-        for (int t = 0; t < PGVRX_HEAPTIDS; t++) {
-            uint8_t *slot = etup.data() + 4 + (size_t)t * TID;
-            if (t < n_tids) {
-                // caller's TIDs are (block << 16 | offset); without them element i gets the synthetic TID of row i
-                const uint64_t v = heap_tids ? heap_tids[(size_t)i * PGVRX_HEAPTIDS + t] : ((((uint64_t)i >> 16) << 16) | (((uint64_t)i & 0xffffu) + 1));
-                wr_tid(slot, (uint32_t)(v >> 16), (uint16_t)(v & 0xffffu));
-            } else {
-                wr_invalid_tid(slot);
+    // page headers follow the last item placed on each page (placement order = element order, element before neighbour)
+    for (int64_t i = 0; i < n; i++)
+        for (const Slot *sl : {&loc[(size_t)i].elem, &loc[(size_t)i].nbr}) {
+            wr16(base + (size_t)sl->blk * BLCKSZ + 12, (uint16_t)(PAGE_HDR + (size_t)sl->off * ITEMID));
+            wr16(base + (size_t)sl->blk * BLCKSZ + 14, sl->at);
+        }
+    std::atomic<int> bad{0};                                             // 1 = heap TID count, 2 = neighbour id
+    parallel_ranges(n, 16384, [&](int64_t lo, int64_t hi) {
+        std::vector<uint8_t> etup(etup_size), ntup;
+        for (int64_t i = lo; i < hi; i++) {
+            const Placement &L = loc[(size_t)i];
+            const int lv = level[i];
+            // element tuple (hnsw.rs:110-128)
+            memset(etup.data(), 0, etup_size);
+            etup[0] = 1;                                                     // HNSW_ELEMENT_TUPLE_TYPE
+            etup[1] = (uint8_t)lv;
+            const int n_tids = heap_tids ? heap_tid_counts[i] : 1;
+            if (n_tids < 0 || n_tids > PGVRX_HEAPTIDS) { bad.store(1); return; }
+            for (int t = 0; t < PGVRX_HEAPTIDS; t++) {
+                uint8_t *slot = etup.data() + 4 + (size_t)t * TID;
+                if (t < n_tids) {
+                    // caller's TIDs are (block << 16 | offset); without them element i gets the synthetic TID of row i:
+                    // block i / 65535, offset i % 65535 + 1 -- the offset is never 0, which would read as "no heap TID"
+                    const uint64_t v = heap_tids ? heap_tids[(size_t)i * PGVRX_HEAPTIDS + t] : ((((uint64_t)i / 0xffffu) << 16) | ((uint64_t)i % 0xffffu + 1));
+                    wr_tid(slot, (uint32_t)(v >> 16), (uint16_t)(v & 0xffffu));
+                } else {
+                    wr_invalid_tid(slot);
+                }
             }
-        }
-        wr_tid(etup.data() + 4 + PGVRX_HEAPTIDS * TID, L.nbr.blk, L.nbr.off);        // neighbortid
-        uint8_t *val = etup.data() + ETUP_HDR;
-        wr32(val, (uint32_t)(value_size << 2));                          // 4-byte varlena header (SET_VARSIZE)
-        if (elem_type == PGVRX_ELEM_BIT) wr32(val + 4, (uint32_t)dims);  // VarBitHeader.bit_len (bitvec.rs:28-32)
-        else { wr16(val + 4, (uint16_t)dims); wr16(val + 6, 0); }        // {dim, unused} (vector.rs:43-48, halfvec.rs:41-46)
-        memcpy(val + VARHDR, (const uint8_t *)rows + (size_t)i * row_bytes, row_bytes);
-        put_item(base + (size_t)L.elem.blk * BLCKSZ, L.elem, etup.data(), etup_size);
-        // neighbour tuple (hnsw.rs:150-160; build.rs:719-790)
-        const size_t n_slots = (size_t)(lv + 2) * (size_t)m;
-        const size_t ntup_size = maxalign(NTUP_HDR + n_slots * TID);
-        ntup.assign(ntup_size, 0);
-        ntup[0] = 2;                                                     // HNSW_NEIGHBOR_TUPLE_TYPE
-        wr16(ntup.data() + 2, (uint16_t)n_slots);
-        size_t t = 0;
-        for (int lc = lv; lc >= 0; lc--) {
-            const int lm = lc == 0 ? 2 * m : m;
-            const int32_t *list = lc == 0 ? adj0 + (size_t)i * 2 * m : adj_up + ((size_t)upper_base[i] + (size_t)(lc - 1)) * (size_t)m;
-            bool ended = false;
-            for (int j = 0; j < lm; j++, t++) {
-                uint8_t *slot = ntup.data() + NTUP_HDR + t * TID;
-                const int32_t nb = ended ? -1 : list[j];
-                if (nb < 0) { ended = true; wr_invalid_tid(slot); continue; }
-                if (nb >= n) return fail("pgvector-rx: neighbour id out of range");
-                wr_tid(slot, loc[(size_t)nb].elem.blk, loc[(size_t)nb].elem.off);
+            wr_tid(etup.data() + 4 + PGVRX_HEAPTIDS * TID, L.nbr.blk, L.nbr.off);        // neighbortid
+            uint8_t *val = etup.data() + ETUP_HDR;
+            wr32(val, (uint32_t)(value_size << 2));                          // 4-byte varlena header (SET_VARSIZE)
+            if (elem_type == PGVRX_ELEM_BIT) wr32(val + 4, (uint32_t)dims);  // VarBitHeader.bit_len (bitvec.rs:28-32)
+            else { wr16(val + 4, (uint16_t)dims); wr16(val + 6, 0); }        // {dim, unused} (vector.rs:43-48, halfvec.rs:41-46)
+            memcpy(val + VARHDR, (const uint8_t *)rows + (size_t)i * row_bytes, row_bytes);
+            put_item(base + (size_t)L.elem.blk * BLCKSZ, L.elem, etup.data(), etup_size);
+            // neighbour tuple (hnsw.rs:150-160; build.rs:719-790)
+            const size_t n_slots = (size_t)(lv + 2) * (size_t)m;
+            const size_t ntup_size = maxalign(NTUP_HDR + n_slots * TID);
+            ntup.assign(ntup_size, 0);
+            ntup[0] = 2;                                                     // HNSW_NEIGHBOR_TUPLE_TYPE
+            wr16(ntup.data() + 2, (uint16_t)n_slots);
+            size_t t = 0;
+            for (int lc = lv; lc >= 0; lc--) {
+                const int lm = lc == 0 ? 2 * m : m;
+                const int32_t *list = lc == 0 ? adj0 + (size_t)i * 2 * m : adj_up + ((size_t)upper_base[i] + (size_t)(lc - 1)) * (size_t)m;
+                bool ended = false;
+                for (int j = 0; j < lm; j++, t++) {
+                    uint8_t *slot = ntup.data() + NTUP_HDR + t * TID;
+                    const int32_t nb = ended ? -1 : list[j];
+                    if (nb < 0) { ended = true; wr_invalid_tid(slot); continue; }
+                    if (nb >= n) { bad.store(2); return; }
+                    wr_tid(slot, loc[(size_t)nb].elem.blk, loc[(size_t)nb].elem.off);
+                }
             }
+            put_item(base + (size_t)L.nbr.blk * BLCKSZ, L.nbr, ntup.data(), ntup_size);
         }
-        put_item(base + (size_t)L.nbr.blk * BLCKSZ, L.nbr, ntup.data(), ntup_size);
-        // page headers follow the last item placed on each page
-        for (const Slot *s : {&L.elem, &L.nbr}) {
-            lower[s->blk] = (uint16_t)(PAGE_HDR + (size_t)s->off * ITEMID);
-            upper[s->blk] = s->at;
-        }
-    }
-    for (int64_t b = 1; b < n_pages; b++) {
-        wr16(base + (size_t)b * BLCKSZ + 12, lower[(size_t)b]);
-        wr16(base + (size_t)b * BLCKSZ + 14, upper[(size_t)b]);
-    }
+    });
+    if (bad.load() == 1) return fail("pgvector-rx: an element holds at most 10 heap TIDs");
+    if (bad.load() == 2) return fail("pgvector-rx: neighbour id out of range");
     return PGVRX_OK;
 }

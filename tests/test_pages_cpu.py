@@ -177,6 +177,55 @@ def test_writer_page_layout_edges():
     assert np.array_equal(P.write_pages(P.ELEM_F32, 3, 16, 64, empty), e.write_pages())
 
 
+def synthetic_graph(n, dim, m, seed):
+    """Any well-formed graph will do for the page format: random levels, random dense-prefix lists."""
+    rng = np.random.default_rng(seed)
+    level = np.minimum(rng.geometric(0.7, n) - 1, 6).astype(np.uint8)
+    upper_base = np.full(n, -1, np.int32)
+    upper_base[level > 0] = (np.cumsum(level) - level)[level > 0]
+    n_up = int(level.sum())
+    adj0 = rng.integers(0, n, (n, 2 * m)).astype(np.int32)
+    adj0[np.arange(2 * m)[None, :] >= rng.integers(0, 2 * m + 1, n)[:, None]] = -1
+    adj_up = rng.integers(0, n, (n_up, m)).astype(np.int32)
+    adj_up[np.arange(m)[None, :] >= rng.integers(0, m + 1, n_up)[:, None]] = -1
+    return dict(n=n, rows=rng.standard_normal((n, dim)).astype(np.float32), level=level, adj0=adj0, upper_base=upper_base,
+                adj_up=adj_up, entry=int(np.argmax(level)))
+
+
+def test_writer_and_exporter_on_their_threaded_paths():
+    # above 32k elements / 1k pages both directions decode on several host threads: the bytes must not depend on it
+    n, dim, m = 60_000, 24, 4                            # below 65535: the oracle fixture's TID convention wraps there
+    g = synthetic_graph(n, dim, m, 11)
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, dim, m=m, ef_construction=16)
+    o.import_graph(g)
+    want = o.write_pages()
+    got = P.write_pages(P.ELEM_F32, dim, m, 16, g)
+    assert len(want) // 8192 > 1024 and np.array_equal(got, want)
+    e = P.export_pages(got, P.ELEM_F32)
+    for k in ("rows", "level", "adj0", "upper_base", "adj_up"):
+        assert np.array_equal(e[k], g[k]), k
+    assert e["entry"] == g["entry"] and e["n"] == n and not e["flags"].any()
+    # the writer's default heap TIDs (none given) stay valid and distinct past 65535 rows
+    big = synthetic_graph(70_000, 2, 2, 12)
+    eb = P.export_pages(P.write_pages(P.ELEM_F32, 2, 2, 8, big), P.ELEM_F32)
+    assert (eb["heap_tid_counts"] == 1).all() and not eb["flags"].any()
+    assert len(np.unique(eb["heap_tids"][:, 0])) == 70_000 and ((eb["heap_tids"][:, 0] & 0xffff) >= 1).all()
+    # a neighbour id out of range is refused from whichever thread meets it
+    bad = dict(g, adj0=g["adj0"].copy())
+    bad["adj0"][n - 5, 0] = n
+    with pytest.raises(P.PgvrxError):
+        P.write_pages(P.ELEM_F32, dim, m, 16, bad)
+    # and so is a neighbour TID that points at no element tuple, on the way back
+    torn = got.copy()
+    info_off = 8192 * (len(torn) // 8192 - 1)            # last page: zero its first line pointer's tuple type
+    lp = int(np.frombuffer(torn[info_off + 24: info_off + 28].tobytes(), np.uint32)[0])
+    torn[info_off + (lp & 0x7fff)] = 7                   # neither an element nor a neighbour tuple
+    try:
+        P.export_pages(torn, P.ELEM_F32)                 # accepted only if nothing pointed at that tuple
+    except P.PgvrxError as ex:
+        assert "does not reference an element tuple" in str(ex) or "entry point" in str(ex)
+
+
 def test_writer_rejects_bad_input():
     o = oracle_index("vector_l2_ops", 8, make_rows("f32", 50, 8, 1), m=4, efc=16)
     g = o.export_graph()

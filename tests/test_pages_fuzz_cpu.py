@@ -43,7 +43,7 @@ def test_exporter_survives_corrupt_relations(tmp_path):
     if cxx is None:
         pytest.skip("no g++")
     exe = str(tmp_path / "pages_fuzz")
-    r = subprocess.run([cxx, "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+    r = subprocess.run([cxx, "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-pthread",
                         "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "fuzz", "pages_fuzz_main.cpp"),
                         os.path.join(ROOT, "pgvector_rx_b200", "csrc", "page_export.cpp"), "-o", exe],
                        capture_output=True, text=True)
@@ -72,7 +72,7 @@ def test_writer_survives_corrupt_graph_arrays(tmp_path):
     if cxx is None:
         pytest.skip("no g++")
     exe = str(tmp_path / "writer_fuzz")
-    r = subprocess.run([cxx, "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+    r = subprocess.run([cxx, "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-pthread",
                         "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "fuzz", "writer_fuzz_main.cpp"),
                         os.path.join(ROOT, "pgvector_rx_b200", "csrc", "page_write.cpp"), "-o", exe],
                        capture_output=True, text=True)
