@@ -9,7 +9,7 @@ Queries shard across GPUs against a replicated graph (weak scaling: 10k queries 
 no data-path collective).  Prints ONE JSON line on rank 0.
 
 The graph is the reference-exact graph built by the CPU oracle's sequential ambuild loop; because
-that takes ~45 minutes for 1M rows it is cached under data_cache/ (tools/build_graph_cache.py) and
+that takes ~45 minutes for 1M rows it is cached under data_cache/ (tests/tools/build_graph_cache.py) and
 only rebuilt when the cache is absent.  Vectors and queries are regenerated from seeds.
 """
 import argparse

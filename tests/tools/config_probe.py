@@ -2,14 +2,14 @@
 the oracle on a sample (the oracle imports the GPU-built graph; adjacency parity of the build itself is covered by
 tests/ and by bench.py at 1M rows).
 
-    python tools/config_probe.py c3|c4|c5 [n] [nq]
+    python tests/tools/config_probe.py c3|c4|c5 [n] [nq]
 """
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
