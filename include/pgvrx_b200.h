@@ -166,6 +166,15 @@ int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_con
                       const int32_t *adj_up, int64_t n_upper_rows, int64_t entry, const uint64_t *heap_tids,
                       const uint8_t *heap_tid_counts, void *pages, int64_t cap_pages, int64_t *n_pages_out);
 
+/* amgettuple's fan-out (src/index/scan.rs:794-811,858-875): the scan entry points return ELEMENT ids in emission order;
+ * every element stands for up to 10 heap tuples, which amgettuple hands to the executor one per call, taking them from
+ * the BACK of the element's list (scan.rs:798).  Given n_ids element ids (-1 = padding, skipped) and the heap TID
+ * arrays of pgvrx_pages_export / pgvrx_index_export_graph (n_elements x 10 and n_elements counts), writes the heap TIDs
+ * in the order xs_heaptid would take them.  *n_out receives the number of TIDs; when it exceeds cap only the first cap
+ * were written.  An element without heap TIDs contributes nothing (scan.rs:866-868).  Host-only. */
+int pgvrx_heap_tid_stream(const int32_t *elem_ids, int64_t n_ids, const uint64_t *heap_tids, const uint8_t *heap_tid_counts,
+                          int64_t n_elements, uint64_t *out_tids, int64_t cap, int64_t *n_out);
+
 /* ---- what a vacuum leaves on disk, as the scan sees it ------------------------------------------ */
 /* Per-element flags of an index that vacuum has touched (src/index/vacuum.rs:118-190,647-790):
  *   PGVRX_ELEM_DELETED      HnswElementTupleData.deleted != 0 -- load_element rejects the element before its

@@ -42,7 +42,7 @@ EXPORTS = [
     "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
-    "pgvrx_pages_element_flags", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
+    "pgvrx_pages_element_flags", "pgvrx_heap_tid_stream", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
     "pgvrx_index_set_heap_tids", "pgvrx_pages_write", "pgvrx_index_vacuum", "pgvrx_index_element_flags",
 ]
 ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
@@ -131,6 +131,7 @@ def lib():
         "pgvrx_pages_inspect": (C.c_int, [vp, i64, i32, C.POINTER(PagesInfo)]),
         "pgvrx_pages_export": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
         "pgvrx_pages_element_flags": (C.c_int, [vp, i64, vp]),
+        "pgvrx_heap_tid_stream": (C.c_int, [vp, i64, vp, vp, i64, vp, i64, vp]),
         "pgvrx_pages_write": (C.c_int, [i32, i32, i32, i32, i64, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, C.POINTER(i64)]),
         "pgvrx_index_set_element_flags": (C.c_int, [vp, vp, i64]),
         "pgvrx_index_build": (C.c_int, [vp, vp, i64, vp, vp, i32, C.POINTER(BuildStats)]),
@@ -268,13 +269,15 @@ def heap_tid_stream(elem_ids, heap_tids, heap_tid_counts):
     (src/index/scan.rs:798 `heaptids.pop()`), elements without a TID are skipped (scan.rs:867).  elem_ids: element ids in
     emission order (negative = padding); heap_tids / heap_tid_counts: the n x 10 / n arrays of export_graph() or
     export_pages().  Returns the TIDs as the executor would receive them."""
-    out = []
-    for e in np.asarray(elem_ids).ravel():
-        if e < 0:
-            continue
-        c = int(heap_tid_counts[e])
-        out.extend(int(t) for t in heap_tids[e, :c][::-1])
-    return np.asarray(out, np.uint64)
+    ids = np.ascontiguousarray(np.asarray(elem_ids).ravel(), np.int32)
+    tids = np.ascontiguousarray(heap_tids, np.uint64).reshape(-1, 10)
+    cnt = np.ascontiguousarray(heap_tid_counts, np.uint8)
+    out = np.empty(10 * len(ids), np.uint64)
+    k = C.c_int64(0)
+    rc = lib().pgvrx_heap_tid_stream(_p(ids), len(ids), _p(tids), _p(cnt), len(cnt), _p(out), len(out), C.byref(k))
+    if rc != OK:
+        raise PgvrxError(rc, lib().pgvrx_last_error(None).decode())
+    return out[:k.value].copy()
 
 
 class HnswIndex:

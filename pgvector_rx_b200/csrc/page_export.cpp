@@ -267,4 +267,22 @@ int pgvrx_pages_element_flags(const void *pages, int64_t n_pages, uint8_t *flags
     return PGVRX_OK;
 }
 
+int pgvrx_heap_tid_stream(const int32_t *elem_ids, int64_t n_ids, const uint64_t *heap_tids, const uint8_t *heap_tid_counts,
+                          int64_t n_elements, uint64_t *out_tids, int64_t cap, int64_t *n_out) {
+    if (n_ids < 0 || n_elements < 0 || cap < 0 || !n_out || (n_ids > 0 && (!elem_ids || !heap_tids || !heap_tid_counts)) || (cap > 0 && !out_tids))
+        return err("pgvector-rx: null argument");
+    int64_t k = 0;
+    for (int64_t i = 0; i < n_ids; i++) {
+        const int32_t e = elem_ids[i];
+        if (e < 0) continue;                                             // padding of a result row
+        if (e >= n_elements) return err("pgvector-rx: element id out of range");
+        const int c = heap_tid_counts[e];
+        if (c > PGVRX_HEAPTIDS) return err("pgvector-rx: an element holds at most 10 heap TIDs");
+        for (int t = c - 1; t >= 0; t--, k++)                            // scan.rs:798: pop() takes the last heap TID first
+            if (k < cap) out_tids[k] = heap_tids[(size_t)e * PGVRX_HEAPTIDS + t];
+    }
+    *n_out = k;                                                          // k > cap: call again with a larger buffer
+    return PGVRX_OK;
+}
+
 }  // extern "C"

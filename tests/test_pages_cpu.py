@@ -257,3 +257,33 @@ def test_export_after_a_real_vacuum():
     assert sorted(gone.tolist()) == sorted(dead.tolist())
     live_lists = g["adj0"][g["flags"] == 0]
     assert not np.isin(live_lists[live_lists >= 0], gone).any()         # repair removed every pointer to a deleted element
+
+
+# ---- amgettuple's heap TID fan-out (pgvrx_heap_tid_stream) -----------------------------------------------------------
+def test_heap_tid_stream_matches_amgettuple_order():
+    # duplicates: 25 copies of one row and 3 of another -> elements holding 10 / 10 / 5 / 3 heap TIDs; the oracle's
+    # amgettuple restatement emits each element's TIDs from the back of its list (scan.rs:798)
+    rows = np.concatenate([np.tile(np.array([1, 2, 3], np.float32), (25, 1)), np.tile(np.array([4, 4, 4], np.float32), (3, 1)),
+                           make_rows("f32", 40, 3, 3)])
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 3)
+    o.build(rows, np.zeros(len(rows), np.int32))
+    g = P.export_pages(o.write_pages(), P.ELEM_F32)
+    assert sorted(g["heap_tid_counts"].tolist(), reverse=True)[:4] == [10, 10, 5, 3]
+    for q in (rows[0], rows[26], rows[40]):
+        tids, eids, _, _ = o.scan_stream(q, ef_search=40)
+        elems = eids[np.concatenate([[True], eids[1:] != eids[:-1]])]          # one entry per emitted element
+        got = P.heap_tid_stream(np.concatenate([elems, [-1, -1]]), g["heap_tids"], g["heap_tid_counts"])
+        want = [((int(t) >> 16) << 16) | ((int(t) & 0xffff) + 1) for t in tids]  # the fixture's TID form (fixture_tids)
+        assert got.tolist() == want
+    # an element without heap TIDs contributes nothing; bad ids and short buffers are reported, not written past
+    cnt = g["heap_tid_counts"].copy()
+    cnt[0] = 0
+    assert len(P.heap_tid_stream([0, 1], g["heap_tids"], cnt)) == cnt[1]
+    with pytest.raises(P.PgvrxError):
+        P.heap_tid_stream([g["n"]], g["heap_tids"], g["heap_tid_counts"])
+    import ctypes as C
+    ids = np.array([0, 1], np.int32)
+    out = np.full(4, 7, np.uint64)
+    k = C.c_int64(0)
+    assert P.lib().pgvrx_heap_tid_stream(P._p(ids), 2, P._p(g["heap_tids"]), P._p(g["heap_tid_counts"]), g["n"], P._p(out), 3, C.byref(k)) == 0
+    assert k.value == int(g["heap_tid_counts"][0]) + int(g["heap_tid_counts"][1]) > 3 and out[3] == 7
