@@ -52,6 +52,7 @@ class PgvrxError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("pgvrx error %d: %s" % (code, msg))
         self.code = code
+        self.message = msg
 
 
 class IndexDesc(C.Structure):

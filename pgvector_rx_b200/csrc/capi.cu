@@ -125,8 +125,11 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
                 int32_t *d_ids, float *d_dists, int32_t *d_counts, pgvrx_search_stats *stats,
                 cudaStream_t stream, bool check_status) {
     if (!ix->loaded) return fail(ix, PGVRX_ERR_STATE, "no graph loaded");
-    if (ef < PGVRX_MIN_EF_SEARCH || ef > PGVRX_MAX_EF_SEARCH)
-        return fail(ix, PGVRX_ERR_INVALID, "hnsw.ef_search must be between 1 and 1000");   // options.rs:157-166
+    if (ef < PGVRX_MIN_EF_SEARCH || ef > PGVRX_MAX_EF_SEARCH) {                         // options.rs:157-166, hnsw_vector.out:167-169
+        char b[112];
+        snprintf(b, sizeof b, "%d is outside the valid range for parameter \"hnsw.ef_search\" (1 .. 1000)", ef);
+        return fail(ix, PGVRX_ERR_INVALID, b);
+    }
     if (k < 1 || nq < 0 || nq > (int64_t)1 << 30) return fail(ix, PGVRX_ERR_INVALID, "bad k or nq");
     if (stats) memset(stats, 0, sizeof *stats);
     if (nq == 0) return PGVRX_OK;
@@ -347,10 +350,17 @@ int pgvrx_index_create(const pgvrx_index_desc *d, pgvrx_index **out) {
     if (!d || !out) return fail(nullptr, PGVRX_ERR_INVALID, "null argument");
     *out = nullptr;
     // messages follow tests/pg_regress/expected/hnsw_vector.out:150-159
-    if (d->m < PGVRX_MIN_M || d->m > PGVRX_MAX_M)
-        return fail(nullptr, PGVRX_ERR_INVALID, "value out of bounds for option \"m\": valid values are between \"2\" and \"100\"");
-    if (d->ef_construction < PGVRX_MIN_EF_CONSTRUCTION || d->ef_construction > PGVRX_MAX_EF_CONSTRUCTION)
-        return fail(nullptr, PGVRX_ERR_INVALID, "value out of bounds for option \"ef_construction\": valid values are between \"4\" and \"1000\"");
+    // (the ERROR line; PostgreSQL's DETAIL line carries the valid range)
+    if (d->m < PGVRX_MIN_M || d->m > PGVRX_MAX_M) {
+        char b[96];
+        snprintf(b, sizeof b, "value %d out of bounds for option \"m\"", d->m);
+        return fail(nullptr, PGVRX_ERR_INVALID, b);
+    }
+    if (d->ef_construction < PGVRX_MIN_EF_CONSTRUCTION || d->ef_construction > PGVRX_MAX_EF_CONSTRUCTION) {
+        char b[96];
+        snprintf(b, sizeof b, "value %d out of bounds for option \"ef_construction\"", d->ef_construction);
+        return fail(nullptr, PGVRX_ERR_INVALID, b);
+    }
     if (d->ef_construction < 2 * d->m)
         return fail(nullptr, PGVRX_ERR_INVALID, "ef_construction must be greater than or equal to 2 * m");
     if (!metric_ok(d->elem_type, d->metric)) return fail(nullptr, PGVRX_ERR_INVALID, "operator class does not match the indexed type");

@@ -60,12 +60,20 @@ int pgvrx_scan_begin(pgvrx_index *ix, const void *queries, int64_t nq, int32_t e
     if (!ix || !out) return PGVRX_ERR_INVALID;
     *out = nullptr;
     if (!ix->loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "no graph loaded");
-    if (ef_search < PGVRX_MIN_EF_SEARCH || ef_search > PGVRX_MAX_EF_SEARCH)
-        return pgvrx_fail(ix, PGVRX_ERR_INVALID, "hnsw.ef_search must be between 1 and 1000");          // options.rs:157-166
-    if (iterative_mode < PGVRX_ITER_OFF || iterative_mode > PGVRX_ITER_STRICT)
-        return pgvrx_fail(ix, PGVRX_ERR_INVALID, "invalid value for hnsw.iterative_scan");               // options.rs:168-175
-    if (max_scan_tuples < 1 || max_scan_tuples > (int64_t)0x7fffffff)
-        return pgvrx_fail(ix, PGVRX_ERR_INVALID, "hnsw.max_scan_tuples must be between 1 and 2147483647");   // options.rs:177-186
+    // GUC range messages as PostgreSQL prints them for the reference (tests/pg_regress/expected/hnsw_vector.out:167-185)
+    char msg[128];
+    if (ef_search < PGVRX_MIN_EF_SEARCH || ef_search > PGVRX_MAX_EF_SEARCH) {                             // options.rs:157-166
+        snprintf(msg, sizeof msg, "%d is outside the valid range for parameter \"hnsw.ef_search\" (1 .. 1000)", ef_search);
+        return pgvrx_fail(ix, PGVRX_ERR_INVALID, msg);
+    }
+    if (iterative_mode < PGVRX_ITER_OFF || iterative_mode > PGVRX_ITER_STRICT) {                          // options.rs:168-175
+        snprintf(msg, sizeof msg, "invalid value for parameter \"hnsw.iterative_scan\": \"%d\"", iterative_mode);
+        return pgvrx_fail(ix, PGVRX_ERR_INVALID, msg);
+    }
+    if (max_scan_tuples < 1 || max_scan_tuples > (int64_t)0x7fffffff) {                                   // options.rs:177-186
+        snprintf(msg, sizeof msg, "%lld is outside the valid range for parameter \"hnsw.max_scan_tuples\" (1 .. 2147483647)", (long long)max_scan_tuples);
+        return pgvrx_fail(ix, PGVRX_ERR_INVALID, msg);
+    }
     if (nq < 0 || nq > (int64_t)1 << 24 || (nq > 0 && !queries)) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "bad queries");
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     pgvrx_scan *s = new (std::nothrow) pgvrx_scan();
