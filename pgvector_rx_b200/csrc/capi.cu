@@ -13,6 +13,7 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "index_internal.h"
@@ -301,8 +302,9 @@ int32_t pgvrx_level_from_uniform(double r, int32_t m) {
 // vector.rs:106-126 / halfvec.rs:204-233.  f32 -> half uses IEEE round-to-nearest-even
 // (__float2half_rn) except that the reference flushes |x| < 2^-24 to zero where IEEE would round
 // (2^-25, 2^-24) up to the smallest subnormal (halfvec.rs:111-113).
-int pgvrx_normalize(int32_t elem_type, int32_t dim, const void *in, void *out, double *norm_out) {
-    if (dim <= 0 || !in || !out) return fail(nullptr, PGVRX_ERR_INVALID, "bad normalize arguments");
+namespace {
+// one row; 0 = ok, 1 = halfvec overflow, 2 = the type has no norm.  No error state: also runs on worker threads.
+int normalize_row(int32_t elem_type, int32_t dim, const void *in, void *out, double *norm_out) {
     double norm = 0.0;
     if (elem_type == PGVRX_ELEM_F32) {
         const float *a = (const float *)in;
@@ -323,26 +325,57 @@ int pgvrx_normalize(int32_t elem_type, int32_t dim, const void *in, void *out, d
             if (std::isinf(__half2float(h))) overflow = true;
             r[i] = h;
         }
-        if (overflow) return fail(nullptr, PGVRX_ERR_INVALID, "value out of range: overflow");   // halfvec.rs:225-230
+        if (overflow) return 1;
     } else {
-        return fail(nullptr, PGVRX_ERR_INVALID, "type has no norm support function");
+        return 2;
     }
     if (norm_out) *norm_out = norm;
+    return 0;
+}
+int normalize_status(int code) {
+    if (code == 1) return fail(nullptr, PGVRX_ERR_INVALID, "value out of range: overflow");   // halfvec.rs:225-230
+    if (code == 2) return fail(nullptr, PGVRX_ERR_INVALID, "type has no norm support function");
     return PGVRX_OK;
+}
+}  // namespace
+
+int pgvrx_normalize(int32_t elem_type, int32_t dim, const void *in, void *out, double *norm_out) {
+    if (dim <= 0 || !in || !out) return fail(nullptr, PGVRX_ERR_INVALID, "bad normalize arguments");
+    return normalize_status(normalize_row(elem_type, dim, in, out, norm_out));
 }
 
 // n rows at once (row i at in + i * row_bytes); norms (optional) receives every row's norm.  Rows with norm 0 come out as
 // zero rows: the caller drops them from a build (build.rs:433-435) -- queries are normalised the same way (scan.rs:749-754).
+// Rows are independent: large batches (a CREATE INDEX worth of halfvec rows is seconds of software half conversions)
+// are split over host threads; the status is that of the first failing row, as in a sequential pass.
 int pgvrx_normalize_rows(int32_t elem_type, int32_t dim, const void *in, void *out, int64_t n, double *norms) {
     if (n < 0 || (n > 0 && (!in || !out))) return fail(nullptr, PGVRX_ERR_INVALID, "bad normalize arguments");
     const size_t rb = pgvrx_row_bytes(elem_type, dim);
     if (rb == 0) return fail(nullptr, PGVRX_ERR_INVALID, "bad normalize arguments");
-    for (int64_t i = 0; i < n; i++) {
-        double nm = 0.0;
-        int rc = pgvrx_normalize(elem_type, dim, (const uint8_t *)in + (size_t)i * rb, (uint8_t *)out + (size_t)i * rb, &nm);
-        if (rc) return rc;
-        if (norms) norms[i] = nm;
+    const int64_t work = n * (int64_t)dim;
+    int nt = (int)std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), work / (1 << 20));
+    if (n > 0 && (const uint8_t *)out < (const uint8_t *)in + (size_t)n * rb && (const uint8_t *)in < (const uint8_t *)out + (size_t)n * rb && out != in)
+        nt = 1;                                          // partially overlapping buffers: keep the sequential order
+    nt = std::max(nt, 1);
+    std::vector<int64_t> first_bad((size_t)nt, -1);
+    std::vector<int> bad_code((size_t)nt, 0);
+    auto run = [&](int t) {
+        const int64_t per = (n + nt - 1) / nt, lo = std::min(n, t * per), hi = std::min(n, lo + per);
+        for (int64_t i = lo; i < hi; i++) {
+            double nm = 0.0;
+            const int code = normalize_row(elem_type, dim, (const uint8_t *)in + (size_t)i * rb, (uint8_t *)out + (size_t)i * rb, &nm);
+            if (code) { first_bad[(size_t)t] = i; bad_code[(size_t)t] = code; return; }
+            if (norms) norms[i] = nm;
+        }
+    };
+    if (nt == 1) run(0);
+    else {
+        std::vector<std::thread> ts;
+        for (int t = 0; t < nt; t++) ts.emplace_back(run, t);
+        for (auto &t : ts) t.join();
     }
+    for (int t = 0; t < nt; t++)
+        if (first_bad[(size_t)t] >= 0) return normalize_status(bad_code[(size_t)t]);
     return PGVRX_OK;
 }
 

@@ -95,3 +95,28 @@ def test_integration_doc_lists_every_export():
     doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
     missing = [e for e in P.EXPORTS if e not in doc]
     assert not missing, missing
+
+
+def test_normalize_rows_on_host_threads_is_the_row_by_row_result():
+    # large batches are split over host threads (a CREATE INDEX worth of halfvec rows is seconds of software half
+    # conversions): same bits as one pgvrx_normalize call per row, in place as well, first failing row's error
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((40_000, 96)).astype(np.float32)
+    x[123] = 0.0                                                       # zero norm: comes out as a zero row
+    norms, u = P.normalize_rows(P.ELEM_F32, 96, x)
+    for i in (0, 123, 9_999, 39_999):
+        nm, row = P.normalize(P.ELEM_F32, 96, x[i])
+        assert nm == norms[i] and np.array_equal(row.view(np.uint32), u[i].view(np.uint32))
+    assert norms[123] == 0.0 and not u[123].any()
+    h = (rng.standard_normal((12_000, 256)) * 3).astype(np.float16).view(np.uint16)
+    hn, hu = P.normalize_rows(P.ELEM_F16, 256, h)
+    one = np.stack([P.normalize(P.ELEM_F16, 256, r)[1] for r in h[::997]])
+    assert np.array_equal(hu[::997], one)
+    inplace = h.copy()
+    L = P.lib()
+    assert L.pgvrx_normalize_rows(P.ELEM_F16, 256, P._p(inplace), P._p(inplace), len(inplace), None) == 0
+    assert np.array_equal(inplace, hu)
+    # an error from a worker thread reaches the caller's error state
+    with pytest.raises(P.PgvrxError) as e:
+        P.normalize_rows(P.ELEM_BIT, 256 * 8, np.zeros((8192, 256), np.uint8))
+    assert "no norm support" in str(e.value)
