@@ -216,7 +216,9 @@ typedef struct {
  * for cosine opclasses, zero-norm rows must be dropped and the rest normalised by the caller, as
  * build.rs:411-438 does before the insert).  levels[i] is the level of row i (the reference draws it
  * from an unseeded RNG, build.rs:373-377; use pgvrx_level_from_uniform).  heap_tids[i] (optional,
- * default i) is recorded per element, up to 10 per element for byte-identical duplicates.
+ * default i) is recorded per element, up to 10 per element for byte-identical duplicates.  The library treats
+ * them as opaque 64-bit values; pass real ItemPointers as (block << 16 | offset), offset >= 1, when the graph is to be
+ * written out with pgvrx_pages_write (which refuses offset 0: a reader would take it for "no heap TID").
  * The search_layer calls of find_element_neighbors (graph/mod.rs:386,407) run on the GPU in
  * speculative batches; select_neighbors, update_neighbor_connections, the duplicate rule and the
  * entry-point rule run on the host in the reference's order, and a batched result is only used when

@@ -173,7 +173,7 @@ extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int
             wr16(base + (size_t)sl->blk * BLCKSZ + 12, (uint16_t)(PAGE_HDR + (size_t)sl->off * ITEMID));
             wr16(base + (size_t)sl->blk * BLCKSZ + 14, sl->at);
         }
-    std::atomic<int> bad{0};                                             // 1 = heap TID count, 2 = neighbour id
+    std::atomic<int> bad{0};                                             // 1 = heap TID count, 2 = neighbour id, 3 = heap TID form
     parallel_ranges(n, 16384, [&](int64_t lo, int64_t hi) {
         std::vector<uint8_t> etup(etup_size), ntup;
         for (int64_t i = lo; i < hi; i++) {
@@ -191,6 +191,8 @@ extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int
                     // caller's TIDs are (block << 16 | offset); without them element i gets the synthetic TID of row i:
                     // block i / 65535, offset i % 65535 + 1 -- the offset is never 0, which would read as "no heap TID"
                     const uint64_t v = heap_tids ? heap_tids[(size_t)i * PGVRX_HEAPTIDS + t] : ((((uint64_t)i / 0xffffu) << 16) | ((uint64_t)i % 0xffffu + 1));
+                    // offset 0 is InvalidOffsetNumber: readers stop at it (scan.rs:203-209) and the element would lose its rows
+                    if ((v & 0xffffu) == 0 || (v >> 16) >= 0xFFFFFFFFull) { bad.store(3); return; }
                     wr_tid(slot, (uint32_t)(v >> 16), (uint16_t)(v & 0xffffu));
                 } else {
                     wr_invalid_tid(slot);
@@ -227,5 +229,6 @@ extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int
     });
     if (bad.load() == 1) return fail("pgvector-rx: an element holds at most 10 heap TIDs");
     if (bad.load() == 2) return fail("pgvector-rx: neighbour id out of range");
+    if (bad.load() == 3) return fail("pgvector-rx: heap TID is not (block << 16 | offset) with offset >= 1");
     return PGVRX_OK;
 }

@@ -226,6 +226,16 @@ def test_writer_and_exporter_on_their_threaded_paths():
         assert "does not reference an element tuple" in str(ex) or "entry point" in str(ex)
 
 
+def test_writer_rejects_heap_tids_a_reader_would_drop():
+    # a TID with offset 0 (e.g. a bare row number used as a TID) reads back as "no heap TID" (scan.rs:203-209)
+    o = oracle_index("vector_l2_ops", 4, make_rows("f32", 50, 4, 2), m=4, efc=16)
+    tids, cnt = fixture_tids(o)
+    tids[7, 0] = np.uint64(3 << 16)
+    with pytest.raises(P.PgvrxError) as e:
+        P.write_pages(P.ELEM_F32, 4, 4, 16, o.export_graph(), tids, cnt)
+    assert "offset >= 1" in str(e.value)
+
+
 def test_writer_rejects_bad_input():
     o = oracle_index("vector_l2_ops", 8, make_rows("f32", 50, 8, 1), m=4, efc=16)
     g = o.export_graph()
