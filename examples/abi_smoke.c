@@ -45,6 +45,18 @@ int main(int argc, char **argv) {
         free(pages);
     }
 
+    /* amgettuple's fan-out (scan.rs:798): element 1 holds TIDs {7, 8, 9}, element 0 holds {5}; -1 is result padding */
+    {
+        uint64_t tids[2 * PGVRX_HEAPTIDS], out[8];
+        uint8_t counts[2] = {1, 3};
+        int32_t ids[3] = {1, -1, 0};
+        int64_t n_out = 0;
+        memset(tids, 0xff, sizeof tids);
+        tids[0] = 5; tids[PGVRX_HEAPTIDS] = 7; tids[PGVRX_HEAPTIDS + 1] = 8; tids[PGVRX_HEAPTIDS + 2] = 9;
+        CHECK(pgvrx_heap_tid_stream(ids, 3, tids, counts, 2, out, 8, &n_out) == PGVRX_OK);
+        CHECK(n_out == 4 && out[0] == 9 && out[1] == 8 && out[2] == 7 && out[3] == 5);
+    }
+
     if (!want_gpu) {
         pgvrx_index_desc d;
         pgvrx_index *ix = NULL;
