@@ -359,8 +359,9 @@ int pgvrx_normalize_rows(int32_t elem_type, int32_t dim, const void *in, void *o
     nt = std::max(nt, 1);
     std::vector<int64_t> first_bad((size_t)nt, -1);
     std::vector<int> bad_code((size_t)nt, 0);
-    auto run = [&](int t) {
-        const int64_t per = (n + nt - 1) / nt, lo = std::min(n, t * per), hi = std::min(n, lo + per);
+    const int64_t per = (n + nt - 1) / nt;
+    auto run = [&](int t, int64_t hi_cap) {               // hi_cap < 0: the chunk's own end
+        const int64_t lo = std::min(n, t * per), hi = hi_cap < 0 ? std::min(n, lo + per) : hi_cap;
         for (int64_t i = lo; i < hi; i++) {
             double nm = 0.0;
             const int code = normalize_row(elem_type, dim, (const uint8_t *)in + (size_t)i * rb, (uint8_t *)out + (size_t)i * rb, &nm);
@@ -368,10 +369,18 @@ int pgvrx_normalize_rows(int32_t elem_type, int32_t dim, const void *in, void *o
             if (norms) norms[i] = nm;
         }
     };
-    if (nt == 1) run(0);
+    if (nt == 1) run(0, -1);
     else {
         std::vector<std::thread> ts;
-        for (int t = 0; t < nt; t++) ts.emplace_back(run, t);
+        int started = 0;
+        try {                                             // a thread that cannot be created leaves the rest to this one
+            ts.reserve((size_t)nt);
+            for (; started < nt; started++) ts.emplace_back(run, started, (int64_t)-1);
+        } catch (...) {
+        }
+        if (started < nt) {                               // chunks started..nt-1 as one range, reported under slot `started`
+            run(started, n);
+        }
         for (auto &t : ts) t.join();
     }
     for (int t = 0; t < nt; t++)

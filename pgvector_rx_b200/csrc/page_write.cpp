@@ -88,7 +88,13 @@ template <class F> void parallel_ranges(int64_t n, int64_t grain, F fn) {
     if (nt <= 1) { fn((int64_t)0, n); return; }
     std::vector<std::thread> ts;
     const int64_t per = (n + nt - 1) / nt;
-    for (int t = 0; t < nt; t++) ts.emplace_back([=]() { fn(std::min(n, t * per), std::min(n, (t + 1) * per)); });
+    int started = 0;
+    try {                                                 // no exception may cross the C ABI: a thread that cannot be
+        ts.reserve((size_t)nt);                           // created (EAGAIN) leaves its range to the calling thread
+        for (; started < nt; started++) ts.emplace_back([=]() { fn(std::min(n, started * per), std::min(n, (started + 1) * per)); });
+    } catch (...) {
+    }
+    if (started < nt) fn(std::min(n, started * per), n);
     for (auto &t : ts) t.join();
 }
 
