@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -179,14 +180,14 @@ int inspect_walk(const Pages &pg, int32_t elem_type, pgvrx_pages_info *info, Wal
 
 extern "C" {
 
-int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, pgvrx_pages_info *info) {
+static int pgvrx_pages_inspect_impl(const void *pages, int64_t n_pages, int32_t elem_type, pgvrx_pages_info *info) {
     if (!pages || !info || n_pages < 2) return err("pgvector-rx: need the meta page and the head page");
     Pages pg{(const uint8_t *)pages, n_pages};
     Walk w;
     return inspect_walk(pg, elem_type, info, w);
 }
 
-int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, void *rows, uint8_t *level, int32_t *adj0,
+static int pgvrx_pages_export_impl(const void *pages, int64_t n_pages, int32_t elem_type, void *rows, uint8_t *level, int32_t *adj0,
                        int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids, uint8_t *heap_tid_counts) {
     if (!pages || n_pages < 2) return err("pgvector-rx: need the meta page and the head page");
     Pages pg{(const uint8_t *)pages, n_pages};
@@ -256,7 +257,7 @@ int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, vo
     return PGVRX_OK;
 }
 
-int pgvrx_pages_element_flags(const void *pages, int64_t n_pages, uint8_t *flags) {
+static int pgvrx_pages_element_flags_impl(const void *pages, int64_t n_pages, uint8_t *flags) {
     if (!pages || !flags || n_pages < 2) return err("pgvector-rx: need the meta page and the head page");
     Pages pg{(const uint8_t *)pages, n_pages};
     Walk w;
@@ -289,6 +290,24 @@ int pgvrx_heap_tid_stream(const int32_t *elem_ids, int64_t n_ids, const uint64_t
     }
     *n_out = k;                                                          // k > cap: call again with a larger buffer
     return PGVRX_OK;
+}
+
+// The entry points proper: host memory running out while the tables for a huge (or corrupt) relation are built comes
+// back as a status code -- no exception crosses the C ABI.
+#define PGVRX_NOTHROW(call)                                                           \
+    try { return call; }                                                              \
+    catch (const std::bad_alloc &) { pgvrx_host::set_create_error("pgvector-rx: out of host memory"); return PGVRX_ERR_NOMEM; } \
+    catch (...) { pgvrx_host::set_create_error("pgvector-rx: unexpected host error"); return PGVRX_ERR_INVALID; }
+
+int pgvrx_pages_inspect(const void *pages, int64_t n_pages, int32_t elem_type, pgvrx_pages_info *info) {
+    PGVRX_NOTHROW(pgvrx_pages_inspect_impl(pages, n_pages, elem_type, info))
+}
+int pgvrx_pages_export(const void *pages, int64_t n_pages, int32_t elem_type, void *rows, uint8_t *level, int32_t *adj0,
+                       int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids, uint8_t *heap_tid_counts) {
+    PGVRX_NOTHROW(pgvrx_pages_export_impl(pages, n_pages, elem_type, rows, level, adj0, upper_base, adj_up, heap_tids, heap_tid_counts))
+}
+int pgvrx_pages_element_flags(const void *pages, int64_t n_pages, uint8_t *flags) {
+    PGVRX_NOTHROW(pgvrx_pages_element_flags_impl(pages, n_pages, flags))
 }
 
 }  // extern "C"

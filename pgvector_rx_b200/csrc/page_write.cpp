@@ -18,6 +18,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -100,7 +101,7 @@ template <class F> void parallel_ranges(int64_t n, int64_t grain, F fn) {
 
 }  // namespace
 
-extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_construction, int64_t n, const void *rows,
+static int pages_write_impl(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_construction, int64_t n, const void *rows,
                                  const uint8_t *level, const int32_t *adj0, const int32_t *upper_base, const int32_t *adj_up,
                                  int64_t n_upper_rows, int64_t entry, const uint64_t *heap_tids, const uint8_t *heap_tid_counts, void *pages,
                                  int64_t cap_pages, int64_t *n_pages_out) {
@@ -237,4 +238,19 @@ extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int
     if (bad.load() == 2) return fail("pgvector-rx: neighbour id out of range");
     if (bad.load() == 3) return fail("pgvector-rx: heap TID is not (block << 16 | offset) with offset >= 1");
     return PGVRX_OK;
+}
+
+// no exception crosses the C ABI: the placement table of a huge graph not fitting in host memory is a status code
+extern "C" int pgvrx_pages_write(int32_t elem_type, int32_t dims, int32_t m, int32_t ef_construction, int64_t n, const void *rows,
+                                 const uint8_t *level, const int32_t *adj0, const int32_t *upper_base, const int32_t *adj_up,
+                                 int64_t n_upper_rows, int64_t entry, const uint64_t *heap_tids, const uint8_t *heap_tid_counts, void *pages,
+                                 int64_t cap_pages, int64_t *n_pages_out) {
+    try {
+        return pages_write_impl(elem_type, dims, m, ef_construction, n, rows, level, adj0, upper_base, adj_up, n_upper_rows, entry,
+                                heap_tids, heap_tid_counts, pages, cap_pages, n_pages_out);
+    } catch (const std::bad_alloc &) {
+        return fail("pgvector-rx: out of host memory"), PGVRX_ERR_NOMEM;
+    } catch (...) {
+        return fail("pgvector-rx: unexpected host error");
+    }
 }
