@@ -1229,14 +1229,27 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     return PGVRX_OK;
 }
 
+// the host mirror could not grow: the graph may be half-updated, the handle is only good for pgvrx_index_destroy
+static int host_oom(pgvrx_index *ix) {
+    return ix ? pgvrx_fail(ix, PGVRX_ERR_NOMEM, "out of host memory while updating the index (destroy the handle)") : PGVRX_ERR_NOMEM;
+}
+
 int pgvrx_index_build(pgvrx_index *ix, const void *rows, int64_t n_rows, const int32_t *levels, const uint64_t *heap_tids,
                       int32_t host_threads, pgvrx_build_stats *stats) {
-    return run_inserts(ix, rows, n_rows, levels, heap_tids, host_threads, stats, false);
+    try {
+        return run_inserts(ix, rows, n_rows, levels, heap_tids, host_threads, stats, false);
+    } catch (const std::bad_alloc &) {                   // no exception crosses the C ABI
+        return host_oom(ix);
+    }
 }
 
 int pgvrx_index_insert(pgvrx_index *ix, const void *rows, int64_t n_rows, const int32_t *levels, const uint64_t *heap_tids,
                        int32_t host_threads, pgvrx_build_stats *stats) {
-    return run_inserts(ix, rows, n_rows, levels, heap_tids, host_threads, stats, true);
+    try {
+        return run_inserts(ix, rows, n_rows, levels, heap_tids, host_threads, stats, true);
+    } catch (const std::bad_alloc &) {
+        return host_oom(ix);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1251,7 +1264,7 @@ int pgvrx_index_insert(pgvrx_index *ix, const void *rows, int64_t n_rows, const 
 //                               searched again.
 //   pass 3 (vacuum.rs:655-790)  emptied elements are marked deleted, their lists and values cleared
 // ------------------------------------------------------------------------------------------------
-int pgvrx_index_vacuum(pgvrx_index *ix, const uint64_t *dead_tids, int64_t n_dead, int32_t host_threads, pgvrx_vacuum_stats *stats) {
+int pgvrx_index_vacuum(pgvrx_index *ix, const uint64_t *dead_tids, int64_t n_dead, int32_t host_threads, pgvrx_vacuum_stats *stats) try {
     if (!ix) return PGVRX_ERR_INVALID;
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_dead < 0 || (n_dead > 0 && !dead_tids)) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null dead TID list");
@@ -1566,6 +1579,8 @@ int pgvrx_index_vacuum(pgvrx_index *ix, const uint64_t *dead_tids, int64_t n_dea
         stats->total_ms = now_ms() - t_start;
     }
     return PGVRX_OK;
+} catch (const std::bad_alloc &) {
+    return host_oom(ix);
 }
 
 int pgvrx_index_element_flags(pgvrx_index *ix, uint8_t *flags, int64_t n) {
