@@ -1,6 +1,7 @@
 """a19: the product's page exporter against pages written by the oracle exactly as the reference's
 flush phase does (build.rs:545-821).  No PostgreSQL exists in this image, so the fixture is
 synthesised; the exporter and the writer are independent implementations of the same layout."""
+import os
 import struct
 
 import numpy as np
@@ -297,3 +298,32 @@ def test_heap_tid_stream_matches_amgettuple_order():
     k = C.c_int64(0)
     assert P.lib().pgvrx_heap_tid_stream(P._p(ids), 2, P._p(g["heap_tids"]), P._p(g["heap_tid_counts"]), g["n"], P._p(out), 3, C.byref(k)) == 0
     assert k.value == int(g["heap_tid_counts"][0]) + int(g["heap_tid_counts"][1]) > 3 and out[3] == 7
+
+
+# ---- the on-disk format, frozen ---------------------------------------------------------------------------------------
+def test_relation_bytes_match_the_frozen_digests():
+    # tests/golden/pages_sha256.json (made by tests/golden/make_pages_golden.py): both page writers -- the oracle's and
+    # the product's pgvrx_pages_write -- must still produce those bytes, so the two cannot drift together
+    import hashlib
+    import importlib.util
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_pages_golden", os.path.join(here, "make_pages_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    want = json.load(open(os.path.join(here, "pages_sha256.json")))
+    assert set(want) == set(G.CASES) | {"vector_l2_vacuumed"}
+    for name, (opclass, kind, n, dim, m, efc, seed) in G.CASES.items():
+        o = G.relation(name)
+        pages = o.write_pages()
+        assert G.digest(pages) == want[name], name
+        tids, cnt = fixture_tids(o)
+        mine = P.write_pages(P.OPCLASSES[opclass][0], dim, m, efc, o.export_graph(), tids, cnt)
+        assert hashlib.sha256(mine.tobytes()).hexdigest() == want[name]["sha256"], name
+    # a vacuumed relation has no flush-layout twin (deleted values are zeroed in place): the oracle's bytes only, and
+    # what the exporter reads out of them
+    ov = G.vacuumed_relation()
+    pv = ov.write_pages()
+    assert G.digest(pv) == want["vector_l2_vacuumed"]
+    g = P.export_pages(pv, P.ELEM_F32)
+    assert np.array_equal(g["flags"], ov.element_flags()) and g["n_deleted"] == int((ov.element_flags() & 1).sum())
