@@ -342,6 +342,24 @@ int pgvrx_topk_merge_device(pgvrx_index *idx, const int32_t *d_part_ids, const f
                             int32_t n_parts, int64_t nq, int32_t k_in, int32_t k_out, int32_t *d_out_ids,
                             float *d_out_dists, void *cuda_stream);
 
+/* ---- diagnostics: the ceiling the scan kernel's row gathers are measured against ------------------------------ */
+/* Random row_stride-byte gathers from the handle's vector table with the scan kernel's own transfer mechanism (one TMA
+ * bulk copy per row into a per-warp staging area, persistent one-warp CTAs) and nothing else -- no visited set, no
+ * distances.  mode 0: row ids uniform over the table; mode 1: a random walk over the layer-0 adjacency (the hub reuse,
+ * hence the L2 hit rate, of real searches; needs a loaded graph).  warps_per_sm 0 = as many as fit; rows_per_step rows
+ * per mbarrier phase (the scan uses 32 for 512-byte rows), depth phases in flight per warp, consume != 0 reads every
+ * staged byte back from shared memory (as the distance loop does).  Measures gathered bytes per second: the denominator
+ * bench.py reports next to the HBM copy peak. */
+typedef struct {
+    uint64_t bytes_per_launch;
+    double   ms_per_launch;
+    double   gb_per_s;
+    int32_t  warps_per_sm, grid;
+    uint32_t row_bytes;
+} pgvrx_gather_probe_result;
+int pgvrx_gather_probe(pgvrx_index *idx, int32_t mode, int32_t warps_per_sm, int32_t rows_per_step, int32_t depth,
+                       int32_t steps, int32_t consume, pgvrx_gather_probe_result *out);
+
 /* ---- scan: iterative index scan (hnsw.iterative_scan = relaxed_order | strict_order) ------------- */
 /* A pgvrx_scan is what amrescan creates for a batch of queries: per query the visited set, the
  * discarded heap, the tuple count and the strict-order watermark (HnswScanState, scan.rs:586-617)

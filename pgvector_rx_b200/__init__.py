@@ -44,6 +44,7 @@ EXPORTS = [
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
     "pgvrx_pages_element_flags", "pgvrx_heap_tid_stream", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
     "pgvrx_index_set_heap_tids", "pgvrx_pages_write", "pgvrx_index_vacuum", "pgvrx_index_element_flags",
+    "pgvrx_gather_probe",
 ]
 ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
 
@@ -91,6 +92,14 @@ class SearchStats(C.Structure):
     _fields_ = [("n_dist", C.c_uint64), ("n_expand0", C.c_uint64), ("n_expand_upper", C.c_uint64),
                 ("n_visited", C.c_uint64), ("n_retried", C.c_uint64), ("n_launches", C.c_uint32),
                 ("kernel_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class GatherProbeResult(C.Structure):
+    _fields_ = [("bytes_per_launch", C.c_uint64), ("ms_per_launch", C.c_double), ("gb_per_s", C.c_double),
+                ("warps_per_sm", C.c_int32), ("grid", C.c_int32), ("row_bytes", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -154,6 +163,7 @@ def lib():
         "pgvrx_scan_begin": (C.c_int, [vp, vp, i64, i32, i32, i64, C.POINTER(vp)]),
         "pgvrx_scan_next": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(SearchStats)]),
         "pgvrx_scan_end": (None, [vp]),
+        "pgvrx_gather_probe": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, C.POINTER(GatherProbeResult)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -405,16 +415,21 @@ class HnswIndex:
                     level=level, adj0=adj0, upper_base=upper_base, adj_up=adj_up[:gi["n_upper_rows"]],
                     entry=gi["entry"], n=n, heap_tids=tids, heap_tid_counts=cnt)
 
-    def prepare_queries(self, queries):
-        """Query-side half of the opclass: normalise when FUNCTION 2 exists (scan.rs:749-754)."""
+    def prepare_queries(self, queries, prepared=False):
+        """Query-side half of the opclass: normalise when FUNCTION 2 exists (scan.rs:749-754).  prepared=True: the
+        caller already did (normalising a unit vector again would change its last bits)."""
         q = _rows(self.elem, self.dim, queries)
-        if self.normalized:
+        if self.normalized and not prepared:
             q = normalize_rows(self.elem, self.dim, q)[1]
         return q
 
-    def search(self, queries, k=10, ef_search=None, with_stats=False):
+    def load_graph_stored(self, rows, level, adj0, upper_base, adj_up, entry):
+        """load_graph under the name bench.py uses to stress that `rows` are in stored form (already normalised)."""
+        self.load_graph(rows, level, adj0, upper_base, adj_up, entry)
+
+    def search(self, queries, k=10, ef_search=None, with_stats=False, prepared=False):
         """Batched index scan (hnsw.iterative_scan = off): k nearest element ids per query."""
-        q = self.prepare_queries(queries)
+        q = self.prepare_queries(queries, prepared)
         ef = self.ef_search if ef_search is None else ef_search
         nq = len(q)
         ids = np.empty((nq, k), np.int32)
@@ -440,9 +455,14 @@ class HnswIndex:
             rows = normalize_rows(self.elem, self.dim, rows)[1]
         self._check(self.L.pgvrx_index_load_rows(self.h, _p(rows), len(rows)))
 
-    def flat_topk(self, queries, k=10, with_stats=False):
+    def load_rows_stored(self, rows):
+        """load_rows for rows that are already in stored form (normalised where the opclass normalises)."""
+        rows = _rows(self.elem, self.dim, rows)
+        self._check(self.L.pgvrx_index_load_rows(self.h, _p(rows), len(rows)))
+
+    def flat_topk(self, queries, k=10, with_stats=False, prepared=False):
         """Exact k nearest rows per query, ordered by (distance, id)."""
-        q = self.prepare_queries(queries)
+        q = self.prepare_queries(queries, prepared)
         nq = len(q)
         ids = np.empty((nq, k), np.int32)
         dists = np.empty((nq, k), np.float32)
@@ -464,9 +484,9 @@ class HnswIndex:
         self._check(self.L.pgvrx_flat_tc_scores(self.h, _p(q), len(q), _p(scores), _p(eps)))
         return scores, eps
 
-    def rerank(self, queries, cand_ids, k=10):
+    def rerank(self, queries, cand_ids, k=10, prepared=False):
         """Exact distances of each query's candidate ids (-1 = none); the k nearest by (distance, id)."""
-        q = self.prepare_queries(queries)
+        q = self.prepare_queries(queries, prepared)
         cand = np.ascontiguousarray(cand_ids, np.int32)
         nq, nc = cand.shape
         if nq != len(q):
@@ -481,10 +501,16 @@ class HnswIndex:
         self._check(self.L.pgvrx_topk_merge_device(self.h, d_part_ids_ptr, d_part_dists_ptr, n_parts, nq, k_in, k_out,
                                                    d_out_ids_ptr, d_out_dists_ptr, C.c_void_p(stream) if stream else None))
 
+    def gather_probe(self, mode=1, warps_per_sm=0, rows_per_step=32, depth=1, steps=256, consume=1):
+        """Diagnostic: bytes/s of random row gathers with the scan kernel's TMA mechanism (see the header)."""
+        r = GatherProbeResult()
+        self._check(self.L.pgvrx_gather_probe(self.h, mode, warps_per_sm, rows_per_step, depth, steps, consume, C.byref(r)))
+        return r.as_dict()
+
     # ---- iterative scan (hnsw.iterative_scan, hnsw.max_scan_tuples: options.rs:85-91) ----
-    def scan_begin(self, queries, ef_search=None, iterative_scan=ITER_RELAXED, max_scan_tuples=20000):
+    def scan_begin(self, queries, ef_search=None, iterative_scan=ITER_RELAXED, max_scan_tuples=20000, prepared=False):
         return IterativeScan(self, queries, self.ef_search if ef_search is None else ef_search, iterative_scan,
-                             max_scan_tuples)
+                             max_scan_tuples, prepared)
 
 
 class IterativeScan:
@@ -492,9 +518,9 @@ class IterativeScan:
     elements in amgettuple's emission order; `stream(limit)` drives rounds until every query has
     `limit` elements or is exhausted."""
 
-    def __init__(self, index, queries, ef_search, mode, max_scan_tuples):
+    def __init__(self, index, queries, ef_search, mode, max_scan_tuples, prepared=False):
         self.ix, self.ef = index, ef_search
-        q = index.prepare_queries(queries)
+        q = index.prepare_queries(queries, prepared)
         self.nq = len(q)
         h = C.c_void_p()
         index._check(index.L.pgvrx_scan_begin(index.h, _p(q), self.nq, ef_search, mode, max_scan_tuples, C.byref(h)))

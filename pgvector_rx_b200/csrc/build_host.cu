@@ -607,6 +607,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     CU_TRY(ix, ix->adj_up.ensure_keep(std::max<size_t>(16, (size_t)up_needed * m * 4), (size_t)g.n_upper * m * 4));
     CU_TRY(ix, ix->upper_base.ensure_keep(std::max<size_t>(16, (size_t)cap * 4), (size_t)g.n * 4));
     CU_TRY(ix, ix->level.ensure_keep(std::max<size_t>(16, (size_t)cap), (size_t)g.n));
+    ix->generation++;                  // open iterative scans were sized for the old graph
     ix->loaded = false;
     ix->rows_loaded = false;
     ix->tc_ready = false;
@@ -723,7 +724,16 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
 
     int window = 4;
     const int WINDOW_MAX = 512;
-    bool big_next = false;
+    // scratch escalation for a search that overflowed its visited table / tie tail: the head of the round is re-run alone
+    // with 16x, 256x, 4096x the visited table (the ef = 1 descent then uses the whole table too) and 2048 / 8192 / 20000
+    // tie slots; if even that is not enough the call fails instead of repeating the same round for ever
+    int big_level = 0;
+    const int BIG_MAX = 3;
+    int big_tail[4] = {-1, 2048, 8192, 20000};
+    if (const char *e = getenv("PGVRX_BUILD_TAILS")) {      // "a,b,c": tie slots of the three escalation levels (tests)
+        int a = 0, b = 0, c = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && b >= a && c >= b && c <= 20000) { big_tail[1] = a; big_tail[2] = b; big_tail[3] = c; }
+    }
     const int rs_cap = std::max(256, 6 * efc + 64);
     const int rs_ent = 3 + (l0 + 31) / 32;               // node, f_dist bits, layer, near-mask words of the list read
     struct GroupPart {                                  // groups of the nodes with node % NP == part; reused across rounds
@@ -756,7 +766,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     PinnedBuf &h_pack = g.scratch->h_pack;
 
     while (f < n_rows) {
-        const int B = (int)std::min<int64_t>(big_next ? 1 : window, n_rows - f);
+        const int B = (int)std::min<int64_t>(big_level > 0 ? 1 : window, n_rows - f);
         const double tP0 = now_ms();
         g.round++;
         n_rounds++;
@@ -785,8 +795,9 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         // ---- K2 on the GPU ----
         ScanConfig cfg;
         uint32_t vis_entries = pgvrx_pow2_at_least(std::max<uint64_t>(1024, (uint64_t)efc * 2 * m * 4));
-        if (big_next) vis_entries = pgvrx_pow2_at_least(std::min<uint64_t>((uint64_t)vis_entries * 16, std::max<uint64_t>(1024, (uint64_t)cap * 2)));
-        rc = pgvrx_make_config(ix, efc, big_next ? 2048 : -1, vis_entries, B, 0, true, &cfg);
+        if (big_level > 0)
+            vis_entries = pgvrx_pow2_at_least(std::min<uint64_t>((uint64_t)vis_entries << (4 * big_level), std::max<uint64_t>(1024, (uint64_t)cap * 2)));
+        rc = pgvrx_make_config(ix, efc, big_tail[big_level], vis_entries, B, 0, true, &cfg);
         if (rc) return rc;
         const int wpb = cfg.wpb;
         CU_TRY(ix, rb.vis.ensure((size_t)cfg.grid * wpb * cfg.vis_entries * 4));
@@ -830,6 +841,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         bp.out_ctr = (uint32_t *)(dpk + o_ctr);
         bp.vis_base = (uint32_t *)rb.vis.p;
         bp.vis_entries = cfg.vis_entries;
+        bp.up_entries = big_level > 0 ? cfg.vis_entries : std::min<uint32_t>(cfg.vis_entries, 1024u);
         bp.work_counter = (int *)rb.work.p;
         bp.stage_stride = cfg.L.stage_stride;
         bp.R = cfg.L.R;
@@ -1046,7 +1058,20 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
             Pending &p = pend[(size_t)i];
             const int64_t e = e_base + i;
             if (h_status[(size_t)i] != 0) {                     // scratch overflow: redo alone with large scratch
-                if (i == 0) { big_next = true; n_retry_big++; }
+                if (i == 0) {
+                    if (big_level >= BIG_MAX) {
+                        char b[200];
+                        snprintf(b, sizeof b, "the search for input row %lld exhausted the largest search scratch (status %u: %s)",
+                                 (long long)(f + i), h_status[(size_t)i],
+                                 (h_status[(size_t)i] & 2u) ? "too many candidates tie with the furthest result" : "visited table");
+                        grow_host(g.n, g.n_upper);          // drop the provisional elements of this round
+                        ix->n = g.n; ix->n_upper = g.n_upper; ix->entry = g.entry; ix->entry_level = g.entry_level;
+                        ix->loaded = g.n > 0; ix->rows_loaded = g.n > 0;
+                        return pgvrx_fail(ix, PGVRX_ERR_UNSUPPORTED, b);
+                    }
+                    big_level++;
+                    n_retry_big++;
+                }
                 break;
             }
             // -- is the speculative search still the one a sequential build would have run? --
@@ -1111,7 +1136,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
             c_dist += h_ctr[(size_t)i * 4];
             c_exp0 += h_ctr[(size_t)i * 4 + 1];
             c_expu += h_ctr[(size_t)i * 4 + 2];
-            big_next = false;
+            big_level = 0;
             committed++;
             // duplicate merge (build.rs:495-512): the probe skipped the TID-capacity test, apply it in order here
             bool merged = false;
@@ -1191,7 +1216,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         // input rows consumed this round: committed elements plus a merged duplicate
         const double tT0 = now_ms();
         f += committed;
-        if (!big_next) window = std::min(WINDOW_MAX, std::max(4, 2 * committed + 2));
+        if (big_level == 0) window = std::min(WINDOW_MAX, std::max(4, 2 * committed + 2));
         // host arrays beyond g.n hold provisional (uncommitted) elements; shrink the logical size back
         grow_host(g.n, g.n_upper);
         t_tail += now_ms() - tT0;
@@ -1271,6 +1296,7 @@ int pgvrx_index_vacuum(pgvrx_index *ix, const uint64_t *dead_tids, int64_t n_dea
     if (!ix->loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "no graph loaded");
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     CU_TRY(ix, cudaDeviceSynchronize());              // scans in flight read the lists this call rewrites
+    ix->generation++;
     int avail = (int)std::max(1u, std::thread::hardware_concurrency());
     {
         cpu_set_t set;
@@ -1432,6 +1458,7 @@ int pgvrx_index_vacuum(pgvrx_index *ix, const uint64_t *dead_tids, int64_t n_dea
         rp.out_ctr = (uint32_t *)(dpk + o_ctr);
         rp.vis_base = (uint32_t *)rb.vis.p;
         rp.vis_entries = cfg.vis_entries;
+        rp.up_entries = cfg.vis_entries;
         rp.work_counter = (int *)rb.work.p;
         rp.stage_stride = cfg.L.stage_stride;
         rp.R = cfg.L.R;

@@ -105,6 +105,7 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     // (the build's latency-bound rounds measured the same with 1 or 4 warps per CTA: 12.4 s of kernels for 300k rows)
     int wpb = for_build ? SEARCH_THREADS / 32 : 1;
     if (const char *e = getenv(for_build ? "PGVRX_BUILD_WARPS" : "PGVRX_SCAN_WARPS")) { int w = atoi(e); if (w >= 1 && w <= SEARCH_THREADS / 32) wpb = w; }
+    if (tail_cap >= 2048) wpb = 1;   // retry / escalation geometry: the tie tail alone is 16 KiB or more per warp
     c.wpb = wpb;
     c.smem_block = search_warp_smem(c.L) * wpb;
     if (c.smem_block > 227 * 1024) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search configuration exceeds shared memory");
@@ -124,7 +125,8 @@ namespace {
 
 int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64_t nq, int ef, int k,
                 int32_t *d_ids, float *d_dists, int32_t *d_counts, pgvrx_search_stats *stats,
-                cudaStream_t stream, bool check_status) {
+                cudaStream_t stream, int64_t *n_failed /* NULL: asynchronous, per-query status stays on the device */,
+                int64_t *first_failed) {
     if (!ix->loaded) return fail(ix, PGVRX_ERR_STATE, "no graph loaded");
     if (ef < PGVRX_MIN_EF_SEARCH || ef > PGVRX_MAX_EF_SEARCH) {                         // options.rs:157-166, hnsw_vector.out:167-169
         char b[112];
@@ -194,6 +196,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
 #endif
     p.vis_base = (uint32_t *)sc->vis.p;
     p.vis_entries = main_cfg.vis_entries;
+    p.up_entries = std::min<uint32_t>(main_cfg.vis_entries, 1024u);   // cleared once per upper layer: keep it small
     p.work_counter = work + 0;
     p.stage_stride = main_cfg.L.stage_stride;
     p.R = main_cfg.L.R;
@@ -208,6 +211,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     r.tail_cap = retry_cfg.L.tail_cap;
     r.vis_base = (uint32_t *)sc->vis_retry.p;
     r.vis_entries = retry_cfg.vis_entries;
+    r.up_entries = retry_cfg.vis_entries;   // the retry's greedy descent gets the whole (16x) table as well
     r.work_counter = work + 1;
     r.stage_stride = retry_cfg.L.stage_stride;
     r.R = retry_cfg.L.R;
@@ -244,16 +248,17 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
         CU_TRY(ix, cudaMemcpy(&nf, work + 2, 4, cudaMemcpyDeviceToHost));
         stats->n_retried = (uint64_t)nf;
     }
-    if (check_status) {
+    if (n_failed) {
+        // per-query outcome: a query that exhausted its scratch even in the retry pass has out_counts = -1; the others
+        // are complete.  The caller reports the failure after it has handed out the results of the rest.
         CU_TRY(ix, cudaStreamSynchronize(stream));
         std::vector<uint32_t> st((size_t)nq);
         CU_TRY(ix, cudaMemcpy(st.data(), sc->status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+        *n_failed = 0;
         for (int64_t i = 0; i < nq; i++)
             if (st[(size_t)i] != 0) {
-                char b[160];
-                snprintf(b, sizeof b, "query %lld exhausted the search scratch (status %u) even after the retry pass",
-                         (long long)i, st[(size_t)i]);
-                return fail(ix, PGVRX_ERR_UNSUPPORTED, b);
+                if (*n_failed == 0 && first_failed) *first_failed = i;
+                (*n_failed)++;
             }
     }
     return PGVRX_OK;
@@ -486,6 +491,7 @@ int pgvrx_index_load_graph(pgvrx_index *ix, const void *rows, int64_t n, const u
         if (adj_up[i] < -1 || adj_up[i] >= n) return fail(ix, PGVRX_ERR_INVALID, "upper-layer neighbour id out of range");
 
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    ix->generation++;
     ix->loaded = false;
     ix->rows_loaded = false;
     ix->tc_ready = false;
@@ -526,6 +532,7 @@ int pgvrx_index_set_element_flags(pgvrx_index *ix, const uint8_t *flags, int64_t
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     // scans in flight on caller streams read the old flags: drain them before the table changes
     CU_TRY(ix, cudaDeviceSynchronize());
+    ix->generation++;
     if (!flags) { ix->has_flags = false; return PGVRX_OK; }
     if (n != ix->n) return fail(ix, PGVRX_ERR_INVALID, "flags must cover every element of the index");
     bool any = false;
@@ -547,7 +554,7 @@ int pgvrx_search_batch_device(pgvrx_index *ix, const void *d_queries, int64_t nq
     if (!ix) return PGVRX_ERR_INVALID;
     if (nq > 0 && (!d_queries || !d_ids || !d_dists || !d_counts)) return fail(ix, PGVRX_ERR_INVALID, "null device buffer");
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ix->stream;
-    return search_core(ix, d_queries, (uint32_t)ix->row_bytes, nq, ef_search, k, d_ids, d_dists, d_counts, stats, s, false);
+    return search_core(ix, d_queries, (uint32_t)ix->row_bytes, nq, ef_search, k, d_ids, d_dists, d_counts, stats, s, nullptr, nullptr);
 }
 
 // device-visible alias of a host buffer when it is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory):
@@ -582,15 +589,24 @@ int pgvrx_search_batch(pgvrx_index *ix, const void *queries, int64_t nq, int32_t
         CU_TRY(ix, ix->dists.ensure((size_t)nq * k * 4));
         CU_TRY(ix, ix->counts.ensure((size_t)nq * 4));
     }
+    int64_t n_failed = 0, first_failed = -1;
     int rc = search_core(ix, zq ? zq : ix->q.p, (uint32_t)ix->row_bytes, nq, ef_search, k, zc_out ? (int32_t *)zi : (int32_t *)ix->ids.p,
                          zc_out ? (float *)zd : (float *)ix->dists.p, zc_out ? (int32_t *)zcnt : (int32_t *)ix->counts.p, stats,
-                         ix->stream, true);
+                         ix->stream, &n_failed, &first_failed);
     if (rc) return rc;
     if (!zc_out) {
         CU_TRY(ix, cudaMemcpyAsync(out_ids, ix->ids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
         CU_TRY(ix, cudaMemcpyAsync(out_dists, ix->dists.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
         CU_TRY(ix, cudaMemcpyAsync(out_counts, ix->counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->stream));
         CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+    }
+    if (n_failed > 0) {
+        // every other query's rows are in the caller's arrays; the failed ones carry out_counts = -1
+        char b[200];
+        snprintf(b, sizeof b, "%lld of %lld queries exhausted the search scratch even in the retry pass (first: query %lld); "
+                              "their out_counts are -1, the other results are complete",
+                 (long long)n_failed, (long long)nq, (long long)first_failed);
+        return fail(ix, PGVRX_ERR_UNSUPPORTED, b);
     }
     return PGVRX_OK;
 }

@@ -84,6 +84,7 @@ int pgvrx_flat_exact_core(pgvrx_index *ix, const void *d_queries, int64_t nq, in
         p.q_bytes = (uint32_t)ix->row_bytes;
         p.nq = (int)nq;
         p.k = k;
+        p.flags = ix->has_flags ? (const uint8_t *)ix->flags.p : nullptr;
         if (pl.n_splits == 1) {
             p.out_ids = d_ids;
             p.out_dists = d_dists;
@@ -120,10 +121,12 @@ namespace {
 int flat_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k, int64_t row_begin, int64_t row_end, int64_t id_base,
               int32_t *d_ids, float *d_dists, pgvrx_flat_stats *stats, cudaStream_t stream) {
     if (!ix->rows_loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "no rows loaded");
-    bool tc = row_begin == 0 && row_end == ix->n && k >= 1 && pgvrx_flat_tc_eligible(ix, nq, k);
+    // (an index that carries vacuum flags takes the CUDA-core kernel, which skips the flagged rows)
+    bool tc = row_begin == 0 && row_end == ix->n && k >= 1 && !ix->has_flags && pgvrx_flat_tc_eligible(ix, nq, k);
     const char *pin = getenv("PGVRX_FLAT_PATH");
     if (pin && !strcmp(pin, "exact")) tc = false;
     else if (!(pin && !strcmp(pin, "tc"))) tc = tc && nq >= 512 && ix->n >= 16384;
+    if (ix->has_flags) tc = false;
     if (tc) return pgvrx_flat_tc_core(ix, d_queries, nq, k, id_base, d_ids, d_dists, stats, nullptr, stream);
     return pgvrx_flat_exact_core(ix, d_queries, nq, k, row_begin, row_end, id_base, d_ids, d_dists, stats, stream);
 }
@@ -138,6 +141,7 @@ int pgvrx_index_load_rows(pgvrx_index *ix, const void *rows, int64_t n) {
     if (n > 0 && !rows) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null rows");
     if (ix->build) return pgvrx_fail(ix, PGVRX_ERR_STATE, "handle holds a built graph");
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    ix->generation++;
     ix->loaded = false;
     ix->rows_loaded = false;
     ix->tc_ready = false;
@@ -213,6 +217,7 @@ int pgvrx_rerank_device(pgvrx_index *ix, const void *d_queries, int64_t nq, cons
     p.k = k;
     p.out_ids = d_ids;
     p.out_dists = d_dists;
+    p.flags = ix->has_flags ? (const uint8_t *)ix->flags.p : nullptr;
     const size_t smem = rerank_smem_bytes(p.row_stride, p.stage_stride, p.R, k);
     if (smem > 227 * 1024) return pgvrx_fail(ix, PGVRX_ERR_UNSUPPORTED, "re-rank configuration exceeds shared memory");
     const int grid = (int)std::min<int64_t>((nq + 3) / 4, (int64_t)ix->sm_count * 3);

@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(FLAT_THREADS) flat_partial_kernel(FlatParams p
         }
         __syncthreads();                    // rows region becomes the candidate buffers
         bool any = false;
-        if (t < nrows) {
+        // a row whose element a vacuum has emptied or deleted is not in the table any more (its heap tuples are dead)
+        if (t < nrows && !(p.flags != nullptr && __ldg(p.flags + (tile + t)) != 0)) {
             const uint32_t id = (uint32_t)(tile + t - p.row_begin) + (uint32_t)p.id_base;
 #pragma unroll
             for (int q = 0; q < FLAT_QT; q++) {
@@ -353,7 +354,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         for (int base_c = 0; base_c < p.nc; base_c += 32) {
             const int i = base_c + lane;
             const int32_t id = i < p.nc ? p.cand[(size_t)q * p.nc + i] : -1;
-            const bool valid = id >= 0 && (int64_t)id - p.id_base < p.n_rows && id >= p.id_base;
+            bool valid = id >= 0 && (int64_t)id - p.id_base < p.n_rows && id >= p.id_base;
+            if (valid && p.flags != nullptr && __ldg(p.flags + (id - p.id_base)) != 0) valid = false;
             const uint32_t vm = __ballot_sync(FULL, valid);
             if (!vm) continue;
             // compact the valid ids to the front so that lane r evaluates staged row r

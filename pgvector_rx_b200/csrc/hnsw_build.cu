@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
         fence_mbar_init();
     }
     __syncwarp();
-    const uint32_t up_entries = p.vis_entries < 1024u ? p.vis_entries : 1024u;
+    const uint32_t up_entries = p.up_entries;
 
     while (true) {
         int w = 0;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_repair_search_kernel(Grap
         fence_mbar_init();
     }
     __syncwarp();
-    const uint32_t up_entries = p.vis_entries < 1024u ? p.vis_entries : 1024u;
+    const uint32_t up_entries = p.up_entries;
 
     while (true) {
         int w = 0;

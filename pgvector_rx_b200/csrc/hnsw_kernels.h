@@ -40,6 +40,8 @@ struct SearchParams {
     uint32_t *out_phase;       // nq x 8 per-phase cycle counts (PGVRX_PHASE_TIMING builds only) or NULL
     uint32_t *vis_base;        // per warp-slot visited tables
     uint32_t vis_entries;      // entries per table, power of two >= 256
+    uint32_t up_entries;       // entries of the table the ef = 1 descent uses per upper layer (<= vis_entries): small in the
+                               // main pass (it is cleared once per layer), the whole table in the retry pass
     int *work_counter;         // zeroed before the launch
     uint32_t stage_stride;     // bytes between staged rows (row_stride, +16 when that avoids bank conflicts)
     int R;                     // staged rows per warp (<= 32)
@@ -63,6 +65,7 @@ struct BuildParams {
     uint32_t *out_ctr;         // n_pending x 4 or NULL
     uint32_t *vis_base;
     uint32_t vis_entries;
+    uint32_t up_entries;       // table entries used by the ef = 1 descent (<= vis_entries)
     int *work_counter;
     uint32_t stage_stride;
     int R;
@@ -86,6 +89,7 @@ struct RepairParams {
     uint32_t *out_ctr;
     uint32_t *vis_base;
     uint32_t vis_entries;
+    uint32_t up_entries;       // table entries used by the ef = 1 descent (<= vis_entries)
     int *work_counter;
     uint32_t stage_stride;
     int R;
@@ -153,6 +157,7 @@ struct FlatParams {
     int nq, k;
     int32_t *out_ids;          // [n_splits][nq][k], ascending (distance, id), -1 / +inf padded
     float *out_dists;
+    const uint8_t *flags;      // per table row or NULL: rows with a non-zero flag (deleted / no heap TID left) are skipped
 };
 
 struct RerankParams {
@@ -165,6 +170,7 @@ struct RerankParams {
     int nq, nc, k, R;
     int32_t *out_ids;          // nq x k
     float *out_dists;
+    const uint8_t *flags;      // per table row or NULL: flagged candidates are dropped
 };
 
 size_t flat_smem_bytes(int elem, uint32_t row_stride, int k, FlatGeom *out);

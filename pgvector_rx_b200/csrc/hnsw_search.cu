@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     }
     __syncwarp();
 
-    const uint32_t up_entries = p.vis_entries < 1024u ? p.vis_entries : 1024u;
+    const uint32_t up_entries = p.up_entries;
 
     while (true) {
         int w = 0;

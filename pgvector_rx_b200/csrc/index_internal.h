@@ -64,6 +64,9 @@ struct pgvrx_index {
     bool has_flags = false;
     int64_t n = 0, n_upper = 0, entry = -1;
     int entry_level = -1;
+    // bumped by everything that changes the graph or the table (load_graph, load_rows, build, insert, vacuum,
+    // set_element_flags): an open pgvrx_scan remembers the value it was begun under and refuses to continue on another
+    uint64_t generation = 0;
     bool loaded = false;        // graph + rows resident
     bool rows_loaded = false;   // vector table resident (enough for the flat / re-rank paths)
     // scratch

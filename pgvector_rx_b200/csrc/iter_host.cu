@@ -15,6 +15,7 @@ using namespace pgvrx;
 
 struct pgvrx_scan {
     pgvrx_index *ix = nullptr;
+    uint64_t generation = 0;      // ix->generation at pgvrx_scan_begin: the visited bitmaps are sized for that graph
     int64_t nq = 0;
     int ef = 0, mode = 0;
     int64_t max_tuples = 0;
@@ -79,6 +80,7 @@ int pgvrx_scan_begin(pgvrx_index *ix, const void *queries, int64_t nq, int32_t e
     pgvrx_scan *s = new (std::nothrow) pgvrx_scan();
     if (!s) return pgvrx_fail(ix, PGVRX_ERR_NOMEM, "out of host memory");
     s->ix = ix;
+    s->generation = ix->generation;
     s->nq = nq;
     s->ef = ef_search;
     s->mode = iterative_mode;
@@ -148,7 +150,9 @@ int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, f
     if (stats) memset(stats, 0, sizeof *stats);
     if (s->nq == 0) return PGVRX_OK;
     if (!out_ids || !out_dists || !out_counts || !out_done) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null output buffer");
-    if (!ix->loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "the index changed under an open scan");
+    if (!ix->loaded || ix->generation != s->generation)
+        return pgvrx_fail(ix, PGVRX_ERR_STATE, "the index changed under an open scan (build, insert, vacuum, load or flags since "
+                                               "pgvrx_scan_begin): end this scan and begin a new one");
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     cudaStream_t stream = ix->stream;
     const int64_t nq = s->nq;

@@ -180,7 +180,7 @@ static int pages_write_impl(int32_t elem_type, int32_t dims, int32_t m, int32_t 
             wr16(base + (size_t)sl->blk * BLCKSZ + 12, (uint16_t)(PAGE_HDR + (size_t)sl->off * ITEMID));
             wr16(base + (size_t)sl->blk * BLCKSZ + 14, sl->at);
         }
-    std::atomic<int> bad{0};                                             // 1 = heap TID count, 2 = neighbour id, 3 = heap TID form
+    std::atomic<int> bad{0};                                             // 1 = heap TID count, 2 = neighbour id, 3 = heap TID form, 4 = no TIDs
     parallel_ranges(n, 16384, [&](int64_t lo, int64_t hi) {
         std::vector<uint8_t> etup(etup_size), ntup;
         for (int64_t i = lo; i < hi; i++) {
@@ -192,6 +192,10 @@ static int pages_write_impl(int32_t elem_type, int32_t dims, int32_t m, int32_t 
             etup[1] = (uint8_t)lv;
             const int n_tids = heap_tids ? heap_tid_counts[i] : 1;
             if (n_tids < 0 || n_tids > PGVRX_HEAPTIDS) { bad.store(1); return; }
+            // an element without heap TIDs is what a VACUUM leaves behind (deleted = 1, lists and value cleared, versions
+            // bumped: vacuum.rs:655-790).  This writer lays out the CREATE INDEX flush, where every element has 1..10 TIDs;
+            // writing such an element as a live zero-TID tuple would resurrect it in every later scan and repair
+            if (n_tids == 0) { bad.store(4); return; }
             for (int t = 0; t < PGVRX_HEAPTIDS; t++) {
                 uint8_t *slot = etup.data() + 4 + (size_t)t * TID;
                 if (t < n_tids) {
@@ -237,6 +241,7 @@ static int pages_write_impl(int32_t elem_type, int32_t dims, int32_t m, int32_t 
     if (bad.load() == 1) return fail("pgvector-rx: an element holds at most 10 heap TIDs");
     if (bad.load() == 2) return fail("pgvector-rx: neighbour id out of range");
     if (bad.load() == 3) return fail("pgvector-rx: heap TID is not (block << 16 | offset) with offset >= 1");
+    if (bad.load() == 4) return fail("pgvector-rx: element without heap TIDs (a vacuumed index): pgvrx_pages_write covers the CREATE INDEX flush only");
     return PGVRX_OK;
 }
 

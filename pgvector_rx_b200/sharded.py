@@ -62,6 +62,34 @@ class ShardedFlat:
 
         return cls(local_topk, merge, group)
 
+    def phase_times(self, queries, k, reps=5):
+        """Per-phase device times of topk() (ms, CUDA events on the current stream, mean of `reps`, this rank): the local
+        top-k over the shard, the all-gather(s), the K6 merge.  Diagnostic: tells which phase bounds strong scaling."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        acc = {"local_topk": 0.0, "all_gather": 0.0, "merge": 0.0}
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            ids, dists = self.local_topk(queries, k)
+            ev[1].record()
+            if world > 1:
+                part_ids = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+                part_dists = torch.empty((world,) + tuple(dists.shape), dtype=dists.dtype, device=dists.device)
+                dist.all_gather_into_tensor(part_ids.view(-1, ids.shape[1]), ids.contiguous(), group=self.group)
+                dist.all_gather_into_tensor(part_dists.view(-1, dists.shape[1]), dists.contiguous(), group=self.group)
+            else:
+                part_ids, part_dists = ids.unsqueeze(0).contiguous(), dists.unsqueeze(0).contiguous()
+            ev[2].record()
+            self.merge(part_ids, part_dists, k)
+            ev[3].record()
+            torch.cuda.synchronize()
+            acc["local_topk"] += ev[0].elapsed_time(ev[1])
+            acc["all_gather"] += ev[1].elapsed_time(ev[2])
+            acc["merge"] += ev[2].elapsed_time(ev[3])
+        return {key: v / reps for key, v in acc.items()}
+
     def topk(self, queries, k):
         """All ranks call this with the same queries; every rank returns the merged global top-k."""
         import torch

@@ -41,12 +41,32 @@ def build_oracle(force=False):
 _lib = None
 
 
+def build_native():
+    """liborc_native.so: the same source, `-O3 -march=native`, compiled on the machine that runs this (bench.py's CPU
+    legs set PGVRX_ORACLE_NATIVE=1: BASELINE.md promises these flags for the timed baseline).  Falls back to the portable
+    build when there is no compiler."""
+    out = os.path.join(ORACLE_DIR, "liborc_native.so")
+    try:
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "native"])
+        return out
+    except (OSError, subprocess.CalledProcessError):
+        return None
+
+
+NATIVE = False        # True once lib() has loaded the -march=native build
+
+
 def lib():
-    global _lib
+    global _lib, NATIVE
     if _lib is not None:
         return _lib
     build_oracle()
-    L = C.CDLL(LIB_PATH)
+    path = LIB_PATH
+    if os.environ.get("PGVRX_ORACLE_NATIVE") == "1":
+        p = build_native()
+        if p:
+            path, NATIVE = p, True
+    L = C.CDLL(path)
     vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
     sig = {
         "orc_half_to_f32": (f32, [C.c_uint16]),

@@ -237,6 +237,18 @@ def test_writer_rejects_heap_tids_a_reader_would_drop():
     assert "offset >= 1" in str(e.value)
 
 
+def test_writer_rejects_elements_a_vacuum_emptied():
+    # an element without heap TIDs is a vacuum's product (deleted = 1, lists cleared, versions bumped, vacuum.rs:655-790);
+    # the writer lays out the CREATE INDEX flush only and must not turn it into a live tuple without TIDs
+    o = oracle_index("vector_l2_ops", 4, make_rows("f32", 50, 4, 2), m=4, efc=16)
+    tids, cnt = fixture_tids(o)
+    cnt[9] = 0
+    tids[9] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with pytest.raises(P.PgvrxError) as e:
+        P.write_pages(P.ELEM_F32, 4, 4, 16, o.export_graph(), tids, cnt)
+    assert "CREATE INDEX flush only" in str(e.value)
+
+
 def test_writer_rejects_bad_input():
     o = oracle_index("vector_l2_ops", 8, make_rows("f32", 50, 8, 1), m=4, efc=16)
     g = o.export_graph()
