@@ -498,6 +498,46 @@ static void reserve_mirror(BuildState &g, int64_t cap) {
     }
 }
 
+// Geometry of the CTA-per-search kernel (hnsw_team.cu) for a round of B searches: as many helper warps as still let every
+// search of the round be resident at once (a round ends with its slowest search), shared-memory visited table of four
+// times the expected visited count (clamped to what fits).  Returns false when nothing fits (the one-warp kernel runs).
+static bool team_config(pgvrx_index *ix, const ScanConfig &cfg, int efc, int B, TeamGeom *out, size_t *smem_out, int *grid_out) {
+    const int m = ix->desc.m;
+    TeamGeom t;
+    t.lmp = (2 * m + 31) / 32 * 32;
+    t.stage_bytes = cfg.L.stage_bytes;
+    t.row_stride = ix->row_stride;
+    t.list_j = cfg.L.list_j;
+    t.ef = efc;
+    t.tail_cap = cfg.L.tail_cap;
+    const uint32_t vis_want = std::min<uint32_t>(16384u, std::max<uint32_t>(2048u, pgvrx_pow2_at_least((uint64_t)efc * 2 * m * 4)));
+    int forced = 0;
+    if (const char *e = getenv("PGVRX_TEAM_WARPS")) forced = atoi(e);
+    static const int options[3] = {8, 4, 2};
+    for (int oi = 0; oi < 3; oi++) {
+        t.warps = forced >= 2 && forced <= TEAM_MAX_WARPS ? forced : options[oi];
+        t.vis_entries = vis_want;
+        t.n_slots = std::min(TEAM_MAX_SLOTS, std::max(4, 4 * t.warps));
+        size_t smem = team_smem_bytes(t);
+        while (smem > 220 * 1024 && t.n_slots > 8) { t.n_slots -= 4; smem = team_smem_bytes(t); }
+        while (smem > 220 * 1024 && t.vis_entries > 4096) { t.vis_entries /= 2; smem = team_smem_bytes(t); }
+        if (smem > 220 * 1024) { if (forced) return false; continue; }
+        int occ = 0;
+        if (team_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, t.list_j, smem, t.warps * 32, &occ) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            if (forced) return false;
+            continue;
+        }
+        if ((int64_t)ix->sm_count * occ >= B || oi == 2 || forced) {
+            *out = t;
+            *smem_out = smem;
+            *grid_out = (int)std::min<int64_t>(B, (int64_t)ix->sm_count * occ);
+            return true;
+        }
+    }
+    return false;
+}
+
 // Host mirror of a graph that came in through pgvrx_index_load_graph: arrays back from the device, edge distances
 // recomputed (the on-disk format stores none; get_update_index recomputes them per insert, insert.rs:569-617).
 static int mirror_from_device(pgvrx_index *ix, int nthreads) {
@@ -724,6 +764,8 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
 
     int window = 4;
     const int WINDOW_MAX = 512;
+    const bool team_on = !(getenv("PGVRX_BUILD_TEAM") && atoi(getenv("PGVRX_BUILD_TEAM")) == 0);
+    uint64_t n_team_rounds = 0;
     // scratch escalation for a search that overflowed its visited table / tie tail: the head of the round is re-run alone
     // with 16x, 256x, 4096x the visited table (the ef = 1 descent then uses the whole table too) and 2048 / 8192 / 20000
     // tie slots; if even that is not enough the call fails instead of repeating the same round for ever
@@ -845,10 +887,24 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         bp.work_counter = (int *)rb.work.p;
         bp.stage_stride = cfg.L.stage_stride;
         bp.R = cfg.L.R;
+        bp.stage_bytes = cfg.L.stage_bytes;
+        bp.chunk_bytes = cfg.L.chunk_bytes;
+        bp.chunk_stride = cfg.L.chunk_stride;
         const double tg0 = now_ms();
         t_prelude += tg0 - tP0;
         CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
-        CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, cfg.wpb * 32, ix->stream));
+        // the first attempt of every search runs on the CTA-per-search kernel (one master warp + helper warps, visited
+        // set in shared memory: single-search latency is what bounds a round); escalation levels use the one-warp kernel
+        TeamGeom tg;
+        size_t team_smem = 0;
+        int team_grid = 0;
+        const bool use_team = team_on && big_level == 0 && team_config(ix, cfg, efc, B, &tg, &team_smem, &team_grid);
+        if (use_team) {
+            CU_TRY(ix, launch_team_build(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, tg, team_grid, team_smem, ix->stream));
+            n_team_rounds++;
+        } else {
+            CU_TRY(ix, launch_build_search(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, cfg.grid, cfg.smem_block, cfg.wpb * 32, ix->stream));
+        }
         if (w_masks) {
             // check_element_closer for the candidate lists the searches just produced (graph/mod.rs:419 -> :315-339)
             CU_TRY(ix, cudaMemsetAsync((int *)rb.work.p + 4, 0, 4, ix->stream));
@@ -1223,6 +1279,8 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     }
 
     if (getenv("PGVRX_BUILD_DEBUG"))
+        fprintf(stderr, "[pgvrx build] rounds on the CTA-per-search kernel: %llu of %llu\n", (unsigned long long)n_team_rounds, (unsigned long long)n_rounds);
+    if (getenv("PGVRX_BUILD_DEBUG"))
         fprintf(stderr, "[pgvrx build] conflicts: log overflow %llu, W-not-full %llu, pending element acceptable %llu, order/removal %llu | ms: gpu %.0f (kernels %.0f) phaseA %.0f groups %.0f (build %.0f enum %.0f) simulate %.0f commit %.0f scatter %.0f | setup %.0f prelude %.0f (place %.0f upload %.0f config+buffers %.0f) tail %.0f total %.0f\n",
                 (unsigned long long)why_overflow, (unsigned long long)why_notfull, (unsigned long long)why_pending,
                 (unsigned long long)why_order, gpu_ms, kernel_ms, t_phase_a, t_groups, t_g1, t_g2, t_sim, t_commit, t_scatter, t_loop0 - t_start, t_prelude, t_place, t_upload, t_cfg, t_tail,
@@ -1462,6 +1520,9 @@ int pgvrx_index_vacuum(pgvrx_index *ix, const uint64_t *dead_tids, int64_t n_dea
         rp.work_counter = (int *)rb.work.p;
         rp.stage_stride = cfg.L.stage_stride;
         rp.R = cfg.L.R;
+        rp.stage_bytes = cfg.L.stage_bytes;
+        rp.chunk_bytes = cfg.L.chunk_bytes;
+        rp.chunk_stride = cfg.L.chunk_stride;
         CU_TRY(ix, cudaEventRecord(ix->ev0, ix->stream));
         CU_TRY(ix, launch_repair_search(ix->desc.elem_type, ix->desc.metric, gv, rp, grid, cfg.smem_block, cfg.wpb * 32, ix->stream));
         CU_TRY(ix, cudaEventRecord(ix->ev1, ix->stream));

@@ -98,6 +98,25 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     // LDS.128 by one lane per row is conflict free when consecutive rows start 16 B * odd apart
     c.L.stage_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
     c.L.R = (int)std::max<uint32_t>(1, std::min<uint32_t>(32, STAGE_BUDGET / c.L.stage_stride));
+    if (const char *e = getenv("PGVRX_STAGE_ROWS")) { int r = atoi(e); if (r >= 1 && r <= 32) c.L.R = r; }   // tuning: exact rows per round
+    c.L.stage_bytes = (uint32_t)c.L.R * c.L.stage_stride;
+    c.L.chunk_bytes = c.L.chunk_stride = 0;
+    // Wide rows (fewer than 17 fit): stage 512-byte chunks of 32 rows instead of a few whole rows, so that every lane has
+    // a row to accumulate -- a 768-d halfvec row (1536 B) otherwise keeps 11 of the 32 lanes busy for six rounds per
+    // 64-entry neighbour list.  PGVRX_NO_CHUNK=1 keeps whole-row staging (A/B measurements).
+    if (c.L.R <= 16 && c.L.stage_stride > 528 && !getenv("PGVRX_NO_CHUNK")) {
+        c.L.chunk_bytes = 512;
+        c.L.chunk_stride = 528;                       // 33 x 16 B: consecutive rows start an odd number of 16-B vectors apart
+        c.L.stage_bytes = std::max<uint32_t>(32u * c.L.chunk_stride, c.L.stage_stride);   // (one whole row for the entry point)
+    }
+    if (const char *e = getenv("PGVRX_CHUNK_BYTES")) {       // tuning: force chunked staging with this chunk size
+        const int cb = atoi(e);
+        if (cb >= 64 && cb % 16 == 0 && (uint32_t)cb < ix->row_stride) {
+            c.L.chunk_bytes = (uint32_t)cb;
+            c.L.chunk_stride = (uint32_t)cb + ((((uint32_t)cb / 16) & 1u) ? 0u : 16u);
+            c.L.stage_bytes = std::max<uint32_t>(32u * c.L.chunk_stride, c.L.stage_stride);
+        }
+    }
     c.vis_entries = vis_entries;
     // scans run one warp (= one query in flight) per CTA: a CTA's slot is handed to the next batch as soon as that warp
     // has finished its last query instead of waiting for three siblings (measured 6.86 / 6.71 / 6.58 M QPS for 1 / 2 / 4
@@ -200,6 +219,9 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     p.work_counter = work + 0;
     p.stage_stride = main_cfg.L.stage_stride;
     p.R = main_cfg.L.R;
+    p.stage_bytes = main_cfg.L.stage_bytes;
+    p.chunk_bytes = main_cfg.L.chunk_bytes;
+    p.chunk_stride = main_cfg.L.chunk_stride;
     p.spec = getenv("PGVRX_NO_SPEC_GATHER") ? 0 : 1;   // measured: 6.46 M QPS speculative vs 6.40 M probe-first (profiles/r1_notes.md)
     CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, main_cfg.wpb * 32, stream));
 
@@ -215,6 +237,9 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     r.work_counter = work + 1;
     r.stage_stride = retry_cfg.L.stage_stride;
     r.R = retry_cfg.L.R;
+    r.stage_bytes = retry_cfg.L.stage_bytes;
+    r.chunk_bytes = retry_cfg.L.chunk_bytes;
+    r.chunk_stride = retry_cfg.L.chunk_stride;
     CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, retry_cfg.L.list_j, g, r, retry_cfg.grid, retry_cfg.smem_block, retry_cfg.wpb * 32, stream));
 
     if (stats) {

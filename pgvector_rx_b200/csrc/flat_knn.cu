@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
     c.stage_stride = p.stage_stride;
     c.R = p.R;
+    c.chunk_bytes = c.chunk_stride = 0;
     c.nvec = (int)(p.row_stride / 16);
     c.lane = lane;
     c.phase = 0;

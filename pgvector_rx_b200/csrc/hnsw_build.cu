@@ -32,12 +32,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
     const int warp = threadIdx.x >> 5;
     const int cap = p.efc + p.tail_cap;
     const size_t s_bytes = LISTJ == 0 ? round16b((uint32_t)((cap + 1) * 8)) : 0;
-    const size_t per_warp = (size_t)p.R * p.stage_stride + g.row_stride + s_bytes + 128 + 16;
+    const size_t per_warp = (size_t)p.stage_bytes + g.row_stride + s_bytes + 128 + 16;
     uint8_t *base = smem + (size_t)warp * per_warp;
 
     WarpCtx c;
     c.stage = base;
-    c.qsm = c.stage + (size_t)p.R * p.stage_stride;
+    c.qsm = c.stage + (size_t)p.stage_bytes;
     uint8_t *s_mem = c.qsm + g.row_stride;
     c.nbr = reinterpret_cast<int32_t *>(s_mem + s_bytes);
     c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
     BListOf<LISTJ>::attach(S, s_mem);
     c.stage_stride = p.stage_stride;
     c.R = p.R;
+    c.chunk_bytes = p.chunk_bytes;
+    c.chunk_stride = p.chunk_stride;
     c.nvec = (int)(g.row_stride / 16);
     c.cap = cap;
     c.lane = lane;
@@ -186,12 +188,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_repair_search_kernel(Grap
     const int warp = threadIdx.x >> 5;
     const int cap = p.ef + p.tail_cap;
     const size_t s_bytes = round16b((uint32_t)((cap + 1) * 8));
-    const size_t per_warp = (size_t)p.R * p.stage_stride + g.row_stride + s_bytes + 128 + 16;
+    const size_t per_warp = (size_t)p.stage_bytes + g.row_stride + s_bytes + 128 + 16;
     uint8_t *base = smem + (size_t)warp * per_warp;
 
     WarpCtx c;
     c.stage = base;
-    c.qsm = c.stage + (size_t)p.R * p.stage_stride;
+    c.qsm = c.stage + (size_t)p.stage_bytes;
     uint8_t *s_mem = c.qsm + g.row_stride;
     c.nbr = reinterpret_cast<int32_t *>(s_mem + s_bytes);
     c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
@@ -200,6 +202,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_repair_search_kernel(Grap
     S.hint = 0;
     c.stage_stride = p.stage_stride;
     c.R = p.R;
+    c.chunk_bytes = p.chunk_bytes;
+    c.chunk_stride = p.chunk_stride;
     c.nvec = (int)(g.row_stride / 16);
     c.cap = cap;
     c.lane = lane;

@@ -184,56 +184,76 @@ __device__ __forceinline__ float acc_step2(float acc, float2 q, float2 x) {
     }
 }
 
+// Resumable form of one (query, row) distance: the row may arrive in several chunks (wide rows are staged 512 bytes at a
+// time so that all 32 lanes of a warp have a row to work on); chunks are added strictly in element order, so the result
+// is the same chain of operations as a single pass -- bit-identical to the reference's scalar loops.
 // q, row: shared memory, 16-B aligned, nvec 16-byte vectors (zero padded: padding adds +0.0 exactly)
 template <int ELEM, int METRIC>
-__device__ __forceinline__ float row_distance(const uint8_t *q, const uint8_t *row, int nvec) {
-    const uint4 *q4 = reinterpret_cast<const uint4 *>(q);
-    const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
-    if (ELEM == ELEM_F32) {
-        float acc = 0.0f;
+struct DistAcc {
+    float acc;
+    uint32_t x, ab, aa, bb;
+    __device__ __forceinline__ void init() { acc = 0.0f; x = ab = aa = bb = 0; }
+    __device__ __forceinline__ void add(const uint8_t *q, const uint8_t *row, int nvec) {
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(q);
+        const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
+        if (ELEM == ELEM_F32) {
+            float a_ = acc;
 #pragma unroll 4
-        for (int j = 0; j < nvec; j++) {
-            uint4 a = q4[j], b = r4[j];
-            acc = acc_step2<METRIC>(acc, make_float2(__uint_as_float(a.x), __uint_as_float(a.y)),
-                                    make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
-            acc = acc_step2<METRIC>(acc, make_float2(__uint_as_float(a.z), __uint_as_float(a.w)),
-                                    make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
-        }
-        return METRIC == METRIC_NEG_IP ? -acc : acc;   // vector.rs:631 (f64 negate, exact)
-    } else if (ELEM == ELEM_F16) {
-        float acc = 0.0f;
+            for (int j = 0; j < nvec; j++) {
+                uint4 a = q4[j], b = r4[j];
+                a_ = acc_step2<METRIC>(a_, make_float2(__uint_as_float(a.x), __uint_as_float(a.y)),
+                                       make_float2(__uint_as_float(b.x), __uint_as_float(b.y)));
+                a_ = acc_step2<METRIC>(a_, make_float2(__uint_as_float(a.z), __uint_as_float(a.w)),
+                                       make_float2(__uint_as_float(b.z), __uint_as_float(b.w)));
+            }
+            acc = a_;
+        } else if (ELEM == ELEM_F16) {
+            float a_ = acc;
 #pragma unroll 2
-        for (int j = 0; j < nvec; j++) {
-            uint4 a = q4[j], b = r4[j];
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+            for (int j = 0; j < nvec; j++) {
+                uint4 a = q4[j], b = r4[j];
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                // half -> f32 is exact for every value (halfvec.rs:54-87 restates IEEE decoding)
-                float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&aw[t]));
-                float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&bw[t]));
-                acc = acc_step2<METRIC>(acc, fa, fb);
+                for (int t = 0; t < 4; t++) {
+                    // half -> f32 is exact for every value (halfvec.rs:54-87 restates IEEE decoding)
+                    float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&aw[t]));
+                    float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&bw[t]));
+                    a_ = acc_step2<METRIC>(a_, fa, fb);
+                }
             }
-        }
-        return METRIC == METRIC_NEG_IP ? -acc : acc;
-    } else {
-        // bitvec.rs:97-132: integer popcounts (order-free, exact)
-        uint32_t x = 0, ab = 0, aa = 0, bb = 0;
+            acc = a_;
+        } else {
+            // bitvec.rs:97-132: integer popcounts (order-free, exact)
 #pragma unroll 4
-        for (int j = 0; j < nvec; j++) {
-            uint4 a = q4[j], b = r4[j];
-            if (METRIC == METRIC_HAMMING) {
-                x += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
-            } else {
-                ab += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
-                aa += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w);
-                bb += __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+            for (int j = 0; j < nvec; j++) {
+                uint4 a = q4[j], b = r4[j];
+                if (METRIC == METRIC_HAMMING) {
+                    x += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+                } else {
+                    ab += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+                    aa += __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w);
+                    bb += __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+                }
             }
         }
-        if (METRIC == METRIC_HAMMING) return (float)x;
-        if (ab == 0) return 1.0f;                                     // bitvec.rs:127-128
-        double j = 1.0 - ((double)ab / (double)(aa + bb - ab));       // bitvec.rs:130
-        return (float)j;                                              // build.rs:367 `as f32`
     }
+    __device__ __forceinline__ float finish() const {
+        if (ELEM == ELEM_BIT) {
+            if (METRIC == METRIC_HAMMING) return (float)x;
+            if (ab == 0) return 1.0f;                                     // bitvec.rs:127-128
+            double j = 1.0 - ((double)ab / (double)(aa + bb - ab));       // bitvec.rs:130
+            return (float)j;                                              // build.rs:367 `as f32`
+        }
+        return METRIC == METRIC_NEG_IP ? -acc : acc;                      // vector.rs:631 (f64 negate, exact)
+    }
+};
+
+template <int ELEM, int METRIC>
+__device__ __forceinline__ float row_distance(const uint8_t *q, const uint8_t *row, int nvec) {
+    DistAcc<ELEM, METRIC> a;
+    a.init();
+    a.add(q, row, nvec);
+    return a.finish();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -248,6 +268,8 @@ struct WarpCtx {
     uint64_t policy;
     uint32_t stage_stride;
     int R, nvec;
+    uint32_t chunk_bytes;  // 0: whole rows are staged (R at a time); else rows are staged in chunks of this many bytes,
+    uint32_t chunk_stride; //    32 rows at a time, chunk_stride bytes apart (wide rows: every lane keeps a row to work on)
     int len, ef, cap;      // list length (W plus retained boundary ties), ef, capacity
     uint32_t phase;
     uint32_t f_ord;        // ordered bits of W's furthest distance (valid when len >= ef)
@@ -501,6 +523,53 @@ __device__ __forceinline__ void gather_rows_masked(WarpCtx &c, const GraphView &
     c.phase ^= 1u;
 }
 
+// Bytes [off, off + cb) of the rows of the lanes with `mine` set (lane r <-> staging slot r, chunk_stride apart).
+__device__ __forceinline__ void gather_chunk(WarpCtx &c, const GraphView &g, bool mine, uint32_t off, uint32_t cb) {
+    const uint32_t m = __ballot_sync(FULL, mine);
+    if (!m) return;
+    if (c.lane == 0) mbar_arrive_expect_tx(c.mbar, (uint32_t)__popc(m) * cb);
+    __syncwarp();
+    if (mine)
+        tma_row_g2s(c.stage + (size_t)c.lane * c.chunk_stride, g.vectors + (size_t)c.nbr[c.lane] * g.row_stride + off, cb, c.mbar, c.policy);
+    mbar_wait(c.mbar, c.phase);
+    c.phase ^= 1u;
+}
+
+// One distance per lane for the neighbours c.nbr[0 .. cnt) (lane r <-> neighbour r); lanes without `want` skip theirs.
+// Whole-row staging: R rows per round, the lanes of the round evaluate.  Chunked staging (wide rows): all rows at once,
+// 512 bytes at a time, every lane accumulating its own row's chain chunk after chunk.
+template <int ELEM, int METRIC>
+__device__ __forceinline__ float eval_neighbours(WarpCtx &c, const GraphView &g, int cnt, bool want, bool masked) {
+    const int lane = c.lane;
+    float d = 0.0f;
+    if (c.chunk_bytes == 0) {
+        for (int s = 0; s < cnt; s += c.R) {
+            const int nrow = min(c.R, cnt - s);
+            if (masked) gather_rows_masked(c, g, s, nrow, want);
+            else gather_rows(c, g, s, nrow);
+            PH_TICK(c, 2);
+            if (want && lane >= s && lane < s + nrow)
+                d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
+            __syncwarp();   // all lanes done with the staging rows before they are overwritten
+            PH_TICK(c, 3);
+        }
+    } else {
+        DistAcc<ELEM, METRIC> acc;
+        acc.init();
+        const bool mine = lane < cnt && (want || !masked);
+        for (uint32_t off = 0; off < g.row_stride; off += c.chunk_bytes) {
+            const uint32_t cb = min(c.chunk_bytes, g.row_stride - off);
+            gather_chunk(c, g, mine, off, cb);
+            PH_TICK(c, 2);
+            if (mine) acc.add(c.qsm + off, c.stage + (size_t)lane * c.chunk_stride, (int)(cb / 16));
+            __syncwarp();
+            PH_TICK(c, 3);
+        }
+        if (mine) d = acc.finish();
+    }
+    return d;
+}
+
 // search_layer (graph/mod.rs:161-255 == scan.rs:302-448 without the iterative-scan bookkeeping).
 // Precondition: S[0, len) holds the entry points (unexpanded), their ids are in the visited set.
 // FLAGGED: also honour GraphView::flags (an index a vacuum has touched); the default instantiation carries no trace of it.
@@ -576,15 +645,7 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             float d = 0.0f;
             if (c.spec) {
                 // (2) gather + one distance per lane (lane r <-> neighbour r of this chunk)
-                for (int s = 0; s < cnt; s += c.R) {
-                    const int nrow = min(c.R, cnt - s);
-                    gather_rows(c, g, s, nrow);
-                    PH_TICK(c, 2);
-                    if (lane >= s && lane < s + nrow)
-                        d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
-                    __syncwarp();   // all lanes done with the staging rows before they are overwritten
-                    PH_TICK(c, 3);
-                }
+                d = eval_neighbours<ELEM, METRIC>(c, g, cnt, valid, false);
                 // build log: which entries of this list are nearer than W's furthest distance was when the expansion
                 // started (every valid lane has its distance, visited or not) -- the host replays against it
                 if (c.rs_log && c.rs_n <= c.rs_cap) {
@@ -613,15 +674,7 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             PH_TICK(c, 1);
             if (!c.spec) {
                 // (2') only the rows that are evaluated
-                for (int s = 0; s < cnt; s += c.R) {
-                    const int nrow = min(c.R, cnt - s);
-                    gather_rows_masked(c, g, s, nrow, pass);
-                    PH_TICK(c, 2);
-                    if (pass && lane >= s && lane < s + nrow)
-                        d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
-                    __syncwarp();
-                    PH_TICK(c, 3);
-                }
+                d = eval_neighbours<ELEM, METRIC>(c, g, cnt, pass, true);
             }
             // (4) accept in neighbour order (graph/mod.rs:226-242): the threshold only tightens and W only
             //     fills up, so lanes failing against the CURRENT threshold can never be accepted later

@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
     up.hint = 0;
     c.stage_stride = p.stage_stride;
     c.R = p.R;
+    c.chunk_bytes = c.chunk_stride = 0;
     c.nvec = (int)(g.row_stride / 16);
     c.cap = cap;
     c.lane = lane;

@@ -45,6 +45,8 @@ struct SearchParams {
     int *work_counter;         // zeroed before the launch
     uint32_t stage_stride;     // bytes between staged rows (row_stride, +16 when that avoids bank conflicts)
     int R;                     // staged rows per warp (<= 32)
+    uint32_t stage_bytes;      // staging area per warp
+    uint32_t chunk_bytes, chunk_stride;   // wide rows: staged in chunks of chunk_bytes for 32 rows at once (0 = whole rows)
     int spec;                  // 1: gather every neighbour's row before the visited probes resolve (see search_layer)
 };
 
@@ -69,7 +71,26 @@ struct BuildParams {
     int *work_counter;
     uint32_t stage_stride;
     int R;
+    uint32_t stage_bytes, chunk_bytes, chunk_stride;   // as in SearchParams
 };
+
+// K2t: the same search with one CTA per pending insert (hnsw_team.cu): a master warp runs search_layer's sequential rules,
+// helper warps compute the neighbour-list distances of the next candidates ahead of it
+constexpr int TEAM_MAX_SLOTS = 32;     // cached expansions per CTA (one per lane of the master for lookups)
+constexpr int TEAM_MAX_WARPS = 8;
+struct TeamGeom {
+    int warps;                 // 1 master + (warps - 1) helpers
+    int n_slots;               // cache slots (<= TEAM_MAX_SLOTS)
+    int lmp;                   // entries per slot: 2m rounded up to 32
+    uint32_t vis_entries;      // shared-memory visited table (power of two)
+    uint32_t stage_bytes;      // per warp
+    uint32_t row_stride;
+    int list_j, ef, tail_cap;
+};
+size_t team_smem_bytes(const TeamGeom &t);
+cudaError_t team_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm);
+cudaError_t launch_team_build(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, const TeamGeom &t, int grid,
+                              size_t smem_block, cudaStream_t stream);
 
 // vacuum repair searches (hnsw_build.cu: hnsw_repair_search_kernel): find_element_neighbors_on_disk with a skip set
 // (src/index/insert.rs:1021-1123 called from vacuum.rs:341-353)
@@ -93,6 +114,7 @@ struct RepairParams {
     int *work_counter;
     uint32_t stage_stride;
     int R;
+    uint32_t stage_bytes, chunk_bytes, chunk_stride;   // as in SearchParams
 };
 cudaError_t launch_repair_search(int elem, int metric, const GraphView &g, const RepairParams &p, int grid, size_t smem_block,
                                  int threads, cudaStream_t stream);
@@ -117,6 +139,8 @@ struct SearchLaunch {
     int R, ef, tail_cap;
     int list_j;                // 0: result list in shared memory; 2/4/8: registers per lane
     uint32_t stage_stride, row_stride;
+    uint32_t stage_bytes;      // staging area per warp: R whole rows, or 32 chunks of a wide row
+    uint32_t chunk_bytes, chunk_stride;
 };
 
 size_t search_warp_smem(const SearchLaunch &L);

@@ -12,7 +12,7 @@ __host__ __device__ inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15
 
 // shared memory bytes one warp needs
 size_t search_warp_smem(const SearchLaunch &L) {
-    size_t b = (size_t)L.R * L.stage_stride;        // staging rows
+    size_t b = L.stage_bytes;                        // staging rows
     b += L.row_stride;                               // query
     if (L.list_j == 0) b += round16((uint32_t)((L.ef + L.tail_cap + 1) * 8));  // S (else it lives in registers)
     b += 128;                                        // nbr ids
@@ -38,12 +38,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     const int warp = threadIdx.x >> 5;
     const int cap = p.ef + p.tail_cap;
     const size_t s_bytes = LISTJ == 0 ? round16((uint32_t)((cap + 1) * 8)) : 0;
-    const size_t per_warp = (size_t)p.R * p.stage_stride + g.row_stride + s_bytes + 128 + 16;
+    const size_t per_warp = (size_t)p.stage_bytes + g.row_stride + s_bytes + 128 + 16;
     uint8_t *base = smem + (size_t)warp * per_warp;
 
     WarpCtx c;
     c.stage = base;
-    c.qsm = c.stage + (size_t)p.R * p.stage_stride;
+    c.qsm = c.stage + (size_t)p.stage_bytes;
     uint8_t *s_mem = c.qsm + g.row_stride;
     c.nbr = reinterpret_cast<int32_t *>(s_mem + s_bytes);
     c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     ListOf<LISTJ>::attach(S, s_mem);
     c.stage_stride = p.stage_stride;
     c.R = p.R;
+    c.chunk_bytes = p.chunk_bytes;
+    c.chunk_stride = p.chunk_stride;
     c.nvec = (int)(g.row_stride / 16);
     c.cap = cap;
     c.lane = lane;

@@ -22,10 +22,14 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0, help="report progress every CHUNK rows (appending calls)")
     ap.add_argument("--compare", default="", help="data_cache dir of an oracle graph built from the same rows")
+    ap.add_argument("--config", default="c2", help="BASELINE config whose rows / options are used (bench.py CONFIGS)")
     a = ap.parse_args()
-    X = D.gaussian_f32(a.n, 128, 2)
-    lv = D.hnsw_levels(a.n, 16, 4)
-    ix = P.HnswIndex("vector_l2_ops", 128, m=16, ef_construction=64, capacity=a.n)
+    import bench
+    c = bench.CONFIGS[a.config]
+    ba = argparse.Namespace(cfg=c, dim=c["dim"])
+    X = bench.raw_rows(ba, a.n, c["data_seed"])
+    lv = D.hnsw_levels(a.n, c["m"], c["level_seed"])
+    ix = P.HnswIndex(c["opclass"], c["dim"], m=c["m"], ef_construction=c["efc"], capacity=a.n)
     chunk = a.chunk or a.n
     t0 = time.time()
     tot = {}

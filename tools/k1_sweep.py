@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--config", default="c2")
     ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-gather", action="store_true")
     x = ap.parse_args()
     sys.argv = ["bench.py", "--config", x.config, "--ef", str(x.ef)] + (["--n", str(x.n)] if x.n else [])
     a = bench.parse()
@@ -35,9 +37,12 @@ def main():
     prep = (lambda q: P.normalize_rows(elem, a.dim, q)[1]) if norm else None
     runner = bench.ScanRunner(a, ix, bench.query_batches(a, 4, 0, prep), dev, 1)
     out = dict(scan=[], gather=[])
-    knobs = [dict(), dict(PGVRX_NO_SPEC_GATHER="1"), dict(PGVRX_STAGE_KB="9"), dict(PGVRX_NO_SPEC_GATHER="1", PGVRX_STAGE_KB="9"),
-             dict(PGVRX_STAGE_KB="13"), dict(PGVRX_NO_SPEC_GATHER="1", PGVRX_STAGE_KB="13"), dict(PGVRX_SCAN_WARPS="2"),
-             dict(PGVRX_SCAN_WARPS="4"), dict()]
+    knobs = [dict()] + [dict(PGVRX_STAGE_ROWS=str(r)) for r in (6, 8, 10, 11, 12, 14, 16, 17, 18, 20, 22, 24, 32)] + \
+            [dict(PGVRX_CHUNK_BYTES=str(cb)) for cb in (256, 128, 384)] + \
+            [dict(PGVRX_STAGE_ROWS="16", PGVRX_NO_SPEC_GATHER="1"), dict(PGVRX_STAGE_ROWS="11", PGVRX_NO_SPEC_GATHER="1"),
+             dict(PGVRX_STAGE_ROWS="16", PGVRX_SCAN_WARPS="2"), dict(PGVRX_STAGE_ROWS="11", PGVRX_SCAN_WARPS="2"), dict()]
+    if x.quick:
+        knobs = [dict(), dict(PGVRX_STAGE_ROWS="16"), dict(PGVRX_CHUNK_BYTES="256")]
     for kn in knobs:
         for k_, v in kn.items():
             os.environ[k_] = v
@@ -45,7 +50,7 @@ def main():
         out["scan"].append(dict(knobs=kn, qps=a.nq * x.steps / (ms / 1e3), ms_per_step=ms / x.steps))
         for k_ in kn:
             del os.environ[k_]
-    for mode in (1, 0):
+    for mode in (() if x.no_gather else (1, 0)):
         for wps, rows, depth in ((0, 32, 1), (6, 32, 1), (3, 32, 1), (0, 16, 2), (0, 16, 1), (0, 32, 2), (0, 8, 4)):
             for consume in (1, 0):
                 try:
