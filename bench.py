@@ -95,6 +95,7 @@ def parse():
     ap.add_argument("--no-ef100", action="store_true", help="C2: skip the ef_search = 100 section")
     ap.add_argument("--no-gather-probe", action="store_true", help="skip the gather-ceiling probe")
     ap.add_argument("--iter-queries", type=int, default=2000, help="C4: queries per filtered iterative-scan batch")
+    ap.add_argument("--sweep", action="store_true", help="also time the scan under other staging geometries (tuning; rank 0, N = 1)")
     a = ap.parse_args()
     c = CONFIGS[a.config]
     for key, attr in (("n", "n"), ("dim", "dim"), ("m", "m"), ("efc", "efc"), ("ef", "ef")):
@@ -729,6 +730,30 @@ def scan_roofline(a, ix, st, step_s, kernel):
                      % (row_stride, 2 * a.m * 4, a.m * 4))
 
 
+def staging_sweep(a, runner):
+    """Device-resident QPS of the scan under other staging geometries (environment knobs of capi.cu's launch
+    configuration), same batches, same two streams.  A tuning aid: which geometry is the default is decided from these."""
+    knobs = [dict(), dict(PGVRX_STAGE_ROWS="32", PGVRX_SPEC_GATHER="1"), dict(PGVRX_STAGE_ROWS="32", PGVRX_SPEC_GATHER="0"),
+             dict(PGVRX_STAGE_ROWS="16", PGVRX_SPEC_GATHER="1"), dict(PGVRX_STAGE_ROWS="16", PGVRX_SPEC_GATHER="0"),
+             dict(PGVRX_STAGE_ROWS="16", PGVRX_SPEC_GATHER="0", PGVRX_SCAN_WARPS="2"), dict(PGVRX_STAGE_ROWS="11"), dict(PGVRX_STAGE_ROWS="8"),
+             dict(PGVRX_CHUNK_BYTES="128"), dict(PGVRX_CHUNK_BYTES="256"), dict(PGVRX_CHUNK_BYTES="256", PGVRX_SPEC_GATHER="1"),
+             dict(PGVRX_CHUNK_BYTES="384"), dict(PGVRX_CHUNK_BYTES="512"), dict(PGVRX_CHUNK_BYTES="512", PGVRX_SPEC_GATHER="1"),
+             dict(PGVRX_CHUNK_BYTES="768"), dict(PGVRX_NO_CHUNK="1", PGVRX_STAGE_KB="17"), dict()]
+    out = []
+    steps = max(6, a.steps // 8)
+    for kn in knobs:
+        for k_, v in kn.items():
+            os.environ[k_] = v
+        try:
+            ms = runner.device_timed(a.ef, a.k, steps, 3)
+            out.append(dict(knobs=kn, qps=a.nq * steps / (ms / 1e3), ms_per_step=ms / steps))
+        except Exception as exc:
+            out.append(dict(knobs=kn, error=repr(exc)[:200]))
+        for k_ in kn:
+            del os.environ[k_]
+    return out
+
+
 def gather_probe_section(ix):
     """Measured ceiling for the scan's gathers (pgvrx_gather_probe): random row gathers with the scan's own TMA mechanism
     and geometry, ids from a random walk over the graph (hub reuse as in real searches) and uniform over the table."""
@@ -1005,6 +1030,8 @@ def run_b200(a):
         if gw:
             roof["frac_of_gather_ceiling"] = roof["achieved"] / max(gw["gb_per_s"], gw["gb_per_s_two_half_phases"])
 
+    sweep = staging_sweep(a, runner) if (a.sweep and rank == 0 and world == 1) else None
+
     # ---- exact kNN: ground truth for recall, and its own line ----
     if a.no_flat:
         flat_info, gt_ids = None, None
@@ -1112,6 +1139,8 @@ def run_b200(a):
                    build=build,
                    flat_knn=flat_info)
         out.update(extras)
+        if sweep:
+            out["staging_sweep"] = sweep
         print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()

@@ -764,7 +764,12 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
 
     int window = 4;
     const int WINDOW_MAX = 512;
-    const bool team_on = !(getenv("PGVRX_BUILD_TEAM") && atoi(getenv("PGVRX_BUILD_TEAM")) == 0);
+    // CTA-per-search kernel: on for wide rows (an expansion is several gather rounds: 20k x 768-d halfvec rows, kernels
+    // 27.7 s -> 18.6 s), off for rows that are staged whole -- there nearly every popped candidate is one the previous
+    // expansion has just inserted, nothing can be computed ahead of it, and the two kernels take the same time (C2 100k
+    // rows: 5.84 s vs 5.93 s).  PGVRX_BUILD_TEAM=0/1 pins the choice.
+    bool team_on = ix->row_stride > 1056;
+    if (const char *e = getenv("PGVRX_BUILD_TEAM")) team_on = atoi(e) != 0;
     uint64_t n_team_rounds = 0;
     // scratch escalation for a search that overflowed its visited table / tie tail: the head of the round is re-run alone
     // with 16x, 256x, 4096x the visited table (the ef = 1 descent then uses the whole table too) and 2048 / 8192 / 20000

@@ -79,9 +79,11 @@ uint32_t pgvrx_pow2_at_least(uint64_t x) {
 // least 16 retained-tie slots), else the shared-memory list with 32 tie slots
 int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entries, int64_t nq, int max_grid,
                       bool for_build, ScanConfig *out) {
-    // bytes of shared memory per warp for staged rows; 32 rows of a 128-d fp32 vector fit in 17 KiB.
-    // PGVRX_STAGE_KB overrides it for tuning experiments (occupancy vs. rows per TMA round).
-    uint32_t STAGE_BUDGET = 17 * 1024;
+    // Bytes of shared memory per warp for staged rows.  Scans: 8.5 KiB = 16 rows of a 128-d fp32 vector, i.e. two gather
+    // rounds per 32-entry neighbour list but twice the resident warps (measured on C2, profiles/r2_notes.md: 7.49 M QPS
+    // at 16 rows against 7.17 M at 32 and 6.9 M at 11).  The build's searches are latency bound at a few dozen resident
+    // warps on the whole device, so they keep all 32 rows in one round.  PGVRX_STAGE_KB / PGVRX_STAGE_ROWS override.
+    uint32_t STAGE_BUDGET = for_build ? 17 * 1024 : 8704;
     if (const char *e = getenv("PGVRX_STAGE_KB")) { int kb = atoi(e); if (kb >= 1 && kb <= 48) STAGE_BUDGET = (uint32_t)kb * 1024; }
     ScanConfig c;
     c.L.ef = ef;
@@ -98,13 +100,15 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     // LDS.128 by one lane per row is conflict free when consecutive rows start 16 B * odd apart
     c.L.stage_stride = ix->row_stride + (((ix->row_stride / 16) & 1u) ? 0u : 16u);
     c.L.R = (int)std::max<uint32_t>(1, std::min<uint32_t>(32, STAGE_BUDGET / c.L.stage_stride));
+    // equal rounds: 32 entries in ceil(32 / R) rounds need no more than ceil(32 / rounds) rows each (21 -> 16)
+    if (c.L.R < 32) { const int rounds = (32 + c.L.R - 1) / c.L.R; c.L.R = (32 + rounds - 1) / rounds; }
     if (const char *e = getenv("PGVRX_STAGE_ROWS")) { int r = atoi(e); if (r >= 1 && r <= 32) c.L.R = r; }   // tuning: exact rows per round
     c.L.stage_bytes = (uint32_t)c.L.R * c.L.stage_stride;
     c.L.chunk_bytes = c.L.chunk_stride = 0;
     // Wide rows (fewer than 17 fit): stage 512-byte chunks of 32 rows instead of a few whole rows, so that every lane has
     // a row to accumulate -- a 768-d halfvec row (1536 B) otherwise keeps 11 of the 32 lanes busy for six rounds per
     // 64-entry neighbour list.  PGVRX_NO_CHUNK=1 keeps whole-row staging (A/B measurements).
-    if (c.L.R <= 16 && c.L.stage_stride > 528 && !getenv("PGVRX_NO_CHUNK")) {
+    if (c.L.stage_stride > 1056 && !getenv("PGVRX_NO_CHUNK")) {
         c.L.chunk_bytes = 512;
         c.L.chunk_stride = 528;                       // 33 x 16 B: consecutive rows start an odd number of 16-B vectors apart
         c.L.stage_bytes = std::max<uint32_t>(32u * c.L.chunk_stride, c.L.stage_stride);   // (one whole row for the entry point)
@@ -222,7 +226,13 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     p.stage_bytes = main_cfg.L.stage_bytes;
     p.chunk_bytes = main_cfg.L.chunk_bytes;
     p.chunk_stride = main_cfg.L.chunk_stride;
-    p.spec = getenv("PGVRX_NO_SPEC_GATHER") ? 0 : 1;   // measured: 6.46 M QPS speculative vs 6.40 M probe-first (profiles/r1_notes.md)
+    // Speculative order (fetch every neighbour's row while the visited probes are in flight) when a list's rows go in
+    // one round; probe-first (fetch only the rows that will be evaluated: 17 % less L2 -> SM traffic) when they take
+    // two or more -- measured on C2: 32 rows/round 7.17 M QPS speculative vs 6.86 M probe-first, 16 rows/round 7.49 M vs
+    // 7.68 M (profiles/r2_notes.md).  PGVRX_SPEC_GATHER=0/1 pins the order.
+    p.spec = (main_cfg.L.R >= 32 && main_cfg.L.chunk_bytes == 0) ? 1 : 0;
+    if (getenv("PGVRX_NO_SPEC_GATHER")) p.spec = 0;
+    if (const char *e = getenv("PGVRX_SPEC_GATHER")) p.spec = atoi(e) != 0;
     CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, main_cfg.wpb * 32, stream));
 
     // queries that overflowed their visited table or tie tail run again with 16x the scratch

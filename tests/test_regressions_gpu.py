@@ -66,20 +66,22 @@ def test_build_descent_longer_than_the_small_upper_table_does_not_hang():
 
 def test_build_tie_overflow_escalates_and_finally_fails_instead_of_looping():
     # 256 distinct rows, each ~23 times: three elements per value (10 heap TIDs each), C(8,d) * 3 elements at Hamming
-    # distance d from any row -- 84 at d = 2, 168 at d = 3 -- so W's 32nd entry always ties with dozens of others
+    # distance d from any row (84 at d = 2, 168 at d = 3).  Entries evicted from W that still tie with its furthest
+    # distance stay expandable (strict `>` stop rule); there can be up to ef - 1 of them, and at ef_construction = 100 the
+    # register-resident list keeps 27: dozens of d = 3 entries are evicted one by one while W's furthest stays at 3
     rows = make_rows("bit", 6000, 8, 5)
     lv = D.hnsw_levels(len(rows), 8, 6)
     old = os.environ.get("PGVRX_BUILD_TAILS")
     try:
-        os.environ["PGVRX_BUILD_TAILS"] = "40,48,4096"       # levels 1 and 2 overflow again, level 3 holds
-        ix = P.HnswIndex("bit_hamming_ops", 8, m=8, ef_construction=32, capacity=len(rows))
+        os.environ["PGVRX_BUILD_TAILS"] = "30,32,4096"       # levels 1 and 2 overflow again, level 3 holds
+        ix = P.HnswIndex("bit_hamming_ops", 8, m=8, ef_construction=100, capacity=len(rows))
         st = ix.build(rows, lv)
-        o = oracle_index("bit_hamming_ops", 8, rows, m=8, efc=32, levels=lv)
+        o = oracle_index("bit_hamming_ops", 8, rows, m=8, efc=100, levels=lv)
         assert same_graph(ix.export_graph(), o.export_graph())
         assert st["n_big_retries"] > 0
         ix.close()
-        os.environ["PGVRX_BUILD_TAILS"] = "33,34,35"         # nothing holds: the call must fail, not spin
-        ix = P.HnswIndex("bit_hamming_ops", 8, m=8, ef_construction=32, capacity=len(rows))
+        os.environ["PGVRX_BUILD_TAILS"] = "28,29,30"         # nothing holds: the call must fail, not spin
+        ix = P.HnswIndex("bit_hamming_ops", 8, m=8, ef_construction=100, capacity=len(rows))
         with pytest.raises(P.PgvrxError) as ei:
             ix.build(rows, lv)
         assert ei.value.code == P.ERR_UNSUPPORTED and "exhausted" in ei.value.message
