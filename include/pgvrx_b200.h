@@ -240,6 +240,34 @@ int pgvrx_index_build(pgvrx_index *idx, const void *rows, int64_t n_rows, const 
 int pgvrx_index_insert(pgvrx_index *idx, const void *rows, int64_t n_rows, const int32_t *levels,
                        const uint64_t *heap_tids, int32_t host_threads, pgvrx_build_stats *stats);
 
+/* ---- the narrow build seam: search_layer on the GPU, heuristic and commit on the CALLER's side --------------------- */
+/* SURVEY 8(b)(4)/(5).  A caller that keeps select_neighbors / update_neighbor_connections / the insert loop itself (the
+ * pgrx build_callback, src/index/build.rs:400-535) replaces only find_element_neighbors' search_layer calls
+ * (src/graph/mod.rs:386,407; signature of the reference's seam: DistanceFn, graph/mod.rs:144-145) and tells the library
+ * what it decided.  pgvrx_index_build / pgvrx_index_insert are the same machinery with both halves inside the library.
+ *
+ * pgvrx_search_layer_batch: search_layer(query, entry_points, ef, layer) (graph/mod.rs:161-255) for nq queries against
+ * the resident graph.  Query i is raw element data (queries, row_bytes apart) or the stored row of element query_ids[i]
+ * (exactly one of the two is non-NULL).  Its entry points are ep_counts[i] <= min(ep_pitch, ef) (id, distance) pairs at
+ * ep_ids / ep_dists + i * ep_pitch, each on `layer`; all of them start out visited, in C and in W (graph/mod.rs:171-184).
+ * out_ids / out_dists: nq x ef, W ascending by (distance, id), -1 / +inf padded; out_counts[i] = |W|.  out_expanded
+ * (optional, exp_cap ids per query, -1 padded) receives the elements the search expanded, in expansion order -- its read
+ * set: a speculative result stays valid while none of those lists has changed; out_n_expanded[i] is the full count (the
+ * list is a prefix when it exceeds exp_cap).  HOST buffers. */
+int pgvrx_search_layer_batch(pgvrx_index *idx, const void *queries, const int32_t *query_ids, int64_t nq,
+                             const int32_t *ep_ids, const float *ep_dists, const int32_t *ep_counts, int32_t ep_pitch,
+                             int32_t ef, int32_t layer, int32_t *out_ids, float *out_dists, int32_t *out_counts,
+                             int32_t *out_expanded, int32_t exp_cap, int32_t *out_n_expanded);
+/* pgvrx_commit_insert: ONE new element as the caller's host code decided it -- appended as the next element id
+ * (returned in *new_id_out): `row` (row_bytes), `level`, `lists` = its neighbour lists, layer 0 first (2m ids) then
+ * layers 1 .. level (m ids each), -1 after the last neighbour of a list (graph/mod.rs:419-422) -- and the n_modified
+ * neighbour lists update_neighbor_connections rewrote (graph/mod.rs:442-489): list t belongs to (mod_nodes[t],
+ * mod_layers[t]) and is the next 2m (layer 0) or m ids of mod_lists.  The entry point moves to the new element when its
+ * level is strictly greater (build.rs:523-529).  The next search sees the commit.  The handle's host mirror is dropped
+ * (pgvrx_index_export_graph / pgvrx_index_insert rebuild it from the device arrays when needed). */
+int pgvrx_commit_insert(pgvrx_index *idx, const void *row, int32_t level, const int32_t *lists, int32_t n_modified,
+                        const int32_t *mod_nodes, const int32_t *mod_layers, const int32_t *mod_lists, int64_t *new_id_out);
+
 /* ---- VACUUM: ambulkdelete (src/index/vacuum.rs:816-842) ----------------------------------------- */
 typedef struct {
     uint64_t n_heap_tids_removed;  /* pass 1 (vacuum.rs:118-216)                                              */
@@ -271,8 +299,9 @@ int pgvrx_index_set_heap_tids(pgvrx_index *idx, const uint64_t *heap_tids, const
 
 int pgvrx_index_graph_info(const pgvrx_index *idx, int64_t *n, int64_t *n_upper_rows, int64_t *entry,
                            int32_t *entry_level);
-/* copies the built graph out (any pointer may be NULL); shapes as in pgvrx_index_load_graph,
- * heap_tids n x 10 (~0 when absent), heap_tid_counts n */
+/* copies the graph out (any pointer may be NULL); shapes as in pgvrx_index_load_graph, heap_tids n x 10 (~0 when
+ * absent), heap_tid_counts n.  A handle without a host mirror (loaded, or fed by pgvrx_commit_insert) reads the arrays
+ * back from the device first; its elements then count as holding one heap TID equal to their id. */
 int pgvrx_index_export_graph(pgvrx_index *idx, void *rows, uint8_t *level, int32_t *adj0,
                              int32_t *upper_base, int32_t *adj_up, uint64_t *heap_tids,
                              uint8_t *heap_tid_counts);
@@ -341,6 +370,40 @@ int pgvrx_rerank_device(pgvrx_index *idx, const void *d_queries, int64_t nq, con
 int pgvrx_topk_merge_device(pgvrx_index *idx, const int32_t *d_part_ids, const float *d_part_dists,
                             int32_t n_parts, int64_t nq, int32_t k_in, int32_t k_out, int32_t *d_out_ids,
                             float *d_out_dists, void *cuda_stream);
+
+/* ---- several GPUs of one box behind one handle (one process; one host thread per device while a call runs) ------- */
+/* The scan shards by QUERIES against a graph replicated on every device (no exchange step); the exact flat kNN shards
+ * the BASE ROWS contiguously, every device computes the top-k of its shard for all queries with global ids, and the
+ * lead device (devices[0]) merges the per-shard lists with one kernel that reads the other devices' lists in place
+ * over NVLink (peer access; staged through a peer copy where that is unavailable).  desc->device is ignored: member i
+ * runs on devices[i] (an ordinal may repeat: several members then share a device).  One process per GPU launchers use
+ * pgvrx_flat_topk_device + an all-gather + pgvrx_topk_merge_device instead (pgvector_rx_b200/sharded.py). */
+typedef struct pgvrx_group pgvrx_group;
+typedef struct {
+    double  total_ms;         /* wall time of the call                                                        */
+    double  local_ms;         /* flat: wall time of the per-device phase (queries up + top-k of the shard)     */
+    float   merge_kernel_ms;  /* flat: device time of the merge kernel on the lead device                      */
+    int32_t n_devices;
+    int32_t n_peer_direct;    /* flat: members whose lists the merge read in place (peer access or same device) */
+} pgvrx_group_stats;
+int pgvrx_group_create(const pgvrx_index_desc *desc, const int32_t *devices, int32_t n_devices, pgvrx_group **out);
+void pgvrx_group_destroy(pgvrx_group *g);
+const char *pgvrx_group_last_error(const pgvrx_group *g);
+int32_t pgvrx_group_size(const pgvrx_group *g);
+pgvrx_index *pgvrx_group_member(pgvrx_group *g, int32_t i);          /* the member's own handle (owned by the group)  */
+int pgvrx_group_peer_access(const pgvrx_group *g, int32_t i);         /* 1: the lead device reads member i in place    */
+/* replicate a finished graph on every member (arguments as pgvrx_index_load_graph) */
+int pgvrx_group_load_graph(pgvrx_group *g, const void *rows, int64_t n, const uint8_t *level, const int32_t *adj0,
+                           const int32_t *upper_base, const int32_t *adj_up, int64_t n_upper_rows, int64_t entry);
+/* pgvrx_search_batch over all members: one caller batch split into contiguous query slices, results written into the
+ * caller's arrays (HOST buffers; page-locked ones are read / written by the kernels in place) */
+int pgvrx_group_search_batch(pgvrx_group *g, const void *queries, int64_t nq, int32_t ef_search, int32_t k, int32_t *out_ids,
+                             float *out_dists, int32_t *out_counts, pgvrx_group_stats *stats /* may be NULL */);
+/* shard n rows contiguously over the members (member i holds rows [i*n/N ...), ids stay global row numbers) */
+int pgvrx_group_load_rows(pgvrx_group *g, const void *rows, int64_t n);
+/* exact k nearest rows per query over the sharded table; results identical to pgvrx_flat_topk on the whole table */
+int pgvrx_group_flat_topk(pgvrx_group *g, const void *queries, int64_t nq, int32_t k, int32_t *out_ids, float *out_dists,
+                          pgvrx_group_stats *stats /* may be NULL */);
 
 /* ---- diagnostics: the ceiling the scan kernel's row gathers are measured against ------------------------------ */
 /* Random row_stride-byte gathers from the handle's vector table with the scan kernel's own transfer mechanism (one TMA

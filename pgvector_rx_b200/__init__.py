@@ -44,7 +44,9 @@ EXPORTS = [
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
     "pgvrx_pages_element_flags", "pgvrx_heap_tid_stream", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
     "pgvrx_index_set_heap_tids", "pgvrx_pages_write", "pgvrx_index_vacuum", "pgvrx_index_element_flags",
-    "pgvrx_gather_probe",
+    "pgvrx_gather_probe", "pgvrx_group_create", "pgvrx_group_destroy", "pgvrx_group_last_error", "pgvrx_group_size",
+    "pgvrx_group_member", "pgvrx_group_peer_access", "pgvrx_group_load_graph", "pgvrx_group_search_batch",
+    "pgvrx_group_load_rows", "pgvrx_group_flat_topk", "pgvrx_search_layer_batch", "pgvrx_commit_insert",
 ]
 ELEM_DELETED, ELEM_NO_HEAPTIDS = 1, 2
 
@@ -100,6 +102,14 @@ class SearchStats(C.Structure):
 class GatherProbeResult(C.Structure):
     _fields_ = [("bytes_per_launch", C.c_uint64), ("ms_per_launch", C.c_double), ("gb_per_s", C.c_double),
                 ("warps_per_sm", C.c_int32), ("grid", C.c_int32), ("row_bytes", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class GroupStats(C.Structure):
+    _fields_ = [("total_ms", C.c_double), ("local_ms", C.c_double), ("merge_kernel_ms", C.c_float), ("n_devices", C.c_int32),
+                ("n_peer_direct", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -164,6 +174,18 @@ def lib():
         "pgvrx_scan_next": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(SearchStats)]),
         "pgvrx_scan_end": (None, [vp]),
         "pgvrx_gather_probe": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, C.POINTER(GatherProbeResult)]),
+        "pgvrx_group_create": (C.c_int, [C.POINTER(IndexDesc), vp, i32, C.POINTER(vp)]),
+        "pgvrx_group_destroy": (None, [vp]),
+        "pgvrx_group_last_error": (C.c_char_p, [vp]),
+        "pgvrx_group_size": (i32, [vp]),
+        "pgvrx_group_member": (vp, [vp, i32]),
+        "pgvrx_group_peer_access": (C.c_int, [vp, i32]),
+        "pgvrx_group_load_graph": (C.c_int, [vp, vp, i64, vp, vp, vp, vp, i64, i64]),
+        "pgvrx_group_search_batch": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, C.POINTER(GroupStats)]),
+        "pgvrx_group_load_rows": (C.c_int, [vp, vp, i64]),
+        "pgvrx_group_flat_topk": (C.c_int, [vp, vp, i64, i32, vp, vp, C.POINTER(GroupStats)]),
+        "pgvrx_search_layer_batch": (C.c_int, [vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
+        "pgvrx_commit_insert": (C.c_int, [vp, vp, i32, vp, i32, vp, vp, vp, C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -501,6 +523,38 @@ class HnswIndex:
         self._check(self.L.pgvrx_topk_merge_device(self.h, d_part_ids_ptr, d_part_dists_ptr, n_parts, nq, k_in, k_out,
                                                    d_out_ids_ptr, d_out_dists_ptr, C.c_void_p(stream) if stream else None))
 
+    # ---- the narrow build seam: searches here, heuristic + commit on the caller's side ----
+    def search_layer_batch(self, ep_ids, ep_dists, ep_counts, ef, layer, queries=None, query_ids=None, exp_cap=0):
+        """search_layer(query, entry_points, ef, layer) for a batch (graph/mod.rs:161-255).  Returns (ids, dists, counts)
+        and, with exp_cap > 0, also (expanded ids, expanded counts)."""
+        ep_ids = np.ascontiguousarray(ep_ids, np.int32)
+        ep_dists = np.ascontiguousarray(ep_dists, np.float32)
+        ep_counts = np.ascontiguousarray(ep_counts, np.int32)
+        nq, pitch = ep_ids.shape
+        q = None if queries is None else _rows(self.elem, self.dim, queries)
+        qi = None if query_ids is None else np.ascontiguousarray(query_ids, np.int32)
+        ids = np.empty((nq, ef), np.int32)
+        dists = np.empty((nq, ef), np.float32)
+        counts = np.empty(nq, np.int32)
+        ex = np.empty((nq, max(exp_cap, 1)), np.int32)
+        nex = np.empty(nq, np.int32)
+        self._check(self.L.pgvrx_search_layer_batch(self.h, _p(q), _p(qi), nq, _p(ep_ids), _p(ep_dists), _p(ep_counts), pitch, ef, layer,
+                                                    _p(ids), _p(dists), _p(counts), _p(ex) if exp_cap else None, exp_cap,
+                                                    _p(nex) if exp_cap else None))
+        return (ids, dists, counts, ex, nex) if exp_cap else (ids, dists, counts)
+
+    def commit_insert(self, row, level, lists, mod_nodes=(), mod_layers=(), mod_lists=()):
+        """One new element as the caller decided it (see the header).  Returns its element id."""
+        r = _rows(self.elem, self.dim, row)
+        lists = np.ascontiguousarray(lists, np.int32)
+        mn = np.ascontiguousarray(mod_nodes, np.int32)
+        ml = np.ascontiguousarray(mod_layers, np.int32)
+        mls = np.ascontiguousarray(mod_lists, np.int32).ravel()
+        new_id = C.c_int64(-1)
+        self._check(self.L.pgvrx_commit_insert(self.h, _p(r), int(level), _p(lists), len(mn), _p(mn) if len(mn) else None,
+                                               _p(ml) if len(mn) else None, _p(mls) if len(mn) else None, C.byref(new_id)))
+        return new_id.value
+
     def gather_probe(self, mode=1, warps_per_sm=0, rows_per_step=32, depth=1, steps=256, consume=1):
         """Diagnostic: bytes/s of random row gathers with the scan kernel's TMA mechanism (see the header)."""
         r = GatherProbeResult()
@@ -511,6 +565,73 @@ class HnswIndex:
     def scan_begin(self, queries, ef_search=None, iterative_scan=ITER_RELAXED, max_scan_tuples=20000, prepared=False):
         return IterativeScan(self, queries, self.ef_search if ef_search is None else ef_search, iterative_scan,
                              max_scan_tuples, prepared)
+
+
+class HnswGroup:
+    """Several GPUs of one box behind one handle (pgvrx_group_*): query-sharded scans over a replicated graph, exact flat
+    kNN over row shards with the merge reading the peers' lists over NVLink.  Rows / queries are taken in STORED form
+    (already normalised where the opclass normalises)."""
+
+    def __init__(self, opclass, dim, devices, m=16, ef_construction=64, capacity=0):
+        if opclass not in OPCLASSES:
+            raise PgvrxError(ERR_INVALID, "operator class \"%s\" does not exist for access method \"hnsw\"" % opclass)
+        self.elem, self.metric, self.normalized = OPCLASSES[opclass]
+        self.dim, self.m = dim, m
+        self.L = lib()
+        d = IndexDesc(self.elem, self.metric, dim, m, ef_construction, 0, capacity)
+        devs = np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        rc = self.L.pgvrx_group_create(C.byref(d), _p(devs), len(devs), C.byref(h))
+        if rc != OK:
+            raise PgvrxError(rc, self.L.pgvrx_group_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pgvrx_group_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != OK:
+            raise PgvrxError(rc, self.L.pgvrx_group_last_error(self.h).decode())
+
+    def __len__(self):
+        return self.L.pgvrx_group_size(self.h)
+
+    def peer_access(self):
+        return [bool(self.L.pgvrx_group_peer_access(self.h, i)) for i in range(len(self))]
+
+    def load_graph(self, rows, level, adj0, upper_base, adj_up, entry):
+        rows = _rows(self.elem, self.dim, rows)
+        level = np.ascontiguousarray(level, np.uint8)
+        adj0 = np.ascontiguousarray(adj0, np.int32)
+        upper_base = np.ascontiguousarray(upper_base, np.int32)
+        adj_up = np.ascontiguousarray(adj_up, np.int32).reshape(-1, self.m)
+        self._check(self.L.pgvrx_group_load_graph(self.h, _p(rows), len(rows), _p(level), _p(adj0), _p(upper_base),
+                                                  _p(adj_up) if len(adj_up) else None, len(adj_up), int(entry)))
+
+    def search(self, queries, k=10, ef_search=40, with_stats=False, out=None):
+        q = _rows(self.elem, self.dim, queries)
+        nq = len(q)
+        ids, dists, counts = out if out is not None else (np.empty((nq, k), np.int32), np.empty((nq, k), np.float32), np.empty(nq, np.int32))
+        st = GroupStats()
+        self._check(self.L.pgvrx_group_search_batch(self.h, _p(q), nq, ef_search, k, _p(ids), _p(dists), _p(counts), C.byref(st)))
+        return (ids, dists, counts, st.as_dict()) if with_stats else (ids, dists, counts)
+
+    def load_rows(self, rows):
+        rows = _rows(self.elem, self.dim, rows)
+        self._check(self.L.pgvrx_group_load_rows(self.h, _p(rows), len(rows)))
+
+    def flat_topk(self, queries, k=10, with_stats=False):
+        q = _rows(self.elem, self.dim, queries)
+        nq = len(q)
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        st = GroupStats()
+        self._check(self.L.pgvrx_group_flat_topk(self.h, _p(q), nq, k, _p(ids), _p(dists), C.byref(st)))
+        return (ids, dists, st.as_dict()) if with_stats else (ids, dists)
 
 
 class IterativeScan:

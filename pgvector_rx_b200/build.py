@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgvrx_b200.so")
-SOURCES = ["capi.cu", "hnsw_search.cu", "hnsw_build.cu", "hnsw_team.cu", "build_host.cu", "flat_knn.cu", "flat_host.cu", "flat_tc.cu", "flat_tc_host.cu", "hnsw_iter.cu", "iter_host.cu", "gather_probe.cu", "page_export.cpp", "page_write.cpp"]
+SOURCES = ["capi.cu", "hnsw_search.cu", "hnsw_build.cu", "hnsw_team.cu", "build_host.cu", "flat_knn.cu", "flat_host.cu", "flat_tc.cu", "flat_tc_host.cu", "hnsw_iter.cu", "iter_host.cu", "gather_probe.cu", "group.cu", "seam.cu", "page_export.cpp", "page_write.cpp"]
 HEADERS = ["hnsw_device.cuh", "hnsw_kernels.h", "index_internal.h", os.path.join("..", "..", "include", "pgvrx_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

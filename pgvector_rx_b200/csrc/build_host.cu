@@ -1718,7 +1718,21 @@ int pgvrx_index_graph_info(const pgvrx_index *ix, int64_t *n, int64_t *n_upper_r
 int pgvrx_index_export_graph(pgvrx_index *ix, void *rows, uint8_t *level, int32_t *adj0, int32_t *upper_base, int32_t *adj_up,
                              uint64_t *heap_tids, uint8_t *heap_tid_counts) {
     if (!ix) return PGVRX_ERR_INVALID;
-    if (!ix->build) return pgvrx_fail(ix, PGVRX_ERR_STATE, "export needs an index built with pgvrx_index_build");
+    if (!ix->build) {
+        // a handle that was loaded (or fed through pgvrx_commit_insert) has no host mirror yet: read the arrays back
+        if (!ix->loaded) return pgvrx_fail(ix, PGVRX_ERR_STATE, "no graph to export");
+        CU_TRY(ix, cudaSetDevice(ix->desc.device));
+        int avail = (int)std::max(1u, std::thread::hardware_concurrency());
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) avail = std::min(avail, (int)CPU_COUNT(&set));
+        try {
+            int rc = mirror_from_device(ix, avail);
+            if (rc) return rc;
+        } catch (const std::bad_alloc &) {
+            return host_oom(ix);
+        }
+    }
     BuildState &g = *ix->build;
     const int m = g.m;
     if (rows) memcpy(rows, g.values.data(), (size_t)g.n * g.row_bytes);

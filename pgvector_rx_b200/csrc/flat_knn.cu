@@ -318,6 +318,43 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const int32_t *__restri
     }
 }
 
+// The same merge with one pointer pair per part (parts may live on other GPUs: peer loads over NVLink).
+__global__ void __launch_bounds__(128) topk_merge_parts_kernel(MergeParts parts, int nq, int k_in, int k_out, int32_t *out_ids,
+                                                               float *out_dists) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    uint64_t *L = reinterpret_cast<uint64_t *>(smem) + (size_t)warp * k_out;
+    int len = 0;
+    for (int part = 0; part < parts.n_parts; part++) {
+        const int32_t *ids = parts.ids[part] + (size_t)q * k_in;
+        const float *dists = parts.dists[part] + (size_t)q * k_in;
+        for (int base = 0; base < k_in; base += 32) {
+            const int i = base + lane;
+            uint64_t key = FKEY_MAX;
+            if (i < k_in) {
+                const int32_t id = ids[i];
+                if (id >= 0) key = flat_key(dists[i], (uint32_t)id);
+            }
+            const uint64_t t = len == k_out ? L[k_out - 1] : FKEY_MAX;
+            uint32_t am = __ballot_sync(FULL, key < t);
+            if (!am) break;                     // lists ascend: nothing later in this part can qualify either
+            while (am) {
+                const int r = __ffs(am) - 1;
+                am &= am - 1;
+                topk_insert(L, len, k_out, __shfl_sync(FULL, key, r), lane);
+            }
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < k_out; i += 32) {
+        const size_t o = (size_t)q * k_out + i;
+        if (i < len) { out_ids[o] = (int32_t)(uint32_t)L[i]; out_dists[o] = ord_f32((uint32_t)(L[i] >> 32)); }
+        else { out_ids[o] = -1; out_dists[o] = __int_as_float(0x7f800000); }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // exact re-rank: per query, nc candidate row ids (-1 = none) -> exact distances, k smallest by (distance, id).
 // One warp per query; rows are gathered with per-row TMA bulk copies and evaluated one lane per row, exactly
@@ -447,6 +484,15 @@ cudaError_t launch_topk_merge(const int32_t *ids, const float *dists, int n_part
     cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     topk_merge_kernel<<<(nq + 3) / 4, 128, smem, stream>>>(ids, dists, n_parts, nq, k_in, k_out, out_ids, out_dists);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_topk_merge_parts(const MergeParts &parts, int nq, int k_in, int k_out, int32_t *out_ids, float *out_dists,
+                                    cudaStream_t stream) {
+    const size_t smem = (size_t)4 * k_out * 8;
+    cudaError_t e = cudaFuncSetAttribute(topk_merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    topk_merge_parts_kernel<<<(nq + 3) / 4, 128, smem, stream>>>(parts, nq, k_in, k_out, out_ids, out_dists);
     return cudaGetLastError();
 }
 

@@ -203,6 +203,16 @@ cudaError_t launch_flat_partial(int elem, int metric, const FlatParams &p, const
                                 size_t smem, cudaStream_t stream);
 cudaError_t launch_topk_merge(const int32_t *ids, const float *dists, int n_parts, int nq, int k_in, int k_out,
                               int32_t *out_ids, float *out_dists, cudaStream_t stream);
+// the same merge over per-shard lists that live in separate allocations -- other GPUs' memory included: with peer
+// access enabled the kernel's loads go over NVLink, so the gather and the merge are one pass (group.cu)
+constexpr int MERGE_MAX_PARTS = 64;
+struct MergeParts {
+    int n_parts;
+    const int32_t *ids[MERGE_MAX_PARTS];      // each [nq][k_in]
+    const float *dists[MERGE_MAX_PARTS];
+};
+cudaError_t launch_topk_merge_parts(const MergeParts &parts, int nq, int k_in, int k_out, int32_t *out_ids, float *out_dists,
+                                    cudaStream_t stream);
 size_t rerank_smem_bytes(uint32_t row_stride, uint32_t stage_stride, int R, int k);
 cudaError_t launch_rerank(int elem, int metric, const RerankParams &p, int grid, size_t smem, cudaStream_t stream);
 

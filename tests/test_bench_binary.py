@@ -55,3 +55,8 @@ def test_bench_binary_builds_replicates_and_scans(tmp_path):
     assert out["full_result_sets"] == 500                     # k rows per query (k <= ef_search)
     assert out["recall_at_k"] > 0.8                           # 32-d N(0,1), 20k rows, ef_search 40
     assert out["n_dist"] > 0 and out["build"]["vectors_per_s"] > 0
+    # the same devices behind one pgvrx_group: row-sharded exact kNN (merge over the members' lists) and one batch split
+    # by queries, both checked inside the binary against the single-device calls
+    grp = out["group"]
+    assert grp["members"] == 2 and grp["flat_equals_single_table"] == 1 and grp["scan_equals_single_device"] == 1
+    assert grp["flat_sharded_qps"] > 0 and grp["scan_one_batch_qps"] > 0 and grp["lists_read_in_place"] >= 1

@@ -253,6 +253,68 @@ int main(int argc, char **argv) {
         }
         recall = (double)hits / ((double)R * std::min<int64_t>(a.k, a.n));
     }
+    // ---- the same GPUs behind ONE handle (pgvrx_group_*): (a) exact flat kNN over row shards, per-shard lists merged by
+    //      one kernel on the lead device that reads the peers' lists over NVLink; (b) one caller batch split by queries
+    //      over the replicas (strong scaling of a single call) ----
+    double grp_flat_qps = 0.0, grp_flat_ms = 0.0, grp_merge_ms = 0.0, grp_scan_qps = 0.0, grp_scan_ms = 0.0;
+    int grp_peer = 0, grp_flat_ok = -1, grp_scan_ok = -1;
+    {
+        std::vector<int32_t> devs((size_t)a.gpus);
+        for (int g = 0; g < a.gpus; g++) devs[(size_t)g] = g % ndev;
+        int64_t n = 0, nu = 0, entry = -1;
+        int32_t entry_level = 0;
+        rc = pgvrx_index_graph_info(ix[0], &n, &nu, &entry, &entry_level);
+        if (rc) return fail(ix[0], "pgvrx_index_graph_info", rc);
+        std::vector<uint8_t> level((size_t)n);
+        std::vector<int32_t> adj0((size_t)n * 2 * a.m), upper_base((size_t)n), adj_up((size_t)std::max<int64_t>(nu, 1) * a.m);
+        std::vector<uint8_t> grows((size_t)n * row_bytes);
+        rc = pgvrx_index_export_graph(ix[0], grows.data(), level.data(), adj0.data(), upper_base.data(), adj_up.data(), nullptr, nullptr);
+        if (rc) return fail(ix[0], "pgvrx_index_export_graph", rc);
+        pgvrx_index_desc dg = d;
+        dg.capacity = n;
+        pgvrx_group *grp = nullptr;
+        rc = pgvrx_group_create(&dg, devs.data(), a.gpus, &grp);
+        if (rc) { std::fprintf(stderr, "pgvrx_bench: pgvrx_group_create failed (status %d): %s\n", rc, pgvrx_group_last_error(nullptr)); return 3; }
+        auto gfail = [&](const char *what, int code) {
+            std::fprintf(stderr, "pgvrx_bench: %s failed (status %d): %s\n", what, code, pgvrx_group_last_error(grp));
+            return 3;
+        };
+        const std::vector<float> &q = batches[0];
+        std::vector<int32_t> gid((size_t)a.nq * a.k), gcnt((size_t)a.nq), wid((size_t)a.nq * a.k), wcnt((size_t)a.nq);
+        std::vector<float> gd((size_t)a.nq * a.k), wd((size_t)a.nq * a.k);
+        const int reps = std::max(3, std::min(a.steps, 10));
+        pgvrx_group_stats gs;
+        // (a) sharded flat
+        rc = pgvrx_group_load_rows(grp, grows.data(), n);
+        if (rc) return gfail("pgvrx_group_load_rows", rc);
+        for (int r = 0; r < 2 && !rc; r++) rc = pgvrx_group_flat_topk(grp, q.data(), a.nq, a.k, gid.data(), gd.data(), &gs);
+        if (rc) return gfail("pgvrx_group_flat_topk", rc);
+        double t0 = now_s();
+        for (int r = 0; r < reps && !rc; r++) { rc = pgvrx_group_flat_topk(grp, q.data(), a.nq, a.k, gid.data(), gd.data(), &gs); grp_merge_ms += gs.merge_kernel_ms; }
+        if (rc) return gfail("pgvrx_group_flat_topk", rc);
+        grp_flat_ms = (now_s() - t0) * 1e3 / reps;
+        grp_flat_qps = a.nq / (grp_flat_ms / 1e3);
+        grp_merge_ms /= reps;
+        grp_peer = gs.n_peer_direct;
+        const int64_t RC = std::min<int64_t>(R > 0 ? R : 256, a.nq);
+        rc = pgvrx_flat_topk(ix[0], q.data(), RC, a.k, wid.data(), wd.data(), nullptr);
+        if (rc) return fail(ix[0], "pgvrx_flat_topk (group check)", rc);
+        grp_flat_ok = std::memcmp(gid.data(), wid.data(), (size_t)RC * a.k * 4) == 0 && std::memcmp(gd.data(), wd.data(), (size_t)RC * a.k * 4) == 0;
+        // (b) query-sharded scan of one batch
+        rc = pgvrx_group_load_graph(grp, grows.data(), n, level.data(), adj0.data(), upper_base.data(), adj_up.data(), nu, entry);
+        if (rc) return gfail("pgvrx_group_load_graph", rc);
+        for (int r = 0; r < 2 && !rc; r++) rc = pgvrx_group_search_batch(grp, q.data(), a.nq, a.ef, a.k, gid.data(), gd.data(), gcnt.data(), nullptr);
+        if (rc) return gfail("pgvrx_group_search_batch", rc);
+        t0 = now_s();
+        for (int r = 0; r < reps && !rc; r++) rc = pgvrx_group_search_batch(grp, q.data(), a.nq, a.ef, a.k, gid.data(), gd.data(), gcnt.data(), nullptr);
+        if (rc) return gfail("pgvrx_group_search_batch", rc);
+        grp_scan_ms = (now_s() - t0) * 1e3 / reps;
+        grp_scan_qps = a.nq / (grp_scan_ms / 1e3);
+        rc = pgvrx_search_batch(ix[0], q.data(), a.nq, a.ef, a.k, wid.data(), wd.data(), wcnt.data(), nullptr);
+        if (rc) return fail(ix[0], "pgvrx_search_batch (group check)", rc);
+        grp_scan_ok = std::memcmp(gid.data(), wid.data(), gid.size() * 4) == 0 && std::memcmp(gcnt.data(), wcnt.data(), gcnt.size() * 4) == 0;
+        pgvrx_group_destroy(grp);
+    }
     for (pgvrx_index *p : ix) pgvrx_index_destroy(p);
 
     std::printf("{\"binary\": \"pgvrx_bench\", \"metric\": \"QPS@recall@10 and build vectors/s\", \"value\": %.1f, \"unit\": \"queries/s\", "
@@ -260,6 +322,9 @@ int main(int argc, char **argv) {
                 "\"gpu_launches\": %llu, \"recall_at_k\": %.5f, \"recall_queries\": %lld, \"full_result_sets\": %lld, "
                 "\"gathered_gb_per_s_kernel\": %.1f, \"n_dist\": %llu, \"n_expand0\": %llu, \"n_expand_upper\": %llu, "
                 "\"build\": {\"vectors_per_s\": %.1f, \"seconds\": %.3f, \"rounds\": %llu, \"conflicts\": %llu, \"duplicates\": %llu, \"host_threads\": %d}, "
+                "\"group\": {\"members\": %d, \"flat_sharded_qps\": %.1f, \"flat_sharded_ms_per_batch\": %.4f, \"merge_kernel_ms\": %.4f, "
+                "\"lists_read_in_place\": %d, \"flat_equals_single_table\": %d, \"scan_one_batch_qps\": %.1f, \"scan_one_batch_ms\": %.4f, "
+                "\"scan_equals_single_device\": %d}, "
                 "\"config\": {\"workload\": \"%lldx%d fp32 vector_l2_ops m=%d ef_construction=%d ef_search=%d k=%d, %lld-query batches per GPU\", "
                 "\"path\": \"blocking pgvrx_search_batch on pageable host buffers, one host thread per GPU, graph replicated\"}}\n",
                 total_q / wall_max, a.gpus, std::min(a.gpus, ndev), a.steps, a.warmup, wall_max * 1e3 / a.steps, total_q / (kernel_max / 1e3),
@@ -267,6 +332,7 @@ int main(int argc, char **argv) {
                 kernel_max > 0 ? gathered / a.gpus / (kernel_max / 1e3) / 1e9 : 0.0, (unsigned long long)n_dist, (unsigned long long)n_e0,
                 (unsigned long long)n_eu, (double)a.n / build_s, build_s, (unsigned long long)bs.n_rounds,
                 (unsigned long long)bs.n_conflicts, (unsigned long long)bs.n_duplicates, bs.host_threads,
+                a.gpus, grp_flat_qps, grp_flat_ms, grp_merge_ms, grp_peer, grp_flat_ok, grp_scan_qps, grp_scan_ms, grp_scan_ok,
                 (long long)a.n, a.dim, a.m, a.efc, a.ef, a.k, (long long)a.nq);
     return 0;
 }
