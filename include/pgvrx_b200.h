@@ -341,6 +341,10 @@ typedef struct {
                                  generation + exact re-rank (large fp32 L2 / IP batches);
                                  2 = the same on CTA pairs (cta_group::2)                         */
     float    kernel_ms;       /* device time of the call's kernels (CUDA events)                  */
+    float    phase_ms[4];     /* tensor-core path only, device time per phase: [0] operand split of the
+                                 queries (+ of the table on its first use), [1] candidate kernel (GEMM +
+                                 per-query candidate sets), [2] exact re-rank, [3] certification and the
+                                 exact re-run of uncertified queries; zeros on the CUDA-core path    */
 } pgvrx_flat_stats;
 
 /* Upload a vector table without a graph (enough for the exact paths).  Element id == row number. */

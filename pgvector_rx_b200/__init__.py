@@ -117,10 +117,12 @@ class GroupStats(C.Structure):
 
 class FlatStats(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_candidates", C.c_uint64), ("n_uncertified", C.c_uint64), ("n_launches", C.c_uint32),
-                ("n_splits", C.c_uint32), ("path", C.c_uint32), ("kernel_ms", C.c_float)]
+                ("n_splits", C.c_uint32), ("path", C.c_uint32), ("kernel_ms", C.c_float), ("phase_ms", C.c_float * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["phase_ms"] = dict(zip(("operand_split", "candidates", "rerank", "certify"), [float(v) for v in self.phase_ms]))
+        return d
 
 
 _lib = None

@@ -472,6 +472,7 @@ int pgvrx_index_create(const pgvrx_index_desc *d, pgvrx_index **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ix->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ix->ev1);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ix->ev_ph[i]);
     if (e != cudaSuccess) {
         std::string msg = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e);
         pgvrx_index_destroy(ix);
@@ -498,6 +499,7 @@ void pgvrx_index_destroy(pgvrx_index *ix) {
     if (ix->build) pgvrx_host::destroy_build_state(ix->build);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
+    for (int i = 0; i < 4; i++) if (ix->ev_ph[i]) cudaEventDestroy(ix->ev_ph[i]);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }

@@ -136,6 +136,7 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     CU_TRY(ix, launch_tc_split((const uint8_t *)d_queries, (uint32_t)ix->row_bytes, nq, nq_pad, ix->desc.dim, d_pad,
                                (float *)ix->tc_qhi.p, (float *)ix->tc_qlo.p, (float *)ix->tc_qnorm.p, nullptr,
                                (uint32_t *)ix->tc_hint.p, stream));
+    if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[0], stream));
     alignas(64) unsigned char map_qhi[128], map_qlo[128];
     rc = make_map(ix, map_qhi, ix->tc_qhi.p, nq_pad, d_pad);
     if (rc) return rc;
@@ -172,9 +173,11 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     else CU_TRY(ix, launch_flat_tc(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, pl.grid, stream));
     int launches = 2;
     uint64_t n_uncert = 0;
+    if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[1], stream));
     if (d_ids) {
         rc = pgvrx_rerank_device(ix, d_queries, nq, (const int32_t *)ix->tc_cand.p, nc, k, id_base, d_ids, d_dists, stream);
         if (rc) return rc;
+        if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[2], stream));
         CU_TRY(ix, launch_tc_certify(d_dists, d_ids, k, (const float *)ix->tc_bound.p, pl.n_splits, (int)nq,
                                      (const float *)ix->tc_qnorm.p, (const uint32_t *)ix->tc_xmax.p, tc_eps_rel(ix->desc.dim),
                                      ix->desc.metric, (int32_t *)ix->tc_uncert.p, (int *)ix->tc_cnt.p, stream));
@@ -208,6 +211,12 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
         stats->n_launches = (uint32_t)launches;
         stats->n_splits = (uint32_t)pl.n_splits;
         stats->path = two_cta ? 2 : 1;
+        CU_TRY(ix, cudaEventElapsedTime(&stats->phase_ms[0], ix->ev0, ix->ev_ph[0]));
+        CU_TRY(ix, cudaEventElapsedTime(&stats->phase_ms[1], ix->ev_ph[0], ix->ev_ph[1]));
+        if (d_ids) {
+            CU_TRY(ix, cudaEventElapsedTime(&stats->phase_ms[2], ix->ev_ph[1], ix->ev_ph[2]));
+            CU_TRY(ix, cudaEventElapsedTime(&stats->phase_ms[3], ix->ev_ph[2], ix->ev1));
+        }
     }
     return PGVRX_OK;
 }

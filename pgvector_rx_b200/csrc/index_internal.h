@@ -58,6 +58,7 @@ struct pgvrx_index {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_ph[4] = {nullptr, nullptr, nullptr, nullptr};   // phase boundaries inside one flat-kNN call (stats only)
     // graph in HBM
     DevBuf vectors, adj0, adj_up, upper_base, level;
     DevBuf flags;               // per-element vacuum state (pgvrx_index_set_element_flags); used only when has_flags

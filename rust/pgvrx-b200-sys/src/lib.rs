@@ -2,8 +2,9 @@
 //!
 //! GENERATED from include/pgvrx_b200.h by tools/gen_rust_sys.py -- do not edit; re-run the generator instead.
 //! The header is the contract (it cites the reference seam each entry point replaces); this file mirrors every
-//! constant, enum value, struct field and prototype of it, in header order.  Safe wrappers and the two call-site
-//! changes in pgvector-rx (src/index/scan.rs, src/index/build.rs) are under rust/patches/.
+//! constant, enum value, struct field and prototype of it, in header order.  The safe wrapper crate is
+//! rust/pgvrx-b200 (with the standalone bench binary), the modules pgvector-rx gains at its two seams
+//! (src/index/scan.rs, src/index/build.rs) are rust/pgvector-rx-shim.
 #![allow(non_camel_case_types, non_upper_case_globals)]
 
 use std::os::raw::{c_char, c_int, c_void};
@@ -148,6 +149,7 @@ pub struct PgvrxFlatStats {
     pub n_splits: u32,
     pub path: u32,
     pub kernel_ms: f32,
+    pub phase_ms: [f32; 4],
 }
 
 #[repr(C)]

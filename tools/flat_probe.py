@@ -32,6 +32,15 @@ for it in range(4):
     print("flat %s n=%d nq=%d k=%d dim=%d path=%d: %.2f ms, %.1f kQPS, %.1f TFLOP/s issued, splits %d, candidates/query %d, uncertified %d"
           % (opclass, n, nq, k, dim, st.path, st.kernel_ms, nq / st.kernel_ms, flops / st.kernel_ms / 1e9, st.n_splits,
              st.n_candidates // max(nq, 1), st.n_uncertified), flush=True)
+    if st.path >= 1:
+        print("    phases (ms): " + ", ".join("%s %.3f" % kv for kv in st.as_dict()["phase_ms"].items()), flush=True)
+# the same call without stats (asynchronous), as the sharded path issues it: wall time per call, 10 calls back to back
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for it in range(10):
+    ix.flat_topk_device(d_q.data_ptr(), nq, k, ids.data_ptr(), ds.data_ptr())
+torch.cuda.synchronize()
+print("    10 calls without stats: %.3f ms per call (wall)" % ((time.perf_counter() - t0) * 100), flush=True)
 if len(sys.argv) > 7:
     # cross-check the two paths against each other on a sample
     os.environ["PGVRX_FLAT_PATH"] = "exact"

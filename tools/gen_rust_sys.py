@@ -100,8 +100,9 @@ def generate(text):
     w("//!")
     w("//! GENERATED from include/pgvrx_b200.h by tools/gen_rust_sys.py -- do not edit; re-run the generator instead.")
     w("//! The header is the contract (it cites the reference seam each entry point replaces); this file mirrors every")
-    w("//! constant, enum value, struct field and prototype of it, in header order.  Safe wrappers and the two call-site")
-    w("//! changes in pgvector-rx (src/index/scan.rs, src/index/build.rs) are under rust/patches/.")
+    w("//! constant, enum value, struct field and prototype of it, in header order.  The safe wrapper crate is")
+    w("//! rust/pgvrx-b200 (with the standalone bench binary), the modules pgvector-rx gains at its two seams")
+    w("//! (src/index/scan.rs, src/index/build.rs) are rust/pgvector-rx-shim.")
     w("#![allow(non_camel_case_types, non_upper_case_globals)]")
     w("")
     w("use std::os::raw::{c_char, c_int, c_void};")
@@ -127,7 +128,11 @@ def generate(text):
         w("#[derive(Debug, Clone, Copy)]")
         w("pub struct %s {" % camel(sname))
         for ty, nm in fields:
-            w("    pub %s: %s," % (nm, rust_type(ty, struct_names)))
+            arr = re.match(r"(\w+)\[(\d+)\]$", nm)            # fixed-size array member: `float phase_ms[4]`
+            if arr:
+                w("    pub %s: [%s; %s]," % (arr.group(1), rust_type(ty, struct_names), arr.group(2)))
+            else:
+                w("    pub %s: %s," % (nm, rust_type(ty, struct_names)))
         w("}")
         w("")
     w('#[link(name = "pgvrx_b200")]')
