@@ -780,43 +780,60 @@ def iterative_section(a, ix, o, queries, filt, nq_it, limit=10):
     mst = a.cfg.get("max_scan_tuples", 20000)
     t0 = time.perf_counter()
     sc = ix.scan_begin(q, ef_search=a.ef, iterative_scan=P.ITER_RELAXED, max_scan_tuples=mst, prepared=True)
-    hits = [[] for _ in range(nq_it)]
+    hit_ids = np.full((nq_it, limit), -1, np.int64)    # the consumer's rows, in the order it received them
     seen = np.zeros(nq_it, np.int64)                   # elements each query's consumer has looked at
     n_hits = np.zeros(nq_it, np.int64)
     done = np.zeros(nq_it, bool)
     rounds = 0
     emitted = 0
+    col = np.arange(a.ef)[None, :]
     while True:
         want = ~done & (n_hits < limit)
         if not want.any():
             break
         ii, dd, cc, dn = sc.next(want.astype(np.uint8))
         rounds += 1
-        for i in np.nonzero(want)[0]:
-            sel = ii[i, :cc[i]]
-            emitted += int(cc[i])
-            seen[i] += int(cc[i])
-            sel = sel[sel % filt == 0]
-            take = sel[: limit - n_hits[i]]
-            hits[i].extend(take.tolist())
-            n_hits[i] += len(take)
-        done |= dn
+        # the executor's filter, for all queries of the round at once: matching elements in emission order, as many as
+        # the query still lacks
+        cw = np.where(want, cc, 0)
+        emitted += int(cw.sum())
+        seen += cw
+        match = (col < cw[:, None]) & (ii % filt == 0)
+        rank = np.cumsum(match, axis=1) - 1 + n_hits[:, None]          # slot each match would take
+        take = match & (rank < limit)
+        r_, c_ = np.nonzero(take)
+        hit_ids[r_, rank[r_, c_]] = ii[r_, c_]
+        n_hits += take.sum(axis=1)
+        done |= dn.astype(bool)
     dt = time.perf_counter() - t0
+    hits = [[int(v) for v in hit_ids[i, :n_hits[i]]] for i in range(nq_it)]
     tot = dict(sc.totals)
     sc.close()
-    ok = True
-    n_chk = min(6 if filt >= 500 else 12, nq_it)
-    for i in range(n_chk):
-        # the oracle's amgettuple stream, as far as the GPU consumer had to look (elements hold one heap TID each here)
+    # the oracle's amgettuple stream for a sample of the queries, as far as the GPU consumer had to look (elements hold one
+    # heap TID each here): parity of the filtered rows, and the CPU arm of this section -- one query per host thread
+    # (one backend = one thread in the reference), wall clock
+    from concurrent.futures import ThreadPoolExecutor
+    cores = host_cores(a)
+    n_chk = min(max(cores, 12), nq_it)
+
+    def cpu_stream(i):
         _, eids, _, _ = o.scan_stream(q[i], ef_search=a.ef, iterative=O.ITER_RELAXED, max_scan_tuples=mst, max_emit=int(seen[i]))
-        ok &= [int(e) for e in eids if e % filt == 0][:limit] == hits[i]
+        return [int(e) for e in eids if e % filt == 0][:limit]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        cpu_hits = list(ex.map(cpu_stream, range(n_chk)))
+    cpu_dt = time.perf_counter() - t0
+    ok = all(cpu_hits[i] == hits[i] for i in range(n_chk))
     rb = ix.L.pgvrx_row_bytes(ix.elem, a.dim)
     gathered = tot["n_dist"] * ((rb + 15) // 16 * 16) + tot["n_expand0"] * 2 * a.m * 4 + tot["n_expand_upper"] * a.m * 4
     return dict(filter="id %% %d == 0" % filt, limit=limit, queries=nq_it, value=nq_it / dt, unit="queries/s (end to end, host buffers)",
                 seconds=dt, rounds=rounds, kernel_ms=tot["kernel_ms"], elements_emitted_per_query=emitted / nq_it,
                 queries_with_all_hits=int((n_hits >= limit).sum()), max_scan_tuples=mst,
                 gathered_GBps_in_kernels=gathered / (tot["kernel_ms"] / 1e3) / 1e9 if tot["kernel_ms"] else None,
-                streams_match_oracle=bool(ok), streams_checked=n_chk)
+                streams_match_oracle=bool(ok), streams_checked=n_chk,
+                cpu_baseline=dict(value=n_chk / cpu_dt, unit="queries/s", cores=cores, kind="port",
+                                  sample="%d queries, the same filter, limit and stream length as the GPU consumer, one query per host thread, %.1f s"
+                                         % (n_chk, cpu_dt)))
 
 
 def rerank_section(a, ix, o, queries, gt_ids, ns=2000, k_prime=100):
@@ -824,6 +841,8 @@ def rerank_section(a, ix, o, queries, gt_ids, ns=2000, k_prime=100):
     ns = min(ns, len(queries))
     q = queries[:ns]
     ef = max(a.ef, k_prime)
+    ix.search(q[:64], k=k_prime, ef_search=ef, prepared=True)        # scratch for this ef / k is allocated on first use
+    ix.rerank(q[:64], np.zeros((64, k_prime), np.int32), k=a.k, prepared=True)
     t0 = time.perf_counter()
     ids, dists, counts = ix.search(q, k=k_prime, ef_search=ef, prepared=True)
     t_scan = time.perf_counter() - t0

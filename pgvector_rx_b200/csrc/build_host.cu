@@ -356,7 +356,11 @@ static void simulate_group(BuildState &g, Group &G, const uint32_t *masks /* row
 // otherwise sort the list by distance to the node (stable: ties keep slot order, the new element last among equals),
 // run the closer-test heuristic in which the new element is never pruned and never prunes, and if the new element is
 // among the lm kept, overwrite the first slot (in stored order) whose element was not kept.  Slots keep their places.
-static void simulate_group_disk(BuildState &g, Group &G, const uint32_t *masks /* rows of this group or NULL */) {
+// On an index a vacuum has touched (`flagged`): a full list that still holds an element flagged deleted, or one left
+// without heap TIDs, gives that slot -- the first such in stored order -- to the new element at once (:569-623).
+// Elements at or above `e_base` are the pending ones of this round (their heap TID is assigned when they commit).
+static void simulate_group_disk(BuildState &g, Group &G, const uint32_t *masks /* rows of this group or NULL */,
+                                const bool flagged = false, const int64_t e_base = 0) {
     constexpr int W = PAIR_MAX_ROWS / 32;
     const int lm = G.lm, n_members = (int)G.ids.size() - G.n_list;
     G.st_ids.assign((size_t)n_members * lm, -1);
@@ -377,6 +381,14 @@ static void simulate_group_disk(BuildState &g, Group &G, const uint32_t *masks /
             cur[cnt] = nw;
             cur_pos[cnt] = epos;
             cnt++;
+        } else if (flagged && [&]() {
+                       for (int t = 0; t < cnt; t++) {
+                           const int64_t x = cur[t].idx;
+                           if (x < e_base && (g.del[(size_t)x] || g.tid_cnt[(size_t)x] == 0)) { cur[t] = nw; cur_pos[t] = epos; return true; }
+                       }
+                       return false;
+                   }()) {
+            // (slot of a deleted / emptied element reused, insert.rs:620-623)
         } else {
             for (int t = 0; t < cnt; t++) { order[t] = t; kept_slot[t] = false; }
             std::stable_sort(order, order + cnt, [&](int x, int y) { return cur[x].distance < cur[y].distance; });   // :628-632
@@ -603,7 +615,9 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_rows < 0 || (n_rows > 0 && (!rows_in || !levels))) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null build input");
     if (!disk_rule && ix->loaded && !ix->build) return pgvrx_fail(ix, PGVRX_ERR_STATE, "index was loaded from arrays; build needs a handle that is empty or was built here");
-    if (ix->has_flags) return pgvrx_fail(ix, PGVRX_ERR_STATE, "element flags are set (vacuumed index); inserts into it are not supported");
+    // CREATE INDEX has no notion of deleted elements; aminsert does (load_element skips them, get_update_index reuses their
+    // slots in neighbour lists: insert.rs:525-528, 569-623)
+    if (ix->has_flags && !disk_rule) return pgvrx_fail(ix, PGVRX_ERR_STATE, "element flags are set (vacuumed index): use pgvrx_index_insert");
     CU_TRY(ix, cudaSetDevice(ix->desc.device));
     if (disk_rule && ix->loaded && !ix->build) {
         int avail0 = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -647,6 +661,10 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     CU_TRY(ix, ix->adj_up.ensure_keep(std::max<size_t>(16, (size_t)up_needed * m * 4), (size_t)g.n_upper * m * 4));
     CU_TRY(ix, ix->upper_base.ensure_keep(std::max<size_t>(16, (size_t)cap * 4), (size_t)g.n * 4));
     CU_TRY(ix, ix->level.ensure_keep(std::max<size_t>(16, (size_t)cap), (size_t)g.n));
+    if (ix->has_flags) {               // new elements carry no flags
+        CU_TRY(ix, ix->flags.ensure_keep(std::max<size_t>(16, (size_t)cap), (size_t)g.n));
+        if (cap > g.n) CU_TRY(ix, cudaMemset((uint8_t *)ix->flags.p + g.n, 0, (size_t)(cap - g.n)));
+    }
     ix->generation++;                  // open iterative scans were sized for the old graph
     ix->loaded = false;
     ix->rows_loaded = false;
@@ -745,18 +763,21 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     uint64_t c_dist = 0, c_exp0 = 0, c_expu = 0;
 
     // the first element of an empty index becomes the entry point without a search (build.rs:526-529)
-    if (g.n == 0 && n_rows > 0) {
-        place_element(0, 0);
-        g.tids[0] = tid_of(0);
-        g.tid_cnt[0] = 1;
+    // (so does the first element inserted after a vacuum that left no entry point behind: insert.rs:1317-1334 finds no
+    // neighbours without one, :1454-1470 makes the element the entry point)
+    if (g.entry < 0 && n_rows > 0) {
+        const int64_t e0 = g.n;
+        place_element(0, e0);
+        g.tids[(size_t)e0 * PGVRX_HEAPTIDS] = tid_of(0);
+        g.tid_cnt[(size_t)e0] = 1;
         g.n_upper += levels[0];
-        g.n = 1;
-        g.entry = 0;
+        g.n = e0 + 1;
+        g.entry = e0;
         g.entry_level = levels[0];
-        int rc = upload_elements(0, 1);
+        int rc = upload_elements(e0, e0 + 1);
         if (rc) return rc;
-        queue_row(0, 0);
-        for (int l = 1; l <= levels[0]; l++) queue_row(0, l);
+        queue_row(e0, 0);
+        for (int l = 1; l <= levels[0]; l++) queue_row(e0, l);
         rc = flush_scatter();
         if (rc) return rc;
         f = 1;
@@ -768,7 +789,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     // 27.7 s -> 18.6 s), off for rows that are staged whole -- there nearly every popped candidate is one the previous
     // expansion has just inserted, nothing can be computed ahead of it, and the two kernels take the same time (C2 100k
     // rows: 5.84 s vs 5.93 s).  PGVRX_BUILD_TEAM=0/1 pins the choice.
-    bool team_on = ix->row_stride > 1056;
+    bool team_on = ix->row_stride > 1056 && !ix->has_flags;     // (the CTA-per-search kernel has no flagged form)
     if (const char *e = getenv("PGVRX_BUILD_TEAM")) team_on = atoi(e) != 0;
     uint64_t n_team_rounds = 0;
     // scratch escalation for a search that overflowed its visited table / tie tail: the head of the round is re-run alone
@@ -903,7 +924,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         TeamGeom tg;
         size_t team_smem = 0;
         int team_grid = 0;
-        const bool use_team = team_on && big_level == 0 && team_config(ix, cfg, efc, B, &tg, &team_smem, &team_grid);
+        const bool use_team = team_on && !ix->has_flags && big_level == 0 && team_config(ix, cfg, efc, B, &tg, &team_smem, &team_grid);
         if (use_team) {
             CU_TRY(ix, launch_team_build(ix->desc.elem_type, ix->desc.metric, cfg.L.list_j, gv, bp, tg, team_grid, team_smem, ix->stream));
             n_team_rounds++;
@@ -1106,7 +1127,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         const double tB0 = now_ms();
         pool.parallel_for(n_groups, [&](int64_t gi) {
             Group &G = *all_groups[(size_t)gi];
-            if (disk_rule) simulate_group_disk(g, G, G.row_off >= 0 ? mask_all + (size_t)G.row_off * MW : nullptr);
+            if (disk_rule) simulate_group_disk(g, G, G.row_off >= 0 ? mask_all + (size_t)G.row_off * MW : nullptr, ix->has_flags, e_base);
             else simulate_group(g, G, G.row_off >= 0 ? mask_all + (size_t)G.row_off * MW : nullptr);
         });
         t_sim += now_ms() - tB0;

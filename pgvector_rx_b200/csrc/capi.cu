@@ -88,8 +88,9 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     ScanConfig c;
     c.L.ef = ef;
     c.L.list_j = 0;
-    // an index that carries vacuum flags scans with the shared-memory list only (one extra kernel per opclass, not four)
-    const bool flagged = !for_build && ix->has_flags;
+    // an index that carries vacuum flags scans -- and takes inserts -- with the shared-memory list only (one extra kernel
+    // per opclass and path, not four)
+    const bool flagged = ix->has_flags;
     if (tail_cap < 0) {
         tail_cap = 32;
         if (!flagged) for (int j = 2; j <= 8; j *= 2)
@@ -133,7 +134,7 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
     c.smem_block = search_warp_smem(c.L) * wpb;
     if (c.smem_block > 227 * 1024) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search configuration exceeds shared memory");
     int occ = 0;
-    if (for_build) CU_TRY(ix, build_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, c.smem_block, wpb * 32, &occ));
+    if (for_build) CU_TRY(ix, build_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, flagged, c.smem_block, wpb * 32, &occ));
     else CU_TRY(ix, scan_kernel_occupancy(ix->desc.elem_type, ix->desc.metric, c.L.list_j, flagged, c.smem_block, wpb * 32, &occ));
     if (occ < 1) return fail(ix, PGVRX_ERR_UNSUPPORTED, "search kernel does not fit on an SM");
     int64_t want = (nq + wpb - 1) / wpb;

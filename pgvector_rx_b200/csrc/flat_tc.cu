@@ -151,15 +151,17 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
     float xn_cur[TN / 128];
 #pragma unroll
     for (int h = 0; h < TN / 128; h++) xn_cur[h] = p.xnorm[(int64_t)nt0 * TN + h * 128 + et];
+    // a set of kp_eff < 32 keys (the hint pre-pass): the other slots hold key 0, which nothing replaces and which is never
+    // the maximum once a real key is present
 #pragma unroll 4
-    for (int i = 0; i < 32; i++) Lw[i * TC_KP + lane] = ~0ull;
+    for (int i = 0; i < 32; i++) Lw[i * TC_KP + lane] = lane < p.kp_eff ? ~0ull : 0ull;
     __syncwarp();
-    for (int nt = nt0; nt < nt1; nt++) {
+    for (int nt = nt0; nt < nt1; nt += p.tile_step) {
         const int64_t row0 = (int64_t)nt * TN;
 #pragma unroll
         for (int h = 0; h < TN / 128; h++) {
             sxn[buf * TN + h * 128 + et] = xn_cur[h];
-            if (nt + 1 < nt1) xn_cur[h] = p.xnorm[row0 + TN + h * 128 + et];   // in flight while this tile is processed
+            if (nt + p.tile_step < nt1) xn_cur[h] = p.xnorm[row0 + (int64_t)p.tile_step * TN + h * 128 + et];   // in flight while this tile is processed
         }
         const uint32_t hint_ord = qvalid ? __ldcg(p.hint + q) : 0xFF800000u;
         asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps only
@@ -248,14 +250,17 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
     }
     __syncwarp();
     // candidates of query (quarter * 32 + i), one per lane; -1 where the split had fewer than KP rows
-    for (int i = 0; i < 32; i++) {
-        const int qi = q_tile0 + quarter * 32 + i;
-        if (qi >= p.nq) break;
-        const uint64_t cur = Lw[i * TC_KP + lane];
-        p.cand_ids[((size_t)qi * p.n_splits + sp) * TC_KP + lane] = cur == ~0ull ? -1 : (int32_t)((uint32_t)cur + (uint32_t)p.id_base);
+    // (the hint pre-pass has no outputs but p.hint)
+    if (p.cand_ids) {
+        for (int i = 0; i < 32; i++) {
+            const int qi = q_tile0 + quarter * 32 + i;
+            if (qi >= p.nq) break;
+            const uint64_t cur = Lw[i * TC_KP + lane];
+            p.cand_ids[((size_t)qi * p.n_splits + sp) * TC_KP + lane] = cur == ~0ull ? -1 : (int32_t)((uint32_t)cur + (uint32_t)p.id_base);
+        }
     }
     // every row of this split that was not kept has an approximate distance >= this bound
-    if (qvalid) p.cand_bound[(size_t)sp * p.nq + q] = tau == ~0ull ? __int_as_float(0x7f800000) : ord_f32((uint32_t)(tau >> 32));
+    if (qvalid && p.cand_bound) p.cand_bound[(size_t)sp * p.nq + q] = tau == ~0ull ? __int_as_float(0x7f800000) : ord_f32((uint32_t)(tau >> 32));
     __syncwarp();
 }
 
@@ -322,7 +327,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                     }
                     aph ^= 1u;
                 }
-                for (int nt = nt0; nt < nt1; nt++) {
+                for (int nt = nt0; nt < nt1; nt += p.tile_step) {
                     for (int kb = 0; kb < n_kb; kb++) {
                         mbar_wait(empty + stage, phase ^ 1u);
                         uint8_t *st = ring + (size_t)stage * stage_bytes;
@@ -354,7 +359,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
                     tc_fence_after();
                     aph ^= 1u;
                 }
-                for (int nt = nt0; nt < nt1; nt++) {
+                for (int nt = nt0; nt < nt1; nt += p.tile_step) {
                     mbar_wait(tempty + buf, aphase ^ 1u);          // the epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_N;
@@ -503,7 +508,7 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                     tma_load_2d_2sm(a_res + (size_t)kb * 2 * TC_TILE_BYTES + TC_TILE_BYTES, &map_qlo, kb * TC_KB, mt * TC2_M + (int)rank * TC_M, l_afull, pol_q);
                 }
                 aph ^= 1u;
-                for (int nt = nt0; nt < nt1; nt++) {
+                for (int nt = nt0; nt < nt1; nt += p.tile_step) {
                     for (int kb = 0; kb < n_kb; kb++) {
 #pragma unroll
                         for (int half = 0; half < 2; half++) {      // x_hi slot, then x_lo slot
@@ -531,7 +536,7 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
                 mbar_wait_backoff(afull, aph, 100);
                 tc_fence_after();
                 aph ^= 1u;
-                for (int nt = nt0; nt < nt1; nt++) {
+                for (int nt = nt0; nt < nt1; nt += p.tile_step) {
                     mbar_wait_backoff(tempty + buf, aphase ^ 1u, 50);          // both CTAs' epilogues have drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC2_N;
@@ -594,11 +599,14 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
 // is provably further away than its k-th result: exact(r) >= approx(r) - eps >= min_s bound_s - eps > E_k.
 __global__ void tc_certify_kernel(const float *__restrict__ topk_dists, const int32_t *__restrict__ topk_ids, int k,
                                   const float *__restrict__ cand_bound, int n_splits, int nq, const float *__restrict__ qnorm,
-                                  const uint32_t *__restrict__ xnorm_max, float eps_rel, int metric, int32_t *uncert_list,
-                                  int *n_uncert) {
+                                  const uint32_t *__restrict__ xnorm_max, float eps_rel, int metric, const uint32_t *__restrict__ hint,
+                                  int32_t *uncert_list, int *n_uncert) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    float bound = __int_as_float(0x7f800000);
+    // Rows were rejected against min(the unit's own full-set maximum, hint[q] at the time); the hint only ever decreases
+    // (atomicMin of full-set maxima, seeded by the sample pre-pass), so its final value is a lower bound of every
+    // threshold used: every unkept row has an approximate distance >= min(split bounds, final hint).
+    float bound = hint ? ord_f32(hint[q]) : __int_as_float(0x7f800000);
     for (int s = 0; s < n_splits; s++) bound = fminf(bound, cand_bound[(size_t)s * nq + q]);
     bool ok = true;
     if (bound < __int_as_float(0x7f800000)) {
@@ -671,10 +679,10 @@ cudaError_t launch_flat_tc2(const void *map_qhi, const void *map_qlo, const void
 }
 
 cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
-                              const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, int32_t *uncert_list,
-                              int *n_uncert, cudaStream_t stream) {
+                              const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, const uint32_t *hint,
+                              int32_t *uncert_list, int *n_uncert, cudaStream_t stream) {
     tc_certify_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(topk_dists, topk_ids, k, cand_bound, n_splits, nq, qnorm, xnorm_max,
-                                                            eps_rel, metric, uncert_list, n_uncert);
+                                                            eps_rel, metric, hint, uncert_list, n_uncert);
     return cudaGetLastError();
 }
 

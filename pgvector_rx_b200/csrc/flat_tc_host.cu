@@ -169,9 +169,35 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     p.cand_bound = (float *)ix->tc_bound.p;
     p.dbg_scores = d_dbg_scores;
     p.hint = (uint32_t *)ix->tc_hint.p;
+    p.tile_step = 1;
+    p.kp_eff = TC_KP;
+    // Hint pre-pass.  A unit (query tile x base split) starts with empty candidate sets, and until a set's maximum has
+    // come down nearly every element takes the serial insertion path: KP (1 + ln(rows / KP)) insertions per query and
+    // unit.  Units of later waves inherit a threshold from earlier ones through p.hint; the first wave does not, and
+    // with short units (a shard of a row-sharded table: 125k rows = 98 tiles per unit) that warm-up is as long as the
+    // tensor work itself (measured: 3.3 ms for 1.65 ms of MMAs).  So every query first sees a strided SAMPLE of the
+    // table -- every step-th tile, one unit per query tile, sets of kp_eff keys -- which leaves in p.hint the kp_eff-th
+    // smallest approximate distance of the sample: about kp_eff * step rows of the table lie below it, several times k.
+    // The main pass then starts from that threshold everywhere.  The certificate takes the final hint into account.
+    const bool prepass = d_ids && pl.tiles_per_split <= 256 && pl.n_ntiles >= 64 && !getenv("PGVRX_TC_NO_PREPASS");
+    if (prepass) {
+        TcParams pa = p;
+        const int want_tiles = std::max(4, std::min(64, pl.n_ntiles / 16));
+        pa.tile_step = std::max(1, pl.n_ntiles / want_tiles);
+        pa.kp_eff = std::max(8, std::min((int)TC_KP, k + 6));
+        pa.n_splits = 1;
+        pa.ntiles_per_split = pl.n_ntiles;
+        pa.cand_ids = nullptr;
+        pa.cand_bound = nullptr;
+        pa.dbg_scores = nullptr;
+        const int workers = two_cta ? ix->sm_count / 2 : ix->sm_count;
+        const int ga = std::min(pl.n_mtiles, workers);
+        if (two_cta) CU_TRY(ix, launch_flat_tc2(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, pa, 2 * ga, stream));
+        else CU_TRY(ix, launch_flat_tc(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, pa, ga, stream));
+    }
     if (two_cta) CU_TRY(ix, launch_flat_tc2(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, 2 * pl.grid, stream));
     else CU_TRY(ix, launch_flat_tc(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, pl.grid, stream));
-    int launches = 2;
+    int launches = prepass ? 3 : 2;
     uint64_t n_uncert = 0;
     if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[1], stream));
     if (d_ids) {
@@ -180,7 +206,7 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
         if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[2], stream));
         CU_TRY(ix, launch_tc_certify(d_dists, d_ids, k, (const float *)ix->tc_bound.p, pl.n_splits, (int)nq,
                                      (const float *)ix->tc_qnorm.p, (const uint32_t *)ix->tc_xmax.p, tc_eps_rel(ix->desc.dim),
-                                     ix->desc.metric, (int32_t *)ix->tc_uncert.p, (int *)ix->tc_cnt.p, stream));
+                                     ix->desc.metric, (const uint32_t *)ix->tc_hint.p, (int32_t *)ix->tc_uncert.p, (int *)ix->tc_cnt.p, stream));
         launches += 2;
         int nu = 0;
         CU_TRY(ix, cudaMemcpyAsync(&nu, ix->tc_cnt.p, 4, cudaMemcpyDeviceToHost, stream));

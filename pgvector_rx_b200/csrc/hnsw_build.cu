@@ -25,7 +25,10 @@ template <> struct BListOf<0> {
     __device__ static __forceinline__ void attach(type &l, uint8_t *mem) { l.S = reinterpret_cast<uint64_t *>(mem); l.hint = 0; }
 };
 
-template <int ELEM, int METRIC, int LISTJ>
+// FLAGGED: the index carries vacuum flags (inserts into a vacuumed index): elements flagged deleted are visited and nothing
+// else (load_element, scan.rs:179), and a deleted entry point leaves the new element without neighbours
+// (find_element_neighbors_on_disk, insert.rs:1036-1047).  Only built for the shared-memory list.
+template <int ELEM, int METRIC, int LISTJ, bool FLAGGED = false>
 __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(GraphView g, BuildParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
@@ -77,6 +80,19 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
         c.rs_cap = p.rs_cap;
         c.rs_n = 0;
         for (int l = lane; l < p.max_layers; l += 32) p.w_counts[(size_t)w * p.max_layers + l] = -1;
+        if constexpr (FLAGGED) {
+            if (__ldg(g.flags + g.entry) & ELEM_FLAG_DELETED) {       // load_element(entry) => None: every list stays empty
+                __syncwarp();
+                for (int l = lane; l < p.max_layers && l <= min(lvl, g.entry_level); l += 32) p.w_counts[(size_t)w * p.max_layers + l] = 0;
+                if (lane == 0) {
+                    p.out_status[w] = 0;
+                    p.rs_counts[w] = 0;
+                    if (p.out_ctr) reinterpret_cast<uint4 *>(p.out_ctr)[w] = make_uint4(0, 0, 0, 0);
+                }
+                __syncwarp();
+                continue;
+            }
+        }
 
         // the new element's own row is the query (build.rs:444-454 copies it into the arena first)
         {
@@ -102,7 +118,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
             __syncwarp();
             c.n_vis++;
             S.reset1(c, ep_key);
-            search_layer<ELEM, METRIC>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
+            search_layer<ELEM, METRIC, FLAGGED>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
             ep_key = S.get(c, 0) & ~1ull;                                           // :396-398 w[0]
         }
         // phase 2: ef_construction search on every layer the new element joins (graph/mod.rs:403-426)
@@ -120,7 +136,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
                 c.n_vis += c.len;
             }
             first = false;
-            search_layer<ELEM, METRIC>(c, S, g, lc, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
+            search_layer<ELEM, METRIC, FLAGGED>(c, S, g, lc, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
             if (c.status == 0 && lc < p.max_layers) {
                 const int out_n = min(c.len, c.ef);
                 const size_t o = ((size_t)w * p.max_layers + lc) * p.efc;
@@ -453,7 +469,8 @@ cudaError_t launch_pairwise(int elem, int metric, const GraphView &g, const Pair
 typedef void (*build_kernel_t)(GraphView, BuildParams);
 
 template <int ELEM, int METRIC>
-static build_kernel_t pick_list(int list_j) {
+static build_kernel_t pick_list(int list_j, bool flagged) {
+    if (flagged) return list_j == 0 ? hnsw_build_search_kernel<ELEM, METRIC, 0, true> : nullptr;
     switch (list_j) {
         case 2: return hnsw_build_search_kernel<ELEM, METRIC, 2>;
         case 4: return hnsw_build_search_kernel<ELEM, METRIC, 4>;
@@ -463,24 +480,24 @@ static build_kernel_t pick_list(int list_j) {
     return nullptr;
 }
 
-static build_kernel_t pick_kernel(int elem, int metric, int list_j) {
+static build_kernel_t pick_kernel(int elem, int metric, int list_j, bool flagged) {
     if (elem == ELEM_F32) {
-        if (metric == METRIC_L2SQ) return pick_list<ELEM_F32, METRIC_L2SQ>(list_j);
-        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F32, METRIC_NEG_IP>(list_j);
-        if (metric == METRIC_L1) return pick_list<ELEM_F32, METRIC_L1>(list_j);
+        if (metric == METRIC_L2SQ) return pick_list<ELEM_F32, METRIC_L2SQ>(list_j, flagged);
+        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F32, METRIC_NEG_IP>(list_j, flagged);
+        if (metric == METRIC_L1) return pick_list<ELEM_F32, METRIC_L1>(list_j, flagged);
     } else if (elem == ELEM_F16) {
-        if (metric == METRIC_L2SQ) return pick_list<ELEM_F16, METRIC_L2SQ>(list_j);
-        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F16, METRIC_NEG_IP>(list_j);
-        if (metric == METRIC_L1) return pick_list<ELEM_F16, METRIC_L1>(list_j);
+        if (metric == METRIC_L2SQ) return pick_list<ELEM_F16, METRIC_L2SQ>(list_j, flagged);
+        if (metric == METRIC_NEG_IP) return pick_list<ELEM_F16, METRIC_NEG_IP>(list_j, flagged);
+        if (metric == METRIC_L1) return pick_list<ELEM_F16, METRIC_L1>(list_j, flagged);
     } else if (elem == ELEM_BIT) {
-        if (metric == METRIC_HAMMING) return pick_list<ELEM_BIT, METRIC_HAMMING>(list_j);
-        if (metric == METRIC_JACCARD) return pick_list<ELEM_BIT, METRIC_JACCARD>(list_j);
+        if (metric == METRIC_HAMMING) return pick_list<ELEM_BIT, METRIC_HAMMING>(list_j, flagged);
+        if (metric == METRIC_JACCARD) return pick_list<ELEM_BIT, METRIC_JACCARD>(list_j, flagged);
     }
     return nullptr;
 }
 
-cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm) {
-    build_kernel_t k = pick_kernel(elem, metric, list_j);
+cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, bool flagged, size_t smem_block, int threads, int *blocks_per_sm) {
+    build_kernel_t k = pick_kernel(elem, metric, list_j, flagged);
     if (!k) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block);
     if (e != cudaSuccess) return e;
@@ -489,7 +506,7 @@ cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem
 
 cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
                                 size_t smem_block, int threads, cudaStream_t stream) {
-    build_kernel_t k = pick_kernel(elem, metric, list_j);
+    build_kernel_t k = pick_kernel(elem, metric, list_j, g.flags != nullptr);
     if (!k) return cudaErrorInvalidValue;
     k<<<grid, threads, smem_block, stream>>>(g, p);
     return cudaGetLastError();

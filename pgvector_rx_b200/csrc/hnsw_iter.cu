@@ -4,9 +4,10 @@
 //
 // What persists per query between rounds lives in HBM:
 //   visited   -- a bitmap over element ids (scan.rs:601-604 keeps one HashSet per scan and never clears it);
-//   discarded -- the reference's unbounded min-heap (scan.rs:340-345, 385-405, 421-438) as an unordered
-//                chain of 64-key chunks drawn from a shared pool; only its contents as a multiset matter,
-//                because it is read solely by "pop the ef_search nearest" at the next resume (scan.rs:552-561);
+//   discarded -- the reference's unbounded min-heap (scan.rs:340-345, 385-405, 421-438) as unordered 64-key
+//                chunks (each with its minimum) in extents drawn from a shared pool; only its contents as a
+//                multiset matter, because it is read solely by "pop the ef_search nearest" at the next resume
+//                (scan.rs:552-561);
 //   tuples, previous_distance (scan.rs:801-806, 871).
 // The reference pushes an element to `discarded` when it is evicted from W and -- if it was never expanded --
 // once more when it is popped at the stop test or drained from C at the end (it stays in C after the
@@ -16,36 +17,59 @@
 
 namespace pgvrx {
 
-// ---- discarded: chunk chain ---------------------------------------------------------------------------
+// ---- discarded: chunks with a per-chunk minimum, allocated in extents ------------------------------------
+// A query's keys live in 64-key chunks; chunks are handed out in EXTENTS of 32 consecutive chunk ids from a shared
+// pool, and a query's extents form a chain.  Every chunk carries its fill count and the minimum of its keys, so
+// "pop the ef nearest" reads one 256-byte line of minima per extent (2048 keys) and opens only the chunks whose
+// minimum is below the running ef-th smallest key: O(n / 2048 + ef ln(n / ef)) warp steps instead of two passes over
+// all n keys -- `discarded` grows by ~n_dist keys per round and a filtered scan runs hundreds of rounds.
 struct DiscWriter {
-    uint64_t *pool;      // n_chunks x ITER_CHUNK keys
-    int *next;           // n_chunks: next chunk of the chain or -1
-    int *pool_next;      // bump allocator
-    int pool_cap;
-    int head, tail, fill, live;
+    uint64_t *pool;      // n_ext x ITER_EXT x ITER_CHUNK keys
+    uint64_t *cmin;      // n_ext x ITER_EXT: smallest key of the chunk (KEY_NONE when empty)
+    int *cfill;          // n_ext x ITER_EXT: keys in the chunk
+    int *next;           // n_ext: next extent of the chain or -1
+    int *pool_next;      // bump allocator (extents)
+    int pool_cap;        // extents
+    int head;            // first extent or -1
+    int tail;            // chunk that takes appends or -1
+    int fill, live;      // keys in the tail chunk, live keys in the chain
+    uint64_t tail_min;   // running minimum of the tail chunk (written back when the tail moves on / at the end of the round)
     uint32_t status;
 };
 
-__device__ __forceinline__ int disc_alloc(DiscWriter &d, int lane) {
-    int c = -1;
-    if (lane == 0) {
-        c = atomicAdd(d.pool_next, 1);
-        if (c >= d.pool_cap) c = -1; else d.next[c] = -1;
-    }
-    c = __shfl_sync(FULL, c, 0);
-    if (c < 0) d.status |= ST_POOL_OVERFLOW;
-    return c;
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mh = __reduce_min_sync(FULL, hi);
+    const uint32_t ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xFFFFFFFFu);
+    return ((uint64_t)mh << 32) | ml;
 }
 
-// chunk that follows `chunk` in the chain, linking a fresh (or previously linked, now unused) one if needed
-__device__ __forceinline__ int disc_next_chunk(DiscWriter &d, int chunk, int lane) {
-    int nx = 0;
-    if (lane == 0) nx = d.next[chunk];
-    nx = __shfl_sync(FULL, nx, 0);
-    if (nx >= 0) return nx;
-    nx = disc_alloc(d, lane);
-    if (nx >= 0 && lane == 0) d.next[chunk] = nx;
-    return nx;
+// a fresh extent: every chunk empty
+__device__ __forceinline__ int disc_alloc_ext(DiscWriter &d, int lane) {
+    int e = -1;
+    if (lane == 0) {
+        e = atomicAdd(d.pool_next, 1);
+        if (e >= d.pool_cap) e = -1; else d.next[e] = -1;
+    }
+    e = __shfl_sync(FULL, e, 0);
+    if (e < 0) { d.status |= ST_POOL_OVERFLOW; return -1; }
+    d.cmin[(size_t)e * ITER_EXT + lane] = KEY_NONE;
+    d.cfill[(size_t)e * ITER_EXT + lane] = 0;
+    return e;
+}
+
+// chunk that follows the tail chunk: the next one of its extent, or the first of a fresh extent linked behind it
+__device__ __forceinline__ int disc_next_chunk(DiscWriter &d, int lane) {
+    if ((d.tail + 1) % ITER_EXT != 0) return d.tail + 1;
+    const int e = disc_alloc_ext(d, lane);
+    if (e < 0) return -1;
+    if (lane == 0) d.next[d.tail / ITER_EXT] = e;
+    return e * ITER_EXT;
+}
+
+// the tail chunk's metadata -> memory (the chunk stays the tail)
+__device__ __forceinline__ void disc_flush_tail(const DiscWriter &d, int lane) {
+    if (d.tail >= 0 && lane == 0) { d.cmin[d.tail] = d.tail_min; d.cfill[d.tail] = d.fill; }
 }
 
 // warp-collective append of the keys of the lanes with pred set
@@ -55,23 +79,35 @@ __device__ __forceinline__ void disc_append(DiscWriter &d, bool pred, uint64_t k
     const int n = __popc(m);
     const int rank = __popc(m & ((1u << lane) - 1u));
     if (d.tail < 0) {
-        const int c = disc_alloc(d, lane);
-        if (c < 0) return;
-        d.head = d.tail = c;
+        const int e = disc_alloc_ext(d, lane);
+        if (e < 0) return;
+        d.head = e;
+        d.tail = e * ITER_EXT;
         d.fill = 0;
+        d.tail_min = KEY_NONE;
     }
+    const bool spill = d.fill + n > ITER_CHUNK;
     int nxt = -1;
-    if (d.fill + n > ITER_CHUNK) {
-        nxt = disc_next_chunk(d, d.tail, lane);
+    if (spill) {
+        nxt = disc_next_chunk(d, lane);
         if (nxt < 0) return;
     }
+    const int pos = d.fill + rank;
+    const bool first = pred && pos < ITER_CHUNK;
     if (pred) {
-        const int pos = d.fill + rank;
-        if (pos < ITER_CHUNK) d.pool[(size_t)d.tail * ITER_CHUNK + pos] = key;
+        if (first) d.pool[(size_t)d.tail * ITER_CHUNK + pos] = key;
         else d.pool[(size_t)nxt * ITER_CHUNK + (pos - ITER_CHUNK)] = key;
     }
-    if (d.fill + n > ITER_CHUNK) { d.tail = nxt; d.fill = d.fill + n - ITER_CHUNK; }
-    else d.fill += n;
+    const uint64_t m1 = warp_min_u64(first ? key : KEY_NONE);
+    if (m1 < d.tail_min) d.tail_min = m1;
+    if (spill) {
+        if (lane == 0) { d.cmin[d.tail] = d.tail_min; d.cfill[d.tail] = ITER_CHUNK; }     // the old tail is full
+        d.tail_min = warp_min_u64(pred && !first ? key : KEY_NONE);
+        d.tail = nxt;
+        d.fill = d.fill + n - ITER_CHUNK;
+    } else {
+        d.fill += n;
+    }
     d.live += n;
     __syncwarp();
 }
@@ -99,77 +135,91 @@ __device__ __forceinline__ void sel_insert(uint64_t *L, int &len, int k, uint64_
     len = newlen;
 }
 
-// discarded.pop() x ef_search (scan.rs:552-561): the `ef` smallest keys go to L[0, n_sel) ascending and are
-// removed from the chain, which is compacted in place.  Returns n_sel.
+// discarded.pop() x ef_search (scan.rs:552-561): the `ef` smallest keys go to L[0, n_sel) ascending and are removed
+// from their chunks (each compacted in place, minimum and fill count updated).  Returns n_sel.  Called at the start of
+// a round, before anything is appended: the tail chunk's metadata in memory is current.
 __device__ __forceinline__ int disc_pop_nearest(DiscWriter &d, uint64_t *L, int ef, int lane) {
     if (d.live == 0 || d.head < 0) return 0;
     int n_sel = 0;
-    // pass 1: select
-    for (int chunk = d.head; chunk >= 0;) {
-        const int limit = chunk == d.tail ? d.fill : ITER_CHUNK;
-        for (int base = 0; base < limit; base += 32) {
-            const int i = base + lane;
-            const uint64_t key = i < limit ? d.pool[(size_t)chunk * ITER_CHUNK + i] : KEY_NONE;
-            const uint64_t T = n_sel == ef ? L[ef - 1] : KEY_NONE;
-            uint32_t am = __ballot_sync(FULL, key < T);
-            while (am) {
-                const int r = __ffs(am) - 1;
-                am &= am - 1;
-                sel_insert(L, n_sel, ef, __shfl_sync(FULL, key, r), lane);
+    // pass 1: select.  A chunk is opened only when its minimum beats the current ef-th smallest key.
+    for (int ext = d.head; ext >= 0;) {
+        int nx = 0;
+        if (lane == 0) nx = d.next[ext];
+        const uint64_t mn = d.cmin[(size_t)ext * ITER_EXT + lane];
+        const int fl = d.cfill[(size_t)ext * ITER_EXT + lane];
+        nx = __shfl_sync(FULL, nx, 0);
+        uint32_t cm = __ballot_sync(FULL, mn < (n_sel == ef ? L[ef - 1] : KEY_NONE));
+        while (cm) {
+            const int r = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const uint64_t mnr = __shfl_sync(FULL, mn, r);
+            const int flr = __shfl_sync(FULL, fl, r);
+            if (!(mnr < (n_sel == ef ? L[ef - 1] : KEY_NONE))) continue;      // the threshold has tightened meanwhile
+            const uint64_t *ck = d.pool + ((size_t)ext * ITER_EXT + r) * ITER_CHUNK;
+            for (int base = 0; base < flr; base += 32) {
+                const int i = base + lane;
+                const uint64_t key = i < flr ? ck[i] : KEY_NONE;
+                uint32_t am = __ballot_sync(FULL, key < (n_sel == ef ? L[ef - 1] : KEY_NONE));
+                while (am) {
+                    const int rr = __ffs(am) - 1;
+                    am &= am - 1;
+                    sel_insert(L, n_sel, ef, __shfl_sync(FULL, key, rr), lane);
+                }
             }
         }
-        if (chunk == d.tail) break;
-        int nx = 0;
-        if (lane == 0) nx = d.next[chunk];
-        chunk = __shfl_sync(FULL, nx, 0);
+        ext = nx;
     }
     if (n_sel == 0) return 0;
-    // pass 2: remove the selected multiset (everything below T, and as many copies of T as were selected)
+    // pass 2: remove the selected multiset (everything below T, and as many copies of T as were selected) from the
+    // chunks that can hold any of it
     const uint64_t T = L[n_sel - 1];
     int eq_left = 0;
     for (int base = 0; base < n_sel; base += 32) {
         const int i = base + lane;
         eq_left += __popc(__ballot_sync(FULL, i < n_sel && L[i] == T));
     }
-    int wchunk = d.head, wfill = 0;
-    for (int chunk = d.head; chunk >= 0;) {
-        const int limit = chunk == d.tail ? d.fill : ITER_CHUNK;
+    int to_remove = n_sel;
+    for (int ext = d.head; ext >= 0 && to_remove > 0;) {
         int nx = 0;
-        if (lane == 0) nx = d.next[chunk];          // read before this chunk can be rewritten as the write cursor's successor
+        if (lane == 0) nx = d.next[ext];
+        const uint64_t mn = d.cmin[(size_t)ext * ITER_EXT + lane];
+        const int fl = d.cfill[(size_t)ext * ITER_EXT + lane];
         nx = __shfl_sync(FULL, nx, 0);
-        for (int base = 0; base < limit; base += 32) {
-            const int i = base + lane;
-            const bool valid = i < limit;
-            const uint64_t key = valid ? d.pool[(size_t)chunk * ITER_CHUNK + i] : KEY_NONE;
-            const uint32_t eqm = __ballot_sync(FULL, valid && key == T);
-            const int take = min(__popc(eqm), eq_left);
-            const bool eq_removed = valid && key == T && __popc(eqm & ((1u << lane) - 1u)) < take;
-            eq_left -= take;
-            const bool keep = valid && !(key < T) && !eq_removed;
-            const uint32_t km = __ballot_sync(FULL, keep);
-            const int n = __popc(km);
-            const int rank = __popc(km & ((1u << lane) - 1u));
-            __syncwarp();
-            int wnext = -1;
-            if (wfill + n > ITER_CHUNK) {
-                if (lane == 0) wnext = d.next[wchunk];   // already linked: the write cursor trails the read cursor
-                wnext = __shfl_sync(FULL, wnext, 0);
+        uint32_t cm = __ballot_sync(FULL, mn <= T);
+        while (cm && to_remove > 0) {
+            const int r = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int flr = __shfl_sync(FULL, fl, r);
+            const int chunk = ext * ITER_EXT + r;
+            uint64_t *ck = d.pool + (size_t)chunk * ITER_CHUNK;
+            int wfill = 0;
+            uint64_t newmin = KEY_NONE;
+            for (int base = 0; base < flr; base += 32) {
+                const int i = base + lane;
+                const bool valid = i < flr;
+                const uint64_t key = valid ? ck[i] : KEY_NONE;
+                const uint32_t eqm = __ballot_sync(FULL, valid && key == T);
+                const int take = min(__popc(eqm), eq_left);
+                const bool eq_removed = valid && key == T && __popc(eqm & ((1u << lane) - 1u)) < take;
+                eq_left -= take;
+                const bool keep = valid && !(key < T) && !eq_removed;
+                const uint32_t km = __ballot_sync(FULL, keep);
+                const int rank = __popc(km & ((1u << lane) - 1u));
+                __syncwarp();
+                if (keep) ck[wfill + rank] = key;              // compaction only moves keys towards the front
+                const uint64_t mk = warp_min_u64(keep ? key : KEY_NONE);
+                if (mk < newmin) newmin = mk;
+                wfill += __popc(km);
+                __syncwarp();
             }
-            if (keep) {
-                const int pos = wfill + rank;
-                if (pos < ITER_CHUNK) d.pool[(size_t)wchunk * ITER_CHUNK + pos] = key;
-                else d.pool[(size_t)wnext * ITER_CHUNK + (pos - ITER_CHUNK)] = key;
-            }
-            if (wfill + n > ITER_CHUNK) { wchunk = wnext; wfill = wfill + n - ITER_CHUNK; }
-            else wfill += n;
-            __syncwarp();
+            to_remove -= flr - wfill;
+            if (lane == 0) { d.cmin[chunk] = newmin; d.cfill[chunk] = wfill; }
+            if (chunk == d.tail) { d.fill = wfill; d.tail_min = newmin; }
         }
-        if (chunk == d.tail) break;
-        chunk = nx;
+        ext = nx;
     }
-    d.tail = wchunk;
-    d.fill = wfill;
     d.live -= n_sel;
+    __syncwarp();
     return n_sel;
 }
 
@@ -357,8 +407,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
             }
             __syncwarp();
             DiscWriter d;
-            d.pool = p.pool; d.next = p.next; d.pool_next = p.pool_next; d.pool_cap = p.pool_cap;
+            d.pool = p.pool; d.cmin = p.cmin; d.cfill = p.cfill; d.next = p.next; d.pool_next = p.pool_next; d.pool_cap = p.pool_cap;
             d.head = st.head; d.tail = st.tail; d.fill = st.fill; d.live = st.live; d.status = 0;
+            d.tail_min = st.tail >= 0 ? p.cmin[st.tail] : KEY_NONE;
             uint32_t *bitmap = p.bitmap + (size_t)qi * p.n_words;
             int n_res = 0;
             if (st.round == 0) {
@@ -454,6 +505,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
             }
             st.tuples += n_counted;                                              // scan.rs:871
             st.round += 1;
+            disc_flush_tail(d, lane);
             st.head = d.head; st.tail = d.tail; st.fill = d.fill; st.live = d.live;
             if (n_res == 0 || p.mode == 0 || d.live == 0) st.done = 1;            // nothing left to resume from
             __syncwarp();

@@ -147,7 +147,7 @@ size_t search_warp_smem(const SearchLaunch &L);
 cudaError_t scan_kernel_occupancy(int elem, int metric, int list_j, bool flagged, size_t smem_block, int threads, int *blocks_per_sm);
 cudaError_t launch_scan_kernel(int elem, int metric, int list_j, const GraphView &g, const SearchParams &p, int grid,
                                size_t smem_block, int threads, cudaStream_t stream);
-cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, size_t smem_block, int threads, int *blocks_per_sm);
+cudaError_t build_kernel_occupancy(int elem, int metric, int list_j, bool flagged, size_t smem_block, int threads, int *blocks_per_sm);
 cudaError_t launch_build_search(int elem, int metric, int list_j, const GraphView &g, const BuildParams &p, int grid,
                                 size_t smem_block, int threads, cudaStream_t stream);
 cudaError_t launch_pairwise(int elem, int metric, const GraphView &g, const PairParams &p, int max_rows, int grid, cudaStream_t stream);
@@ -218,7 +218,8 @@ cudaError_t launch_rerank(int elem, int metric, const RerankParams &p, int grid,
 
 
 // ---- K3: iterative scan (hnsw_iter.cu) ------------------------------------------------------------------
-constexpr int ITER_CHUNK = 64;            // keys per chunk of a query's discarded chain
+constexpr int ITER_CHUNK = 64;            // keys per chunk of a query's discarded set
+constexpr int ITER_EXT = 32;              // chunks per extent (consecutive chunk ids: one warp-wide load reads their minima)
 constexpr int ITER_UP_ENTRIES = 4096;     // per-warp hashed visited table for the ef = 1 descent
 constexpr int ITER_TAIL_CAP = 1024;       // retained boundary ties behind W (bit types)
 constexpr int ITER_TAIL_CAP_FLOAT = 256;  // float types
@@ -228,7 +229,7 @@ struct IterQueryState {
     long long tuples;          // scan.rs:871
     uint32_t prev_ord;         // ordered bits of previous_distance (scan.rs:801-806); 0 = -infinity
     int round;                 // rounds this query has run
-    int head, tail, fill, live;   // discarded chain: first / last chunk (-1: none), keys in the last chunk, live keys
+    int head, tail, fill, live;   // discarded: first extent / chunk taking appends (-1: none), keys in that chunk, live keys
     int done;
     int pad;
 };
@@ -243,10 +244,12 @@ struct IterParams {
     IterQueryState *state;
     uint32_t *bitmap;          // nq x n_words visited bits
     uint32_t n_words;
-    uint64_t *pool;            // discarded chunks
-    int *next;
-    int *pool_next;
-    int pool_cap;
+    uint64_t *pool;            // discarded keys: extents x ITER_EXT chunks x ITER_CHUNK
+    uint64_t *cmin;            // per chunk: smallest key
+    int *cfill;                // per chunk: keys held
+    int *next;                 // per extent: next extent of the owning query's chain
+    int *pool_next;            // extents handed out
+    int pool_cap;              // extents
     uint32_t *vis_up;          // per warp slot, ITER_UP_ENTRIES
     int32_t *out_ids;          // nq x ef
     float *out_dists;
@@ -287,6 +290,8 @@ struct TcParams {
     float *cand_bound;             // [n_splits][nq]: approximate distance every unkept row of the split is at least
     float *dbg_scores;             // nq x n_rows approximate distances (diagnostic) or NULL
     uint32_t *hint;                // nq: ordered bits of the smallest full candidate-set maximum seen so far per query
+    int tile_step;                 // a unit visits tiles nt0, nt0 + tile_step, ... (1 = all of them; > 1: the sample pre-pass)
+    int kp_eff;                    // keys a candidate set really holds (TC_KP, or fewer in the pre-pass)
 };
 
 size_t tc_smem_bytes(int kp);
@@ -297,8 +302,8 @@ cudaError_t launch_flat_tc(const void *map_qhi, const void *map_qlo, const void 
 cudaError_t launch_flat_tc2(const void *map_qhi, const void *map_qlo, const void *map_xhi, const void *map_xlo, const TcParams &p,
                             int grid, cudaStream_t stream);
 cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
-                              const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, int32_t *uncert_list,
-                              int *n_uncert, cudaStream_t stream);
+                              const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, const uint32_t *hint,
+                              int32_t *uncert_list, int *n_uncert, cudaStream_t stream);
 cudaError_t launch_tc_gather_queries(const uint8_t *q, uint32_t q_stride, const int32_t *list, int n, uint8_t *out, cudaStream_t stream);
 cudaError_t launch_tc_scatter_results(const int32_t *ids, const float *dists, int k, const int32_t *list, int n, int32_t *out_ids,
                                       float *out_dists, cudaStream_t stream);

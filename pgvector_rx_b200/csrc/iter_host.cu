@@ -27,14 +27,14 @@ struct pgvrx_scan {
     int R = 0, grid = 0, tail_cap = 0;
     uint32_t stage_stride = 0;
     size_t smem_block = 0;
-    DevBuf q, bitmap, state, pool, next, pool_next, ids, dists, counts, done, want, status, ctr, vis_up, work;
+    DevBuf q, bitmap, state, pool, cmin, cfill, next, pool_next, ids, dists, counts, done, want, status, ctr, vis_up, work;
     std::vector<uint8_t> h_done;
 };
 
 namespace {
 
 void scan_release(pgvrx_scan *s) {
-    DevBuf *b[] = {&s->q, &s->bitmap, &s->state, &s->pool, &s->next, &s->pool_next, &s->ids, &s->dists, &s->counts,
+    DevBuf *b[] = {&s->q, &s->bitmap, &s->state, &s->pool, &s->cmin, &s->cfill, &s->next, &s->pool_next, &s->ids, &s->dists, &s->counts,
                    &s->done, &s->want, &s->status, &s->ctr, &s->vis_up, &s->work};
     for (DevBuf *x : b) x->release();
 }
@@ -42,13 +42,17 @@ void scan_release(pgvrx_scan *s) {
 // make room for one more round of every active query (a round appends at most a few keys per distance evaluation)
 int ensure_pool(pgvrx_scan *s, int64_t active) {
     pgvrx_index *ix = s->ix;
-    const int64_t want = (int64_t)s->pool_used + active * s->reserve_chunks + 64;
-    if (want > (int64_t)0x7ffffff0) return pgvrx_fail(ix, PGVRX_ERR_NOMEM, "discarded pool would exceed 2^31 chunks");
+    // pool_used / pool_cap / reserve_chunks count EXTENTS (ITER_EXT chunks of ITER_CHUNK keys each)
+    const int64_t want = (int64_t)s->pool_used + active * s->reserve_chunks + 8;
+    if (want > (int64_t)0x7ffffff0 / ITER_EXT) return pgvrx_fail(ix, PGVRX_ERR_NOMEM, "discarded pool would exceed 2^31 chunks");
     if (want <= s->pool_cap) return PGVRX_OK;
     const int64_t cap = want + want / 4;
-    CU_TRY(ix, s->pool.ensure_keep((size_t)cap * ITER_CHUNK * 8, (size_t)s->pool_used * ITER_CHUNK * 8));
+    const size_t ext_keys = (size_t)ITER_EXT * ITER_CHUNK;
+    CU_TRY(ix, s->pool.ensure_keep((size_t)cap * ext_keys * 8, (size_t)s->pool_used * ext_keys * 8));
+    CU_TRY(ix, s->cmin.ensure_keep((size_t)cap * ITER_EXT * 8, (size_t)s->pool_used * ITER_EXT * 8));
+    CU_TRY(ix, s->cfill.ensure_keep((size_t)cap * ITER_EXT * 4, (size_t)s->pool_used * ITER_EXT * 4));
     CU_TRY(ix, s->next.ensure_keep((size_t)cap * 4, (size_t)s->pool_used * 4));
-    s->pool_cap = (int)std::min<int64_t>(cap, std::min<int64_t>((int64_t)(s->pool.cap / (ITER_CHUNK * 8)), (int64_t)(s->next.cap / 4)));
+    s->pool_cap = (int)cap;
     return PGVRX_OK;
 }
 
@@ -86,7 +90,11 @@ int pgvrx_scan_begin(pgvrx_index *ix, const void *queries, int64_t nq, int32_t e
     s->mode = iterative_mode;
     s->max_tuples = max_scan_tuples;
     s->n_words = (uint32_t)((std::max<int64_t>(ix->n, 1) + 31) / 32);
-    s->reserve_chunks = (int)(((int64_t)ef_search * 2 * ix->desc.m * 2 + 256 + ITER_CHUNK - 1) / ITER_CHUNK) + 2;
+    {
+        // a round appends at most a few keys per distance evaluation; + the partially used extent a query may start with
+        const int64_t chunks = ((int64_t)ef_search * 2 * ix->desc.m * 2 + 256 + ITER_CHUNK - 1) / ITER_CHUNK + 2;
+        s->reserve_chunks = (int)((chunks + ITER_EXT - 1) / ITER_EXT) + 1;
+    }
     s->active = nq;
     s->h_done.assign((size_t)nq, 0);
     // staging geometry: the same rule as the one-shot scan (capi.cu), result list always in shared memory
@@ -178,6 +186,8 @@ int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, f
     p.bitmap = (uint32_t *)s->bitmap.p;
     p.n_words = s->n_words;
     p.pool = (uint64_t *)s->pool.p;
+    p.cmin = (uint64_t *)s->cmin.p;
+    p.cfill = (int *)s->cfill.p;
     p.next = (int *)s->next.p;
     p.pool_next = (int *)s->pool_next.p;
     p.pool_cap = s->pool_cap;

@@ -124,16 +124,106 @@ def test_insert_duplicates_and_level_changes():
     ix.close()
 
 
-def test_insert_refused_on_flagged_index():
-    rows = make_rows("f32", 100, 8, 1)
-    ix = P.HnswIndex("vector_l2_ops", 8, m=4, ef_construction=16, capacity=200)
-    ix.build(rows, np.zeros(100, np.int32))
-    f = np.zeros(100, np.uint8)
-    f[3] = P.ELEM_DELETED | P.ELEM_NO_HEAPTIDS
-    ix.set_element_flags(f)
-    with pytest.raises(P.PgvrxError) as e:
-        ix.insert(rows[:5], np.zeros(5, np.int32))
-    assert e.value.code == P.ERR_STATE
+def _same_live_state(ix, o, what):
+    g, w = ix.export_graph(), o.export_graph()
+    assert g["n"] == w["n"] and g["entry"] == w["entry"], (what, g["n"], w["n"], g["entry"], w["entry"])
+    bad = np.nonzero((g["adj0"] != w["adj0"]).any(axis=1))[0]
+    assert len(bad) == 0, "%s: %d layer-0 lists differ, first %d:\n gpu %s\n orc %s" % (
+        what, len(bad), bad[0], g["adj0"][bad[0]], w["adj0"][bad[0]])
+    assert np.array_equal(g["adj_up"], w["adj_up"]) and np.array_equal(g["level"], w["level"]), what
+    assert np.array_equal(ix.element_flags(), o.element_flags()), what
+    assert np.array_equal(g["rows"].view(np.uint8), w["rows"].view(np.uint8)), what
+    for i in range(o.n):
+        t = o.heap_tids(i)
+        assert g["heap_tid_counts"][i] == len(t) and g["heap_tids"][i, :len(t)].astype(np.int64).tolist() == t.tolist(), (what, i)
+
+
+def _life_cycle(opclass, kind, n0, dim, m, efc, seed, kill_entry=False, dup_rows=0):
+    """CREATE INDEX -> VACUUM -> INSERT -> scan -> VACUUM -> INSERT -> scan, every step against the oracle: the normal
+    life of an index (aminsert on a relation that holds deleted elements: insert.rs:525-528, 569-623, 1036-1047)."""
+    elem, metric, _ = P.OPCLASSES[opclass]
+    n_new = n0 // 2
+    rows = make_rows(kind, n0 + 2 * n_new, dim, seed)
+    if dup_rows:
+        rows[n0:n0 + dup_rows] = rows[:dup_rows]                 # re-inserted values: some of their twins are dead by then
+    lv = D.hnsw_levels(len(rows), m, seed + 1)
+    o = O.Oracle(elem, metric, dim, m=m, ef_construction=efc, tie_mode=O.TIE_TOTAL_ORDER)
+    ix = P.HnswIndex(opclass, dim, m=m, ef_construction=efc, capacity=len(rows))
+    o.build(rows[:n0], lv[:n0])
+    ix.build(rows[:n0], lv[:n0], heap_tids=np.arange(n0, dtype=np.uint64))
+    rng = np.random.default_rng(seed)
+    q = make_rows(kind, 64, dim, seed + 2)
+    alive = np.arange(n0)
+    lo = n0
+    for cycle in range(2):
+        dead = rng.permutation(alive)[: len(alive) // 3]
+        if kill_entry and cycle == 0 and o.entry not in dead:
+            dead = np.append(dead, o.entry)
+        alive = np.setdiff1d(alive, dead)
+        assert o.bulk_delete(dead) == ix.vacuum(dead)["n_heap_tids_removed"]
+        _same_live_state(ix, o, "%s vacuum %d" % (opclass, cycle))
+        hi = lo + n_new
+        o.insert(rows[lo:hi], lv[lo:hi], base_tid=lo)
+        st = _insert_raw(ix, rows[lo:hi], lv[lo:hi], np.arange(lo, hi, dtype=np.uint64))
+        assert st["n_host_dist"] == 0
+        _same_live_state(ix, o, "%s insert after vacuum %d" % (opclass, cycle))
+        alive = np.concatenate([alive, np.arange(lo, hi)])       # (heap TID t <-> input row t; merged duplicates keep their TID)
+        assert_same_results(ix.search(q, k=10, ef_search=40), o.search_batch(q, ef_search=40, k=10), "scan, cycle %d" % cycle)
+        lo = hi
+    ix.close()
+
+
+def test_insert_into_vacuumed_index_l2():
+    _life_cycle("vector_l2_ops", "f32", 1500, 12, 6, 24, seed=71)
+
+
+def test_insert_into_vacuumed_index_entry_point_deleted_and_duplicates():
+    _life_cycle("vector_l2_ops", "f32", 900, 8, 4, 16, seed=73, kill_entry=True, dup_rows=120)
+
+
+def test_insert_into_vacuumed_index_bit_hamming():
+    _life_cycle("bit_hamming_ops", "bit", 1200, 64, 6, 24, seed=75)
+
+
+def test_insert_into_index_whose_every_element_was_vacuumed():
+    rows = make_rows("f32", 300, 8, 77)
+    lv = D.hnsw_levels(300, 4, 78)
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, 8, m=4, ef_construction=16, tie_mode=O.TIE_TOTAL_ORDER)
+    ix = P.HnswIndex("vector_l2_ops", 8, m=4, ef_construction=16, capacity=300)
+    o.build(rows[:100], lv[:100])
+    ix.build(rows[:100], lv[:100], heap_tids=np.arange(100, dtype=np.uint64))
+    dead = np.arange(100)
+    assert o.bulk_delete(dead) == ix.vacuum(dead)["n_heap_tids_removed"] == 100
+    o.insert(rows[100:], lv[100:], base_tid=100)
+    _insert_raw(ix, rows[100:], lv[100:], np.arange(100, 300, dtype=np.uint64))
+    _same_live_state(ix, o, "insert into an emptied index")
+    q = make_rows("f32", 16, 8, 79)
+    assert_same_results(ix.search(q, k=5, ef_search=20), o.search_batch(q, ef_search=20, k=5), "scan of the refilled index")
+    ix.close()
+
+
+def test_insert_into_loaded_index_that_carries_flags():
+    # flags that came from a relation's pages (pgvrx_pages_element_flags), not from a vacuum run here: deleted elements are
+    # still referenced by live lists, which is where get_update_index's slot reuse applies
+    n, dim, m, efc = 800, 10, 4, 16
+    rows = make_rows("f32", n + 300, dim, 81)
+    lv = D.hnsw_levels(n + 300, m, 82)
+    o = O.Oracle(O.ELEM_F32, O.L2SQ, dim, m=m, ef_construction=efc, tie_mode=O.TIE_TOTAL_ORDER)
+    o.build(rows[:n], lv[:n])
+    rng = np.random.default_rng(83)
+    pick = np.setdiff1d(rng.permutation(n)[: n // 4], [o.entry])
+    o.vacuum_mark(pick[: len(pick) // 2], O.VACUUM_MARK_DELETED)      # deleted in place: live lists still point at them
+    o.vacuum_mark(pick[len(pick) // 2:], O.VACUUM_REMOVE_HEAPTIDS)    # pass 1 of a vacuum only: no heap TID left, not deleted yet
+    g = o.export_graph()
+    ix = P.HnswIndex("vector_l2_ops", dim, m=m, ef_construction=efc, capacity=n + 300)
+    ix.load_graph(g["rows"], g["level"], g["adj0"], g["upper_base"], g["adj_up"], g["entry"])
+    ix.set_element_flags(o.element_flags())
+    o.insert(rows[n:], lv[n:], base_tid=n)
+    _insert_raw(ix, rows[n:], lv[n:], np.arange(n, n + 300, dtype=np.uint64))
+    gg, w = ix.export_graph(), o.export_graph()
+    assert np.array_equal(gg["adj0"], w["adj0"]) and np.array_equal(gg["adj_up"], w["adj_up"]) and gg["entry"] == w["entry"]
+    q = make_rows("f32", 32, dim, 84)
+    assert_same_results(ix.search(q, k=10, ef_search=40), o.search_batch(q, ef_search=40, k=10), "scan after inserts over flags")
     ix.close()
 
 
