@@ -233,7 +233,7 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     // 7.68 M (profiles/r2_notes.md).  PGVRX_SPEC_GATHER=0/1 pins the order.
     p.spec = (main_cfg.L.R >= 32 && main_cfg.L.chunk_bytes == 0) ? 1 : 0;
     if (getenv("PGVRX_NO_SPEC_GATHER")) p.spec = 0;
-    if (const char *e = getenv("PGVRX_SPEC_GATHER")) p.spec = atoi(e) != 0;
+    if (const char *e = getenv("PGVRX_SPEC_GATHER")) { const int v = atoi(e); p.spec = v == 2 ? 2 : (v != 0); }   // 2: round 0 speculative, later rounds probe-first
     CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, main_cfg.wpb * 32, stream));
 
     // queries that overflowed their visited table or tie tail run again with 16x the scratch

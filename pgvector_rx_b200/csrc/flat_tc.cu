@@ -143,7 +143,7 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
     const int q = q_tile0 + r;
     const bool qvalid = q < p.nq;
     const float qn = qvalid ? p.qnorm[q] : 0.0f;
-    uint64_t tau = ~0ull;                                            // this lane's query: max of its set (all-ones = not full)
+    uint32_t tau_hi = 0xFFFFFFFFu;                                   // this lane's query: distance bits of its set's maximum (all-ones = not full)
     float tau_f = __int_as_float(0x7f800000);                        // the same threshold as a distance
     // Thresholds travel between the units of a query: hint[q] is the smallest full-set maximum any unit has
     // reached so far.  Rejecting against it is sound because certification uses the minimum over all units'
@@ -189,7 +189,7 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
             for (int j = 0; j < 32; j++) {
                 const float s = __uint_as_float(v[j]);
                 const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TN + c + j]) : -s;
-                mask |= (dist <= thr_f ? 1u : 0u) << j;             // superset of key < tau (ties resolved below)
+                mask |= (dist <= thr_f ? 1u : 0u) << j;             // superset of "nearer than the set's maximum" (decided below)
             }
             const int nvalid = valid_cols - c;
             if (!qvalid || nvalid <= 0) mask = 0;
@@ -207,30 +207,35 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
                     const float s = __uint_as_float(sv);
                     const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TN + c + j]) : -s;
                     const uint32_t khi = f32_ord(dist), klo = (uint32_t)(row0 + c + j);
-                    const uint64_t key = ((uint64_t)khi << 32) | klo;
-                    uint32_t am = __ballot_sync(FULL, ((mask >> j) & 1u) && key < tau);
+                    // Sets are ordered by the distance bits alone (an element that ties with the set's maximum is not
+                    // taken: it is >= the bound either way), which halves the REDUX chain of an insertion; and two
+                    // queries' insertions run interleaved -- their sets are independent -- so that the chains overlap.
+                    uint32_t am = __ballot_sync(FULL, ((mask >> j) & 1u) && khi < tau_hi);
                     while (am) {
-                        const int src = __ffs(am) - 1;
+                        const int s0 = __ffs(am) - 1;
                         am &= am - 1;
-                        const uint32_t nhi = __shfl_sync(FULL, khi, src), nlo = __shfl_sync(FULL, klo, src);
-                        const uint64_t cur = Lw[src * TC_KP + lane];
-                        uint32_t chi = (uint32_t)(cur >> 32), clo = (uint32_t)cur;
+                        const bool two = am != 0;
+                        const int s1 = two ? __ffs(am) - 1 : s0;
+                        if (two) am &= am - 1;
+                        const uint32_t nhi0 = __shfl_sync(FULL, khi, s0), nlo0 = __shfl_sync(FULL, klo, s0);
+                        const uint32_t nhi1 = __shfl_sync(FULL, khi, s1), nlo1 = __shfl_sync(FULL, klo, s1);
+                        uint32_t chi0 = (uint32_t)(Lw[s0 * TC_KP + lane] >> 32);
+                        uint32_t chi1 = (uint32_t)(Lw[s1 * TC_KP + lane] >> 32);
                         // the set's maximum is replaced by the new key
-                        uint32_t mhi = __reduce_max_sync(FULL, chi);
-                        uint32_t mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
-                        const int owner = __ffs(__ballot_sync(FULL, chi == mhi && clo == mlo)) - 1;
-                        if (lane == owner) {
-                            chi = nhi; clo = nlo;
-                            Lw[src * TC_KP + lane] = ((uint64_t)nhi << 32) | nlo;
-                        }
-                        mhi = __reduce_max_sync(FULL, chi);
-                        mlo = __reduce_max_sync(FULL, chi == mhi ? clo : 0u);
-                        if (lane == src) {
-                            tau = ((uint64_t)mhi << 32) | mlo;
-                            if (tau != ~0ull) {
-                                tau_f = ord_f32(mhi);
+                        const uint32_t m0 = __reduce_max_sync(FULL, chi0);
+                        const uint32_t m1 = __reduce_max_sync(FULL, chi1);
+                        const int o0 = __ffs(__ballot_sync(FULL, chi0 == m0)) - 1;
+                        const int o1 = __ffs(__ballot_sync(FULL, chi1 == m1)) - 1;
+                        if (lane == o0) { chi0 = nhi0; Lw[s0 * TC_KP + lane] = ((uint64_t)nhi0 << 32) | nlo0; }
+                        if (two && lane == o1) { chi1 = nhi1; Lw[s1 * TC_KP + lane] = ((uint64_t)nhi1 << 32) | nlo1; }
+                        const uint32_t t0 = __reduce_max_sync(FULL, chi0);
+                        const uint32_t t1 = __reduce_max_sync(FULL, chi1);
+                        if (lane == s0 || (two && lane == s1)) {
+                            tau_hi = lane == s0 ? t0 : t1;
+                            if (tau_hi != 0xFFFFFFFFu) {                      // the set is full: its maximum is a threshold
+                                tau_f = ord_f32(tau_hi);
                                 thr_f = fminf(thr_f, tau_f);
-                                atomicMin(p.hint + q, mhi);
+                                atomicMin(p.hint + q, tau_hi);
                             }
                         }
                         __syncwarp();
@@ -260,7 +265,7 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
         }
     }
     // every row of this split that was not kept has an approximate distance >= this bound
-    if (qvalid && p.cand_bound) p.cand_bound[(size_t)sp * p.nq + q] = tau == ~0ull ? __int_as_float(0x7f800000) : ord_f32((uint32_t)(tau >> 32));
+    if (qvalid && p.cand_bound) p.cand_bound[(size_t)sp * p.nq + q] = tau_hi == 0xFFFFFFFFu ? __int_as_float(0x7f800000) : ord_f32(tau_hi);
     __syncwarp();
 }
 

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
         c.rs_log = p.rs_log + (size_t)w * p.rs_cap * p.rs_ent;
         c.rs_ent = p.rs_ent;
         c.spec = true;                 // the log needs the distance of every entry of every list read
+        c.hybrid = false;
         c.rs_cap = p.rs_cap;
         c.rs_n = 0;
         for (int l = lane; l < p.max_layers; l += 32) p.w_counts[(size_t)w * p.max_layers + l] = -1;
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_repair_search_kernel(Grap
         c.rs_log = p.rs_log + (size_t)w * p.rs_cap * p.rs_ent;
         c.rs_ent = p.rs_ent;
         c.spec = true;
+        c.hybrid = false;
         c.rs_cap = p.rs_cap;
         c.rs_n = 0;
         c.self_id = e;

@@ -278,6 +278,7 @@ struct WarpCtx {
     int rs_cap, rs_n;      // capacity / count (rs_n may exceed rs_cap: the host then treats the set as unknown)
     int rs_ent;            // ints per log entry: 3 + one word per 32 list slots
     bool spec;             // fetch every neighbour's row while the visited probes are in flight (see search_layer)
+    bool hybrid;           // whole-row staging in several rounds: round 0 speculative (issued before the probes resolve), the rest probe-first
     int32_t self_id;       // vacuum repair search only: the element being repaired (member of the skip set)
     int excess;            // vacuum repair search only: counted entry points seeded beyond ef (w_len - ef, scan.rs:326-336)
     int lane;
@@ -643,7 +644,15 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             // (PGVRX_NO_SPEC_GATHER): resolve the probes, then fetch only the rows that are evaluated -- 17 % less
             // L2 -> SM traffic, but measured 1 % slower at C2 (the kernel is latency bound, not fabric bound).
             float d = 0.0f;
-            if (c.spec) {
+            int nrow0 = 0;
+            if (c.hybrid) {
+                // (2h) the first round's rows are requested NOW, before the probes are consumed: the two round trips overlap
+                nrow0 = min(c.R, cnt);
+                if (lane == 0) mbar_arrive_expect_tx(c.mbar, (uint32_t)nrow0 * g.row_stride);
+                __syncwarp();
+                if (lane < nrow0)
+                    tma_row_g2s(c.stage + (size_t)lane * c.stage_stride, g.vectors + (size_t)nb * g.row_stride, g.row_stride, c.mbar, c.policy);
+            } else if (c.spec) {
                 // (2) gather + one distance per lane (lane r <-> neighbour r of this chunk)
                 d = eval_neighbours<ELEM, METRIC>(c, g, cnt, valid, false);
                 // build log: which entries of this list are nearer than W's furthest distance was when the expansion
@@ -667,12 +676,33 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             const uint32_t fm = __ballot_sync(FULL, fresh);
             vis_count += __popc(fm);
             c.n_vis += __popc(fm);
-            if (vis_count > vis_limit) { c.status |= ST_VIS_OVERFLOW; return; }
+            if (vis_count > vis_limit) {
+                if (c.hybrid) { mbar_wait(c.mbar, c.phase); c.phase ^= 1u; }      // round 0's rows are still landing
+                c.status |= ST_VIS_OVERFLOW;
+                return;
+            }
             // graph/mod.rs:214, scan.rs:410; a deleted element fails load_element before its distance (scan.rs:179)
             const bool pass = fresh && lvl >= layer && !(eflags & ELEM_FLAG_DELETED);
             c.n_dist += __popc(__ballot_sync(FULL, pass));
             PH_TICK(c, 1);
-            if (!c.spec) {
+            if (c.hybrid) {
+                // (2h') round 0 has been in flight since before the probes; later rounds fetch only what is evaluated
+                mbar_wait(c.mbar, c.phase);
+                c.phase ^= 1u;
+                PH_TICK(c, 2);
+                if (pass && lane < nrow0) d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)lane * c.stage_stride, c.nvec);
+                __syncwarp();
+                PH_TICK(c, 3);
+                for (int s = nrow0; s < cnt; s += c.R) {
+                    const int nrow = min(c.R, cnt - s);
+                    gather_rows_masked(c, g, s, nrow, pass);
+                    PH_TICK(c, 2);
+                    if (pass && lane >= s && lane < s + nrow)
+                        d = row_distance<ELEM, METRIC>(c.qsm, c.stage + (size_t)(lane - s) * c.stage_stride, c.nvec);
+                    __syncwarp();
+                    PH_TICK(c, 3);
+                }
+            } else if (!c.spec) {
                 // (2') only the rows that are evaluated
                 d = eval_neighbours<ELEM, METRIC>(c, g, cnt, pass, true);
             }

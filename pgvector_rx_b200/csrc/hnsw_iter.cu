@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
     c.rs_cap = c.rs_n = 0;
     c.rs_ent = 3;
     c.spec = true;
+    c.hybrid = false;
     const int slot = blockIdx.x * (blockDim.x / 32) + warp;
     c.vis = p.vis_up + (size_t)slot * ITER_UP_ENTRIES;
     if (lane == 0) { mbar_init(c.mbar, 1); fence_mbar_init(); }

@@ -47,7 +47,7 @@ struct SearchParams {
     int R;                     // staged rows per warp (<= 32)
     uint32_t stage_bytes;      // staging area per warp
     uint32_t chunk_bytes, chunk_stride;   // wide rows: staged in chunks of chunk_bytes for 32 rows at once (0 = whole rows)
-    int spec;                  // 1: gather every neighbour's row before the visited probes resolve (see search_layer)
+    int spec;                  // 1: gather every neighbour's row before the visited probes resolve (see search_layer); 2: only the first round's
 };
 
 // K2: build-side search of a batch of pending inserts (hnsw_build.cu)

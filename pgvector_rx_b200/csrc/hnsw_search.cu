@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     c.rs_log = nullptr;
     c.rs_cap = c.rs_n = 0;
     c.rs_ent = 3;
-    c.spec = p.spec != 0;
+    c.spec = p.spec == 1;
+    c.hybrid = p.spec == 2 && p.chunk_bytes == 0 && p.R < 32;   // (one round holds every list: plain speculative order)
+    if (p.spec == 2 && !c.hybrid) c.spec = true;
     const int slot = blockIdx.x * (blockDim.x / 32) + warp;
     c.vis = p.vis_base + (size_t)slot * p.vis_entries;
 

@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(TEAM_MAX_WARPS * 32) hnsw_team_build_kernel(Gr
     c.policy = l2_policy_evict_first();
     c.vis = nullptr;
     c.spec = true;
+    c.hybrid = false;
     if (lane == 0) {
         mbar_init(c.mbar, 1);
         fence_mbar_init();

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(32) hnsw_layer_search_kernel(GraphView g, Laye
     c.phase = 0;
     c.policy = l2_policy_evict_first();
     c.spec = true;
+    c.hybrid = false;
     c.vis = p.vis_base + (size_t)blockIdx.x * p.vis_entries;
     if (lane == 0) { mbar_init(c.mbar, 1); fence_mbar_init(); }
     __syncwarp();

@@ -153,3 +153,15 @@ def test_concurrent_streams_and_page_locked_buffers():
                                  C.c_void_p(pc.data_ptr()), None)
     assert rc == 0 and np.array_equal(pi.numpy(), want[0][0])
     ix.close()
+
+
+@pytest.mark.parametrize("order", ["0", "1", "2"])
+def test_gather_orders_give_identical_results(order, monkeypatch):
+    # the scan may fetch a list's rows before the visited probes resolve (1), after (0), or the first staging round before
+    # and the rest after (2): three schedules of the same arithmetic -- ids, distance bits and work counters cannot differ.
+    # 128-d fp32 rows with m = 16 take two staging rounds per layer-0 list, so all three paths are really exercised.
+    monkeypatch.setenv("PGVRX_SPEC_GATHER", order)
+    run_case("vector_l2_ops", "f32", 6000, 128, 400, efs=(40, 150))
+    run_case("bit_hamming_ops", "bit", 3000, 1024, 200, efs=(40,), allow_retry=True)
+    monkeypatch.setenv("PGVRX_STAGE_ROWS", "11")                  # three rounds, the last one short
+    run_case("vector_ip_ops", "f32", 3000, 96, 200, efs=(40,))

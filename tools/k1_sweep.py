@@ -42,7 +42,8 @@ def main():
             [dict(PGVRX_STAGE_ROWS="16", PGVRX_NO_SPEC_GATHER="1"), dict(PGVRX_STAGE_ROWS="11", PGVRX_NO_SPEC_GATHER="1"),
              dict(PGVRX_STAGE_ROWS="16", PGVRX_SCAN_WARPS="2"), dict(PGVRX_STAGE_ROWS="11", PGVRX_SCAN_WARPS="2"), dict()]
     if x.quick:
-        knobs = [dict(), dict(PGVRX_STAGE_ROWS="16"), dict(PGVRX_CHUNK_BYTES="256")]
+        knobs = [dict(), dict(PGVRX_SPEC_GATHER="2"), dict(PGVRX_SPEC_GATHER="0"), dict(PGVRX_SPEC_GATHER="1"), dict(PGVRX_SPEC_GATHER="2"), dict(),
+                 dict(PGVRX_CHUNK_BYTES="256"), dict(PGVRX_CHUNK_BYTES="256", PGVRX_SPEC_GATHER="0")]
     for kn in knobs:
         for k_, v in kn.items():
             os.environ[k_] = v
