@@ -446,6 +446,13 @@ int pgvrx_scan_begin(pgvrx_index *idx, const void *queries, int64_t nq, int32_t 
  * PGVRX_ITER_OFF emits get_scan_items' batch and is then done.  HOST buffers. */
 int pgvrx_scan_next(pgvrx_scan *scan, const uint8_t *want_more, int32_t *out_ids, float *out_dists,
                     int32_t *out_counts, uint8_t *out_done, pgvrx_search_stats *stats /* may be NULL */);
+/* `rounds` refills in one call (one kernel launch, one copy back): amgettuple asks for the next batch only once the
+ * previous one is used up (scan.rs:817), so several batches handed out together are the same stream -- a consumer
+ * that stops early has merely had the later ones computed for nothing.  Worth it under a selective filter (WHERE i % 500
+ * = 0 needs ~125 refills for 10 rows at ef_search = 40).  out_ids / out_dists: nq * rounds * ef_search, batch r of query q
+ * at (q * rounds + r) * ef_search; out_counts: nq * rounds; out_done: nq.  pgvrx_scan_next is rounds = 1. */
+int pgvrx_scan_next_rounds(pgvrx_scan *scan, const uint8_t *want_more, int32_t rounds, int32_t *out_ids, float *out_dists,
+                           int32_t *out_counts, uint8_t *out_done, pgvrx_search_stats *stats /* may be NULL */);
 void pgvrx_scan_end(pgvrx_scan *scan);
 
 #ifdef __cplusplus

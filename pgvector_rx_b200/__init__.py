@@ -41,7 +41,7 @@ EXPORTS = [
     "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export", "pgvrx_index_build",
     "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
     "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
-    "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
+    "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_next_rounds", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
     "pgvrx_pages_element_flags", "pgvrx_heap_tid_stream", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
     "pgvrx_index_set_heap_tids", "pgvrx_pages_write", "pgvrx_index_vacuum", "pgvrx_index_element_flags",
     "pgvrx_gather_probe", "pgvrx_group_create", "pgvrx_group_destroy", "pgvrx_group_last_error", "pgvrx_group_size",
@@ -174,6 +174,7 @@ def lib():
         "pgvrx_flat_tc_scores": (C.c_int, [vp, vp, i64, vp, vp]),
         "pgvrx_scan_begin": (C.c_int, [vp, vp, i64, i32, i32, i64, C.POINTER(vp)]),
         "pgvrx_scan_next": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(SearchStats)]),
+        "pgvrx_scan_next_rounds": (C.c_int, [vp, vp, i32, vp, vp, vp, vp, C.POINTER(SearchStats)]),
         "pgvrx_scan_end": (None, [vp]),
         "pgvrx_gather_probe": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, C.POINTER(GatherProbeResult)]),
         "pgvrx_group_create": (C.c_int, [C.POINTER(IndexDesc), vp, i32, C.POINTER(vp)]),
@@ -650,17 +651,22 @@ class IterativeScan:
         self.h = h
         self.totals = dict(n_dist=0, n_expand0=0, n_expand_upper=0, n_visited=0, kernel_ms=0.0, rounds=0)
 
-    def next(self, want_more=None):
-        ids = np.empty((self.nq, self.ef), np.int32)
-        dists = np.empty((self.nq, self.ef), np.float32)
-        counts = np.empty(self.nq, np.int32)
+    def next(self, want_more=None, rounds=None):
+        """One refill per query (rounds=None: arrays [nq, ef] / [nq]) or `rounds` refills in one launch
+        (arrays [nq, rounds, ef] / [nq, rounds]: batch r of a query follows batch r - 1 in its stream)."""
+        r = 1 if rounds is None else int(rounds)
+        ids = np.empty((self.nq, r, self.ef), np.int32)
+        dists = np.empty((self.nq, r, self.ef), np.float32)
+        counts = np.empty((self.nq, r), np.int32)
         done = np.empty(self.nq, np.uint8)
         wm = None if want_more is None else np.ascontiguousarray(want_more, np.uint8)
         st = SearchStats()
-        self.ix._check(self.ix.L.pgvrx_scan_next(self.h, _p(wm), _p(ids), _p(dists), _p(counts), _p(done), C.byref(st)))
+        self.ix._check(self.ix.L.pgvrx_scan_next_rounds(self.h, _p(wm), r, _p(ids), _p(dists), _p(counts), _p(done), C.byref(st)))
         for k in ("n_dist", "n_expand0", "n_expand_upper", "n_visited", "kernel_ms"):
             self.totals[k] += getattr(st, k)
-        self.totals["rounds"] += 1
+        self.totals["rounds"] += r
+        if rounds is None:
+            return ids[:, 0], dists[:, 0], counts[:, 0], done.astype(bool)
         return ids, dists, counts, done.astype(bool)
 
     def stream(self, limit):

@@ -230,8 +230,11 @@ int search_core(pgvrx_index *ix, const void *d_queries, uint32_t q_stride, int64
     // Speculative order (fetch every neighbour's row while the visited probes are in flight) when a list's rows go in
     // one round; probe-first (fetch only the rows that will be evaluated: 17 % less L2 -> SM traffic) when they take
     // two or more -- measured on C2: 32 rows/round 7.17 M QPS speculative vs 6.86 M probe-first, 16 rows/round 7.49 M vs
-    // 7.68 M (profiles/r2_notes.md).  PGVRX_SPEC_GATHER=0/1 pins the order.
-    p.spec = (main_cfg.L.R >= 32 && main_cfg.L.chunk_bytes == 0) ? 1 : 0;
+    // 7.68 M (profiles/r2_notes.md).  In between (2, the default for several rounds of whole rows): the FIRST round's rows
+    // are requested before the probes are consumed, so the probe's L2 round trip -- the top stall of the probe-first
+    // order, 10 % of the samples -- overlaps that gather, and the later rounds fetch only what is evaluated (+0.4 .. 3.6 %
+    // over probe-first in back-to-back runs).  PGVRX_SPEC_GATHER=0/1/2 pins the order.
+    p.spec = main_cfg.L.chunk_bytes != 0 ? 0 : (main_cfg.L.R >= 32 ? 1 : 2);
     if (getenv("PGVRX_NO_SPEC_GATHER")) p.spec = 0;
     if (const char *e = getenv("PGVRX_SPEC_GATHER")) { const int v = atoi(e); p.spec = v == 2 ? 2 : (v != 0); }   // 2: round 0 speculative, later rounds probe-first
     CU_TRY(ix, launch_scan_kernel(ix->desc.elem_type, ix->desc.metric, main_cfg.L.list_j, g, p, main_cfg.grid, main_cfg.smem_block, main_cfg.wpb * 32, stream));

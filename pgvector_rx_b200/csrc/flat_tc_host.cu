@@ -84,7 +84,7 @@ int prepare_table(pgvrx_index *ix, cudaStream_t stream) {
 struct TcPlan { int n_mtiles, n_ntiles, n_splits, tiles_per_split, grid; };
 
 // tile_m x tile_n = 128 x 128 per CTA, or 256 x 256 per CTA pair (`workers` = CTAs or pairs)
-TcPlan plan_tc(int workers, int64_t nq_pad, int64_t n_pad, int tile_m, int tile_n) {
+TcPlan plan_tc(int workers, int64_t nq_pad, int64_t n_pad, int tile_m, int tile_n, int split_penalty = 10) {
     const int sm_count = workers;
     TcPlan pl;
     pl.n_mtiles = (int)(nq_pad / tile_m);
@@ -99,7 +99,7 @@ TcPlan plan_tc(int workers, int64_t nq_pad, int64_t n_pad, int tile_m, int tile_
         const int s_eff = (pl.n_ntiles + tps - 1) / tps;
         const long units = (long)pl.n_mtiles * s_eff;
         const long waves = (units + sm_count - 1) / sm_count;
-        const long cost = waves * tps + 10L * s_eff;      // each split adds KP candidates per query to the re-rank
+        const long cost = waves * tps + (long)split_penalty * s_eff;   // each split adds up to KP candidates per query to the re-rank
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; pl.n_splits = s_eff; pl.tiles_per_split = tps; }
     }
     pl.grid = (int)std::min<long>((long)pl.n_mtiles * pl.n_splits, sm_count);
@@ -143,7 +143,11 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     rc = make_map(ix, map_qlo, ix->tc_qlo.p, nq_pad, d_pad);
     if (rc) return rc;
 
-    const TcPlan pl = plan_tc(two_cta ? ix->sm_count / 2 : ix->sm_count, nq_pad, ix->tc_n_pad, tile_m, tile_n);
+    TcPlan pl = plan_tc(two_cta ? ix->sm_count / 2 : ix->sm_count, nq_pad, ix->tc_n_pad, tile_m, tile_n);
+    // short units get a threshold from the sample pre-pass (below): what a query inserts is then the rows under that
+    // threshold, however the table is split, so splits cost little and the plan may balance the waves more finely
+    const bool want_prepass = d_ids && pl.tiles_per_split <= 256 && pl.n_ntiles >= 64 && !getenv("PGVRX_TC_NO_PREPASS");
+    if (want_prepass) pl = plan_tc(two_cta ? ix->sm_count / 2 : ix->sm_count, nq_pad, ix->tc_n_pad, tile_m, tile_n, 3);
     const int nc = pl.n_splits * TC_KP;
     CU_TRY(ix, ix->tc_cand.ensure((size_t)nq * nc * 4));
     CU_TRY(ix, ix->tc_bound.ensure((size_t)pl.n_splits * nq * 4));
@@ -179,12 +183,15 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     // table -- every step-th tile, one unit per query tile, sets of kp_eff keys -- which leaves in p.hint the kp_eff-th
     // smallest approximate distance of the sample: about kp_eff * step rows of the table lie below it, several times k.
     // The main pass then starts from that threshold everywhere.  The certificate takes the final hint into account.
-    const bool prepass = d_ids && pl.tiles_per_split <= 256 && pl.n_ntiles >= 64 && !getenv("PGVRX_TC_NO_PREPASS");
+    const bool prepass = want_prepass;
     if (prepass) {
         TcParams pa = p;
-        const int want_tiles = std::max(4, std::min(64, pl.n_ntiles / 16));
+        // a 1/24 sample and the (k / 2 + 3)-th smallest of it: ~ 24 (k / 2 + 3) rows of the table below the threshold
+        // (190 for k = 10), an order of magnitude more than the k the certificate needs, a fraction of what unguided
+        // candidate sets would insert
+        const int want_tiles = std::max(4, std::min(48, pl.n_ntiles / 24));
         pa.tile_step = std::max(1, pl.n_ntiles / want_tiles);
-        pa.kp_eff = std::max(8, std::min((int)TC_KP, k + 6));
+        pa.kp_eff = std::max(8, std::min((int)TC_KP, k / 2 + 3));
         pa.n_splits = 1;
         pa.ntiles_per_split = pl.n_ntiles;
         pa.cand_ids = nullptr;

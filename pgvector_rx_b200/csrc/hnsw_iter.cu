@@ -399,12 +399,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
         IterQueryState st = p.state[qi];
         c.n_dist = c.n_exp0 = c.n_expu = c.n_vis = 0;
         c.status = 0;
-        int emitted = 0;
         const bool wanted = p.want_more == nullptr || p.want_more[qi] != 0;
-        if (wanted && !st.done) {
-            {
+        bool q_loaded = false;
+        // p.rounds refills of so.results (scan.rs:817-856) in one launch: amgettuple asks for the next batch only when
+        // the previous one is used up, so handing out several batches at once gives the same stream -- a consumer that
+        // stops early has merely had the later ones computed for nothing
+        for (int rr = 0; rr < p.rounds; rr++) {
+        int emitted = 0;
+        int32_t *o_ids = p.out_ids + ((size_t)qi * p.rounds + rr) * p.ef;
+        float *o_dists = p.out_dists + ((size_t)qi * p.rounds + rr) * p.ef;
+        if (wanted && !st.done && c.status == 0) {
+            if (!q_loaded) {
                 const uint8_t *q = p.queries + (size_t)qi * p.q_stride;
                 for (uint32_t i = lane; i < g.row_stride; i += 32) c.qsm[i] = i < p.q_bytes ? __ldg(q + i) : (uint8_t)0;
+                q_loaded = true;
             }
             __syncwarp();
             DiscWriter d;
@@ -475,8 +483,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
                 emitted = n_res - skip;
                 for (int i = lane; i < emitted; i += 32) {
                     const uint64_t key = S.S[skip + i];
-                    p.out_ids[(size_t)qi * p.ef + i] = (int32_t)key_id(key);
-                    p.out_dists[(size_t)qi * p.ef + i] = ord_f32(key_ord(key));
+                    o_ids[i] = (int32_t)key_id(key);
+                    o_dists[i] = ord_f32(key_ord(key));
                 }
                 if (emitted > 0) st.prev_ord = key_ord(S.S[n_res - 1]);
             } else {
@@ -496,8 +504,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
                     const uint32_t om = __ballot_sync(FULL, out);
                     if (out) {
                         const int pos = emitted + __popc(om & ((1u << lane) - 1u));
-                        p.out_ids[(size_t)qi * p.ef + pos] = (int32_t)key_id(key);
-                        p.out_dists[(size_t)qi * p.ef + pos] = ord_f32(key_ord(key));
+                        o_ids[pos] = (int32_t)key_id(key);
+                        o_dists[pos] = ord_f32(key_ord(key));
                     }
                     if (om) last_ord = __shfl_sync(FULL, key_ord(key), 31 - __clz(om));   // ascending: the last one out is the largest
                     emitted += __popc(om);
@@ -512,12 +520,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
             __syncwarp();
         }
         for (int i = emitted + lane; i < p.ef; i += 32) {
-            p.out_ids[(size_t)qi * p.ef + i] = -1;
-            p.out_dists[(size_t)qi * p.ef + i] = __int_as_float(0x7f800000);
+            o_ids[i] = -1;
+            o_dists[i] = __int_as_float(0x7f800000);
         }
+        if (lane == 0) p.out_counts[(size_t)qi * p.rounds + rr] = emitted;
+        __syncwarp();
+        }   // rounds
         if (lane == 0) {
             p.state[qi] = st;
-            p.out_counts[qi] = emitted;
             p.out_done[qi] = (uint8_t)st.done;
             p.out_status[qi] = c.status;
             if (p.out_ctr) reinterpret_cast<uint4 *>(p.out_ctr)[qi] = make_uint4(c.n_dist, c.n_exp0, c.n_expu, c.n_vis);

@@ -239,6 +239,7 @@ struct IterParams {
     uint32_t q_stride, q_bytes;
     int nq, ef, tail_cap;
     int mode;                  // pgvrx_iterative
+    int rounds;                // refills per launch (>= 1); outputs are nq x rounds x ef / nq x rounds
     long long max_scan_tuples;
     const uint8_t *want_more;  // nq or NULL
     IterQueryState *state;

@@ -153,9 +153,15 @@ int pgvrx_scan_begin(pgvrx_index *ix, const void *queries, int64_t nq, int32_t e
 
 int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, float *out_dists, int32_t *out_counts,
                     uint8_t *out_done, pgvrx_search_stats *stats) {
+    return pgvrx_scan_next_rounds(s, want_more, 1, out_ids, out_dists, out_counts, out_done, stats);
+}
+
+int pgvrx_scan_next_rounds(pgvrx_scan *s, const uint8_t *want_more, int32_t rounds, int32_t *out_ids, float *out_dists,
+                           int32_t *out_counts, uint8_t *out_done, pgvrx_search_stats *stats) {
     if (!s) return PGVRX_ERR_INVALID;
     pgvrx_index *ix = s->ix;
     if (stats) memset(stats, 0, sizeof *stats);
+    if (rounds < 1 || rounds > 1024) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "rounds must be between 1 and 1024");
     if (s->nq == 0) return PGVRX_OK;
     if (!out_ids || !out_dists || !out_counts || !out_done) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null output buffer");
     if (!ix->loaded || ix->generation != s->generation)
@@ -166,8 +172,11 @@ int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, f
     const int64_t nq = s->nq;
     int64_t active = 0;
     for (int64_t i = 0; i < nq; i++) active += !s->h_done[(size_t)i] && (!want_more || want_more[i]);
-    int rc = ensure_pool(s, active);
+    int rc = ensure_pool(s, active * rounds);
     if (rc) return rc;
+    CU_TRY(ix, s->ids.ensure((size_t)nq * rounds * s->ef * 4));
+    CU_TRY(ix, s->dists.ensure((size_t)nq * rounds * s->ef * 4));
+    CU_TRY(ix, s->counts.ensure((size_t)nq * rounds * 4));
     if (want_more) CU_TRY(ix, cudaMemcpyAsync(s->want.p, want_more, (size_t)nq, cudaMemcpyHostToDevice, stream));
     CU_TRY(ix, cudaMemsetAsync(s->work.p, 0, 64, stream));
     CU_TRY(ix, cudaEventRecord(ix->ev0, stream));
@@ -180,6 +189,7 @@ int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, f
     p.ef = s->ef;
     p.tail_cap = s->tail_cap;
     p.mode = s->mode;
+    p.rounds = rounds;
     p.max_scan_tuples = s->max_tuples;
     p.want_more = want_more ? (const uint8_t *)s->want.p : nullptr;
     p.state = (IterQueryState *)s->state.p;
@@ -203,9 +213,9 @@ int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, f
     p.R = s->R;
     CU_TRY(ix, launch_iter_scan(ix->desc.elem_type, ix->desc.metric, pgvrx_view_of(ix), p, s->grid, s->smem_block, stream));
     CU_TRY(ix, cudaEventRecord(ix->ev1, stream));
-    CU_TRY(ix, cudaMemcpyAsync(out_ids, s->ids.p, (size_t)nq * s->ef * 4, cudaMemcpyDeviceToHost, stream));
-    CU_TRY(ix, cudaMemcpyAsync(out_dists, s->dists.p, (size_t)nq * s->ef * 4, cudaMemcpyDeviceToHost, stream));
-    CU_TRY(ix, cudaMemcpyAsync(out_counts, s->counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(ix, cudaMemcpyAsync(out_ids, s->ids.p, (size_t)nq * rounds * s->ef * 4, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(ix, cudaMemcpyAsync(out_dists, s->dists.p, (size_t)nq * rounds * s->ef * 4, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(ix, cudaMemcpyAsync(out_counts, s->counts.p, (size_t)nq * rounds * 4, cudaMemcpyDeviceToHost, stream));
     CU_TRY(ix, cudaMemcpyAsync(out_done, s->done.p, (size_t)nq, cudaMemcpyDeviceToHost, stream));
     std::vector<uint32_t> st((size_t)nq), ctr((size_t)nq * 4);
     int used = 0;
@@ -214,7 +224,7 @@ int pgvrx_scan_next(pgvrx_scan *s, const uint8_t *want_more, int32_t *out_ids, f
     CU_TRY(ix, cudaMemcpyAsync(&used, s->pool_next.p, 4, cudaMemcpyDeviceToHost, stream));
     CU_TRY(ix, cudaStreamSynchronize(stream));
     s->pool_used = std::min(used, s->pool_cap);
-    s->rounds++;
+    s->rounds += rounds;
     for (int64_t i = 0; i < nq; i++) {
         s->h_done[(size_t)i] = out_done[i];
         if (st[(size_t)i] != 0) {

@@ -224,5 +224,6 @@ extern "C" {
     pub fn pgvrx_gather_probe(idx: *mut PgvrxIndex, mode: i32, warps_per_sm: i32, rows_per_step: i32, depth: i32, steps: i32, consume: i32, out: *mut PgvrxGatherProbeResult) -> c_int;
     pub fn pgvrx_scan_begin(idx: *mut PgvrxIndex, queries: *const c_void, nq: i64, ef_search: i32, iterative_mode: i32, max_scan_tuples: i64, out: *mut *mut PgvrxScan) -> c_int;
     pub fn pgvrx_scan_next(scan: *mut PgvrxScan, want_more: *const u8, out_ids: *mut i32, out_dists: *mut f32, out_counts: *mut i32, out_done: *mut u8, stats: *mut PgvrxSearchStats) -> c_int;
+    pub fn pgvrx_scan_next_rounds(scan: *mut PgvrxScan, want_more: *const u8, rounds: i32, out_ids: *mut i32, out_dists: *mut f32, out_counts: *mut i32, out_done: *mut u8, stats: *mut PgvrxSearchStats) -> c_int;
     pub fn pgvrx_scan_end(scan: *mut PgvrxScan);
 }

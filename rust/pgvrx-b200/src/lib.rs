@@ -453,6 +453,30 @@ impl<'a> Scan<'a> {
     }
 }
 
+impl<'a> Scan<'a> {
+    /// `rounds` refills in one launch (batch r of query q at `(q * rounds + r) * ef`): the same stream as `rounds` calls
+    /// of `next`, without the per-call launch and copy -- for consumers under a selective filter.
+    pub fn next_rounds(&mut self, want_more: Option<&[u8]>, rounds: i32) -> Result<(Vec<i32>, Vec<f32>, Vec<i32>, Vec<u8>)> {
+        let n = self.nq * rounds as usize;
+        let (mut ids, mut dists, mut counts) = (vec![-1i32; n * self.ef], vec![f32::INFINITY; n * self.ef], vec![0i32; n]);
+        let mut done = vec![0u8; self.nq];
+        let rc = unsafe {
+            ffi::pgvrx_scan_next_rounds(
+                self.raw,
+                want_more.map_or(ptr::null(), |w| w.as_ptr()),
+                rounds,
+                ids.as_mut_ptr(),
+                dists.as_mut_ptr(),
+                counts.as_mut_ptr(),
+                done.as_mut_ptr(),
+                ptr::null_mut(),
+            )
+        };
+        self.index.check(rc)?;
+        Ok((ids, dists, counts, done))
+    }
+}
+
 impl<'a> Drop for Scan<'a> {
     fn drop(&mut self) {
         unsafe { ffi::pgvrx_scan_end(self.raw) }

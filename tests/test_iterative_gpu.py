@@ -175,3 +175,40 @@ def test_heap_tid_fanout_with_duplicates():
             assert np.array_equal(got.astype(np.int64), tids)
     assert g["heap_tid_counts"].max() == 10
     ix.close()
+
+
+@pytest.mark.parametrize("mode,rounds,max_tuples", [(P.ITER_RELAXED, 4, 20000), (P.ITER_STRICT, 7, 20000), (P.ITER_RELAXED, 16, 600)])
+def test_several_refills_per_call_give_the_same_stream(mode, rounds, max_tuples):
+    # pgvrx_scan_next_rounds: `rounds` refills in one launch == `rounds` calls of pgvrx_scan_next (also across the switch to
+    # the max_scan_tuples drain, and when a query runs dry in the middle of a call)
+    n, dim, nq, ef = 2500, 24, 20, 12
+    rows = make_rows("f32", n, dim, 91)
+    o = oracle_index("vector_l2_ops", dim, rows, m=8, efc=32)
+    ix = gpu_index("vector_l2_ops", dim, o.export_graph(), m=8, efc=32)
+    q = make_rows("f32", nq, dim, 92)
+    one = ix.scan_begin(q, ef_search=ef, iterative_scan=mode, max_scan_tuples=max_tuples)
+    want_i, want_d = one.stream(None)
+    many = ix.scan_begin(q, ef_search=ef, iterative_scan=mode, max_scan_tuples=max_tuples)
+    got_i = [[] for _ in range(nq)]
+    got_d = [[] for _ in range(nq)]
+    done = np.zeros(nq, bool)
+    calls = 0
+    while not done.all():
+        ids, dists, counts, d = many.next((~done).astype(np.uint8), rounds=rounds)
+        assert ids.shape == (nq, rounds, ef) and counts.shape == (nq, rounds)
+        for i in np.nonzero(~done)[0]:
+            for r in range(rounds):
+                got_i[i].extend(ids[i, r, :counts[i, r]].tolist())
+                got_d[i].extend(dists[i, r, :counts[i, r]].tolist())
+                assert (ids[i, r, counts[i, r]:] == -1).all()
+        done |= d
+        calls += 1
+    for i in range(nq):
+        assert got_i[i] == list(want_i[i]), i
+        assert np.array_equal(np.asarray(got_d[i], np.float32), want_d[i]), i
+    for k in ("n_dist", "n_expand0", "n_visited"):
+        assert many.totals[k] == one.totals[k], k
+    assert calls * rounds >= one.totals["rounds"] > (calls - 1) * rounds
+    one.close()
+    many.close()
+    ix.close()
