@@ -481,6 +481,13 @@ namespace pgvrx_host {
 struct RoundScratch {
     RoundBuffers rb;
     PinnedBuf h_pack, h_mat;
+    // Host-to-device traffic of a round (the pending elements' rows, committed neighbour rows, group descriptions) leaves
+    // from page-locked staging: a cudaMemcpyAsync from pageable memory is staged by the driver synchronously (tens of
+    // microseconds each, a dozen per round).  Two arenas alternate by round: what round r queued behind its last kernel
+    // has certainly been read when round r + 2 starts writing (round r + 1 waited for its own search results in between).
+    PinnedBuf h_up[2];
+    size_t up_off = 0;
+    int up_sel = 0;
     ~RoundScratch() { rb.release(); }
 };
 void destroy_build_state(BuildState *b) {
@@ -710,6 +717,30 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
 
     if (!g.scratch) g.scratch = new RoundScratch();
     RoundBuffers &rb = g.scratch->rb;
+    RoundScratch &rsx = *g.scratch;
+    // copy `bytes` at src to page-locked staging and queue the transfer to dst on the index's stream
+    auto h2d = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (bytes == 0) return PGVRX_OK;
+        PinnedBuf &a = rsx.h_up[rsx.up_sel];
+        const size_t need = rsx.up_off + ((bytes + 255) & ~(size_t)255);
+        if (need > a.cap) {
+            // growing frees the arena: everything queued from it must have been read first
+            CU_TRY(ix, cudaStreamSynchronize(ix->stream));
+            PinnedBuf bigger;
+            CU_TRY(ix, bigger.ensure(std::max<size_t>(need * 2, (size_t)8 << 20)));
+            if (rsx.up_off) memcpy(bigger.p, a.p, rsx.up_off);
+            std::swap(a.p, bigger.p);
+            std::swap(a.cap, bigger.cap);
+        }
+        void *stage = (uint8_t *)a.p + rsx.up_off;
+        memcpy(stage, src, bytes);
+        rsx.up_off = need;
+        CU_TRY(ix, cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, ix->stream));
+        return PGVRX_OK;
+    };
+    auto next_arena = [&]() { rsx.up_sel ^= 1; rsx.up_off = 0; };
+    CU_TRY(ix, cudaStreamSynchronize(ix->stream));       // nothing an earlier call queued still reads the arenas
+    rsx.up_off = 0;
 
     // scatter staging on the host
     std::vector<int64_t> sc_off0, sc_offu;
@@ -732,11 +763,11 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
             const int row_len = pass == 0 ? l0 : m;
             CU_TRY(ix, rb.sc_off.ensure(off.size() * 8));
             CU_TRY(ix, rb.sc_rows.ensure(dat.size() * 4));
-            CU_TRY(ix, cudaMemcpyAsync(rb.sc_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ix->stream));
-            CU_TRY(ix, cudaMemcpyAsync(rb.sc_rows.p, dat.data(), dat.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+            // the two passes share rb.sc_off / rb.sc_rows: the second pass's copies queue behind the first pass's kernel
+            { int rc_ = h2d(rb.sc_off.p, off.data(), off.size() * 8); if (rc_) return rc_; }
+            { int rc_ = h2d(rb.sc_rows.p, dat.data(), dat.size() * 4); if (rc_) return rc_; }
             CU_TRY(ix, launch_scatter_rows((int32_t *)(pass == 0 ? ix->adj0.p : ix->adj_up.p), (const int64_t *)rb.sc_off.p,
                                            (const int32_t *)rb.sc_rows.p, row_len, (int)off.size(), ix->stream));
-            // (pageable sources are staged before cudaMemcpyAsync returns, so the vectors can be reused at once)
             off.clear();
             dat.clear();
         }
@@ -745,16 +776,16 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
     // upload vector rows / level / upper_base of elements [e0, e1)
     auto upload_elements = [&](int64_t e0, int64_t e1) -> int {
         if (e1 <= e0) return PGVRX_OK;
-        if (ix->row_stride == ix->row_bytes)
-            CU_TRY(ix, cudaMemcpyAsync((uint8_t *)ix->vectors.p + (size_t)e0 * ix->row_stride, g.row(e0), (size_t)(e1 - e0) * g.row_bytes,
-                                       cudaMemcpyHostToDevice, ix->stream));
-        else {
+        if (ix->row_stride == ix->row_bytes) {
+            int rc_ = h2d((uint8_t *)ix->vectors.p + (size_t)e0 * ix->row_stride, g.row(e0), (size_t)(e1 - e0) * g.row_bytes);
+            if (rc_) return rc_;
+        } else {
             CU_TRY(ix, cudaMemsetAsync((uint8_t *)ix->vectors.p + (size_t)e0 * ix->row_stride, 0, (size_t)(e1 - e0) * ix->row_stride, ix->stream));
             CU_TRY(ix, cudaMemcpy2DAsync((uint8_t *)ix->vectors.p + (size_t)e0 * ix->row_stride, ix->row_stride, g.row(e0), g.row_bytes,
                                          g.row_bytes, (size_t)(e1 - e0), cudaMemcpyHostToDevice, ix->stream));
         }
-        CU_TRY(ix, cudaMemcpyAsync((uint8_t *)ix->level.p + e0, &g.level[(size_t)e0], (size_t)(e1 - e0), cudaMemcpyHostToDevice, ix->stream));
-        CU_TRY(ix, cudaMemcpyAsync((int32_t *)ix->upper_base.p + e0, &g.upper_base[(size_t)e0], (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ix->stream));
+        { int rc_ = h2d((uint8_t *)ix->level.p + e0, &g.level[(size_t)e0], (size_t)(e1 - e0)); if (rc_) return rc_; }
+        { int rc_ = h2d((int32_t *)ix->upper_base.p + e0, &g.upper_base[(size_t)e0], (size_t)(e1 - e0) * 4); if (rc_) return rc_; }
         return PGVRX_OK;
     };
 
@@ -838,6 +869,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         const double tP0 = now_ms();
         g.round++;
         n_rounds++;
+        next_arena();
         // ---- provisional placement: input row f+i -> element id g.n + i (valid while no duplicate commits) ----
         const int64_t e_base = g.n;
         const int64_t up_base = g.n_upper;
@@ -886,7 +918,7 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
         t_cfg += now_ms() - tP2;
         h_elem.resize((size_t)B);
         for (int i = 0; i < B; i++) h_elem[(size_t)i] = (int32_t)(e_base + i);
-        CU_TRY(ix, cudaMemcpyAsync(rb.elem_ids.p, h_elem.data(), (size_t)B * 4, cudaMemcpyHostToDevice, ix->stream));
+        { int rc_ = h2d(rb.elem_ids.p, h_elem.data(), (size_t)B * 4); if (rc_) return rc_; }
         CU_TRY(ix, cudaMemsetAsync(rb.work.p, 0, 64, ix->stream));
         ix->n = e_base;                 // snapshot: only committed elements are reachable, but rows of the pending ones are resident
         ix->entry = g.entry;
@@ -1090,9 +1122,9 @@ static int run_inserts(pgvrx_index *ix, const void *rows_in, int64_t n_rows, con
             CU_TRY(ix, rb.g_off.ensure(h_goff.size() * 4));
             CU_TRY(ix, rb.g_mat.ensure(n_rows_dev * MW * 4));
             CU_TRY(ix, h_mat.ensure(n_rows_dev * MW * 4));
-            CU_TRY(ix, cudaMemcpyAsync(rb.g_ids.p, h_gids.data(), n_rows_dev * 4, cudaMemcpyHostToDevice, ix->stream));
-            CU_TRY(ix, cudaMemcpyAsync(rb.g_own.p, h_gown.data(), n_rows_dev * 4, cudaMemcpyHostToDevice, ix->stream));
-            CU_TRY(ix, cudaMemcpyAsync(rb.g_off.p, h_goff.data(), h_goff.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+            { int rc_ = h2d(rb.g_ids.p, h_gids.data(), n_rows_dev * 4); if (rc_) return rc_; }
+            { int rc_ = h2d(rb.g_own.p, h_gown.data(), n_rows_dev * 4); if (rc_) return rc_; }
+            { int rc_ = h2d(rb.g_off.p, h_goff.data(), h_goff.size() * 4); if (rc_) return rc_; }
             CU_TRY(ix, cudaMemsetAsync((int *)rb.work.p + 8, 0, 4, ix->stream));
             PairParams pp;
             pp.ids = (const int32_t *)rb.g_ids.p;
