@@ -94,7 +94,7 @@ def parse():
     ap.add_argument("--no-recall-curve", action="store_true", help="C2: skip the ef_search sweep (gaussian and low-intrinsic-dimension data)")
     ap.add_argument("--no-ef100", action="store_true", help="C2: skip the ef_search = 100 section")
     ap.add_argument("--no-gather-probe", action="store_true", help="skip the gather-ceiling probe")
-    ap.add_argument("--iter-queries", type=int, default=2000, help="C4: queries per filtered iterative-scan batch")
+    ap.add_argument("--iter-queries", type=int, default=10000, help="C4: queries per filtered iterative-scan batch (a quarter of it under the 1-in-500 filter)")
     ap.add_argument("--sweep", action="store_true", help="also time the scan under other staging geometries (tuning; rank 0, N = 1)")
     a = ap.parse_args()
     c = CONFIGS[a.config]
@@ -825,7 +825,7 @@ def iterative_section(a, ix, o, queries, filt, nq_it, limit=10):
     # (one backend = one thread in the reference), wall clock
     from concurrent.futures import ThreadPoolExecutor
     cores = host_cores(a)
-    n_chk = min(max(cores, 12), nq_it)
+    n_chk = min(max(4 * cores, 48), nq_it)
 
     def cpu_stream(i):
         _, eids, _, _ = o.scan_stream(q[i], ef_search=a.ef, iterative=O.ITER_RELAXED, max_scan_tuples=mst, max_emit=int(seen[i]))

@@ -122,6 +122,14 @@ int pgvrx_make_config(pgvrx_index *ix, int ef, int tail_cap, uint32_t vis_entrie
             c.L.stage_bytes = std::max<uint32_t>(32u * c.L.chunk_stride, c.L.stage_stride);
         }
     }
+    // The build's searches are latency bound with shared memory to spare (a few dozen resident warps on the whole device):
+    // two chunk buffers, the next chunk in flight while this one is accumulated (hnsw_device.cuh eval_neighbours).
+    // PGVRX_CHUNK_DB=0/1 pins the choice for either kind of search.
+    if (c.L.chunk_bytes != 0) {
+        bool db = for_build;
+        if (const char *e = getenv("PGVRX_CHUNK_DB")) db = atoi(e) != 0;
+        if (db) c.L.stage_bytes = std::max<uint32_t>(64u * c.L.chunk_stride, c.L.stage_stride);
+    }
     c.vis_entries = vis_entries;
     // scans run one warp (= one query in flight) per CTA: a CTA's slot is handed to the next batch as soon as that warp
     // has finished its last query instead of waiting for three siblings (measured 6.86 / 6.71 / 6.58 M QPS for 1 / 2 / 4

@@ -378,6 +378,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     c.nvec = (int)(p.row_stride / 16);
     c.lane = lane;
     c.phase = 0;
+    c.phase2 = 0;
+    c.stage2 = nullptr;
     c.policy = l2_policy_evict_first();
     GraphView g{};
     g.vectors = p.vectors;

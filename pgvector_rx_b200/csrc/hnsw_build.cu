@@ -54,11 +54,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
     c.cap = cap;
     c.lane = lane;
     c.phase = 0;
+    c.phase2 = 0;
+    c.stage2 = (c.chunk_bytes != 0 && (uint32_t)p.stage_bytes >= 64u * c.chunk_stride) ? c.stage + 32u * (size_t)c.chunk_stride : nullptr;
     c.policy = l2_policy_evict_first();
     const int slot = blockIdx.x * (blockDim.x / 32) + warp;
     c.vis = p.vis_base + (size_t)slot * p.vis_entries;
     if (lane == 0) {
         mbar_init(c.mbar, 1);
+        mbar_init(c.mbar + 1, 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -225,11 +228,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_repair_search_kernel(Grap
     c.cap = cap;
     c.lane = lane;
     c.phase = 0;
+    c.phase2 = 0;
+    c.stage2 = (c.chunk_bytes != 0 && (uint32_t)p.stage_bytes >= 64u * c.chunk_stride) ? c.stage + 32u * (size_t)c.chunk_stride : nullptr;
     c.policy = l2_policy_evict_first();
     const int slot = blockIdx.x * (blockDim.x / 32) + warp;
     c.vis = p.vis_base + (size_t)slot * p.vis_entries;
     if (lane == 0) {
         mbar_init(c.mbar, 1);
+        mbar_init(c.mbar + 1, 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -335,12 +341,21 @@ __global__ void scatter_rows_kernel(int32_t *dst, const int64_t *row_offsets, co
 // One CTA per group: the rows are staged once (one TMA bulk copy per row), lane <-> column b, row a is
 // broadcast from shared memory; distances use the same sequential arithmetic as everywhere else.
 // ---------------------------------------------------------------------------------------------------
+// Every distance here is symmetric bit for bit (the element-wise terms commute exactly and are added in the same element
+// order), so each unordered pair is evaluated once and feeds both masks: bit b of mask[a] and bit a of mask[b].  Sixteen
+// warps share a group: a group of 128 wide rows is 16 k chains of up to thousands of dependent additions each, and four
+// warps -- one per scheduler -- left every chain's latency exposed (C3: 0.46 ms per group, more than the searches of the
+// round).
+constexpr int PAIR_THREADS = 512;
 template <int ELEM, int METRIC>
-__global__ void __launch_bounds__(SEARCH_THREADS) pairwise_kernel(GraphView g, PairParams p) {
+__global__ void __launch_bounds__(PAIR_THREADS) pairwise_kernel(GraphView g, PairParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     uint8_t *stage = smem + 128;
+    constexpr int MW = PAIR_MAX_ROWS / 32;
     __shared__ int s_group;
+    __shared__ uint32_t s_mask[PAIR_MAX_ROWS * MW];
+    __shared__ float s_own[PAIR_MAX_ROWS];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -366,22 +381,28 @@ __global__ void __launch_bounds__(SEARCH_THREADS) pairwise_kernel(GraphView g, P
         }
         if (cnt == 0) { __syncthreads(); continue; }
         if (t == 0) mbar_arrive_expect_tx(mbar, (uint32_t)cnt * g.row_stride);
+        for (int i = t; i < PAIR_MAX_ROWS * MW; i += PAIR_THREADS) s_mask[i] = 0u;
+        if (t < cnt) s_own[t] = p.own_dist[off + t];
         __syncthreads();
         if (t < cnt)
             tma_row_g2s(stage + (size_t)t * p.stage_stride, g.vectors + (size_t)p.ids[off + t] * g.row_stride, g.row_stride, mbar, policy);
         mbar_wait(mbar, phase);
         phase ^= 1u;
-        for (int a = warp; a < cnt; a += SEARCH_THREADS / 32) {
-            const uint8_t *ra = stage + (size_t)a * p.stage_stride;
-            const float own = p.own_dist[off + a];
-            for (int b0 = 0; b0 < PAIR_MAX_ROWS; b0 += 32) {
-                const int b = b0 + lane;
-                bool le = false;
-                if (b0 < cnt && b < cnt) le = row_distance<ELEM, METRIC>(ra, stage + (size_t)b * p.stage_stride, nvec) <= own;   // :333
-                const uint32_t word = b0 < cnt ? __ballot_sync(FULL, le) : 0u;
-                if (lane == 0) p.out[((size_t)off + a) * (PAIR_MAX_ROWS / 32) + (b0 >> 5)] = word;
-            }
+        // work items: (row a, block of 32 columns) for the blocks that reach column a or beyond; lanes on columns b >= a
+        const int nblk = (cnt + 31) >> 5;
+        for (int item = warp; item < cnt * nblk; item += PAIR_THREADS / 32) {
+            const int a = item / nblk, b0 = (item - a * nblk) << 5;
+            if (b0 + 31 < a) continue;
+            const int b = b0 + lane;
+            const bool act = b >= a && b < cnt;
+            float d = 0.0f;
+            if (act) d = row_distance<ELEM, METRIC>(stage + (size_t)a * p.stage_stride, stage + (size_t)b * p.stage_stride, nvec);
+            const uint32_t wa = __ballot_sync(FULL, act && d <= s_own[a]);                    // :333, e = a against r = b
+            if (lane == 0 && wa) atomicOr(&s_mask[a * MW + (b0 >> 5)], wa);
+            if (act && b > a && d <= s_own[b]) atomicOr(&s_mask[b * MW + (a >> 5)], 1u << (a & 31));   // e = b against r = a
         }
+        __syncthreads();
+        for (int i = t; i < cnt * MW; i += PAIR_THREADS) p.out[(size_t)off * MW + i] = s_mask[i];
         // generic-proxy reads of the staging rows are ordered before the next group's TMA writes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -464,7 +485,7 @@ cudaError_t launch_pairwise(int elem, int metric, const GraphView &g, const Pair
     const size_t smem = 128 + (size_t)max_rows * p.stage_stride;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<grid, SEARCH_THREADS, smem, stream>>>(g, p);
+    k<<<grid, PAIR_THREADS, smem, stream>>>(g, p);
     return cudaGetLastError();
 }
 

@@ -270,6 +270,8 @@ struct WarpCtx {
     int R, nvec;
     uint32_t chunk_bytes;  // 0: whole rows are staged (R at a time); else rows are staged in chunks of this many bytes,
     uint32_t chunk_stride; //    32 rows at a time, chunk_stride bytes apart (wide rows: every lane keeps a row to work on)
+    uint8_t *stage2;       // chunked staging with room for two chunk buffers: the second one (else NULL); chunk i + 1 is then
+    uint32_t phase2;       //    in flight (second mbarrier, c.mbar + 1) while chunk i is accumulated
     int len, ef, cap;      // list length (W plus retained boundary ties), ef, capacity
     uint32_t phase;
     uint32_t f_ord;        // ordered bits of W's furthest distance (valid when len >= ef)
@@ -558,6 +560,35 @@ __device__ __forceinline__ float eval_neighbours(WarpCtx &c, const GraphView &g,
         DistAcc<ELEM, METRIC> acc;
         acc.init();
         const bool mine = lane < cnt && (want || !masked);
+        if (c.stage2 != nullptr) {
+            // two chunk buffers: the next chunk's bulk copies are issued before this chunk is accumulated, so the memory
+            // round trip of chunk i + 1 hides behind the arithmetic of chunk i (the build's searches are latency bound)
+            const uint32_t m = __ballot_sync(FULL, mine);
+            if (m) {
+                const uint32_t n_mine = (uint32_t)__popc(m);
+                const uint8_t *src = g.vectors + (size_t)(mine ? c.nbr[lane] : 0) * g.row_stride;
+                auto issue = [&](uint32_t off, int b) {
+                    const uint32_t cb = min(c.chunk_bytes, g.row_stride - off);
+                    if (lane == 0) mbar_arrive_expect_tx(c.mbar + b, n_mine * cb);
+                    __syncwarp();
+                    if (mine) tma_row_g2s((b ? c.stage2 : c.stage) + (size_t)lane * c.chunk_stride, src + off, cb, c.mbar + b, c.policy);
+                };
+                issue(0, 0);
+                int b = 0;
+                for (uint32_t off = 0; off < g.row_stride; off += c.chunk_bytes, b ^= 1) {
+                    const uint32_t cb = min(c.chunk_bytes, g.row_stride - off);
+                    if (off + c.chunk_bytes < g.row_stride) issue(off + c.chunk_bytes, b ^ 1);
+                    if (b == 0) { mbar_wait(c.mbar, c.phase); c.phase ^= 1u; }
+                    else { mbar_wait(c.mbar + 1, c.phase2); c.phase2 ^= 1u; }
+                    PH_TICK(c, 2);
+                    if (mine) acc.add(c.qsm + off, (b ? c.stage2 : c.stage) + (size_t)lane * c.chunk_stride, (int)(cb / 16));
+                    __syncwarp();
+                    PH_TICK(c, 3);
+                }
+            }
+            if (mine) d = acc.finish();
+            return d;
+        }
         for (uint32_t off = 0; off < g.row_stride; off += c.chunk_bytes) {
             const uint32_t cb = min(c.chunk_bytes, g.row_stride - off);
             gather_chunk(c, g, mine, off, cb);

@@ -379,6 +379,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_iter_scan_kernel(GraphVie
     c.cap = cap;
     c.lane = lane;
     c.phase = 0;
+    c.phase2 = 0;
+    c.stage2 = nullptr;
     c.policy = l2_policy_evict_first();
     c.rs_log = nullptr;
     c.rs_cap = c.rs_n = 0;

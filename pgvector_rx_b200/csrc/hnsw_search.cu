@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
     c.cap = cap;
     c.lane = lane;
     c.phase = 0;
+    c.phase2 = 0;
+    c.stage2 = (c.chunk_bytes != 0 && (uint32_t)p.stage_bytes >= 64u * c.chunk_stride) ? c.stage + 32u * (size_t)c.chunk_stride : nullptr;
     c.policy = l2_policy_evict_first();
     c.rs_log = nullptr;
     c.rs_cap = c.rs_n = 0;
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_scan_kernel(GraphView g, 
 
     if (lane == 0) {
         mbar_init(c.mbar, 1);
+        mbar_init(c.mbar + 1, 1);
         fence_mbar_init();
     }
     __syncwarp();

@@ -308,12 +308,15 @@ __global__ void __launch_bounds__(TEAM_MAX_WARPS * 32) hnsw_team_build_kernel(Gr
     c.cap = cap;
     c.lane = lane;
     c.phase = 0;
+    c.phase2 = 0;
+    c.stage2 = (c.chunk_bytes != 0 && (uint32_t)t.stage_bytes >= 64u * c.chunk_stride) ? c.stage + 32u * (size_t)c.chunk_stride : nullptr;
     c.policy = l2_policy_evict_first();
     c.vis = nullptr;
     c.spec = true;
     c.hybrid = false;
     if (lane == 0) {
         mbar_init(c.mbar, 1);
+        mbar_init(c.mbar + 1, 1);
         fence_mbar_init();
     }
     if (threadIdx.x == 0) {

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(32) hnsw_layer_search_kernel(GraphView g, Laye
     c.cap = cap;
     c.lane = lane;
     c.phase = 0;
+    c.phase2 = 0;
+    c.stage2 = nullptr;
     c.policy = l2_policy_evict_first();
     c.spec = true;
     c.hybrid = false;
