@@ -502,7 +502,7 @@ void pgvrx_index_destroy(pgvrx_index *ix) {
                       &ix->counts,
                       &ix->part_ids, &ix->part_dists, &ix->cand, &ix->tc_xhi, &ix->tc_xlo, &ix->tc_xnorm, &ix->tc_xmax,
                       &ix->tc_qhi, &ix->tc_qlo, &ix->tc_qnorm, &ix->tc_cand, &ix->tc_bound, &ix->tc_uncert, &ix->tc_cnt,
-                      &ix->tc_fq, &ix->tc_fids, &ix->tc_fdists, &ix->tc_dbg, &ix->tc_hint};
+                      &ix->tc_fq, &ix->tc_fids, &ix->tc_fdists, &ix->tc_dbg, &ix->tc_hint, &ix->tc_appcnt};
     for (DevBuf *b : bufs) b->release();
     for (auto &sc : ix->scan_scratch) {
         DevBuf *sb[] = {&sc.status, &sc.ctr, &sc.vis, &sc.vis_retry, &sc.qmap, &sc.work, &sc.phase};

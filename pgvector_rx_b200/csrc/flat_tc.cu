@@ -194,6 +194,17 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
             const int nvalid = valid_cols - c;
             if (!qvalid || nvalid <= 0) mask = 0;
             else if (nvalid < 32) mask &= (1u << nvalid) - 1u;
+            if (p.app_ids != nullptr) {
+                // append mode: the threshold is the pre-pass hint and does not move; a lane appends its own query's rows,
+                // no cross-lane work at all
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int pos = atomicAdd(p.app_cnt + q, 1);
+                    if (pos < p.app_cap) p.app_ids[(size_t)q * p.app_cap + pos] = (int32_t)((uint32_t)(row0 + c + j) + (uint32_t)p.id_base);
+                }
+                continue;
+            }
             if (__ballot_sync(FULL, mask != 0)) {
                 // slow path (rare once the sets have warmed up): column by column over the union of the masks
                 uint32_t um = __reduce_or_sync(FULL, mask);
@@ -605,7 +616,7 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
 __global__ void tc_certify_kernel(const float *__restrict__ topk_dists, const int32_t *__restrict__ topk_ids, int k,
                                   const float *__restrict__ cand_bound, int n_splits, int nq, const float *__restrict__ qnorm,
                                   const uint32_t *__restrict__ xnorm_max, float eps_rel, int metric, const uint32_t *__restrict__ hint,
-                                  int32_t *uncert_list, int *n_uncert) {
+                                  const int *__restrict__ app_cnt, int app_cap, int32_t *uncert_list, int *n_uncert) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     // Rows were rejected against min(the unit's own full-set maximum, hint[q] at the time); the hint only ever decreases
@@ -614,7 +625,8 @@ __global__ void tc_certify_kernel(const float *__restrict__ topk_dists, const in
     float bound = hint ? ord_f32(hint[q]) : __int_as_float(0x7f800000);
     for (int s = 0; s < n_splits; s++) bound = fminf(bound, cand_bound[(size_t)s * nq + q]);
     bool ok = true;
-    if (bound < __int_as_float(0x7f800000)) {
+    if (app_cnt != nullptr && app_cnt[q] > app_cap) ok = false;        // rows under the threshold were dropped
+    else if (bound < __int_as_float(0x7f800000)) {
         const float xm = __uint_as_float(*xnorm_max);
         const float eps = eps_rel * (qnorm[q] + xm);
         // the k-th result must exist and lie strictly inside the certified radius
@@ -685,9 +697,9 @@ cudaError_t launch_flat_tc2(const void *map_qhi, const void *map_qlo, const void
 
 cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
                               const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, const uint32_t *hint,
-                              int32_t *uncert_list, int *n_uncert, cudaStream_t stream) {
+                              const int *app_cnt, int app_cap, int32_t *uncert_list, int *n_uncert, cudaStream_t stream) {
     tc_certify_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(topk_dists, topk_ids, k, cand_bound, n_splits, nq, qnorm, xnorm_max,
-                                                            eps_rel, metric, hint, uncert_list, n_uncert);
+                                                            eps_rel, metric, hint, app_cnt, app_cap, uncert_list, n_uncert);
     return cudaGetLastError();
 }
 

@@ -175,6 +175,9 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     p.hint = (uint32_t *)ix->tc_hint.p;
     p.tile_step = 1;
     p.kp_eff = TC_KP;
+    p.app_ids = nullptr;
+    p.app_cnt = nullptr;
+    p.app_cap = 0;
     // Hint pre-pass.  A unit (query tile x base split) starts with empty candidate sets, and until a set's maximum has
     // come down nearly every element takes the serial insertion path: KP (1 + ln(rows / KP)) insertions per query and
     // unit.  Units of later waves inherit a threshold from earlier ones through p.hint; the first wave does not, and
@@ -184,12 +187,13 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     // smallest approximate distance of the sample: about kp_eff * step rows of the table lie below it, several times k.
     // The main pass then starts from that threshold everywhere.  The certificate takes the final hint into account.
     const bool prepass = want_prepass;
+    int app_cap = 0;
     if (prepass) {
         TcParams pa = p;
         // a 1/24 sample and the (k / 2 + 3)-th smallest of it: ~ 24 (k / 2 + 3) rows of the table below the threshold
         // (190 for k = 10), an order of magnitude more than the k the certificate needs, a fraction of what unguided
         // candidate sets would insert
-        const int want_tiles = std::max(4, std::min(48, pl.n_ntiles / 24));
+        const int want_tiles = std::max(4, pl.n_ntiles / 24);
         pa.tile_step = std::max(1, pl.n_ntiles / want_tiles);
         pa.kp_eff = std::max(8, std::min((int)TC_KP, k / 2 + 3));
         pa.n_splits = 1;
@@ -201,6 +205,22 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
         const int ga = std::min(pl.n_mtiles, workers);
         if (two_cta) CU_TRY(ix, launch_flat_tc2(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, pa, 2 * ga, stream));
         else CU_TRY(ix, launch_flat_tc(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, pa, ga, stream));
+        // Main pass in append mode: with a threshold known up front nothing has to be maintained -- a lane appends its own
+        // query's rows under the threshold (expected kp_eff * step of them per query, Gamma distributed; the list holds
+        // five times that) and the serial set insertions disappear from the epilogue.  PGVRX_TC_NO_APPEND=1 keeps the sets.
+        if (!getenv("PGVRX_TC_NO_APPEND")) {
+            app_cap = (int)pgvrx_pow2_at_least((uint64_t)5 * pa.kp_eff * pa.tile_step);
+            app_cap = std::max(256, std::min(app_cap, 8192));
+            CU_TRY(ix, ix->tc_cand.ensure((size_t)nq * app_cap * 4));
+            CU_TRY(ix, ix->tc_appcnt.ensure((size_t)nq * 4));
+            CU_TRY(ix, cudaMemsetAsync(ix->tc_cand.p, 0xff, (size_t)nq * app_cap * 4, stream));
+            CU_TRY(ix, cudaMemsetAsync(ix->tc_appcnt.p, 0, (size_t)nq * 4, stream));
+            p.app_ids = (int32_t *)ix->tc_cand.p;
+            p.app_cnt = (int *)ix->tc_appcnt.p;
+            p.app_cap = app_cap;
+            p.cand_ids = nullptr;
+            p.cand_bound = nullptr;
+        }
     }
     if (two_cta) CU_TRY(ix, launch_flat_tc2(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, 2 * pl.grid, stream));
     else CU_TRY(ix, launch_flat_tc(map_qhi, map_qlo, ix->tc_map_xhi, ix->tc_map_xlo, p, pl.grid, stream));
@@ -208,12 +228,13 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     uint64_t n_uncert = 0;
     if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[1], stream));
     if (d_ids) {
-        rc = pgvrx_rerank_device(ix, d_queries, nq, (const int32_t *)ix->tc_cand.p, nc, k, id_base, d_ids, d_dists, stream);
+        rc = pgvrx_rerank_device(ix, d_queries, nq, (const int32_t *)ix->tc_cand.p, app_cap ? app_cap : nc, k, id_base, d_ids, d_dists, stream);
         if (rc) return rc;
         if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[2], stream));
-        CU_TRY(ix, launch_tc_certify(d_dists, d_ids, k, (const float *)ix->tc_bound.p, pl.n_splits, (int)nq,
+        CU_TRY(ix, launch_tc_certify(d_dists, d_ids, k, (const float *)ix->tc_bound.p, app_cap ? 0 : pl.n_splits, (int)nq,
                                      (const float *)ix->tc_qnorm.p, (const uint32_t *)ix->tc_xmax.p, tc_eps_rel(ix->desc.dim),
-                                     ix->desc.metric, (const uint32_t *)ix->tc_hint.p, (int32_t *)ix->tc_uncert.p, (int *)ix->tc_cnt.p, stream));
+                                     ix->desc.metric, (const uint32_t *)ix->tc_hint.p, app_cap ? (const int *)ix->tc_appcnt.p : nullptr, app_cap,
+                                     (int32_t *)ix->tc_uncert.p, (int *)ix->tc_cnt.p, stream));
         launches += 2;
         int nu = 0;
         CU_TRY(ix, cudaMemcpyAsync(&nu, ix->tc_cnt.p, 4, cudaMemcpyDeviceToHost, stream));
@@ -240,6 +261,13 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
         CU_TRY(ix, cudaEventElapsedTime(&stats->kernel_ms, ix->ev0, ix->ev1));
         stats->n_pairs = (uint64_t)nq * (uint64_t)ix->n;
         stats->n_candidates = (uint64_t)nq * (uint64_t)nc;
+        if (app_cap) {                                   // append mode: what the lists really hold
+            std::vector<int> cnt((size_t)nq);
+            CU_TRY(ix, cudaMemcpy(cnt.data(), ix->tc_appcnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+            uint64_t tot = 0;
+            for (int c : cnt) tot += (uint64_t)std::min(c, app_cap);
+            stats->n_candidates = tot;
+        }
         stats->n_uncertified = n_uncert;
         stats->n_launches = (uint32_t)launches;
         stats->n_splits = (uint32_t)pl.n_splits;

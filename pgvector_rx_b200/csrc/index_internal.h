@@ -86,7 +86,7 @@ struct pgvrx_index {
     DevBuf part_ids, part_dists, cand;   // flat kNN partial lists, re-rank candidates
     // tensor-core flat path (K4b): tf32 hi/lo splits of the table (built lazily, dropped when the table changes)
     DevBuf tc_xhi, tc_xlo, tc_xnorm, tc_xmax, tc_qhi, tc_qlo, tc_qnorm, tc_cand, tc_bound, tc_uncert, tc_cnt, tc_fq, tc_fids,
-        tc_fdists, tc_dbg, tc_hint;
+        tc_fdists, tc_dbg, tc_hint, tc_appcnt;
     bool tc_ready = false;
     int64_t tc_n_pad = 0;
     int tc_d_pad = 0;
