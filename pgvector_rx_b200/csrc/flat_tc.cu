@@ -151,6 +151,8 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
     float xn_cur[TN / 128];
 #pragma unroll
     for (int h = 0; h < TN / 128; h++) xn_cur[h] = p.xnorm[(int64_t)nt0 * TN + h * 128 + et];
+    int app_n = 0;                                                   // append mode: rows this lane's query has appended in this unit
+    int32_t *app_seg = p.app_ids ? p.app_ids + ((size_t)(qvalid ? q : 0) * p.n_splits + sp) * p.app_cap : nullptr;
     // a set of kp_eff < 32 keys (the hint pre-pass): the other slots hold key 0, which nothing replaces and which is never
     // the maximum once a real key is present
 #pragma unroll 4
@@ -195,13 +197,14 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
             if (!qvalid || nvalid <= 0) mask = 0;
             else if (nvalid < 32) mask &= (1u << nvalid) - 1u;
             if (p.app_ids != nullptr) {
-                // append mode: the threshold is the pre-pass hint and does not move; a lane appends its own query's rows,
-                // no cross-lane work at all
+                // append mode: the threshold is the pre-pass hint and does not move; a lane appends its own query's rows to
+                // the segment this unit owns in the query's list -- a private counter, plain stores, no cross-lane work and
+                // no atomics (a returning atomic per append would stall the warp for an L2 round trip each time)
                 while (mask) {
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const int pos = atomicAdd(p.app_cnt + q, 1);
-                    if (pos < p.app_cap) p.app_ids[(size_t)q * p.app_cap + pos] = (int32_t)((uint32_t)(row0 + c + j) + (uint32_t)p.id_base);
+                    if (app_n < p.app_cap) app_seg[app_n] = (int32_t)((uint32_t)(row0 + c + j) + (uint32_t)p.id_base);
+                    app_n++;
                 }
                 continue;
             }
@@ -275,6 +278,7 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
             p.cand_ids[((size_t)qi * p.n_splits + sp) * TC_KP + lane] = cur == ~0ull ? -1 : (int32_t)((uint32_t)cur + (uint32_t)p.id_base);
         }
     }
+    if (qvalid && p.app_cnt) p.app_cnt[(size_t)q * p.n_splits + sp] = app_n;
     // every row of this split that was not kept has an approximate distance >= this bound
     if (qvalid && p.cand_bound) p.cand_bound[(size_t)sp * p.nq + q] = tau_hi == 0xFFFFFFFFu ? __int_as_float(0x7f800000) : ord_f32(tau_hi);
     __syncwarp();
@@ -616,7 +620,7 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
 __global__ void tc_certify_kernel(const float *__restrict__ topk_dists, const int32_t *__restrict__ topk_ids, int k,
                                   const float *__restrict__ cand_bound, int n_splits, int nq, const float *__restrict__ qnorm,
                                   const uint32_t *__restrict__ xnorm_max, float eps_rel, int metric, const uint32_t *__restrict__ hint,
-                                  const int *__restrict__ app_cnt, int app_cap, int32_t *uncert_list, int *n_uncert) {
+                                  const int *__restrict__ app_cnt, int app_cap, int app_splits, int32_t *uncert_list, int *n_uncert) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     // Rows were rejected against min(the unit's own full-set maximum, hint[q] at the time); the hint only ever decreases
@@ -625,7 +629,10 @@ __global__ void tc_certify_kernel(const float *__restrict__ topk_dists, const in
     float bound = hint ? ord_f32(hint[q]) : __int_as_float(0x7f800000);
     for (int s = 0; s < n_splits; s++) bound = fminf(bound, cand_bound[(size_t)s * nq + q]);
     bool ok = true;
-    if (app_cnt != nullptr && app_cnt[q] > app_cap) ok = false;        // rows under the threshold were dropped
+    bool dropped = false;                                              // rows under the threshold that found no room
+    if (app_cnt != nullptr)
+        for (int s = 0; s < app_splits; s++) dropped = dropped || app_cnt[(size_t)q * app_splits + s] > app_cap;
+    if (dropped) ok = false;
     else if (bound < __int_as_float(0x7f800000)) {
         const float xm = __uint_as_float(*xnorm_max);
         const float eps = eps_rel * (qnorm[q] + xm);
@@ -697,9 +704,9 @@ cudaError_t launch_flat_tc2(const void *map_qhi, const void *map_qlo, const void
 
 cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
                               const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, const uint32_t *hint,
-                              const int *app_cnt, int app_cap, int32_t *uncert_list, int *n_uncert, cudaStream_t stream) {
+                              const int *app_cnt, int app_cap, int app_splits, int32_t *uncert_list, int *n_uncert, cudaStream_t stream) {
     tc_certify_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(topk_dists, topk_ids, k, cand_bound, n_splits, nq, qnorm, xnorm_max,
-                                                            eps_rel, metric, hint, app_cnt, app_cap, uncert_list, n_uncert);
+                                                            eps_rel, metric, hint, app_cnt, app_cap, app_splits, uncert_list, n_uncert);
     return cudaGetLastError();
 }
 

@@ -209,12 +209,13 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
         // query's rows under the threshold (expected kp_eff * step of them per query, Gamma distributed; the list holds
         // five times that) and the serial set insertions disappear from the epilogue.  PGVRX_TC_NO_APPEND=1 keeps the sets.
         if (!getenv("PGVRX_TC_NO_APPEND")) {
-            app_cap = (int)pgvrx_pow2_at_least((uint64_t)5 * pa.kp_eff * pa.tile_step);
-            app_cap = std::max(256, std::min(app_cap, 8192));
-            CU_TRY(ix, ix->tc_cand.ensure((size_t)nq * app_cap * 4));
-            CU_TRY(ix, ix->tc_appcnt.ensure((size_t)nq * 4));
-            CU_TRY(ix, cudaMemsetAsync(ix->tc_cand.p, 0xff, (size_t)nq * app_cap * 4, stream));
-            CU_TRY(ix, cudaMemsetAsync(ix->tc_appcnt.p, 0, (size_t)nq * 4, stream));
+            // one segment per (query, split): expected kp_eff * step / n_splits rows each, room for five times that + 32
+            app_cap = (int)pgvrx_pow2_at_least((uint64_t)(5 * pa.kp_eff * pa.tile_step / pl.n_splits + 32));
+            app_cap = std::max(64, std::min(app_cap, 4096));
+            CU_TRY(ix, ix->tc_cand.ensure((size_t)nq * pl.n_splits * app_cap * 4));
+            CU_TRY(ix, ix->tc_appcnt.ensure((size_t)nq * pl.n_splits * 4));
+            CU_TRY(ix, cudaMemsetAsync(ix->tc_cand.p, 0xff, (size_t)nq * pl.n_splits * app_cap * 4, stream));
+            CU_TRY(ix, cudaMemsetAsync(ix->tc_appcnt.p, 0, (size_t)nq * pl.n_splits * 4, stream));
             p.app_ids = (int32_t *)ix->tc_cand.p;
             p.app_cnt = (int *)ix->tc_appcnt.p;
             p.app_cap = app_cap;
@@ -228,12 +229,12 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     uint64_t n_uncert = 0;
     if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[1], stream));
     if (d_ids) {
-        rc = pgvrx_rerank_device(ix, d_queries, nq, (const int32_t *)ix->tc_cand.p, app_cap ? app_cap : nc, k, id_base, d_ids, d_dists, stream);
+        rc = pgvrx_rerank_device(ix, d_queries, nq, (const int32_t *)ix->tc_cand.p, app_cap ? app_cap * pl.n_splits : nc, k, id_base, d_ids, d_dists, stream);
         if (rc) return rc;
         if (stats) CU_TRY(ix, cudaEventRecord(ix->ev_ph[2], stream));
         CU_TRY(ix, launch_tc_certify(d_dists, d_ids, k, (const float *)ix->tc_bound.p, app_cap ? 0 : pl.n_splits, (int)nq,
                                      (const float *)ix->tc_qnorm.p, (const uint32_t *)ix->tc_xmax.p, tc_eps_rel(ix->desc.dim),
-                                     ix->desc.metric, (const uint32_t *)ix->tc_hint.p, app_cap ? (const int *)ix->tc_appcnt.p : nullptr, app_cap,
+                                     ix->desc.metric, (const uint32_t *)ix->tc_hint.p, app_cap ? (const int *)ix->tc_appcnt.p : nullptr, app_cap, pl.n_splits,
                                      (int32_t *)ix->tc_uncert.p, (int *)ix->tc_cnt.p, stream));
         launches += 2;
         int nu = 0;
@@ -262,8 +263,8 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
         stats->n_pairs = (uint64_t)nq * (uint64_t)ix->n;
         stats->n_candidates = (uint64_t)nq * (uint64_t)nc;
         if (app_cap) {                                   // append mode: what the lists really hold
-            std::vector<int> cnt((size_t)nq);
-            CU_TRY(ix, cudaMemcpy(cnt.data(), ix->tc_appcnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+            std::vector<int> cnt((size_t)nq * pl.n_splits);
+            CU_TRY(ix, cudaMemcpy(cnt.data(), ix->tc_appcnt.p, cnt.size() * 4, cudaMemcpyDeviceToHost));
             uint64_t tot = 0;
             for (int c : cnt) tot += (uint64_t)std::min(c, app_cap);
             stats->n_candidates = tot;

@@ -295,8 +295,8 @@ struct TcParams {
     int kp_eff;                    // keys a candidate set really holds (TC_KP, or fewer in the pre-pass)
     // append mode (after a pre-pass): no candidate sets -- every row whose approximate distance is <= hint[q] is appended to
     // query q's list; the certificate's bound is the hint, a list that overflows leaves its query uncertified
-    int32_t *app_ids;              // nq x app_cap global ids (caller pre-fills -1) or NULL
-    int *app_cnt;                  // nq counters (caller zeroes)
+    int32_t *app_ids;              // nq x n_splits x app_cap global ids (caller pre-fills -1) or NULL: one segment per unit
+    int *app_cnt;                  // nq x n_splits: rows the unit wanted to append (> app_cap: some were dropped)
     int app_cap;
 };
 
@@ -309,7 +309,7 @@ cudaError_t launch_flat_tc2(const void *map_qhi, const void *map_qlo, const void
                             int grid, cudaStream_t stream);
 cudaError_t launch_tc_certify(const float *topk_dists, const int32_t *topk_ids, int k, const float *cand_bound, int n_splits, int nq,
                               const float *qnorm, const uint32_t *xnorm_max, float eps_rel, int metric, const uint32_t *hint,
-                              const int *app_cnt, int app_cap, int32_t *uncert_list, int *n_uncert, cudaStream_t stream);
+                              const int *app_cnt, int app_cap, int app_splits, int32_t *uncert_list, int *n_uncert, cudaStream_t stream);
 cudaError_t launch_tc_gather_queries(const uint8_t *q, uint32_t q_stride, const int32_t *list, int n, uint8_t *out, cudaStream_t stream);
 cudaError_t launch_tc_scatter_results(const int32_t *ids, const float *dists, int k, const int32_t *list, int n, int32_t *out_ids,
                                       float *out_dists, cudaStream_t stream);
