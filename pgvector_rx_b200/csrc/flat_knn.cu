@@ -364,14 +364,14 @@ template <int ELEM, int METRIC>
 __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)p.R * p.stage_stride + p.row_stride + (((size_t)p.k * 8 + 15) & ~(size_t)15) + 128 + 16;
+    const size_t per_warp = (size_t)p.R * p.stage_stride + p.row_stride + (((size_t)p.k * 8 + 15) & ~(size_t)15) + 256 + 16;
     uint8_t *base = smem + (size_t)warp * per_warp;
     WarpCtx c;
     c.stage = base;
     c.qsm = base + (size_t)p.R * p.stage_stride;
     uint64_t *L = reinterpret_cast<uint64_t *>(c.qsm + p.row_stride);
     c.nbr = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(L) + (((size_t)p.k * 8 + 15) & ~(size_t)15));
-    c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 128);
+    c.mbar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(c.nbr) + 256);     // c.nbr holds up to 64 pending ids here
     c.stage_stride = p.stage_stride;
     c.R = p.R;
     c.chunk_bytes = c.chunk_stride = 0;
@@ -391,18 +391,10 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         for (uint32_t i = lane; i < p.row_stride; i += 32) c.qsm[i] = i < p.q_bytes ? __ldg(qp + i) : (uint8_t)0;
         __syncwarp();
         int len = 0;
-        for (int base_c = 0; base_c < p.nc; base_c += 32) {
-            const int i = base_c + lane;
-            const int32_t id = i < p.nc ? p.cand[(size_t)q * p.nc + i] : -1;
-            bool valid = id >= 0 && (int64_t)id - p.id_base < p.n_rows && id >= p.id_base;
-            if (valid && p.flags != nullptr && __ldg(p.flags + (id - p.id_base)) != 0) valid = false;
-            const uint32_t vm = __ballot_sync(FULL, valid);
-            if (!vm) continue;
-            // compact the valid ids to the front so that lane r evaluates staged row r
-            const int slot = __popc(vm & ((1u << lane) - 1u));
-            if (valid) c.nbr[slot] = id - p.id_base;
-            __syncwarp();
-            const int cnt = __popc(vm);
+        // candidate lists may be sparse (-1 padded segments): valid ids are collected across 32-id blocks and evaluated 32
+        // at a time, so a gather round is always full
+        int npend = 0;
+        auto evaluate = [&](int cnt) {                         // the ids in c.nbr[0, cnt), cnt <= 32
             uint64_t key = FKEY_MAX;
             for (int s = 0; s < cnt; s += c.R) {
                 const int nrow = min(c.R, cnt - s);
@@ -413,8 +405,35 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
                 }
                 __syncwarp();
             }
-            for (int r = 0; r < cnt; r++) topk_insert(L, len, p.k, __shfl_sync(FULL, key, r), lane);
+            // only keys that beat the current k-th can enter (the list only tightens while they are inserted)
+            uint32_t am = __ballot_sync(FULL, lane < cnt && (len < p.k || key < L[p.k - 1]));
+            while (am) {
+                const int r = __ffs(am) - 1;
+                am &= am - 1;
+                topk_insert(L, len, p.k, __shfl_sync(FULL, key, r), lane);
+            }
+        };
+        for (int base_c = 0; base_c < p.nc; base_c += 32) {
+            const int i = base_c + lane;
+            const int32_t id = i < p.nc ? p.cand[(size_t)q * p.nc + i] : -1;
+            bool valid = id >= 0 && (int64_t)id - p.id_base < p.n_rows && id >= p.id_base;
+            if (valid && p.flags != nullptr && __ldg(p.flags + (id - p.id_base)) != 0) valid = false;
+            const uint32_t vm = __ballot_sync(FULL, valid);
+            if (!vm) continue;
+            const int slot = npend + __popc(vm & ((1u << lane) - 1u));
+            if (valid) c.nbr[slot] = id - p.id_base;
+            npend += __popc(vm);
+            __syncwarp();
+            if (npend >= 32) {
+                evaluate(32);
+                const int32_t carry = lane < npend - 32 ? c.nbr[32 + lane] : 0;
+                __syncwarp();
+                if (lane < npend - 32) c.nbr[lane] = carry;
+                npend -= 32;
+                __syncwarp();
+            }
         }
+        if (npend > 0) evaluate(npend);
         for (int i = lane; i < p.k; i += 32) {
             const size_t o = (size_t)q * p.k + i;
             if (i < len) { p.out_ids[o] = (int32_t)(uint32_t)L[i]; p.out_dists[o] = ord_f32((uint32_t)(L[i] >> 32)); }
@@ -499,7 +518,7 @@ cudaError_t launch_topk_merge_parts(const MergeParts &parts, int nq, int k_in, i
 }
 
 size_t rerank_smem_bytes(uint32_t row_stride, uint32_t stage_stride, int R, int k) {
-    return 4 * ((size_t)R * stage_stride + row_stride + (((size_t)k * 8 + 15) & ~(size_t)15) + 128 + 16);
+    return 4 * ((size_t)R * stage_stride + row_stride + (((size_t)k * 8 + 15) & ~(size_t)15) + 256 + 16);
 }
 
 cudaError_t launch_rerank(int elem, int metric, const RerankParams &p, int grid, size_t smem, cudaStream_t stream) {

@@ -3,7 +3,7 @@ set -u
 N=${1:-2}
 out=gpurun_out; mkdir -p $out
 nvidia-smi -L | head -8
-timeout 600 python -m pytest tests/test_group_gpu.py -q --timeout 300 > $out/r2m_pytest_group_n$N.log 2>&1; echo "pytest rc=$?"; tail -3 $out/r2m_pytest_group_n$N.log
+timeout 600 python -m pytest tests/test_group_gpu.py tests/test_flat_gpu.py tests/test_flat_tc_gpu.py -q --timeout 300 > $out/r2m_pytest_group_n$N.log 2>&1; echo "pytest rc=$?"; tail -3 $out/r2m_pytest_group_n$N.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 10 --no-recall-curve --build-rows 0 > $out/r2m_bench_n$N.json 2> $out/r2m_bench_n$N.err; echo "bench rc=$?"
 python - <<PY
 import json
