@@ -616,6 +616,7 @@ class ScanRunner:
         import torch
         self.torch, self.a, self.ix, self.world, self.dev = torch, a, ix, world, dev
         self.nb, self.n_fly = len(batches), 2
+        self.collective = True
         self.batches = batches
         as_u8 = lambda b: b if b.dtype == np.float32 else b.view(np.uint8)
         self.d_q = [torch.from_numpy(as_u8(b)).to(dev) for b in batches]
@@ -634,7 +635,9 @@ class ScanRunner:
         return store[k]
 
     def barrier(self):
-        if self.world > 1:
+        # `collective` is switched off for the sections only rank 0 runs (ef_search sweeps, CPU arms): a process-group
+        # barrier there would wait for ranks that are not coming
+        if self.world > 1 and self.collective:
             import torch.distributed as dist
             dist.barrier()
         self.torch.cuda.synchronize()
@@ -669,7 +672,7 @@ class ScanRunner:
         e1.record(t0s)
         self.barrier()
         ms = e0.elapsed_time(e1)
-        if self.world > 1:
+        if self.world > 1 and self.collective:
             import torch.distributed as dist
             t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -686,7 +689,7 @@ class ScanRunner:
             step_fn(i)
         self.barrier()
         dt = time.perf_counter() - t0
-        if self.world > 1:
+        if self.world > 1 and self.collective:
             import torch.distributed as dist
             tt = torch.tensor([dt], dtype=torch.float64, device=self.dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -1076,6 +1079,7 @@ def run_b200(a):
 
     if rank == 0:
         import oracle_ffi as O
+        runner.collective = False          # from here on rank 0 is alone: its timed loops must not wait for the other ranks
         o = oracle_for(a, g)
         # parity: ids, distance bits and work counters of a sample against the oracle's scan of the same graph
         parity = parity_sample(a, ix, o, last_batch, a.ef, a.k, a.parity_sample)
