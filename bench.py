@@ -790,8 +790,8 @@ def iterative_section(a, ix, o, queries, filt, nq_it, limit=10):
     rounds = 0
     emitted = 0
     # refills per call (pgvrx_scan_next_rounds): a filter that keeps 1 row in c needs about limit * c / ef_search refills;
-    # asking for an eighth of that at a time bounds the work wasted on a query that finishes early to ~12 %
-    rpc = int(max(1, min(16, limit * filt // (a.ef * 8))))
+    # asking for a quarter of that at a time bounds the work wasted on a query that finishes early to ~25 % of a scan
+    rpc = int(max(1, min(16, limit * filt // (a.ef * 4))))
     col = np.arange(rpc * a.ef)[None, :]
     calls = 0
     while True:
