@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
             __syncwarp();
             c.n_vis++;
             S.reset1(c, ep_key);
-            search_layer<ELEM, METRIC, FLAGGED, false, true>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
+            search_layer<ELEM, METRIC, FLAGGED>(c, S, g, lc, up_entries - 1, up_entries / 4 * 3 - 32);
             ep_key = S.get(c, 0) & ~1ull;                                           // :396-398 w[0]
         }
         // phase 2: ef_construction search on every layer the new element joins (graph/mod.rs:403-426)
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) hnsw_build_search_kernel(Graph
                 c.n_vis += c.len;
             }
             first = false;
-            search_layer<ELEM, METRIC, FLAGGED, false, true>(c, S, g, lc, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
+            search_layer<ELEM, METRIC, FLAGGED>(c, S, g, lc, p.vis_entries - 1, p.vis_entries / 4 * 3 - 32);
             if (c.status == 0 && lc < p.max_layers) {
                 const int out_n = min(c.len, c.ef);
                 const size_t o = ((size_t)w * p.max_layers + lc) * p.efc;

@@ -107,12 +107,6 @@ __device__ __forceinline__ uint64_t make_key(float d, uint32_t id) {
     return ((uint64_t)f32_ord(d) << 32) | ((uint64_t)id << 1);
 }
 __device__ __forceinline__ uint32_t key_ord(uint64_t k) { return (uint32_t)(k >> 32); }
-__device__ __forceinline__ uint64_t warp_min_key(uint64_t v) {
-    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-    const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
-    const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, hi == mh ? lo : 0xFFFFFFFFu);
-    return ((uint64_t)mh << 32) | ml;
-}
 __device__ __forceinline__ uint32_t key_id(uint64_t k) { return ((uint32_t)k) >> 1; }
 
 // ------------------------------------------------------------------------------------------
@@ -373,18 +367,6 @@ struct RegList {
         }
         return true;
     }
-    // nearest unexpanded entry without marking it (KEY_NONE when there is none)
-    __device__ __forceinline__ uint64_t peek_nearest(const WarpCtx &c) const {
-        int jf = -1;
-#pragma unroll
-        for (int j = J - 1; j >= 0; j--) if (k[j] != KEY_NONE && (k[j] & 1ull) == 0) jf = j;
-        const uint32_t b = __ballot_sync(FULL, jf >= 0);
-        if (!b) return KEY_NONE;
-        uint64_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < J; j++) if (j == jf) mine = k[j];
-        return __shfl_sync(FULL, mine, __ffs(b) - 1);
-    }
     // Build phase 2 (graph/mod.rs:425 `ep = w`): W of this layer becomes the entry-point list of the next
     // one.  Drops retained ties (they are not in W), clears the expanded flags, sets f_ord, and inserts
     // every id into the (freshly cleared) visited table.
@@ -473,15 +455,6 @@ struct SmemList {
             }
         }
         return false;
-    }
-    __device__ __forceinline__ uint64_t peek_nearest(const WarpCtx &c) const {
-        for (int base = (hint >> 5) << 5; base < c.len; base += 32) {
-            const int i = base + c.lane;
-            const bool un = i >= hint && i < c.len && (S[i] & 1ull) == 0;
-            const uint32_t b = __ballot_sync(FULL, un);
-            if (b) return S[base + __ffs(b) - 1];
-        }
-        return KEY_NONE;
     }
     __device__ __forceinline__ void reopen(WarpCtx &c, uint32_t *vis, uint32_t vis_mask) {
         c.len = min(c.len, c.ef);
@@ -640,11 +613,7 @@ __device__ __forceinline__ float eval_neighbours(WarpCtx &c, const GraphView &g,
 // counted entry points starts with w_len > ef (nothing is evicted while seeding), and then `if w_len > ef` fires after
 // every push, skip members included, each time taking w_len down by one: the first `excess` skip pushes evict like
 // counted ones and only the later ones move the boundary.
-// PREFETCH (the build's latency-bound searches): which candidate is expanded next is known as soon as this expansion's
-// distances are -- the nearest of (the nearest unexpanded entry of S, the nearest neighbour about to be accepted: it is
-// accepted whenever any is, because everything accepted before it is farther) -- so its layer-0 neighbour row is requested
-// before the accept loop runs instead of after the next pop.  A wrong guess only means the row is loaded as usual.
-template <int ELEM, int METRIC, bool FLAGGED = false, bool SKIP = false, bool PREFETCH = false, class LIST>
+template <int ELEM, int METRIC, bool FLAGGED = false, bool SKIP = false, class LIST>
 __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphView &g, int layer, uint32_t vis_mask,
                                              uint32_t vis_limit) {
     const int lane = c.lane;
@@ -654,8 +623,6 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
     // before the NEXT probe of the table, by which time the claim's round trip has long completed
     bool lost_fresh = false;
     uint32_t lost_old = VIS_EMPTY, lost_id = 0, lost_from = 0;
-    uint32_t pf_id = 0xFFFFFFFFu;                  // PREFETCH: the element whose first 32 layer-0 entries sit in pf_nb
-    int32_t pf_nb = -1;
     while (true) {
         uint64_t ckey;
         PH_START(c);
@@ -683,9 +650,7 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
         }
         for (int base = 0; base < lm; base += 32) {
             const int j = base + lane;
-            int32_t nb;
-            if (PREFETCH && base == 0 && cid == pf_id) nb = pf_nb;
-            else nb = j < lm ? __ldg(row + j) : -1;
+            const int32_t nb = j < lm ? __ldg(row + j) : -1;
             const bool valid = nb >= 0;                 // lists are dense prefixes (scan.rs:273-279)
             const uint32_t vm = __ballot_sync(FULL, valid);
             if (!vm) break;
@@ -776,16 +741,6 @@ __device__ __forceinline__ void search_layer(WarpCtx &c, LIST &S, const GraphVie
             //     fills up, so lanes failing against the CURRENT threshold can never be accepted later
             const uint32_t dord = f32_ord(d);
             uint32_t am = __ballot_sync(FULL, pass && (c.len < c.ef || dord < c.f_ord));
-            if (PREFETCH && layer == 0 && !SKIP && base + 32 >= lm) {
-                const uint64_t best_new = warp_min_key(((am >> lane) & 1u) ? make_key(d, (uint32_t)nb) : KEY_NONE);
-                const uint64_t best_old = S.peek_nearest(c);
-                const uint64_t pred = best_new < (best_old & ~1ull) ? best_new : best_old;
-                pf_id = 0xFFFFFFFFu;
-                if (pred != KEY_NONE) {
-                    pf_id = key_id(pred);
-                    pf_nb = lane < lm ? __ldg(g.adj0 + (size_t)pf_id * (size_t)lm + lane) : -1;
-                }
-            }
             while (am) {
                 const int r = __ffs(am) - 1;
                 am &= am - 1;
