@@ -74,3 +74,19 @@ def test_recorded_gpu_lines_carry_the_contract(name, n_gpus):
     assert 0 < rf["frac"] < 1.0
     cb = out["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
+
+
+def test_rank0_only_sections_do_not_enter_process_group_barriers():
+    # At N > 1 everything after `if rank == 0:` in run_b200 runs on rank 0 alone (CPU arms, ef_search = 100, the recall
+    # sweep).  ScanRunner's timed loops contain process-group barriers unless its collectives are switched off first; a
+    # forgotten switch deadlocks the job until NCCL's watchdog kills it (it did, once, on the first 2-GPU run of round 2).
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    body = src[src.index("def run_b200(a):"):src.index("def lowdim_curve(")]
+    alone = body[body.index("    if rank == 0:\n        import oracle_ffi as O"):]
+    off = alone.index("runner.collective = False")
+    for call in ("runner.device_timed(", "runner.wall_timed(", "ef_sweep("):
+        first = alone.find(call)
+        assert first < 0 or off < first, call
+    runner = src[src.index("class ScanRunner"):src.index("def parity_sample(")]
+    assert runner.count("self.world > 1 and self.collective") == 3      # barrier, device_timed, wall_timed
