@@ -135,7 +135,11 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const uint8_t *__restrict
 // is an UNORDERED set of TC_KP = 32 keys in shared memory, one per lane, maintained by the whole warp: a qualifying
 // element replaces the set's maximum (two REDUX per 32-bit half), so an insertion is ~20 warp instructions with no
 // divergent loop.  Qualifying elements are rare once the sets have warmed up (KP * ln(rows / KP) per query).
-template <int TN, bool REMOTE_EMPTY>
+// KL > 0 is the hint pre-pass: no sets at all -- every lane keeps the KL smallest approximate distances of ITS query in
+// registers (a branch-free insertion network, entered for a column only when some lane of the warp has a taker) and
+// leaves the KL-th smallest in hint[q].  The set-maintaining form spent 79 warp instructions per insertion on cross-lane
+// maxima; the sample pre-pass of a 125k-row shard took 0.39 ms for 0.04 ms of MMAs.
+template <int TN, bool REMOTE_EMPTY, int KL>
 __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0, int sp, int nt0, int nt1, uint32_t tmem_base,
                                                  float *sxn, uint64_t *Lw, uint64_t *tfull, uint64_t *tempty,
                                                  uint32_t tempty_leader_addr, int &buf, uint32_t &aphase, int quarter, int lane, int et) {
@@ -151,6 +155,54 @@ __device__ __forceinline__ void tc_epilogue_unit(const TcParams &p, int q_tile0,
     float xn_cur[TN / 128];
 #pragma unroll
     for (int h = 0; h < TN / 128; h++) xn_cur[h] = p.xnorm[(int64_t)nt0 * TN + h * 128 + et];
+    if constexpr (KL > 0) {
+        float top[KL];
+#pragma unroll
+        for (int i = 0; i < KL; i++) top[i] = __int_as_float(0x7f800000);
+        for (int nt = nt0; nt < nt1; nt += p.tile_step) {
+            const int64_t row0 = (int64_t)nt * TN;
+#pragma unroll
+            for (int h = 0; h < TN / 128; h++) {
+                sxn[buf * TN + h * 128 + et] = xn_cur[h];
+                if (nt + p.tile_step < nt1) xn_cur[h] = p.xnorm[row0 + (int64_t)p.tile_step * TN + h * 128 + et];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(tfull + buf, aphase);
+            tc_fence_after();
+            const int valid_cols = (int)min((int64_t)TN, p.n_rows - row0);
+            for (int c = 0; c < TN; c += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TN + c), v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float s = __uint_as_float(v[j]);
+                    const float dist = p.metric == METRIC_L2SQ ? __fmaf_rn(-2.0f, s, qn + sxn[buf * TN + c + j]) : -s;
+                    const bool take = qvalid && c + j < valid_cols && dist < top[KL - 1];
+                    if (__any_sync(FULL, take)) {
+                        float x = take ? dist : __int_as_float(0x7f800000);
+#pragma unroll
+                        for (int i = 0; i < KL; i++) {                       // sorted insert, the largest falls off the end
+                            const float lo = fminf(top[i], x);
+                            x = fmaxf(top[i], x);
+                            top[i] = lo;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            if (REMOTE_EMPTY) {
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader_addr + (uint32_t)buf * 8u) : "memory");
+            } else {
+                mbar_arrive(tempty + buf);
+            }
+            buf ^= 1;
+            if (buf == 0) aphase ^= 1u;
+        }
+        // the KL-th smallest of the sample (if the sample held that many rows): rows are rejected against it from now on
+        if (qvalid && top[KL - 1] < __int_as_float(0x7f800000)) atomicMin(p.hint + q, f32_ord(top[KL - 1]));
+        __syncwarp();
+        return;
+    }
     int app_n = 0;                                                   // append mode: rows this lane's query has appended in this unit
     int32_t *app_seg = p.app_ids ? p.app_ids + ((size_t)(qvalid ? q : 0) * p.n_splits + sp) * p.app_cap : nullptr;
     // a set of kp_eff < 32 keys (the hint pre-pass): the other slots hold key 0, which nothing replaces and which is never
@@ -419,7 +471,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constan
             const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
             const int nt0 = sp * p.ntiles_per_split;
             const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
-            tc_epilogue_unit<TC_N, false>(p, mt * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, 0u, buf, aphase, quarter, lane, et);
+            if (p.local_k == 8) tc_epilogue_unit<TC_N, false, 8>(p, mt * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, 0u, buf, aphase, quarter, lane, et);
+            else if (p.local_k == 16) tc_epilogue_unit<TC_N, false, 16>(p, mt * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, 0u, buf, aphase, quarter, lane, et);
+            else tc_epilogue_unit<TC_N, false, 0>(p, mt * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, 0u, buf, aphase, quarter, lane, et);
         }
     }
     tc_fence_before();
@@ -601,8 +655,15 @@ flat_tc2_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_consta
             const int mt = u % p.n_mtiles, sp = u / p.n_mtiles;
             const int nt0 = sp * p.ntiles_per_split;
             const int nt1 = min(nt0 + p.ntiles_per_split, p.n_ntiles);
-            tc_epilogue_unit<TC2_N, true>(p, mt * TC2_M + (int)rank * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, l_tempty, buf,
-                                          aphase, quarter, lane, et);
+            if (p.local_k == 8)
+                tc_epilogue_unit<TC2_N, true, 8>(p, mt * TC2_M + (int)rank * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, l_tempty, buf,
+                                                 aphase, quarter, lane, et);
+            else if (p.local_k == 16)
+                tc_epilogue_unit<TC2_N, true, 16>(p, mt * TC2_M + (int)rank * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, l_tempty, buf,
+                                                  aphase, quarter, lane, et);
+            else
+                tc_epilogue_unit<TC2_N, true, 0>(p, mt * TC2_M + (int)rank * TC_M, sp, nt0, nt1, tmem_base, sxn, Lw, tfull, tempty, l_tempty, buf,
+                                                 aphase, quarter, lane, et);
         }
     }
     tc_fence_before();

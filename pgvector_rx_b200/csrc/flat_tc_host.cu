@@ -175,6 +175,7 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     p.hint = (uint32_t *)ix->tc_hint.p;
     p.tile_step = 1;
     p.kp_eff = TC_KP;
+    p.local_k = 0;
     p.app_ids = nullptr;
     p.app_cnt = nullptr;
     p.app_cap = 0;
@@ -196,6 +197,8 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
         const int want_tiles = std::max(4, pl.n_ntiles / 24);
         pa.tile_step = std::max(1, pl.n_ntiles / want_tiles);
         pa.kp_eff = std::max(8, std::min((int)TC_KP, k / 2 + 3));
+        // lane-local top lists of 8 (k <= 10) or 16 keys; PGVRX_TC_PREPASS_SETS=1 keeps the set-maintaining form (kp_eff keys)
+        if (!getenv("PGVRX_TC_PREPASS_SETS")) { pa.local_k = k <= 10 ? 8 : 16; pa.kp_eff = pa.local_k; }
         pa.n_splits = 1;
         pa.ntiles_per_split = pl.n_ntiles;
         pa.cand_ids = nullptr;

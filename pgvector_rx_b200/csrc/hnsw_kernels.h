@@ -292,7 +292,8 @@ struct TcParams {
     float *dbg_scores;             // nq x n_rows approximate distances (diagnostic) or NULL
     uint32_t *hint;                // nq: ordered bits of the smallest full candidate-set maximum seen so far per query
     int tile_step;                 // a unit visits tiles nt0, nt0 + tile_step, ... (1 = all of them; > 1: the sample pre-pass)
-    int kp_eff;                    // keys a candidate set really holds (TC_KP, or fewer in the pre-pass)
+    int kp_eff;                    // keys a candidate set really holds (TC_KP, or fewer in a set-maintaining pre-pass)
+    int local_k;                   // 8 / 16: hint pre-pass with lane-local top lists (no sets); 0: sets or append mode
     // append mode (after a pre-pass): no candidate sets -- every row whose approximate distance is <= hint[q] is appended to
     // query q's list; the certificate's bound is the hint, a list that overflows leaves its query uncertified
     int32_t *app_ids;              // nq x n_splits x app_cap global ids (caller pre-fills -1) or NULL: one segment per unit
