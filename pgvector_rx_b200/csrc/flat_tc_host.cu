@@ -146,7 +146,11 @@ int pgvrx_flat_tc_core(pgvrx_index *ix, const void *d_queries, int64_t nq, int k
     TcPlan pl = plan_tc(two_cta ? ix->sm_count / 2 : ix->sm_count, nq_pad, ix->tc_n_pad, tile_m, tile_n);
     // short units get a threshold from the sample pre-pass (below): what a query inserts is then the rows under that
     // threshold, however the table is split, so splits cost little and the plan may balance the waves more finely
-    const bool want_prepass = d_ids && pl.tiles_per_split <= 256 && pl.n_ntiles >= 64 && !getenv("PGVRX_TC_NO_PREPASS");
+    // (the pre-pass runs one unit per query tile -- 40 of the 74 CTA pairs for 10k queries -- over 1/24 of the table: worth
+    // it up to about a million 128-d rows per device (1M: 11.45 -> 10.27 ms), a loss beyond (4M x 96: 38.1 -> 41.6 ms))
+    int max_tps = 512;
+    if (const char *e = getenv("PGVRX_TC_PREPASS_MAX_TILES")) max_tps = atoi(e);
+    const bool want_prepass = d_ids && pl.tiles_per_split <= max_tps && pl.n_ntiles >= 64 && !getenv("PGVRX_TC_NO_PREPASS");
     if (want_prepass) pl = plan_tc(two_cta ? ix->sm_count / 2 : ix->sm_count, nq_pad, ix->tc_n_pad, tile_m, tile_n, 3);
     const int nc = pl.n_splits * TC_KP;
     CU_TRY(ix, ix->tc_cand.ensure((size_t)nq * nc * 4));
