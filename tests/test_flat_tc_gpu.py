@@ -120,3 +120,26 @@ def test_auto_dispatch_picks_tensor_cores_for_large_batches_only():
     ix.load_rows(rows)
     assert ix.flat_topk(make_rows("f32", 600, 64, 4), k=10, with_stats=True)[2]["path"] == 0      # L1 is not a contraction
     ix.close()
+
+
+@pytest.mark.parametrize("knobs", [{}, {"PGVRX_TC_1CTA": "1"}, {"PGVRX_TC_NO_APPEND": "1"}, {"PGVRX_TC_PREPASS_SETS": "1"},
+                                   {"PGVRX_TC_NO_PREPASS": "1"}])
+@pytest.mark.parametrize("k", [10, 24])
+def test_tc_prepass_and_append_forms_are_all_exact(tc_path, monkeypatch, knobs, k):
+    # tables of 64+ tiles take the hint pre-pass (lane-local top lists of 8 keys for k <= 10, 16 beyond; or sets) and then
+    # the append-only pass (or sets again); every combination must still return the oracle's exact result
+    for name, value in knobs.items():
+        monkeypatch.setenv(name, value)
+    st = tc_case("vector_l2_ops", O.L2SQ, 40000, 64, 700, k, seed=95)
+    assert st["n_uncertified"] == 0
+    tc_case("vector_ip_ops", O.NEG_IP, 33000, 40, 520, k, seed=96)
+
+
+def test_tc_append_overflow_falls_back_to_exact(tc_path):
+    # 3000 copies of one row: a query next to it has thousands of rows under any threshold the sample can produce, its
+    # list segments overflow, the query stays uncertified and is answered by the exact path -- identically
+    rows = make_rows("f32", 40000, 32, 97)
+    rows[1000:4000] = rows[7]
+    q = np.concatenate([rows[7:8] + 1e-3, make_rows("f32", 600, 32, 98)]).astype(np.float32)
+    st = tc_case("vector_l2_ops", O.L2SQ, None, 32, None, 10, rows=rows, q=q, max_uncert=1.0)
+    assert st["n_uncertified"] >= 1
