@@ -374,6 +374,12 @@ int pgvrx_rerank_device(pgvrx_index *idx, const void *d_queries, int64_t nq, con
 int pgvrx_topk_merge_device(pgvrx_index *idx, const int32_t *d_part_ids, const float *d_part_dists,
                             int32_t n_parts, int64_t nq, int32_t k_in, int32_t k_out, int32_t *d_out_ids,
                             float *d_out_dists, void *cuda_stream);
+/* The same merge over per-part DEVICE pointers (HOST arrays of n_parts <= 64 pointers, each list [query][k_in]): for
+ * lists that are not contiguous with each other -- one packed all-gather of (ids | distances) per rank, or peers' lists
+ * read in place. */
+int pgvrx_topk_merge_parts_device(pgvrx_index *idx, const int32_t *const *d_part_ids, const float *const *d_part_dists,
+                                  int32_t n_parts, int64_t nq, int32_t k_in, int32_t k_out, int32_t *d_out_ids,
+                                  float *d_out_dists, void *cuda_stream);
 
 /* ---- several GPUs of one box behind one handle (one process; one host thread per device while a call runs) ------- */
 /* The scan shards by QUERIES against a graph replicated on every device (no exchange step); the exact flat kNN shards

@@ -40,7 +40,7 @@ EXPORTS = [
     "pgvrx_index_destroy", "pgvrx_index_load_graph", "pgvrx_index_size", "pgvrx_search_batch",
     "pgvrx_search_batch_device", "pgvrx_pages_inspect", "pgvrx_pages_export", "pgvrx_index_build",
     "pgvrx_index_graph_info", "pgvrx_index_export_graph", "pgvrx_index_load_rows", "pgvrx_flat_topk",
-    "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device",
+    "pgvrx_flat_topk_device", "pgvrx_rerank", "pgvrx_rerank_device", "pgvrx_topk_merge_device", "pgvrx_topk_merge_parts_device",
     "pgvrx_scan_begin", "pgvrx_scan_next", "pgvrx_scan_next_rounds", "pgvrx_scan_end", "pgvrx_flat_tc_scores", "pgvrx_normalize_rows",
     "pgvrx_pages_element_flags", "pgvrx_heap_tid_stream", "pgvrx_index_set_element_flags", "pgvrx_index_insert",
     "pgvrx_index_set_heap_tids", "pgvrx_pages_write", "pgvrx_index_vacuum", "pgvrx_index_element_flags",
@@ -171,6 +171,7 @@ def lib():
         "pgvrx_rerank": (C.c_int, [vp, vp, i64, vp, i32, i32, vp, vp]),
         "pgvrx_rerank_device": (C.c_int, [vp, vp, i64, vp, i32, i32, i64, vp, vp, vp]),
         "pgvrx_topk_merge_device": (C.c_int, [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]),
+        "pgvrx_topk_merge_parts_device": (C.c_int, [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp]),
         "pgvrx_flat_tc_scores": (C.c_int, [vp, vp, i64, vp, vp]),
         "pgvrx_scan_begin": (C.c_int, [vp, vp, i64, i32, i32, i64, C.POINTER(vp)]),
         "pgvrx_scan_next": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(SearchStats)]),
@@ -525,6 +526,14 @@ class HnswIndex:
                           stream=0):
         self._check(self.L.pgvrx_topk_merge_device(self.h, d_part_ids_ptr, d_part_dists_ptr, n_parts, nq, k_in, k_out,
                                                    d_out_ids_ptr, d_out_dists_ptr, C.c_void_p(stream) if stream else None))
+
+    def topk_merge_parts_device(self, part_ids_ptrs, part_dists_ptrs, nq, k_in, k_out, d_out_ids_ptr, d_out_dists_ptr, stream=0):
+        """K6 over per-part device pointers (lists that are not contiguous with each other)."""
+        n = len(part_ids_ptrs)
+        pi = (C.c_void_p * n)(*part_ids_ptrs)
+        pd = (C.c_void_p * n)(*part_dists_ptrs)
+        self._check(self.L.pgvrx_topk_merge_parts_device(self.h, pi, pd, n, nq, k_in, k_out, d_out_ids_ptr, d_out_dists_ptr,
+                                                         C.c_void_p(stream) if stream else None))
 
     # ---- the narrow build seam (SURVEY 8b(4)/(5)): searches here, heuristic + commit on the caller's side ----
     def search_layer_batch(self, ep_ids, ep_dists, ep_counts, ef, layer, queries=None, query_ids=None, exp_cap=0):

@@ -260,4 +260,26 @@ int pgvrx_topk_merge_device(pgvrx_index *ix, const int32_t *d_part_ids, const fl
     return PGVRX_OK;
 }
 
+// The same merge over per-part pointers: the lists need not be contiguous with each other (one packed all-gather of
+// (ids | distances) per rank leaves every rank's two lists at different strides; peers' lists read in place).
+int pgvrx_topk_merge_parts_device(pgvrx_index *ix, const int32_t *const *d_part_ids, const float *const *d_part_dists, int32_t n_parts,
+                                  int64_t nq, int32_t k_in, int32_t k_out, int32_t *d_out_ids, float *d_out_dists, void *cuda_stream) {
+    if (!ix) return PGVRX_ERR_INVALID;
+    if (n_parts < 1 || n_parts > MERGE_MAX_PARTS || k_in < 1 || k_out < 1 || k_out > FLAT_MAX_K || nq < 0)
+        return pgvrx_fail(ix, PGVRX_ERR_INVALID, "bad merge shape");
+    if (nq > 0 && (!d_part_ids || !d_part_dists || !d_out_ids || !d_out_dists)) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null device buffer");
+    if (nq == 0) return PGVRX_OK;
+    MergeParts parts;
+    parts.n_parts = n_parts;
+    for (int i = 0; i < n_parts; i++) {
+        if (!d_part_ids[i] || !d_part_dists[i]) return pgvrx_fail(ix, PGVRX_ERR_INVALID, "null part");
+        parts.ids[i] = d_part_ids[i];
+        parts.dists[i] = d_part_dists[i];
+    }
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ix->stream;
+    CU_TRY(ix, cudaSetDevice(ix->desc.device));
+    CU_TRY(ix, launch_topk_merge_parts(parts, (int)nq, k_in, k_out, d_out_ids, d_out_dists, s));
+    return PGVRX_OK;
+}
+
 }  // extern "C"

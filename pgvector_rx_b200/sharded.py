@@ -44,10 +44,13 @@ class ShardedFlat:
         """index: an HnswIndex whose loaded rows are this rank's shard; id_base: its first global row id."""
         import torch
 
-        def local_topk(d_queries, k):
+        def local_topk(d_queries, k, out=None):
             nq = d_queries.shape[0]
-            ids = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
-            dists = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
+            if out is None:
+                ids = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
+                dists = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
+            else:
+                ids, dists = out                       # the two halves of one packed send buffer
             index.flat_topk_device(d_queries.data_ptr(), nq, k, ids.data_ptr(), dists.data_ptr(), id_base=id_base,
                                    stream=stream or torch.cuda.current_stream().cuda_stream)
             return ids, dists
@@ -56,8 +59,15 @@ class ShardedFlat:
             world, nq, k_in = part_ids.shape
             ids = torch.empty((nq, k), dtype=torch.int32, device=part_ids.device)
             dists = torch.empty((nq, k), dtype=torch.float32, device=part_ids.device)
-            index.topk_merge_device(part_ids.data_ptr(), part_dists.data_ptr(), world, nq, k_in, k, ids.data_ptr(),
-                                    dists.data_ptr(), stream=stream or torch.cuda.current_stream().cuda_stream)
+            s = stream or torch.cuda.current_stream().cuda_stream
+            if part_ids.is_contiguous() and part_dists.is_contiguous():
+                index.topk_merge_device(part_ids.data_ptr(), part_dists.data_ptr(), world, nq, k_in, k, ids.data_ptr(),
+                                        dists.data_ptr(), stream=s)
+            else:
+                # views into a packed gather buffer: every part's list is contiguous, the parts are not adjacent
+                index.topk_merge_parts_device([part_ids[w].data_ptr() for w in range(world)],
+                                              [part_dists[w].data_ptr() for w in range(world)], nq, k_in, k,
+                                              ids.data_ptr(), dists.data_ptr(), stream=s)
             return ids, dists
 
         return cls(local_topk, merge, group)
@@ -72,13 +82,14 @@ class ShardedFlat:
         for _ in range(reps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-            ids, dists = self.local_topk(queries, k)
+            if world > 1:
+                send, ids, dists = self._packed(queries, k)
+                self.local_topk(queries, k, out=(ids, dists))
+            else:
+                ids, dists = self.local_topk(queries, k)
             ev[1].record()
             if world > 1:
-                part_ids = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-                part_dists = torch.empty((world,) + tuple(dists.shape), dtype=dists.dtype, device=dists.device)
-                dist.all_gather_into_tensor(part_ids.view(-1, ids.shape[1]), ids.contiguous(), group=self.group)
-                dist.all_gather_into_tensor(part_dists.view(-1, dists.shape[1]), dists.contiguous(), group=self.group)
+                part_ids, part_dists = self._gather_packed(send, world)
             else:
                 part_ids, part_dists = ids.unsqueeze(0).contiguous(), dists.unsqueeze(0).contiguous()
             ev[2].record()
@@ -92,20 +103,33 @@ class ShardedFlat:
 
     def topk(self, queries, k):
         """All ranks call this with the same queries; every rank returns the merged global top-k."""
-        import torch
         import torch.distributed as dist
-        ids, dists = self.local_topk(queries, k)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
+            ids, dists = self.local_topk(queries, k)
             return self.merge(ids.unsqueeze(0).contiguous(), dists.unsqueeze(0).contiguous(), k)
-        part_ids = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-        part_dists = torch.empty((world,) + tuple(dists.shape), dtype=dists.dtype, device=dists.device)
-        # rank r's list lands in part[r]: the merge is order-independent for distinct ids, but keeping rank
-        # order makes the result reproducible when shards hold identical (distance, id) pairs
-        # (the collective sees the output as the dim-0 concatenation of the inputs, which is the same memory)
-        dist.all_gather_into_tensor(part_ids.view(-1, ids.shape[1]), ids.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(part_dists.view(-1, dists.shape[1]), dists.contiguous(), group=self.group)
+        send, ids, dists = self._packed(queries, k)
+        self.local_topk(queries, k, out=(ids, dists))
+        # rank r's lists land in part[r]: the merge is order-independent for distinct ids, but keeping rank order makes
+        # the result reproducible when shards hold identical (distance, id) pairs
+        part_ids, part_dists = self._gather_packed(send, world)
         return self.merge(part_ids, part_dists, k)
+
+    @staticmethod
+    def _packed(queries, k):
+        """One send buffer [2, nq, k] of 32-bit words: ids in the first half, distance bits in the second (a view)."""
+        import torch
+        send = torch.empty((2, queries.shape[0], k), dtype=torch.int32, device=queries.device)
+        return send, send[0], send[1].view(torch.float32)
+
+    def _gather_packed(self, send, world):
+        """ONE all-gather of nq * k * 8 bytes per rank (at this size a collective is latency, not bandwidth); returns the
+        [world, nq, k] id and distance views into the receive buffer."""
+        import torch
+        import torch.distributed as dist
+        recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+        return recv[:, 0], recv[:, 1].view(torch.float32)
 
 
 def gather_query_shards(local_ids, local_dists, nq, group=None):

@@ -211,6 +211,7 @@ extern "C" {
     pub fn pgvrx_rerank(idx: *mut PgvrxIndex, queries: *const c_void, nq: i64, cand_ids: *const i32, nc: i32, k: i32, out_ids: *mut i32, out_dists: *mut f32) -> c_int;
     pub fn pgvrx_rerank_device(idx: *mut PgvrxIndex, d_queries: *const c_void, nq: i64, d_cand: *const i32, nc: i32, k: i32, id_base: i64, d_ids: *mut i32, d_dists: *mut f32, cuda_stream: *mut c_void) -> c_int;
     pub fn pgvrx_topk_merge_device(idx: *mut PgvrxIndex, d_part_ids: *const i32, d_part_dists: *const f32, n_parts: i32, nq: i64, k_in: i32, k_out: i32, d_out_ids: *mut i32, d_out_dists: *mut f32, cuda_stream: *mut c_void) -> c_int;
+    pub fn pgvrx_topk_merge_parts_device(idx: *mut PgvrxIndex, d_part_ids: *const *const i32, d_part_dists: *const *const f32, n_parts: i32, nq: i64, k_in: i32, k_out: i32, d_out_ids: *mut i32, d_out_dists: *mut f32, cuda_stream: *mut c_void) -> c_int;
     pub fn pgvrx_group_create(desc: *const PgvrxIndexDesc, devices: *const i32, n_devices: i32, out: *mut *mut PgvrxGroup) -> c_int;
     pub fn pgvrx_group_destroy(g: *mut PgvrxGroup);
     pub fn pgvrx_group_last_error(g: *const PgvrxGroup) -> *const c_char;

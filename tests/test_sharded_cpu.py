@@ -55,9 +55,13 @@ def _worker(rank, world, port, n, dim, nq, k, out_dir):
         q = make_rows("f32", nq, dim, 62)
         lo, hi = S.shard_bounds(n, world)[rank]
 
-        def local_topk(queries, kk):
+        def local_topk(queries, kk, out=None):
             ids, ds = O.flat_topk(O.ELEM_F32, O.L2SQ, dim, rows[lo:hi], queries.numpy(), kk)
             ids = np.where(ids >= 0, ids + lo, -1).astype(np.int32)       # global ids
+            if out is not None:                  # the two halves of the packed send buffer (one all-gather per call)
+                out[0].copy_(torch.from_numpy(ids))
+                out[1].copy_(torch.from_numpy(ds))
+                return out
             return torch.from_numpy(ids), torch.from_numpy(ds)
 
         flat = S.ShardedFlat(local_topk, _numpy_merge)

@@ -71,7 +71,7 @@ def rust_type(c, struct_names):
     const = toks[0] == "const"
     if const:
         toks = toks[1:]
-    base, stars = toks[0], toks[1:].count("*")
+    base = toks[0]
     if base in SCALARS:
         r = SCALARS[base]
     elif base in OPAQUE:
@@ -80,11 +80,17 @@ def rust_type(c, struct_names):
         r = camel(base)
     else:
         raise ValueError("unknown C type %r" % c)
-    if stars == 0:
-        return r
-    out = ("*const " if const else "*mut ") + r
-    for _ in range(stars - 1):
-        out = "*mut " + out
+    # every `*` points at what stands to its left; a `const` between two stars qualifies the pointer before it
+    # (`const int32_t *const *` = pointer to const pointer to const int32_t)
+    out, pointee_const = r, const
+    for t in toks[1:]:
+        if t == "*":
+            out = ("*const " if pointee_const else "*mut ") + out
+            pointee_const = False
+        elif t == "const":
+            pointee_const = True
+        else:
+            raise ValueError("unexpected token %r in C type %r" % (t, c))
     return out
 
 
