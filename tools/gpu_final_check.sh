@@ -1,3 +1,7 @@
+# One gpurun call that re-establishes a round's single-GPU evidence on a fresh B200 (run from the repository root):
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_final_check.sh'
+# the whole GPU parity suite, smoke(), the default bench line and the reference arm; results under gpurun_out/r2v_*
+# (profiles/r2_bench_1gpu_final.json, r2_bench_reference_arm.json, r2_smoke.txt, r2_pytest_gpu_tail.txt came from it).
 set -u
 out=gpurun_out; mkdir -p $out
 timeout 1200 python -m pytest tests -m gpu -q --timeout 900 > $out/r2v_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $out/r2v_pytest_gpu.log

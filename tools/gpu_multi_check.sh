@@ -1,3 +1,7 @@
+# Multi-GPU check (run from the repository root):
+#   /usr/local/graft/bin/gpurun --gpus N --timeout 900 -- 'bash tools/gpu_multi_check.sh N'
+# the merge / group tests, then bench.py under torchrun on N GPUs without the single-GPU-only sections: weak-scaling scan,
+# one caller batch split over the ranks, row-sharded exact kNN with its per-phase times (profiles/r2_bench_{2,8}gpu.json).
 set -u
 N=${1:-2}
 out=gpurun_out; mkdir -p $out
