@@ -63,6 +63,10 @@ def test_c4_inner_product_iterative_filtered(tmp_path):
     assert [x["filter"] for x in it] == ["id % 50 == 0", "id % 500 == 0"]
     assert all(x["streams_match_oracle"] and x["rounds"] >= 1 for x in it)
     assert it[0]["queries_with_all_hits"] > 0
+    # several refills per call under the selective filter, and a CPU arm for the section
+    assert all(1 <= x["calls"] <= x["rounds"] and x["rounds"] == x["calls"] * x["refills_per_call"] for x in it)
+    assert it[1]["refills_per_call"] > 1
+    assert all(x["cpu_baseline"]["value"] > 0 and x["cpu_baseline"]["kind"] == "port" for x in it)
 
 
 def test_c5_bit_hamming_rerank(tmp_path):
